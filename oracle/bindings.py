@@ -1,0 +1,365 @@
+"""ctypes bindings for the CPU oracle.  TEST INFRASTRUCTURE ONLY.
+
+Two libraries:
+  * ``Port``  -> oracle/liboracle.so      (oracle.c, our scalar restatement; always buildable with gcc)
+  * ``Ref``   -> oracle/_ref/libsrslte_ref.so (the UNMODIFIED reference compiled by oracle/build_ref.sh
+                 from /root/reference; exists only where it was built -- it travels to the GPU box as a
+                 prebuilt file)
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import this.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "liboracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libsrslte_ref.so")
+
+CRC24A = 0x1864CFB
+CRC24B = 0x1800063
+CRC16 = 0x11021
+CRC8 = 0x19B
+
+# srslte_tdec_impl_type_t (turbodecoder_impl.h:28-38)
+TDEC_AUTO, TDEC_GENERIC, TDEC_SSE, TDEC_SSE_WINDOW, TDEC_NEON_WINDOW, TDEC_AVX_WINDOW, TDEC_SSE8_WINDOW, TDEC_AVX8_WINDOW = range(8)
+
+
+def build(ref=True):
+    """Compile liboracle.so (always) and the reference library (if /root/reference exists)."""
+    subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
+    if ref and os.path.isdir(os.environ.get("SRSLTE_REFERENCE", "/root/reference")):
+        subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+
+
+def aligned_zeros(n, dtype, align=64):
+    """The reference decodes in place from its input with aligned SIMD loads (turbodecoder_win.h:633):
+    LLR buffers handed to Ref.tdec_* must be 32-byte aligned."""
+    dtype = np.dtype(dtype)
+    raw = np.zeros(n * dtype.itemsize + align, np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n * dtype.itemsize].view(dtype)
+
+
+def _p(a, t=None):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _i16(x):
+    return np.ascontiguousarray(x, dtype=np.int16)
+
+
+def _i8(x):
+    return np.ascontiguousarray(x, dtype=np.int8)
+
+
+def _u8(x):
+    return np.ascontiguousarray(x, dtype=np.uint8)
+
+
+class Port:
+    """oracle.c"""
+
+    def __init__(self):
+        if not os.path.exists(PORT_SO):
+            build(ref=False)
+        L = self.L = C.CDLL(PORT_SO)
+        L.orc_tdec_new.restype = C.c_void_p
+        L.orc_softbuffer_new.restype = C.c_void_p
+        L.orc_crc_bytes.restype = C.c_uint32
+        L.orc_crc_bits.restype = C.c_uint32
+        L.orc_subblocks16.restype = C.c_uint32
+        L.orc_subblocks8.restype = C.c_uint32
+
+    # tables
+    def cbsegm(self, tbs):
+        out = np.zeros(9, np.uint32)
+        r = self.L.orc_cbsegm(C.c_uint32(tbs), _p(out))
+        return r, dict(zip(["F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs"], out.tolist()))
+
+    def cbsize(self, idx):
+        return self.L.orc_cbsize(C.c_uint32(idx))
+
+    def cbindex(self, K):
+        return self.L.orc_cbindex(C.c_uint32(K))
+
+    def subblocks16(self, K):
+        return self.L.orc_subblocks16(C.c_uint32(K))
+
+    def subblocks8(self, K):
+        return self.L.orc_subblocks8(C.c_uint32(K))
+
+    def qpp(self, K, nsb):
+        f = np.zeros(K, np.uint16)
+        r = np.zeros(K, np.uint16)
+        rc = self.L.orc_qpp(C.c_uint32(K), C.c_uint32(nsb), _p(f), _p(r))
+        assert rc == 0
+        return f, r
+
+    def rm_table(self, K, rv, nsb):
+        t = np.zeros(3 * K + 12, np.uint16)
+        self.L.orc_rm_table(C.c_uint32(K), C.c_uint32(rv), C.c_uint32(nsb), _p(t))
+        return t
+
+    def rm_rx16(self, e, out, K, rv, nsb):
+        e = _i16(e)
+        assert out.dtype == np.int16 and out.flags.c_contiguous
+        return self.L.orc_rm_rx16(_p(e), _p(out), C.c_uint32(len(e)), C.c_uint32(K), C.c_uint32(rv), C.c_uint32(nsb))
+
+    def rm_rx8(self, e, out, K, rv, nsb):
+        e = _i8(e)
+        assert out.dtype == np.int8 and out.flags.c_contiguous
+        return self.L.orc_rm_rx8(_p(e), _p(out), C.c_uint32(len(e)), C.c_uint32(K), C.c_uint32(rv), C.c_uint32(nsb))
+
+    def crc_bytes(self, poly, order, data):
+        d = _u8(data)
+        return self.L.orc_crc_bytes(C.c_uint32(poly), C.c_int(order), _p(d), C.c_uint32(len(d)))
+
+    def crc_bits(self, poly, order, bits):
+        d = _u8(bits)
+        return self.L.orc_crc_bits(C.c_uint32(poly), C.c_int(order), _p(d), C.c_uint32(len(d)))
+
+    # decoder object
+    def tdec_new(self, dec_type=TDEC_AUTO, force_not_sb=False):
+        return C.c_void_p(self.L.orc_tdec_new(C.c_int(dec_type), C.c_int(int(force_not_sb))))
+
+    def tdec_del(self, h):
+        self.L.orc_tdec_del(h)
+
+    def tdec_new_cb(self, h, K):
+        return self.L.orc_tdec_new_cb(h, C.c_uint32(K))
+
+    def tdec_iteration(self, h, llr, K):
+        """llr: np.int16 or np.int8 array; returns K/8 decided bytes"""
+        assert llr.dtype in (np.int16, np.int8) and llr.flags.c_contiguous
+        out = np.zeros(K // 8, np.uint8)
+        self.L.orc_tdec_iteration(h, _p(llr), C.c_int(16 if llr.dtype == np.int16 else 8), _p(out))
+        return out
+
+    def tdec_run_all(self, h, llr, nof_iter, K):
+        assert llr.dtype in (np.int16, np.int8) and llr.flags.c_contiguous
+        out = np.zeros(K // 8, np.uint8)
+        rc = self.L.orc_tdec_run_all(h, _p(llr), C.c_int(16 if llr.dtype == np.int16 else 8), _p(out), C.c_uint32(nof_iter), C.c_uint32(K))
+        return rc, out
+
+    def tdec_get_llr(self, h, which, n):
+        d = np.zeros(n, np.int16)
+        self.L.orc_tdec_get_llr(h, C.c_int(which), _p(d), C.c_uint32(n))
+        return d
+
+    def tdec_n_iter(self, h):
+        return self.L.orc_tdec_n_iter(h)
+
+    # TB level
+    def softbuffer_new(self):
+        return C.c_void_p(self.L.orc_softbuffer_new())
+
+    def softbuffer_del(self, s):
+        self.L.orc_softbuffer_del(s)
+
+    def softbuffer_reset(self, s):
+        self.L.orc_softbuffer_reset(s)
+
+    def softbuffer_get(self, s, cb, n=18600):
+        d = np.zeros(n, np.int16)
+        self.L.orc_softbuffer_get(s, C.c_uint32(cb), _p(d), C.c_uint32(n))
+        return d
+
+    def decode_tb(self, s, tbs, Qm, rv, e_bits, max_iter, ncb_hint=32):
+        assert e_bits.dtype in (np.int16, np.int8) and e_bits.flags.c_contiguous
+        data = np.zeros(tbs // 8 + 8 + 768, np.uint8)
+        nit = np.zeros(32, np.uint32)
+        avg = C.c_float(0)
+        rc = self.L.orc_decode_tb(s, C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(rv), C.c_uint32(len(e_bits)), _p(e_bits),
+                                  C.c_int(int(e_bits.dtype == np.int8)), C.c_uint32(max_iter), _p(data), _p(nit), C.byref(avg))
+        crc = np.zeros(32, np.uint8)
+        self.L.orc_softbuffer_get_crc(s, _p(crc), C.c_uint32(32))
+        return rc, data, nit, avg.value, crc
+
+
+class Ref:
+    """The unmodified reference (srsLTE 20.10.1) through oracle/ref_shim.c"""
+
+    @staticmethod
+    def available():
+        return os.path.exists(REF_SO)
+
+    def __init__(self):
+        if not os.path.exists(REF_SO):
+            raise RuntimeError("reference library not built: run oracle/build_ref.sh where /root/reference exists")
+        L = self.L = C.CDLL(REF_SO)
+        L.ref_tdec_new.restype = C.c_void_p
+        L.ref_sch_new.restype = C.c_void_p
+        L.ref_crc_byte.restype = C.c_uint32
+        L.ref_crc_bits.restype = C.c_uint32
+        L.ref_subblocks16.restype = C.c_uint32
+        L.ref_subblocks8.restype = C.c_uint32
+        L.ref_bench_c1.restype = C.c_double
+        L.ref_bench_tb.restype = C.c_double
+        L.ref_init()
+
+    def cbsegm(self, tbs):
+        out = np.zeros(9, np.uint32)
+        r = self.L.ref_cbsegm(C.c_uint32(tbs), _p(out))
+        return r, dict(zip(["F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs"], out.tolist()))
+
+    def cbsize(self, idx):
+        return self.L.ref_cbsize(C.c_uint32(idx))
+
+    def cbindex(self, K):
+        return self.L.ref_cbindex(C.c_uint32(K))
+
+    def subblocks16(self, K):
+        return self.L.ref_subblocks16(C.c_uint32(K))
+
+    def subblocks8(self, K):
+        return self.L.ref_subblocks8(C.c_uint32(K))
+
+    def qpp(self, K, nsb):
+        f = np.zeros(K, np.uint16)
+        r = np.zeros(K, np.uint16)
+        rc = self.L.ref_qpp(C.c_uint32(K), C.c_uint32(max(nsb, 1)), _p(f), _p(r))
+        assert rc == 0
+        return f, r
+
+    def crc_bytes(self, poly, order, data):
+        d = _u8(data).copy()
+        return self.L.ref_crc_byte(C.c_uint32(poly), C.c_int(order), _p(d), C.c_int(8 * len(d)))
+
+    def crc_bits(self, poly, order, bits):
+        d = _u8(bits).copy()
+        return self.L.ref_crc_bits(C.c_uint32(poly), C.c_int(order), _p(d), C.c_int(len(d)))
+
+    def rm_rx16(self, e, out, cb_idx, rv, enable_sb=True):
+        e = _i16(e).copy()
+        assert out.dtype == np.int16 and out.flags.c_contiguous
+        return self.L.ref_rm_rx_lut16(_p(e), _p(out), C.c_uint32(len(e)), C.c_uint32(cb_idx), C.c_uint32(rv), C.c_int(int(enable_sb)))
+
+    def rm_rx8(self, e, out, cb_idx, rv):
+        e = _i8(e).copy()
+        assert out.dtype == np.int8 and out.flags.c_contiguous
+        return self.L.ref_rm_rx_lut8(_p(e), _p(out), C.c_uint32(len(e)), C.c_uint32(cb_idx), C.c_uint32(rv))
+
+    def rm_tx(self, bits, E, rv):
+        b = _u8(bits).copy()
+        out = np.zeros(E, np.uint8)
+        rc = self.L.ref_rm_tx(_p(b), C.c_uint32(len(b)), _p(out), C.c_uint32(E), C.c_uint32(rv))
+        assert rc == 0
+        return out
+
+    def rm_rx_float(self, e, out_len, rv):
+        e = np.ascontiguousarray(e, np.float32).copy()
+        out = np.zeros(out_len, np.float32)
+        rc = self.L.ref_rm_rx_float(_p(e), C.c_uint32(len(e)), _p(out), C.c_uint32(out_len), C.c_uint32(rv))
+        assert rc == 0
+        return out
+
+    def tcod_encode(self, bits):
+        b = _u8(bits).copy()
+        K = len(b)
+        out = np.zeros(3 * K + 12, np.uint8)
+        rc = self.L.ref_tcod_encode(_p(b), _p(out), C.c_uint32(K))
+        assert rc == 0
+        return out
+
+    def tdec_new(self, dec_type=TDEC_AUTO, force_not_sb=False, max_k=6144):
+        h = self.L.ref_tdec_new(C.c_uint32(max_k), C.c_int(dec_type), C.c_int(int(force_not_sb)))
+        assert h
+        return C.c_void_p(h)
+
+    def tdec_del(self, h):
+        self.L.ref_tdec_del(h)
+
+    def tdec_new_cb(self, h, K):
+        return self.L.ref_tdec_new_cb(h, C.c_uint32(K))
+
+    def tdec_iteration(self, h, llr, K, patched=True):
+        """NOTE: the reference decodes in place from `llr` (it is the HARQ soft buffer); pass the same array each call"""
+        assert llr.dtype in (np.int16, np.int8) and llr.flags.c_contiguous and llr.ctypes.data % 32 == 0
+        out = np.zeros(K // 8, np.uint8)
+        if llr.dtype == np.int16:
+            self.L.ref_tdec_iteration16(h, _p(llr), _p(out))
+        else:
+            self.L.ref_tdec_iteration8(h, _p(llr), _p(out), C.c_int(int(patched)))
+        return out
+
+    def tdec_run_all(self, h, llr, nof_iter, K):
+        assert llr.dtype in (np.int16, np.int8) and llr.flags.c_contiguous and llr.ctypes.data % 32 == 0
+        out = np.zeros(K // 8, np.uint8)
+        if llr.dtype == np.int16:
+            rc = self.L.ref_tdec_run_all16(h, _p(llr), _p(out), C.c_uint32(nof_iter), C.c_uint32(K))
+        else:
+            rc = self.L.ref_tdec_run_all8(h, _p(llr), _p(out), C.c_uint32(nof_iter), C.c_uint32(K))
+        return rc, out
+
+    def tdec_get_llr(self, h, which, n):
+        d = np.zeros(n, np.int16)
+        self.L.ref_tdec_get_llr(h, C.c_int(which), _p(d), C.c_uint32(n))
+        return d
+
+    def tdec_n_iter(self, h):
+        return self.L.ref_tdec_n_iter(h)
+
+    def tdec_current(self, h):
+        o = np.zeros(3, np.int32)
+        self.L.ref_tdec_current(h, _p(o))
+        return o.tolist()
+
+    # TB level through the real sch.c
+    def sch_new(self, llr_is_8bit=False, max_iter=10, nof_prb=100):
+        s = self.L.ref_sch_new(C.c_int(int(llr_is_8bit)), C.c_uint32(max_iter), C.c_uint32(nof_prb))
+        assert s
+        return C.c_void_p(s)
+
+    def sch_del(self, s):
+        self.L.ref_sch_del(s)
+
+    def sch_reset_rx(self, s, tbs):
+        self.L.ref_sch_reset_rx(s, C.c_uint32(tbs))
+
+    def sch_encode(self, s, tbs, Qm, G, rv, data):
+        d = np.zeros(tbs // 8 + 16, np.uint8)
+        d[: tbs // 8] = _u8(data)[: tbs // 8]
+        e = np.zeros((G + 7) // 8 + 64, np.uint8)
+        rc = self.L.ref_sch_encode(s, C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(G), C.c_uint32(rv), _p(d), _p(e))
+        assert rc == 0, rc
+        return np.unpackbits(e)[:G]
+
+    def sch_decode(self, s, tbs, Qm, rv, llr):
+        assert llr.dtype in (np.int16, np.int8) and llr.flags.c_contiguous
+        data = np.zeros(tbs // 8 + 8 + 768, np.uint8)
+        avg = C.c_float(0)
+        crc = np.zeros(32, np.uint8)
+        rc = self.L.ref_sch_decode(s, C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(len(llr)), C.c_uint32(rv), _p(llr), _p(data),
+                                   C.byref(avg), _p(crc), C.c_uint32(32))
+        return rc, data, avg.value, crc
+
+    def sch_get_softbuffer(self, s, cb, n=18600):
+        d = np.zeros(n, np.int16)
+        rc = self.L.ref_sch_get_softbuffer(s, C.c_uint32(cb), _p(d), C.c_uint32(n))
+        assert rc == 0
+        return d
+
+    # CPU baseline runners
+    def bench_c1(self, nthreads, llr, K, nof_iter, layout_sb=False):
+        """llr: (ncb, stride) int16/int8.  Returns (seconds, out bytes (ncb, K/8))."""
+        assert llr.ndim == 2 and llr.flags.c_contiguous
+        ncb, stride = llr.shape
+        out = np.zeros((ncb, K // 8), np.uint8)
+        t = self.L.ref_bench_c1(C.c_int(nthreads), _p(llr), C.c_uint32(stride), C.c_uint32(ncb), C.c_uint32(K), C.c_uint32(nof_iter),
+                                C.c_int(int(llr.dtype == np.int8)), C.c_int(int(layout_sb)), _p(out))
+        return t, out
+
+    def bench_tb(self, nthreads, llr, tbs, Qm, rv, max_iter):
+        """llr: (ntb, G) int16/int8.  Returns (seconds, data (ntb, stride), rc (ntb,), avg_iter (ntb,))."""
+        assert llr.ndim == 2 and llr.flags.c_contiguous
+        ntb, G = llr.shape
+        stride = tbs // 8 + 8 + 768
+        out = np.zeros((ntb, stride), np.uint8)
+        rc = np.zeros(ntb, np.int32)
+        avg = np.zeros(ntb, np.float32)
+        t = self.L.ref_bench_tb(C.c_int(nthreads), _p(llr), C.c_uint32(ntb), C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(G), C.c_uint32(rv),
+                                C.c_uint32(max_iter), C.c_int(int(llr.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg))
+        return t, out, rc, avg

@@ -1,0 +1,816 @@
+/*
+ * oracle.c -- CPU restatement of the reference's LTE turbo-decode hot path.
+ *
+ * THIS IS TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and the cpu_baseline /
+ * --impl reference legs of bench.py may build, load or call it.  The product library
+ * (srsran_b200/csrc -> libsrslte_fec_b200.so) never links or calls anything in oracle/.
+ *
+ * Parity status: PINNED.  Every function below is checked element-for-element against the
+ * UNMODIFIED reference compiled from /root/reference by oracle/build_ref.sh
+ * (tests/test_oracle_vs_ref.py; golden vectors produced by that binary are committed under
+ * tests/golden/ by tests/golden/make_golden.py), and against the reference's own known-answer
+ * material (crc_test.h:36-39, turbodecoder_test.h:70-125 via the golden files).
+ *
+ * Everything is written scalar, one sub-block lane at a time, from the numerical contract in
+ * SURVEY.md 8a-3; each function cites the reference lines it restates (paths relative to
+ * /root/reference/lib).
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "lte_qpp_table.h"
+
+#define ORC_MAX_K 6144
+#define ORC_SOFTBUFFER_SIZE 18600 /* include/srslte/phy/fec/softbuffer.h:50 */
+#define ORC_WIN_OVERLAP 40        /* include/srslte/phy/fec/turbodecoder_win.h:54 */
+
+/* ============================================================ code block sizes / segmentation */
+
+/* src/phy/fec/cbsegm.c:29-39 (table), :114-125 (lookup of the smallest K >= len) */
+int orc_cbsize(uint32_t idx) { return idx < LTE_NOF_CB_SIZES ? (int)lte_qpp_table[idx].K : -1; }
+int orc_cbindex(uint32_t len)
+{
+  for (int j = 0; j < LTE_NOF_CB_SIZES; j++)
+    if (lte_qpp_table[j].K >= len)
+      return j;
+  return -1;
+}
+
+/* src/phy/fec/cbsegm.c:48-103.  out = {F, C, K1, K2, K1_idx, K2_idx, C1, C2, tbs}.
+ * C = ceil(B/6120) is evaluated in single-precision float in the reference (:65). */
+int orc_cbsegm(uint32_t tbs, uint32_t out[9])
+{
+  memset(out, 0, 9 * sizeof(uint32_t));
+  if (tbs == 0)
+    return 0;
+  uint32_t B = tbs + 24, C, Bp;
+  if (B <= ORC_MAX_K) {
+    C  = 1;
+    Bp = B;
+  } else {
+    float q = (float)B / (float)(ORC_MAX_K - 24);
+    C       = (uint32_t)q;
+    if ((float)C < q)
+      C++;
+    Bp = B + 24 * C;
+  }
+  int idx1 = orc_cbindex((Bp - 1) / C + 1);
+  if (idx1 < 0)
+    return -1;
+  uint32_t K1 = lte_qpp_table[idx1].K, K2 = 0, K2i = 0, C1 = 1, C2 = 0;
+  if (C > 1) {
+    /* for idx1 == 0 the reference reuses K1 for K2 (division by zero follows); unreachable for C > 1 */
+    K2i = idx1 > 0 ? (uint32_t)idx1 - 1 : 0;
+    K2  = lte_qpp_table[K2i].K;
+    C2  = (C * K1 - Bp) / (K1 - K2);
+    C1  = C - C2;
+  }
+  out[0] = C1 * K1 + C2 * K2 - Bp;
+  out[1] = C;
+  out[2] = K1;
+  out[3] = K2;
+  out[4] = (uint32_t)idx1;
+  out[5] = K2i;
+  out[6] = C1;
+  out[7] = C2;
+  out[8] = tbs;
+  return 0;
+}
+
+/* src/phy/fec/turbodecoder.c:381-424: number of sub-block lanes of the AUTO decoder (AVX2 build) */
+uint32_t orc_subblocks16(uint32_t K) { return (K % 16 == 0 && K > 800) ? 16 : (K % 8 == 0 && K > 400) ? 8 : 0; }
+uint32_t orc_subblocks8(uint32_t K)
+{
+  return (K % 32 == 0 && K > 2048) ? 32 : (K % 16 == 0 && K > 800) ? 16 : (K % 8 == 0 && K > 400) ? 8 : 0;
+}
+
+/* ============================================================================ QPP interleaver */
+
+/* natural index n -> lane layout: element (lane n / W, step n % W) lives at step*N + lane
+ * (src/phy/fec/tc_interl_lte.c:66-67 "deinter"/"inter") */
+static inline uint32_t to_lane(uint32_t n, uint32_t K, uint32_t N) { return (n % (K / N)) * N + n / (K / N); }
+static inline uint32_t from_lane(uint32_t j, uint32_t K, uint32_t N) { return (j % N) * (K / N) + j / N; }
+
+/* src/phy/fec/tc_interl_lte.c:69-109.  nsb <= 1: natural order. */
+int orc_qpp(uint32_t K, uint32_t nsb, uint16_t* fwd, uint16_t* rev)
+{
+  int ci = orc_cbindex(K);
+  if (ci < 0 || lte_qpp_table[ci].K != K)
+    return -1;
+  uint64_t  f1 = lte_qpp_table[ci].f1, f2 = lte_qpp_table[ci].f2;
+  uint16_t* f = malloc(K * sizeof(uint16_t));
+  uint16_t* r = malloc(K * sizeof(uint16_t));
+  for (uint64_t i = 0; i < K; i++) {
+    uint32_t j = (uint32_t)((f1 * i + f2 * i * i) % K);
+    f[i]       = (uint16_t)j;
+    r[j]       = (uint16_t)i;
+  }
+  for (uint32_t i = 0; i < K; i++) {
+    if (nsb > 1) {
+      fwd[i] = (uint16_t)to_lane(f[from_lane(i, K, nsb)], K, nsb);
+      rev[i] = (uint16_t)to_lane(r[from_lane(i, K, nsb)], K, nsb);
+    } else {
+      fwd[i] = f[i];
+      rev[i] = r[i];
+    }
+  }
+  free(f);
+  free(r);
+  return 0;
+}
+
+/* ============================================================ rate de-matching (TS 36.212 5.1.4.1) */
+
+static const uint8_t rm_col_perm[32] = {0, 16, 8,  24, 4, 20, 12, 28, 2, 18, 10, 26, 6, 22, 14, 30,
+                                        1, 17, 9,  25, 5, 21, 13, 29, 3, 19, 11, 27, 7, 23, 15, 31};
+
+/* Restates srslte_rm_turbo_gentable_receive (src/phy/fec/rm_turbo.c:177-251) from the standard:
+ * table[i] = 3*k + s  <=>  the i-th transmitted bit (starting at k0(rv), NULLs skipped) is bit k of
+ * stream s (s = 0 systematic, 1 parity0, 2 parity1; k < K+4, the 4 extra columns carry the 12 tail bits in
+ * the order the turbo coder emits them).  nsb > 0 additionally applies interleave_table_sb (:263-277). */
+int orc_rm_table(uint32_t K, uint32_t rv, uint32_t nsb, uint16_t* table)
+{
+  uint32_t D = K + 4, R = (D - 1) / 32 + 1, Kp = 32 * R, ND = Kp - D, Ncb = 3 * Kp;
+  uint32_t k0 = R * (2 * ((Ncb + 8 * R - 1) / (8 * R)) * rv + 2);
+  /* w[j] = codeword position held by circular-buffer slot j, or -1 for a <NULL> */
+  int32_t* w = malloc(Ncb * sizeof(int32_t));
+  for (uint32_t col = 0; col < 32; col++) {
+    for (uint32_t row = 0; row < R; row++) {
+      uint32_t j = col * R + row;
+      int32_t  y = (int32_t)(row * 32 + rm_col_perm[col]) - (int32_t)ND; /* streams 0 and 1 */
+      w[j]          = y >= 0 ? 3 * y + 0 : -1;
+      w[Kp + 2 * j] = y >= 0 ? 3 * y + 1 : -1;
+      int32_t y2    = (int32_t)((rm_col_perm[col] + 32 * row + 1) % Kp) - (int32_t)ND; /* stream 2: shifted perm */
+      w[Kp + 2 * j + 1] = y2 >= 0 ? 3 * y2 + 2 : -1;
+    }
+  }
+  uint32_t n = 0, len = 3 * K + 12;
+  for (uint32_t j = 0; n < len; j++) {
+    int32_t v = w[(k0 + j) % Ncb];
+    if (v < 0)
+      continue;
+    if (nsb > 0) {
+      if ((uint32_t)v < 3 * K)
+        v = (v % 3) * (int32_t)(K + 32) + (int32_t)to_lane((uint32_t)v / 3, K, nsb);
+      else
+        v = v - 3 * (int32_t)K + 3 * (int32_t)(K + 32);
+    }
+    table[n++] = (uint16_t)v;
+  }
+  free(w);
+  return 0;
+}
+
+/* src/phy/fec/rm_turbo.c:397-454 / :456-493: out[tab[i mod (3K+12)]] += in[i], wrapping.
+ * layout: 0 = standard (3k+s), N = lane layout with N lanes. */
+int orc_rm_rx16(const int16_t* in, int16_t* out, uint32_t E, uint32_t K, uint32_t rv, uint32_t nsb)
+{
+  uint32_t  len = 3 * K + 12;
+  uint16_t* tab = malloc(len * sizeof(uint16_t));
+  orc_rm_table(K, rv, nsb, tab);
+  for (uint32_t i = 0; i < E; i++) {
+    uint16_t p = tab[i % len];
+    out[p]     = (int16_t)(uint16_t)((uint16_t)out[p] + (uint16_t)in[i]);
+  }
+  free(tab);
+  return 0;
+}
+int orc_rm_rx8(const int8_t* in, int8_t* out, uint32_t E, uint32_t K, uint32_t rv, uint32_t nsb)
+{
+  uint32_t  len = 3 * K + 12;
+  uint16_t* tab = malloc(len * sizeof(uint16_t));
+  orc_rm_table(K, rv, nsb, tab);
+  for (uint32_t i = 0; i < E; i++) {
+    uint16_t p = tab[i % len];
+    out[p]     = (int8_t)(uint8_t)((uint8_t)out[p] + (uint8_t)in[i]);
+  }
+  free(tab);
+  return 0;
+}
+
+/* ======================================================================================= CRC */
+
+/* src/phy/fec/crc.c:30-46,143-157 + include/srslte/phy/fec/crc.h:56-70: MSB-first, init 0, no reflection,
+ * no final xor.  Restated bit-serially (the table method is the same polynomial division). */
+uint32_t orc_crc_bytes(uint32_t poly, int order, const uint8_t* data, uint32_t nbytes)
+{
+  uint64_t reg = 0, top = 1ull << order, mask = top - 1;
+  for (uint32_t i = 0; i < nbytes; i++) {
+    for (int b = 7; b >= 0; b--) {
+      reg = (reg << 1) | ((data[i] >> b) & 1u);
+      if (reg & top)
+        reg ^= ((uint64_t)poly | top);
+    }
+  }
+  /* flush `order` zero bits (the table form multiplies the message by x^order) */
+  for (int b = 0; b < order; b++) {
+    reg <<= 1;
+    if (reg & top)
+      reg ^= ((uint64_t)poly | top);
+  }
+  return (uint32_t)(reg & mask);
+}
+/* src/phy/fec/crc.c:102-140: same CRC over an array of unpacked bits (one bit per byte) */
+uint32_t orc_crc_bits(uint32_t poly, int order, const uint8_t* bits, uint32_t nbits)
+{
+  uint64_t reg = 0, top = 1ull << order, mask = top - 1;
+  for (uint32_t i = 0; i < nbits + (uint32_t)order; i++) {
+    reg = (reg << 1) | (i < nbits ? (bits[i] & 1u) : 0u);
+    if (reg & top)
+      reg ^= ((uint64_t)poly | top);
+  }
+  return (uint32_t)(reg & mask);
+}
+
+/* ============================================================================== arithmetic */
+
+typedef struct {
+  int      bits;        /* 8 or 16 */
+  uint32_t N;           /* lanes; 0 = generic (un-windowed) decoder */
+  int32_t  inf;         /* 10000 / 0   (turbodecoder_win.h:56,151,186,287) */
+  int      norm_max;    /* 8-bit: subtract the max every step (win.h:180-181,289-290) */
+  int      out_shift;   /* 8-bit: output >>= 1 (win.h:184,293) */
+} orc_cfg_t;
+
+static inline int32_t sat(const orc_cfg_t* c, int32_t v)
+{
+  int32_t hi = c->bits == 16 ? 32767 : 127, lo = -hi - 1;
+  return v > hi ? hi : (v < lo ? lo : v);
+}
+static inline int32_t wrap(const orc_cfg_t* c, int32_t v)
+{
+  return c->bits == 16 ? (int32_t)(int16_t)(uint16_t)v : (int32_t)(int8_t)(uint8_t)v;
+}
+/* tail-trellis adder (turbodecoder_win.h:470-478): 16-bit wraps; 8-bit saturates only upwards */
+static inline int32_t tail_add(const orc_cfg_t* c, int32_t a, int32_t b)
+{
+  if (c->bits == 16)
+    return wrap(c, a + b);
+  int32_t z = (int32_t)(int16_t)(a + b);
+  return z > 127 ? 127 : (int32_t)(int8_t)(uint8_t)z;
+}
+
+/* backward branch metrics (turbodecoder_win.h:643-659 == turbodecoder_gen.c:80-96) */
+#define BWD_STEP(ADD)                                                                                                  \
+  do {                                                                                                                 \
+    mb[0] = ADD(o[4], xy); mb[1] = o[4];        mb[2] = ADD(o[5], y);  mb[3] = ADD(o[5], x);                            \
+    mb[4] = ADD(o[6], x);  mb[5] = ADD(o[6], y); mb[6] = o[7];         mb[7] = ADD(o[7], xy);                           \
+    nw[0] = o[0];          nw[1] = ADD(o[0], xy); nw[2] = ADD(o[1], x); nw[3] = ADD(o[1], y);                           \
+    nw[4] = ADD(o[2], y);  nw[5] = ADD(o[2], x);  nw[6] = ADD(o[3], xy); nw[7] = o[3];                                  \
+  } while (0)
+/* forward branch metrics (turbodecoder_win.h:769-785 == turbodecoder_gen.c:148-164) */
+#define FWD_STEP(ADD)                                                                                                  \
+  do {                                                                                                                 \
+    mb[0] = o[0];          mb[1] = ADD(o[3], y);  mb[2] = ADD(o[4], y); mb[3] = o[7];                                   \
+    mb[4] = o[1];          mb[5] = ADD(o[2], y);  mb[6] = ADD(o[5], y); mb[7] = o[6];                                   \
+    nw[0] = ADD(o[1], xy); nw[1] = ADD(o[2], x);  nw[2] = ADD(o[5], x); nw[3] = ADD(o[6], xy);                          \
+    nw[4] = ADD(o[0], xy); nw[5] = ADD(o[3], x);  nw[6] = ADD(o[4], x); nw[7] = ADD(o[7], xy);                          \
+  } while (0)
+
+/* turbodecoder_win.h:480-498 */
+static void win_normalize(const orc_cfg_t* c, uint32_t k, int32_t o[8])
+{
+  if (c->norm_max) {
+    if (k == 0)
+      return;
+    int32_t m = o[0];
+    for (int i = 1; i < 8; i++)
+      m = o[i] > m ? o[i] : m;
+    for (int i = 0; i < 8; i++)
+      o[i] = sat(c, o[i] - m);
+  } else {
+    if (k % 2 != 0 || k == 0)
+      return;
+    for (int i = 1; i < 8; i++)
+      o[i] = sat(c, o[i] - o[0]);
+    o[0] = 0;
+  }
+}
+
+/* Windowed max-log-MAP: tdec_win*_dec = beta + alpha (turbodecoder_win.h:551-681, 684-832, 860-868).
+ * in/app/par/out are in lane layout (element (lane d, step p) at p*N+d); in[K..K+2], par[K..K+2] hold the tail.
+ * app may be NULL.  All values are carried in int32 but always inside the range of the configured width. */
+#define SADD(a, b) sat(c, (a) + (b))
+static void map_win(const orc_cfg_t* c, const int32_t* in, const int32_t* app, const int32_t* par, int32_t* out,
+                    uint32_t K)
+{
+  const uint32_t N = c->N, W = K / N;
+  int32_t*       beta = malloc((size_t)(W + 1) * N * 8 * sizeof(int32_t)); /* beta[p][d][s] */
+  int32_t(*warm)[8]   = malloc(N * sizeof(*warm));
+  int32_t o[8], mb[8], nw[8];
+
+  /* ---- beta, pass 0: 40 warm-up steps on each lane's own first steps (win.h:622-630) */
+  for (uint32_t d = 0; d < N; d++) {
+    for (int i = 0; i < 8; i++)
+      o[i] = -c->inf;
+    for (int k = ORC_WIN_OVERLAP - 1; k >= 0; k--) {
+      int32_t x = in[k * N + d], y = par[k * N + d];
+      if (app)
+        x = SADD(app[k * N + d], x);
+      int32_t xy = SADD(x, y);
+      BWD_STEP(SADD);
+      for (int i = 0; i < 8; i++)
+        o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+      win_normalize(c, (uint32_t)k, o);
+    }
+    memcpy(warm[d], o, sizeof(o));
+  }
+  /* ---- beta, pass 1 (win.h:577-620, 632-679) */
+  for (uint32_t d = 0; d < N; d++) {
+    if (d + 1 < N) {
+      memcpy(o, warm[d + 1], sizeof(o)); /* lane d starts from what lane d+1 estimated at its step 0 */
+    } else {
+      /* last lane: 3 tail steps from the known zero state, no a-priori (win.h:500-548) */
+      o[0] = 0;
+      for (int i = 1; i < 8; i++)
+        o[i] = -c->inf;
+      for (uint32_t k = K + 2; k >= K; k--) {
+        int32_t x = in[k], y = par[k];
+#define TADD(a, b) tail_add(c, (a), (b))
+        int32_t xy = TADD(x, y);
+        BWD_STEP(TADD);
+        for (int i = 0; i < 8; i++)
+          o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+      }
+    }
+    memcpy(&beta[((size_t)W * N + d) * 8], o, sizeof(o));
+    for (int k = (int)W - 1; k >= 0; k--) {
+      int32_t x = in[k * N + d], y = par[k * N + d];
+      if (app)
+        x = SADD(app[k * N + d], x);
+      int32_t xy = SADD(x, y);
+      BWD_STEP(SADD);
+      for (int i = 0; i < 8; i++)
+        o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+      memcpy(&beta[((size_t)k * N + d) * 8], o, sizeof(o)); /* stored before normalising (win.h:666-678) */
+      win_normalize(c, (uint32_t)k, o);
+    }
+  }
+  /* ---- alpha, pass 0: warm-up on each lane's own last 40 steps (win.h:747-756) */
+  for (uint32_t d = 0; d < N; d++) {
+    for (int i = 0; i < 8; i++)
+      o[i] = -c->inf;
+    for (uint32_t k = 0; k < ORC_WIN_OVERLAP; k++) {
+      uint32_t p = W - ORC_WIN_OVERLAP + k;
+      int32_t  x = in[p * N + d], y = par[p * N + d];
+      if (app)
+        x = SADD(app[p * N + d], x);
+      int32_t xy = SADD(x, y);
+      FWD_STEP(SADD);
+      for (int i = 0; i < 8; i++)
+        o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+      win_normalize(c, k, o);
+    }
+    memcpy(warm[d], o, sizeof(o));
+  }
+  /* ---- alpha, pass 1 with LLR output (win.h:715-746, 758-830) */
+  for (uint32_t d = 0; d < N; d++) {
+    if (d > 0) {
+      memcpy(o, warm[d - 1], sizeof(o));
+    } else {
+      o[0] = 0;
+      for (int i = 1; i < 8; i++)
+        o[i] = -c->inf;
+    }
+    for (uint32_t k = 0; k < W; k++) {
+      int32_t x = in[k * N + d], y = par[k * N + d];
+      if (app)
+        x = SADD(app[k * N + d], x);
+      int32_t xy = SADD(x, y);
+      FWD_STEP(SADD);
+      const int32_t* b  = &beta[((size_t)(k + 1) * N + d) * 8];
+      int32_t        m1 = SADD(b[0], nw[0]), m0 = SADD(b[0], mb[0]);
+      for (int i = 1; i < 8; i++) {
+        int32_t t1 = SADD(b[i], nw[i]), t0 = SADD(b[i], mb[i]);
+        m1 = t1 > m1 ? t1 : m1;
+        m0 = t0 > m0 ? t0 : m0;
+      }
+      int32_t l = sat(c, m1 - m0);
+      if (c->out_shift)
+        l >>= c->out_shift; /* arithmetic shift per element (win.h:188-193,811-813) */
+      out[k * N + d] = l;
+      for (int i = 0; i < 8; i++)
+        o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+      win_normalize(c, k, o);
+    }
+  }
+  free(beta);
+  free(warm);
+}
+
+/* Generic decoder: tdec_gen_dec (src/phy/fec/turbodecoder_gen.c:58-112, 114-198, 226-236).
+ * Natural order, un-windowed, every add/sub WRAPS in int16. */
+#define WADD(a, b) ((int32_t)(int16_t)(uint16_t)((a) + (b)))
+static void map_gen(const int32_t* in, const int32_t* app, const int32_t* par, int32_t* out, uint32_t K)
+{
+  const int32_t INF  = 10000;
+  int32_t*      beta = malloc((size_t)(K + 4) * 8 * sizeof(int32_t));
+  int32_t       o[8], mb[8], nw[8];
+  o[0] = 0;
+  for (int i = 1; i < 8; i++)
+    o[i] = -INF;
+  memcpy(&beta[(size_t)(K + 3) * 8], o, sizeof(o));
+  for (int k = (int)K + 2; k >= 0; k--) {
+    int32_t x = in[k];
+    if (app && (uint32_t)k < K)
+      x = WADD(x, app[k]);
+    int32_t y = par[k], xy = WADD(x, y);
+    BWD_STEP(WADD);
+    for (int i = 0; i < 8; i++)
+      o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+    memcpy(&beta[(size_t)k * 8], o, sizeof(o));
+    if (k % 4 == 0 && (uint32_t)k < K) {
+      for (int i = 1; i < 8; i++)
+        o[i] = WADD(o[i], -o[0]);
+      o[0] = 0;
+    }
+  }
+  o[0] = 0;
+  for (int i = 1; i < 8; i++)
+    o[i] = -INF;
+  for (uint32_t k = 1; k <= K; k++) {
+    int32_t x = in[k - 1];
+    if (app)
+      x = WADD(x, app[k - 1]);
+    int32_t y = par[k - 1], xy = WADD(x, y);
+    FWD_STEP(WADD);
+    const int32_t* b  = &beta[(size_t)k * 8];
+    int32_t        m1 = WADD(nw[0], b[0]), m0 = WADD(mb[0], b[0]);
+    for (int i = 1; i < 8; i++) {
+      int32_t t1 = WADD(nw[i], b[i]), t0 = WADD(mb[i], b[i]);
+      m1 = t1 > m1 ? t1 : m1;
+      m0 = t0 > m0 ? t0 : m0;
+    }
+    for (int i = 0; i < 8; i++)
+      o[i] = mb[i] > nw[i] ? mb[i] : nw[i];
+    if (k % 4 == 0) {
+      for (int i = 1; i < 8; i++)
+        o[i] = WADD(o[i], -o[0]);
+      o[0] = 0;
+    }
+    out[k - 1] = WADD(m1, -m0);
+  }
+  free(beta);
+}
+
+/* ============================================================================ decoder object */
+
+/* implementation selector; values follow srslte_tdec_impl_type_t (include/srslte/phy/fec/turbodecoder_impl.h:28-38) */
+enum { ORC_AUTO = 0, ORC_GENERIC = 1, ORC_SSE = 2, ORC_SSE_WIN = 3, ORC_NEON_WIN = 4, ORC_AVX_WIN = 5, ORC_SSE8_WIN = 6, ORC_AVX8_WIN = 7 };
+
+typedef struct {
+  int       dec_type, force_not_sb;
+  uint32_t  K;
+  int       n_iter;
+  orc_cfg_t cfg;          /* active MAP configuration */
+  int       llr8;         /* arithmetic of the active decoder is 8-bit */
+  int       input_sb;     /* input arrives in lane layout */
+  uint16_t *fwd, *rev;
+  int32_t * syst, *par0, *par1, *app1, *app2, *ext1, *ext2; /* K+3 each */
+} orc_tdec_t;
+
+void* orc_tdec_new(int dec_type, int force_not_sb)
+{
+  orc_tdec_t* h   = calloc(1, sizeof(*h));
+  h->dec_type     = dec_type;
+  h->force_not_sb = force_not_sb;
+  size_t n        = ORC_MAX_K + 16;
+  h->fwd          = malloc(n * 2);
+  h->rev          = malloc(n * 2);
+  int32_t** a[]   = {&h->syst, &h->par0, &h->par1, &h->app1, &h->app2, &h->ext1, &h->ext2};
+  for (int i = 0; i < 7; i++)
+    *a[i] = calloc(n, sizeof(int32_t));
+  return h;
+}
+void orc_tdec_del(void* hh)
+{
+  orc_tdec_t* h = hh;
+  if (!h)
+    return;
+  free(h->fwd); free(h->rev); free(h->syst); free(h->par0); free(h->par1);
+  free(h->app1); free(h->app2); free(h->ext1); free(h->ext2); free(h);
+}
+
+static orc_cfg_t mk_cfg(int bits, uint32_t N)
+{
+  orc_cfg_t c;
+  c.bits      = bits;
+  c.N         = N;
+  c.inf       = bits == 16 ? 10000 : 0;
+  c.norm_max  = bits == 8;
+  c.out_shift = bits == 8 ? 1 : 0;
+  return c;
+}
+
+/* srslte_tdec_new_cb (src/phy/fec/turbodecoder.c:511-526) */
+int orc_tdec_new_cb(void* hh, uint32_t K)
+{
+  orc_tdec_t* h  = hh;
+  int         ci = orc_cbindex(K);
+  if (K > ORC_MAX_K || ci < 0 || lte_qpp_table[ci].K != K)
+    return -1;
+  h->K      = K;
+  h->n_iter = 0;
+  return 0;
+}
+
+/* dispatch of tdec_iteration_16 / tdec_iteration_8 (src/phy/fec/turbodecoder.c:458-508) for `in_bits`-wide input.
+ * patched8: for int8 input and 400 < K <= 800 convert the WHOLE lane-layout buffer (documented deviation from the
+ * reference, which reads uninitialised memory there: SURVEY 8a-4 #1). */
+static void select_impl(orc_tdec_t* h, int in_bits)
+{
+  uint32_t K = h->K, N;
+  switch (h->dec_type) {
+    case ORC_AUTO:
+      if (in_bits == 16) {
+        N           = orc_subblocks16(K);
+        h->cfg      = mk_cfg(16, N);
+        h->llr8     = 0;
+        h->input_sb = N > 0; /* iter.h:41 input_is_interleaved = current_dec > 0 */
+      } else {
+        N = orc_subblocks8(K);
+        if (N >= 16) {
+          h->cfg  = mk_cfg(8, N);
+          h->llr8 = 1;
+        } else {
+          h->cfg  = mk_cfg(16, N); /* widened to int16, then gen (N==0) or sse16 (N==8) */
+          h->llr8 = 0;
+        }
+        h->input_sb = N > 0;
+      }
+      break;
+    case ORC_GENERIC:
+      h->cfg = mk_cfg(16, 0); h->llr8 = 0; h->input_sb = 0;
+      break;
+    case ORC_SSE_WIN:
+      h->cfg = mk_cfg(16, 8); h->llr8 = 0; h->input_sb = 0; /* manual 16-bit: current_dec == 0 -> standard layout */
+      break;
+    case ORC_AVX_WIN:
+      h->cfg = mk_cfg(16, 16); h->llr8 = 0; h->input_sb = 0;
+      break;
+    case ORC_SSE8_WIN:
+      h->cfg = mk_cfg(8, 16); h->llr8 = 1; h->input_sb = 1;
+      break;
+    case ORC_AVX8_WIN:
+      h->cfg = mk_cfg(8, 32); h->llr8 = 1; h->input_sb = 1;
+      break;
+    default:
+      h->cfg = mk_cfg(16, 0); h->llr8 = 0; h->input_sb = 0;
+  }
+  if (h->force_not_sb)
+    h->input_sb = 0;
+}
+
+/* srslte_vec_sub_sss (16-bit: wraps) / srslte_vec_sub_bbb (8-bit: saturates for i < floor(K/32)*32, then wraps;
+ * AVX2 build, src/phy/utils/vector_simd.c:132-190) */
+static void vec_sub(const orc_tdec_t* h, const int32_t* a, const int32_t* b, int32_t* z)
+{
+  uint32_t K = h->K, simd_end = h->llr8 ? (K / 32) * 32 : 0;
+  for (uint32_t i = 0; i < K; i++) {
+    int32_t v = a[i] - b[i];
+    z[i]      = (h->llr8 && i < simd_end) ? sat(&h->cfg, v) : wrap(&h->cfg, v);
+  }
+}
+
+/* One half-iteration: run_tdec_iteration_{16,8}bit (include/srslte/phy/fec/turbodecoder_iter.h:72-144).
+ * input: the caller's LLR buffer widened to int32 (3K+12 standard, or 3(K+32)+12 lane layout). */
+static void half_iteration(orc_tdec_t* h, const int32_t* input)
+{
+  uint32_t K = h->K, N = h->cfg.N;
+  if (h->n_iter == 0) {
+    orc_qpp(K, N, h->fwd, h->rev);
+    if (h->input_sb) {
+      /* iter.h:59-69,90-97: three planes (K+32 apart) + tail */
+      memcpy(h->syst, input, K * sizeof(int32_t));
+      memcpy(h->par0, input + (K + 32), K * sizeof(int32_t));
+      memcpy(h->par1, input + 2 * (K + 32), K * sizeof(int32_t));
+      const int32_t* t = input + 3 * (K + 32);
+      for (uint32_t i = 0; i < 3; i++) {
+        h->syst[K + i] = t[2 * i];
+        h->par0[K + i] = t[2 * i + 1];
+        h->app2[K + i] = t[6 + 2 * i];
+        h->par1[K + i] = t[6 + 2 * i + 1];
+      }
+    } else {
+      /* extract_input: win.h:880-923 (to lane layout) / gen.c:238-258 (natural order) */
+      for (uint32_t n = 0; n < K; n++) {
+        uint32_t j = N > 0 ? to_lane(n, K, N) : n;
+        h->syst[j] = input[3 * n];
+        h->par0[j] = input[3 * n + 1];
+        h->par1[j] = input[3 * n + 2];
+      }
+      const int32_t* t = input + 3 * K;
+      for (uint32_t i = 0; i < 3; i++) {
+        h->syst[K + i] = t[2 * i];
+        h->par0[K + i] = t[2 * i + 1];
+        h->app2[K + i] = t[6 + 2 * i];
+        h->par1[K + i] = t[6 + 2 * i + 1];
+      }
+    }
+  }
+  if (h->n_iter % 2 == 0) {
+    if (h->n_iter)
+      vec_sub(h, h->app1, h->ext1, h->app1);
+    if (N)
+      map_win(&h->cfg, h->syst, h->n_iter ? h->app1 : NULL, h->par0, h->ext1, K);
+    else
+      map_gen(h->syst, h->n_iter ? h->app1 : NULL, h->par0, h->ext1, K);
+  } else {
+    if (h->n_iter > 1)
+      vec_sub(h, h->ext1, h->app1, h->ext1);
+    for (uint32_t i = 0; i < K; i++)
+      h->app2[h->rev[i]] = h->ext1[i];
+    if (N)
+      map_win(&h->cfg, h->app2, NULL, h->par1, h->ext2, K);
+    else
+      map_gen(h->app2, NULL, h->par1, h->ext2, K);
+    for (uint32_t i = 0; i < K; i++)
+      h->app1[h->fwd[i]] = h->ext2[i];
+  }
+  h->n_iter++;
+}
+
+/* tdec_decision_byte (turbodecoder.c:370-378) -> win.h:925-993 / gen.c:260-277 */
+static void decision(const orc_tdec_t* h, uint8_t* out)
+{
+  const int32_t* llr = (h->n_iter % 2 == 0) ? h->app1 : h->ext1;
+  uint32_t       K = h->K, N = h->cfg.N;
+  memset(out, 0, K / 8);
+  for (uint32_t n = 0; n < K; n++) {
+    uint32_t j = N > 0 ? to_lane(n, K, N) : n;
+    if (llr[j] > 0)
+      out[n >> 3] |= (uint8_t)(0x80u >> (n & 7));
+  }
+}
+
+static void widen(orc_tdec_t* h, const void* input, int in_bits, int32_t* dst)
+{
+  uint32_t K = h->K, n = h->input_sb ? 3 * (K + 32) + 12 : 3 * K + 12;
+  for (uint32_t i = 0; i < n; i++) {
+    int32_t v = in_bits == 16 ? (int32_t)((const int16_t*)input)[i] : (int32_t)((const int8_t*)input)[i];
+    /* manual 8-bit decoder driven through the 16-bit entry point: convert_16_to_8 truncates
+     * (src/phy/fec/turbodecoder.c:451-456, 499-504) */
+    dst[i] = (in_bits == 16 && h->llr8) ? (int32_t)(int8_t)(uint8_t)v : v;
+  }
+}
+
+/* srslte_tdec_iteration / srslte_tdec_iteration_8bit (turbodecoder.c:528-535, 552-558) */
+void orc_tdec_iteration(void* hh, const void* input, int in_bits, uint8_t* out)
+{
+  orc_tdec_t* h = hh;
+  if (h->K == 0)
+    return;
+  select_impl(h, in_bits);
+  int32_t* w = malloc((3 * (ORC_MAX_K + 32) + 12) * sizeof(int32_t));
+  if (h->n_iter == 0)
+    widen(h, input, in_bits, w);
+  half_iteration(h, w);
+  decision(h, out);
+  free(w);
+}
+/* srslte_tdec_run_all[_8bit] (turbodecoder.c:537-550, 560-578): do-while => at least one half-iteration */
+int orc_tdec_run_all(void* hh, const void* input, int in_bits, uint8_t* out, uint32_t nof_iter, uint32_t K)
+{
+  orc_tdec_t* h = hh;
+  if (orc_tdec_new_cb(h, K))
+    return -1;
+  select_impl(h, in_bits);
+  int32_t* w = malloc((3 * (ORC_MAX_K + 32) + 12) * sizeof(int32_t));
+  widen(h, input, in_bits, w);
+  do {
+    half_iteration(h, w);
+  } while ((uint32_t)h->n_iter < nof_iter);
+  decision(h, out);
+  free(w);
+  return 0;
+}
+int orc_tdec_n_iter(void* hh) { return ((orc_tdec_t*)hh)->n_iter; }
+/* which: 0 app1, 1 app2, 2 ext1, 3 ext2 (as int16) */
+void orc_tdec_get_llr(void* hh, int which, int16_t* dst, uint32_t n)
+{
+  orc_tdec_t*    h = hh;
+  const int32_t* s = which == 0 ? h->app1 : which == 1 ? h->app2 : which == 2 ? h->ext1 : h->ext2;
+  for (uint32_t i = 0; i < n; i++)
+    dst[i] = (int16_t)s[i];
+}
+
+/* ================================================================== transport block (sch.c) */
+
+#define ORC_MAX_CB 32 /* include/srslte/phy/common/phy_common.h:63 SRSLTE_MAX_CODEBLOCKS */
+#define CRC24A 0x1864CFB
+#define CRC24B 0x1800063
+
+typedef struct {
+  int16_t buffer[ORC_MAX_CB][ORC_SOFTBUFFER_SIZE]; /* int8 decoders view the same memory as int8 */
+  uint8_t data[ORC_MAX_CB][ORC_MAX_K / 8];
+  uint8_t cb_crc[ORC_MAX_CB];
+  uint8_t tb_crc;
+  void*   tdec;
+} orc_softbuffer_t;
+
+void* orc_softbuffer_new(void)
+{
+  orc_softbuffer_t* s = calloc(1, sizeof(*s));
+  s->tdec             = orc_tdec_new(ORC_AUTO, 0);
+  return s;
+}
+void orc_softbuffer_del(void* ss)
+{
+  orc_softbuffer_t* s = ss;
+  if (s) {
+    orc_tdec_del(s->tdec);
+    free(s);
+  }
+}
+/* srslte_softbuffer_rx_reset_cb (src/phy/fec/softbuffer.c:133-155), whole buffer */
+void orc_softbuffer_reset(void* ss)
+{
+  orc_softbuffer_t* s = ss;
+  void*             t = s->tdec;
+  memset(s, 0, sizeof(*s));
+  s->tdec = t;
+}
+int orc_softbuffer_get(void* ss, uint32_t cb, int16_t* dst, uint32_t n)
+{
+  memcpy(dst, ((orc_softbuffer_t*)ss)->buffer[cb], n * sizeof(int16_t));
+  return 0;
+}
+
+/* decode_tb + decode_tb_cb (src/phy/phch/sch.c:363-488, 503-570).
+ * Returns 0 / -1 / -2 like the reference; n_iter_out[cb] = half-iterations spent on CB cb (0 if skipped);
+ * *avg_iter = sum / C.  is8 selects int8 e_bits and the 8-bit AUTO decoders. */
+int orc_decode_tb(void* ss, uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const void* e_bits, int is8,
+                  uint32_t max_iter, uint8_t* data, uint32_t* n_iter_out, float* avg_iter)
+{
+  orc_softbuffer_t* sb = ss;
+  uint32_t          seg[9];
+  if (orc_cbsegm(tbs, seg))
+    return -1;
+  uint32_t F = seg[0], C = seg[1], K1 = seg[2], K2 = seg[3], C1 = seg[6];
+  if (tbs == 0 || C == 0)
+    return 0;
+  if (F)
+    return -2;
+  if (C > ORC_MAX_CB)
+    return -1;
+  data[tbs / 8 + 0] = 0;
+  data[tbs / 8 + 1] = 0;
+  data[tbs / 8 + 2] = 0;
+  uint32_t total = 0;
+  for (uint32_t cb = 0; cb < C; cb++) {
+    uint32_t K = cb < C1 ? K1 : K2, rlen = C == 1 ? K : K - 24;
+    if (n_iter_out)
+      n_iter_out[cb] = 0;
+    if (sb->cb_crc[cb]) {
+      memcpy(&data[cb * rlen / 8], sb->data[cb], rlen / 8);
+      continue;
+    }
+    uint32_t Gp = nof_e_bits / Qm, gamma = Gp % C, n_e = Qm * (Gp / C), rp = cb * n_e, n_e2 = n_e;
+    if (cb > C - gamma) { /* strict '>' as in sch.c:398 */
+      n_e2 = n_e + Qm;
+      rp   = (C - gamma) * n_e + (cb - (C - gamma)) * n_e2;
+    }
+    if (is8)
+      orc_rm_rx8((const int8_t*)e_bits + rp, (int8_t*)sb->buffer[cb], n_e2, K, rv, orc_subblocks8(K));
+    else
+      orc_rm_rx16((const int16_t*)e_bits + rp, sb->buffer[cb], n_e2, K, rv, orc_subblocks16(K));
+    orc_tdec_new_cb(sb->tdec, K);
+    uint32_t noi = 0;
+    int      ok  = 0;
+    do {
+      orc_tdec_iteration(sb->tdec, sb->buffer[cb], is8 ? 8 : 16, &data[cb * rlen / 8]);
+      noi++;
+      uint32_t len_crc = C > 1 ? K : tbs + 24;
+      if (orc_crc_bytes(C > 1 ? CRC24B : CRC24A, 24, &data[cb * rlen / 8], len_crc / 8) == 0) {
+        sb->cb_crc[cb] = 1;
+        ok             = 1;
+      }
+    } while (noi < max_iter && !ok);
+    total += noi;
+    if (n_iter_out)
+      n_iter_out[cb] = noi;
+  }
+  sb->tb_crc = 1;
+  for (uint32_t i = 0; i < C; i++)
+    sb->tb_crc = sb->tb_crc && sb->cb_crc[i];
+  if (!sb->tb_crc) {
+    for (uint32_t i = 0; i < C; i++) {
+      if (sb->cb_crc[i]) {
+        uint32_t K = i < C1 ? K1 : K2, rlen = C == 1 ? K : K - 24;
+        memcpy(sb->data[i], &data[i * rlen / 8], rlen / 8);
+      }
+    }
+  }
+  if (avg_iter)
+    *avg_iter = (float)total / (float)C;
+  if (!sb->tb_crc)
+    return -1;
+  uint32_t par_rx = orc_crc_bytes(CRC24A, 24, data, tbs / 8);
+  uint32_t par_tx = ((uint32_t)data[tbs / 8] << 16) | ((uint32_t)data[tbs / 8 + 1] << 8) | data[tbs / 8 + 2];
+  return (par_rx == par_tx && par_rx) ? 0 : -1;
+}
+void orc_softbuffer_get_crc(void* ss, uint8_t* cb_crc, uint32_t n)
+{
+  memcpy(cb_crc, ((orc_softbuffer_t*)ss)->cb_crc, n);
+}

@@ -1,0 +1,480 @@
+/*
+ * TEST INFRASTRUCTURE ONLY -- never linked into the product library.
+ *
+ * Thin flat-C shim over the UNMODIFIED reference (srsLTE 20.10.1) compiled by
+ * oracle/build_ref.sh into oracle/_ref/libsrslte_ref.so.  It only forwards to
+ * the reference's own public entry points so that Python (ctypes) tests and
+ * bench.py's CPU-baseline arm can drive them:
+ *
+ *   srslte_tdec_*            lib/include/srslte/phy/fec/turbodecoder.h:97-121
+ *   srslte_rm_turbo_rx_lut*  lib/include/srslte/phy/fec/rm_turbo.h:75-89
+ *   srslte_crc_*             lib/include/srslte/phy/fec/crc.h:48-74
+ *   srslte_cbsegm*           lib/include/srslte/phy/fec/cbsegm.h:46-52
+ *   srslte_dlsch_encode2 / srslte_dlsch_decode2   lib/src/phy/phch/sch.c:577,611
+ *
+ * Nothing in here re-implements reference arithmetic.
+ */
+#include <pthread.h>
+#include <stdbool.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include "srslte/phy/common/phy_common.h"
+#include "srslte/phy/fec/cbsegm.h"
+#include "srslte/phy/fec/crc.h"
+#include "srslte/phy/fec/rm_turbo.h"
+#include "srslte/phy/fec/softbuffer.h"
+#include "srslte/phy/fec/tc_interl.h"
+#include "srslte/phy/fec/turbocoder.h"
+#include "srslte/phy/fec/turbodecoder.h"
+#include "srslte/phy/phch/pdsch_cfg.h"
+#include "srslte/phy/phch/sch.h"
+
+static double now_s(void)
+{
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+int ref_init(void)
+{
+  srslte_rm_turbo_gentables();
+  return 0;
+}
+
+/* ------------------------------------------------------------------ tables */
+int ref_cbsegm(uint32_t tbs, uint32_t out[9])
+{
+  srslte_cbsegm_t s;
+  memset(&s, 0, sizeof(s));
+  int r  = srslte_cbsegm(&s, tbs);
+  out[0] = s.F;
+  out[1] = s.C;
+  out[2] = s.K1;
+  out[3] = s.K2;
+  out[4] = s.K1_idx;
+  out[5] = s.K2_idx;
+  out[6] = s.C1;
+  out[7] = s.C2;
+  out[8] = s.tbs;
+  return r;
+}
+int      ref_cbsize(uint32_t idx) { return srslte_cbsegm_cbsize(idx); }
+int      ref_cbindex(uint32_t K) { return srslte_cbsegm_cbindex(K); }
+uint32_t ref_subblocks16(uint32_t K) { return srslte_tdec_autoimp_get_subblocks(K); }
+uint32_t ref_subblocks8(uint32_t K) { return srslte_tdec_autoimp_get_subblocks_8bit(K); }
+
+int ref_qpp(uint32_t K, uint32_t nsb, uint16_t* fwd, uint16_t* rev)
+{
+  srslte_tc_interl_t t;
+  if (srslte_tc_interl_init(&t, K) < 0)
+    return -1;
+  int r = srslte_tc_interl_LTE_gen_interl(&t, K, nsb);
+  if (r == 0) {
+    memcpy(fwd, t.forward, K * sizeof(uint16_t));
+    memcpy(rev, t.reverse, K * sizeof(uint16_t));
+  }
+  srslte_tc_interl_free(&t);
+  return r;
+}
+
+/* --------------------------------------------------------------------- crc */
+uint32_t ref_crc_byte(uint32_t poly, int order, uint8_t* data, int len_bits)
+{
+  srslte_crc_t c;
+  srslte_crc_init(&c, poly, order);
+  return srslte_crc_checksum_byte(&c, data, len_bits);
+}
+uint32_t ref_crc_bits(uint32_t poly, int order, uint8_t* bits, int len_bits)
+{
+  srslte_crc_t c;
+  srslte_crc_init(&c, poly, order);
+  return srslte_crc_checksum(&c, bits, len_bits);
+}
+
+/* --------------------------------------------------------- rate (de)matching */
+int ref_rm_rx_lut16(int16_t* in, int16_t* out, uint32_t E, uint32_t cb_idx, uint32_t rv, int enable_sb)
+{
+  return srslte_rm_turbo_rx_lut_(in, out, E, cb_idx, rv, enable_sb ? true : false);
+}
+int ref_rm_rx_lut8(int8_t* in, int8_t* out, uint32_t E, uint32_t cb_idx, uint32_t rv)
+{
+  return srslte_rm_turbo_rx_lut_8bit(in, out, E, cb_idx, rv);
+}
+/* procedural transmitter rate matcher on unpacked bits (rm_turbo.c:870) */
+int ref_rm_tx(uint8_t* in_bits, uint32_t in_len, uint8_t* out_bits, uint32_t E, uint32_t rv)
+{
+  uint32_t buff_len = 3 * 6176 + 64;
+  uint8_t* w        = calloc(buff_len, 1);
+  int      r        = srslte_rm_turbo_tx(w, buff_len, in_bits, in_len, out_bits, E, rv);
+  free(w);
+  return r;
+}
+/* procedural float receiver (rm_turbo.c:950), the function rm_turbo_test.c:171-190 compares against */
+int ref_rm_rx_float(float* in, uint32_t E, float* out, uint32_t out_len, uint32_t rv)
+{
+  uint32_t buff_len = 3 * 6176 + 64;
+  float*   w        = calloc(buff_len, sizeof(float));
+  for (uint32_t i = 0; i < buff_len; i++)
+    w[i] = SRSLTE_RX_NULL;
+  int r = srslte_rm_turbo_rx(w, buff_len, in, E, out, out_len, rv, 0);
+  free(w);
+  return r;
+}
+
+/* ----------------------------------------------------------------- encoder */
+int ref_tcod_encode(uint8_t* bits, uint8_t* out_bits, uint32_t K)
+{
+  srslte_tcod_t t;
+  if (srslte_tcod_init(&t, 6144))
+    return -1;
+  int r = srslte_tcod_encode(&t, bits, out_bits, K);
+  srslte_tcod_free(&t);
+  return r;
+}
+
+/* ----------------------------------------------------------------- decoder */
+typedef struct {
+  srslte_tdec_t td;
+  int16_t*      conv; /* patched 8->16 conversion buffer */
+  int           use_patched;
+} ref_tdec_t;
+
+void* ref_tdec_new(uint32_t max_k, int dec_type, int force_not_sb)
+{
+  ref_tdec_t* h = calloc(1, sizeof(ref_tdec_t));
+  if (srslte_tdec_init_manual(&h->td, max_k, (srslte_tdec_impl_type_t)dec_type)) {
+    free(h);
+    return NULL;
+  }
+  if (force_not_sb)
+    srslte_tdec_force_not_sb(&h->td);
+  h->conv = calloc(3 * (6144 + 32) + 12 + 64, sizeof(int16_t));
+  return h;
+}
+void ref_tdec_del(void* hh)
+{
+  ref_tdec_t* h = hh;
+  if (!h)
+    return;
+  srslte_tdec_free(&h->td);
+  free(h->conv);
+  free(h);
+}
+int ref_tdec_new_cb(void* hh, uint32_t K) { return srslte_tdec_new_cb(&((ref_tdec_t*)hh)->td, K); }
+int ref_tdec_n_iter(void* hh) { return srslte_tdec_get_nof_iterations(&((ref_tdec_t*)hh)->td); }
+int ref_tdec_current(void* hh, int out[3])
+{
+  ref_tdec_t* h = hh;
+  out[0]        = (int)h->td.current_llr_type;
+  out[1]        = (int)h->td.current_dec;
+  out[2]        = (int)h->td.current_inter_idx;
+  return 0;
+}
+
+void ref_tdec_iteration16(void* hh, int16_t* input, uint8_t* out)
+{
+  srslte_tdec_iteration(&((ref_tdec_t*)hh)->td, input, out);
+}
+
+/* patched!=0: for 400 < K <= 800 the reference's int8 AUTO path reads uninitialised memory
+ * (turbodecoder.c:478 converts 3K+12 of the 3(K+32)+12 SB-8 elements); the patched variant converts
+ * the whole SB buffer to int16 and then runs the reference's own 16-bit path. */
+void ref_tdec_iteration8(void* hh, int8_t* input, uint8_t* out, int patched)
+{
+  ref_tdec_t* h = hh;
+  uint32_t    K = h->td.current_long_cb;
+  if (patched && K > 400 && K <= 800 && h->td.dec_type == SRSLTE_TDEC_AUTO) {
+    if (h->td.n_iter == 0) {
+      uint32_t n = 3 * (K + 32) + 12;
+      for (uint32_t i = 0; i < n; i++)
+        h->conv[i] = (int16_t)input[i];
+    }
+    h->use_patched = 1;
+    srslte_tdec_iteration(&h->td, h->conv, out);
+  } else {
+    h->use_patched = 0;
+    srslte_tdec_iteration_8bit(&h->td, input, out);
+  }
+}
+
+/* copy an internal LLR array widened to int16: which = 0 app1, 1 app2, 2 ext1, 3 ext2 */
+int ref_tdec_get_llr(void* hh, int which, int16_t* dst, uint32_t n)
+{
+  ref_tdec_t* h   = hh;
+  void*       src = which == 0 ? h->td.app1 : which == 1 ? h->td.app2 : which == 2 ? h->td.ext1 : h->td.ext2;
+  if (h->td.current_llr_type == SRSLTE_TDEC_16) {
+    memcpy(dst, src, n * sizeof(int16_t));
+  } else {
+    for (uint32_t i = 0; i < n; i++)
+      dst[i] = ((int8_t*)src)[i];
+  }
+  return (int)h->td.current_llr_type;
+}
+
+int ref_tdec_run_all16(void* hh, int16_t* input, uint8_t* out, uint32_t nof_iter, uint32_t K)
+{
+  return srslte_tdec_run_all(&((ref_tdec_t*)hh)->td, input, out, nof_iter, K);
+}
+int ref_tdec_run_all8(void* hh, int8_t* input, uint8_t* out, uint32_t nof_iter, uint32_t K)
+{
+  return srslte_tdec_run_all_8bit(&((ref_tdec_t*)hh)->td, input, out, nof_iter, K);
+}
+
+/* ------------------------------------------------- TB level (the real sch.c) */
+typedef struct {
+  srslte_sch_t           sch;
+  srslte_softbuffer_rx_t rx;
+  srslte_softbuffer_tx_t tx;
+} ref_sch_t;
+
+static srslte_mod_t mod_from_qm(uint32_t Qm)
+{
+  switch (Qm) {
+    case 1:
+      return SRSLTE_MOD_BPSK;
+    case 2:
+      return SRSLTE_MOD_QPSK;
+    case 4:
+      return SRSLTE_MOD_16QAM;
+    case 6:
+      return SRSLTE_MOD_64QAM;
+    default:
+      return SRSLTE_MOD_256QAM;
+  }
+}
+
+void* ref_sch_new(int llr_is_8bit, uint32_t max_iter, uint32_t nof_prb)
+{
+  ref_sch_t* s = calloc(1, sizeof(ref_sch_t));
+  if (srslte_sch_init(&s->sch))
+    return NULL;
+  s->sch.llr_is_8bit = llr_is_8bit ? true : false;
+  srslte_sch_set_max_noi(&s->sch, max_iter);
+  if (srslte_softbuffer_rx_init(&s->rx, nof_prb))
+    return NULL;
+  if (srslte_softbuffer_tx_init(&s->tx, nof_prb))
+    return NULL;
+  srslte_softbuffer_rx_reset(&s->rx);
+  srslte_softbuffer_tx_reset(&s->tx);
+  return s;
+}
+void ref_sch_del(void* ss)
+{
+  ref_sch_t* s = ss;
+  if (!s)
+    return;
+  srslte_softbuffer_rx_free(&s->rx);
+  srslte_softbuffer_tx_free(&s->tx);
+  /* srslte_sch_free() also tears down the process-global rm tables; regenerate them for other users */
+  srslte_sch_free(&s->sch);
+  srslte_rm_turbo_gentables();
+  free(s);
+}
+void ref_sch_set_max_noi(void* ss, uint32_t n) { srslte_sch_set_max_noi(&((ref_sch_t*)ss)->sch, n); }
+void ref_sch_reset_rx(void* ss, uint32_t tbs) { srslte_softbuffer_rx_reset_tbs(&((ref_sch_t*)ss)->rx, tbs); }
+
+static void fill_cfg(ref_sch_t* s, srslte_pdsch_cfg_t* cfg, uint32_t tbs, uint32_t Qm, uint32_t G, uint32_t rv, int tx)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->grant.nof_tb         = 1;
+  cfg->grant.nof_layers     = 1;
+  cfg->grant.nof_re         = G / Qm;
+  cfg->grant.tb[0].enabled  = true;
+  cfg->grant.tb[0].tbs      = (int)tbs;
+  cfg->grant.tb[0].rv       = (int)rv;
+  cfg->grant.tb[0].mod      = mod_from_qm(Qm);
+  cfg->grant.tb[0].nof_bits = G;
+  if (tx)
+    cfg->softbuffers.tx[0] = &s->tx;
+  else
+    cfg->softbuffers.rx[0] = &s->rx;
+}
+
+/* data: tbs/8 bytes in; e_bytes: ceil(G/8) packed bytes out */
+int ref_sch_encode(void* ss, uint32_t tbs, uint32_t Qm, uint32_t G, uint32_t rv, uint8_t* data, uint8_t* e_bytes)
+{
+  ref_sch_t*         s = ss;
+  srslte_pdsch_cfg_t cfg;
+  fill_cfg(s, &cfg, tbs, Qm, G, rv, 1);
+  if (rv == 0)
+    srslte_softbuffer_tx_reset_tbs(&s->tx, tbs);
+  return srslte_dlsch_encode2(&s->sch, &cfg, data, e_bytes, 0, 1);
+}
+
+/* llr: int16[G] or int8[G]; data_out: >= tbs/8+6 bytes; cb_crc_out: C flags; returns the reference's return code */
+int ref_sch_decode(void*    ss,
+                   uint32_t tbs,
+                   uint32_t Qm,
+                   uint32_t G,
+                   uint32_t rv,
+                   void*    llr,
+                   uint8_t* data_out,
+                   float*   avg_iter,
+                   uint8_t* cb_crc_out,
+                   uint32_t max_cb_out)
+{
+  ref_sch_t*         s = ss;
+  srslte_pdsch_cfg_t cfg;
+  fill_cfg(s, &cfg, tbs, Qm, G, rv, 0);
+  int r = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, data_out, 0, 1);
+  if (avg_iter)
+    *avg_iter = srslte_sch_last_noi(&s->sch);
+  if (cb_crc_out) {
+    for (uint32_t i = 0; i < max_cb_out && i < s->rx.max_cb; i++)
+      cb_crc_out[i] = s->rx.cb_crc[i] ? 1 : 0;
+  }
+  return r;
+}
+/* peek at the HARQ soft buffer of one CB (int16 view of SOFTBUFFER_SIZE elements) */
+int ref_sch_get_softbuffer(void* ss, uint32_t cb, int16_t* dst, uint32_t n)
+{
+  ref_sch_t* s = ss;
+  if (cb >= s->rx.max_cb)
+    return -1;
+  memcpy(dst, s->rx.buffer_f[cb], n * sizeof(int16_t));
+  return 0;
+}
+
+/* --------------------------------------------- CPU baseline runners (pthreads) */
+typedef struct {
+  int       tid, nthreads;
+  uint32_t  ncb, K, nof_iter;
+  int       is8, layout_sb;
+  void*     llr; /* ncb x stride elements */
+  uint32_t  stride;
+  uint8_t*  out; /* ncb x K/8 */
+  pthread_barrier_t* bar;
+  double    t0, t1;
+} c1_arg_t;
+
+static void* c1_worker(void* p)
+{
+  c1_arg_t*   a = p;
+  ref_tdec_t* h = ref_tdec_new(6144, SRSLTE_TDEC_AUTO, a->layout_sb ? 0 : 1);
+  pthread_barrier_wait(a->bar);
+  a->t0 = now_s();
+  for (uint32_t cb = a->tid; cb < a->ncb; cb += a->nthreads) {
+    uint8_t* o = a->out + (size_t)cb * (a->K / 8);
+    if (a->is8)
+      srslte_tdec_run_all_8bit(&h->td, (int8_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
+    else
+      srslte_tdec_run_all(&h->td, (int16_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
+  }
+  a->t1 = now_s();
+  ref_tdec_del(h);
+  return NULL;
+}
+
+/* Decode ncb code blocks of size K (fixed nof_iter half-iterations, srslte_tdec_run_all[_8bit]) on nthreads
+ * threads; returns wall seconds of the decode phase (max over threads). */
+double ref_bench_c1(int       nthreads,
+                    void*     llr,
+                    uint32_t  stride,
+                    uint32_t  ncb,
+                    uint32_t  K,
+                    uint32_t  nof_iter,
+                    int       is8,
+                    int       layout_sb,
+                    uint8_t*  out)
+{
+  pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
+  c1_arg_t*         a  = calloc(nthreads, sizeof(c1_arg_t));
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    a[t] = (c1_arg_t){t, nthreads, ncb, K, nof_iter, is8, layout_sb, llr, stride, out, &bar, 0, 0};
+    pthread_create(&th[t], NULL, c1_worker, &a[t]);
+  }
+  double t0 = 1e300, t1 = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    if (a[t].t0 < t0)
+      t0 = a[t].t0;
+    if (a[t].t1 > t1)
+      t1 = a[t].t1;
+  }
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(a);
+  return t1 - t0;
+}
+
+typedef struct {
+  int       tid, nthreads;
+  uint32_t  ntb, tbs, Qm, G, rv, max_iter;
+  int       is8;
+  void*     llr; /* ntb x G */
+  uint8_t*  out; /* ntb x out_stride */
+  uint32_t  out_stride;
+  int*      rc;
+  float*    avg_iter;
+  pthread_barrier_t* bar;
+  double    t0, t1;
+} tb_arg_t;
+
+static void* tb_worker(void* p)
+{
+  tb_arg_t*  a = p;
+  ref_sch_t* s = calloc(1, sizeof(ref_sch_t));
+  srslte_sch_init(&s->sch);
+  s->sch.llr_is_8bit = a->is8 ? true : false;
+  srslte_sch_set_max_noi(&s->sch, a->max_iter);
+  srslte_softbuffer_rx_init(&s->rx, 100);
+  pthread_barrier_wait(a->bar);
+  a->t0 = now_s();
+  for (uint32_t tb = a->tid; tb < a->ntb; tb += a->nthreads) {
+    srslte_softbuffer_rx_reset_tbs(&s->rx, a->tbs);
+    void* llr = a->is8 ? (void*)((int8_t*)a->llr + (size_t)tb * a->G) : (void*)((int16_t*)a->llr + (size_t)tb * a->G);
+    srslte_pdsch_cfg_t cfg;
+    fill_cfg(s, &cfg, a->tbs, a->Qm, a->G, a->rv, 0);
+    a->rc[tb]       = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, a->out + (size_t)tb * a->out_stride, 0, 1);
+    a->avg_iter[tb] = srslte_sch_last_noi(&s->sch);
+  }
+  a->t1 = now_s();
+  srslte_softbuffer_rx_free(&s->rx);
+  /* do not call srslte_sch_free: it frees the process-global rm tables other threads still use */
+  return NULL;
+}
+
+/* Decode ntb transport blocks (new transmissions: soft buffer reset before each) with the reference's real
+ * srslte_dlsch_decode2 on nthreads threads; returns wall seconds. */
+double ref_bench_tb(int      nthreads,
+                    void*    llr,
+                    uint32_t ntb,
+                    uint32_t tbs,
+                    uint32_t Qm,
+                    uint32_t G,
+                    uint32_t rv,
+                    uint32_t max_iter,
+                    int      is8,
+                    uint8_t* out,
+                    uint32_t out_stride,
+                    int*     rc,
+                    float*   avg_iter)
+{
+  srslte_rm_turbo_gentables();
+  pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
+  tb_arg_t*         a  = calloc(nthreads, sizeof(tb_arg_t));
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    a[t] = (tb_arg_t){t, nthreads, ntb, tbs, Qm, G, rv, max_iter, is8, llr, out, out_stride, rc, avg_iter, &bar, 0, 0};
+    pthread_create(&th[t], NULL, tb_worker, &a[t]);
+  }
+  double t0 = 1e300, t1 = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    if (a[t].t0 < t0)
+      t0 = a[t].t0;
+    if (a[t].t1 > t1)
+      t1 = a[t].t1;
+  }
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(a);
+  return t1 - t0;
+}
