@@ -1,0 +1,116 @@
+/*
+ * srslte_b200/batch.h -- the NEW batched C-ABI entry points of the B200 turbo-decode engine.
+ *
+ * These are what the existing C host code calls instead of looping over code blocks one at a time
+ * (reference: the per-code-block loop decode_tb_cb, lib/src/phy/phch/sch.c:363-488, driven from
+ * srslte_dlsch_decode2 sch.c:577-606 / srslte_ulsch_decode sch.c:1105-1180).  Plain C: pointers and sizes
+ * only, no CUDA or torch types.  All work runs on the GPU; there is no CPU fallback -- every entry point
+ * returns SRSLTE_B200_ERROR_NO_DEVICE when no sm_100 device is usable.
+ */
+#ifndef SRSLTE_B200_BATCH_H
+#define SRSLTE_B200_BATCH_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRSLTE_B200_API __attribute__((visibility("default")))
+
+#define SRSLTE_B200_SUCCESS 0
+#define SRSLTE_B200_ERROR -1
+#define SRSLTE_B200_ERROR_INVALID_INPUTS -2
+#define SRSLTE_B200_ERROR_NO_DEVICE -3
+
+#define SRSLTE_B200_MAX_CODEBLOCKS 32 /* SRSLTE_MAX_CODEBLOCKS, lib/include/srslte/phy/common/phy_common.h:63 */
+
+/* flags for the batch calls */
+#define SRSLTE_B200_IN_DEVICE 1u  /* LLR / e_bits pointers are device pointers (already resident in HBM) */
+#define SRSLTE_B200_OUT_DEVICE 2u /* output byte pointers are device pointers */
+
+typedef struct srslte_b200_ctx srslte_b200_ctx_t;             /* one engine instance = one GPU + one stream */
+typedef struct srslte_b200_softbuffer srslte_b200_softbuffer_t; /* device-resident srslte_softbuffer_rx_t */
+
+/* Create / destroy an engine on CUDA device `device` (-1: current device).  Generates and uploads all tables
+ * (QPP: tc_interl_lte.c:69-109 for 188 K x {1,8,16,32} lanes; rate de-matching: rm_turbo.c:280-321). */
+SRSLTE_B200_API int  srslte_b200_ctx_create(srslte_b200_ctx_t** ctx, int device);
+SRSLTE_B200_API void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API const char* srslte_b200_last_error(void);
+
+/* Pinned host memory helpers (page-locked buffers make the H2D/D2H copies asynchronous). */
+SRSLTE_B200_API void* srslte_b200_host_alloc(uint64_t bytes);
+SRSLTE_B200_API void  srslte_b200_host_free(void* p);
+SRSLTE_B200_API void* srslte_b200_device_alloc(uint64_t bytes);
+SRSLTE_B200_API void  srslte_b200_device_free(void* p);
+SRSLTE_B200_API int   srslte_b200_memcpy_h2d(srslte_b200_ctx_t* ctx, void* dst, const void* src, uint64_t bytes);
+SRSLTE_B200_API int   srslte_b200_memcpy_d2h(srslte_b200_ctx_t* ctx, void* dst, const void* src, uint64_t bytes);
+
+/* ---- batch of independent code blocks, fixed number of half-iterations, no CRC:
+ * the batched form of srslte_tdec_run_all[_8bit] (turbodecoder.c:537-578).
+ *   llr        nof_cb blocks, llr_stride elements apart, int16 (llr_bits 16) or int8 (llr_bits 8)
+ *   input_sb   0: standard order 3k+s, 3K+12 values (what srslte_tdec_force_not_sb selects, turbodecoder.c:365);
+ *              1: the lane layout written by srslte_rm_turbo_rx_lut (3(K+32)+12 values, rm_turbo.c:263-277)
+ *   dec_type   srslte_tdec_impl_type_t value (0 = AUTO)
+ *   out        nof_cb x K/8 bytes, MSB first
+ */
+typedef struct {
+  uint32_t K;
+  uint32_t nof_cb;
+  uint32_t nof_iterations;
+  uint32_t llr_bits;
+  uint32_t llr_stride;
+  uint32_t input_sb;
+  uint32_t dec_type;
+} srslte_b200_cb_batch_t;
+
+SRSLTE_B200_API int
+srslte_b200_tdec_batch(srslte_b200_ctx_t* ctx, const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags);
+
+/* ---- batch of transport blocks: the batched form of decode_tb (sch.c:503-570) for many TBs / TTIs at once. */
+typedef struct {
+  /* inputs */
+  const void*               e_bits;     /* int16[nof_e_bits] or int8[nof_e_bits] (llr_is_8bit) */
+  uint32_t                  nof_e_bits; /* G */
+  uint32_t                  tbs;        /* transport block size in bits */
+  uint32_t                  Qm;         /* modulation order x layers, as decode_tb's Qm */
+  uint32_t                  rv;
+  srslte_b200_softbuffer_t* softbuffer; /* HARQ state, or NULL for a one-shot new transmission */
+  uint8_t*                  data;       /* >= tbs/8 + 6 bytes */
+  /* outputs */
+  int32_t  ret;                                   /* decode_tb's return value: 0, -1 (CRC), -2 (invalid) */
+  float    avg_iterations;                        /* srslte_sch_last_noi */
+  uint8_t  cb_crc[SRSLTE_B200_MAX_CODEBLOCKS];    /* softbuffer->cb_crc after the call */
+  uint8_t  cb_noi[SRSLTE_B200_MAX_CODEBLOCKS];    /* half-iterations spent per code block in this call */
+  uint32_t nof_cb;
+} srslte_b200_tb_t;
+
+SRSLTE_B200_API int srslte_b200_decode_tbs(srslte_b200_ctx_t* ctx,
+                                           srslte_b200_tb_t*  tbs,
+                                           uint32_t           nof_tb,
+                                           int                llr_is_8bit,
+                                           uint32_t           max_iterations,
+                                           uint32_t           flags);
+
+/* asynchronous split of the two calls above: submit enqueues copies + kernels on the engine's stream and returns;
+ * wait blocks until they are done and fills the outputs.  One submit may be outstanding per context. */
+SRSLTE_B200_API int srslte_b200_tdec_batch_submit(srslte_b200_ctx_t* ctx, const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags);
+SRSLTE_B200_API int srslte_b200_decode_tbs_submit(srslte_b200_ctx_t* ctx, srslte_b200_tb_t* tbs, uint32_t nof_tb, int llr_is_8bit, uint32_t max_iterations, uint32_t flags);
+SRSLTE_B200_API int srslte_b200_wait(srslte_b200_ctx_t* ctx);
+
+/* device-resident HARQ soft buffers (srslte_softbuffer_rx_init / _reset / _free, softbuffer.c:41-155) */
+SRSLTE_B200_API int  srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer_t** sb, uint32_t max_cb);
+SRSLTE_B200_API void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb);
+SRSLTE_B200_API void srslte_b200_softbuffer_free(srslte_b200_softbuffer_t* sb);
+
+/* measurement hooks: device time of the kernels of the last completed batch, kernel launches it issued */
+SRSLTE_B200_API float    srslte_b200_last_gpu_ms(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API uint32_t srslte_b200_last_launches(srslte_b200_ctx_t* ctx);
+/* device time (ms) and launch count of only the max-log-MAP kernel in the last batch */
+SRSLTE_B200_API float    srslte_b200_last_map_ms(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API uint32_t srslte_b200_last_map_launches(srslte_b200_ctx_t* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -121,6 +121,27 @@ class Port:
         d = _u8(bits)
         return self.L.orc_crc_bits(C.c_uint32(poly), C.c_int(order), _p(d), C.c_uint32(len(d)))
 
+    # transmit side (test-input synthesis)
+    def tcod_encode(self, bits):
+        b = _u8(bits)
+        out = np.zeros(3 * len(b) + 12, np.uint8)
+        rc = self.L.orc_tcod_encode(_p(b), _p(out), C.c_uint32(len(b)))
+        assert rc == 0
+        return out
+
+    def encode_tb(self, tbs, Qm, rv, G, data):
+        d = _u8(data)
+        assert len(d) >= tbs // 8
+        e = np.zeros(G, np.uint8)
+        rc = self.L.orc_encode_tb(C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(rv), C.c_uint32(G), _p(d), _p(e))
+        assert rc == 0, rc
+        return e
+
+    def map_win(self, bits, N, x, apr, par, K):
+        out = np.zeros(K + 3, np.int16)
+        self.L.orc_map_win(C.c_int(bits), C.c_uint32(N), _p(_i16(x)), _p(_i16(apr)) if apr is not None else None, _p(_i16(par)), _p(out), C.c_uint32(K))
+        return out[:K]
+
     # decoder object
     def tdec_new(self, dec_type=TDEC_AUTO, force_not_sb=False):
         return C.c_void_p(self.L.orc_tdec_new(C.c_int(dec_type), C.c_int(int(force_not_sb))))

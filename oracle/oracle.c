@@ -814,3 +814,108 @@ void orc_softbuffer_get_crc(void* ss, uint8_t* cb_crc, uint32_t n)
 {
   memcpy(cb_crc, ((orc_softbuffer_t*)ss)->cb_crc, n);
 }
+
+/* ------------------------------------------------------------------ single MAP call, exported for unit tests
+ * (lane-layout int16 arrays in, K+3 elements for in/par; app may be NULL) */
+void orc_map_win(int bits, uint32_t N, const int16_t* in, const int16_t* app, const int16_t* par, int16_t* out, uint32_t K)
+{
+  orc_cfg_t c = mk_cfg(bits, N);
+  int32_t * i32 = malloc((K + 3) * 4), *a32 = app ? malloc((K + 3) * 4) : NULL, *p32 = malloc((K + 3) * 4), *o32 = malloc((K + 3) * 4);
+  for (uint32_t i = 0; i < K + 3; i++) {
+    i32[i] = in[i];
+    p32[i] = par[i];
+    if (a32)
+      a32[i] = i < K ? app[i] : 0;
+  }
+  map_win(&c, i32, a32, p32, o32, K);
+  for (uint32_t i = 0; i < K; i++)
+    out[i] = (int16_t)o32[i];
+  free(i32); free(p32); free(o32);
+  if (a32) free(a32);
+}
+
+/* ============================================================== transmit side (test-input synthesis only)
+ * Restates the reference encoder chain so tests can build valid code words / transport blocks anywhere:
+ * srslte_tcod_encode (src/phy/fec/turbocoder.c:80-187), encode_tb_off (src/phy/phch/sch.c:235-349) and the
+ * bit-selection of TS 36.212 5.1.4.1.2 via the receive table (e_k = codeword[table[k mod (3K+12)]]). */
+static inline void rsc_step(uint8_t bit, uint8_t s[3], uint8_t* parity)
+{
+  uint8_t fb = bit ^ s[1] ^ s[2];   /* g0 = 1 + D^2 + D^3 */
+  *parity    = fb ^ s[0] ^ s[2];    /* g1 = 1 + D + D^3   */
+  s[2]       = s[1];
+  s[1]       = s[0];
+  s[0]       = fb;
+}
+/* in: K bits (one per byte) -> out: 3K+12 bits: (x_k, z_k, z'_k) triples then 12 tail bits */
+int orc_tcod_encode(const uint8_t* in, uint8_t* out, uint32_t K)
+{
+  int ci = orc_cbindex(K);
+  if (ci < 0 || lte_qpp_table[ci].K != K)
+    return -1;
+  uint64_t f1 = lte_qpp_table[ci].f1, f2 = lte_qpp_table[ci].f2;
+  uint8_t  s1[3] = {0, 0, 0}, s2[3] = {0, 0, 0};
+  for (uint64_t i = 0; i < K; i++) {
+    uint8_t p;
+    out[3 * i] = in[i];
+    rsc_step(in[i], s1, &p);
+    out[3 * i + 1] = p;
+    rsc_step(in[(f1 * i + f2 * i * i) % K], s2, &p);
+    out[3 * i + 2] = p;
+  }
+  uint32_t k = 3 * K;
+  for (int e = 0; e < 2; e++) {
+    uint8_t* s = e ? s2 : s1;
+    for (int j = 0; j < 3; j++) {
+      uint8_t bit = s[1] ^ s[2], p; /* drives the register back to zero */
+      out[k++]    = bit;
+      rsc_step(bit, s, &p);
+      out[k++] = p;
+    }
+  }
+  return 0;
+}
+
+static void put_crc24(uint32_t crc, uint8_t* dst)
+{
+  dst[0] = (uint8_t)(crc >> 16);
+  dst[1] = (uint8_t)(crc >> 8);
+  dst[2] = (uint8_t)crc;
+}
+
+/* data: tbs/8 bytes -> e_bits: nof_e_bits bits (one per byte).  Returns 0 or -1 / -2 like encode_tb_off. */
+int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, const uint8_t* data, uint8_t* e_bits)
+{
+  uint32_t seg[9];
+  if (orc_cbsegm(tbs, seg))
+    return -1;
+  uint32_t F = seg[0], C = seg[1], K1 = seg[2], K2 = seg[3], C2 = seg[7];
+  if (F)
+    return -2;
+  uint32_t B    = tbs + 24;
+  uint8_t* tb   = calloc(B / 8 + 8, 1);
+  memcpy(tb, data, tbs / 8);
+  put_crc24(orc_crc_bytes(CRC24A, 24, tb, tbs / 8), tb + tbs / 8);
+  uint32_t  Gp = nof_e_bits / Qm, gamma = Gp % C, rp = 0, wp = 0;
+  uint8_t*  cb  = malloc(ORC_MAX_K / 8 + 8);
+  uint8_t*  cbb = malloc(ORC_MAX_K);
+  uint8_t*  cw  = malloc(3 * ORC_MAX_K + 12);
+  uint16_t* tab = malloc((3 * ORC_MAX_K + 12) * sizeof(uint16_t));
+  for (uint32_t i = 0; i < C; i++) {
+    uint32_t K    = i < C2 ? K2 : K1; /* encoder order (sch.c:277-283) */
+    uint32_t rlen = C > 1 ? K - 24 : K;
+    uint32_t n_e  = (i + gamma + 1 <= C) ? Qm * (Gp / C) : Qm * ((Gp + C - 1) / C); /* sch.c:289-293 */
+    memcpy(cb, tb + rp / 8, rlen / 8);
+    if (C > 1)
+      put_crc24(orc_crc_bytes(CRC24B, 24, cb, rlen / 8), cb + rlen / 8);
+    for (uint32_t b = 0; b < K; b++)
+      cbb[b] = (cb[b >> 3] >> (7 - (b & 7))) & 1u;
+    orc_tcod_encode(cbb, cw, K);
+    orc_rm_table(K, rv, 0, tab);
+    for (uint32_t k = 0; k < n_e && wp + k < nof_e_bits; k++)
+      e_bits[wp + k] = cw[tab[k % (3 * K + 12)]];
+    rp += rlen;
+    wp += n_e;
+  }
+  free(tb); free(cb); free(cbb); free(cw); free(tab);
+  return 0;
+}

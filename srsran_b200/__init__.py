@@ -1,0 +1,307 @@
+"""srsran_b200 -- Python host mirror of the B200 LTE turbo-decode engine's C ABI.
+
+The product is ``libsrslte_fec_b200.so`` (hand-written sm_100a CUDA behind the srsLTE FEC API, see
+include/srslte_b200/*.h).  This module only binds it with ctypes so tests and bench.py can drive it; it contains
+no arithmetic and has no CPU fallback: importing works anywhere, but creating a ``Context`` (or calling any
+srslte_* symbol) without the built library or without a GPU raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsrslte_fec_b200.so")
+
+IN_DEVICE = 1
+OUT_DEVICE = 2
+MAX_CODEBLOCKS = 32
+
+TDEC_AUTO, TDEC_GENERIC, TDEC_SSE, TDEC_SSE_WINDOW, TDEC_NEON_WINDOW, TDEC_AVX_WINDOW, TDEC_SSE8_WINDOW, TDEC_AVX8_WINDOW = range(8)
+
+CRC24A = 0x1864CFB
+CRC24B = 0x1800063
+CRC16 = 0x11021
+CRC8 = 0x19B
+
+
+class B200Error(RuntimeError):
+    pass
+
+
+class CbBatch(C.Structure):  # srslte_b200_cb_batch_t
+    _fields_ = [("K", C.c_uint32), ("nof_cb", C.c_uint32), ("nof_iterations", C.c_uint32), ("llr_bits", C.c_uint32),
+                ("llr_stride", C.c_uint32), ("input_sb", C.c_uint32), ("dec_type", C.c_uint32)]
+
+
+class Tb(C.Structure):  # srslte_b200_tb_t
+    _fields_ = [("e_bits", C.c_void_p), ("nof_e_bits", C.c_uint32), ("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32),
+                ("softbuffer", C.c_void_p), ("data", C.c_void_p),
+                ("ret", C.c_int32), ("avg_iterations", C.c_float), ("cb_crc", C.c_uint8 * MAX_CODEBLOCKS),
+                ("cb_noi", C.c_uint8 * MAX_CODEBLOCKS), ("nof_cb", C.c_uint32)]
+
+
+class CbSegm(C.Structure):  # srslte_cbsegm_t
+    _fields_ = [(n, C.c_uint32) for n in ("F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs")]
+
+
+class Crc(C.Structure):  # srslte_crc_t
+    _fields_ = [("table", C.c_uint64 * 256), ("polynom", C.c_int), ("order", C.c_int), ("crcinit", C.c_uint64),
+                ("crcmask", C.c_uint64), ("crchighbit", C.c_uint64), ("srslte_crc_out", C.c_uint32)]
+
+
+class Tdec(C.Structure):  # srslte_tdec_t
+    _fields_ = [("max_long_cb", C.c_uint32), ("b200_engine", C.c_void_p), ("force_not_sb", C.c_bool), ("dec_type", C.c_int),
+                ("current_long_cb", C.c_uint32), ("current_cbidx", C.c_int), ("n_iter", C.c_int)]
+
+
+class SoftbufferRx(C.Structure):  # srslte_softbuffer_rx_t
+    _fields_ = [("max_cb", C.c_uint32), ("b200_softbuffer", C.c_void_p), ("cb_crc", C.POINTER(C.c_bool)), ("tb_crc", C.c_bool)]
+
+
+_lib = None
+
+
+def lib():
+    """Load libsrslte_fec_b200.so; fails loudly if it has not been built (python -m srsran_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise B200Error("libsrslte_fec_b200.so is missing: build it with `python -m srsran_b200.build` "
+                            "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.srslte_b200_last_error.restype = C.c_char_p
+        L.srslte_b200_host_alloc.restype = C.c_void_p
+        L.srslte_b200_host_alloc.argtypes = [C.c_uint64]
+        L.srslte_b200_host_free.argtypes = [C.c_void_p]
+        L.srslte_b200_device_alloc.restype = C.c_void_p
+        L.srslte_b200_device_alloc.argtypes = [C.c_uint64]
+        L.srslte_b200_device_free.argtypes = [C.c_void_p]
+        L.srslte_b200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.srslte_b200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.srslte_b200_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int]
+        L.srslte_b200_ctx_destroy.argtypes = [C.c_void_p]
+        for f in ("srslte_b200_tdec_batch", "srslte_b200_tdec_batch_submit"):
+            getattr(L, f).argtypes = [C.c_void_p, C.POINTER(CbBatch), C.c_void_p, C.c_void_p, C.c_uint32]
+        for f in ("srslte_b200_decode_tbs", "srslte_b200_decode_tbs_submit"):
+            getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Tb), C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]
+        L.srslte_b200_wait.argtypes = [C.c_void_p]
+        L.srslte_b200_softbuffer_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]
+        L.srslte_b200_softbuffer_reset.argtypes = [C.c_void_p]
+        L.srslte_b200_softbuffer_free.argtypes = [C.c_void_p]
+        for f in ("srslte_b200_last_gpu_ms", "srslte_b200_last_map_ms"):
+            getattr(L, f).restype = C.c_float
+            getattr(L, f).argtypes = [C.c_void_p]
+        for f in ("srslte_b200_last_launches", "srslte_b200_last_map_launches"):
+            getattr(L, f).restype = C.c_uint32
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.srslte_crc_checksum_byte.restype = C.c_uint32
+        L.srslte_crc_checksum.restype = C.c_uint32
+        L.srslte_crc_attach_byte.restype = C.c_uint32
+        L.srslte_tdec_autoimp_get_subblocks.restype = C.c_uint32
+        L.srslte_tdec_autoimp_get_subblocks_8bit.restype = C.c_uint32
+        L.srslte_cbsegm_cbsize_isvalid.restype = C.c_bool
+        _lib = L
+    return _lib
+
+
+def _err(what, rc):
+    raise B200Error("%s failed (%d): %s" % (what, rc, lib().srslte_b200_last_error().decode()))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """numpy view over page-locked host memory (srslte_b200_host_alloc)"""
+
+    def __init__(self, shape, dtype):
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        self.ptr = lib().srslte_b200_host_alloc(max(self.nbytes, 16))
+        if not self.ptr:
+            raise B200Error("pinned host allocation failed")
+        buf = (C.c_uint8 * max(self.nbytes, 16)).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            lib().srslte_b200_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One engine = one GPU + one stream (srslte_b200_ctx_t)."""
+
+    def __init__(self, device=-1):
+        self.h = C.c_void_p()
+        rc = lib().srslte_b200_ctx_create(C.byref(self.h), device)
+        if rc:
+            _err("srslte_b200_ctx_create", rc)
+        self._keep = None
+
+    def close(self):
+        if self.h:
+            lib().srslte_b200_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- device memory helpers
+    def device_alloc(self, nbytes):
+        p = lib().srslte_b200_device_alloc(nbytes)
+        if not p:
+            raise B200Error("device allocation of %d bytes failed" % nbytes)
+        return p
+
+    def device_free(self, p):
+        lib().srslte_b200_device_free(p)
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        rc = lib().srslte_b200_memcpy_h2d(self.h, dptr, _ptr(arr), arr.nbytes)
+        if rc:
+            _err("h2d", rc)
+
+    def d2h(self, arr, dptr):
+        rc = lib().srslte_b200_memcpy_d2h(self.h, _ptr(arr), dptr, arr.nbytes)
+        if rc:
+            _err("d2h", rc)
+
+    # ---- batch of code blocks (srslte_tdec_run_all semantics)
+    def tdec_batch(self, llr, K, nof_iterations, input_sb=False, dec_type=TDEC_AUTO, out=None):
+        """llr: (nof_cb, stride) int16/int8 host array.  Returns (nof_cb, K/8) uint8."""
+        assert llr.ndim == 2 and llr.flags.c_contiguous and llr.dtype in (np.int16, np.int8)
+        ncb, stride = llr.shape
+        cfg = CbBatch(K, ncb, nof_iterations, 16 if llr.dtype == np.int16 else 8, stride, int(input_sb), dec_type)
+        if out is None:
+            out = np.zeros((ncb, K // 8), np.uint8)
+        rc = lib().srslte_b200_tdec_batch(self.h, C.byref(cfg), _ptr(llr), _ptr(out), 0)
+        if rc:
+            _err("srslte_b200_tdec_batch", rc)
+        return out
+
+    def tdec_batch_device(self, d_llr, d_out, K, ncb, stride, llr_bits, nof_iterations, input_sb=False, dec_type=TDEC_AUTO, submit_only=False):
+        cfg = CbBatch(K, ncb, nof_iterations, llr_bits, stride, int(input_sb), dec_type)
+        f = lib().srslte_b200_tdec_batch_submit if submit_only else lib().srslte_b200_tdec_batch
+        rc = f(self.h, C.byref(cfg), d_llr, d_out, IN_DEVICE | OUT_DEVICE)
+        if rc:
+            _err("srslte_b200_tdec_batch", rc)
+
+    def tdec_batch_submit(self, llr_ptr, out_ptr, K, ncb, stride, llr_bits, nof_iterations, input_sb=False, dec_type=TDEC_AUTO, flags=0):
+        cfg = CbBatch(K, ncb, nof_iterations, llr_bits, stride, int(input_sb), dec_type)
+        rc = lib().srslte_b200_tdec_batch_submit(self.h, C.byref(cfg), llr_ptr, out_ptr, flags)
+        if rc:
+            _err("srslte_b200_tdec_batch_submit", rc)
+
+    def wait(self):
+        rc = lib().srslte_b200_wait(self.h)
+        if rc:
+            _err("srslte_b200_wait", rc)
+
+    # ---- batch of transport blocks (decode_tb semantics)
+    def decode_tbs(self, tbs, llr_is_8bit, max_iterations, flags=0, submit_only=False):
+        """tbs: ctypes array of Tb (inputs filled in); results are written into it."""
+        f = lib().srslte_b200_decode_tbs_submit if submit_only else lib().srslte_b200_decode_tbs
+        rc = f(self.h, tbs, len(tbs), int(llr_is_8bit), max_iterations, flags)
+        if rc:
+            _err("srslte_b200_decode_tbs", rc)
+
+    def softbuffer_create(self, max_cb=MAX_CODEBLOCKS):
+        sb = C.c_void_p()
+        rc = lib().srslte_b200_softbuffer_create(self.h, C.byref(sb), max_cb)
+        if rc:
+            _err("srslte_b200_softbuffer_create", rc)
+        return sb
+
+    def softbuffer_reset(self, sb):
+        lib().srslte_b200_softbuffer_reset(sb)
+
+    def softbuffer_free(self, sb):
+        lib().srslte_b200_softbuffer_free(sb)
+
+    # ---- measurement hooks
+    def last_gpu_ms(self):
+        return lib().srslte_b200_last_gpu_ms(self.h)
+
+    def last_map_ms(self):
+        return lib().srslte_b200_last_map_ms(self.h)
+
+    def last_launches(self):
+        return lib().srslte_b200_last_launches(self.h)
+
+    def last_map_launches(self):
+        return lib().srslte_b200_last_map_launches(self.h)
+
+
+def make_tbs(n):
+    return (Tb * n)()
+
+
+# ------------------------------------------------------------------ drop-in srslte_* symbols (host pointers)
+def cbsegm(tbs):
+    s = CbSegm()
+    r = lib().srslte_cbsegm(C.byref(s), C.c_uint32(tbs))
+    return r, {n: getattr(s, n) for n, _ in CbSegm._fields_}
+
+
+def crc_checksum_byte(poly, order, data):
+    c = Crc()
+    assert lib().srslte_crc_init(C.byref(c), C.c_uint32(poly), C.c_int(order)) == 0
+    d = np.ascontiguousarray(data, np.uint8)
+    return lib().srslte_crc_checksum_byte(C.byref(c), _ptr(d), C.c_int(8 * len(d)))
+
+
+def crc_checksum_bits(poly, order, bits):
+    c = Crc()
+    assert lib().srslte_crc_init(C.byref(c), C.c_uint32(poly), C.c_int(order)) == 0
+    d = np.ascontiguousarray(bits, np.uint8)
+    return lib().srslte_crc_checksum(C.byref(c), _ptr(d), C.c_int(len(d)))
+
+
+def rm_turbo_rx_lut(e, out, cb_idx, rv, enable_input_tdec=True):
+    """srslte_rm_turbo_rx_lut_ / _8bit on host arrays (accumulates into `out` in place)."""
+    assert e.dtype == out.dtype and e.flags.c_contiguous and out.flags.c_contiguous
+    if e.dtype == np.int16:
+        return lib().srslte_rm_turbo_rx_lut_(_ptr(e), _ptr(out), C.c_uint32(len(e)), C.c_uint32(cb_idx), C.c_uint32(rv), C.c_bool(enable_input_tdec))
+    return lib().srslte_rm_turbo_rx_lut_8bit(_ptr(e), _ptr(out), C.c_uint32(len(e)), C.c_uint32(cb_idx), C.c_uint32(rv))
+
+
+class TurboDecoder:
+    """srslte_tdec_t through the drop-in symbols."""
+
+    def __init__(self, max_long_cb=6144, dec_type=TDEC_AUTO, force_not_sb=False):
+        self.h = Tdec()
+        rc = lib().srslte_tdec_init_manual(C.byref(self.h), C.c_uint32(max_long_cb), C.c_int(dec_type))
+        if rc:
+            raise B200Error("srslte_tdec_init_manual failed: %s" % lib().srslte_b200_last_error().decode())
+        if force_not_sb:
+            lib().srslte_tdec_force_not_sb(C.byref(self.h))
+
+    def new_cb(self, K):
+        return lib().srslte_tdec_new_cb(C.byref(self.h), C.c_uint32(K))
+
+    def iteration(self, llr, K):
+        out = np.zeros(K // 8, np.uint8)
+        if llr.dtype == np.int16:
+            lib().srslte_tdec_iteration(C.byref(self.h), _ptr(llr), _ptr(out))
+        else:
+            lib().srslte_tdec_iteration_8bit(C.byref(self.h), _ptr(llr), _ptr(out))
+        return out
+
+    def run_all(self, llr, nof_iterations, K):
+        out = np.zeros(K // 8, np.uint8)
+        f = lib().srslte_tdec_run_all if llr.dtype == np.int16 else lib().srslte_tdec_run_all_8bit
+        rc = f(C.byref(self.h), _ptr(llr), _ptr(out), C.c_uint32(nof_iterations), C.c_uint32(K))
+        return rc, out
+
+    def n_iter(self):
+        return lib().srslte_tdec_get_nof_iterations(C.byref(self.h))
+
+    def free(self):
+        lib().srslte_tdec_free(C.byref(self.h))

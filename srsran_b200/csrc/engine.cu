@@ -1,0 +1,969 @@
+// engine.cu -- host side of the B200 LTE turbo-decode engine: device tables, batch planning, kernel launches and
+// the batched C-ABI (include/srslte_b200/batch.h).  The drop-in srslte_* symbols live in api.cu on top of this.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "kernels.cuh"
+
+namespace b200 {
+
+static thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+const char* last_error() { return g_last_error.c_str(); }
+
+#define CUDA_OK(expr)                                                                                                  \
+  do {                                                                                                                 \
+    cudaError_t _e = (expr);                                                                                           \
+    if (_e != cudaSuccess) {                                                                                           \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                                                   \
+      return SRSLTE_B200_ERROR;                                                                                        \
+    }                                                                                                                  \
+  } while (0)
+
+struct Plan {
+  std::vector<CbDev> cbs;
+  std::vector<TbDev> tbs;
+  uint32_t           max_iter     = 0;
+  bool               prepare      = true;
+  uint32_t           cb_out_bytes = 0;
+};
+
+static int lanes_idx(uint32_t lanes) { return lanes == 8 ? 1 : lanes == 16 ? 2 : lanes == 32 ? 3 : 0; }
+
+// byte table of crc.c:30-46 for a 24-bit polynomial
+static void crc24_table(uint32_t poly, uint32_t* tab)
+{
+  for (uint32_t i = 0; i < 256; i++) {
+    uint32_t c = i << 16;
+    for (int j = 0; j < 8; j++)
+      c = (c & 0x800000u) ? ((c << 1) ^ poly) : (c << 1);
+    tab[i] = c & 0xffffffu;
+  }
+}
+
+template <typename T>
+int DevBuf<T>::reserve(size_t n)
+{
+  if (n <= cap)
+    return 0;
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = n + n / 4 + 64;
+  cudaError_t e = cudaMalloc((void**)&ptr, want * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return SRSLTE_B200_ERROR;
+  }
+  cap = want;
+  return 0;
+}
+template <typename T>
+void DevBuf<T>::release()
+{
+  if (ptr)
+    cudaFree(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+template <typename T>
+int PinBuf<T>::reserve(size_t n)
+{
+  if (n <= cap)
+    return 0;
+  if (ptr)
+    cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+  size_t want = n + n / 4 + 64;
+  cudaError_t e = cudaMallocHost((void**)&ptr, want * sizeof(T));
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaMallocHost: ") + cudaGetErrorString(e));
+    return SRSLTE_B200_ERROR;
+  }
+  cap = want;
+  return 0;
+}
+template <typename T>
+void PinBuf<T>::release()
+{
+  if (ptr)
+    cudaFreeHost(ptr);
+  ptr = nullptr;
+  cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------- Engine
+int Engine::create(Engine** out, int device)
+{
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device: the B200 engine has no CPU fallback");
+    return SRSLTE_B200_ERROR_NO_DEVICE;
+  }
+  if (device < 0) {
+    if (cudaGetDevice(&device) != cudaSuccess)
+      device = 0;
+  }
+  if (device >= ndev) {
+    set_error("device index out of range");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) {
+    set_error("device is not sm_100-class; this library carries sm_100a code only");
+    return SRSLTE_B200_ERROR_NO_DEVICE;
+  }
+  Engine* e  = new Engine();
+  e->device   = device;
+  e->num_sms  = prop.multiProcessorCount;
+  e->plan_ptr = new Plan();
+  CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreate(&e->ev_begin));
+  CUDA_OK(cudaEventCreate(&e->ev_end));
+  int rc = e->build_tables();
+  if (rc) {
+    delete e;
+    return rc;
+  }
+  *out = e;
+  return 0;
+}
+
+Engine::~Engine()
+{
+  cudaSetDevice(device);
+  if (stream)
+    cudaStreamSynchronize(stream);
+  for (auto ev : map_events)
+    cudaEventDestroy(ev);
+  if (ev_begin)
+    cudaEventDestroy(ev_begin);
+  if (ev_end)
+    cudaEventDestroy(ev_end);
+  d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
+  d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
+  d_sb.release(); d_genbeta.release();
+  h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
+  if (stream)
+    cudaStreamDestroy(stream);
+  delete plan_ptr;
+}
+
+int Engine::build_tables()
+{
+  // QPP tables: for every K and lane count {1, 8, 16, 32} that divides K: fwd[K] | rev[K]
+  std::vector<uint16_t> qpp;
+  for (int li = 0; li < 4; li++) {
+    const uint32_t lanes = li == 0 ? 1 : (4u << li);
+    for (int ci = 0; ci < kNofCbSizes; ci++) {
+      const uint32_t K = (uint32_t)cb_size(ci);
+      qpp_off[li][ci]  = 0xffffffffu;
+      if (lanes > 1 && (K % lanes != 0 || K / lanes < (uint32_t)kWinOverlap))
+        continue;
+      qpp_off[li][ci] = (uint32_t)qpp.size();
+      qpp.resize(qpp.size() + 2 * K);
+      qpp_tables(K, lanes, &qpp[qpp_off[li][ci]], &qpp[qpp_off[li][ci] + K]);
+    }
+  }
+  // rate de-matching base tables for layout {standard, 8, 16, 32 lanes}
+  std::vector<uint16_t> rm;
+  for (int li = 0; li < 4; li++) {
+    const uint32_t lanes = li == 0 ? 0 : (4u << li);
+    for (int ci = 0; ci < kNofCbSizes; ci++) {
+      const uint32_t K = (uint32_t)cb_size(ci);
+      rm_off[li][ci]   = 0xffffffffu;
+      if (lanes > 1 && K % lanes != 0)
+        continue;
+      RmTable t;
+      rm_table(K, lanes, &t);
+      rm_off[li][ci] = (uint32_t)rm.size();
+      for (int rv = 0; rv < 4; rv++)
+        rm_start[li][ci][rv] = t.start[rv];
+      rm.insert(rm.end(), t.base.begin(), t.base.end());
+      if (rm.size() & 1)
+        rm.push_back(0);
+    }
+  }
+  if (d_qpp.reserve(qpp.size()) || d_rm.reserve(rm.size()))
+    return SRSLTE_B200_ERROR;
+  CUDA_OK(cudaMemcpy(d_qpp.ptr, qpp.data(), qpp.size() * 2, cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(d_rm.ptr, rm.data(), rm.size() * 2, cudaMemcpyHostToDevice));
+  uint32_t tab[2][256];
+  crc24_table(kCrc24A, tab[0]);
+  crc24_table(kCrc24B, tab[1]);
+  CUDA_OK(cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab)));
+  return 0;
+}
+
+// decoder selection: AUTO dispatch of turbodecoder.c:458-508 (AVX2 build) or a manual implementation
+int Engine::select_decoder(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, DecSel* s)
+{
+  if (K > kMaxK || !cb_size_valid(K)) {
+    set_error("invalid code block size");
+    return SRSLTE_B200_ERROR;
+  }
+  s->in_sb = false;
+  switch (dec_type) {
+    case 0: // SRSLTE_TDEC_AUTO
+      if (in_bits == 16) {
+        s->lanes = auto_lanes16(K);
+        s->bits  = 16;
+      } else {
+        s->lanes = auto_lanes8(K);
+        s->bits  = s->lanes >= 16 ? 8 : 16; // K <= 800: widened to int16 (gen / sse16 rules), SURVEY 8a-4 #1
+      }
+      s->in_sb = s->lanes > 0;
+      break;
+    case 1: s->lanes = 0;  s->bits = 16; break; // GENERIC
+    case 3: s->lanes = 8;  s->bits = 16; break; // SSE_WINDOW
+    case 5: s->lanes = 16; s->bits = 16; break; // AVX_WINDOW
+    case 6: s->lanes = 16; s->bits = 8;  s->in_sb = in_bits == 8; break; // SSE8_WINDOW
+    case 7: s->lanes = 32; s->bits = 8;  s->in_sb = in_bits == 8; break; // AVX8_WINDOW
+    default:
+      set_error("decoder type not supported by the B200 engine (SSE state-parallel and NEON variants are not provided)");
+      return SRSLTE_B200_ERROR;
+  }
+  if (force_not_sb)
+    s->in_sb = false;
+  if (s->lanes && (K % s->lanes != 0 || K / s->lanes < (uint32_t)kWinOverlap)) {
+    set_error("code block size not usable with the selected windowed decoder (needs K % lanes == 0 and K/lanes >= 40)");
+    return SRSLTE_B200_ERROR;
+  }
+  return 0;
+}
+
+void Engine::fill_geometry(CbDev* d, uint32_t K, const DecSel& s)
+{
+  const int ci = cb_index(K);
+  d->K         = K;
+  d->N         = (uint8_t)s.lanes;
+  d->W         = (uint16_t)(s.lanes ? K / s.lanes : 0);
+  d->bits      = (uint8_t)s.bits;
+  d->ps        = (K + 63) / 64 * 64;
+  d->qpp_off   = qpp_off[lanes_idx(s.lanes)][ci];
+  d->sat_end   = s.bits == 8 ? (K / 32) * 32 : 0;
+  d->in_sb     = s.in_sb ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------- batch run
+struct WinClass {
+  int bits, lanes;
+};
+static const WinClass kWinClasses[4] = {{16, 8}, {16, 16}, {8, 16}, {8, 32}};
+
+template <class P, int N>
+static cudaError_t launch_map(const MapArgs& a, int n_slots, int max_w, cudaStream_t st)
+{
+  constexpr int L = 16, T = N / 2, G = 32 / T;
+  const int     S = (max_w + L - 1) / L;
+  const int     warps = (n_slots + G - 1) / G;
+  // shared memory: S checkpoints x 8 states x 4 bytes per thread
+  auto go = [&](auto nt_tag) -> cudaError_t {
+    constexpr int NT   = decltype(nt_tag)::value;
+    const size_t  smem = (size_t)S * 8 * 4 * NT;
+    auto          kern = k_map_win<P, N, L, NT>;
+    cudaError_t   e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess)
+      return e;
+    const int blocks = (warps + NT / 32 - 1) / (NT / 32);
+    kern<<<blocks, NT, smem, st>>>(a);
+    return cudaGetLastError();
+  };
+  if ((size_t)S * 32 * 256 <= 200 * 1024)
+    return go(std::integral_constant<int, 256>{});
+  if ((size_t)S * 32 * 128 <= 200 * 1024)
+    return go(std::integral_constant<int, 128>{});
+  return go(std::integral_constant<int, 64>{});
+}
+
+int Engine::run(Plan& p)
+{
+  CUDA_OK(cudaSetDevice(device));
+  const int n_cb = (int)p.cbs.size();
+  last_launches = 0;
+  last_map_launches = 0;
+  n_map_events_used = 0;
+  if (n_cb == 0)
+    return 0;
+
+  // ---- workspace layout + output slots
+  uint64_t ws_elems = 0;
+  uint32_t out_bytes = 0;
+  for (auto& d : p.cbs) {
+    d.ws_off = ws_elems;
+    ws_elems += 6ull * d.ps;
+    d.out_off = out_bytes;
+    out_bytes += d.K / 8;
+  }
+  p.cb_out_bytes = out_bytes;
+
+  // ---- work lists: [all active CBs] [dematch16] [dematch8] then one list per decoder class, grouped by K
+  std::vector<int> lists;
+  auto             add_list = [&](const std::vector<int>& v) {
+    size_t off = lists.size();
+    lists.insert(lists.end(), v.begin(), v.end());
+    return off;
+  };
+  std::vector<int> active, dm16, dm8;
+  for (int i = 0; i < n_cb; i++) {
+    if (p.cbs[i].skip)
+      continue;
+    active.push_back(i);
+    if (p.cbs[i].dematch)
+      (p.cbs[i].in_bits == 16 ? dm16 : dm8).push_back(i);
+  }
+  const size_t off_active = add_list(active), off_dm16 = add_list(dm16), off_dm8 = add_list(dm8);
+  struct ClassRun {
+    size_t off;
+    int    n_slots, max_w;
+  } cls[4];
+  for (int c = 0; c < 4; c++) {
+    std::vector<int> ids;
+    for (int i : active)
+      if (p.cbs[i].N == kWinClasses[c].lanes && p.cbs[i].bits == kWinClasses[c].bits)
+        ids.push_back(i);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p.cbs[a].K > p.cbs[b].K; });
+    const int        G = 32 / (kWinClasses[c].lanes / 2);
+    std::vector<int> w;
+    int              max_w = 0;
+    for (size_t i = 0; i < ids.size(); i++) {
+      if (i > 0 && p.cbs[ids[i]].K != p.cbs[ids[i - 1]].K)
+        while (w.size() % G)
+          w.push_back(-1); // a warp never mixes code block sizes
+      w.push_back(ids[i]);
+      max_w = std::max(max_w, (int)p.cbs[ids[i]].W);
+    }
+    cls[c].off     = add_list(w);
+    cls[c].n_slots = (int)w.size();
+    cls[c].max_w   = max_w;
+  }
+  // generic decoder: pairs of equal K
+  std::vector<int> gen_pairs;
+  uint32_t         gen_max_k = 0;
+  {
+    std::vector<int> ids;
+    for (int i : active)
+      if (p.cbs[i].N == 0)
+        ids.push_back(i);
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p.cbs[a].K > p.cbs[b].K; });
+    for (size_t i = 0; i < ids.size();) {
+      gen_max_k = std::max(gen_max_k, p.cbs[ids[i]].K);
+      if (i + 1 < ids.size() && p.cbs[ids[i + 1]].K == p.cbs[ids[i]].K) {
+        gen_pairs.push_back(ids[i]);
+        gen_pairs.push_back(ids[i + 1]);
+        i += 2;
+      } else {
+        gen_pairs.push_back(ids[i]);
+        gen_pairs.push_back(-1);
+        i += 1;
+      }
+    }
+  }
+  const size_t off_gen = add_list(gen_pairs);
+  const int    n_pairs = (int)gen_pairs.size() / 2;
+
+  // ---- device buffers
+  if (d_cbs.reserve(n_cb) || d_state.reserve(n_cb) || d_ws.reserve(ws_elems) || d_tails.reserve((size_t)n_cb * 12) ||
+      d_cbout.reserve(out_bytes + 64) || d_lists.reserve(lists.size() + 1) || d_tbs.reserve(p.tbs.size() + 1) ||
+      d_res.reserve(p.tbs.size() + 1))
+    return SRSLTE_B200_ERROR;
+  const int gen_threads = (n_pairs + 63) / 64 * 64;
+  if (n_pairs && d_genbeta.reserve((size_t)(gen_max_k + 4) * 8 * gen_threads))
+    return SRSLTE_B200_ERROR;
+
+  // descriptors travel through one pinned staging buffer
+  const size_t desc_bytes = n_cb * sizeof(CbDev) + lists.size() * sizeof(int) + p.tbs.size() * sizeof(TbDev);
+  if (h_desc.reserve(desc_bytes + 64))
+    return SRSLTE_B200_ERROR;
+  uint8_t* hp = h_desc.ptr;
+  memcpy(hp, p.cbs.data(), n_cb * sizeof(CbDev));
+  CUDA_OK(cudaMemcpyAsync(d_cbs.ptr, hp, n_cb * sizeof(CbDev), cudaMemcpyHostToDevice, stream));
+  hp += n_cb * sizeof(CbDev);
+  if (!lists.empty()) {
+    memcpy(hp, lists.data(), lists.size() * sizeof(int));
+    CUDA_OK(cudaMemcpyAsync(d_lists.ptr, hp, lists.size() * sizeof(int), cudaMemcpyHostToDevice, stream));
+    hp += lists.size() * sizeof(int);
+  }
+  if (!p.tbs.empty()) {
+    memcpy(hp, p.tbs.data(), p.tbs.size() * sizeof(TbDev));
+    CUDA_OK(cudaMemcpyAsync(d_tbs.ptr, hp, p.tbs.size() * sizeof(TbDev), cudaMemcpyHostToDevice, stream));
+  }
+
+  CUDA_OK(cudaEventRecord(ev_begin, stream));
+
+  // ---- rate de-matching (HARQ combine) straight into the decoder's lane layout
+  if (!dm16.empty()) {
+    k_dematch<int16_t><<<(int)dm16.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr);
+    last_launches++;
+  }
+  if (!dm8.empty()) {
+    k_dematch<int8_t><<<(int)dm8.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr);
+    last_launches++;
+  }
+  if (active.empty()) {
+    // nothing to decode (all code blocks cached from earlier HARQ transmissions)
+  } else if (p.prepare) {
+    k_prepare<<<(int)active.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_active, d_ws.ptr, d_tails.ptr, d_state.ptr, 1);
+    last_launches++;
+  }
+  CUDA_OK(cudaGetLastError());
+
+  // ---- half-iterations
+  for (uint32_t it = 0; it < p.max_iter && !active.empty(); it++) {
+    for (int c = 0; c < 4; c++) {
+      if (!cls[c].n_slots)
+        continue;
+      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr};
+      cudaEvent_t e0, e1;
+      if (map_event_pair(&e0, &e1))
+        return SRSLTE_B200_ERROR;
+      CUDA_OK(cudaEventRecord(e0, stream));
+      cudaError_t e;
+      switch (c) {
+        case 0: e = launch_map<Sat16, 8>(a, cls[c].n_slots, cls[c].max_w, stream); break;
+        case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break;
+        case 2: e = launch_map<Sat8, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break;
+        default: e = launch_map<Sat8, 32>(a, cls[c].n_slots, cls[c].max_w, stream); break;
+      }
+      CUDA_OK(e);
+      CUDA_OK(cudaEventRecord(e1, stream));
+      last_launches++;
+      last_map_launches++;
+    }
+    if (n_pairs) {
+      GenArgs g{d_lists.ptr + off_gen, n_pairs, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_genbeta.ptr, gen_threads};
+      k_map_gen<<<gen_threads / 64, 64, 0, stream>>>(g);
+      CUDA_OK(cudaGetLastError());
+      last_launches++;
+    }
+    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr};
+    k_decide_crc<<<((int)active.size() + 3) / 4, 128, 0, stream>>>(da);
+    CUDA_OK(cudaGetLastError());
+    last_launches++;
+  }
+
+  // ---- transport block assembly + CRC24A + HARQ bookkeeping
+  if (!p.tbs.empty()) {
+    TbArgs ta{d_tbs.ptr, (int)p.tbs.size(), d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr};
+    k_tb_finish<<<((int)p.tbs.size() + 3) / 4, 128, 0, stream>>>(ta);
+    CUDA_OK(cudaGetLastError());
+    last_launches++;
+  }
+  CUDA_OK(cudaEventRecord(ev_end, stream));
+  return 0;
+}
+
+int Engine::map_event_pair(cudaEvent_t* a, cudaEvent_t* b)
+{
+  while (map_events.size() < n_map_events_used + 2) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    map_events.push_back(e);
+  }
+  *a = map_events[n_map_events_used];
+  *b = map_events[n_map_events_used + 1];
+  n_map_events_used += 2;
+  return 0;
+}
+
+int Engine::finish_timing()
+{
+  last_gpu_ms = 0;
+  last_map_ms = 0;
+  if (cudaEventElapsedTime(&last_gpu_ms, ev_begin, ev_end) != cudaSuccess)
+    last_gpu_ms = 0;
+  for (size_t i = 0; i + 1 < n_map_events_used; i += 2) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, map_events[i], map_events[i + 1]) == cudaSuccess)
+      last_map_ms += ms;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- CB batch
+int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags)
+{
+  if (pending != PENDING_NONE) {
+    set_error("a batch is already outstanding on this context: call srslte_b200_wait first");
+    return SRSLTE_B200_ERROR;
+  }
+  if (!cfg || !llr || !out || (cfg->llr_bits != 16 && cfg->llr_bits != 8)) {
+    set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  DecSel sel;
+  int    rc = select_decoder(cfg->K, cfg->llr_bits, cfg->dec_type, cfg->input_sb == 0, &sel);
+  if (rc)
+    return rc;
+  if (cfg->input_sb && !sel.in_sb) {
+    set_error("lane-layout input requested but the selected decoder takes standard-order input for this K");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  const uint32_t n_in = sel.in_sb ? 3 * (cfg->K + kSbPad) + 12 : 3 * cfg->K + 12;
+  if (cfg->llr_stride < n_in) {
+    set_error("llr_stride smaller than one code block");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  const size_t esz = cfg->llr_bits / 8;
+  const void*  d_llr = llr;
+  if (!(flags & SRSLTE_B200_IN_DEVICE)) {
+    const size_t bytes = ((size_t)(cfg->nof_cb - 1) * cfg->llr_stride + n_in) * esz;
+    if (d_in.reserve(bytes + 64))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaMemcpyAsync(d_in.ptr, llr, bytes, cudaMemcpyHostToDevice, stream));
+    d_llr = d_in.ptr;
+  }
+  *plan_ptr  = Plan();
+  Plan& plan = *plan_ptr;
+  plan.max_iter = std::max(1u, cfg->nof_iterations);
+  plan.cbs.resize(cfg->nof_cb);
+  for (uint32_t i = 0; i < cfg->nof_cb; i++) {
+    CbDev& d = plan.cbs[i];
+    memset(&d, 0, sizeof(d));
+    fill_geometry(&d, cfg->K, sel);
+    d.max_iter = plan.max_iter;
+    d.crc_poly = 0;
+    d.in_ptr   = (void*)((const uint8_t*)d_llr + (size_t)i * cfg->llr_stride * esz);
+    d.in_bits  = (uint8_t)cfg->llr_bits;
+  }
+  rc = run(plan);
+  if (rc)
+    return rc;
+  const size_t ob = (size_t)cfg->nof_cb * (cfg->K / 8);
+  if (flags & SRSLTE_B200_OUT_DEVICE) {
+    CUDA_OK(cudaMemcpyAsync(out, d_cbout.ptr, ob, cudaMemcpyDeviceToDevice, stream));
+    cb_out_host = nullptr;
+  } else {
+    if (h_stage_out.reserve(ob + 64))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaMemcpyAsync(h_stage_out.ptr, d_cbout.ptr, ob, cudaMemcpyDeviceToHost, stream));
+    cb_out_host  = out;
+    cb_out_bytes = ob;
+  }
+  pending = PENDING_CB;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- TB batch
+struct Softbuffer {
+  Engine*  eng;
+  uint32_t max_cb;
+  int16_t* buf;   // max_cb x kSoftbufElems int16 (int8 decoders view the same memory as int8)
+  uint8_t* data;  // max_cb x 768
+  uint8_t* crc;   // max_cb flags (device)
+  std::vector<uint8_t> crc_host;
+  bool     tb_crc;
+};
+
+int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uint32_t max_iterations, uint32_t flags)
+{
+  if (pending != PENDING_NONE) {
+    set_error("a batch is already outstanding on this context: call srslte_b200_wait first");
+    return SRSLTE_B200_ERROR;
+  }
+  if (!tbs && nof_tb) {
+    set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  *plan_ptr  = Plan();
+  Plan& plan = *plan_ptr;
+  plan.max_iter = max_iterations;
+  tb_user       = tbs;
+  tb_user_n     = nof_tb;
+  tb_flags      = flags;
+  tb_map.clear();
+  const size_t esz = is8 ? 1 : 2;
+
+  // pass 1: validate, segment, size the pools
+  size_t in_bytes = 0, out_bytes = 0, scratch_cb = 0;
+  std::vector<CbSegm> segs(nof_tb);
+  for (uint32_t t = 0; t < nof_tb; t++) {
+    srslte_b200_tb_t& u = tbs[t];
+    u.ret = SRSLTE_B200_ERROR_INVALID_INPUTS;
+    u.avg_iterations = 0;
+    u.nof_cb = 0;
+    memset(u.cb_crc, 0, sizeof(u.cb_crc));
+    memset(u.cb_noi, 0, sizeof(u.cb_noi));
+    tb_map.push_back(-1);
+    if (!u.e_bits || !u.data || u.Qm == 0 || u.rv > 3)
+      continue; // decode_tb: SRSLTE_ERROR_INVALID_INPUTS (sch.c:561-568)
+    if (cb_segm(&segs[t], u.tbs)) {
+      u.ret = SRSLTE_B200_ERROR;
+      continue;
+    }
+    const CbSegm& s = segs[t];
+    if (u.tbs == 0 || s.C == 0) {
+      u.ret = 0; // sch.c:515-517
+      continue;
+    }
+    if (s.F || s.C > SRSLTE_B200_MAX_CODEBLOCKS || (u.softbuffer && s.C > ((Softbuffer*)u.softbuffer)->max_cb))
+      continue; // sch.c:519-530
+    tb_map[t] = 0;
+    in_bytes += ((size_t)u.nof_e_bits * esz + 15) / 16 * 16;
+    out_bytes += ((size_t)u.tbs / 8 + 6 + 15) / 16 * 16;
+    if (!u.softbuffer)
+      scratch_cb += s.C;
+  }
+  if (!(flags & SRSLTE_B200_IN_DEVICE)) {
+    if (d_in.reserve(in_bytes + 64))
+      return SRSLTE_B200_ERROR;
+  }
+  if (!(flags & SRSLTE_B200_OUT_DEVICE)) {
+    if (d_tbout.reserve(out_bytes + 64) || h_stage_out.reserve(out_bytes + 64))
+      return SRSLTE_B200_ERROR;
+  }
+  if (d_sb.reserve(scratch_cb * kSoftbufElems + 64))
+    return SRSLTE_B200_ERROR;
+
+  // pass 2: descriptors
+  size_t in_off = 0, out_off = 0, sb_off = 0;
+  tb_out_off.assign(nof_tb, 0);
+  for (uint32_t t = 0; t < nof_tb; t++) {
+    if (tb_map[t] < 0)
+      continue;
+    srslte_b200_tb_t& u  = tbs[t];
+    const CbSegm&     s  = segs[t];
+    Softbuffer*       sb = (Softbuffer*)u.softbuffer;
+    const uint8_t*    e_dev;
+    if (flags & SRSLTE_B200_IN_DEVICE) {
+      e_dev = (const uint8_t*)u.e_bits;
+    } else {
+      CUDA_OK(cudaMemcpyAsync(d_in.ptr + in_off, u.e_bits, (size_t)u.nof_e_bits * esz, cudaMemcpyHostToDevice, stream));
+      e_dev = d_in.ptr + in_off;
+      in_off += ((size_t)u.nof_e_bits * esz + 15) / 16 * 16;
+    }
+    TbDev td;
+    memset(&td, 0, sizeof(td));
+    td.tbs           = u.tbs;
+    td.C             = s.C;
+    td.C1            = s.C1;
+    td.first_cb      = (uint32_t)plan.cbs.size();
+    td.rlen_bytes[0] = (s.C == 1 ? s.K1 : s.K1 - 24) / 8;
+    td.rlen_bytes[1] = s.K2 ? (s.K2 - 24) / 8 : 0;
+    if (flags & SRSLTE_B200_OUT_DEVICE) {
+      td.data = u.data;
+    } else {
+      td.data       = d_tbout.ptr + out_off;
+      tb_out_off[t] = out_off;
+      out_off += ((size_t)u.tbs / 8 + 6 + 15) / 16 * 16;
+    }
+    td.hdata = sb ? sb->data : nullptr;
+    td.hcrc  = sb ? sb->crc : nullptr;
+    tb_map[t] = (int)plan.tbs.size();
+    u.nof_cb  = s.C;
+
+    const uint32_t Gp = u.nof_e_bits / u.Qm, gamma = Gp % s.C, n_e = u.Qm * (Gp / s.C);
+    for (uint32_t c = 0; c < s.C; c++) {
+      const uint32_t K = c < s.C1 ? s.K1 : s.K2;
+      DecSel         sel;
+      int            rc = select_decoder(K, is8 ? 8 : 16, 0, false, &sel);
+      if (rc)
+        return rc;
+      CbDev d;
+      memset(&d, 0, sizeof(d));
+      fill_geometry(&d, K, sel);
+      d.max_iter = max_iterations;
+      d.crc_poly = s.C > 1 ? kCrc24B : kCrc24A;
+      d.in_bits  = is8 ? 8 : 16;
+      d.dematch  = 1;
+      d.tb       = (uint32_t)plan.tbs.size();
+      d.cb_in_tb = c;
+      // e-bit split of decode_tb_cb (sch.c:391-401), strict '>' kept
+      uint32_t rp = c * n_e, n_e2 = n_e;
+      if (c > s.C - gamma) {
+        n_e2 = n_e + u.Qm;
+        rp   = (s.C - gamma) * n_e + (c - (s.C - gamma)) * n_e2;
+      }
+      d.E     = n_e2;
+      d.e_ptr = e_dev + (size_t)rp * esz;
+      // the rate-dematching layout follows the decoder the LLR width selects (rm_turbo.c:421-431, 461-471)
+      const uint32_t rm_lanes = is8 ? auto_lanes8(K) : auto_lanes16(K);
+      const int      li = lanes_idx(rm_lanes), ci = cb_index(K);
+      d.rm_off   = rm_off[li][ci];
+      d.rm_start = rm_start[li][ci][u.rv];
+      if (sb) {
+        d.in_ptr = (void*)(sb->buf + (size_t)c * kSoftbufElems);
+        d.fresh  = 0;
+        d.skip   = sb->crc_host[c] ? 1 : 0; // sch.c:385
+      } else {
+        d.in_ptr = (void*)(d_sb.ptr + sb_off);
+        sb_off += kSoftbufElems;
+        d.fresh = 1;
+      }
+      if (d.skip)
+        d.dematch = 0;
+      plan.cbs.push_back(d);
+    }
+    plan.tbs.push_back(td);
+  }
+  int rc = run(plan);
+  if (rc)
+    return rc;
+  if (!plan.tbs.empty()) {
+    if (h_res.reserve(plan.tbs.size()) || h_state.reserve(plan.cbs.size()))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaMemcpyAsync(h_res.ptr, d_res.ptr, plan.tbs.size() * sizeof(TbResult), cudaMemcpyDeviceToHost, stream));
+    CUDA_OK(cudaMemcpyAsync(h_state.ptr, d_state.ptr, plan.cbs.size() * sizeof(CbState), cudaMemcpyDeviceToHost, stream));
+    if (!(flags & SRSLTE_B200_OUT_DEVICE))
+      CUDA_OK(cudaMemcpyAsync(h_stage_out.ptr, d_tbout.ptr, out_off, cudaMemcpyDeviceToHost, stream));
+  }
+  pending = PENDING_TB;
+  return 0;
+}
+
+int Engine::wait()
+{
+  if (pending == PENDING_NONE)
+    return 0;
+  CUDA_OK(cudaSetDevice(device));
+  cudaError_t e = cudaStreamSynchronize(stream);
+  const int   kind = pending;
+  pending = PENDING_NONE;
+  if (e != cudaSuccess) {
+    set_error(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
+    return SRSLTE_B200_ERROR;
+  }
+  finish_timing();
+  Plan& plan = *plan_ptr;
+  if (kind == PENDING_CB) {
+    if (cb_out_host)
+      memcpy(cb_out_host, h_stage_out.ptr, cb_out_bytes);
+    return 0;
+  }
+  for (uint32_t t = 0; t < tb_user_n; t++) {
+    if (tb_map[t] < 0)
+      continue;
+    srslte_b200_tb_t& u  = tb_user[t];
+    const TbDev&      td = plan.tbs[tb_map[t]];
+    const TbResult&   r  = h_res.ptr[tb_map[t]];
+    Softbuffer*       sb = (Softbuffer*)u.softbuffer;
+    u.ret = r.ret;
+    uint32_t sum = 0;
+    for (uint32_t c = 0; c < td.C; c++) {
+      const CbDev&   d = plan.cbs[td.first_cb + c];
+      const CbState& s = h_state.ptr[td.first_cb + c];
+      u.cb_crc[c]      = (r.cb_crc >> c) & 1u;
+      u.cb_noi[c]      = d.skip ? 0 : (uint8_t)s.n_iter;
+      sum += u.cb_noi[c];
+      if (sb)
+        sb->crc_host[c] = u.cb_crc[c];
+    }
+    if (sb)
+      sb->tb_crc = r.cb_crc == (td.C >= 32 ? 0xffffffffu : ((1u << td.C) - 1u));
+    u.avg_iterations = (float)sum / (float)td.C; // sch.c:381,426,486
+    if (!(tb_flags & SRSLTE_B200_OUT_DEVICE))
+    {
+      // copy exactly the bytes decode_tb writes: payload + TB CRC, plus the last CB's own CRC24B when that CB was
+      // decoded in this call (a CB cached from an earlier HARQ transmission only copies its payload, sch.c:462-467)
+      const bool last_decoded = !plan.cbs[td.first_cb + td.C - 1].skip;
+      memcpy(u.data, h_stage_out.ptr + tb_out_off[t], (size_t)u.tbs / 8 + 3 + ((td.C > 1 && last_decoded) ? 3 : 0));
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- soft buffers
+int Engine::softbuffer_create(Softbuffer** out, uint32_t max_cb)
+{
+  CUDA_OK(cudaSetDevice(device));
+  if (max_cb == 0 || max_cb > SRSLTE_B200_MAX_CODEBLOCKS)
+    max_cb = SRSLTE_B200_MAX_CODEBLOCKS;
+  Softbuffer* s = new Softbuffer();
+  s->eng        = this;
+  s->max_cb     = max_cb;
+  s->tb_crc     = false;
+  s->crc_host.assign(max_cb, 0);
+  const size_t bytes = (size_t)max_cb * (kSoftbufElems * 2 + 768 + 1) + 256;
+  uint8_t*     base  = nullptr;
+  cudaError_t  e     = cudaMalloc((void**)&base, bytes);
+  if (e != cudaSuccess) {
+    delete s;
+    set_error(std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    return SRSLTE_B200_ERROR;
+  }
+  s->buf  = (int16_t*)base;
+  s->data = base + (size_t)max_cb * kSoftbufElems * 2;
+  s->crc  = s->data + (size_t)max_cb * 768;
+  CUDA_OK(cudaMemsetAsync(base, 0, bytes, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  *out = s;
+  return 0;
+}
+
+void softbuffer_reset(Softbuffer* s)
+{
+  if (!s)
+    return;
+  cudaSetDevice(s->eng->device);
+  const size_t bytes = (size_t)s->max_cb * (kSoftbufElems * 2 + 768 + 1);
+  cudaMemsetAsync(s->buf, 0, bytes, s->eng->stream);
+  cudaStreamSynchronize(s->eng->stream);
+  std::fill(s->crc_host.begin(), s->crc_host.end(), 0);
+  s->tb_crc = false;
+}
+
+void softbuffer_set_crc(Softbuffer* s, const bool* cb_crc, uint32_t n)
+{
+  if (!s || !cb_crc)
+    return;
+  for (uint32_t i = 0; i < n && i < s->max_cb; i++)
+    s->crc_host[i] = cb_crc[i] ? 1 : 0;
+}
+
+void softbuffer_free(Softbuffer* s)
+{
+  if (!s)
+    return;
+  cudaSetDevice(s->eng->device);
+  cudaFree(s->buf);
+  delete s;
+}
+
+template struct DevBuf<uint8_t>;
+template struct DevBuf<int16_t>;
+template struct DevBuf<uint16_t>;
+template struct DevBuf<int>;
+template struct DevBuf<u32>;
+template struct DevBuf<CbDev>;
+template struct DevBuf<CbState>;
+template struct DevBuf<TbDev>;
+template struct DevBuf<TbResult>;
+template struct PinBuf<uint8_t>;
+template struct PinBuf<TbResult>;
+template struct PinBuf<CbState>;
+
+} // namespace b200
+
+#include "api.inc"
+
+// ===================================================================================================== C ABI
+using b200::Engine;
+
+struct srslte_b200_ctx {
+  Engine* e;
+};
+
+extern "C" {
+
+const char* srslte_b200_last_error(void) { return b200::last_error(); }
+
+int srslte_b200_ctx_create(srslte_b200_ctx_t** ctx, int device)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  Engine* e  = nullptr;
+  int     rc = Engine::create(&e, device);
+  if (rc)
+    return rc;
+  *ctx      = new srslte_b200_ctx();
+  (*ctx)->e = e;
+  return 0;
+}
+void srslte_b200_ctx_destroy(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx)
+    return;
+  delete ctx->e;
+  delete ctx;
+}
+void* srslte_b200_host_alloc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess)
+    return nullptr;
+  return p;
+}
+void  srslte_b200_host_free(void* p) { cudaFreeHost(p); }
+void* srslte_b200_device_alloc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess)
+    return nullptr;
+  return p;
+}
+void srslte_b200_device_free(void* p) { cudaFree(p); }
+int  srslte_b200_memcpy_h2d(srslte_b200_ctx_t* ctx, void* dst, const void* src, uint64_t bytes)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  cudaSetDevice(ctx->e->device);
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->e->stream) != cudaSuccess)
+    return SRSLTE_B200_ERROR;
+  return cudaStreamSynchronize(ctx->e->stream) == cudaSuccess ? 0 : SRSLTE_B200_ERROR;
+}
+int srslte_b200_memcpy_d2h(srslte_b200_ctx_t* ctx, void* dst, const void* src, uint64_t bytes)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  cudaSetDevice(ctx->e->device);
+  if (cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->e->stream) != cudaSuccess)
+    return SRSLTE_B200_ERROR;
+  return cudaStreamSynchronize(ctx->e->stream) == cudaSuccess ? 0 : SRSLTE_B200_ERROR;
+}
+
+int srslte_b200_tdec_batch_submit(srslte_b200_ctx_t* ctx, const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->submit_cb_batch(cfg, llr, out, flags);
+}
+int srslte_b200_decode_tbs_submit(srslte_b200_ctx_t* ctx, srslte_b200_tb_t* tbs, uint32_t nof_tb, int llr_is_8bit, uint32_t max_iterations, uint32_t flags)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->submit_tb_batch(tbs, nof_tb, llr_is_8bit, max_iterations, flags);
+}
+int srslte_b200_wait(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->wait();
+}
+int srslte_b200_tdec_batch(srslte_b200_ctx_t* ctx, const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags)
+{
+  int rc = srslte_b200_tdec_batch_submit(ctx, cfg, llr, out, flags);
+  if (rc)
+    return rc;
+  return srslte_b200_wait(ctx);
+}
+int srslte_b200_decode_tbs(srslte_b200_ctx_t* ctx, srslte_b200_tb_t* tbs, uint32_t nof_tb, int llr_is_8bit, uint32_t max_iterations, uint32_t flags)
+{
+  int rc = srslte_b200_decode_tbs_submit(ctx, tbs, nof_tb, llr_is_8bit, max_iterations, flags);
+  if (rc)
+    return rc;
+  return srslte_b200_wait(ctx);
+}
+
+int srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer_t** sb, uint32_t max_cb)
+{
+  if (!ctx || !sb)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  b200::Softbuffer* s  = nullptr;
+  int               rc = ctx->e->softbuffer_create(&s, max_cb);
+  if (rc)
+    return rc;
+  *sb = (srslte_b200_softbuffer_t*)s;
+  return 0;
+}
+void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb) { b200::softbuffer_reset((b200::Softbuffer*)sb); }
+void srslte_b200_softbuffer_free(srslte_b200_softbuffer_t* sb) { b200::softbuffer_free((b200::Softbuffer*)sb); }
+
+float    srslte_b200_last_gpu_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_gpu_ms : 0.f; }
+uint32_t srslte_b200_last_launches(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_launches : 0; }
+float    srslte_b200_last_map_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_map_ms : 0.f; }
+uint32_t srslte_b200_last_map_launches(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_map_launches : 0; }
+}

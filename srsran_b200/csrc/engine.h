@@ -1,0 +1,122 @@
+// engine.h -- internal C++ interface of the B200 turbo-decode engine (one instance = one GPU + one stream).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/srslte_b200/batch.h"
+#include "lte_tables.h"
+
+namespace b200 {
+
+struct CbDev;
+struct CbState;
+struct TbDev;
+struct TbResult;
+struct Softbuffer;
+
+void        set_error(const std::string& s);
+const char* last_error();
+
+template <typename T>
+struct DevBuf { // grow-only device buffer
+  T*     ptr = nullptr;
+  size_t cap = 0;
+  int    reserve(size_t n);
+  void   release();
+};
+template <typename T>
+struct PinBuf { // grow-only pinned host buffer
+  T*     ptr = nullptr;
+  size_t cap = 0;
+  int    reserve(size_t n);
+  void   release();
+};
+
+struct DecSel {
+  uint32_t lanes; // 0 = generic decoder
+  uint32_t bits;  // arithmetic width
+  bool     in_sb; // input arrives in lane layout
+};
+
+struct Plan; // defined in engine.cu (needs the device descriptor types)
+
+class Engine
+{
+public:
+  static int create(Engine** out, int device);
+  ~Engine();
+
+  int submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags);
+  int submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uint32_t max_iterations, uint32_t flags);
+  int wait();
+
+  int softbuffer_create(Softbuffer** out, uint32_t max_cb);
+  // host-pointer compatibility operations behind the drop-in srslte_* symbols (api.inc)
+  int tdec_step(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, const void* input, uint32_t n_done, uint32_t n_more,
+                uint8_t* out);
+  int dematch_host(const void* in, void* out, uint32_t E, uint32_t cb_idx, uint32_t rv, uint32_t lanes, int bits);
+  int crc_host(const uint8_t* data, uint32_t nbytes, const uint64_t* table, int order, uint32_t poly, uint64_t* out);
+
+  // single code block sessions used by the srslte_tdec_* drop-in symbols (api.cu)
+  int select_decoder(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, DecSel* s);
+  void fill_geometry(CbDev* d, uint32_t K, const DecSel& s);
+  int run(Plan& p);
+
+  int          device  = 0;
+  int          num_sms = 0;
+  cudaStream_t stream  = nullptr;
+
+  float    last_gpu_ms       = 0;
+  float    last_map_ms       = 0;
+  uint32_t last_launches     = 0;
+  uint32_t last_map_launches = 0;
+
+  // device tables
+  DevBuf<uint16_t> d_qpp, d_rm;
+  uint32_t         qpp_off[4][kNofCbSizes];
+  uint32_t         rm_off[4][kNofCbSizes];
+  uint32_t         rm_start[4][kNofCbSizes][4];
+
+  // per-batch device state
+  DevBuf<CbDev>    d_cbs;
+  DevBuf<CbState>  d_state;
+  DevBuf<TbDev>    d_tbs;
+  DevBuf<TbResult> d_res;
+  DevBuf<int16_t>  d_ws, d_tails, d_sb;
+  DevBuf<uint8_t>  d_cbout, d_in, d_tbout;
+  DevBuf<int>      d_lists;
+  DevBuf<uint32_t> d_genbeta;
+  PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc;
+  PinBuf<TbResult> h_res;
+  PinBuf<CbState>  h_state;
+
+private:
+  Engine() {}
+  int build_tables();
+  int map_event_pair(cudaEvent_t* a, cudaEvent_t* b);
+  int finish_timing();
+
+  cudaEvent_t              ev_begin = nullptr, ev_end = nullptr;
+  std::vector<cudaEvent_t> map_events;
+  size_t                   n_map_events_used = 0;
+
+  enum { PENDING_NONE = 0, PENDING_CB, PENDING_TB };
+  int               pending = PENDING_NONE;
+  Plan*             plan_ptr = nullptr;
+  uint8_t*          cb_out_host  = nullptr;
+  size_t            cb_out_bytes = 0;
+  srslte_b200_tb_t* tb_user   = nullptr;
+  uint32_t          tb_user_n = 0;
+  uint32_t          tb_flags  = 0;
+  std::vector<int>    tb_map;
+  std::vector<size_t> tb_out_off;
+};
+
+void softbuffer_reset(Softbuffer* s);
+void softbuffer_set_crc(Softbuffer* s, const bool* cb_crc, uint32_t n);
+void softbuffer_free(Softbuffer* s);
+
+} // namespace b200

@@ -1,0 +1,631 @@
+// Device kernels of the B200 LTE turbo-decode engine (sm_100a).  Included by engine.cu only.
+//
+//   k_dematch      srslte_rm_turbo_rx_lut[_8bit]          (rm_turbo.c:397-493)        HARQ combine + scatter
+//   k_prepare      extract_input / extract_input_tail_sb  (win.h:880-923, iter.h:59-69, gen.c:238-258)
+//   k_map_win      tdec_win*_dec + half-iteration glue    (win.h:551-868, iter.h:104-128)
+//   k_map_gen      tdec_gen_dec + glue                    (turbodecoder_gen.c:58-236)
+//   k_decide_crc   tdec_*_decision_byte + srslte_crc_checksum_byte + early stop (win.h:925-993, crc.c:143-157,
+//                  sch.c:420-450)
+//   k_tb_finish    TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "map_core.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------------------------------ descriptors
+struct CbDev {
+  uint32_t K;        // code block size
+  uint16_t W;        // steps per lane (K / N); 0 for the generic decoder
+  uint8_t  N;        // sub-block lanes (0 = generic decoder)
+  uint8_t  bits;     // arithmetic of the decoder: 16 or 8
+  uint32_t ps;       // plane stride in int16 elements
+  uint32_t qpp_off;  // offset (uint16 elements) of fwd[K] | rev[K] in the QPP pool
+  uint64_t ws_off;   // offset (int16 elements) of plane 0 in the workspace
+  uint32_t max_iter; // half-iteration limit
+  uint32_t crc_poly; // early-stop CRC polynomial (24 bit), 0 = no CRC (run_all semantics)
+  uint32_t out_off;  // byte offset of this CB's K/8 decided bytes in the CB output pool
+  uint32_t sat_end;  // 8-bit glue: elements below this index use the saturating subtract
+  // input description for k_prepare / k_dematch
+  void*       in_ptr; // decoder input: HARQ soft buffer of this CB, or the caller's LLRs (device memory)
+  const void* e_ptr;  // rate-matched e-bits of this CB (device memory), dematch only
+  uint8_t  in_bits;  // 16 or 8
+  uint8_t  in_sb;    // 1: lane layout with K+32 plane stride; 0: standard 3k+s
+  uint8_t  dematch;  // 1: run k_dematch into in_ptr first
+  uint8_t  skip;     // CB already decoded in a previous HARQ transmission
+  uint32_t E;        // number of e-bits of this CB
+  uint32_t rm_off;   // offset of the base table (uint16[3K+12]) in the rm pool
+  uint32_t rm_start; // rank of the first transmitted entry for this rv
+  uint32_t tb;       // owning transport block
+  uint32_t cb_in_tb;
+  uint32_t fresh;    // soft buffer must be cleared before combining (new transmission)
+};
+
+struct CbState {
+  uint32_t n_iter;
+  uint32_t done;   // early stop hit (CRC passed)
+  uint32_t crc_ok;
+  uint32_t crc;
+};
+
+struct TbDev {
+  uint32_t tbs;
+  uint32_t C;
+  uint32_t first_cb; // index of CB 0 of this TB in the CB arrays
+  uint32_t rlen_bytes[2]; // payload bytes per CB for (K1, K2) type CBs
+  uint32_t C1;
+  uint8_t* data;       // TB output bytes (device memory), >= tbs/8 + 6
+  uint8_t* hdata;      // HARQ saved-CB area (C x 768 bytes) or nullptr
+  uint8_t* hcrc;       // HARQ cb_crc flags (C bytes) or nullptr
+};
+
+struct TbResult {
+  int32_t  ret;      // 0 ok, -1 CRC error
+  uint32_t sum_iter; // total half-iterations over the CBs processed in this call
+  uint32_t cb_crc;   // bit i = CB i passed its CRC
+  uint32_t par_rx;
+};
+
+constexpr uint32_t kSbPadDev = 32; // plane padding of the lane layout (rm_turbo.c:272)
+
+__constant__ uint32_t c_crc_tab[2][256]; // [0] = CRC24A, [1] = CRC24B byte tables (crc.c:30-46)
+
+constexpr uint32_t kCrc24A = 0x1864CFB;
+constexpr uint32_t kCrc24B = 0x1800063;
+
+// ------------------------------------------------------------------------------------------ de-rate-matching
+// One CTA per code block.  Gather form of  out[tab[i % L]] += in[i]  (wrapping): thread i < L sums its
+// repetitions i, i+L, ... and does a single read-modify-write, so no atomics are needed.
+template <typename T>
+__global__ void __launch_bounds__(256) k_dematch(const CbDev* __restrict__ cbs, const int* __restrict__ list,
+                                                 const uint16_t* __restrict__ rm_pool)
+{
+  const CbDev d = cbs[list[blockIdx.x]];
+  const uint32_t L = 3 * d.K + 12;
+  T*             out = (T*)d.in_ptr;
+  if (d.fresh) {
+    const uint32_t n = d.in_sb ? 3 * (d.K + kSbPadDev) + 12 : L;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+      out[i] = 0;
+    __syncthreads();
+  }
+  const T*        in  = (const T*)d.e_ptr;
+  const uint16_t* tab = rm_pool + d.rm_off;
+  for (uint32_t i = threadIdx.x; i < L && i < d.E; i += blockDim.x) {
+    uint32_t acc = 0;
+    for (uint32_t r = i; r < d.E; r += L)
+      acc += (uint32_t)(int32_t)in[r];
+    uint32_t pos = i + d.rm_start;
+    if (pos >= L)
+      pos -= L;
+    const uint16_t o = tab[pos];
+    out[o]           = (T)(uint32_t)((uint32_t)(int32_t)out[o] + acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ input extraction
+// One CTA per code block: decoder input -> int16 planes syst | par0 | par1 in the decoder's own layout + 12 tail
+// values {syst[3], par0[3], app2[3], par1[3]}.
+__global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list, int16_t* __restrict__ ws,
+                                                 int16_t* __restrict__ tails, CbState* __restrict__ state, int reset_state)
+{
+  const int   cb = list[blockIdx.x];
+  const CbDev d  = cbs[cb];
+  const int16_t* in16 = (const int16_t*)d.in_ptr;
+  const int8_t*  in8  = (const int8_t*)d.in_ptr;
+  auto get = [&](uint32_t i) -> int32_t {
+    int32_t v = d.in_bits == 16 ? (int32_t)in16[i] : (int32_t)in8[i];
+    // 16-bit LLRs into an 8-bit decoder are truncated like convert_16_to_8 (turbodecoder.c:451-456)
+    if (d.bits == 8 && d.in_bits == 16)
+      v = (int32_t)(int8_t)(uint8_t)v;
+    return v;
+  };
+  int16_t* p0 = ws + d.ws_off;
+  const uint32_t K = d.K, N = d.N, W = d.W;
+  if (threadIdx.x == 0 && reset_state) {
+    state[cb].n_iter = 0;
+    state[cb].done   = 0;
+    state[cb].crc_ok = 0;
+    state[cb].crc    = 0;
+  }
+  if (d.in_sb) {
+    // planes are K+32 apart (rm_turbo.c:263-277); the decoder layout equals the input layout
+    for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
+      p0[i]            = (int16_t)get(i);
+      p0[d.ps + i]     = (int16_t)get(K + kSbPadDev + i);
+      p0[2 * d.ps + i] = (int16_t)get(2 * (K + kSbPadDev) + i);
+    }
+  } else {
+    for (uint32_t n = threadIdx.x; n < K; n += blockDim.x) {
+      const uint32_t j = N ? (n % W) * N + n / W : n;
+      p0[j]            = (int16_t)get(3 * n);
+      p0[d.ps + j]     = (int16_t)get(3 * n + 1);
+      p0[2 * d.ps + j] = (int16_t)get(3 * n + 2);
+    }
+  }
+  if (threadIdx.x < 12) {
+    const uint32_t tb = d.in_sb ? 3 * (K + kSbPadDev) : 3 * K;
+    // tail order on the wire: x_K z_K x_K+1 z_K+1 x_K+2 z_K+2 | x'_K z'_K x'_K+1 z'_K+1 x'_K+2 z'_K+2
+    const uint32_t t = threadIdx.x, grp = t / 3, i = t % 3;
+    const uint32_t src = (grp == 0) ? 2 * i : (grp == 1) ? 2 * i + 1 : (grp == 2) ? 6 + 2 * i : 6 + 2 * i + 1;
+    tails[(size_t)cb * 12 + t] = (int16_t)get(tb + src);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ windowed MAP
+struct MapArgs {
+  const int*      work;    // code block per slot, -1 = padding (slots of one warp share K)
+  int             n_slots;
+  const CbDev*    cbs;
+  const CbState*  state;
+  int16_t*        ws;
+  const int16_t*  tails;
+  const uint16_t* qpp;
+};
+
+// DEC1 epilogue: a-posteriori -> post (linear), extrinsic -> app2 through the QPP permutation (iter.h:117-121)
+template <class P>
+struct EpiDec1 {
+  u32*       post;
+  const u32* apr; // nullptr at n_iter == 0
+  int16_t*   app2;
+  const u32* rev2; // rev[] viewed as pairs
+  int        T, j;
+  uint32_t   sat_end;
+  __device__ __forceinline__ void operator()(int p, u32 llr, u32) const
+  {
+    const int w = p * T + j;
+    post[w]     = llr;
+    u32 e       = llr;
+    if (apr)
+      e = P::glue_sub(llr, apr[w], (uint32_t)(2 * w) < sat_end, (uint32_t)(2 * w + 1) < sat_end);
+    const u32 r       = rev2[w];
+    app2[r & 0xffffu] = (int16_t)lo16(e);
+    app2[r >> 16]     = (int16_t)hi16(e);
+  }
+};
+
+// DEC2 epilogue: a-posteriori -> post[fwd], extrinsic (= a-posteriori - own input) -> a-priori[fwd]
+// (iter.h:107-109 fused with :127)
+template <class P>
+struct EpiDec2 {
+  int16_t*   post;
+  int16_t*   apr;
+  const u32* fwd2;
+  int        T, j;
+  uint32_t   sat_end;
+  __device__ __forceinline__ void operator()(int p, u32 llr, u32 x) const
+  {
+    const int      w  = p * T + j;
+    const u32      f  = fwd2[w];
+    const uint32_t t0 = f & 0xffffu, t1 = f >> 16;
+    const u32      a  = P::glue_sub(llr, x, t0 < sat_end, t1 < sat_end);
+    apr[t0]           = (int16_t)lo16(a);
+    apr[t1]           = (int16_t)hi16(a);
+    post[t0]          = (int16_t)lo16(llr);
+    post[t1]          = (int16_t)hi16(llr);
+  }
+};
+
+template <class P, int N, int L, int NT>
+__global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
+{
+  constexpr int T = N / 2;  // threads per code block
+  constexpr int G = 32 / T; // code blocks per warp
+  extern __shared__ u32 smem_ck[];
+
+  const int lane = threadIdx.x & 31;
+  const int slot = (blockIdx.x * (NT / 32) + (threadIdx.x >> 5)) * G + lane / T;
+  const int j    = lane % T;
+  const int cb   = slot < a.n_slots ? a.work[slot] : -1;
+  if (cb < 0)
+    return;
+  const CbDev   d  = a.cbs[cb];
+  const CbState st0 = a.state[cb];
+  if (st0.done || st0.n_iter >= d.max_iter)
+    return;
+  const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (lane / T * T));
+
+  int16_t*       ws   = a.ws + d.ws_off;
+  const int16_t* tl   = a.tails + (size_t)cb * 12;
+  const bool     dec2 = st0.n_iter & 1u;
+
+  MapWin<P, L> m;
+  m.T   = T;
+  m.W   = d.W;
+  m.j   = j;
+  m.ck  = smem_ck + threadIdx.x;
+  m.cks = NT;
+  const int16_t *tin, *tpar;
+  if (!dec2) {
+    m.in  = (const u32*)(ws);
+    m.par = (const u32*)(ws + d.ps);
+    m.apr = st0.n_iter ? (const u32*)(ws + 3 * (size_t)d.ps) : nullptr;
+    tin   = tl;
+    tpar  = tl + 3;
+  } else {
+    m.in  = (const u32*)(ws + 4 * (size_t)d.ps);
+    m.par = (const u32*)(ws + 2 * (size_t)d.ps);
+    m.apr = nullptr;
+    tin   = tl + 6;
+    tpar  = tl + 9;
+  }
+
+  u32 st[8];
+  // ---- backward: warm-up, hand the estimate to the lane below, tail for the last lane, checkpointed pass
+  m.beta_warm(st);
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const u32 nx = __shfl_down_sync(gmask, st[s], 1, T);
+    st[s]        = shift_down_lanes(st[s], nx);
+  }
+  if (j == T - 1) {
+    int32_t t[8];
+    tail_trellis<P>(tin, tpar, t);
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      st[s] = (st[s] & 0xffffu) | ((u32)(uint16_t)t[s] << 16);
+  }
+  m.beta_main(st);
+
+  // ---- forward: warm-up, hand the estimate to the lane above, known start for lane 0, output pass
+  m.alpha_warm(st);
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const u32 pv = __shfl_up_sync(gmask, st[s], 1, T);
+    st[s]        = shift_up_lanes(pv, st[s]);
+  }
+  if (j == 0) {
+    st[0] = st[0] & 0xffff0000u;
+#pragma unroll
+    for (int s = 1; s < 8; s++)
+      st[s] = (st[s] & 0xffff0000u) | (u32)(uint16_t)(-P::kInf);
+  }
+  const uint16_t* q = a.qpp + d.qpp_off;
+  if (!dec2) {
+    EpiDec1<P> e{(u32*)(ws + 5 * (size_t)d.ps), m.apr, ws + 4 * (size_t)d.ps, (const u32*)(q + d.K), T, j, d.sat_end};
+    m.alpha_main(st, e);
+  } else {
+    EpiDec2<P> e{ws + 5 * (size_t)d.ps, ws + 3 * (size_t)d.ps, (const u32*)q, T, j, d.sat_end};
+    m.alpha_main(st, e);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ generic MAP
+// tdec_gen_dec: un-windowed, wrapping int16, natural order.  One thread decodes TWO code blocks of the same K
+// (one per int16x2 half); beta lives in a global scratch interleaved by thread for coalescing.
+struct GenArgs {
+  const int*      work; // pairs: work[2t], work[2t+1] (second may be -1)
+  int             n_pairs;
+  const CbDev*    cbs;
+  const CbState*  state;
+  int16_t*        ws;
+  const int16_t*  tails;
+  const uint16_t* qpp;
+  u32*            beta;  // (K_max+4) * 8 * n_threads
+  int             n_threads;
+};
+
+__device__ __forceinline__ void gen_norm(uint32_t k, u32 (&o)[8])
+{
+  if ((k & 3u) == 0) {
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+      o[i] = p_sub_wrap(o[i], o[0]);
+    o[0] = 0;
+  }
+}
+
+struct Wrap16 { // turbodecoder_gen.c: plain C int16 arithmetic
+  static constexpr int kInf = 10000;
+  B200_HD static u32 add(u32 a, u32 b) { return p_add_wrap(a, b); }
+  B200_HD static u32 sub(u32 a, u32 b) { return p_sub_wrap(a, b); }
+  B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
+  B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  B200_HD static u32 out(u32 v) { return v; }
+};
+
+__global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
+{
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= a.n_pairs)
+    return;
+  const int cb0 = a.work[2 * t], cb1r = a.work[2 * t + 1];
+  if (cb0 < 0)
+    return;
+  const int     cb1 = cb1r < 0 ? cb0 : cb1r;
+  const CbDev   d0 = a.cbs[cb0], d1 = a.cbs[cb1];
+  const CbState s0 = a.state[cb0], s1 = a.state[cb1];
+  // both halves always run (same K); results of an inactive half are simply not stored
+  const bool act0 = !(s0.done || s0.n_iter >= d0.max_iter);
+  const bool act1 = cb1r >= 0 && !(s1.done || s1.n_iter >= d1.max_iter);
+  if (!act0 && !act1)
+    return;
+  const uint32_t K = d0.K;
+  int16_t *      w0 = a.ws + d0.ws_off, *w1 = a.ws + d1.ws_off;
+  const size_t   ps0 = d0.ps, ps1 = d1.ps;
+  const bool     dec2_0 = s0.n_iter & 1u, dec2_1 = s1.n_iter & 1u;
+  // per-half plane selection (the two blocks may be at different half-iterations)
+  const int16_t* in0  = dec2_0 ? w0 + 4 * ps0 : w0;
+  const int16_t* in1  = dec2_1 ? w1 + 4 * ps1 : w1;
+  const int16_t* pa0  = dec2_0 ? w0 + 2 * ps0 : w0 + ps0;
+  const int16_t* pa1  = dec2_1 ? w1 + 2 * ps1 : w1 + ps1;
+  const int16_t* ap0  = (!dec2_0 && s0.n_iter) ? w0 + 3 * ps0 : nullptr;
+  const int16_t* ap1  = (!dec2_1 && s1.n_iter) ? w1 + 3 * ps1 : nullptr;
+  const int16_t* tl0  = a.tails + (size_t)cb0 * 12 + (dec2_0 ? 6 : 0);
+  const int16_t* tl1  = a.tails + (size_t)cb1 * 12 + (dec2_1 ? 6 : 0);
+  auto ldx = [&](uint32_t k, u32& x, u32& y, u32& ap) {
+    int32_t x0, x1, y0, y1;
+    if (k < K) {
+      x0 = in0[k]; x1 = in1[k]; y0 = pa0[k]; y1 = pa1[k];
+    } else {
+      x0 = tl0[k - K]; x1 = tl1[k - K]; y0 = tl0[3 + k - K]; y1 = tl1[3 + k - K];
+    }
+    const int32_t a0 = (ap0 && k < K) ? ap0[k] : 0, a1 = (ap1 && k < K) ? ap1[k] : 0;
+    ap = pack16(a0, a1);
+    x  = p_add_wrap(pack16(x0, x1), ap);
+    y  = pack16(y0, y1);
+  };
+  u32*      beta = a.beta + t;
+  const int nt   = a.n_threads;
+  u32       o[8];
+  o[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++)
+    o[i] = splat16(-Wrap16::kInf);
+  for (int k = (int)K + 2; k >= 0; k--) { // map_gen_beta, gen.c:71-111
+    u32 x, y, ap;
+    ldx((uint32_t)k, x, y, ap);
+    bwd_step<Wrap16>(o, x, y, p_add_wrap(x, y));
+    if (k >= 1 && k <= (int)K) {
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        beta[((size_t)k * 8 + s) * nt] = o[s];
+    }
+    if ((uint32_t)k < K)
+      gen_norm((uint32_t)k, o);
+  }
+  o[0] = 0;
+#pragma unroll
+  for (int i = 1; i < 8; i++)
+    o[i] = splat16(-Wrap16::kInf);
+  const uint16_t* q0 = a.qpp + d0.qpp_off;
+  const uint16_t* q1 = a.qpp + d1.qpp_off;
+  for (uint32_t k = 1; k <= K; k++) { // map_gen_alpha, gen.c:135-197
+    u32 x, y, ap;
+    ldx(k - 1, x, y, ap);
+    u32 b[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      b[s] = beta[((size_t)k * 8 + s) * nt];
+    const u32 llr = fwd_step_llr<Wrap16>(o, b, x, y, p_add_wrap(x, y));
+    gen_norm(k, o);
+    const uint32_t i = k - 1;
+    // glue (iter.h:107-127), per half
+    if (act0) {
+      const int32_t l = lo16(llr);
+      if (!dec2_0) {
+        w0[5 * ps0 + i]             = (int16_t)l;
+        w0[4 * ps0 + q0[K + i]]     = (int16_t)(l - lo16(ap)); // app2[rev[i]] = ext1[i] - app1[i]
+      } else {
+        const uint32_t f = q0[i];
+        w0[5 * ps0 + f]  = (int16_t)l;
+        w0[3 * ps0 + f]  = (int16_t)(l - (int32_t)in0[i]);      // app1[fwd[i]] = ext2[i] - app2[i]
+      }
+    }
+    if (act1) {
+      const int32_t l = hi16(llr);
+      if (!dec2_1) {
+        w1[5 * ps1 + i]         = (int16_t)l;
+        w1[4 * ps1 + q1[K + i]] = (int16_t)(l - hi16(ap));
+      } else {
+        const uint32_t f = q1[i];
+        w1[5 * ps1 + f]  = (int16_t)l;
+        w1[3 * ps1 + f]  = (int16_t)(l - (int32_t)in1[i]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ decision + CRC
+__device__ __forceinline__ uint32_t crc24_mulmod(uint32_t a, uint32_t b, uint32_t poly)
+{
+  uint32_t r = 0;
+#pragma unroll 1
+  for (int i = 23; i >= 0; i--) {
+    r <<= 1;
+    if (r & 0x1000000u)
+      r ^= poly;
+    if ((b >> i) & 1u)
+      r ^= a;
+  }
+  return r & 0xffffffu;
+}
+
+// CRC24 of `nbytes` bytes produced by get_byte(i), computed by one warp: each lane runs the reference's byte
+// recurrence (crc.h:56-63) over one chunk; chunks are combined with crc(A||B) = crc(A) x^(8|B|) + crc(B) mod g.
+// The message is virtually left-padded with zero bytes to 32 equal chunks (leading zeros do not change a
+// zero-initialised CRC), so the result equals the serial recurrence bit for bit.
+template <class GetByte>
+__device__ __forceinline__ uint32_t warp_crc24(uint32_t nbytes, int tab, uint32_t poly, GetByte get_byte)
+{
+  const int      lane = threadIdx.x & 31;
+  const uint32_t cb   = (nbytes + 31) / 32, pad = 32 * cb - nbytes;
+  uint32_t       crc  = 0;
+  for (uint32_t q = 0; q < cb; q++) {
+    const uint32_t pos = lane * cb + q;
+    if (pos >= pad) {
+      const uint32_t byte = get_byte(pos - pad);
+      crc                 = ((crc << 8) ^ c_crc_tab[tab][((crc >> 16) & 0xffu) ^ byte]) & 0xffffffu;
+    }
+  }
+  // x^(8*cb) mod g
+  uint32_t xp = 1;
+  for (uint32_t q = 0; q < cb; q++)
+    xp = ((xp << 8) ^ c_crc_tab[tab][(xp >> 16) & 0xffu]) & 0xffffffu;
+#pragma unroll
+  for (int l = 1; l < 32; l <<= 1) {
+    const uint32_t other = __shfl_down_sync(0xffffffffu, crc, l); // chunk(s) to the right
+    if ((lane & (2 * l - 1)) == 0)
+      crc = crc24_mulmod(crc, xp, poly) ^ other;
+    xp = crc24_mulmod(xp, xp, poly);
+  }
+  return __shfl_sync(0xffffffffu, crc, 0);
+}
+
+struct DecideArgs {
+  const int*     list;
+  int            n;
+  const CbDev*   cbs;
+  CbState*       state;
+  const int16_t* ws;
+  uint8_t*       cb_out;
+};
+
+// one warp per code block
+__global__ void __launch_bounds__(128) k_decide_crc(const DecideArgs a)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= a.n)
+    return;
+  const int   cb = a.list[w];
+  const CbDev d  = a.cbs[cb];
+  CbState*    s  = &a.state[cb];
+  const uint32_t n_iter0 = s->n_iter, done0 = s->done;
+  if (done0 || n_iter0 >= d.max_iter)
+    return;
+  const uint32_t n_iter = n_iter0 + 1; // the half-iteration that just ran
+  const int      lane   = threadIdx.x & 31;
+  const bool     need   = d.crc_poly != 0 || n_iter >= d.max_iter;
+  uint32_t       crc    = 1;
+  if (need) {
+    const int16_t* post = a.ws + d.ws_off + 5 * (size_t)d.ps;
+    uint8_t*       out  = a.cb_out + d.out_off;
+    const uint32_t K = d.K, N = d.N, W = d.W;
+    auto get_byte = [&](uint32_t b) -> uint32_t {
+      uint32_t v = 0;
+      uint32_t n = 8 * b;
+      if (N) {
+        uint32_t lane_d = n / W, step = n - lane_d * W;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          v = (v << 1) | (post[step * N + lane_d] > 0 ? 1u : 0u);
+          if (++step == W) {
+            step = 0;
+            lane_d++;
+          }
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          v = (v << 1) | (post[n + i] > 0 ? 1u : 0u);
+      }
+      out[b] = (uint8_t)v;
+      return v;
+    };
+    const bool is_a = d.crc_poly == kCrc24A;
+    crc = warp_crc24(K / 8, is_a ? 0 : 1, is_a ? kCrc24A : kCrc24B, get_byte);
+  }
+  if (lane == 0) {
+    s->n_iter = n_iter;
+    if (d.crc_poly != 0 && crc == 0) { // early stop (sch.c:441-450); the iteration limit is checked against n_iter
+      s->crc_ok = 1;
+      s->done   = 1;
+    }
+    s->crc = crc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ TB finish
+struct TbArgs {
+  const TbDev*   tbs;
+  int            n_tb;
+  const CbDev*   cbs;
+  const CbState* state;
+  const uint8_t* cb_out;
+  TbResult*      res;
+};
+
+// one warp per transport block: assemble payload (sch.c:390,422-424,462-467), TB CRC24A (sch.c:546-552),
+// HARQ bookkeeping (sch.c:469-484)
+__global__ void __launch_bounds__(128) k_tb_finish(const TbArgs a)
+{
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= a.n_tb)
+    return;
+  const int   lane = threadIdx.x & 31;
+  const TbDev t    = a.tbs[w];
+  uint8_t*    data = t.data;
+  uint8_t*    hdat = t.hdata;
+  uint8_t*    hcrc = t.hcrc;
+  uint32_t    ok_mask = 0, sum_iter = 0;
+  // data[tbs/8 .. +2] = 0 happens before the CB loop in the reference; CB payload copies follow in CB order
+  if (lane < 3)
+    data[t.tbs / 8 + lane] = 0;
+  __syncwarp();
+  for (uint32_t c = 0; c < t.C; c++) {
+    const uint32_t cb   = t.first_cb + c;
+    const CbDev    d    = a.cbs[cb];
+    const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
+    uint8_t*       dst  = data + (size_t)c * rlen;
+    if (d.skip) {
+      for (uint32_t i = lane; i < rlen; i += 32)
+        dst[i] = hdat[(size_t)c * 768 + i];
+      ok_mask |= 1u << c;
+    } else {
+      const CbState  s   = a.state[cb];
+      const uint8_t* src = a.cb_out + d.out_off;
+      // the reference writes K/8 bytes per CB; all but the last CB's trailing CRC bytes are overwritten by the
+      // next CB's copy, so write payload only, plus the 3 CRC bytes of the last CB
+      const uint32_t nb = (c + 1 == t.C) ? d.K / 8 : rlen;
+      for (uint32_t i = lane; i < nb; i += 32)
+        dst[i] = src[i];
+      if (s.crc_ok)
+        ok_mask |= 1u << c;
+      sum_iter += s.n_iter;
+    }
+    __syncwarp();
+  }
+  const bool all_ok = ok_mask == (t.C >= 32 ? 0xffffffffu : ((1u << t.C) - 1u));
+  if (hcrc) {
+    for (uint32_t c = lane; c < t.C; c += 32)
+      hcrc[c] = (ok_mask >> c) & 1u;
+    if (!all_ok) {
+      for (uint32_t c = 0; c < t.C; c++) {
+        if (((ok_mask >> c) & 1u) && !a.cbs[t.first_cb + c].skip) {
+          const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
+          for (uint32_t i = lane; i < rlen; i += 32)
+            hdat[(size_t)c * 768 + i] = data[(size_t)c * rlen + i];
+        }
+      }
+    }
+  }
+  __syncwarp();
+  int32_t  ret    = -1;
+  uint32_t par_rx = 0;
+  if (all_ok) {
+    par_rx = warp_crc24(t.tbs / 8, 0, kCrc24A, [&](uint32_t b) -> uint32_t { return data[b]; });
+    const uint32_t o      = t.tbs / 8;
+    const uint32_t par_tx = ((uint32_t)data[o] << 16) | ((uint32_t)data[o + 1] << 8) | data[o + 2];
+    ret                   = (par_rx == par_tx && par_rx != 0) ? 0 : -1;
+  }
+  if (lane == 0) {
+    a.res[w].ret      = ret;
+    a.res[w].sum_iter = sum_iter;
+    a.res[w].cb_crc   = ok_mask;
+    a.res[w].par_rx   = par_rx;
+  }
+}
+
+// plain CRC of a byte buffer (device side of srslte_crc_checksum_byte); one warp, generic order <= 24 handled by
+// the host for orders other than 24
+__global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uint32_t poly, uint32_t* out)
+{
+  const uint32_t c = warp_crc24(nbytes, tab, poly, [&](uint32_t b) -> uint32_t { return data[b]; });
+  if (threadIdx.x == 0)
+    *out = c;
+}
+
+} // namespace b200

@@ -1,0 +1,304 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsrslte_fec_b200.so) against the CPU oracle on the
+same seeded inputs.  Bit-exact: decided bytes after every half-iteration, CRC outcomes, iteration counts,
+soft-buffer contents.  Marked gpu: run on the B200 box."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import srsran_b200 as b
+from oracle.bindings import (CRC8, CRC16, CRC24A, CRC24B, TDEC_AUTO, TDEC_AVX8_WINDOW, TDEC_AVX_WINDOW, TDEC_GENERIC, TDEC_SSE8_WINDOW,
+                             TDEC_SSE_WINDOW)
+from util import all_K, bpsk_awgn_llr, lanes8, lanes16, random_llr, std_to_sb
+
+pytestmark = pytest.mark.gpu
+
+
+# ----------------------------------------------------------------------------------------- CRC (D1)
+def test_crc_drop_in(port):
+    rng = np.random.default_rng(11)
+    for n in (1, 2, 3, 5, 31, 32, 33, 64, 100, 728, 768, 1000, 9422, 12237):
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        for poly, order in ((CRC24A, 24), (CRC24B, 24), (CRC16, 16), (CRC8, 8)):
+            assert b.crc_checksum_byte(poly, order, d) == port.crc_bytes(poly, order, d), (n, hex(poly))
+    for n in (5001, 40, 41, 47, 6144):
+        bits = rng.integers(0, 2, n, dtype=np.uint8)
+        for poly, order in ((CRC24A, 24), (CRC24B, 24), (CRC16, 16), (CRC8, 8)):
+            assert b.crc_checksum_bits(poly, order, bits) == port.crc_bits(poly, order, bits), (n, hex(poly))
+
+
+def test_crc_zero_and_codeword(port):
+    # a message followed by its own CRC checks to zero (the early-stop criterion, sch.c:441)
+    rng = np.random.default_rng(12)
+    d = rng.integers(0, 256, 765, dtype=np.uint8)
+    c = port.crc_bytes(CRC24B, 24, d)
+    full = np.concatenate([d, np.array([(c >> 16) & 255, (c >> 8) & 255, c & 255], np.uint8)])
+    assert b.crc_checksum_byte(CRC24B, 24, full) == 0
+    assert b.crc_checksum_byte(CRC24A, 24, np.zeros(100, np.uint8)) == 0
+
+
+# ----------------------------------------------------------------------------------------- rate de-matching (B1)
+@pytest.mark.parametrize("K,E", [(40, 132), (40, 500), (504, 1000), (1024, 1000), (5824, 6918), (5824, 6924), (6144, 7200), (6144, 18444), (6144, 30000),
+                                 (2048, 6156), (2112, 3000), (816, 2460)])
+def test_rm_rx_lut(port, K, E):
+    rng = np.random.default_rng(K + E)
+    ci = port.cbindex(K)
+    for rv in range(4):
+        e = random_llr(rng, E, 32767, np.int16)
+        for sb in (True, False):
+            a = random_llr(rng, 18600, 32767, np.int16)
+            want = a.copy()
+            port.rm_rx16(e, want, K, rv, lanes16(K) if sb else 0)
+            assert b.rm_turbo_rx_lut(e, a, ci, rv, sb) == 0
+            assert (a == want).all(), (K, E, rv, sb)
+        e8 = random_llr(rng, E, 127, np.int8)
+        a = random_llr(rng, 18600 * 2, 127, np.int8)
+        want = a.copy()
+        port.rm_rx8(e8, want, K, rv, lanes8(K))
+        assert b.rm_turbo_rx_lut(e8, a, ci, rv) == 0
+        assert (a == want).all(), (K, E, rv, "int8")
+
+
+def test_rm_rx_lut_invalid():
+    e = np.zeros(100, np.int16)
+    o = np.zeros(18600, np.int16)
+    assert b.rm_turbo_rx_lut(e, o, 188, 0) == -2
+    assert b.rm_turbo_rx_lut(e, o, 0, 4) == -2
+
+
+# ----------------------------------------------------------------------------------------- decoder, per half-iteration (C1-C6)
+def _tdec_case(port, K, dtype, amp, nit, dec_type=TDEC_AUTO, force_not_sb=False, seed=0):
+    rng = np.random.default_rng(seed + K)
+    bits = 16 if dtype == np.int16 else 8
+    if dec_type == TDEC_AUTO:
+        N = lanes16(K) if bits == 16 else lanes8(K)
+        sb_in = N > 0 and not force_not_sb
+    else:
+        sb_in = False
+    n = 3 * (K + 32) + 12 if sb_in else 3 * K + 12
+    llr = random_llr(rng, n, amp, dtype)
+    hp = port.tdec_new(dec_type, force_not_sb)
+    assert port.tdec_new_cb(hp, K) == 0
+    td = b.TurboDecoder(6144, dec_type, force_not_sb)
+    assert td.new_cb(K) == 0
+    for it in range(nit):
+        want = port.tdec_iteration(hp, llr, K)
+        got = td.iteration(llr, K)
+        assert td.n_iter() == it + 1
+        assert (got == want).all(), "K=%d bits=%d amp=%d dec=%d half-iteration %d: %d byte mismatches" % (K, bits, amp, dec_type, it, int((got != want).sum()))
+    td.free()
+    port.tdec_del(hp)
+
+
+@pytest.mark.parametrize("K,amp,nit", [(6144, 300, 4), (6144, 30000, 6), (816, 5000, 6), (512, 20000, 6), (408, 300, 5), (800, 32767, 4), (5824, 2000, 10),
+                                       (1008, 700, 4), (2048, 100, 4), (2112, 32767, 3), (4160, 900, 5)])
+def test_tdec_int16_windowed(port, K, amp, nit):
+    _tdec_case(port, K, np.int16, amp, nit)
+
+
+@pytest.mark.parametrize("K,amp,nit", [(6144, 60, 6), (6144, 127, 6), (2112, 100, 5), (816, 127, 6), (2048, 90, 6), (1008, 127, 4), (5824, 50, 10), (3072, 30, 4)])
+def test_tdec_int8_windowed(port, K, amp, nit):
+    _tdec_case(port, K, np.int8, amp, nit)
+
+
+@pytest.mark.parametrize("K,amp,nit", [(40, 100, 6), (400, 300, 6), (400, 20000, 6), (200, 32767, 5), (104, 1000, 10), (48, 50, 3)])
+def test_tdec_generic(port, K, amp, nit):
+    _tdec_case(port, K, np.int16, amp, nit)
+
+
+@pytest.mark.parametrize("K,amp,nit", [(40, 100, 4), (400, 127, 6), (408, 127, 4), (512, 60, 6), (800, 127, 5)])
+def test_tdec_int8_small_K(port, K, amp, nit):
+    # int8 input, K <= 800: widened to int16 then generic / 8-lane rules (408..800 is the documented deviation:
+    # full conversion instead of the reference's uninitialised read)
+    _tdec_case(port, K, np.int8, amp, nit)
+
+
+@pytest.mark.parametrize("K,dec,fnsb", [(6144, TDEC_AVX_WINDOW, True), (504, TDEC_SSE_WINDOW, True), (504, TDEC_GENERIC, True), (6144, TDEC_GENERIC, False),
+                                        (1024, TDEC_SSE_WINDOW, False), (6144, TDEC_SSE_WINDOW, True), (6144, TDEC_AVX8_WINDOW, True),
+                                        (1024, TDEC_SSE8_WINDOW, True), (6144, TDEC_SSE8_WINDOW, True)])
+def test_tdec_manual(port, K, dec, fnsb):
+    _tdec_case(port, K, np.int16, 400, 4, dec, fnsb)
+
+
+@pytest.mark.parametrize("K", [504, 6144, 40, 2048])
+def test_tdec_auto_force_not_sb(port, K):
+    _tdec_case(port, K, np.int16, 400, 4, TDEC_AUTO, True)
+
+
+def test_tdec_errors():
+    td = b.TurboDecoder(6144)
+    assert td.new_cb(6145) == -1
+    assert td.new_cb(41) == -1  # not an LTE size (stricter than the reference)
+    td.free()
+    td = b.TurboDecoder(1024)
+    assert td.new_cb(2048) == -1
+    # iteration without new_cb is a silent no-op (turbodecoder.c:530)
+    out = td.iteration(np.zeros(3 * 1024 + 12 + 96, np.int16), 1024)
+    assert td.n_iter() == 0 and not out.any()
+    td.free()
+    with pytest.raises(b.B200Error):
+        b.TurboDecoder(6144, 2)  # SRSLTE_TDEC_SSE (state-parallel) is not provided
+
+
+# ----------------------------------------------------------------------------------------- all 188 sizes (config C3)
+def test_tdec_all_sizes_batch(port, ctx):
+    rng = np.random.default_rng(188)
+    for dtype, amp in ((np.int16, 600), (np.int8, 40)):
+        for K in all_K():
+            bits = rng.integers(0, 2, K, dtype=np.uint8)
+            cw = port.tcod_encode(bits)
+            llr = bpsk_awgn_llr(rng, cw, amp / 4, 0.8, dtype)
+            N = lanes16(K) if dtype == np.int16 else lanes8(K)
+            x = std_to_sb(llr, K, N) if N else llr
+            batch = np.ascontiguousarray(np.stack([x, x]))
+            got = ctx.tdec_batch(batch, K, 3, input_sb=N > 0)
+            hp = port.tdec_new(TDEC_AUTO, False)
+            rc, want = port.tdec_run_all(hp, x, 3, K)
+            port.tdec_del(hp)
+            assert rc == 0
+            assert (got[0] == want).all() and (got[1] == want).all(), (K, dtype)
+
+
+# ----------------------------------------------------------------------------------------- batched code blocks (config C1)
+def test_cb_batch_c1(port, ctx):
+    rng = np.random.default_rng(61)
+    K, ncb = 6144, 150
+    llr = np.zeros((ncb, 3 * K + 12), np.int16)
+    data = []
+    for i in range(ncb):
+        bits = rng.integers(0, 2, K, dtype=np.uint8)
+        data.append(bits)
+        llr[i] = bpsk_awgn_llr(rng, port.tcod_encode(bits), 100, 0.9 + 0.4 * (i % 5) / 4, np.int16)
+    got = ctx.tdec_batch(llr, K, 4, input_sb=False)
+    hp = port.tdec_new(TDEC_AUTO, True)
+    n_ok = 0
+    for i in range(ncb):
+        rc, want = port.tdec_run_all(hp, llr[i], 4, K)
+        assert (got[i] == want).all(), i
+        n_ok += int((np.unpackbits(want) == data[i]).all())
+    port.tdec_del(hp)
+    assert n_ok > ncb // 4  # the synthetic SNR range really decodes a good share of blocks
+    assert ctx.last_launches() > 0 and ctx.last_map_launches() == 4
+
+
+def test_cb_batch_saturating_and_int8(port, ctx):
+    rng = np.random.default_rng(62)
+    for K, dtype, amp, nit in ((6144, np.int16, 32767, 6), (6144, np.int8, 127, 5), (1024, np.int16, 20000, 4), (504, np.int16, 32767, 4), (120, np.int16, 32767, 5)):
+        N = lanes16(K) if dtype == np.int16 else lanes8(K)
+        n = 3 * (K + 32) + 12 if N else 3 * K + 12
+        llr = np.stack([random_llr(rng, n, amp, dtype) for _ in range(21)])
+        got = ctx.tdec_batch(llr, K, nit, input_sb=N > 0)
+        hp = port.tdec_new(TDEC_AUTO, False)
+        for i in range(llr.shape[0]):
+            rc, want = port.tdec_run_all(hp, llr[i], nit, K)
+            assert (got[i] == want).all(), (K, dtype, i)
+        port.tdec_del(hp)
+
+
+# ----------------------------------------------------------------------------------------- transport blocks (A1, A2, E2; configs C2, C4)
+def _tb_inputs(port, rng, tbs, Qm, G, rv, dtype, amp, sigma, data=None):
+    if data is None:
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    e = port.encode_tb(tbs, Qm, rv, G, data)
+    return data, bpsk_awgn_llr(rng, e, amp, sigma, dtype)
+
+
+def _decode_both(port, ctx, tbs, Qm, rv, llr, max_iter, sb_port, sb_gpu):
+    rc_p, d_p, nit_p, avg_p, crc_p = port.decode_tb(sb_port, tbs, Qm, rv, llr, max_iter)
+    t = b.make_tbs(1)
+    out = np.zeros(tbs // 8 + 6 + 16, np.uint8)
+    t[0].e_bits = llr.ctypes.data
+    t[0].nof_e_bits = len(llr)
+    t[0].tbs = tbs
+    t[0].Qm = Qm
+    t[0].rv = rv
+    t[0].softbuffer = sb_gpu
+    t[0].data = out.ctypes.data
+    ctx.decode_tbs(t, llr.dtype == np.int8, max_iter)
+    C_ = t[0].nof_cb
+    n = tbs // 8 + (3 if C_ == 1 else 6)
+    assert t[0].ret == rc_p
+    assert (out[:n] == d_p[:n]).all()
+    assert list(t[0].cb_crc[:C_]) == crc_p[:C_].tolist()
+    assert list(t[0].cb_noi[:C_]) == nit_p[:C_].tolist()
+    assert abs(t[0].avg_iterations - avg_p) < 1e-6
+    return rc_p, avg_p
+
+
+@pytest.mark.parametrize("tbs,Qm,G,dtype,amp,sigma,max_iter", [
+    (75376, 6, 90000, np.int16, 100, 0.0, 8), (75376, 6, 90000, np.int16, 100, 0.46, 8), (75376, 6, 90000, np.int16, 100, 0.52, 8), (75376, 6, 90000, np.int16, 100, 3.0, 4),
+    (97896, 8, 115200, np.int8, 20, 0.42, 8), (6120, 2, 14400, np.int16, 50, 0.9, 8), (1000, 2, 2880, np.int16, 50, 0.9, 8),
+    (296, 2, 1200, np.int8, 30, 0.5, 8), (15264, 4, 20000, np.int16, 200, 0.55, 10), (40, 2, 480, np.int16, 80, 0.5, 4),
+    (2216, 2, 7000, np.int8, 30, 0.6, 6)])
+def test_decode_tb(port, ctx, tbs, Qm, G, dtype, amp, sigma, max_iter):
+    rng = np.random.default_rng(tbs + G)
+    sbp = port.softbuffer_new()
+    data, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, dtype, amp, sigma)
+    _decode_both(port, ctx, tbs, Qm, 0, llr, max_iter, sbp, None)
+    port.softbuffer_del(sbp)
+
+
+def test_decode_tb_harq(port, ctx):
+    """HARQ: failed first transmission, soft-combining of retransmissions, CRC-ok code blocks skipped (sch.c:385,462-484)"""
+    rng = np.random.default_rng(77)
+    for tbs, Qm, G, dtype, amp, sigma in ((75376, 6, 90000, np.int16, 100, 0.95), (97896, 8, 115200, np.int8, 20, 0.8), (15264, 4, 20000, np.int16, 200, 0.75)):
+        sbp = port.softbuffer_new()
+        sbg = ctx.softbuffer_create()
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        rcs = []
+        for rv in (0, 2, 3, 1):
+            _, llr = _tb_inputs(port, rng, tbs, Qm, G, rv, dtype, amp, sigma, data)
+            rc, avg = _decode_both(port, ctx, tbs, Qm, rv, llr, 8, sbp, sbg)
+            rcs.append(rc)
+            if rc == 0:
+                break
+        assert rcs[0] == -1 and rcs[-1] == 0, rcs  # the case really exercises combining
+        # reset + new data on the same soft buffer
+        port.softbuffer_reset(sbp)
+        ctx.softbuffer_reset(sbg)
+        _, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, dtype, amp, 0.3)
+        rc, _ = _decode_both(port, ctx, tbs, Qm, 0, llr, 8, sbp, sbg)
+        assert rc == 0
+        port.softbuffer_del(sbp)
+        ctx.softbuffer_free(sbg)
+
+
+def test_decode_tbs_batch_mixed(port, ctx):
+    """many TBs of different sizes in one launch, mixed outcomes and iteration counts"""
+    rng = np.random.default_rng(99)
+    cases = [(75376, 6, 90000, 0.42), (75376, 6, 90000, 0.5), (6120, 2, 14400, 0.9), (1000, 2, 2880, 0.9), (15264, 4, 20000, 0.5), (40, 2, 480, 0.5),
+             (75376, 6, 90000, 2.0), (2216, 2, 7000, 0.8), (31704, 6, 40000, 0.5), (4584, 4, 9000, 0.6)] * 2
+    n = len(cases)
+    t = b.make_tbs(n)
+    llrs, outs = [], []
+    for i, (tbs, Qm, G, sigma) in enumerate(cases):
+        _, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, np.int16, 100, sigma)
+        out = np.zeros(tbs // 8 + 22, np.uint8)
+        llrs.append(llr)
+        outs.append(out)
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = llr.ctypes.data, len(llr), tbs, Qm, 0, out.ctypes.data
+    ctx.decode_tbs(t, False, 8)
+    rets = []
+    for i, (tbs, Qm, G, sigma) in enumerate(cases):
+        sbp = port.softbuffer_new()
+        rc, d, nit, avg, crc = port.decode_tb(sbp, tbs, Qm, 0, llrs[i], 8)
+        port.softbuffer_del(sbp)
+        C_ = t[i].nof_cb
+        nb = tbs // 8 + (3 if C_ == 1 else 6)
+        assert t[i].ret == rc and (outs[i][:nb] == d[:nb]).all(), i
+        assert list(t[i].cb_noi[:C_]) == nit[:C_].tolist(), i
+        assert abs(t[i].avg_iterations - avg) < 1e-6
+        rets.append(rc)
+    assert 0 in rets and -1 in rets
+
+
+def test_decode_tb_invalid(ctx):
+    t = b.make_tbs(3)
+    out = np.zeros(20000, np.uint8)
+    llr = np.zeros(90000, np.int16)
+    for i, tbs in enumerate((75376, 0, 75000)):  # ok-shaped, empty, filler bits needed (F > 0)
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = llr.ctypes.data, 90000, tbs, 6, 0, out.ctypes.data
+    ctx.decode_tbs(t, False, 2)
+    assert t[0].ret == -1       # all-zero LLRs: CRC fails
+    assert t[1].ret == 0        # tbs == 0 -> SRSLTE_SUCCESS (sch.c:515)
+    assert t[2].ret == -2       # filler bits not supported (sch.c:519-522)
