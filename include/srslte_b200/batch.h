@@ -110,6 +110,27 @@ SRSLTE_B200_API uint32_t srslte_b200_last_launches(srslte_b200_ctx_t* ctx);
 SRSLTE_B200_API float    srslte_b200_last_map_ms(srslte_b200_ctx_t* ctx);
 SRSLTE_B200_API uint32_t srslte_b200_last_map_launches(srslte_b200_ctx_t* ctx);
 
+/* options: "fast16" (default 1): int16 windowed decoders first try the native packed-instruction path (VIADD.16x2 /
+ * VIMNMX.S16x2 / VIADDMNMX.S16x2) under a range monitor and replay with the exact saturating arithmetic whenever
+ * a saturation cannot be ruled out; 0 forces the exact arithmetic everywhere.  Results are identical either way. */
+SRSLTE_B200_API int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value);
+/* statistics of the last completed batch: (code block x half-iteration) units run, and how many were replayed */
+SRSLTE_B200_API uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API uint32_t srslte_b200_last_replayed(srslte_b200_ctx_t* ctx);
+
+/* host-side tables as the engine uploads them: QPP permutation (tc_interl_lte.c:69-109) in the index space of a
+ * `lanes`-lane layout (lanes <= 1: natural order), and the rate de-matching table of one rv
+ * (rm_turbo.c:177-251 [+ :263-277 when lanes > 0]): table[i] = buffer position of the i-th received e-bit */
+SRSLTE_B200_API int srslte_b200_qpp_table(uint32_t K, uint32_t lanes, uint16_t* fwd, uint16_t* rev);
+SRSLTE_B200_API int srslte_b200_rm_table(uint32_t K, uint32_t rv, uint32_t lanes, uint16_t* table);
+
+/* CUDA-event stopwatch on the engine's own stream (torch.cuda.Event would only see torch's stream) */
+SRSLTE_B200_API int   srslte_b200_timer_start(srslte_b200_ctx_t* ctx);
+SRSLTE_B200_API float srslte_b200_timer_stop_ms(srslte_b200_ctx_t* ctx);
+/* integer-ALU roofline probe: packed int16x2 operations per second sustained by the instruction mix of the MAP
+ * kernel (mode 0: wrapping add / max / fused add-max; mode 1: with the saturating-add emulation) */
+SRSLTE_B200_API double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int mode);
+
 #ifdef __cplusplus
 }
 #endif

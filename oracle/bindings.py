@@ -364,16 +364,16 @@ class Ref:
         return d
 
     # CPU baseline runners
-    def bench_c1(self, nthreads, llr, K, nof_iter, layout_sb=False):
+    def bench_c1(self, nthreads, llr, K, nof_iter, layout_sb=False, repeat=1):
         """llr: (ncb, stride) int16/int8.  Returns (seconds, out bytes (ncb, K/8))."""
         assert llr.ndim == 2 and llr.flags.c_contiguous
         ncb, stride = llr.shape
         out = np.zeros((ncb, K // 8), np.uint8)
         t = self.L.ref_bench_c1(C.c_int(nthreads), _p(llr), C.c_uint32(stride), C.c_uint32(ncb), C.c_uint32(K), C.c_uint32(nof_iter),
-                                C.c_int(int(llr.dtype == np.int8)), C.c_int(int(layout_sb)), _p(out))
+                                C.c_int(int(llr.dtype == np.int8)), C.c_int(int(layout_sb)), _p(out), C.c_uint32(repeat))
         return t, out
 
-    def bench_tb(self, nthreads, llr, tbs, Qm, rv, max_iter):
+    def bench_tb(self, nthreads, llr, tbs, Qm, rv, max_iter, repeat=1):
         """llr: (ntb, G) int16/int8.  Returns (seconds, data (ntb, stride), rc (ntb,), avg_iter (ntb,))."""
         assert llr.ndim == 2 and llr.flags.c_contiguous
         ntb, G = llr.shape
@@ -382,5 +382,6 @@ class Ref:
         rc = np.zeros(ntb, np.int32)
         avg = np.zeros(ntb, np.float32)
         t = self.L.ref_bench_tb(C.c_int(nthreads), _p(llr), C.c_uint32(ntb), C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(G), C.c_uint32(rv),
-                                C.c_uint32(max_iter), C.c_int(int(llr.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg))
+                                C.c_uint32(max_iter), C.c_int(int(llr.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg),
+                                C.c_uint32(repeat))
         return t, out, rc, avg

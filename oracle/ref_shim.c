@@ -132,7 +132,7 @@ int ref_tcod_encode(uint8_t* bits, uint8_t* out_bits, uint32_t K)
   if (srslte_tcod_init(&t, 6144))
     return -1;
   int r = srslte_tcod_encode(&t, bits, out_bits, K);
-  srslte_tcod_free(&t);
+  free(t.temp); /* srslte_tcod_free() would also free the process-global interleaver tables other objects use */
   return r;
 }
 
@@ -342,7 +342,7 @@ int ref_sch_get_softbuffer(void* ss, uint32_t cb, int16_t* dst, uint32_t n)
 /* --------------------------------------------- CPU baseline runners (pthreads) */
 typedef struct {
   int       tid, nthreads;
-  uint32_t  ncb, K, nof_iter;
+  uint32_t  ncb, K, nof_iter, repeat;
   int       is8, layout_sb;
   void*     llr; /* ncb x stride elements */
   uint32_t  stride;
@@ -351,21 +351,23 @@ typedef struct {
   double    t0, t1;
 } c1_arg_t;
 
+static ref_tdec_t* g_c1_dec[256][2];
 static void* c1_worker(void* p)
 {
   c1_arg_t*   a = p;
-  ref_tdec_t* h = ref_tdec_new(6144, SRSLTE_TDEC_AUTO, a->layout_sb ? 0 : 1);
+  ref_tdec_t* h = g_c1_dec[a->tid][a->layout_sb ? 1 : 0];
   pthread_barrier_wait(a->bar);
   a->t0 = now_s();
-  for (uint32_t cb = a->tid; cb < a->ncb; cb += a->nthreads) {
-    uint8_t* o = a->out + (size_t)cb * (a->K / 8);
-    if (a->is8)
-      srslte_tdec_run_all_8bit(&h->td, (int8_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
-    else
-      srslte_tdec_run_all(&h->td, (int16_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
+  for (uint32_t r = 0; r < a->repeat; r++) {
+    for (uint32_t cb = a->tid; cb < a->ncb; cb += a->nthreads) {
+      uint8_t* o = a->out + (size_t)cb * (a->K / 8);
+      if (a->is8)
+        srslte_tdec_run_all_8bit(&h->td, (int8_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
+      else
+        srslte_tdec_run_all(&h->td, (int16_t*)a->llr + (size_t)cb * a->stride, o, a->nof_iter, a->K);
+    }
   }
   a->t1 = now_s();
-  ref_tdec_del(h);
   return NULL;
 }
 
@@ -379,14 +381,20 @@ double ref_bench_c1(int       nthreads,
                     uint32_t  nof_iter,
                     int       is8,
                     int       layout_sb,
-                    uint8_t*  out)
+                    uint8_t*  out,
+                    uint32_t  repeat)
 {
+  if (nthreads > 256)
+    nthreads = 256;
+  for (int t = 0; t < nthreads; t++)
+    if (!g_c1_dec[t][layout_sb ? 1 : 0])
+      g_c1_dec[t][layout_sb ? 1 : 0] = ref_tdec_new(6144, SRSLTE_TDEC_AUTO, layout_sb ? 0 : 1);
   pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
   c1_arg_t*         a  = calloc(nthreads, sizeof(c1_arg_t));
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, NULL, nthreads);
   for (int t = 0; t < nthreads; t++) {
-    a[t] = (c1_arg_t){t, nthreads, ncb, K, nof_iter, is8, layout_sb, llr, stride, out, &bar, 0, 0};
+    a[t] = (c1_arg_t){t, nthreads, ncb, K, nof_iter, repeat ? repeat : 1, is8, layout_sb, llr, stride, out, &bar, 0, 0};
     pthread_create(&th[t], NULL, c1_worker, &a[t]);
   }
   double t0 = 1e300, t1 = 0;
@@ -405,7 +413,7 @@ double ref_bench_c1(int       nthreads,
 
 typedef struct {
   int       tid, nthreads;
-  uint32_t  ntb, tbs, Qm, G, rv, max_iter;
+  uint32_t  ntb, tbs, Qm, G, rv, max_iter, repeat;
   int       is8;
   void*     llr; /* ntb x G */
   uint8_t*  out; /* ntb x out_stride */
@@ -416,27 +424,41 @@ typedef struct {
   double    t0, t1;
 } tb_arg_t;
 
+/* the reference keeps process-global tables behind plain bools (rm_turbo.c:81, turbocoder.c table_initiated), so
+ * srslte_sch_init() must not run concurrently: worker objects are created once, sequentially, and cached */
+#define MAX_WORKERS 256
+static ref_sch_t* g_workers[MAX_WORKERS];
+static int        g_workers_is8[MAX_WORKERS];
+static ref_sch_t* get_worker(int tid, int is8, uint32_t max_iter)
+{
+  if (!g_workers[tid]) {
+    ref_sch_t* s = calloc(1, sizeof(ref_sch_t));
+    srslte_sch_init(&s->sch);
+    srslte_softbuffer_rx_init(&s->rx, 100);
+    g_workers[tid] = s;
+  }
+  g_workers[tid]->sch.llr_is_8bit = is8 ? true : false;
+  srslte_sch_set_max_noi(&g_workers[tid]->sch, max_iter);
+  return g_workers[tid];
+}
+
 static void* tb_worker(void* p)
 {
   tb_arg_t*  a = p;
-  ref_sch_t* s = calloc(1, sizeof(ref_sch_t));
-  srslte_sch_init(&s->sch);
-  s->sch.llr_is_8bit = a->is8 ? true : false;
-  srslte_sch_set_max_noi(&s->sch, a->max_iter);
-  srslte_softbuffer_rx_init(&s->rx, 100);
+  ref_sch_t* s = g_workers[a->tid];
   pthread_barrier_wait(a->bar);
   a->t0 = now_s();
-  for (uint32_t tb = a->tid; tb < a->ntb; tb += a->nthreads) {
-    srslte_softbuffer_rx_reset_tbs(&s->rx, a->tbs);
-    void* llr = a->is8 ? (void*)((int8_t*)a->llr + (size_t)tb * a->G) : (void*)((int16_t*)a->llr + (size_t)tb * a->G);
-    srslte_pdsch_cfg_t cfg;
-    fill_cfg(s, &cfg, a->tbs, a->Qm, a->G, a->rv, 0);
-    a->rc[tb]       = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, a->out + (size_t)tb * a->out_stride, 0, 1);
-    a->avg_iter[tb] = srslte_sch_last_noi(&s->sch);
+  for (uint32_t r = 0; r < a->repeat; r++) {
+    for (uint32_t tb = a->tid; tb < a->ntb; tb += a->nthreads) {
+      srslte_softbuffer_rx_reset_tbs(&s->rx, a->tbs);
+      void* llr = a->is8 ? (void*)((int8_t*)a->llr + (size_t)tb * a->G) : (void*)((int16_t*)a->llr + (size_t)tb * a->G);
+      srslte_pdsch_cfg_t cfg;
+      fill_cfg(s, &cfg, a->tbs, a->Qm, a->G, a->rv, 0);
+      a->rc[tb]       = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, a->out + (size_t)tb * a->out_stride, 0, 1);
+      a->avg_iter[tb] = srslte_sch_last_noi(&s->sch);
+    }
   }
   a->t1 = now_s();
-  srslte_softbuffer_rx_free(&s->rx);
-  /* do not call srslte_sch_free: it frees the process-global rm tables other threads still use */
   return NULL;
 }
 
@@ -454,15 +476,20 @@ double ref_bench_tb(int      nthreads,
                     uint8_t* out,
                     uint32_t out_stride,
                     int*     rc,
-                    float*   avg_iter)
+                    float*   avg_iter,
+                    uint32_t repeat)
 {
   srslte_rm_turbo_gentables();
+  if (nthreads > MAX_WORKERS)
+    nthreads = MAX_WORKERS;
+  for (int t = 0; t < nthreads; t++)
+    get_worker(t, is8, max_iter);
   pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
   tb_arg_t*         a  = calloc(nthreads, sizeof(tb_arg_t));
   pthread_barrier_t bar;
   pthread_barrier_init(&bar, NULL, nthreads);
   for (int t = 0; t < nthreads; t++) {
-    a[t] = (tb_arg_t){t, nthreads, ntb, tbs, Qm, G, rv, max_iter, is8, llr, out, out_stride, rc, avg_iter, &bar, 0, 0};
+    a[t] = (tb_arg_t){t, nthreads, ntb, tbs, Qm, G, rv, max_iter, repeat ? repeat : 1, is8, llr, out, out_stride, rc, avg_iter, &bar, 0, 0};
     pthread_create(&th[t], NULL, tb_worker, &a[t]);
   }
   double t0 = 1e300, t1 = 0;

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsrslte_fec_b200.so")
+LIB_PATH = os.environ.get("SRSLTE_B200_LIB", os.path.join(HERE, "libsrslte_fec_b200.so"))
 
 IN_DEVICE = 1
 OUT_DEVICE = 2
@@ -93,6 +93,15 @@ def lib():
             getattr(L, f).restype = C.c_float
             getattr(L, f).argtypes = [C.c_void_p]
         for f in ("srslte_b200_last_launches", "srslte_b200_last_map_launches"):
+            getattr(L, f).restype = C.c_uint32
+            getattr(L, f).argtypes = [C.c_void_p]
+        L.srslte_b200_timer_start.argtypes = [C.c_void_p]
+        L.srslte_b200_timer_stop_ms.argtypes = [C.c_void_p]
+        L.srslte_b200_timer_stop_ms.restype = C.c_float
+        L.srslte_b200_alu_probe.argtypes = [C.c_void_p, C.c_int]
+        L.srslte_b200_alu_probe.restype = C.c_double
+        L.srslte_b200_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        for f in ("srslte_b200_last_replayed", "srslte_b200_last_half_iterations"):
             getattr(L, f).restype = C.c_uint32
             getattr(L, f).argtypes = [C.c_void_p]
         L.srslte_crc_checksum_byte.restype = C.c_uint32
@@ -225,7 +234,30 @@ class Context:
     def softbuffer_free(self, sb):
         lib().srslte_b200_softbuffer_free(sb)
 
+    def set_option(self, name, value):
+        rc = lib().srslte_b200_set_option(self.h, name.encode(), int(value))
+        if rc:
+            _err("srslte_b200_set_option(%s)" % name, rc)
+
+    def last_replayed(self):
+        return lib().srslte_b200_last_replayed(self.h)
+
+    def last_half_iterations(self):
+        return lib().srslte_b200_last_half_iterations(self.h)
+
     # ---- measurement hooks
+    def timer_start(self):
+        rc = lib().srslte_b200_timer_start(self.h)
+        if rc:
+            _err("srslte_b200_timer_start", rc)
+
+    def timer_stop_ms(self):
+        return lib().srslte_b200_timer_stop_ms(self.h)
+
+    def alu_probe(self, mode=0):
+        """packed int16x2 operations per second (see include/srslte_b200/batch.h)"""
+        return lib().srslte_b200_alu_probe(self.h, mode)
+
     def last_gpu_ms(self):
         return lib().srslte_b200_last_gpu_ms(self.h)
 
@@ -241,6 +273,23 @@ class Context:
 
 def make_tbs(n):
     return (Tb * n)()
+
+
+def qpp_table(K, lanes=1):
+    f = np.zeros(K, np.uint16)
+    r = np.zeros(K, np.uint16)
+    rc = lib().srslte_b200_qpp_table(C.c_uint32(K), C.c_uint32(lanes), _ptr(f), _ptr(r))
+    if rc:
+        raise B200Error("srslte_b200_qpp_table(%d, %d) failed" % (K, lanes))
+    return f, r
+
+
+def rm_table(K, rv, lanes=0):
+    t = np.zeros(3 * K + 12, np.uint16)
+    rc = lib().srslte_b200_rm_table(C.c_uint32(K), C.c_uint32(rv), C.c_uint32(lanes), _ptr(t))
+    if rc:
+        raise B200Error("srslte_b200_rm_table(%d, %d, %d) failed" % (K, rv, lanes))
+    return t
 
 
 # ------------------------------------------------------------------ drop-in srslte_* symbols (host pointers)

@@ -40,6 +40,7 @@ B200_HD u32 p_max(u32 a, u32 b) { return __vmaxs2(a, b); }
 B200_HD u32 p_min(u32 a, u32 b) { return __vmins2(a, b); }
 B200_HD u32 p_addmax(u32 a, u32 b, u32 c) { return __viaddmax_s16x2(a, b, c); } // max(a+b (wrapping), c)
 B200_HD u32 p_max3(u32 a, u32 b, u32 c) { return __vimax3_s16x2(a, b, c); }
+B200_HD u32 p_min3(u32 a, u32 b, u32 c) { return __vimin3_s16x2(a, b, c); }
 #else
 B200_HD u32 p_add_wrap(u32 a, u32 b) { return pack16(lo16(a) + lo16(b), hi16(a) + hi16(b)); }
 B200_HD u32 p_sub_wrap(u32 a, u32 b) { return pack16(lo16(a) - lo16(b), hi16(a) - hi16(b)); }
@@ -61,6 +62,7 @@ B200_HD u32 p_min(u32 a, u32 b)
 }
 B200_HD u32 p_addmax(u32 a, u32 b, u32 c) { return p_max(p_add_wrap(a, b), c); }
 B200_HD u32 p_max3(u32 a, u32 b, u32 c) { return p_max(p_max(a, b), c); }
+B200_HD u32 p_min3(u32 a, u32 b, u32 c) { return p_min(p_min(a, b), c); }
 #endif
 
 B200_HD u32 splat16(int32_t v) { return pack16(v, v); }
@@ -70,20 +72,25 @@ struct Sat16 {
   static constexpr int  kBits    = 16;
   static constexpr int  kInf     = 10000;
   static constexpr bool kNormMax = false;
+  static constexpr bool kMonitor = false;
   B200_HD static u32 add(u32 a, u32 b) { return p_add_sat(a, b); }
   B200_HD static u32 sub(u32 a, u32 b) { return p_sub_sat(a, b); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   // max(a + b, c) with the reference's saturating add
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_max(p_add_sat(a, b), c); }
+  static constexpr int kNormPeriod = 2;
+  B200_HD static void normalize_now(u32 (&o)[8])
+  {
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+      o[i] = p_sub_sat(o[i], o[0]);
+    o[0] = 0;
+  }
   // normalize(k) of turbodecoder_win.h:480-498 (period 2, by state 0)
   B200_HD static void normalize(uint32_t k, u32 (&o)[8])
   {
-    if ((k & 1u) == 0 && k != 0) {
-#pragma unroll
-      for (int i = 1; i < 8; i++)
-        o[i] = p_sub_sat(o[i], o[0]);
-      o[0] = 0;
-    }
+    if ((k & 1u) == 0 && k != 0)
+      normalize_now(o);
   }
   B200_HD static u32 out(u32 llr) { return llr; }
   // scalar tail-trellis adder (turbodecoder_win.h:470-478): plain C int16 addition -> wraps
@@ -92,27 +99,64 @@ struct Sat16 {
   B200_HD static u32 glue_sub(u32 a, u32 b, bool, bool) { return p_sub_wrap(a, b); }
 };
 
+// Fast16: the SAME int16 decoder computed with sm_100a's native packed instructions only (VIADD.16x2,
+// VIMNMX.S16x2, VIADDMNMX.S16x2 -- wrapping adds).  Wrapping and saturating arithmetic agree as long as no
+// intermediate leaves the int16 range; MapWin tracks the range of the path metrics while it runs (kMonitor) and
+// the kernel REPLAYS a code block with the exact Sat16 policy whenever the tracked ranges cannot rule a
+// saturation out.  The results delivered are therefore always those of the saturating reference decoder.
+struct Fast16 {
+  static constexpr int  kBits    = 16;
+  static constexpr int  kInf     = 10000;
+  static constexpr bool kNormMax = false;
+  static constexpr bool kMonitor = true;
+  B200_HD static u32 add(u32 a, u32 b) { return p_add_wrap(a, b); }
+  B200_HD static u32 sub(u32 a, u32 b) { return p_sub_wrap(a, b); }
+  B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
+  B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  static constexpr int kNormPeriod = 2;
+  B200_HD static void normalize_now(u32 (&o)[8])
+  {
+#pragma unroll
+    for (int i = 1; i < 8; i++)
+      o[i] = p_sub_wrap(o[i], o[0]);
+    o[0] = 0;
+  }
+  B200_HD static void normalize(uint32_t k, u32 (&o)[8])
+  {
+    if ((k & 1u) == 0 && k != 0)
+      normalize_now(o);
+  }
+  B200_HD static u32 out(u32 llr) { return llr; }
+  B200_HD static int32_t tail_add(int32_t a, int32_t b) { return (int32_t)(int16_t)(uint16_t)(a + b); }
+  B200_HD static u32 glue_sub(u32 a, u32 b, bool, bool) { return p_sub_wrap(a, b); }
+};
+
 struct Sat8 {
   static constexpr int  kBits    = 8;
   static constexpr int  kInf     = 0;
   static constexpr bool kNormMax = true;
+  static constexpr bool kMonitor = false;
   B200_HD static u32 clamp8(u32 v) { return p_min(p_max(v, 0xff80ff80u), 0x007f007fu); }
   B200_HD static u32 add(u32 a, u32 b) { return p_min(p_addmax(a, b, 0xff80ff80u), 0x007f007fu); }
   B200_HD static u32 sub(u32 a, u32 b) { return clamp8(p_sub_wrap(a, b)); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_max(add(a, b), c); }
+  static constexpr int kNormPeriod = 1;
+  B200_HD static void normalize_now(u32 (&o)[8])
+  {
+    u32 m = p_max3(o[0], o[1], o[2]);
+    m     = p_max3(m, o[3], o[4]);
+    m     = p_max3(m, o[5], o[6]);
+    m     = p_max(m, o[7]);
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+      o[i] = sub(o[i], m);
+  }
   // normalize_max, period 1 (turbodecoder_win.h:180-181, 483-490)
   B200_HD static void normalize(uint32_t k, u32 (&o)[8])
   {
-    if (k != 0) {
-      u32 m = p_max3(o[0], o[1], o[2]);
-      m     = p_max3(m, o[3], o[4]);
-      m     = p_max3(m, o[5], o[6]);
-      m     = p_max(m, o[7]);
-#pragma unroll
-      for (int i = 0; i < 8; i++)
-        o[i] = sub(o[i], m);
-    }
+    if (k != 0)
+      normalize_now(o);
   }
   // divide_output: per-element arithmetic >> 1 (turbodecoder_win.h:188-193, 811-813)
   B200_HD static u32 out(u32 llr) { return pack16(lo16(llr) >> 1, hi16(llr) >> 1); }

@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -129,6 +130,8 @@ int Engine::create(Engine** out, int device)
   e->device   = device;
   e->num_sms  = prop.multiProcessorCount;
   e->plan_ptr = new Plan();
+  if (const char* ev = getenv("SRSLTE_B200_FAST16"))
+    e->opt_fast16 = atoi(ev) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventCreate(&e->ev_end));
@@ -154,7 +157,7 @@ Engine::~Engine()
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
   d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
-  d_sb.release(); d_genbeta.release();
+  d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   if (stream)
     cudaStreamDestroy(stream);
@@ -263,29 +266,35 @@ struct WinClass {
 };
 static const WinClass kWinClasses[4] = {{16, 8}, {16, 16}, {8, 16}, {8, 32}};
 
-template <class P, int N>
-static cudaError_t launch_map(const MapArgs& a, int n_slots, int max_w, cudaStream_t st)
+constexpr int kSegLen = 8; // trellis steps per register-resident beta segment (template parameter L)
+constexpr int kMapThreads = 256; // threads per block of the MAP kernel (one block per SM)
+
+// threads per block of the MAP kernel and its grid for n_slots code block slots
+template <int N>
+static void map_geometry(int n_slots, int* nt, int* blocks)
 {
-  constexpr int L = 16, T = N / 2, G = 32 / T;
-  const int     S = (max_w + L - 1) / L;
+  constexpr int T = N / 2, G = 32 / T;
   const int     warps = (n_slots + G - 1) / G;
-  // shared memory: S checkpoints x 8 states x 4 bytes per thread
-  auto go = [&](auto nt_tag) -> cudaError_t {
-    constexpr int NT   = decltype(nt_tag)::value;
-    const size_t  smem = (size_t)S * 8 * 4 * NT;
-    auto          kern = k_map_win<P, N, L, NT>;
-    cudaError_t   e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess)
-      return e;
-    const int blocks = (warps + NT / 32 - 1) / (NT / 32);
-    kern<<<blocks, NT, smem, st>>>(a);
-    return cudaGetLastError();
-  };
-  if ((size_t)S * 32 * 256 <= 200 * 1024)
-    return go(std::integral_constant<int, 256>{});
-  if ((size_t)S * 32 * 128 <= 200 * 1024)
-    return go(std::integral_constant<int, 128>{});
-  return go(std::integral_constant<int, 64>{});
+  *nt     = kMapThreads;
+  *blocks = (warps + (*nt / 32) - 1) / (*nt / 32);
+}
+
+template <class P, int N>
+static cudaError_t launch_map(MapArgs a, int n_slots, int max_w, cudaStream_t st)
+{
+  constexpr int L = kSegLen, NT = kMapThreads;
+  int           nt, blocks;
+  map_geometry<N>(n_slots, &nt, &blocks);
+  a.ck_slots = (max_w + L - 1) / L + 1;
+  // shared memory: double-buffered staging of 4 rows (in, parity, a-priori, QPP table) x L steps + one 8-word
+  // checkpoint, per thread
+  const size_t smem = (size_t)NT * 2 * (L * 4 + 8) * 4;
+  auto         kern = k_map_win<P, N, L, NT>;
+  cudaError_t  e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  kern<<<blocks, NT, smem, st>>>(a);
+  return cudaGetLastError();
 }
 
 int Engine::run(Plan& p)
@@ -375,7 +384,7 @@ int Engine::run(Plan& p)
   const int    n_pairs = (int)gen_pairs.size() / 2;
 
   // ---- device buffers
-  if (d_cbs.reserve(n_cb) || d_state.reserve(n_cb) || d_ws.reserve(ws_elems) || d_tails.reserve((size_t)n_cb * 12) ||
+  if (d_gmax.reserve((size_t)n_cb * 4) || d_cbs.reserve(n_cb) || d_state.reserve(n_cb) || d_ws.reserve(ws_elems) || d_tails.reserve((size_t)n_cb * 12) ||
       d_cbout.reserve(out_bytes + 64) || d_lists.reserve(lists.size() + 1) || d_tbs.reserve(p.tbs.size() + 1) ||
       d_res.reserve(p.tbs.size() + 1))
     return SRSLTE_B200_ERROR;
@@ -401,6 +410,9 @@ int Engine::run(Plan& p)
     CUDA_OK(cudaMemcpyAsync(d_tbs.ptr, hp, p.tbs.size() * sizeof(TbDev), cudaMemcpyHostToDevice, stream));
   }
 
+  if (d_counters.reserve(4) || h_counters.reserve(4))
+    return SRSLTE_B200_ERROR;
+  CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, 16, stream));
   CUDA_OK(cudaEventRecord(ev_begin, stream));
 
   // ---- rate de-matching (HARQ combine) straight into the decoder's lane layout
@@ -415,22 +427,51 @@ int Engine::run(Plan& p)
   if (active.empty()) {
     // nothing to decode (all code blocks cached from earlier HARQ transmissions)
   } else if (p.prepare) {
-    k_prepare<<<(int)active.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_active, d_ws.ptr, d_tails.ptr, d_state.ptr, 1);
+    k_prepare<<<(int)active.size(), 256, (3 * kMaxK + 12) * sizeof(int16_t), stream>>>(d_cbs.ptr, d_lists.ptr + off_active, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
     last_launches++;
   }
   CUDA_OK(cudaGetLastError());
+
+  // ---- global scratch for the beta checkpoints of the windowed kernels
+  {
+    size_t need = 0;
+    for (int c = 0; c < 4; c++) {
+      if (!cls[c].n_slots)
+        continue;
+      int nt, blocks;
+      if (kWinClasses[c].lanes == 8)
+        map_geometry<8>(cls[c].n_slots, &nt, &blocks);
+      else if (kWinClasses[c].lanes == 16)
+        map_geometry<16>(cls[c].n_slots, &nt, &blocks);
+      else
+        map_geometry<32>(cls[c].n_slots, &nt, &blocks);
+      const size_t slots = (size_t)(cls[c].max_w + kSegLen - 1) / kSegLen + 1;
+      need = std::max(need, slots * (size_t)blocks * nt * 8);
+    }
+    if (need && d_ckscratch.reserve(need))
+      return SRSLTE_B200_ERROR;
+  }
 
   // ---- half-iterations
   for (uint32_t it = 0; it < p.max_iter && !active.empty(); it++) {
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots)
         continue;
-      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr};
+      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0};
       cudaEvent_t e0, e1;
       if (map_event_pair(&e0, &e1))
         return SRSLTE_B200_ERROR;
       CUDA_OK(cudaEventRecord(e0, stream));
       cudaError_t e;
+      const bool  fast = opt_fast16 && c < 2;
+      if (fast) {
+        // native packed-instruction attempt with range monitoring, then exact replay of the flagged code blocks
+        a.mode = 1;
+        e = c == 0 ? launch_map<Fast16, 8>(a, cls[c].n_slots, cls[c].max_w, stream) : launch_map<Fast16, 16>(a, cls[c].n_slots, cls[c].max_w, stream);
+        CUDA_OK(e);
+        last_launches++;
+        a.mode = 2;
+      }
       switch (c) {
         case 0: e = launch_map<Sat16, 8>(a, cls[c].n_slots, cls[c].max_w, stream); break;
         case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break;
@@ -448,7 +489,7 @@ int Engine::run(Plan& p)
       CUDA_OK(cudaGetLastError());
       last_launches++;
     }
-    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr};
+    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr};
     k_decide_crc<<<((int)active.size() + 3) / 4, 128, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
@@ -462,7 +503,29 @@ int Engine::run(Plan& p)
     last_launches++;
   }
   CUDA_OK(cudaEventRecord(ev_end, stream));
+  CUDA_OK(cudaMemcpyAsync(h_counters.ptr, d_counters.ptr, 16, cudaMemcpyDeviceToHost, stream));
   return 0;
+}
+
+int Engine::timer_start()
+{
+  CUDA_OK(cudaSetDevice(device));
+  if (!ev_t0) {
+    CUDA_OK(cudaEventCreate(&ev_t0));
+    CUDA_OK(cudaEventCreate(&ev_t1));
+  }
+  CUDA_OK(cudaStreamSynchronize(stream));
+  CUDA_OK(cudaEventRecord(ev_t0, stream));
+  return 0;
+}
+float Engine::timer_stop_ms()
+{
+  cudaSetDevice(device);
+  if (!ev_t0 || cudaEventRecord(ev_t1, stream) != cudaSuccess || cudaEventSynchronize(ev_t1) != cudaSuccess)
+    return -1.f;
+  float ms = -1.f;
+  cudaEventElapsedTime(&ms, ev_t0, ev_t1);
+  return ms;
 }
 
 int Engine::map_event_pair(cudaEvent_t* a, cudaEvent_t* b)
@@ -480,6 +543,8 @@ int Engine::map_event_pair(cudaEvent_t* a, cudaEvent_t* b)
 
 int Engine::finish_timing()
 {
+  last_redo      = h_counters.ptr ? h_counters.ptr[0] : 0;
+  last_half_iter = h_counters.ptr ? h_counters.ptr[1] : 0;
   last_gpu_ms = 0;
   last_map_ms = 0;
   if (cudaEventElapsedTime(&last_gpu_ms, ev_begin, ev_end) != cudaSuccess)
@@ -843,6 +908,7 @@ template struct DevBuf<CbState>;
 template struct DevBuf<TbDev>;
 template struct DevBuf<TbResult>;
 template struct PinBuf<uint8_t>;
+template struct PinBuf<uint32_t>;
 template struct PinBuf<TbResult>;
 template struct PinBuf<CbState>;
 
@@ -962,6 +1028,72 @@ int srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer
 void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb) { b200::softbuffer_reset((b200::Softbuffer*)sb); }
 void srslte_b200_softbuffer_free(srslte_b200_softbuffer_t* sb) { b200::softbuffer_free((b200::Softbuffer*)sb); }
 
+// packed-op issue rate probe: returns packed operations per second (each operation = 2 int16 lane-ops)
+double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int mode)
+{
+  if (!ctx)
+    return 0;
+  Engine* e = ctx->e;
+  cudaSetDevice(e->device);
+  const int blocks = e->num_sms * 8, iters = 4096;
+  if (e->d_genbeta.reserve((size_t)blocks * 256))
+    return 0;
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  b200::k_alu_probe<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, 64, mode, 0x1234567u); // warm-up
+  cudaEventRecord(a, e->stream);
+  b200::k_alu_probe<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, iters, mode, 0x1234567u);
+  cudaEventRecord(b, e->stream);
+  cudaStreamSynchronize(e->stream);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, a, b);
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  if (ms <= 0)
+    return 0;
+  const double ops = (double)blocks * 256 * (double)iters * 8 * 4;
+  return ops / (ms * 1e-3);
+}
+// host-side table access (init-time products; used by input synthesis and by tests)
+int srslte_b200_qpp_table(uint32_t K, uint32_t lanes, uint16_t* fwd, uint16_t* rev)
+{
+  if (!b200::cb_size_valid(K) || (lanes > 1 && K % lanes))
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  b200::qpp_tables(K, lanes, fwd, rev);
+  return 0;
+}
+int srslte_b200_rm_table(uint32_t K, uint32_t rv, uint32_t lanes, uint16_t* table)
+{
+  if (!b200::cb_size_valid(K) || rv > 3 || (lanes > 1 && K % lanes))
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  b200::RmTable t;
+  b200::rm_table(K, lanes, &t);
+  const uint32_t L = 3 * K + 12;
+  for (uint32_t i = 0; i < L; i++)
+    table[i] = t.base[(i + t.start[rv]) % L];
+  return 0;
+}
+int srslte_b200_timer_start(srslte_b200_ctx_t* ctx)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->timer_start();
+}
+float srslte_b200_timer_stop_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->timer_stop_ms() : -1.f; }
+
+int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
+{
+  if (!ctx || !name)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  if (!strcmp(name, "fast16")) {
+    ctx->e->opt_fast16 = value != 0;
+    return 0;
+  }
+  return SRSLTE_B200_ERROR_INVALID_INPUTS;
+}
+uint32_t srslte_b200_last_replayed(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_redo : 0; }
+uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_half_iter : 0; }
 float    srslte_b200_last_gpu_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_gpu_ms : 0.f; }
 uint32_t srslte_b200_last_launches(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_launches : 0; }
 float    srslte_b200_last_map_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_map_ms : 0.f; }

@@ -52,6 +52,8 @@ public:
   int submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags);
   int submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uint32_t max_iterations, uint32_t flags);
   int wait();
+  int   timer_start();   // records a CUDA event on the engine's stream (after draining it)
+  float timer_stop_ms(); // records the closing event, waits for it, returns the device time between the two
 
   int softbuffer_create(Softbuffer** out, uint32_t max_cb);
   // host-pointer compatibility operations behind the drop-in srslte_* symbols (api.inc)
@@ -87,8 +89,11 @@ public:
   DevBuf<TbResult> d_res;
   DevBuf<int16_t>  d_ws, d_tails, d_sb;
   DevBuf<uint8_t>  d_cbout, d_in, d_tbout;
-  DevBuf<int>      d_lists;
-  DevBuf<uint32_t> d_genbeta;
+  DevBuf<int>      d_lists, d_gmax;
+  bool             opt_fast16 = true; // try the native packed-instruction path first (exact replay on range alarm)
+  DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch;
+  PinBuf<uint32_t> h_counters;
+  uint32_t         last_redo = 0, last_half_iter = 0;
   PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc;
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
@@ -99,7 +104,7 @@ private:
   int map_event_pair(cudaEvent_t* a, cudaEvent_t* b);
   int finish_timing();
 
-  cudaEvent_t              ev_begin = nullptr, ev_end = nullptr;
+  cudaEvent_t              ev_begin = nullptr, ev_end = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
   std::vector<cudaEvent_t> map_events;
   size_t                   n_map_events_used = 0;
 

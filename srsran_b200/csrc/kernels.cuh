@@ -48,6 +48,8 @@ struct CbState {
   uint32_t done;   // early stop hit (CRC passed)
   uint32_t crc_ok;
   uint32_t crc;
+  uint32_t redo;   // Fast16 range monitor could not rule out a saturation: replay this half-iteration exactly
+  uint32_t n_redo; // statistics: half-iterations replayed
 };
 
 struct TbDev {
@@ -109,8 +111,13 @@ __global__ void __launch_bounds__(256) k_dematch(const CbDev* __restrict__ cbs, 
 // One CTA per code block: decoder input -> int16 planes syst | par0 | par1 in the decoder's own layout + 12 tail
 // values {syst[3], par0[3], app2[3], par1[3]}.
 __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list, int16_t* __restrict__ ws,
-                                                 int16_t* __restrict__ tails, CbState* __restrict__ state, int reset_state)
+                                                 int16_t* __restrict__ tails, CbState* __restrict__ state, int* __restrict__ gmax, int reset_state)
 {
+  __shared__ int s_g[3];
+  if (threadIdx.x < 3)
+    s_g[threadIdx.x] = 0;
+  __syncthreads();
+  int g0 = 0, g1 = 0, g2 = 0;
   const int   cb = list[blockIdx.x];
   const CbDev d  = cbs[cb];
   const int16_t* in16 = (const int16_t*)d.in_ptr;
@@ -129,20 +136,33 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
     state[cb].done   = 0;
     state[cb].crc_ok = 0;
     state[cb].crc    = 0;
+    state[cb].redo   = 0;
+    state[cb].n_redo = 0;
   }
+  auto amax = [](int& g, int32_t v) { v = v < 0 ? -v : v; g = v > g ? v : g; };
   if (d.in_sb) {
     // planes are K+32 apart (rm_turbo.c:263-277); the decoder layout equals the input layout
     for (uint32_t i = threadIdx.x; i < K; i += blockDim.x) {
-      p0[i]            = (int16_t)get(i);
-      p0[d.ps + i]     = (int16_t)get(K + kSbPadDev + i);
-      p0[2 * d.ps + i] = (int16_t)get(2 * (K + kSbPadDev) + i);
+      const int32_t a = get(i), b = get(K + kSbPadDev + i), c = get(2 * (K + kSbPadDev) + i);
+      p0[i]            = (int16_t)a;
+      p0[d.ps + i]     = (int16_t)b;
+      p0[2 * d.ps + i] = (int16_t)c;
+      amax(g0, a); amax(g1, b); amax(g2, c);
     }
   } else {
-    for (uint32_t n = threadIdx.x; n < K; n += blockDim.x) {
-      const uint32_t j = N ? (n % W) * N + n / W : n;
-      p0[j]            = (int16_t)get(3 * n);
-      p0[d.ps + j]     = (int16_t)get(3 * n + 1);
-      p0[2 * d.ps + j] = (int16_t)get(3 * n + 2);
+    // standard order 3n+s: read the block contiguously into shared memory, then emit the three planes in the
+    // decoder's layout with consecutive threads writing consecutive elements (both sides coalesced)
+    extern __shared__ int16_t s_in[];
+    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x)
+      s_in[i] = (int16_t)get(i);
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) {
+      const uint32_t n = N ? (j % N) * W + j / N : j;
+      const int32_t  a = s_in[3 * n], b = s_in[3 * n + 1], c = s_in[3 * n + 2];
+      p0[j]            = (int16_t)a;
+      p0[d.ps + j]     = (int16_t)b;
+      p0[2 * d.ps + j] = (int16_t)c;
+      amax(g0, a); amax(g1, b); amax(g2, c);
     }
   }
   if (threadIdx.x < 12) {
@@ -152,6 +172,15 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
     const uint32_t src = (grp == 0) ? 2 * i : (grp == 1) ? 2 * i + 1 : (grp == 2) ? 6 + 2 * i : 6 + 2 * i + 1;
     tails[(size_t)cb * 12 + t] = (int16_t)get(tb + src);
   }
+  // per-plane max |LLR| (bounds the branch metrics for the Fast16 range monitor)
+  atomicMax(&s_g[0], g0);
+  atomicMax(&s_g[1], g1);
+  atomicMax(&s_g[2], g2);
+  __syncthreads();
+  if (threadIdx.x < 3)
+    gmax[(size_t)cb * 4 + threadIdx.x] = s_g[threadIdx.x];
+  if (threadIdx.x == 3)
+    gmax[(size_t)cb * 4 + 3] = 0;
 }
 
 // ------------------------------------------------------------------------------------------ windowed MAP
@@ -159,29 +188,136 @@ struct MapArgs {
   const int*      work;    // code block per slot, -1 = padding (slots of one warp share K)
   int             n_slots;
   const CbDev*    cbs;
-  const CbState*  state;
+  CbState*        state;
   int16_t*        ws;
   const int16_t*  tails;
   const uint16_t* qpp;
+  int*            gmax; // per CB: max|syst|, max|par0|, max|par1|, max|extrinsic handed to the next half-iteration|
+  int             mode; // 0: decode every active CB; 1: Fast16 attempt (flags redo); 2: replay only CBs flagged redo
+  u32*            ck_scratch; // global beta-checkpoint scratch: ck_slots x (grid threads) x 8 words
+  int             ck_slots;
+};
+
+// Row source staged through shared memory with cp.async (LDGSTS): chunk c+1 streams in while chunk c is being
+// processed, so the global-memory latency is off the dependent-instruction chain.  Each thread stages and reads
+// only its own words, so no block barrier is involved: cp.async.wait_group orders a thread's own copies.
+//
+// The beta checkpoints (8 words per thread and segment) go to a per-thread global scratch -- written with two
+// 128-bit stores in the backward pass, prefetched back with the rows of the segment that needs them.  At one
+// block per SM the scratch in flight is a few tens of MB, i.e. L2-resident; shared memory then only holds the
+// double-buffered staging area (2 x (3L + 8) words per thread), which is what lets more warps share an SM.
+//
+// staging layout per buffer: rows: word (i, a) at stage[(i*4 + a) * NT] with a = in, parity, a-priori, QPP table;
+// checkpoint: 8 words at ckst[0..7]
+template <int L, int NT, int T>
+struct StagedSrc {
+  const u32 *in, *apr, *par, *lut;
+  int        j;
+  u32*       stage; // smem + threadIdx.x                   (rows, 2 buffers of L*4*NT words)
+  u32*       ckst;  // smem + 2*L*4*NT + threadIdx.x*8      (checkpoints, 2 buffers of NT*8 words)
+  u32*       ckg;   // global scratch of this thread: slot s at ckg[s * ck_stride .. +8)
+  size_t     ck_stride;
+  __device__ __forceinline__ static void cp4(u32* dst_smem, const u32* src)
+  {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ static void cp16(u32* dst_smem, const u32* src)
+  {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+  }
+  __device__ __forceinline__ void prefetch(int c, int p0, int lo, int hi, int ck_slot)
+  {
+    u32*            b    = stage + (size_t)(c & 1) * L * 4 * NT;
+    const ptrdiff_t row0 = (ptrdiff_t)p0 * T + j;
+    const u32 *     gi = in + row0, *gp = par + row0, *ga = apr + row0, *gl = lut + row0;
+    const bool      full = p0 >= lo && p0 + L <= hi;
+    if (full) { // interior chunk: constant offsets only
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        cp4(b + (i * 4 + 0) * NT, gi + i * T);
+        cp4(b + (i * 4 + 1) * NT, gp + i * T);
+      }
+      if (apr) {
+#pragma unroll
+        for (int i = 0; i < L; i++)
+          cp4(b + (i * 4 + 2) * NT, ga + i * T);
+      }
+      if (ck_slot >= 0) {
+#pragma unroll
+        for (int i = 0; i < L; i++)
+          cp4(b + (i * 4 + 3) * NT, gl + i * T);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < L; i++) {
+        const int p = p0 + i;
+        if (p >= lo && p < hi) {
+          cp4(b + (i * 4 + 0) * NT, gi + i * T);
+          cp4(b + (i * 4 + 1) * NT, gp + i * T);
+          if (apr)
+            cp4(b + (i * 4 + 2) * NT, ga + i * T);
+          if (ck_slot >= 0)
+            cp4(b + (i * 4 + 3) * NT, gl + i * T);
+        }
+      }
+    }
+    if (ck_slot >= 0) {
+      u32*       d = ckst + (size_t)(c & 1) * NT * 8;
+      const u32* g = ckg + (size_t)ck_slot * ck_stride;
+      cp16(d, g);
+      cp16(d + 4, g + 4);
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+  }
+  __device__ __forceinline__ void prefetch_none() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+  // the group of chunk c+1 was committed right before: everything older than the newest group must have landed
+  __device__ __forceinline__ void wait(int) { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+  __device__ __forceinline__ void drain() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+  __device__ __forceinline__ u32 get_apr(int c, int i, int) const
+  {
+    return apr ? stage[((size_t)(c & 1) * L * 4 + i * 4 + 2) * NT] : 0u;
+  }
+  __device__ __forceinline__ u32 get_lut(int c, int i, int) const { return stage[((size_t)(c & 1) * L * 4 + i * 4 + 3) * NT]; }
+  __device__ __forceinline__ void get(int c, int i, int, u32& vin, u32& vapr, u32& vpar) const
+  {
+    const u32* b = stage + (size_t)(c & 1) * L * 4 * NT;
+    vin          = b[(i * 4 + 0) * NT];
+    vpar         = b[(i * 4 + 1) * NT];
+    vapr         = apr ? b[(i * 4 + 2) * NT] : 0u;
+  }
+  __device__ __forceinline__ void ck_put(int slot, const u32 (&st)[8])
+  {
+    uint4* g = reinterpret_cast<uint4*>(ckg + (size_t)slot * ck_stride);
+    g[0]     = make_uint4(st[0], st[1], st[2], st[3]);
+    g[1]     = make_uint4(st[4], st[5], st[6], st[7]);
+  }
+  __device__ __forceinline__ void ck_get(int c, int, u32 (&st)[8]) const
+  {
+    const uint4* d = reinterpret_cast<const uint4*>(ckst + (size_t)(c & 1) * NT * 8);
+    const uint4  a = d[0], b = d[1];
+    st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w;
+    st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
+  }
 };
 
 // DEC1 epilogue: a-posteriori -> post (linear), extrinsic -> app2 through the QPP permutation (iter.h:117-121)
 template <class P>
 struct EpiDec1 {
   u32*       post;
-  const u32* apr; // nullptr at n_iter == 0
   int16_t*   app2;
-  const u32* rev2; // rev[] viewed as pairs
   int        T, j;
   uint32_t   sat_end;
-  __device__ __forceinline__ void operator()(int p, u32 llr, u32) const
+  u32        ehi, elo; // running max / min of the extrinsic values emitted
+  // apr == 0 when the call had no a-priori input (n_iter == 0): the subtraction is then the identity
+  __device__ __forceinline__ void operator()(int p, u32 llr, u32, u32 apr, u32 r)
   {
     const int w = p * T + j;
     post[w]     = llr;
-    u32 e       = llr;
-    if (apr)
-      e = P::glue_sub(llr, apr[w], (uint32_t)(2 * w) < sat_end, (uint32_t)(2 * w + 1) < sat_end);
-    const u32 r       = rev2[w];
+    const u32 e = P::glue_sub(llr, apr, (uint32_t)(2 * w) < sat_end, (uint32_t)(2 * w + 1) < sat_end);
+    ehi = p_max(ehi, e);
+    elo = p_min(elo, e);
     app2[r & 0xffffu] = (int16_t)lo16(e);
     app2[r >> 16]     = (int16_t)hi16(e);
   }
@@ -193,15 +329,14 @@ template <class P>
 struct EpiDec2 {
   int16_t*   post;
   int16_t*   apr;
-  const u32* fwd2;
-  int        T, j;
   uint32_t   sat_end;
-  __device__ __forceinline__ void operator()(int p, u32 llr, u32 x) const
+  u32        ehi, elo;
+  __device__ __forceinline__ void operator()(int, u32 llr, u32 x, u32, u32 f)
   {
-    const int      w  = p * T + j;
-    const u32      f  = fwd2[w];
     const uint32_t t0 = f & 0xffffu, t1 = f >> 16;
     const u32      a  = P::glue_sub(llr, x, t0 < sat_end, t1 < sat_end);
+    ehi = p_max(ehi, a);
+    elo = p_min(elo, a);
     apr[t0]           = (int16_t)lo16(a);
     apr[t1]           = (int16_t)hi16(a);
     post[t0]          = (int16_t)lo16(llr);
@@ -214,7 +349,7 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
 {
   constexpr int T = N / 2;  // threads per code block
   constexpr int G = 32 / T; // code blocks per warp
-  extern __shared__ u32 smem_ck[];
+  extern __shared__ __align__(16) u32 smem_ck[];
 
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * (NT / 32) + (threadIdx.x >> 5)) * G + lane / T;
@@ -226,32 +361,42 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   const CbState st0 = a.state[cb];
   if (st0.done || st0.n_iter >= d.max_iter)
     return;
+  if (a.mode == 2 && !st0.redo)
+    return;
   const unsigned gmask = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (lane / T * T));
 
   int16_t*       ws   = a.ws + d.ws_off;
   const int16_t* tl   = a.tails + (size_t)cb * 12;
   const bool     dec2 = st0.n_iter & 1u;
 
-  MapWin<P, L> m;
-  m.T   = T;
-  m.W   = d.W;
-  m.j   = j;
-  m.ck  = smem_ck + threadIdx.x;
-  m.cks = NT;
+  const int S = (d.W + L - 1) / L;
+  const uint16_t* q = a.qpp + d.qpp_off;
+  MapWin<P, L, StagedSrc<L, NT, T>> m;
+  m.W       = d.W;
+  m.src.j   = j;
+  m.src.stage = smem_ck + threadIdx.x;
+  m.src.ckst  = smem_ck + (size_t)2 * L * 4 * NT + (size_t)threadIdx.x * 8;
+  // global checkpoint scratch: slot-major, 8 words per thread, threads of the whole grid contiguous
+  m.src.ck_stride = (size_t)gridDim.x * NT * 8;
+  m.src.ckg       = a.ck_scratch + ((size_t)blockIdx.x * NT + threadIdx.x) * 8;
   const int16_t *tin, *tpar;
   if (!dec2) {
-    m.in  = (const u32*)(ws);
-    m.par = (const u32*)(ws + d.ps);
-    m.apr = st0.n_iter ? (const u32*)(ws + 3 * (size_t)d.ps) : nullptr;
-    tin   = tl;
-    tpar  = tl + 3;
+    m.src.in  = (const u32*)(ws);
+    m.src.par = (const u32*)(ws + d.ps);
+    m.src.apr = st0.n_iter ? (const u32*)(ws + 3 * (size_t)d.ps) : nullptr;
+    m.src.lut = (const u32*)(q + d.K); // rev[] as pairs
+    tin       = tl;
+    tpar      = tl + 3;
   } else {
-    m.in  = (const u32*)(ws + 4 * (size_t)d.ps);
-    m.par = (const u32*)(ws + 2 * (size_t)d.ps);
-    m.apr = nullptr;
-    tin   = tl + 6;
-    tpar  = tl + 9;
+    m.src.in  = (const u32*)(ws + 4 * (size_t)d.ps);
+    m.src.par = (const u32*)(ws + 2 * (size_t)d.ps);
+    m.src.apr = nullptr;
+    m.src.lut = (const u32*)q; // fwd[] as pairs
+    tin       = tl + 6;
+    tpar      = tl + 9;
   }
+  (void)S;
+  m.begin();
 
   u32 st[8];
   // ---- backward: warm-up, hand the estimate to the lane below, tail for the last lane, checkpointed pass
@@ -270,6 +415,20 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   }
   m.beta_main(st);
 
+  // bound on every |branch metric| of this call: max|a-priori| + max|systematic| + max|parity|
+  int* gm = a.gmax + (size_t)cb * 4;
+  int  g  = 0;
+  if (P::kMonitor) {
+    g = dec2 ? gm[3] + gm[2] : (st0.n_iter ? gm[3] : 0) + gm[0] + gm[1];
+    const bool bad = !fast16_beta_ok(m.mon_b.spread_lo(), g) || !fast16_beta_ok(m.mon_b.spread_hi(), g);
+    if (__any_sync(gmask, bad)) { // the whole code block is replayed with the exact policy (mode 2 launch)
+      if (j == 0)
+        a.state[cb].redo = 1;
+      m.src.drain();
+      return;
+    }
+  }
+
   // ---- forward: warm-up, hand the estimate to the lane above, known start for lane 0, output pass
   m.alpha_warm(st);
 #pragma unroll
@@ -283,14 +442,34 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
     for (int s = 1; s < 8; s++)
       st[s] = (st[s] & 0xffff0000u) | (u32)(uint16_t)(-P::kInf);
   }
-  const uint16_t* q = a.qpp + d.qpp_off;
+  u32             ehi, elo;
   if (!dec2) {
-    EpiDec1<P> e{(u32*)(ws + 5 * (size_t)d.ps), m.apr, ws + 4 * (size_t)d.ps, (const u32*)(q + d.K), T, j, d.sat_end};
+    EpiDec1<P> e{(u32*)(ws + 5 * (size_t)d.ps), ws + 4 * (size_t)d.ps, T, j, d.sat_end, 0u, 0u};
     m.alpha_main(st, e);
+    ehi = e.ehi;
+    elo = e.elo;
   } else {
-    EpiDec2<P> e{ws + 5 * (size_t)d.ps, ws + 3 * (size_t)d.ps, (const u32*)q, T, j, d.sat_end};
+    EpiDec2<P> e{ws + 5 * (size_t)d.ps, ws + 3 * (size_t)d.ps, d.sat_end, 0u, 0u};
     m.alpha_main(st, e);
+    ehi = e.ehi;
+    elo = e.elo;
   }
+  // max |extrinsic| handed to the next half-iteration (its a-priori / systematic input)
+  int ge = max(max(lo16(ehi), hi16(ehi)), max(-lo16(elo), -hi16(elo)));
+#pragma unroll
+  for (int o = T / 2; o >= 1; o >>= 1)
+    ge = max(ge, __shfl_xor_sync(gmask, ge, o, T));
+  if (P::kMonitor) {
+    const bool bad = !fast16_alpha_ok(m.mon_a.spread_lo(), m.mon_b.spread_lo(), g) ||
+                     !fast16_alpha_ok(m.mon_a.spread_hi(), m.mon_b.spread_hi(), g) || (m.mon_a.ovf & 0x80008000u) != 0;
+    if (__any_sync(gmask, bad)) {
+      if (j == 0)
+        a.state[cb].redo = 1;
+      return;
+    }
+  }
+  if (j == 0)
+    gm[3] = ge;
 }
 
 // ------------------------------------------------------------------------------------------ generic MAP
@@ -319,7 +498,8 @@ __device__ __forceinline__ void gen_norm(uint32_t k, u32 (&o)[8])
 }
 
 struct Wrap16 { // turbodecoder_gen.c: plain C int16 arithmetic
-  static constexpr int kInf = 10000;
+  static constexpr int  kInf     = 10000;
+  static constexpr bool kMonitor = false;
   B200_HD static u32 add(u32 a, u32 b) { return p_add_wrap(a, b); }
   B200_HD static u32 sub(u32 a, u32 b) { return p_sub_wrap(a, b); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
@@ -400,7 +580,8 @@ __global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
 #pragma unroll
     for (int s = 0; s < 8; s++)
       b[s] = beta[((size_t)k * 8 + s) * nt];
-    const u32 llr = fwd_step_llr<Wrap16>(o, b, x, y, p_add_wrap(x, y));
+    RangeMon  nomon;
+    const u32 llr = fwd_step_llr<Wrap16>(o, b, x, y, p_add_wrap(x, y), nomon);
     gen_norm(k, o);
     const uint32_t i = k - 1;
     // glue (iter.h:107-127), per half
@@ -482,6 +663,7 @@ struct DecideArgs {
   CbState*       state;
   const int16_t* ws;
   uint8_t*       cb_out;
+  uint32_t*      counters; // [0]: half-iterations replayed with the exact policy, [1]: half-iterations run
 };
 
 // one warp per code block
@@ -530,6 +712,12 @@ __global__ void __launch_bounds__(128) k_decide_crc(const DecideArgs a)
   }
   if (lane == 0) {
     s->n_iter = n_iter;
+    atomicAdd(&a.counters[1], 1u);
+    if (s->redo) {
+      s->redo = 0;
+      s->n_redo++;
+      atomicAdd(&a.counters[0], 1u);
+    }
     if (d.crc_poly != 0 && crc == 0) { // early stop (sch.c:441-450); the iteration limit is checked against n_iter
       s->crc_ok = 1;
       s->done   = 1;
@@ -626,6 +814,46 @@ __global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uin
   const uint32_t c = warp_crc24(nbytes, tab, poly, [&](uint32_t b) -> uint32_t { return data[b]; });
   if (threadIdx.x == 0)
     *out = c;
+}
+
+// ------------------------------------------------------------------------------------------ ALU roofline probe
+// Measures the issue rate of exactly the packed instructions the MAP kernel is made of (VIADD.16x2,
+// VIMNMX.S16x2, VIADDMNMX.S16x2): 8 independent dependency chains per thread, 4 packed operations per chain
+// step.  mode 0: wrapping add / max / fused add-max mix; mode 1: the same mix with the saturating add
+// (__vaddss2, a multi-instruction emulation on sm_100a).
+__global__ void __launch_bounds__(256) k_alu_probe(u32* out, int iters, int mode, u32 seed)
+{
+  u32 a[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    a[i] = seed * (threadIdx.x + 1) + i * 0x00010003u;
+  const u32 g = seed | 0x00010001u;
+  if (mode == 0) {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i] = p_add_wrap(a[i], g);
+        a[i] = p_max(a[i], a[(i + 1) & 7]);
+        a[i] = p_addmax(a[i], g, a[(i + 3) & 7]);
+        a[i] = p_add_wrap(a[i], a[(i + 5) & 7]);
+      }
+    }
+  } else {
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        a[i] = p_add_sat(a[i], g);
+        a[i] = p_max(a[i], a[(i + 1) & 7]);
+        a[i] = p_max(p_add_sat(a[i], g), a[(i + 3) & 7]);
+        a[i] = p_add_sat(a[i], a[(i + 5) & 7]);
+      }
+    }
+  }
+  u32 r = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+    r ^= a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
 } // namespace b200

@@ -9,22 +9,18 @@
 
 using namespace b200;
 
+// returns 1 if (Fast16 only) any lane's range monitor could not rule out a saturation
 template <class P, int L>
-static void run(int N, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out)
+static int run(int N, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out, int g = 0, int* stats = nullptr)
 {
   const int T = N / 2, W = K / N, S = (W + L - 1) / L;
   std::vector<std::vector<u32>> ck(T, std::vector<u32>((size_t)(S + 1) * 8));
-  std::vector<MapWin<P, L>>     m(T);
+  std::vector<MapWin<P, L, DirectSrc>> m(T);
   std::vector<u32>              st((size_t)T * 8);
   for (int j = 0; j < T; j++) {
-    m[j].in  = (const u32*)in;
-    m[j].apr = (const u32*)apr;
-    m[j].par = (const u32*)par;
-    m[j].T   = T;
-    m[j].W   = W;
-    m[j].j   = j;
-    m[j].ck  = ck[j].data();
-    m[j].cks = 1;
+    m[j].src     = DirectSrc{(const u32*)in, (const u32*)apr, (const u32*)par, T, j, ck[j].data(), nullptr};
+    m[j].W       = W;
+    m[j].begin();
   }
   auto S8 = [&](int j) -> u32(&)[8] { return *reinterpret_cast<u32(*)[8]>(&st[(size_t)j * 8]); };
   for (int j = 0; j < T; j++)
@@ -58,9 +54,35 @@ static void run(int N, int K, const int16_t* in, const int16_t* apr, const int16
   }
   for (int j = 0; j < T; j++) {
     u32* o   = (u32*)out;
-    auto epi = [&](int p, u32 llr, u32) { o[p * T + j] = llr; };
+    auto epi = [&](int p, u32 llr, u32, u32, u32) { o[p * T + j] = llr; };
     m[j].alpha_main(S8(j), epi);
   }
+  int flagged = 0;
+  if (P::kMonitor) {
+    int mx_a = 0, mx_b = 0;
+    for (int j = 0; j < T; j++) {
+      const int sa[2] = {m[j].mon_a.spread_lo(), m[j].mon_a.spread_hi()}, sb[2] = {m[j].mon_b.spread_lo(), m[j].mon_b.spread_hi()};
+      for (int h = 0; h < 2; h++) {
+        if (!fast16_beta_ok(sb[h], g) || !fast16_alpha_ok(sa[h], sb[h], g))
+          flagged = 1;
+        mx_a = sa[h] > mx_a ? sa[h] : mx_a;
+        mx_b = sb[h] > mx_b ? sb[h] : mx_b;
+      }
+      if (m[j].mon_a.ovf & 0x80008000u)
+        flagged = 1;
+    }
+    if (stats) {
+      stats[0] = mx_a;
+      stats[1] = mx_b;
+    }
+  }
+  return flagged;
+}
+
+// Fast16 with monitoring: returns the flag; g = bound on every |branch metric|
+extern "C" int emul_map_fast16(int N, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out, int g, int* stats)
+{
+  return run<Fast16, 16>(N, K, in, apr, par, out, g, stats);
 }
 
 extern "C" int emul_map_win(int bits, int N, int L, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out)

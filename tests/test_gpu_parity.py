@@ -302,3 +302,66 @@ def test_decode_tb_invalid(ctx):
     assert t[0].ret == -1       # all-zero LLRs: CRC fails
     assert t[1].ret == 0        # tbs == 0 -> SRSLTE_SUCCESS (sch.c:515)
     assert t[2].ret == -2       # filler bits not supported (sch.c:519-522)
+
+
+# ----------------------------------------------------------------------------------------- Fast16 path: monitor + exact replay
+def test_fast16_replay_accounting(port, ctx):
+    """small LLRs decode entirely on the native packed-instruction path; full-scale LLRs are all replayed with the
+    exact saturating arithmetic; either way the bytes equal the oracle's and fast16=0 gives the same bytes"""
+    rng = np.random.default_rng(1616)
+    K, ncb = 6144, 24
+    for amp, nit, expect in ((100, 4, "none"), (32767, 4, "all"), (300, 6, "some")):
+        llr = np.zeros((ncb, 3 * K + 12), np.int16)
+        for i in range(ncb):
+            bits = rng.integers(0, 2, K, dtype=np.uint8)
+            llr[i] = bpsk_awgn_llr(rng, port.tcod_encode(bits), amp, 0.9, np.int16) if amp < 32767 else random_llr(rng, 3 * K + 12, amp, np.int16)
+        ctx.set_option("fast16", 1)
+        got = ctx.tdec_batch(llr, K, nit)
+        rep, tot = ctx.last_replayed(), ctx.last_half_iterations()
+        assert tot == ncb * nit
+        if expect == "none":
+            assert rep == 0
+        elif expect == "all":
+            assert rep == tot
+        else:
+            assert 0 < rep < tot
+        ctx.set_option("fast16", 0)
+        exact = ctx.tdec_batch(llr, K, nit)
+        assert ctx.last_replayed() == 0
+        ctx.set_option("fast16", 1)
+        assert (got == exact).all()
+        hp = port.tdec_new(TDEC_AUTO, True)
+        for i in range(ncb):
+            rc, want = port.tdec_run_all(hp, llr[i], nit, K)
+            assert (got[i] == want).all(), (amp, i)
+        port.tdec_del(hp)
+
+
+def test_fast16_amplitude_sweep(port, ctx):
+    """sweep the LLR amplitude across the range-monitor's decision boundary: bit-exact everywhere, 8 half-iterations"""
+    rng = np.random.default_rng(1717)
+    for K in (6144, 1024, 512):
+        N = lanes16(K)
+        for amp in (30, 100, 180, 250, 400, 700, 1500, 4000, 12000):
+            bits = rng.integers(0, 2, K, dtype=np.uint8)
+            x = std_to_sb(bpsk_awgn_llr(rng, port.tcod_encode(bits), amp, 0.8, np.int16), K, N)
+            batch = np.ascontiguousarray(np.stack([x] * 3))
+            got = ctx.tdec_batch(batch, K, 8, input_sb=True)
+            hp = port.tdec_new(TDEC_AUTO, False)
+            rc, want = port.tdec_run_all(hp, x, 8, K)
+            port.tdec_del(hp)
+            assert (got == want[None, :]).all(), (K, amp)
+
+
+def test_exact_path_full_suite_sample(port, ctx):
+    """the exact-arithmetic kernels alone (fast16 = 0) on the transport-block path"""
+    rng = np.random.default_rng(1818)
+    ctx.set_option("fast16", 0)
+    try:
+        for tbs, Qm, G, dtype, amp, sigma in ((75376, 6, 90000, np.int16, 100, 0.46), (15264, 4, 20000, np.int16, 3000, 0.55)):
+            sbp = port.softbuffer_new()
+            data, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, dtype, amp, sigma)
+            _decode_both(port, ctx, tbs, Qm, 0, llr, 8, sbp, None)
+            port.softbuffer_del(sbp)
+    finally:
+        ctx.set_option("fast16", 1)
