@@ -325,15 +325,17 @@ int Engine::run(Plan& p)
     lists.insert(lists.end(), v.begin(), v.end());
     return off;
   };
-  std::vector<int> active, dm16, dm8;
+  std::vector<int> active, dm16, dm8, plain;
   for (int i = 0; i < n_cb; i++) {
     if (p.cbs[i].skip)
       continue;
     active.push_back(i);
     if (p.cbs[i].dematch)
       (p.cbs[i].in_bits == 16 ? dm16 : dm8).push_back(i);
+    else
+      plain.push_back(i);
   }
-  const size_t off_active = add_list(active), off_dm16 = add_list(dm16), off_dm8 = add_list(dm8);
+  const size_t off_active = add_list(active), off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
   struct ClassRun {
     size_t off;
     int    n_slots, max_w;
@@ -415,19 +417,23 @@ int Engine::run(Plan& p)
   CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, 16, stream));
   CUDA_OK(cudaEventRecord(ev_begin, stream));
 
-  // ---- rate de-matching (HARQ combine) straight into the decoder's lane layout
+  // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
+  //      directly supplied LLRs: extraction only
+  const size_t sb_smem = (3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t);
   if (!dm16.empty()) {
-    k_dematch<int16_t><<<(int)dm16.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr);
+    auto kern = k_dematch_prepare<int16_t>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+    kern<<<(int)dm16.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
     last_launches++;
   }
   if (!dm8.empty()) {
-    k_dematch<int8_t><<<(int)dm8.size(), 256, 0, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr);
+    auto kern = k_dematch_prepare<int8_t>;
+    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+    kern<<<(int)dm8.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
     last_launches++;
   }
-  if (active.empty()) {
-    // nothing to decode (all code blocks cached from earlier HARQ transmissions)
-  } else if (p.prepare) {
-    k_prepare<<<(int)active.size(), 256, (3 * kMaxK + 12) * sizeof(int16_t), stream>>>(d_cbs.ptr, d_lists.ptr + off_active, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
+  if (!plain.empty() && p.prepare) {
+    k_prepare<<<(int)plain.size(), 256, (3 * kMaxK + 12) * sizeof(int16_t), stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
     last_launches++;
   }
   CUDA_OK(cudaGetLastError());
@@ -490,7 +496,7 @@ int Engine::run(Plan& p)
       last_launches++;
     }
     DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr};
-    k_decide_crc<<<((int)active.size() + 3) / 4, 128, 0, stream>>>(da);
+    k_decide_crc<<<((int)active.size() + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
   }
@@ -691,11 +697,10 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     if (d_tbout.reserve(out_bytes + 64) || h_stage_out.reserve(out_bytes + 64))
       return SRSLTE_B200_ERROR;
   }
-  if (d_sb.reserve(scratch_cb * kSoftbufElems + 64))
-    return SRSLTE_B200_ERROR;
+  (void)scratch_cb;
 
   // pass 2: descriptors
-  size_t in_off = 0, out_off = 0, sb_off = 0;
+  size_t in_off = 0, out_off = 0;
   tb_out_off.assign(nof_tb, 0);
   for (uint32_t t = 0; t < nof_tb; t++) {
     if (tb_map[t] < 0)
@@ -765,9 +770,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
         d.fresh  = 0;
         d.skip   = sb->crc_host[c] ? 1 : 0; // sch.c:385
       } else {
-        d.in_ptr = (void*)(d_sb.ptr + sb_off);
-        sb_off += kSoftbufElems;
-        d.fresh = 1;
+        d.in_ptr = nullptr; // one-shot decode: the combined soft bits never leave the SM (k_dematch_prepare)
+        d.fresh  = 1;
       }
       if (d.skip)
         d.dematch = 0;

@@ -152,13 +152,138 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
   } else {
     // standard order 3n+s: read the block contiguously into shared memory, then emit the three planes in the
     // decoder's layout with consecutive threads writing consecutive elements (both sides coalesced)
-    extern __shared__ int16_t s_in[];
-    for (uint32_t i = threadIdx.x; i < 3 * K + 12; i += blockDim.x)
-      s_in[i] = (int16_t)get(i);
+    extern __shared__ __align__(16) int16_t s_in[];
+    const uint32_t n_in = 3 * K + 12;
+    if (d.in_bits == 16 && d.bits == 16 && (((uintptr_t)in16) & 7u) == 0) {
+      // 8-byte vector loads (n_in is a multiple of 4)
+      const uint2* src = reinterpret_cast<const uint2*>(in16);
+      uint2*       dst = reinterpret_cast<uint2*>(s_in);
+      for (uint32_t i = threadIdx.x; i < n_in / 4; i += blockDim.x)
+        dst[i] = __ldg(src + i);
+    } else {
+      for (uint32_t i = threadIdx.x; i < n_in; i += blockDim.x)
+        s_in[i] = (int16_t)get(i);
+    }
     __syncthreads();
-    for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) {
-      const uint32_t n = N ? (j % N) * W + j / N : j;
-      const int32_t  a = s_in[3 * n], b = s_in[3 * n + 1], c = s_in[3 * n + 2];
+    if (N) {
+      // two adjacent lanes (j, j+1) of one step per thread: one 32-bit store per plane
+      u32* q0 = reinterpret_cast<u32*>(p0);
+      u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
+      u32* q2 = reinterpret_cast<u32*>(p0 + 2 * (size_t)d.ps);
+      for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
+        const uint32_t j = 2 * h, n0 = (j % N) * W + j / N, n1 = n0 + W;
+        const int32_t  a0 = s_in[3 * n0], b0 = s_in[3 * n0 + 1], c0 = s_in[3 * n0 + 2];
+        const int32_t  a1 = s_in[3 * n1], b1 = s_in[3 * n1 + 1], c1 = s_in[3 * n1 + 2];
+        q0[h] = pack16(a0, a1);
+        q1[h] = pack16(b0, b1);
+        q2[h] = pack16(c0, c1);
+        amax(g0, a0); amax(g1, b0); amax(g2, c0);
+        amax(g0, a1); amax(g1, b1); amax(g2, c1);
+      }
+    } else {
+      for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) {
+        const int32_t a = s_in[3 * j], b = s_in[3 * j + 1], c = s_in[3 * j + 2];
+        p0[j]            = (int16_t)a;
+        p0[d.ps + j]     = (int16_t)b;
+        p0[2 * d.ps + j] = (int16_t)c;
+        amax(g0, a); amax(g1, b); amax(g2, c);
+      }
+    }
+  }
+  if (threadIdx.x < 12) { // (the shared-memory copy is not used here: generic inputs may not have filled it)
+    const uint32_t tb = d.in_sb ? 3 * (K + kSbPadDev) : 3 * K;
+    // tail order on the wire: x_K z_K x_K+1 z_K+1 x_K+2 z_K+2 | x'_K z'_K x'_K+1 z'_K+1 x'_K+2 z'_K+2
+    const uint32_t t = threadIdx.x, grp = t / 3, i = t % 3;
+    const uint32_t src = (grp == 0) ? 2 * i : (grp == 1) ? 2 * i + 1 : (grp == 2) ? 6 + 2 * i : 6 + 2 * i + 1;
+    tails[(size_t)cb * 12 + t] = (int16_t)get(tb + src);
+  }
+  // per-plane max |LLR| (bounds the branch metrics for the Fast16 range monitor)
+  atomicMax(&s_g[0], g0);
+  atomicMax(&s_g[1], g1);
+  atomicMax(&s_g[2], g2);
+  __syncthreads();
+  if (threadIdx.x < 3)
+    gmax[(size_t)cb * 4 + threadIdx.x] = s_g[threadIdx.x];
+  if (threadIdx.x == 3)
+    gmax[(size_t)cb * 4 + 3] = 0;
+}
+
+// ------------------------------------------------------------------------------------------ dematch + extraction
+// Transport-block path: rate de-matching (HARQ combining) and input extraction in ONE pass per code block.  The
+// soft buffer of the block is assembled in shared memory (zero-filled for a new transmission, loaded for a
+// retransmission), the e-bits are accumulated into it (same gather form as k_dematch), and the result leaves the
+// SM as the decoder's three int16 planes + tails + per-plane max|LLR|; it is written back to the HARQ soft buffer
+// only when the caller keeps one (d.fresh == 0 means a caller-owned buffer).
+template <typename T>
+__global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list,
+                                                         const uint16_t* __restrict__ rm_pool, int16_t* __restrict__ ws,
+                                                         int16_t* __restrict__ tails, CbState* __restrict__ state, int* __restrict__ gmax)
+{
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  __shared__ int s_g[3];
+  T*             sb = reinterpret_cast<T*>(s_raw);
+  const int      cb = list[blockIdx.x];
+  const CbDev    d  = cbs[cb];
+  const uint32_t K = d.K, N = d.N, W = d.W, L = 3 * K + 12;
+  const uint32_t n_sb = d.in_sb ? 3 * (K + kSbPadDev) + 12 : L;
+  T*             gsb  = (T*)d.in_ptr;
+  if (threadIdx.x < 3)
+    s_g[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    state[cb].n_iter = 0;
+    state[cb].done   = 0;
+    state[cb].crc_ok = 0;
+    state[cb].crc    = 0;
+    state[cb].redo   = 0;
+    state[cb].n_redo = 0;
+  }
+  if (d.fresh) {
+    for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
+      sb[i] = 0;
+  } else {
+    for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
+      sb[i] = gsb[i];
+  }
+  __syncthreads();
+  const T*        in  = (const T*)d.e_ptr;
+  const uint16_t* tab = rm_pool + d.rm_off;
+  for (uint32_t i = threadIdx.x; i < L && i < d.E; i += blockDim.x) {
+    uint32_t acc = 0;
+    for (uint32_t r = i; r < d.E; r += L)
+      acc += (uint32_t)(int32_t)in[r];
+    uint32_t pos = i + d.rm_start;
+    if (pos >= L)
+      pos -= L;
+    const uint16_t o = tab[pos];
+    sb[o]            = (T)(uint32_t)((uint32_t)(int32_t)sb[o] + acc); // wraps in the width of the soft buffer
+  }
+  __syncthreads();
+  if (!d.fresh) {
+    for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
+      gsb[i] = sb[i];
+  }
+  // decoder planes (int16 containers), tails, max |LLR| per plane
+  int16_t* p0 = ws + d.ws_off;
+  int      g0 = 0, g1 = 0, g2 = 0;
+  auto     amax = [](int& g, int32_t v) { v = v < 0 ? -v : v; g = v > g ? v : g; };
+  if (d.in_sb) {
+    u32* q0 = reinterpret_cast<u32*>(p0);
+    u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
+    u32* q2 = reinterpret_cast<u32*>(p0 + 2 * (size_t)d.ps);
+    for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
+      const uint32_t j  = 2 * h;
+      const int32_t  a0 = sb[j], a1 = sb[j + 1], b0 = sb[K + kSbPadDev + j], b1 = sb[K + kSbPadDev + j + 1];
+      const int32_t  c0 = sb[2 * (K + kSbPadDev) + j], c1 = sb[2 * (K + kSbPadDev) + j + 1];
+      q0[h] = pack16(a0, a1);
+      q1[h] = pack16(b0, b1);
+      q2[h] = pack16(c0, c1);
+      amax(g0, a0); amax(g1, b0); amax(g2, c0);
+      amax(g0, a1); amax(g1, b1); amax(g2, c1);
+    }
+  } else {
+    for (uint32_t n = threadIdx.x; n < K; n += blockDim.x) {
+      const uint32_t j = N ? (n % W) * N + n / W : n;
+      const int32_t  a = sb[3 * n], b = sb[3 * n + 1], c = sb[3 * n + 2];
       p0[j]            = (int16_t)a;
       p0[d.ps + j]     = (int16_t)b;
       p0[2 * d.ps + j] = (int16_t)c;
@@ -167,12 +292,10 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
   }
   if (threadIdx.x < 12) {
     const uint32_t tb = d.in_sb ? 3 * (K + kSbPadDev) : 3 * K;
-    // tail order on the wire: x_K z_K x_K+1 z_K+1 x_K+2 z_K+2 | x'_K z'_K x'_K+1 z'_K+1 x'_K+2 z'_K+2
     const uint32_t t = threadIdx.x, grp = t / 3, i = t % 3;
     const uint32_t src = (grp == 0) ? 2 * i : (grp == 1) ? 2 * i + 1 : (grp == 2) ? 6 + 2 * i : 6 + 2 * i + 1;
-    tails[(size_t)cb * 12 + t] = (int16_t)get(tb + src);
+    tails[(size_t)cb * 12 + t] = (int16_t)sb[tb + src];
   }
-  // per-plane max |LLR| (bounds the branch metrics for the Fast16 range monitor)
   atomicMax(&s_g[0], g0);
   atomicMax(&s_g[1], g1);
   atomicMax(&s_g[2], g2);
@@ -666,10 +789,18 @@ struct DecideArgs {
   uint32_t*      counters; // [0]: half-iterations replayed with the exact policy, [1]: half-iterations run
 };
 
-// one warp per code block
-__global__ void __launch_bounds__(128) k_decide_crc(const DecideArgs a)
+// One warp per code block.  Hard decisions (win.h:925-993 / gen.c:260-277): the a-posteriori LLRs sit in lane
+// layout (row = trellis step, N lanes per row).  Each lane loads one whole row with vector loads, and one warp
+// ballot per decoder lane turns 32 rows into 32 consecutive natural-order bits of that lane; the bit rows are then
+// cut into MSB-first bytes (bit n of the block is step n % W of lane n / W), the bytes go out coalesced and feed
+// the warp-parallel CRC.
+constexpr int kDecideWarps = 4;
+__global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideArgs a)
 {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  __shared__ u32 s_bits[kDecideWarps][6144 / 32 + 64]; // bit rows: lane d at word d * wpr
+  __shared__ u32 s_bytes[kDecideWarps][6144 / 32];     // decided bytes, 4 per word
+  const int wib = threadIdx.x >> 5;
+  const int w   = blockIdx.x * kDecideWarps + wib;
   if (w >= a.n)
     return;
   const int   cb = a.list[w];
@@ -684,31 +815,68 @@ __global__ void __launch_bounds__(128) k_decide_crc(const DecideArgs a)
   uint32_t       crc    = 1;
   if (need) {
     const int16_t* post = a.ws + d.ws_off + 5 * (size_t)d.ps;
-    uint8_t*       out  = a.cb_out + d.out_off;
-    const uint32_t K = d.K, N = d.N, W = d.W;
-    auto get_byte = [&](uint32_t b) -> uint32_t {
-      uint32_t v = 0;
-      uint32_t n = 8 * b;
-      if (N) {
-        uint32_t lane_d = n / W, step = n - lane_d * W;
+    const uint32_t K = d.K, N = d.N ? d.N : 1, W = d.N ? d.W : K;
+    const uint32_t wpr = (W + 31) / 32 + 1; // words per bit row (+1 so a 64-bit window never runs off the row)
+    u32*           bits = s_bits[wib];
+    for (uint32_t i = lane; i < N * wpr; i += 32)
+      bits[i] = 0;
+    __syncwarp();
+    for (uint32_t r0 = 0; r0 < W; r0 += 32) {
+      const uint32_t p     = r0 + lane;
+      const bool     valid = p < W;
+      if (N >= 8) {
+        // row of N int16 = N/8 uint4
+        for (uint32_t q = 0; q < N / 8; q++) {
+          uint4 v = make_uint4(0, 0, 0, 0);
+          if (valid)
+            v = *reinterpret_cast<const uint4*>(post + (size_t)p * N + 8 * q);
+          const u32 ww[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          v = (v << 1) | (post[step * N + lane_d] > 0 ? 1u : 0u);
-          if (++step == W) {
-            step = 0;
-            lane_d++;
+          for (int e = 0; e < 8; e++) {
+            const int32_t val = (e & 1) ? hi16(ww[e >> 1]) : lo16(ww[e >> 1]);
+            const u32     b   = __ballot_sync(0xffffffffu, val > 0);
+            if (lane == 0)
+              bits[(8 * q + e) * wpr + r0 / 32] = b;
           }
         }
       } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++)
-          v = (v << 1) | (post[n + i] > 0 ? 1u : 0u);
+        const int32_t val = valid ? (int32_t)post[p] : 0;
+        const u32     b   = __ballot_sync(0xffffffffu, val > 0);
+        if (lane == 0)
+          bits[r0 / 32] = b;
       }
-      out[b] = (uint8_t)v;
-      return v;
-    };
-    const bool is_a = d.crc_poly == kCrc24A;
-    crc = warp_crc24(K / 8, is_a ? 0 : 1, is_a ? kCrc24A : kCrc24B, get_byte);
+    }
+    __syncwarp();
+    // bytes: natural bit n = 8*byte + i lives at bit (n % W) of row n / W; rows are LSB-first in step order
+    const uint32_t nbytes = K / 8;
+    u32*           obytes = s_bytes[wib];
+    uint8_t*       ob8    = reinterpret_cast<uint8_t*>(obytes);
+    for (uint32_t b = lane; b < nbytes; b += 32) {
+      const uint32_t n = 8 * b, dl = n / W, p = n - dl * W;
+      const uint32_t* row = bits + dl * wpr;
+      const uint64_t  win = ((uint64_t)row[p / 32 + 1] << 32) | row[p / 32];
+      u32             v   = (u32)(win >> (p & 31)) & 0xffu;
+      if (p + 8 > W) { // the byte straddles two decoder lanes
+        const uint32_t c1 = W - p;
+        v = (v & ((1u << c1) - 1u)) | ((bits[(dl + 1) * wpr] << c1) & 0xffu);
+      }
+      ob8[b] = (uint8_t)(__brev(v) >> 24); // first bit in time is the MSB
+    }
+    __syncwarp();
+    u32* out = reinterpret_cast<u32*>(a.cb_out + d.out_off);
+    if ((d.out_off & 3u) == 0) {
+      for (uint32_t i = lane; i < nbytes / 4; i += 32)
+        out[i] = obytes[i];
+      for (uint32_t i = (nbytes / 4) * 4 + lane; i < nbytes; i += 32)
+        a.cb_out[d.out_off + i] = ob8[i];
+    } else {
+      for (uint32_t i = lane; i < nbytes; i += 32)
+        a.cb_out[d.out_off + i] = ob8[i];
+    }
+    if (d.crc_poly != 0) {
+      const bool is_a = d.crc_poly == kCrc24A;
+      crc = warp_crc24(nbytes, is_a ? 0 : 1, is_a ? kCrc24A : kCrc24B, [&](uint32_t b) -> uint32_t { return ob8[b]; });
+    }
   }
   if (lane == 0) {
     s->n_iter = n_iter;
