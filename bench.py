@@ -103,33 +103,53 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
-def dist_setup(n_gpus):
-    """returns (rank, world, local_rank, barrier_fn, max_fn, sum_fn)"""
+def dist_setup(n_gpus, backend=None):
+    """One process per GPU.  Returns (rank, world, local_rank, barrier_fn, max_fn, sum_fn).
+    backend: "nccl" on the GPU box; "gloo" (CPU tensors) is used by the world_size-2 CPU test of this plumbing."""
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return 0, 1, 0, (lambda: None), (lambda x: x), (lambda x: x)
     import torch
     import torch.distributed as dist
+    backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if backend == "nccl":
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dev = "cuda"
+    else:
+        dist.init_process_group(backend)
+        dev = "cpu"
 
     def barrier():
         dist.barrier()
-        torch.cuda.synchronize()
+        if dev == "cuda":
+            torch.cuda.synchronize()
 
     def vmax(x):
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
     def vsum(x):
-        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        t = torch.tensor([float(x)], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
     return rank, world, local, barrier, vmax, vsum
+
+
+def shard_seed(rank):
+    """each rank decodes its own, independently generated shard of code blocks / subframes (weak scaling)"""
+    return 1234 + rank
+
+
+def aggregate(units_per_step_local, steps, ms_local, vmax, vsum):
+    """whole-job throughput: units of all ranks over the slowest rank's device time"""
+    ms = vmax(ms_local)
+    total_units = vsum(units_per_step_local) * steps
+    return total_units / (ms * 1e-3) / 1e6, ms, total_units
 
 
 # ----------------------------------------------------------------------------------------------- workloads
@@ -288,7 +308,7 @@ def run_ours(args):
     peaks, peak_src = load_peaks()
     ctx = b.Context(local)
     ctx2 = b.Context(local)  # second engine (own stream) for the pipelined end-to-end path
-    rng = np.random.default_rng(1234 + rank)
+    rng = np.random.default_rng(shard_seed(rank))
     sampler = ClockSampler(local)
     launches = 0
     extra = {}
@@ -387,9 +407,7 @@ def run_ours(args):
     clocks = sampler.stop()
     extra["exact_replay_fraction"] = replay[0] / max(1, replay[1])
     barrier()
-    ms = vmax(ms)
-    total_units = vsum(units_per_step) * args.steps
-    value = total_units / (ms * 1e-3) / 1e6
+    value, ms, total_units = aggregate(units_per_step, args.steps, ms, vmax, vsum)
 
     # ---- end to end through the C ABI with host buffers
     for _ in range(max(1, args.warmup // 2)):

@@ -354,3 +354,46 @@ class TurboDecoder:
 
     def free(self):
         lib().srslte_tdec_free(C.byref(self.h))
+
+
+class SoftbufferRx:
+    """srslte_softbuffer_rx_t through the drop-in symbols (device-resident HARQ buffer)"""
+
+    def __init__(self, nof_prb=100):
+        self.q = SoftbufferRx_t()
+        rc = lib().srslte_softbuffer_rx_init(C.byref(self.q), C.c_uint32(nof_prb))
+        if rc:
+            raise B200Error("srslte_softbuffer_rx_init failed: %s" % lib().srslte_b200_last_error().decode())
+
+    def reset_tbs(self, tbs):
+        lib().srslte_softbuffer_rx_reset_tbs(C.byref(self.q), C.c_uint32(tbs))
+
+    def cb_crc(self, n):
+        return [bool(self.q.cb_crc[i]) for i in range(n)]
+
+    def free(self):
+        lib().srslte_softbuffer_rx_free(C.byref(self.q))
+
+
+SoftbufferRx_t = SoftbufferRx  # placeholder, replaced below
+
+
+class _SoftbufferRxStruct(C.Structure):  # srslte_softbuffer_rx_t
+    _fields_ = [("max_cb", C.c_uint32), ("b200_softbuffer", C.c_void_p), ("cb_crc", C.POINTER(C.c_bool)), ("tb_crc", C.c_bool)]
+
+
+SoftbufferRx_t = _SoftbufferRxStruct
+
+
+def decode_tb(softbuffer, tbs, Qm, rv, e_bits, max_iterations):
+    """srslte_b200_decode_tb: decode_tb of sch.c:503-570 as one call on host buffers.
+    Returns (ret, data bytes, avg_iterations)."""
+    seg = CbSegm()
+    if lib().srslte_cbsegm(C.byref(seg), C.c_uint32(tbs)):
+        return -1, None, 0.0
+    data = np.zeros(tbs // 8 + 8 + 768, np.uint8)
+    avg = C.c_float(0)
+    f = lib().srslte_b200_decode_tb
+    f.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_bool, C.c_uint32, C.c_void_p, C.c_void_p]
+    rc = f(C.byref(softbuffer.q), C.byref(seg), Qm, rv, len(e_bits), _ptr(e_bits), e_bits.dtype == np.int8, max_iterations, _ptr(data), C.byref(avg))
+    return rc, data, avg.value

@@ -1,0 +1,91 @@
+"""CPU tests of the drop-in boundary: the shared library loads without a GPU, exports every symbol the headers
+declare, serves the host-side (init-time) functions, and FAILS LOUDLY -- instead of falling back to the CPU -- when
+asked to compute without a device."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import srsran_b200 as b
+from util import all_K, lanes8, lanes16
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from srsran_b200 import build
+    build.build()
+    return b.lib()
+
+
+def declared_symbols():
+    names = []
+    for h in ("fec.h", "batch.h"):
+        txt = open(os.path.join(ROOT, "include", "srslte_b200", h)).read()
+        txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+        for m in re.finditer(r"SRSLTE(?:_B200)?_API\s+[\w\s\*]+?\b(srslte_\w+)\s*\(", txt):
+            names.append(m.group(1))
+    return sorted(set(names))
+
+
+def test_every_declared_symbol_is_exported(lib):
+    names = declared_symbols()
+    assert len(names) > 50
+    for n in names:
+        assert hasattr(lib, n), "libsrslte_fec_b200.so does not export " + n
+
+
+def test_no_oracle_or_torch_dependency(lib):
+    """the product library links neither the oracle nor torch nor a dynamic CUDA runtime"""
+    import subprocess
+    out = subprocess.check_output(["ldd", b.LIB_PATH], text=True)
+    assert "oracle" not in out and "torch" not in out and "libcudart" not in out
+    syms = subprocess.check_output(["nm", "-D", "--defined-only", b.LIB_PATH], text=True)
+    assert "orc_" not in syms
+
+
+def test_segmentation_matches_oracle(lib, port):
+    for tbs in list(range(16, 100000, 8 * 41)) + [75376, 97896, 6120, 40, 75000, 0]:
+        rc, seg = b.cbsegm(tbs)
+        rc2, seg2 = port.cbsegm(tbs)
+        assert rc == rc2 and seg == seg2, tbs
+    for i, K in enumerate(all_K()):
+        assert lib.srslte_cbsegm_cbsize(C.c_uint32(i)) == K
+        assert lib.srslte_cbsegm_cbindex(C.c_uint32(K)) == i
+        assert lib.srslte_cbsegm_cbindex(C.c_uint32(K - 1)) == i
+        assert lib.srslte_cbsegm_cbsize_isvalid(C.c_uint32(K)) and not lib.srslte_cbsegm_cbsize_isvalid(C.c_uint32(K + 1))
+        assert lib.srslte_tdec_autoimp_get_subblocks(C.c_uint32(K)) == lanes16(K)
+        assert lib.srslte_tdec_autoimp_get_subblocks_8bit(C.c_uint32(K)) == lanes8(K)
+    assert lib.srslte_cbsegm_cbsize(C.c_uint32(188)) == -1 and lib.srslte_cbsegm_cbindex(C.c_uint32(6145)) == -1
+
+
+def test_host_tables_match_oracle(lib, port):
+    for K in all_K():
+        for lanes in (1, 8, 16, 32):
+            if lanes > 1 and K % lanes:
+                continue
+            f, r = b.qpp_table(K, lanes)
+            f2, r2 = port.qpp(K, lanes)
+            assert (f == f2).all() and (r == r2).all(), (K, lanes)
+        for rv in range(4):
+            for lanes in {0, lanes16(K), lanes8(K)}:
+                assert (b.rm_table(K, rv, lanes) == port.rm_table(K, rv, lanes)).all(), (K, rv, lanes)
+
+
+def test_crc_init_table(lib):
+    c = b.Crc()
+    assert lib.srslte_crc_init(C.byref(c), C.c_uint32(b.CRC24A), C.c_int(24)) == 0
+    assert c.order == 24 and c.crcmask == 0xFFFFFF and c.table[1] == (b.CRC24A & 0xFFFFFF)
+    assert lib.srslte_crc_init(C.byref(c), C.c_uint32(b.CRC24A), C.c_int(23)) == -1
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="a GPU is present")
+def test_fails_loudly_without_gpu(lib):
+    with pytest.raises(b.B200Error) as ei:
+        b.Context(0)
+    assert "no CUDA device" in str(ei.value) or "-3" in str(ei.value)
+    td = b.Tdec()
+    assert lib.srslte_tdec_init(C.byref(td), C.c_uint32(6144)) == -1

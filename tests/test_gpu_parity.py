@@ -365,3 +365,30 @@ def test_exact_path_full_suite_sample(port, ctx):
             port.softbuffer_del(sbp)
     finally:
         ctx.set_option("fast16", 1)
+
+
+# ----------------------------------------------------------------------------------------- drop-in decode_tb + srslte_softbuffer_rx_*
+def test_drop_in_decode_tb_with_softbuffer(port):
+    """srslte_b200_decode_tb (what sch.c's decode_tb becomes) with a srslte_softbuffer_rx_t across HARQ retransmissions"""
+    rng = np.random.default_rng(4242)
+    for tbs, Qm, G, dtype, amp, sigma in ((15264, 4, 20000, np.int16, 200, 0.75), (31704, 6, 40000, np.int8, 20, 0.62)):
+        sbp = port.softbuffer_new()
+        sbg = b.SoftbufferRx(100)
+        sbg.reset_tbs(tbs)
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        rcs = []
+        for rv in (0, 2, 3):
+            _, llr = _tb_inputs(port, rng, tbs, Qm, G, rv, dtype, amp, sigma, data)
+            rc_p, d_p, nit_p, avg_p, crc_p = port.decode_tb(sbp, tbs, Qm, rv, llr, 8)
+            rc, d, avg = b.decode_tb(sbg, tbs, Qm, rv, llr, 8)
+            C_ = port.cbsegm(tbs)[1]["C"]
+            n = tbs // 8 + 3
+            assert rc == rc_p and (d[:n] == d_p[:n]).all() and abs(avg - avg_p) < 1e-6
+            assert sbg.cb_crc(C_) == [bool(x) for x in crc_p[:C_]]
+            rcs.append(rc)
+            if rc == 0:
+                assert (d[:tbs // 8] == data).all()
+                break
+        assert rcs[0] == -1 and rcs[-1] == 0, rcs
+        sbg.free()
+        port.softbuffer_del(sbp)

@@ -1,0 +1,108 @@
+"""CPU tests: the oracle (oracle/oracle.c) against the committed golden fixtures.
+
+tests/golden/*.npz were produced by tests/golden/make_golden.py from the UNMODIFIED reference
+(oracle/_ref/libsrslte_ref.so compiled from /root/reference) and from the reference's own known-answer test
+material (turbodecoder_test.h:70-125, crc_test.h:36-39).  These tests run anywhere gcc runs."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle.bindings import CRC8, CRC16, CRC24A, CRC24B
+from util import all_K, lanes8, lanes16
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def digest(a):
+    return np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], np.uint64)[0]
+
+
+def test_kat_crc_words(port):
+    """crc_test.h:36-39: CRC words of the srand(1) 5001-bit vector (bit-wise srslte_crc_checksum, crc_test.c:101)"""
+    k = np.load(os.path.join(G, "kat.npz"))
+    bits, words = k["crc_bits"], k["crc_words"]
+    for (poly, order), want in zip(((CRC24A, 24), (CRC24B, 24), (CRC16, 16), (CRC8, 8)), words):
+        assert port.crc_bits(poly, order, bits) == int(want), hex(poly)
+
+
+def test_kat_turbo_encoder_vector(port):
+    """turbodecoder_test.h:70-125: known_data -> known_data_encoded pins the QPP parameters of K=504, the constituent
+    encoders and the tail-bit order the decoder's input extraction relies on"""
+    k = np.load(os.path.join(G, "kat.npz"))
+    got, want = port.tcod_encode(k["known_data"]), k["known_data_encoded"]
+    # 1523 of the 1524 symbols agree.  Position 1512 (the first tail bit) of the reference's fixture differs from the
+    # output of the reference's OWN srslte_tcod_encode (checked in test_oracle_vs_ref.py::test_known_vector_vs_reference_encoder);
+    # turbodecoder_test only ever feeds the fixture to the decoder (turbodecoder_test.c:240), it never compares it.
+    assert np.nonzero(got != want)[0].tolist() == [1512]
+
+
+def test_kat_decodes_known_vector(port):
+    """noise-free decode of the reference's known code word returns the known data (all decoder families that take K=504)"""
+    k = np.load(os.path.join(G, "kat.npz"))
+    cw = k["known_data_encoded"].astype(np.int16) * 200 - 100
+    for dec, fnsb in ((0, True), (1, True), (3, True)):
+        h = port.tdec_new(dec, fnsb)
+        rc, out = port.tdec_run_all(h, cw, 2, 504)
+        port.tdec_del(h)
+        assert rc == 0 and (np.unpackbits(out) == k["known_data"]).all(), dec
+
+
+def test_tables_against_reference_digests(port):
+    t = np.load(os.path.join(G, "tables.npz"))
+    Ks = t["K"].tolist()
+    assert Ks == all_K() == [port.cbsize(i) for i in range(188)]
+    qi = ri = 0
+    for ci, K in enumerate(Ks):
+        for lanes in (1, 8, 16, 32):
+            if lanes > 1 and K % lanes:
+                assert t["qpp"][qi] == 0
+            else:
+                f, r = port.qpp(K, lanes)
+                assert digest(np.concatenate([f, r])) == t["qpp"][qi], (K, lanes)
+            qi += 1
+        for rv in range(4):
+            e = (np.arange(3 * K + 12) + 1).astype(np.int16)
+            for lanes in (0, lanes16(K)):
+                out = np.zeros(18600, np.int16)
+                port.rm_rx16(e, out, K, rv, lanes)
+                assert digest(out) == t["rm"][ri], (K, rv, lanes)
+                ri += 1
+            e8 = ((np.arange(3 * K + 12) * 7 + 3) % 251 - 125).astype(np.int8)
+            out8 = np.zeros(18600 * 2, np.int8)
+            port.rm_rx8(e8, out8, K, rv, lanes8(K))
+            assert digest(out8) == t["rm"][ri], (K, rv, "int8")
+            ri += 1
+
+
+def test_decoder_against_reference_outputs(port):
+    t = np.load(os.path.join(G, "tdec.npz"))
+    for idx, (K, bits, amp, nit) in enumerate(t["cases"].tolist()):
+        llr = np.ascontiguousarray(t["in%d" % idx])
+        h = port.tdec_new(0, False)
+        assert port.tdec_new_cb(h, K) == 0
+        for it in range(nit):
+            out = port.tdec_iteration(h, llr, K)
+            assert (out == t["bytes%d" % idx][it]).all(), (K, bits, amp, it)
+            assert digest(port.tdec_get_llr(h, 2 if it % 2 == 0 else 0, K)) == t["llr%d" % idx][it], (K, bits, amp, it, "llr")
+        port.tdec_del(h)
+
+
+def test_transport_blocks_against_reference_outputs(port):
+    t = np.load(os.path.join(G, "tb.npz"))
+    for idx, c in enumerate(t["cases"].tolist()):
+        tbs, Qm, Gb, bits, amp, sigma, mi = int(c[0]), int(c[1]), int(c[2]), int(c[3]), c[4], c[5], int(c[6])
+        sb = port.softbuffer_new()
+        for j in range(int(t["nrv"][idx])):
+            rv, rc_ref = t["rv%d_%d" % (idx, j)].tolist()
+            llr = np.ascontiguousarray(t["llr%d_%d" % (idx, j)])
+            rc, d, nit, avg, crc = port.decode_tb(sb, tbs, Qm, rv, llr, mi)
+            n = tbs // 8 + 6
+            assert rc == rc_ref, (idx, j)
+            assert (d[:n] == t["out%d_%d" % (idx, j)]).all(), (idx, j)
+            assert abs(avg - float(t["avg%d_%d" % (idx, j)][0])) < 1e-6
+            assert (crc == t["crc%d_%d" % (idx, j)]).all()
+            if rc == 0:
+                assert (d[:tbs // 8] == t["data%d" % idx]).all()
+        port.softbuffer_del(sb)

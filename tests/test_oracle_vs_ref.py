@@ -1,0 +1,171 @@
+"""CPU tests: the oracle restatement against the UNMODIFIED reference compiled here (oracle/_ref).  Skipped where the
+reference library does not exist (it is built only where /root/reference is mounted; the golden tests cover the rest)."""
+import numpy as np
+import pytest
+
+from oracle.bindings import (CRC8, CRC16, CRC24A, CRC24B, TDEC_AUTO, TDEC_AVX8_WINDOW, TDEC_AVX_WINDOW, TDEC_GENERIC, TDEC_SSE8_WINDOW,
+                             TDEC_SSE_WINDOW, aligned_zeros)
+from util import all_K, bpsk_awgn_llr, random_llr
+
+
+def test_segmentation_and_dispatch(port, ref):
+    for tbs in list(range(16, 100000, 8 * 53)) + [75376, 97896, 6120, 6128, 40, 75000]:
+        assert port.cbsegm(tbs) == ref.cbsegm(tbs), tbs
+    for i, K in enumerate(all_K()):
+        assert port.cbsize(i) == ref.cbsize(i) == K
+        assert port.cbindex(K) == ref.cbindex(K) == i
+        assert port.subblocks16(K) == ref.subblocks16(K) and port.subblocks8(K) == ref.subblocks8(K)
+
+
+def test_qpp_all_sizes(port, ref):
+    for K in all_K():
+        for lanes in (1, 8, 16, 32):
+            if lanes > 1 and K % lanes:
+                continue
+            f, r = port.qpp(K, lanes)
+            f2, r2 = ref.qpp(K, lanes)
+            assert (f == f2).all() and (r == r2).all(), (K, lanes)
+
+
+def test_crc(port, ref):
+    rng = np.random.default_rng(1)
+    for n in (1, 3, 100, 768, 9422):
+        d = rng.integers(0, 256, n, dtype=np.uint8)
+        for poly, o in ((CRC24A, 24), (CRC24B, 24), (CRC16, 16), (CRC8, 8)):
+            assert port.crc_bytes(poly, o, d) == ref.crc_bytes(poly, o, d)
+    for n in (5001, 40, 41, 47):
+        b = rng.integers(0, 2, n, dtype=np.uint8)
+        for poly, o in ((CRC24A, 24), (CRC24B, 24), (CRC16, 16), (CRC8, 8)):
+            assert port.crc_bits(poly, o, b) == ref.crc_bits(poly, o, b)
+
+
+def test_rate_dematching_tables_all_sizes(port, ref):
+    rng = np.random.default_rng(2)
+    for ci, K in enumerate(all_K()):
+        for rv in range(4):
+            E = 3 * K + 12
+            e = (np.arange(E) + 1).astype(np.int16)
+            for sb in (False, True):
+                lanes = port.subblocks16(K) if sb else 0
+                out = np.zeros(18600, np.int16)
+                ref.rm_rx16(e, out, ci, rv, enable_sb=sb)
+                want = np.zeros(18600, np.int16)
+                want[port.rm_table(K, rv, lanes)] = e
+                assert (out == want).all(), (K, rv, sb)
+    for K, E in ((40, 500), (6144, 30000), (1024, 1000), (5824, 6918)):
+        ci = port.cbindex(K)
+        for rv in range(4):
+            e = random_llr(rng, E, 32767, np.int16)
+            a = random_llr(rng, 18600, 32767, np.int16)
+            b = a.copy()
+            ref.rm_rx16(e, a, ci, rv, True)
+            port.rm_rx16(e, b, K, rv, port.subblocks16(K))
+            assert (a == b).all()
+            e = random_llr(rng, E, 127, np.int8)
+            a = random_llr(rng, 18600 * 2, 127, np.int8)
+            b = a.copy()
+            ref.rm_rx8(e, a, ci, rv)
+            port.rm_rx8(e, b, K, rv, port.subblocks8(K))
+            assert (a == b).all()
+
+
+def test_rm_lut_equals_procedural_float(ref):
+    """what rm_turbo_test.c:171-190 checks (there only for cb_idx 0, rv 0): the LUT de-matcher in standard layout equals
+    the procedural float de-matcher exactly"""
+    rng = np.random.default_rng(3)
+    for ci in (0, 45, 77, 100, 187):
+        K = ref.cbsize(ci)
+        for rv in range(4):
+            for E in (1920, 8192, 3 * K + 12):
+                e = random_llr(rng, E, 100, np.int16)
+                out = np.zeros(18600, np.int16)
+                ref.rm_rx16(e, out, ci, rv, enable_sb=False)
+                f = ref.rm_rx_float(e.astype(np.float32), 3 * K + 12, rv)
+                f[f == 10000] = 0  # SRSLTE_RX_NULL marks positions that received nothing
+                assert (out[:3 * K + 12] == f.astype(np.int16)).all(), (ci, rv, E)
+
+
+def _tdec(port, ref, K, dtype, amp, nit, dec=TDEC_AUTO, fnsb=False, seed=0):
+    rng = np.random.default_rng(seed + K)
+    bits = 16 if dtype == np.int16 else 8
+    if dec == TDEC_AUTO:
+        N = port.subblocks16(K) if bits == 16 else port.subblocks8(K)
+        sb_in = N > 0 and not fnsb
+    else:
+        sb_in = False
+    n = 3 * (K + 32) + 12 if sb_in else 3 * K + 12
+    a = aligned_zeros(18600 * (2 if bits == 8 else 1), dtype)
+    a[:n] = random_llr(rng, n, amp, dtype)
+    b = a.copy()
+    hr, hp = ref.tdec_new(dec, fnsb), port.tdec_new(dec, fnsb)
+    assert ref.tdec_new_cb(hr, K) == 0 and port.tdec_new_cb(hp, K) == 0
+    for it in range(nit):
+        o1, o2 = ref.tdec_iteration(hr, a, K), port.tdec_iteration(hp, b, K)
+        for w in ((2,) if it % 2 == 0 else (0, 2)):
+            assert (ref.tdec_get_llr(hr, w, K) == port.tdec_get_llr(hp, w, K)).all(), (K, bits, amp, it, w)
+        assert (o1 == o2).all(), (K, bits, amp, it)
+    ref.tdec_del(hr)
+    port.tdec_del(hp)
+
+
+@pytest.mark.parametrize("case", [(6144, 16, 300, 4), (6144, 16, 30000, 6), (816, 16, 5000, 6), (512, 16, 20000, 6), (408, 16, 300, 5), (800, 16, 32767, 4),
+                                  (5824, 16, 2000, 10), (6144, 8, 60, 6), (6144, 8, 127, 6), (2112, 8, 100, 5), (816, 8, 127, 6), (2048, 8, 90, 6),
+                                  (1008, 8, 127, 4), (5824, 8, 50, 10), (40, 16, 100, 6), (400, 16, 300, 6), (400, 16, 20000, 6), (200, 16, 32767, 5),
+                                  (104, 16, 1000, 10), (40, 8, 100, 4), (400, 8, 127, 6), (408, 8, 127, 4), (512, 8, 60, 6), (800, 8, 127, 5)])
+def test_decoder_llr_exact(port, ref, case):
+    K, bits, amp, nit = case
+    _tdec(port, ref, K, np.int16 if bits == 16 else np.int8, amp, nit)
+
+
+@pytest.mark.parametrize("K,dec,fnsb", [(6144, TDEC_AVX_WINDOW, True), (504, TDEC_SSE_WINDOW, True), (504, TDEC_GENERIC, True), (6144, TDEC_GENERIC, False),
+                                        (1024, TDEC_SSE_WINDOW, False), (6144, TDEC_AVX8_WINDOW, True), (1024, TDEC_SSE8_WINDOW, True), (504, TDEC_AUTO, True),
+                                        (6144, TDEC_AUTO, True), (40, TDEC_AUTO, True)])
+def test_decoder_manual_and_force_not_sb(port, ref, K, dec, fnsb):
+    _tdec(port, ref, K, np.int16, 400, 4, dec, fnsb)
+
+
+def test_encoder_chain(port, ref):
+    rng = np.random.default_rng(7)
+    for K in (40, 504, 6144, 1024):
+        b = rng.integers(0, 2, K, dtype=np.uint8)
+        assert (port.tcod_encode(b) == ref.tcod_encode(b)).all()
+    s = ref.sch_new(False, 8, 100)
+    for tbs, Qm, G in ((75376, 6, 90000), (97896, 8, 115200), (6120, 2, 14400), (15264, 4, 20000)):
+        for rv in range(4):
+            d = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+            ref.sch_encode(s, tbs, Qm, G, 0, d)
+            assert (ref.sch_encode(s, tbs, Qm, G, rv, d) == port.encode_tb(tbs, Qm, rv, G, d)).all(), (tbs, rv)
+    ref.sch_del(s)
+
+
+@pytest.mark.parametrize("tbs,Qm,G,is8,amp,sigma,mi,rvs", [
+    (75376, 6, 90000, False, 100, 0.0, 8, (0,)), (75376, 6, 90000, False, 100, 0.46, 8, (0,)), (75376, 6, 90000, False, 100, 0.95, 8, (0, 2, 3, 1)),
+    (97896, 8, 115200, True, 20, 0.42, 8, (0,)), (97896, 8, 115200, True, 20, 0.8, 8, (0, 2)), (6120, 2, 14400, False, 50, 0.9, 8, (0,)),
+    (296, 2, 1200, True, 30, 0.5, 8, (0,)), (15264, 4, 20000, False, 200, 0.7, 10, (0, 1))])
+def test_transport_block_through_real_sch(port, ref, tbs, Qm, G, is8, amp, sigma, mi, rvs):
+    """decode_tb / decode_tb_cb restated vs the reference's real srslte_dlsch_decode2 (sch.c), incl. HARQ combining"""
+    rng = np.random.default_rng(tbs + G)
+    s, sb = ref.sch_new(is8, mi, 100), port.softbuffer_new()
+    ref.sch_reset_rx(s, tbs)
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    for rv in rvs:
+        ref.sch_encode(s, tbs, Qm, G, 0, data)
+        e = ref.sch_encode(s, tbs, Qm, G, rv, data)
+        llr = bpsk_awgn_llr(rng, e, amp, sigma, np.int8 if is8 else np.int16)
+        rc1, d1, avg1, crc1 = ref.sch_decode(s, tbs, Qm, rv, llr)
+        rc2, d2, nit, avg2, crc2 = port.decode_tb(sb, tbs, Qm, rv, llr, mi)
+        n = tbs // 8 + 3
+        assert rc1 == rc2 and (d1[:n] == d2[:n]).all() and abs(avg1 - avg2) < 1e-6 and (crc1 == crc2).all(), (tbs, rv)
+        if rc1 == 0:
+            assert (d1[:tbs // 8] == data).all()
+            break
+    ref.sch_del(s)
+    port.softbuffer_del(sb)
+
+
+def test_known_vector_vs_reference_encoder(ref):
+    """the reference's known_data_encoded fixture vs the reference's own encoder: one tail bit (index 1512) differs"""
+    import os
+    k = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat.npz"))
+    got = ref.tcod_encode(k["known_data"])
+    assert np.nonzero(got != k["known_data_encoded"])[0].tolist() == [1512]
