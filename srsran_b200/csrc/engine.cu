@@ -288,7 +288,7 @@ static cudaError_t launch_map(MapArgs a, int n_slots, int max_w, cudaStream_t st
   a.ck_slots = (max_w + L - 1) / L + 1;
   // shared memory: double-buffered staging of 4 rows (in, parity, a-priori, QPP table) x L steps + one 8-word
   // checkpoint, per thread
-  const size_t smem = (size_t)NT * 2 * (L * 4 + 8) * 4;
+  const size_t smem = (size_t)NT * 3 * (L * 4 + 8) * 4; // StagedSrc::kStages buffers
   auto         kern = k_map_win<P, N, L, NT>;
   cudaError_t  e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)

@@ -330,82 +330,85 @@ struct MapArgs {
 // block per SM the scratch in flight is a few tens of MB, i.e. L2-resident; shared memory then only holds the
 // double-buffered staging area (2 x (3L + 8) words per thread), which is what lets more warps share an SM.
 //
-// staging layout per buffer: rows: word (i, a) at stage[(i*4 + a) * NT] with a = in, parity, a-priori, QPP table;
-// checkpoint: 8 words at ckst[0..7]
+// staging layout: kStages buffers; per buffer: rows: word (i, a) at (i*4 + a) * NT with a = in, parity, a-priori, QPP
+// table; then per thread 8 checkpoint words.  Chunk c uses buffer c % kStages and is requested kAhead chunks early.
 template <int L, int NT, int T>
 struct StagedSrc {
+  static constexpr int kAhead  = 2;
+  static constexpr int kStages = 3;
+  static constexpr int kRowWords = L * 4 * NT;              // words of row staging per buffer
+  static constexpr int kBufWords = kRowWords + 8 * NT;      // + checkpoint staging
   const u32 *in, *apr, *par, *lut;
   int        j;
-  u32*       stage; // smem + threadIdx.x                   (rows, 2 buffers of L*4*NT words)
-  u32*       ckst;  // smem + 2*L*4*NT + threadIdx.x*8      (checkpoints, 2 buffers of NT*8 words)
-  u32*       ckg;   // global scratch of this thread: slot s at ckg[s * ck_stride .. +8)
+  u32*       stage;  // smem base (generic pointer), already offset by threadIdx.x for rows
+  unsigned   stage_s; // the same as a shared-window address
+  u32*       ckg;    // global scratch of this thread: slot s at ckg[s * ck_stride .. +8)
   size_t     ck_stride;
-  __device__ __forceinline__ static void cp4(u32* dst_smem, const u32* src)
+  __device__ __forceinline__ static void cp4(unsigned dst_s, const u32* src)
   {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst_s), "l"(src) : "memory");
   }
-  __device__ __forceinline__ static void cp16(u32* dst_smem, const u32* src)
+  __device__ __forceinline__ static void cp16(unsigned dst_s, const u32* src)
   {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_s), "l"(src) : "memory");
   }
+  __device__ __forceinline__ unsigned row_s(int buf, int i, int a) const { return stage_s + 4u * (unsigned)(buf * kBufWords + (i * 4 + a) * NT); }
+  __device__ __forceinline__ const u32* row_p(int buf) const { return stage + buf * kBufWords; }
+  // checkpoint words of this thread in buffer buf: after the rows, 8 consecutive words per thread
+  __device__ __forceinline__ int ck_word(int buf) const { return buf * kBufWords + kRowWords + 7 * (int)threadIdx.x; }
   __device__ __forceinline__ void prefetch(int c, int p0, int lo, int hi, int ck_slot)
   {
-    u32*            b    = stage + (size_t)(c & 1) * L * 4 * NT;
+    const int       buf  = c % kStages;
     const ptrdiff_t row0 = (ptrdiff_t)p0 * T + j;
     const u32 *     gi = in + row0, *gp = par + row0, *ga = apr + row0, *gl = lut + row0;
     const bool      full = p0 >= lo && p0 + L <= hi;
     if (full) { // interior chunk: constant offsets only
 #pragma unroll
       for (int i = 0; i < L; i++) {
-        cp4(b + (i * 4 + 0) * NT, gi + i * T);
-        cp4(b + (i * 4 + 1) * NT, gp + i * T);
+        cp4(row_s(buf, i, 0), gi + i * T);
+        cp4(row_s(buf, i, 1), gp + i * T);
       }
       if (apr) {
 #pragma unroll
         for (int i = 0; i < L; i++)
-          cp4(b + (i * 4 + 2) * NT, ga + i * T);
+          cp4(row_s(buf, i, 2), ga + i * T);
       }
       if (ck_slot >= 0) {
 #pragma unroll
         for (int i = 0; i < L; i++)
-          cp4(b + (i * 4 + 3) * NT, gl + i * T);
+          cp4(row_s(buf, i, 3), gl + i * T);
       }
     } else {
 #pragma unroll
       for (int i = 0; i < L; i++) {
         const int p = p0 + i;
         if (p >= lo && p < hi) {
-          cp4(b + (i * 4 + 0) * NT, gi + i * T);
-          cp4(b + (i * 4 + 1) * NT, gp + i * T);
+          cp4(row_s(buf, i, 0), gi + i * T);
+          cp4(row_s(buf, i, 1), gp + i * T);
           if (apr)
-            cp4(b + (i * 4 + 2) * NT, ga + i * T);
+            cp4(row_s(buf, i, 2), ga + i * T);
           if (ck_slot >= 0)
-            cp4(b + (i * 4 + 3) * NT, gl + i * T);
+            cp4(row_s(buf, i, 3), gl + i * T);
         }
       }
     }
     if (ck_slot >= 0) {
-      u32*       d = ckst + (size_t)(c & 1) * NT * 8;
-      const u32* g = ckg + (size_t)ck_slot * ck_stride;
+      const unsigned d = stage_s + 4u * (unsigned)ck_word(buf);
+      const u32*     g = ckg + (size_t)ck_slot * ck_stride;
       cp16(d, g);
-      cp16(d + 4, g + 4);
+      cp16(d + 16, g + 4);
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   }
   __device__ __forceinline__ void prefetch_none() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-  // the group of chunk c+1 was committed right before: everything older than the newest group must have landed
-  __device__ __forceinline__ void wait(int) { asm volatile("cp.async.wait_group 1;\n" ::: "memory"); }
+  // kAhead newer groups were committed after chunk c's: everything older must have landed
+  __device__ __forceinline__ void wait(int) { asm volatile("cp.async.wait_group 2;\n" ::: "memory"); }
   __device__ __forceinline__ void drain() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
-  __device__ __forceinline__ u32 get_apr(int c, int i, int) const
-  {
-    return apr ? stage[((size_t)(c & 1) * L * 4 + i * 4 + 2) * NT] : 0u;
-  }
-  __device__ __forceinline__ u32 get_lut(int c, int i, int) const { return stage[((size_t)(c & 1) * L * 4 + i * 4 + 3) * NT]; }
+  __device__ __forceinline__ u32 get_apr(int c, int i, int) const { return apr ? row_p(c % kStages)[(i * 4 + 2) * NT] : 0u; }
+  __device__ __forceinline__ u32 get_lut(int c, int i, int) const { return row_p(c % kStages)[(i * 4 + 3) * NT]; }
   __device__ __forceinline__ void get(int c, int i, int, u32& vin, u32& vapr, u32& vpar) const
   {
-    const u32* b = stage + (size_t)(c & 1) * L * 4 * NT;
+    const u32* b = row_p(c % kStages);
     vin          = b[(i * 4 + 0) * NT];
     vpar         = b[(i * 4 + 1) * NT];
     vapr         = apr ? b[(i * 4 + 2) * NT] : 0u;
@@ -418,7 +421,8 @@ struct StagedSrc {
   }
   __device__ __forceinline__ void ck_get(int c, int, u32 (&st)[8]) const
   {
-    const uint4* d = reinterpret_cast<const uint4*>(ckst + (size_t)(c & 1) * NT * 8);
+    // (stage is offset by threadIdx.x already: ck_word uses 7*tid so that stage + ck_word = base + ... + 8*tid)
+    const uint4* d = reinterpret_cast<const uint4*>(stage + ck_word(c % kStages));
     const uint4  a = d[0], b = d[1];
     st[0] = a.x; st[1] = a.y; st[2] = a.z; st[3] = a.w;
     st[4] = b.x; st[5] = b.y; st[6] = b.z; st[7] = b.w;
@@ -497,8 +501,8 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   MapWin<P, L, StagedSrc<L, NT, T>> m;
   m.W       = d.W;
   m.src.j   = j;
-  m.src.stage = smem_ck + threadIdx.x;
-  m.src.ckst  = smem_ck + (size_t)2 * L * 4 * NT + (size_t)threadIdx.x * 8;
+  m.src.stage   = smem_ck + threadIdx.x;
+  m.src.stage_s = (unsigned)__cvta_generic_to_shared(smem_ck + threadIdx.x);
   // global checkpoint scratch: slot-major, 8 words per thread, threads of the whole grid contiguous
   m.src.ck_stride = (size_t)gridDim.x * NT * 8;
   m.src.ckg       = a.ck_scratch + ((size_t)blockIdx.x * NT + threadIdx.x) * 8;

@@ -147,6 +147,7 @@ B200_HD bool fast16_alpha_ok(int32_t sp_a, int32_t sp_b, int32_t g)
 //   get(c, i, p, ...)        raw words of row p = p0 + i of chunk c
 // DirectSrc reads global memory at the point of use (host emulation, reference for the staged source).
 struct DirectSrc {
+  static constexpr int kAhead = 1;
   const u32 *in, *apr, *par;
   int        T, j;
   u32*       ck;  // checkpoint store of this thread: 8 words per slot
@@ -232,7 +233,7 @@ struct MapWin {
   // lowest chunk of a pass, odd W, the warm-up passes) runs the guarded variant; both compute the same values.
   B200_HD void begin_chunk(int c)
   {
-    prefetch_chunk(c + 1); // overlap the next chunk's memory traffic with this chunk's arithmetic
+    prefetch_chunk(c + Src::kAhead); // keep kAhead chunks of memory traffic in flight behind the arithmetic
     src.wait(c);
   }
   B200_HD void row(int c, int i, int p, u32& x, u32& y) const
@@ -246,7 +247,8 @@ struct MapWin {
   {
     mon_b.reset();
     mon_a.reset();
-    prefetch_chunk(0);
+    for (int c = 0; c < Src::kAhead; c++)
+      prefetch_chunk(c);
   }
   B200_HD bool interior(int p0, int min_p) const { return (L % 2 == 0) && p0 >= min_p && (p0 & 1) == 0 && p0 > 0; }
 
