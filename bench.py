@@ -112,6 +112,8 @@ def dist_setup(n_gpus, backend=None):
     import torch
     import torch.distributed as dist
     backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     if backend == "nccl":

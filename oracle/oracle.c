@@ -820,7 +820,7 @@ void orc_softbuffer_get_crc(void* ss, uint8_t* cb_crc, uint32_t n)
 void orc_map_win(int bits, uint32_t N, const int16_t* in, const int16_t* app, const int16_t* par, int16_t* out, uint32_t K)
 {
   orc_cfg_t c = mk_cfg(bits, N);
-  int32_t * i32 = malloc((K + 3) * 4), *a32 = app ? malloc((K + 3) * 4) : NULL, *p32 = malloc((K + 3) * 4), *o32 = malloc((K + 3) * 4);
+  int32_t * i32 = calloc(K + 3, 4), *a32 = app ? calloc(K + 3, 4) : NULL, *p32 = calloc(K + 3, 4), *o32 = calloc(K + 3, 4);
   for (uint32_t i = 0; i < K + 3; i++) {
     i32[i] = in[i];
     p32[i] = par[i];

@@ -50,6 +50,35 @@ static void crc24_table(uint32_t poly, uint32_t* tab)
   }
 }
 
+// x^(8*cb*2^l) mod g for l = 0..4, cb = ceil(nbytes/32): constants of the warp-parallel CRC (kernels.cuh warp_crc24)
+static uint32_t crc24_mulmod_host(uint32_t a, uint32_t b, uint32_t poly)
+{
+  uint32_t r = 0;
+  for (int i = 23; i >= 0; i--) {
+    r <<= 1;
+    if (r & 0x1000000u)
+      r ^= poly;
+    if ((b >> i) & 1u)
+      r ^= a;
+  }
+  return r & 0xffffffu;
+}
+static void crc24_xpows(uint32_t nbytes, uint32_t poly, uint32_t out[5])
+{
+  const uint32_t cb = (nbytes + 31) / 32;
+  uint32_t       xp = 1;
+  for (uint32_t q = 0; q < 8 * cb; q++) { // multiply by x, 8*cb times
+    xp <<= 1;
+    if (xp & 0x1000000u)
+      xp ^= poly;
+  }
+  xp &= 0xffffffu;
+  for (int l = 0; l < 5; l++) {
+    out[l] = xp;
+    xp     = crc24_mulmod_host(xp, xp, poly);
+  }
+}
+
 template <typename T>
 int DevBuf<T>::reserve(size_t n)
 {
@@ -412,9 +441,10 @@ int Engine::run(Plan& p)
     CUDA_OK(cudaMemcpyAsync(d_tbs.ptr, hp, p.tbs.size() * sizeof(TbDev), cudaMemcpyHostToDevice, stream));
   }
 
-  if (d_counters.reserve(4) || h_counters.reserve(4))
+  const size_t n_counters = 4 + (size_t)p.max_iter + 1;
+  if (d_counters.reserve(n_counters) || h_counters.reserve(4))
     return SRSLTE_B200_ERROR;
-  CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, 16, stream));
+  CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, n_counters * sizeof(uint32_t), stream));
   CUDA_OK(cudaEventRecord(ev_begin, stream));
 
   // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
@@ -463,7 +493,7 @@ int Engine::run(Plan& p)
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots)
         continue;
-      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0};
+      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0, d_counters.ptr, (int)it};
       cudaEvent_t e0, e1;
       if (map_event_pair(&e0, &e1))
         return SRSLTE_B200_ERROR;
@@ -495,7 +525,7 @@ int Engine::run(Plan& p)
       CUDA_OK(cudaGetLastError());
       last_launches++;
     }
-    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr};
+    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
     k_decide_crc<<<((int)active.size() + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
@@ -504,7 +534,7 @@ int Engine::run(Plan& p)
   // ---- transport block assembly + CRC24A + HARQ bookkeeping
   if (!p.tbs.empty()) {
     TbArgs ta{d_tbs.ptr, (int)p.tbs.size(), d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr};
-    k_tb_finish<<<((int)p.tbs.size() + 3) / 4, 128, 0, stream>>>(ta);
+    k_tb_finish<<<(int)p.tbs.size(), kTbThreads, 0, stream>>>(ta);
     CUDA_OK(cudaGetLastError());
     last_launches++;
   }
@@ -737,6 +767,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     u.nof_cb  = s.C;
 
     const uint32_t Gp = u.nof_e_bits / u.Qm, gamma = Gp % s.C, n_e = u.Qm * (Gp / s.C);
+    uint32_t       xp_cache[5];
+    crc24_xpows(u.tbs / 8, kCrc24A, td.crc_xp);
     for (uint32_t c = 0; c < s.C; c++) {
       const uint32_t K = c < s.C1 ? s.K1 : s.K2;
       DecSel         sel;
@@ -748,6 +780,9 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
       fill_geometry(&d, K, sel);
       d.max_iter = max_iterations;
       d.crc_poly = s.C > 1 ? kCrc24B : kCrc24A;
+      if (c == 0 || K != (c - 1 < s.C1 ? s.K1 : s.K2))
+        crc24_xpows(K / 8, d.crc_poly, xp_cache);
+      memcpy(d.crc_xp, xp_cache, sizeof(xp_cache));
       d.in_bits  = is8 ? 8 : 16;
       d.dematch  = 1;
       d.tb       = (uint32_t)plan.tbs.size();

@@ -28,6 +28,7 @@ struct CbDev {
   uint32_t crc_poly; // early-stop CRC polynomial (24 bit), 0 = no CRC (run_all semantics)
   uint32_t out_off;  // byte offset of this CB's K/8 decided bytes in the CB output pool
   uint32_t sat_end;  // 8-bit glue: elements below this index use the saturating subtract
+  uint32_t crc_xp[5]; // CRC chunk-combination constants for K/8 bytes under crc_poly (warp_crc24)
   // input description for k_prepare / k_dematch
   void*       in_ptr; // decoder input: HARQ soft buffer of this CB, or the caller's LLRs (device memory)
   const void* e_ptr;  // rate-matched e-bits of this CB (device memory), dematch only
@@ -61,6 +62,7 @@ struct TbDev {
   uint8_t* data;       // TB output bytes (device memory), >= tbs/8 + 6
   uint8_t* hdata;      // HARQ saved-CB area (C x 768 bytes) or nullptr
   uint8_t* hcrc;       // HARQ cb_crc flags (C bytes) or nullptr
+  uint32_t crc_xp[5];  // CRC24A chunk-combination constants for tbs/8 bytes
 };
 
 struct TbResult {
@@ -238,8 +240,10 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     state[cb].n_redo = 0;
   }
   if (d.fresh) {
-    for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
-      sb[i] = 0;
+    uint4*         z  = reinterpret_cast<uint4*>(s_raw);
+    const uint32_t nz = (n_sb * sizeof(T) + 15) / 16;
+    for (uint32_t i = threadIdx.x; i < nz; i += blockDim.x)
+      z[i] = make_uint4(0, 0, 0, 0);
   } else {
     for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
       sb[i] = gsb[i];
@@ -247,15 +251,35 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
   __syncthreads();
   const T*        in  = (const T*)d.e_ptr;
   const uint16_t* tab = rm_pool + d.rm_off;
-  for (uint32_t i = threadIdx.x; i < L && i < d.E; i += blockDim.x) {
-    uint32_t acc = 0;
-    for (uint32_t r = i; r < d.E; r += L)
-      acc += (uint32_t)(int32_t)in[r];
-    uint32_t pos = i + d.rm_start;
-    if (pos >= L)
-      pos -= L;
-    const uint16_t o = tab[pos];
-    sb[o]            = (T)(uint32_t)((uint32_t)(int32_t)sb[o] + acc); // wraps in the width of the soft buffer
+  const uint32_t  n_i = d.E < L ? d.E : L;
+  // eight independent elements per thread and trip; all their global loads are issued before the first use
+  constexpr int kU = 8;
+  for (uint32_t i0 = threadIdx.x; i0 < n_i; i0 += kU * blockDim.x) {
+    int32_t  v[kU];
+    uint16_t o[kU];
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint32_t i = i0 + u * blockDim.x;
+      v[u]             = i < n_i ? (int32_t)in[i] : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint32_t i   = i0 + u * blockDim.x;
+      uint32_t       pos = i + d.rm_start;
+      if (pos >= L)
+        pos -= L;
+      o[u] = i < n_i ? tab[pos] : (uint16_t)0;
+    }
+#pragma unroll
+    for (int u = 0; u < kU; u++) {
+      const uint32_t i = i0 + u * blockDim.x;
+      if (i < n_i) {
+        uint32_t acc = (uint32_t)v[u];
+        for (uint32_t r = i + L; r < d.E; r += L) // repetitions (E > 3K+12): same soft bit received again
+          acc += (uint32_t)(int32_t)in[r];
+        sb[o[u]] = (T)(uint32_t)((uint32_t)(int32_t)sb[o[u]] + acc); // wraps in the width of the soft buffer
+      }
+    }
   }
   __syncthreads();
   if (!d.fresh) {
@@ -270,15 +294,35 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     u32* q0 = reinterpret_cast<u32*>(p0);
     u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
     u32* q2 = reinterpret_cast<u32*>(p0 + 2 * (size_t)d.ps);
-    for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
-      const uint32_t j  = 2 * h;
-      const int32_t  a0 = sb[j], a1 = sb[j + 1], b0 = sb[K + kSbPadDev + j], b1 = sb[K + kSbPadDev + j + 1];
-      const int32_t  c0 = sb[2 * (K + kSbPadDev) + j], c1 = sb[2 * (K + kSbPadDev) + j + 1];
-      q0[h] = pack16(a0, a1);
-      q1[h] = pack16(b0, b1);
-      q2[h] = pack16(c0, c1);
-      amax(g0, a0); amax(g1, b0); amax(g2, c0);
-      amax(g0, a1); amax(g1, b1); amax(g2, c1);
+    if (sizeof(T) == 2) {
+      // int16 soft buffer: the planes are already pairs of adjacent lanes, copy them as 32-bit words
+      const u32* s0 = reinterpret_cast<const u32*>(sb);
+      const u32* s1 = reinterpret_cast<const u32*>(sb + (K + kSbPadDev));
+      const u32* s2 = reinterpret_cast<const u32*>(sb + 2 * (K + kSbPadDev));
+      u32        h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
+      for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
+        const u32 a = s0[h], b = s1[h], c = s2[h];
+        q0[h] = a;
+        q1[h] = b;
+        q2[h] = c;
+        h0 = p_max(h0, a); l0 = p_min(l0, a);
+        h1 = p_max(h1, b); l1 = p_min(l1, b);
+        h2 = p_max(h2, c); l2 = p_min(l2, c);
+      }
+      g0 = max(max(lo16(h0), hi16(h0)), max(-lo16(l0), -hi16(l0)));
+      g1 = max(max(lo16(h1), hi16(h1)), max(-lo16(l1), -hi16(l1)));
+      g2 = max(max(lo16(h2), hi16(h2)), max(-lo16(l2), -hi16(l2)));
+    } else {
+      for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
+        const uint32_t j  = 2 * h;
+        const int32_t  a0 = sb[j], a1 = sb[j + 1], b0 = sb[K + kSbPadDev + j], b1 = sb[K + kSbPadDev + j + 1];
+        const int32_t  c0 = sb[2 * (K + kSbPadDev) + j], c1 = sb[2 * (K + kSbPadDev) + j + 1];
+        q0[h] = pack16(a0, a1);
+        q1[h] = pack16(b0, b1);
+        q2[h] = pack16(c0, c1);
+        amax(g0, a0); amax(g1, b0); amax(g2, c0);
+        amax(g0, a1); amax(g1, b1); amax(g2, c1);
+      }
     }
   } else {
     for (uint32_t n = threadIdx.x; n < K; n += blockDim.x) {
@@ -319,6 +363,8 @@ struct MapArgs {
   int             mode; // 0: decode every active CB; 1: Fast16 attempt (flags redo); 2: replay only CBs flagged redo
   u32*            ck_scratch; // global beta-checkpoint scratch: ck_slots x (grid threads) x 8 words
   int             ck_slots;
+  const uint32_t* counters; // DecideArgs::counters
+  int             iter;     // half-iteration index of this launch within the batch
 };
 
 // Row source staged through shared memory with cp.async (LDGSTS): chunk c+1 streams in while chunk c is being
@@ -478,6 +524,8 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   constexpr int G = 32 / T; // code blocks per warp
   extern __shared__ __align__(16) u32 smem_ck[];
 
+  if (a.iter > 0 && a.counters[4 + a.iter - 1] == 0)
+    return; // nothing left to decode in this batch
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * (NT / 32) + (threadIdx.x >> 5)) * G + lane / T;
   const int j    = lane % T;
@@ -756,8 +804,12 @@ __device__ __forceinline__ uint32_t crc24_mulmod(uint32_t a, uint32_t b, uint32_
 // recurrence (crc.h:56-63) over one chunk; chunks are combined with crc(A||B) = crc(A) x^(8|B|) + crc(B) mod g.
 // The message is virtually left-padded with zero bytes to 32 equal chunks (leading zeros do not change a
 // zero-initialised CRC), so the result equals the serial recurrence bit for bit.
+// tab: 256-entry byte table of the polynomial in SHARED memory (lanes index it divergently, which constant memory
+// would serialise)
+// xpow[l] = x^(8*cb*2^l) mod g, cb = ceil(nbytes/32): chunk-combination constants precomputed on the host
+// (crc24_xpows in engine.cu), so the warp runs 5 modular multiplications instead of 10
 template <class GetByte>
-__device__ __forceinline__ uint32_t warp_crc24(uint32_t nbytes, int tab, uint32_t poly, GetByte get_byte)
+__device__ __forceinline__ uint32_t warp_crc24(uint32_t nbytes, const uint32_t* tab, uint32_t poly, const uint32_t* xpow, GetByte get_byte)
 {
   const int      lane = threadIdx.x & 31;
   const uint32_t cb   = (nbytes + 31) / 32, pad = 32 * cb - nbytes;
@@ -766,21 +818,24 @@ __device__ __forceinline__ uint32_t warp_crc24(uint32_t nbytes, int tab, uint32_
     const uint32_t pos = lane * cb + q;
     if (pos >= pad) {
       const uint32_t byte = get_byte(pos - pad);
-      crc                 = ((crc << 8) ^ c_crc_tab[tab][((crc >> 16) & 0xffu) ^ byte]) & 0xffffffu;
+      crc                 = ((crc << 8) ^ tab[((crc >> 16) & 0xffu) ^ byte]) & 0xffffffu;
     }
   }
-  // x^(8*cb) mod g
-  uint32_t xp = 1;
-  for (uint32_t q = 0; q < cb; q++)
-    xp = ((xp << 8) ^ c_crc_tab[tab][(xp >> 16) & 0xffu]) & 0xffffffu;
 #pragma unroll
-  for (int l = 1; l < 32; l <<= 1) {
+  for (int lv = 0; lv < 5; lv++) {
+    const int      l     = 1 << lv;
     const uint32_t other = __shfl_down_sync(0xffffffffu, crc, l); // chunk(s) to the right
     if ((lane & (2 * l - 1)) == 0)
-      crc = crc24_mulmod(crc, xp, poly) ^ other;
-    xp = crc24_mulmod(xp, xp, poly);
+      crc = crc24_mulmod(crc, xpow[lv], poly) ^ other;
   }
   return __shfl_sync(0xffffffffu, crc, 0);
+}
+
+// copies both CRC24 byte tables from constant to shared memory (call with all threads of the block, then sync)
+__device__ __forceinline__ void load_crc_tables(uint32_t (*s_tab)[256])
+{
+  for (int i = threadIdx.x; i < 512; i += blockDim.x)
+    s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
 }
 
 struct DecideArgs {
@@ -790,7 +845,9 @@ struct DecideArgs {
   CbState*       state;
   const int16_t* ws;
   uint8_t*       cb_out;
-  uint32_t*      counters; // [0]: half-iterations replayed with the exact policy, [1]: half-iterations run
+  uint32_t*      counters; // [0]: half-iterations replayed with the exact policy, [1]: half-iterations run,
+                           // [4 + t]: code blocks still undecided after half-iteration t of this batch
+  int            iter;     // half-iteration index t of this launch within the batch
 };
 
 // One warp per code block.  Hard decisions (win.h:925-993 / gen.c:260-277): the a-posteriori LLRs sit in lane
@@ -803,15 +860,27 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
 {
   __shared__ u32 s_bits[kDecideWarps][6144 / 32 + 64]; // bit rows: lane d at word d * wpr
   __shared__ u32 s_bytes[kDecideWarps][6144 / 32];     // decided bytes, 4 per word
+  __shared__ uint32_t s_tab[2][256];
+  if (a.iter > 0 && a.counters[4 + a.iter - 1] == 0)
+    return; // every code block of the batch was finished by an earlier half-iteration
   const int wib = threadIdx.x >> 5;
   const int w   = blockIdx.x * kDecideWarps + wib;
-  if (w >= a.n)
-    return;
-  const int   cb = a.list[w];
-  const CbDev d  = a.cbs[cb];
-  CbState*    s  = &a.state[cb];
-  const uint32_t n_iter0 = s->n_iter, done0 = s->done;
-  if (done0 || n_iter0 >= d.max_iter)
+  const int cb  = w < a.n ? a.list[w] : -1;
+  CbDev     d;
+  CbState*  s = nullptr;
+  uint32_t  n_iter0 = 0;
+  bool      active = false;
+  if (cb >= 0) {
+    d       = a.cbs[cb];
+    s       = &a.state[cb];
+    n_iter0 = s->n_iter;
+    active  = !(s->done || n_iter0 >= d.max_iter);
+  }
+  if (!__syncthreads_or(active))
+    return; // none of this block's code blocks is still being decoded
+  load_crc_tables(s_tab);
+  __syncthreads();
+  if (!active)
     return;
   const uint32_t n_iter = n_iter0 + 1; // the half-iteration that just ran
   const int      lane   = threadIdx.x & 31;
@@ -879,11 +948,13 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
     }
     if (d.crc_poly != 0) {
       const bool is_a = d.crc_poly == kCrc24A;
-      crc = warp_crc24(nbytes, is_a ? 0 : 1, is_a ? kCrc24A : kCrc24B, [&](uint32_t b) -> uint32_t { return ob8[b]; });
+      crc = warp_crc24(nbytes, s_tab[is_a ? 0 : 1], is_a ? kCrc24A : kCrc24B, d.crc_xp, [&](uint32_t b) -> uint32_t { return ob8[b]; });
     }
   }
   if (lane == 0) {
     s->n_iter = n_iter;
+    if (!(d.crc_poly != 0 && crc == 0) && n_iter < d.max_iter)
+      atomicAdd(&a.counters[4 + a.iter], 1u);
     atomicAdd(&a.counters[1], 1u);
     if (s->redo) {
       s->redo = 0;
@@ -908,82 +979,102 @@ struct TbArgs {
   TbResult*      res;
 };
 
-// one warp per transport block: assemble payload (sch.c:390,422-424,462-467), TB CRC24A (sch.c:546-552),
-// HARQ bookkeeping (sch.c:469-484)
-__global__ void __launch_bounds__(128) k_tb_finish(const TbArgs a)
+// One CTA per transport block: assemble the payload (sch.c:390,422-424,462-467), TB CRC24A (sch.c:546-552), HARQ
+// bookkeeping (sch.c:469-484).  All threads copy; warp 0 computes the CRC over the assembled bytes.
+constexpr int kTbThreads = 256;
+__global__ void __launch_bounds__(kTbThreads) k_tb_finish(const TbArgs a)
 {
-  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (w >= a.n_tb)
-    return;
-  const int   lane = threadIdx.x & 31;
+  __shared__ uint32_t s_tab[2][256];
+  __shared__ uint32_t s_ok, s_iter;
+  const int   w    = blockIdx.x;
+  const int   tid  = threadIdx.x;
   const TbDev t    = a.tbs[w];
   uint8_t*    data = t.data;
   uint8_t*    hdat = t.hdata;
   uint8_t*    hcrc = t.hcrc;
-  uint32_t    ok_mask = 0, sum_iter = 0;
-  // data[tbs/8 .. +2] = 0 happens before the CB loop in the reference; CB payload copies follow in CB order
-  if (lane < 3)
-    data[t.tbs / 8 + lane] = 0;
-  __syncwarp();
+  load_crc_tables(s_tab);
+  if (tid == 0) {
+    uint32_t ok = 0, it = 0;
+    for (uint32_t c = 0; c < t.C; c++) {
+      const uint32_t cb = t.first_cb + c;
+      if (a.cbs[cb].skip) {
+        ok |= 1u << c;
+      } else {
+        const CbState s = a.state[cb];
+        if (s.crc_ok)
+          ok |= 1u << c;
+        it += s.n_iter;
+      }
+    }
+    s_ok   = ok;
+    s_iter = it;
+  }
+  // data[tbs/8 .. +2] = 0 happens before the CB loop in the reference; the payload copies below overwrite it
+  if (tid < 3)
+    data[t.tbs / 8 + tid] = 0;
+  __syncthreads();
+  const uint32_t ok_mask = s_ok;
   for (uint32_t c = 0; c < t.C; c++) {
     const uint32_t cb   = t.first_cb + c;
     const CbDev    d    = a.cbs[cb];
     const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
     uint8_t*       dst  = data + (size_t)c * rlen;
     if (d.skip) {
-      for (uint32_t i = lane; i < rlen; i += 32)
+      for (uint32_t i = tid; i < rlen; i += kTbThreads)
         dst[i] = hdat[(size_t)c * 768 + i];
-      ok_mask |= 1u << c;
     } else {
-      const CbState  s   = a.state[cb];
       const uint8_t* src = a.cb_out + d.out_off;
       // the reference writes K/8 bytes per CB; all but the last CB's trailing CRC bytes are overwritten by the
       // next CB's copy, so write payload only, plus the 3 CRC bytes of the last CB
       const uint32_t nb = (c + 1 == t.C) ? d.K / 8 : rlen;
-      for (uint32_t i = lane; i < nb; i += 32)
+      for (uint32_t i = tid; i < nb; i += kTbThreads)
         dst[i] = src[i];
-      if (s.crc_ok)
-        ok_mask |= 1u << c;
-      sum_iter += s.n_iter;
     }
-    __syncwarp();
   }
+  __syncthreads();
   const bool all_ok = ok_mask == (t.C >= 32 ? 0xffffffffu : ((1u << t.C) - 1u));
   if (hcrc) {
-    for (uint32_t c = lane; c < t.C; c += 32)
+    for (uint32_t c = tid; c < t.C; c += kTbThreads)
       hcrc[c] = (ok_mask >> c) & 1u;
     if (!all_ok) {
       for (uint32_t c = 0; c < t.C; c++) {
         if (((ok_mask >> c) & 1u) && !a.cbs[t.first_cb + c].skip) {
           const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
-          for (uint32_t i = lane; i < rlen; i += 32)
+          for (uint32_t i = tid; i < rlen; i += kTbThreads)
             hdat[(size_t)c * 768 + i] = data[(size_t)c * rlen + i];
         }
       }
     }
   }
-  __syncwarp();
-  int32_t  ret    = -1;
-  uint32_t par_rx = 0;
-  if (all_ok) {
-    par_rx = warp_crc24(t.tbs / 8, 0, kCrc24A, [&](uint32_t b) -> uint32_t { return data[b]; });
-    const uint32_t o      = t.tbs / 8;
-    const uint32_t par_tx = ((uint32_t)data[o] << 16) | ((uint32_t)data[o + 1] << 8) | data[o + 2];
-    ret                   = (par_rx == par_tx && par_rx != 0) ? 0 : -1;
-  }
-  if (lane == 0) {
-    a.res[w].ret      = ret;
-    a.res[w].sum_iter = sum_iter;
-    a.res[w].cb_crc   = ok_mask;
-    a.res[w].par_rx   = par_rx;
+  if (tid < 32) {
+    int32_t  ret    = -1;
+    uint32_t par_rx = 0;
+    if (all_ok) {
+      par_rx = warp_crc24(t.tbs / 8, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return data[b]; });
+      const uint32_t o      = t.tbs / 8;
+      const uint32_t par_tx = ((uint32_t)data[o] << 16) | ((uint32_t)data[o + 1] << 8) | data[o + 2];
+      ret                   = (par_rx == par_tx && par_rx != 0) ? 0 : -1;
+    }
+    if (tid == 0) {
+      a.res[w].ret      = ret;
+      a.res[w].sum_iter = s_iter;
+      a.res[w].cb_crc   = ok_mask;
+      a.res[w].par_rx   = par_rx;
+    }
   }
 }
 
 // plain CRC of a byte buffer (device side of srslte_crc_checksum_byte); one warp, generic order <= 24 handled by
 // the host for orders other than 24
-__global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uint32_t poly, uint32_t* out)
+struct CrcXp {
+  uint32_t v[5];
+};
+__global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uint32_t poly, CrcXp xp, uint32_t* out)
 {
-  const uint32_t c = warp_crc24(nbytes, tab, poly, [&](uint32_t b) -> uint32_t { return data[b]; });
+  __shared__ uint32_t s_tab[2][256];
+  load_crc_tables(s_tab);
+  __syncthreads();
+  const uint32_t c = warp_crc24(nbytes, s_tab[tab], poly, xp.v, [&](uint32_t b) -> uint32_t { return data[b]; });
   if (threadIdx.x == 0)
     *out = c;
 }
