@@ -65,6 +65,17 @@ static uint32_t crc24_mulmod_host(uint32_t a, uint32_t b, uint32_t poly)
 }
 static void crc24_xpows(uint32_t nbytes, uint32_t poly, uint32_t out[5])
 {
+  // memoised per (length, polynomial): batch planning calls this once per code block
+  struct Entry {
+    uint32_t v[5];
+  };
+  static thread_local std::map<uint64_t, Entry> cache;
+  const uint64_t key = ((uint64_t)poly << 32) | nbytes;
+  auto           it  = cache.find(key);
+  if (it != cache.end()) {
+    memcpy(out, it->second.v, sizeof(it->second.v));
+    return;
+  }
   const uint32_t cb = (nbytes + 31) / 32;
   uint32_t       xp = 1;
   for (uint32_t q = 0; q < 8 * cb; q++) { // multiply by x, 8*cb times
@@ -73,10 +84,12 @@ static void crc24_xpows(uint32_t nbytes, uint32_t poly, uint32_t out[5])
       xp ^= poly;
   }
   xp &= 0xffffffu;
+  Entry e;
   for (int l = 0; l < 5; l++) {
-    out[l] = xp;
+    out[l] = e.v[l] = xp;
     xp     = crc24_mulmod_host(xp, xp, poly);
   }
+  cache[key] = e;
 }
 
 template <typename T>
@@ -731,6 +744,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
 
   // pass 2: descriptors
   size_t in_off = 0, out_off = 0;
+  const uint8_t* cp_src = nullptr;
+  size_t         cp_dst = 0, cp_bytes = 0;
   tb_out_off.assign(nof_tb, 0);
   for (uint32_t t = 0; t < nof_tb; t++) {
     if (tb_map[t] < 0)
@@ -742,9 +757,22 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     if (flags & SRSLTE_B200_IN_DEVICE) {
       e_dev = (const uint8_t*)u.e_bits;
     } else {
-      CUDA_OK(cudaMemcpyAsync(d_in.ptr + in_off, u.e_bits, (size_t)u.nof_e_bits * esz, cudaMemcpyHostToDevice, stream));
+      // host LLRs: adjacent transport blocks of one caller buffer are uploaded with a single copy
+      const size_t nb = (size_t)u.nof_e_bits * esz;
+      if (cp_bytes && (const uint8_t*)u.e_bits == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
+        cp_bytes += nb;
+      } else {
+        if (cp_bytes)
+          CUDA_OK(cudaMemcpyAsync(d_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+        cp_src   = (const uint8_t*)u.e_bits;
+        cp_dst   = in_off;
+        cp_bytes = nb;
+      }
       e_dev = d_in.ptr + in_off;
-      in_off += ((size_t)u.nof_e_bits * esz + 15) / 16 * 16;
+      in_off += nb;
+      if (nb % 16) { // keep every block 16-byte aligned on the device; breaks the run
+        in_off = (in_off + 15) / 16 * 16;
+      }
     }
     TbDev td;
     memset(&td, 0, sizeof(td));
@@ -814,6 +842,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     }
     plan.tbs.push_back(td);
   }
+  if (cp_bytes)
+    CUDA_OK(cudaMemcpyAsync(d_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
   int rc = run(plan);
   if (rc)
     return rc;
