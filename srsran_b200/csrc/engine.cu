@@ -33,6 +33,7 @@ struct Plan {
   std::vector<CbDev> cbs;
   std::vector<TbDev> tbs;
   uint32_t           max_iter     = 0;
+  uint32_t           iter0        = 0; // half-iterations the code blocks have already run (single-block sessions)
   bool               prepare      = true;
   uint32_t           cb_out_bytes = 0;
 };
@@ -201,6 +202,7 @@ Engine::~Engine()
   d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
+  h_tmaps.release(); d_tmaps.release();
   if (stream)
     cudaStreamDestroy(stream);
   delete plan_ptr;
@@ -321,18 +323,72 @@ static void map_geometry(int n_slots, int* nt, int* blocks)
   *blocks = (warps + (*nt / 32) - 1) / (*nt / 32);
 }
 
-template <class P, int N>
+template <class P, int N, int L = kSegLen, int NT = kMapThreads, int MINB = 1>
 static cudaError_t launch_map(MapArgs a, int n_slots, int max_w, cudaStream_t st)
 {
-  constexpr int L = kSegLen, NT = kMapThreads;
-  int           nt, blocks;
-  map_geometry<N>(n_slots, &nt, &blocks);
+  constexpr int T = N / 2, G = 32 / T;
+  const int     warps  = (n_slots + G - 1) / G;
+  const int     blocks = (warps + (NT / 32) - 1) / (NT / 32);
   a.ck_slots = (max_w + L - 1) / L + 1;
   // shared memory: double-buffered staging of 4 rows (in, parity, a-priori, QPP table) x L steps + one 8-word
   // checkpoint, per thread
   const size_t smem = (size_t)NT * 3 * (L * 4 + 8) * 4; // StagedSrc::kStages buffers
-  auto         kern = k_map_win<P, N, L, NT>;
+  auto         kern = k_map_win<P, N, L, NT, MINB>;
   cudaError_t  e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  kern<<<blocks, NT, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point lookup (the library does not link libcuda)
+typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                 const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static TmapEncodeFn tmap_encoder()
+{
+  static TmapEncodeFn fn = nullptr;
+  static bool         tried = false;
+  if (!tried) {
+    tried = true;
+    cudaDriverEntryPointQueryResult qr;
+    void*                           p = nullptr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+      fn = (TmapEncodeFn)p;
+  }
+  return fn;
+}
+// workspace of one K-group as the tensor (T words | block | row | plane); box = (T, G, L, planes)
+static int encode_group_map(CUtensorMap* out, int16_t* base, uint32_t lanes, uint32_t n_blocks, uint32_t W, uint32_t ps, uint32_t L, uint32_t planes)
+{
+  TmapEncodeFn enc = tmap_encoder();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is not available from this driver");
+    return SRSLTE_B200_ERROR;
+  }
+  const uint32_t T = lanes / 2, G = 32 / T;
+  cuuint64_t     dims[4]    = {T, n_blocks, W, 6};
+  cuuint64_t     strides[3] = {(cuuint64_t)6 * ps * 2, (cuuint64_t)T * 4, (cuuint64_t)ps * 2};
+  cuuint32_t     box[4]     = {T, G, L, planes};
+  cuuint32_t     estr[4]    = {1, 1, 1, 1};
+  CUresult       r = enc(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+    return SRSLTE_B200_ERROR;
+  }
+  return 0;
+}
+
+template <int N, int NT, int MINB, int STAGES>
+static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaStream_t st)
+{
+  constexpr int T = N / 2, G = 32 / T;
+  const int     warps  = (n_slots + G - 1) / G;
+  const int     blocks = (warps + (NT / 32) - 1) / (NT / 32);
+  const size_t  smem   = (size_t)(NT / 32) * F16Lay<T, STAGES>::kWarpWords * 4;
+  void (*kern)(const MapArgs) = (n_iter & 1) ? k_map_f16<N, 2, NT, MINB, STAGES>
+                                             : (n_iter ? k_map_f16<N, 1, NT, MINB, STAGES> : k_map_f16<N, 0, NT, MINB, STAGES>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
   kern<<<blocks, NT, smem, st>>>(a);
@@ -350,11 +406,11 @@ int Engine::run(Plan& p)
     return 0;
 
   // ---- workspace layout + output slots
+  // (workspace offsets are assigned below in work-list order: the slots of a warp are adjacent in memory)
   uint64_t ws_elems = 0;
   uint32_t out_bytes = 0;
   for (auto& d : p.cbs) {
-    d.ws_off = ws_elems;
-    ws_elems += 6ull * d.ps;
+    d.ws_off  = 0;
     d.out_off = out_bytes;
     out_bytes += d.K / 8;
   }
@@ -379,9 +435,15 @@ int Engine::run(Plan& p)
   }
   const size_t off_active = add_list(active), off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
   struct ClassRun {
-    size_t off;
+    size_t off, winfo_off;
     int    n_slots, max_w;
   } cls[4];
+  struct KGroup { // code blocks of one size in one decoder class: consecutive slots, consecutive workspace
+    int      cls, first_slot, n_blocks;
+    uint32_t W, ps;
+    uint64_t ws_off;
+  };
+  std::vector<KGroup> groups;
   for (int c = 0; c < 4; c++) {
     std::vector<int> ids;
     for (int i : active)
@@ -391,16 +453,35 @@ int Engine::run(Plan& p)
     const int        G = 32 / (kWinClasses[c].lanes / 2);
     std::vector<int> w;
     int              max_w = 0;
+    std::vector<int> winfo; // per warp: K-group, block coordinate of its first slot inside the group
     for (size_t i = 0; i < ids.size(); i++) {
-      if (i > 0 && p.cbs[ids[i]].K != p.cbs[ids[i - 1]].K)
+      CbDev& d = p.cbs[ids[i]];
+      if (i == 0 || d.K != p.cbs[ids[i - 1]].K) {
         while (w.size() % G)
           w.push_back(-1); // a warp never mixes code block sizes
+        groups.push_back(KGroup{c, (int)w.size(), 0, d.W, d.ps, ws_elems});
+      }
+      d.ws_off = ws_elems;
+      ws_elems += 6ull * d.ps;
+      groups.back().n_blocks++;
       w.push_back(ids[i]);
-      max_w = std::max(max_w, (int)p.cbs[ids[i]].W);
+      max_w = std::max(max_w, (int)d.W);
     }
-    cls[c].off     = add_list(w);
-    cls[c].n_slots = (int)w.size();
-    cls[c].max_w   = max_w;
+    while (w.size() % G)
+      w.push_back(-1);
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      if (groups[gi].cls != c)
+        continue;
+      const int end = groups[gi].first_slot + (groups[gi].n_blocks + G - 1) / G * G;
+      for (int sl = groups[gi].first_slot; sl < end; sl += G) {
+        winfo.push_back((int)gi);
+        winfo.push_back(sl - groups[gi].first_slot);
+      }
+    }
+    cls[c].off       = add_list(w);
+    cls[c].winfo_off = add_list(winfo);
+    cls[c].n_slots   = (int)w.size();
+    cls[c].max_w     = max_w;
   }
   // generic decoder: pairs of equal K
   std::vector<int> gen_pairs;
@@ -411,6 +492,10 @@ int Engine::run(Plan& p)
       if (p.cbs[i].N == 0)
         ids.push_back(i);
     std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p.cbs[a].K > p.cbs[b].K; });
+    for (int i : ids) {
+      p.cbs[i].ws_off = ws_elems;
+      ws_elems += 6ull * p.cbs[i].ps;
+    }
     for (size_t i = 0; i < ids.size();) {
       gen_max_k = std::max(gen_max_k, p.cbs[ids[i]].K);
       if (i + 1 < ids.size() && p.cbs[ids[i + 1]].K == p.cbs[ids[i]].K) {
@@ -435,6 +520,24 @@ int Engine::run(Plan& p)
   const int gen_threads = (n_pairs + 63) / 64 * 64;
   if (n_pairs && d_genbeta.reserve((size_t)(gen_max_k + 4) * 8 * gen_threads))
     return SRSLTE_B200_ERROR;
+
+  // tensor maps of the K-groups (TMA staging of the windowed MAP kernel): [2g] 3-plane box, [2g+1] 2-plane box
+  const uint32_t seg_len = map_seg_len();
+  const bool     use_tmaps = opt_fast16;
+  if (use_tmaps && !groups.empty()) {
+    if (d_tmaps.reserve(groups.size() * 2 * sizeof(CUtensorMap)) || h_tmaps.reserve(groups.size() * 2 * sizeof(CUtensorMap)))
+      return SRSLTE_B200_ERROR;
+    CUtensorMap* hm = (CUtensorMap*)h_tmaps.ptr;
+    for (size_t gi = 0; gi < groups.size(); gi++) {
+      const KGroup& g = groups[gi];
+      if (g.cls >= 2)
+        continue; // the int8 classes run k_map_win (per-thread staging)
+      for (uint32_t v = 0; v < 2; v++)
+        if (encode_group_map(&hm[2 * gi + v], d_ws.ptr + g.ws_off, kWinClasses[g.cls].lanes, g.n_blocks, g.W, g.ps, seg_len, v == 0 ? 3 : 2))
+          return SRSLTE_B200_ERROR;
+    }
+    CUDA_OK(cudaMemcpyAsync(d_tmaps.ptr, hm, groups.size() * 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice, stream));
+  }
 
   // descriptors travel through one pinned staging buffer
   const size_t desc_bytes = n_cb * sizeof(CbDev) + lists.size() * sizeof(int) + p.tbs.size() * sizeof(TbDev);
@@ -494,8 +597,8 @@ int Engine::run(Plan& p)
         map_geometry<16>(cls[c].n_slots, &nt, &blocks);
       else
         map_geometry<32>(cls[c].n_slots, &nt, &blocks);
-      const size_t slots = (size_t)(cls[c].max_w + kSegLen - 1) / kSegLen + 1;
-      need = std::max(need, slots * (size_t)blocks * nt * 8);
+      const size_t slots = (size_t)(cls[c].max_w + 3) / 4 + 1; // sized for the shortest segment length in use
+      need = std::max(need, slots * ((size_t)blocks * nt + 256) * 8);
     }
     if (need && d_ckscratch.reserve(need))
       return SRSLTE_B200_ERROR;
@@ -506,7 +609,8 @@ int Engine::run(Plan& p)
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots)
         continue;
-      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0, d_counters.ptr, (int)it};
+      MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0, d_counters.ptr, (int)it,
+                d_lists.ptr + cls[c].winfo_off, (const CUtensorMap*)d_tmaps.ptr};
       cudaEvent_t e0, e1;
       if (map_event_pair(&e0, &e1))
         return SRSLTE_B200_ERROR;
@@ -516,7 +620,14 @@ int Engine::run(Plan& p)
       if (fast) {
         // native packed-instruction attempt with range monitoring, then exact replay of the flagged code blocks
         a.mode = 1;
-        e = c == 0 ? launch_map<Fast16, 8>(a, cls[c].n_slots, cls[c].max_w, stream) : launch_map<Fast16, 16>(a, cls[c].n_slots, cls[c].max_w, stream);
+        a.mode |= opt_map_cfg & 0xff00; // (measurement switches of k_map_f16)
+        const uint32_t n_it = p.iter0 + it;
+        const int      ns   = cls[c].n_slots;
+        switch (opt_map_cfg & 0xff) {
+          case 1: e = c == 0 ? launch_map_f16<8, 256, 2, 2>(a, ns, n_it, stream) : launch_map_f16<16, 256, 2, 2>(a, ns, n_it, stream); break;
+          case 2: e = c == 0 ? launch_map_f16<8, 256, 1, 3>(a, ns, n_it, stream) : launch_map_f16<16, 256, 1, 3>(a, ns, n_it, stream); break;
+          default: e = c == 0 ? launch_map_f16<8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<16, 128, 3, 3>(a, ns, n_it, stream); break;
+        }
         CUDA_OK(e);
         last_launches++;
         a.mode = 2;
@@ -555,6 +666,8 @@ int Engine::run(Plan& p)
   CUDA_OK(cudaMemcpyAsync(h_counters.ptr, d_counters.ptr, 16, cudaMemcpyDeviceToHost, stream));
   return 0;
 }
+
+uint32_t Engine::map_seg_len() const { return 8; }
 
 int Engine::timer_start()
 {
@@ -1157,6 +1270,10 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (!strcmp(name, "fast16")) {
     ctx->e->opt_fast16 = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "map_cfg")) {
+    ctx->e->opt_map_cfg = value;
     return 0;
   }
   return SRSLTE_B200_ERROR_INVALID_INPUTS;

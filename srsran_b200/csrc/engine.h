@@ -66,6 +66,7 @@ public:
   int select_decoder(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, DecSel* s);
   void fill_geometry(CbDev* d, uint32_t K, const DecSel& s);
   int run(Plan& p);
+  uint32_t map_seg_len() const; // trellis steps per beta segment of the MAP kernel variant in use
 
   int          device  = 0;
   int          num_sms = 0;
@@ -90,11 +91,13 @@ public:
   DevBuf<int16_t>  d_ws, d_tails, d_sb;
   DevBuf<uint8_t>  d_cbout, d_in, d_tbout;
   DevBuf<int>      d_lists, d_gmax;
+  int              opt_map_cfg = 0;
   bool             opt_fast16 = true; // try the native packed-instruction path first (exact replay on range alarm)
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch;
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;
-  PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc;
+  PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc, h_tmaps;
+  DevBuf<uint8_t>  d_tmaps;
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
 

@@ -8,6 +8,7 @@
 //                  sch.c:420-450)
 //   k_tb_finish    TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
 #pragma once
+#include <cuda.h> // CUtensorMap (type only: the encoder is reached through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -72,6 +73,9 @@ struct TbResult {
   uint32_t par_rx;
 };
 
+// Planes of a code block's workspace (plane stride d.ps int16 each).  The order keeps the inputs of each constituent
+// decoder adjacent so one TMA box covers them: DEC1 reads {syst, par0, apr}, DEC2 reads {app2, par1}.
+constexpr int kPlSyst = 0, kPlPar0 = 1, kPlApr = 2, kPlApp2 = 3, kPlPar1 = 4, kPlPost = 5;
 constexpr uint32_t kSbPadDev = 32; // plane padding of the lane layout (rm_turbo.c:272)
 
 __constant__ uint32_t c_crc_tab[2][256]; // [0] = CRC24A, [1] = CRC24B byte tables (crc.c:30-46)
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
       const int32_t a = get(i), b = get(K + kSbPadDev + i), c = get(2 * (K + kSbPadDev) + i);
       p0[i]            = (int16_t)a;
       p0[d.ps + i]     = (int16_t)b;
-      p0[2 * d.ps + i] = (int16_t)c;
+      p0[kPlPar1 * (size_t)d.ps + i] = (int16_t)c;
       amax(g0, a); amax(g1, b); amax(g2, c);
     }
   } else {
@@ -171,7 +175,7 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
       // two adjacent lanes (j, j+1) of one step per thread: one 32-bit store per plane
       u32* q0 = reinterpret_cast<u32*>(p0);
       u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
-      u32* q2 = reinterpret_cast<u32*>(p0 + 2 * (size_t)d.ps);
+      u32* q2 = reinterpret_cast<u32*>(p0 + kPlPar1 * (size_t)d.ps);
       for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
         const uint32_t j = 2 * h, n0 = (j % N) * W + j / N, n1 = n0 + W;
         const int32_t  a0 = s_in[3 * n0], b0 = s_in[3 * n0 + 1], c0 = s_in[3 * n0 + 2];
@@ -187,7 +191,7 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
         const int32_t a = s_in[3 * j], b = s_in[3 * j + 1], c = s_in[3 * j + 2];
         p0[j]            = (int16_t)a;
         p0[d.ps + j]     = (int16_t)b;
-        p0[2 * d.ps + j] = (int16_t)c;
+        p0[kPlPar1 * (size_t)d.ps + j] = (int16_t)c;
         amax(g0, a); amax(g1, b); amax(g2, c);
       }
     }
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
   if (d.in_sb) {
     u32* q0 = reinterpret_cast<u32*>(p0);
     u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
-    u32* q2 = reinterpret_cast<u32*>(p0 + 2 * (size_t)d.ps);
+    u32* q2 = reinterpret_cast<u32*>(p0 + kPlPar1 * (size_t)d.ps);
     if (sizeof(T) == 2) {
       // int16 soft buffer: the planes are already pairs of adjacent lanes, copy them as 32-bit words
       const u32* s0 = reinterpret_cast<const u32*>(sb);
@@ -330,7 +334,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
       const int32_t  a = sb[3 * n], b = sb[3 * n + 1], c = sb[3 * n + 2];
       p0[j]            = (int16_t)a;
       p0[d.ps + j]     = (int16_t)b;
-      p0[2 * d.ps + j] = (int16_t)c;
+      p0[kPlPar1 * (size_t)d.ps + j] = (int16_t)c;
       amax(g0, a); amax(g1, b); amax(g2, c);
     }
   }
@@ -365,6 +369,9 @@ struct MapArgs {
   int             ck_slots;
   const uint32_t* counters; // DecideArgs::counters
   int             iter;     // half-iteration index of this launch within the batch
+  // tensor-map staging (k_map_t): per warp {index of its K-group's pair of tensor maps, block coordinate of its first slot}
+  const int*         winfo;
+  const CUtensorMap* tmaps; // per K-group: [2g] box of 3 planes, [2g+1] box of 2 planes
 };
 
 // Row source staged through shared memory with cp.async (LDGSTS): chunk c+1 streams in while chunk c is being
@@ -517,8 +524,8 @@ struct EpiDec2 {
   }
 };
 
-template <class P, int N, int L, int NT>
-__global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
+template <class P, int N, int L, int NT, int MINB = 1>
+__global__ void __launch_bounds__(NT, MINB) k_map_win(const MapArgs a)
 {
   constexpr int T = N / 2;  // threads per code block
   constexpr int G = 32 / T; // code blocks per warp
@@ -558,13 +565,13 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   if (!dec2) {
     m.src.in  = (const u32*)(ws);
     m.src.par = (const u32*)(ws + d.ps);
-    m.src.apr = st0.n_iter ? (const u32*)(ws + 3 * (size_t)d.ps) : nullptr;
+    m.src.apr = st0.n_iter ? (const u32*)(ws + kPlApr * (size_t)d.ps) : nullptr;
     m.src.lut = (const u32*)(q + d.K); // rev[] as pairs
     tin       = tl;
     tpar      = tl + 3;
   } else {
-    m.src.in  = (const u32*)(ws + 4 * (size_t)d.ps);
-    m.src.par = (const u32*)(ws + 2 * (size_t)d.ps);
+    m.src.in  = (const u32*)(ws + kPlApp2 * (size_t)d.ps);
+    m.src.par = (const u32*)(ws + kPlPar1 * (size_t)d.ps);
     m.src.apr = nullptr;
     m.src.lut = (const u32*)q; // fwd[] as pairs
     tin       = tl + 6;
@@ -619,12 +626,12 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   }
   u32             ehi, elo;
   if (!dec2) {
-    EpiDec1<P> e{(u32*)(ws + 5 * (size_t)d.ps), ws + 4 * (size_t)d.ps, T, j, d.sat_end, 0u, 0u};
+    EpiDec1<P> e{(u32*)(ws + kPlPost * (size_t)d.ps), ws + kPlApp2 * (size_t)d.ps, T, j, d.sat_end, 0u, 0u};
     m.alpha_main(st, e);
     ehi = e.ehi;
     elo = e.elo;
   } else {
-    EpiDec2<P> e{ws + 5 * (size_t)d.ps, ws + 3 * (size_t)d.ps, d.sat_end, 0u, 0u};
+    EpiDec2<P> e{ws + kPlPost * (size_t)d.ps, ws + kPlApr * (size_t)d.ps, d.sat_end, 0u, 0u};
     m.alpha_main(st, e);
     ehi = e.ehi;
     elo = e.elo;
@@ -646,6 +653,59 @@ __global__ void __launch_bounds__(NT, 1) k_map_win(const MapArgs a)
   if (j == 0)
     gm[3] = ge;
 }
+
+// ------------------------------------------------------------------------------------------ TMA / mbarrier primitives
+// (used by k_map_f16, map_f16.cuh).  Staging history: per-thread LDGSTS costs ~8 LSU cycles per warp instruction
+// whatever its payload and saturated the L1 data pipe before the integer pipe; plain bulk copies (UBLKCP) take
+// uniform-register operands, so a copy per (code block, plane) costs ~10 issue slots each; one tensor copy per warp
+// and tile does neither.
+__device__ __forceinline__ void mbar_init(unsigned bar_s, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar_s), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar_s, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar_s), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar_s, unsigned parity)
+{
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "B200_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra B200_DONE;\n"
+      "bra B200_WAIT;\n"
+      "B200_DONE:\n"
+      "}\n" ::"r"(bar_s),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_s, const void* src, unsigned bytes, unsigned bar_s)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst_s), "l"(src), "r"(bytes),
+               "r"(bar_s)
+               : "memory");
+}
+
+// ------------------------------------------------------------------------------------------ windowed MAP, tensor-map staging
+// One TMA tensor copy per warp and chunk.  The workspace of a K-group (code blocks of equal K, consecutive slots of
+// the work list) is a 4-D tensor (T words | block | row | plane) with strides (4, 6*ps*2, 4T, ps*2) bytes; the box
+// (T, G, L, P) is exactly what the G code blocks of a warp need for a chunk of L trellis steps: P = 3 planes
+// {syst, par0, apr} for DEC1 with a-priori input, P = 2 for the first half-iteration {syst, par0} and for DEC2
+// {app2, par1}.  Listing the block dimension second makes a box row 32 words = one word per lane of the warp, so
+// the staging area is read without bank conflicts and with a single address per (plane, step).  Rows outside the
+// tensor (top-aligned chunks start below row 0 when W is not a multiple of L) are zero-filled by the hardware.
+__device__ __forceinline__ void tma_tile4(unsigned dst_s, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar_s)
+{
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];\n" ::"r"(dst_s),
+               "l"(tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar_s)
+               : "memory");
+}
+
+} // namespace b200
+#include "map_f16.cuh"
+namespace b200 {
 
 // ------------------------------------------------------------------------------------------ generic MAP
 // tdec_gen_dec: un-windowed, wrapping int16, natural order.  One thread decodes TWO code blocks of the same K
@@ -703,12 +763,12 @@ __global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
   const size_t   ps0 = d0.ps, ps1 = d1.ps;
   const bool     dec2_0 = s0.n_iter & 1u, dec2_1 = s1.n_iter & 1u;
   // per-half plane selection (the two blocks may be at different half-iterations)
-  const int16_t* in0  = dec2_0 ? w0 + 4 * ps0 : w0;
-  const int16_t* in1  = dec2_1 ? w1 + 4 * ps1 : w1;
-  const int16_t* pa0  = dec2_0 ? w0 + 2 * ps0 : w0 + ps0;
-  const int16_t* pa1  = dec2_1 ? w1 + 2 * ps1 : w1 + ps1;
-  const int16_t* ap0  = (!dec2_0 && s0.n_iter) ? w0 + 3 * ps0 : nullptr;
-  const int16_t* ap1  = (!dec2_1 && s1.n_iter) ? w1 + 3 * ps1 : nullptr;
+  const int16_t* in0  = dec2_0 ? w0 + kPlApp2 * ps0 : w0;
+  const int16_t* in1  = dec2_1 ? w1 + kPlApp2 * ps1 : w1;
+  const int16_t* pa0  = dec2_0 ? w0 + kPlPar1 * ps0 : w0 + ps0;
+  const int16_t* pa1  = dec2_1 ? w1 + kPlPar1 * ps1 : w1 + ps1;
+  const int16_t* ap0  = (!dec2_0 && s0.n_iter) ? w0 + kPlApr * ps0 : nullptr;
+  const int16_t* ap1  = (!dec2_1 && s1.n_iter) ? w1 + kPlApr * ps1 : nullptr;
   const int16_t* tl0  = a.tails + (size_t)cb0 * 12 + (dec2_0 ? 6 : 0);
   const int16_t* tl1  = a.tails + (size_t)cb1 * 12 + (dec2_1 ? 6 : 0);
   auto ldx = [&](uint32_t k, u32& x, u32& y, u32& ap) {
@@ -763,23 +823,23 @@ __global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
     if (act0) {
       const int32_t l = lo16(llr);
       if (!dec2_0) {
-        w0[5 * ps0 + i]             = (int16_t)l;
-        w0[4 * ps0 + q0[K + i]]     = (int16_t)(l - lo16(ap)); // app2[rev[i]] = ext1[i] - app1[i]
+        w0[kPlPost * ps0 + i]             = (int16_t)l;
+        w0[kPlApp2 * ps0 + q0[K + i]]     = (int16_t)(l - lo16(ap)); // app2[rev[i]] = ext1[i] - app1[i]
       } else {
         const uint32_t f = q0[i];
-        w0[5 * ps0 + f]  = (int16_t)l;
-        w0[3 * ps0 + f]  = (int16_t)(l - (int32_t)in0[i]);      // app1[fwd[i]] = ext2[i] - app2[i]
+        w0[kPlPost * ps0 + f]  = (int16_t)l;
+        w0[kPlApr * ps0 + f]  = (int16_t)(l - (int32_t)in0[i]);      // app1[fwd[i]] = ext2[i] - app2[i]
       }
     }
     if (act1) {
       const int32_t l = hi16(llr);
       if (!dec2_1) {
-        w1[5 * ps1 + i]         = (int16_t)l;
-        w1[4 * ps1 + q1[K + i]] = (int16_t)(l - hi16(ap));
+        w1[kPlPost * ps1 + i]         = (int16_t)l;
+        w1[kPlApp2 * ps1 + q1[K + i]] = (int16_t)(l - hi16(ap));
       } else {
         const uint32_t f = q1[i];
-        w1[5 * ps1 + f]  = (int16_t)l;
-        w1[3 * ps1 + f]  = (int16_t)(l - (int32_t)in1[i]);
+        w1[kPlPost * ps1 + f]  = (int16_t)l;
+        w1[kPlApr * ps1 + f]  = (int16_t)(l - (int32_t)in1[i]);
       }
     }
   }
@@ -887,7 +947,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
   const bool     need   = d.crc_poly != 0 || n_iter >= d.max_iter;
   uint32_t       crc    = 1;
   if (need) {
-    const int16_t* post = a.ws + d.ws_off + 5 * (size_t)d.ps;
+    const int16_t* post = a.ws + d.ws_off + kPlPost * (size_t)d.ps;
     const uint32_t K = d.K, N = d.N ? d.N : 1, W = d.N ? d.W : K;
     const uint32_t wpr = (W + 31) / 32 + 1; // words per bit row (+1 so a 64-bit window never runs off the row)
     u32*           bits = s_bits[wib];
