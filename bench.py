@@ -35,6 +35,9 @@ sys.path.insert(0, ROOT)
 
 W16_OPS = 82.0   # algorithmic int16 lane-ops per trellis step per half-iteration
 W8_OPS = 106.0
+# DRAM traffic of the dominant kernel per code block and launch (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture divided by the code blocks of that launch; see profiles/README.md for the capture)
+MAP_TRAFFIC_PER_CB = {"c1": {"bytes_per_cb": 92.3e3, "source": "profiles/r01_k_map_f16.metrics.txt (mean of the 4 half-iteration launches)"}}
 
 
 def load_peaks():
@@ -469,6 +472,33 @@ def run_ours(args):
     barrier()
     e2e_value = total_units / e2e_s / 1e6
 
+    # ---- per-TTI latency (second half of the metric): ONE subframe's worth of work submitted from host buffers,
+    #      submit -> results on the host, back to back on an otherwise idle GPU
+    lat = []
+    n_lat = 300
+    if args.workload == "c1":
+        tti_cb = 13
+        tti_desc = "%d code blocks x K=6144 x 4 half-iterations (one 75 kbit subframe), host buffers in and out" % tti_cb
+        for i in range(n_lat + 20):
+            lo = (i * tti_cb) % (ncb - tti_cb)
+            t0 = time.perf_counter()
+            ctx.tdec_batch_submit(pin_in.array[lo:lo + tti_cb].ctypes.data, pin_out.array[lo:lo + tti_cb].ctypes.data, K, tti_cb, stride, 16, nit)
+            ctx.wait()
+            lat.append(time.perf_counter() - t0)
+    else:
+        tti_desc = "1 transport block of %d bits (%d code blocks), <=%d half-iterations with CRC early stop, host buffers in and out" % (tbs, cfg["C"], cfg["max_iter"])
+        one = b.make_tbs(1)
+        for i in range(n_lat + 20):
+            k = i % ntb
+            t = one[0]
+            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = pin_in.ptr + k * G * esz, G, tbs, Qm, 0, None, pin_out.ptr + k * ostride
+            t0 = time.perf_counter()
+            ctx.decode_tbs(one, dt == np.int8, cfg["max_iter"], flags=0)
+            lat.append(time.perf_counter() - t0)
+    lat = np.sort(np.array(lat[20:])) * 1e6
+    latency = {"tti": tti_desc, "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "max_us": float(lat[-1]), "n": int(len(lat))}
+    barrier()
+
     if args.workload != "c1":
         avg_it = float(np.mean([tb_dev[i].avg_iterations for i in range(ntb)]))
         K, nit = cfg["K"], avg_it
@@ -489,17 +519,25 @@ def run_ours(args):
         r_map_ms += ctx.last_map_ms()
         r_map_launches += ctx.last_map_launches()
     ms_single = ctx.timer_stop_ms() / rsteps
-    probe = ctx.alu_probe(0)           # packed int16x2 operations / s of the kernel's instruction mix
-    probe_sat = ctx.alu_probe(1)
-    peak_lane_ops = 2.0 * probe
+    # peak: issue rate of the packed instructions the kernel is made of, each measured on its own (VIADD.16x2, VIMNMX.S16x2,
+    # VIADDMNMX.S16x2, VIMNMX3.S16x2 all sustain 0.5 warp-instructions/clk/SM sub-partition on B200: 16-lane integer pipe)
+    probes = [ctx.alu_probe(op) for op in range(4)]
+    probe = min(probes)                # packed int16x2 instructions / s
+    probe_sat = ctx.alu_probe(4)
+    peak_lane_ops = 2.0 * probe        # one algorithmic operation per int16 lane and instruction
     map_s_per_launch = (r_map_ms * 1e-3) / max(1, r_map_launches)
     ach_lane_ops = (algo_ops_per_step * rsteps / max(1, r_map_launches)) / map_s_per_launch if r_map_launches else 0.0
     map_ms, map_launches = r_map_ms, r_map_launches
+    traffic = MAP_TRAFFIC_PER_CB.get(args.workload)
     roofline = {"bound": "int_alu", "achieved": ach_lane_ops / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s (int16)",
-                "frac": ach_lane_ops / peak_lane_ops if peak_lane_ops else None, "traffic": None,
-                "kernel": "k_map_win", "launches": map_launches, "avg_launch_ms": 1e3 * map_s_per_launch,
+                "frac": ach_lane_ops / peak_lane_ops if peak_lane_ops else None,
+                "traffic": None if traffic is None else traffic["bytes_per_cb"] * (units_per_step / K if args.workload == "c1" else cfg["C"] * ntb),
+                "traffic_source": None if traffic is None else traffic["source"],
+                "kernel": "k_map_f16", "launches": map_launches, "avg_launch_ms": 1e3 * map_s_per_launch,
                 "map_share_of_step": (r_map_ms / rsteps) / ms_single, "single_stream_mbps": units_per_step / (ms_single * 1e-3) / 1e6,
-                "peak_source": "live micro-benchmark of VIADD.16x2/VIMNMX.S16x2/VIADDMNMX.S16x2 issue rate (k_alu_probe), x2 lanes",
+                "peak_source": "live micro-benchmark (k_alu_probe): min over VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2 of the packed "
+                               "instruction rate, x2 int16 lanes; algorithmic work = 82 (int8: 106) lane-ops per trellis step and half-iteration",
+                "probe_packed_tops": [x / 1e12 for x in probes],
                 "peak_with_saturating_emulation": 2.0 * probe_sat / 1e12,
                 "hbm": {"achieved_gbs": algo_bytes_per_step / ((ms / args.steps) * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
                         "frac": algo_bytes_per_step / ((ms / args.steps) * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src}}
@@ -518,7 +556,7 @@ def run_ours(args):
                 "config": {"workload": workload, "l2": "inputs (%.0f MB per GPU per step) larger than the 126 MB L2" % (h2d_b / 1e6), "parallelism": "batch-sharded x%d, no collective" % world},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d_b * world), "d2h_bytes_per_step": int(d2h_b * world)},
-                "gpu_launches": int(launches * world), "roofline": roofline}
+                "gpu_launches": int(launches * world), "latency": latency, "roofline": roofline}
         if cpu is not None:
             line["cpu_baseline"] = cpu
         line.update(extra)

@@ -127,9 +127,10 @@ SRSLTE_B200_API int srslte_b200_rm_table(uint32_t K, uint32_t rv, uint32_t lanes
 /* CUDA-event stopwatch on the engine's own stream (torch.cuda.Event would only see torch's stream) */
 SRSLTE_B200_API int   srslte_b200_timer_start(srslte_b200_ctx_t* ctx);
 SRSLTE_B200_API float srslte_b200_timer_stop_ms(srslte_b200_ctx_t* ctx);
-/* integer-ALU roofline probe: packed int16x2 operations per second sustained by the instruction mix of the MAP
- * kernel (mode 0: wrapping add / max / fused add-max; mode 1: with the saturating-add emulation) */
-SRSLTE_B200_API double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int mode);
+/* integer-ALU roofline probe: packed int16x2 instructions per second (whole GPU, one instruction kind at a time, 8
+ * independent chains per thread) -- op 0 VIADD.16x2, 1 VIMNMX.S16x2, 2 VIADDMNMX.S16x2, 3 VIMNMX3.S16x2,
+ * 4 the saturating add __vaddss2 (multi-instruction emulation on sm_100a, counted per source operation) */
+SRSLTE_B200_API double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int op);
 
 #ifdef __cplusplus
 }

@@ -579,7 +579,10 @@ int Engine::run(Plan& p)
     last_launches++;
   }
   if (!plain.empty() && p.prepare) {
-    k_prepare<<<(int)plain.size(), 256, (3 * kMaxK + 12) * sizeof(int16_t), stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
+    // staging of one code block (3K+12 LLRs) + one padded plane for the transposition into the lane layout
+    const size_t prep_smem = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
+    CUDA_OK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    k_prepare<<<(int)plain.size(), 256, prep_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
     last_launches++;
   }
   CUDA_OK(cudaGetLastError());
@@ -1210,22 +1213,28 @@ int srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer
 void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb) { b200::softbuffer_reset((b200::Softbuffer*)sb); }
 void srslte_b200_softbuffer_free(srslte_b200_softbuffer_t* sb) { b200::softbuffer_free((b200::Softbuffer*)sb); }
 
-// packed-op issue rate probe: returns packed operations per second (each operation = 2 int16 lane-ops)
-double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int mode)
+// packed-instruction issue rate probe: returns operations per second over the whole GPU (each = one packed int16x2
+// instruction per thread) for op 0 VIADD.16x2, 1 VIMNMX.S16x2, 2 VIADDMNMX.S16x2, 3 VIMNMX3.S16x2, 4 __vaddss2
+double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int op)
 {
-  if (!ctx)
+  if (!ctx || op < 0 || op > 4)
     return 0;
   Engine* e = ctx->e;
   cudaSetDevice(e->device);
-  const int blocks = e->num_sms * 8, iters = 4096;
+  const int blocks = e->num_sms * 8, iters = 2048;
   if (e->d_genbeta.reserve((size_t)blocks * 256))
     return 0;
+  void (*kern)(b200::u32*, int, b200::u32) = op == 0 ? b200::k_alu_probe<0>
+                                             : op == 1 ? b200::k_alu_probe<1>
+                                             : op == 2 ? b200::k_alu_probe<2>
+                                             : op == 3 ? b200::k_alu_probe<3>
+                                                       : b200::k_alu_probe<4>;
   cudaEvent_t a, b;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
-  b200::k_alu_probe<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, 64, mode, 0x1234567u); // warm-up
+  kern<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, 64, 0x1234567u); // warm-up
   cudaEventRecord(a, e->stream);
-  b200::k_alu_probe<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, iters, mode, 0x1234567u);
+  kern<<<blocks, 256, 0, e->stream>>>(e->d_genbeta.ptr, iters, 0x1234567u);
   cudaEventRecord(b, e->stream);
   cudaStreamSynchronize(e->stream);
   float ms = 0;
@@ -1234,7 +1243,7 @@ double srslte_b200_alu_probe(srslte_b200_ctx_t* ctx, int mode)
   cudaEventDestroy(b);
   if (ms <= 0)
     return 0;
-  const double ops = (double)blocks * 256 * (double)iters * 8 * 4;
+  const double ops = (double)blocks * 256 * (double)iters * 32;
   return ops / (ms * 1e-3);
 }
 // host-side table access (init-time products; used by input synthesis and by tests)

@@ -172,19 +172,51 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
     }
     __syncthreads();
     if (N) {
-      // two adjacent lanes (j, j+1) of one step per thread: one 32-bit store per plane
-      u32* q0 = reinterpret_cast<u32*>(p0);
-      u32* q1 = reinterpret_cast<u32*>(p0 + d.ps);
-      u32* q2 = reinterpret_cast<u32*>(p0 + kPlPar1 * (size_t)d.ps);
-      for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
-        const uint32_t j = 2 * h, n0 = (j % N) * W + j / N, n1 = n0 + W;
-        const int32_t  a0 = s_in[3 * n0], b0 = s_in[3 * n0 + 1], c0 = s_in[3 * n0 + 2];
-        const int32_t  a1 = s_in[3 * n1], b1 = s_in[3 * n1 + 1], c1 = s_in[3 * n1 + 2];
-        q0[h] = pack16(a0, a1);
-        q1[h] = pack16(b0, b1);
-        q2[h] = pack16(c0, c1);
-        amax(g0, a0); amax(g1, b0); amax(g2, c0);
-        amax(g0, a1); amax(g1, b1); amax(g2, c1);
+      // transpose natural order (n = lane * W + step) into the lane layout (step * N + lane) one plane at a time
+      // through a padded shared-memory plane: consecutive threads read consecutive n and write rows that are an odd
+      // number of words apart (no bank conflicts either way); the plane then leaves with consecutive 32-bit stores
+      int16_t*       s_out = s_in + (n_in + 7) / 8 * 8;
+      const uint32_t rs    = N + 2, hw = N / 2; // padded row length (int16), words per row
+      const uint32_t hsh = 31 - __clz(hw); // hw is a power of two and divides the block size
+      const uint32_t nth = blockDim.x;
+      for (int sp = 0; sp < 3; sp++) {
+        // natural order -> padded lane layout; (lane, step) of n = idx and both offsets advance without divisions
+        {
+          uint32_t dl = threadIdx.x / W, p = threadIdx.x - dl * W;
+          uint32_t oo = p * rs + dl;
+          const int16_t* si = s_in + 3 * threadIdx.x + sp;
+          for (uint32_t idx = threadIdx.x; idx < K; idx += nth) {
+            s_out[oo] = *si;
+            si += 3 * nth;
+            p += nth;
+            oo += nth * rs;
+            while (p >= W) {
+              p -= W;
+              oo += 1 - W * rs;
+            }
+          }
+        }
+        __syncthreads();
+        // padded plane -> global, one word (two lanes of one step) per thread and trip; max |LLR| on packed words
+        u32*       q  = reinterpret_cast<u32*>(p0 + (sp == 0 ? kPlSyst : sp == 1 ? kPlPar0 : kPlPar1) * (size_t)d.ps);
+        const u32* so = reinterpret_cast<const u32*>(s_out) + (threadIdx.x >> hsh) * (rs / 2) + (threadIdx.x & (hw - 1));
+        const uint32_t so_step = (nth >> hsh) * (rs / 2);
+        u32            vhi = 0, vlo = 0;
+        for (uint32_t w = threadIdx.x; w < W * hw; w += nth) {
+          const u32 v = *so;
+          q[w]        = v;
+          vhi         = p_max(vhi, v);
+          vlo         = p_min(vlo, v);
+          so += so_step;
+        }
+        const int g = max(max(lo16(vhi), hi16(vhi)), max(-lo16(vlo), -hi16(vlo)));
+        __syncthreads();
+        if (sp == 0)
+          g0 = g;
+        else if (sp == 1)
+          g1 = g;
+        else
+          g2 = g;
       }
     } else {
       for (uint32_t j = threadIdx.x; j < K; j += blockDim.x) {
@@ -936,15 +968,18 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
     n_iter0 = s->n_iter;
     active  = !(s->done || n_iter0 >= d.max_iter);
   }
-  if (!__syncthreads_or(active))
-    return; // none of this block's code blocks is still being decoded
-  load_crc_tables(s_tab);
-  __syncthreads();
-  if (!active)
-    return;
   const uint32_t n_iter = n_iter0 + 1; // the half-iteration that just ran
   const int      lane   = threadIdx.x & 31;
-  const bool     need   = d.crc_poly != 0 || n_iter >= d.max_iter;
+  const bool     need   = active && (d.crc_poly != 0 || n_iter >= d.max_iter);
+  const int      any    = __syncthreads_or((active ? 1 : 0) | (need && d.crc_poly != 0 ? 2 : 0));
+  if (!any)
+    return; // none of this block's code blocks is still being decoded
+  if (any & 2) { // (run_all semantics: no CRC, the tables are not needed)
+    load_crc_tables(s_tab);
+    __syncthreads();
+  }
+  if (!active)
+    return;
   uint32_t       crc    = 1;
   if (need) {
     const int16_t* post = a.ws + d.ws_off + kPlPost * (size_t)d.ps;
@@ -1140,35 +1175,35 @@ __global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uin
 }
 
 // ------------------------------------------------------------------------------------------ ALU roofline probe
-// Measures the issue rate of exactly the packed instructions the MAP kernel is made of (VIADD.16x2,
-// VIMNMX.S16x2, VIADDMNMX.S16x2): 8 independent dependency chains per thread, 4 packed operations per chain
-// step.  mode 0: wrapping add / max / fused add-max mix; mode 1: the same mix with the saturating add
-// (__vaddss2, a multi-instruction emulation on sm_100a).
-__global__ void __launch_bounds__(256) k_alu_probe(u32* out, int iters, int mode, u32 seed)
+// Issue rate of ONE packed instruction at a time, the way the MAP kernels use it: 8 independent dependency chains
+// per thread, 32 operations per chain and loop trip, every operation exactly one SASS instruction (checked with
+// cuobjdump: VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2).  op 4 is the saturating add
+// (__vaddss2, a multi-instruction emulation on sm_100a), counted per source operation.
+// Measured on B200: every one of the four native instructions issues at 0.5 warp-instructions per clock and SM
+// sub-partition (the integer pipe is 16 lanes wide), i.e. 64 packed operations = 128 int16 lane-ops per clock and SM.
+template <int OP>
+__global__ void __launch_bounds__(256) k_alu_probe(u32* out, int iters, u32 seed)
 {
   u32 a[8];
 #pragma unroll
   for (int i = 0; i < 8; i++)
     a[i] = seed * (threadIdx.x + 1) + i * 0x00010003u;
   const u32 g = seed | 0x00010001u;
-  if (mode == 0) {
-    for (int it = 0; it < iters; it++) {
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
 #pragma unroll
       for (int i = 0; i < 8; i++) {
-        a[i] = p_add_wrap(a[i], g);
-        a[i] = p_max(a[i], a[(i + 1) & 7]);
-        a[i] = p_addmax(a[i], g, a[(i + 3) & 7]);
-        a[i] = p_add_wrap(a[i], a[(i + 5) & 7]);
-      }
-    }
-  } else {
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        a[i] = p_add_sat(a[i], g);
-        a[i] = p_max(a[i], a[(i + 1) & 7]);
-        a[i] = p_max(p_add_sat(a[i], g), a[(i + 3) & 7]);
-        a[i] = p_add_sat(a[i], a[(i + 5) & 7]);
+        if (OP == 0)
+          a[i] = p_add_wrap(a[i], g);
+        if (OP == 1)
+          a[i] = p_max(a[i], a[(i + 1) & 7]);
+        if (OP == 2)
+          a[i] = p_addmax(a[i], g, a[(i + 3) & 7]);
+        if (OP == 3)
+          a[i] = p_max3(a[i], a[(i + 1) & 7], a[(i + 2) & 7]);
+        if (OP == 4)
+          a[i] = p_add_sat(a[i], g);
       }
     }
   }

@@ -5,7 +5,7 @@
 #include <cstring>
 #include <vector>
 
-#include "../../srsran_b200/csrc/map_core.cuh"
+#include "../../srsran_b200/csrc/map_f16.cuh"
 
 using namespace b200;
 
@@ -77,6 +77,143 @@ static int run(int N, int K, const int16_t* in, const int16_t* apr, const int16_
     }
   }
   return flagged;
+}
+
+// The arithmetic of k_map_f16 (srsran_b200/csrc/map_f16.cuh) for one code block: same sequence of packed operations,
+// same tracking points, the factored LLR, the head monitor of the first four forward steps -- only the memory staging
+// and the checkpoint/recompute of the beta values (deterministic, checked on the device) are replaced by a plain array.
+// Returns 1 if a range monitor could not rule out a saturation.
+static int run_f16(int N, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out, int g)
+{
+  using P = Fast16;
+  const int  T = N / 2, W = K / N;
+  const u32 *in32 = (const u32*)in, *apr32 = (const u32*)apr, *par32 = (const u32*)par;
+  auto row = [&](int p, int j, u32& x, u32& y) {
+    y = par32[p * T + j];
+    x = apr32 ? P::add(apr32[p * T + j], in32[p * T + j]) : in32[p * T + j];
+  };
+  std::vector<u32>      st((size_t)T * 8);
+  std::vector<RangeMon> mon_b(T), mon_a(T), mon_h(T);
+  for (int j = 0; j < T; j++) {
+    mon_b[j].reset();
+    mon_a[j].reset();
+    mon_h[j].reset();
+  }
+  auto S8 = [&](int j) -> u32(&)[8] { return *reinterpret_cast<u32(*)[8]>(&st[(size_t)j * 8]); };
+  // backward warm-up
+  for (int j = 0; j < T; j++) {
+    u32(&s)[8] = S8(j);
+    for (int i = 0; i < 8; i++)
+      s[i] = splat16(-P::kInf);
+    for (int k = kWinOverlap - 1; k >= 0; k--) {
+      u32 x, y;
+      row(k, j, x, y);
+      bwd_step<P>(s, x, y, P::add(x, y));
+      if ((k & 1) == 0) {
+        if (k < kWinOverlap - 2)
+          mon_b[j].track(s);
+        if (k != 0)
+          P::normalize_now(s);
+      }
+    }
+  }
+  {
+    std::vector<u32> old = st;
+    for (int j = 0; j < T; j++)
+      for (int s = 0; s < 8; s++) {
+        u32 nx                = j + 1 < T ? old[(size_t)(j + 1) * 8 + s] : old[(size_t)j * 8 + s];
+        st[(size_t)j * 8 + s] = shift_down_lanes(old[(size_t)j * 8 + s], nx);
+      }
+    int32_t t[8];
+    tail_trellis<P>(in + K, par + K, t);
+    for (int s = 0; s < 8; s++)
+      st[(size_t)(T - 1) * 8 + s] = (st[(size_t)(T - 1) * 8 + s] & 0xffffu) | ((u32)(uint16_t)t[s] << 16);
+  }
+  // backward main pass: beta[k] before normalisation
+  std::vector<std::vector<u32>> beta(T, std::vector<u32>((size_t)(W + 1) * 8));
+  int                           flagged = 0;
+  for (int j = 0; j < T; j++) {
+    u32(&s)[8] = S8(j);
+    mon_b[j].track(s);
+    memcpy(&beta[j][(size_t)W * 8], s, 32);
+    for (int k = W - 1; k >= 0; k--) {
+      u32 x, y;
+      row(k, j, x, y);
+      bwd_step<P>(s, x, y, P::add(x, y));
+      memcpy(&beta[j][(size_t)k * 8], s, 32);
+      if ((k & 1) == 0) {
+        mon_b[j].track(s);
+        if (k != 0)
+          P::normalize_now(s);
+      }
+    }
+    if (!fast16_beta_ok(mon_b[j].spread_lo(), g) || !fast16_beta_ok(mon_b[j].spread_hi(), g))
+      flagged = 1;
+  }
+  // forward warm-up (normalisation follows the loop counter)
+  for (int j = 0; j < T; j++) {
+    u32(&s)[8] = S8(j);
+    for (int i = 0; i < 8; i++)
+      s[i] = splat16(-P::kInf);
+    for (int kk = 0; kk < kWinOverlap; kk++) {
+      u32 x, y;
+      row(W - kWinOverlap + kk, j, x, y);
+      fwd_step<P>(s, x, y, P::add(x, y));
+      if ((kk & 1) == 0) {
+        if (kk > 2)
+          mon_a[j].track(s);
+        if (kk != 0)
+          P::normalize_now(s);
+      }
+    }
+  }
+  {
+    std::vector<u32> old = st;
+    for (int j = 0; j < T; j++)
+      for (int s = 0; s < 8; s++) {
+        u32 pv                = j > 0 ? old[(size_t)(j - 1) * 8 + s] : old[(size_t)j * 8 + s];
+        st[(size_t)j * 8 + s] = shift_up_lanes(pv, old[(size_t)j * 8 + s]);
+      }
+    st[0] &= 0xffff0000u;
+    for (int s = 1; s < 8; s++)
+      st[s] = (st[s] & 0xffff0000u) | (u32)(uint16_t)(-P::kInf);
+  }
+  // output pass
+  u32* o = (u32*)out;
+  for (int j = 0; j < T; j++) {
+    u32(&al)[8] = S8(j);
+    mon_h[j].track(al);
+    for (int p = 0; p < W; p++) {
+      u32 x, y, b[8];
+      row(p, j, x, y);
+      memcpy(b, &beta[j][(size_t)(p + 1) * 8], 32);
+      const u32 xy  = P::add(x, y);
+      const u32 llr = llr_factored<P>(al, b, x, y, xy, mon_a[j]);
+      fwd_step<P>(al, x, y, xy);
+      if ((p & 1) == 0) {
+        mon_a[j].track(al);
+        if (p != 0)
+          P::normalize_now(al);
+      }
+      o[p * T + j] = llr;
+      if (p == 3) { // what was tracked so far belongs to the head monitor
+        mon_h[j].hi = p_max(mon_h[j].hi, mon_a[j].hi);
+        mon_h[j].lo = p_min(mon_h[j].lo, mon_a[j].lo);
+        mon_a[j].hi = 0;
+        mon_a[j].lo = 0;
+      }
+    }
+    const bool bad = !fast16_alpha_ok(mon_a[j].spread_lo(), mon_b[j].spread_lo(), g) || !fast16_alpha_ok(mon_a[j].spread_hi(), mon_b[j].spread_hi(), g) ||
+                     !fast16_alpha_ok(mon_h[j].spread_lo(), mon_b[j].spread_lo(), g) || !fast16_alpha_ok(mon_h[j].spread_hi(), mon_b[j].spread_hi(), g) ||
+                     ((mon_a[j].ovf | mon_h[j].ovf) & 0x80008000u) != 0;
+    if (bad)
+      flagged = 1;
+  }
+  return flagged;
+}
+extern "C" int emul_map_f16(int N, int K, const int16_t* in, const int16_t* apr, const int16_t* par, int16_t* out, int g)
+{
+  return run_f16(N, K, in, apr, par, out, g);
 }
 
 // Fast16 with monitoring: returns the flag; g = bound on every |branch metric|

@@ -19,7 +19,7 @@ CSRC = os.path.join(os.path.dirname(HERE), "srsran_b200", "csrc")
 
 @pytest.fixture(scope="module")
 def emul():
-    deps = [SRC, os.path.join(CSRC, "map_core.cuh"), os.path.join(CSRC, "arith.cuh")]
+    deps = [SRC, os.path.join(CSRC, "map_core.cuh"), os.path.join(CSRC, "arith.cuh"), os.path.join(CSRC, "map_f16.cuh")]
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", SO, SRC])
     return C.CDLL(SO)
@@ -70,6 +70,35 @@ def test_fast16_monitor_is_sound(port, emul):
         else:
             clean += 1
             assert (got[:K] == want).all(), (N, K, amp, aamp, g, st.tolist())
+    assert flagged > 20 and clean > 20
+
+
+def test_f16_kernel_arithmetic_is_sound(port, emul):
+    """The arithmetic of the hot kernel k_map_f16 (factored LLR, head monitor for lane 0's known start state, tracking
+    points of its passes): whenever none of its monitors raises the replay flag the output must equal the saturating
+    oracle; across the amplitude sweep both outcomes must occur."""
+    rng = np.random.default_rng(7)
+    flagged = clean = 0
+    for trial in range(200):
+        N = (8, 16)[trial % 2]
+        K = (408, 816, 1008, 2048, 6144, 5824, 512, 800, 6080, 1056)[trial % 10]
+        if N == 16 and K <= 800:
+            N = 8
+        if K % N or K // N < 40:
+            continue
+        amp = int(10 ** rng.uniform(1.0, 4.3))
+        aamp = min(int(amp * rng.uniform(0.5, 4)), 32767)
+        a_in, a_par = random_llr(rng, K + 3, amp, np.int16), random_llr(rng, K + 3, amp, np.int16)
+        a_apr = random_llr(rng, K + 3, aamp, np.int16) if trial % 3 else None
+        g = int(np.abs(a_in[:K]).max()) + int(np.abs(a_par[:K]).max()) + (int(np.abs(a_apr[:K]).max()) if a_apr is not None else 0)
+        want = port.map_win(16, N, a_in, a_apr, a_par, K)
+        got = np.zeros(K + 3, np.int16)
+        f = emul.emul_map_f16(N, K, _p(a_in), _p(a_apr), _p(a_par), _p(got), g)
+        if f:
+            flagged += 1
+        else:
+            clean += 1
+            assert (got[:K] == want).all(), (N, K, amp, aamp, g)
     assert flagged > 20 and clean > 20
 
 
