@@ -312,7 +312,13 @@ def run_ours(args):
     from srsran_b200 import synth  # noqa: F401
     peaks, peak_src = load_peaks()
     ctx = b.Context(local)
-    ctx2 = b.Context(local)  # second engine (own stream) for the pipelined end-to-end path
+    # engines (= streams) of this GPU: batches rotate over them, so the latency-bound tail of one batch (last wave, code
+    # blocks that need all their iterations) overlaps the head of the next; the end-to-end loop also overlaps the
+    # H2D copy and host-side planning of one chunk with the decode of the previous ones
+    n_eng = max(2, args.engines)
+    all_ctx = [ctx] + [b.Context(local) for _ in range(n_eng - 1)]
+    ctx2 = all_ctx[1]
+    e2e_ctx = all_ctx
     rng = np.random.default_rng(shard_seed(rank))
     sampler = ClockSampler(local)
     launches = 0
@@ -335,25 +341,24 @@ def run_ours(args):
         h2d_b, d2h_b = llr.nbytes, ncb * K // 8
         workload = "c1-batched: %d code blocks x K=6144 x 4 half-iterations, int16 LLRs (standard order), no early stop" % ncb
 
-        d_out2 = ctx.device_alloc(ncb * K // 8)
-        engines = [(ctx, d_out), (ctx2, d_out2)]
+        engines = [(ctx, d_out)] + [(c, ctx.device_alloc(ncb * K // 8)) for c in all_ctx[1:]]
 
         def dev_submit(i):
-            e, o = engines[i & 1]
+            e, o = engines[i % n_eng]
             e.wait()  # the batch this engine ran two steps ago
             e.tdec_batch_device(d_llr, o, K, ncb, stride, 16, nit, input_sb=False, submit_only=True)
 
-        chunks = 4
+        chunks = args.e2e_chunks
         per = (ncb + chunks - 1) // chunks
 
         def e2e_step():
-            # (the two engines keep streaming across steps; e2e_drain() closes the timed region)
-            cs = [ctx, ctx2]
+            # (the engines keep streaming across steps; e2e_drain() closes the timed region)
+            cs = e2e_ctx
             for c in range(chunks):
                 lo, hi = c * per, min(ncb, (c + 1) * per)
                 if lo >= hi:
                     break
-                e = cs[c % 2]
+                e = cs[c % len(cs)]
                 e.wait()
                 e.tdec_batch_submit(pin_in.array[lo:hi].ctypes.data, pin_out.array[lo:hi].ctypes.data, K, hi - lo, stride, 16, nit)
 
@@ -380,21 +385,23 @@ def run_ours(args):
         workload = "%s: %d TBs x TBS %d (%d x K=%d), %s e-bits, rate de-matching + <=%d half-iterations with CRC early stop" % (
             args.workload, ntb, tbs, cfg["C"], cfg["K"], np.dtype(dt).name, cfg["max_iter"])
 
-        d_out2 = ctx.device_alloc(ntb * ostride)
-        tb_dev2 = b.make_tbs(ntb)
-        for i in range(ntb):
-            t = tb_dev2[i]
-            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = d_llr + i * G * esz, G, tbs, Qm, 0, None, d_out2 + i * ostride
-        engines = [(ctx, tb_dev), (ctx2, tb_dev2)]
+        engines = [(ctx, tb_dev)]
+        for c in all_ctx[1:]:
+            d_o = ctx.device_alloc(ntb * ostride)
+            tbd = b.make_tbs(ntb)
+            for i in range(ntb):
+                t = tbd[i]
+                t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = d_llr + i * G * esz, G, tbs, Qm, 0, None, d_o + i * ostride
+            engines.append((c, tbd))
 
         def dev_submit(i):
-            e, t = engines[i & 1]
+            e, t = engines[i % n_eng]
             e.wait()
             e.decode_tbs(t, dt == np.int8, cfg["max_iter"], flags=b.IN_DEVICE | b.OUT_DEVICE, submit_only=True)
 
         # end to end: the TTIs of a step go down in 4 chunks that alternate between the two engines, so the H2D copy
         # of one chunk overlaps the decode of the previous one
-        n_chunks = 4
+        n_chunks = args.e2e_chunks
         per = (ntb + n_chunks - 1) // n_chunks
         host_chunks = []
         for c in range(n_chunks):
@@ -408,9 +415,9 @@ def run_ours(args):
             host_chunks.append(arr)
 
         def e2e_step():
-            cs = [ctx, ctx2]
+            cs = e2e_ctx
             for c, arr in enumerate(host_chunks):
-                e = cs[c & 1]
+                e = cs[c % len(cs)]
                 e.wait()
                 e.decode_tbs(arr, dt == np.int8, cfg["max_iter"], flags=0, submit_only=True)
 
@@ -425,25 +432,26 @@ def run_ours(args):
         return e.last_launches(), e.last_map_ms(), e.last_map_launches()
 
     sampler.start()
-    for i in range(max(args.warmup, 2)):
+    for i in range(max(args.warmup, n_eng)):
         dev_submit(i)
-    ctx.wait()
-    ctx2.wait()
+    for c in all_ctx:
+        c.wait()
     replay[0] = replay[1] = 0
     barrier()
     sampler.mark()
     ctx.timer_start()
     map_ms, map_launches = 0.0, 0
     for i in range(args.steps):
-        e = engines[i & 1][0]
-        if i >= 2:
+        e = engines[i % n_eng][0]
+        if i >= n_eng:
             e.wait()
             l, mm, ml = stats(e)
             launches += l
             map_ms += mm
             map_launches += ml
         dev_submit(i)
-    for e in ([ctx2, ctx] if args.steps & 1 else [ctx, ctx2])[:min(2, args.steps)]:
+    for i in range(max(0, args.steps - n_eng), args.steps): # the batches still in flight, oldest first
+        e = engines[i % n_eng][0]
         e.wait()
         l, mm, ml = stats(e)
         launches += l
@@ -457,8 +465,8 @@ def run_ours(args):
 
     # ---- end to end through the C ABI with host buffers
     def e2e_drain():
-        ctx.wait()
-        ctx2.wait()
+        for e in e2e_ctx:
+            e.wait()
 
     for _ in range(max(1, args.warmup // 2)):
         e2e_step()
@@ -553,7 +561,8 @@ def run_ours(args):
         line = {"metric": "turbo_decoded_mbps", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int8" if args.workload == "c4" else "int16", "data": "synthetic",
-                "config": {"workload": workload, "l2": "inputs (%.0f MB per GPU per step) larger than the 126 MB L2" % (h2d_b / 1e6), "parallelism": "batch-sharded x%d, no collective" % world},
+                "config": {"workload": workload, "l2": "inputs (%.0f MB per GPU per step) larger than the 126 MB L2" % (h2d_b / 1e6),
+                           "parallelism": "batch-sharded x%d, no collective" % world, "engines_per_gpu": n_eng, "e2e_chunks_per_step": args.e2e_chunks},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d_b * world), "d2h_bytes_per_step": int(d2h_b * world)},
                 "gpu_launches": int(launches * world), "latency": latency, "roofline": roofline}
@@ -578,6 +587,8 @@ def main():
     ap.add_argument("--ntb", type=int, default=1000, help="transport blocks per step per GPU (c2/c4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--engines", type=int, default=4, help="engines (streams) per GPU the batches / end-to-end chunks rotate over")
+    ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks one end-to-end step is split into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

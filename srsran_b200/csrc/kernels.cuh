@@ -971,10 +971,9 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
   const uint32_t n_iter = n_iter0 + 1; // the half-iteration that just ran
   const int      lane   = threadIdx.x & 31;
   const bool     need   = active && (d.crc_poly != 0 || n_iter >= d.max_iter);
-  const int      any    = __syncthreads_or((active ? 1 : 0) | (need && d.crc_poly != 0 ? 2 : 0));
-  if (!any)
+  if (!__syncthreads_or(active))
     return; // none of this block's code blocks is still being decoded
-  if (any & 2) { // (run_all semantics: no CRC, the tables are not needed)
+  if (__syncthreads_or(need && d.crc_poly != 0)) { // (run_all semantics: no CRC, the tables are not needed)
     load_crc_tables(s_tab);
     __syncthreads();
   }
