@@ -379,15 +379,15 @@ static int encode_group_map(CUtensorMap* out, int16_t* base, uint32_t lanes, uin
   return 0;
 }
 
-template <int N, int NT, int MINB, int STAGES>
+template <class P, int N, int NT, int MINB, int STAGES>
 static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaStream_t st)
 {
   constexpr int T = N / 2, G = 32 / T;
   const int     warps  = (n_slots + G - 1) / G;
   const int     blocks = (warps + (NT / 32) - 1) / (NT / 32);
   const size_t  smem   = (size_t)(NT / 32) * F16Lay<T, STAGES>::kWarpWords * 4;
-  void (*kern)(const MapArgs) = (n_iter & 1) ? k_map_f16<N, 2, NT, MINB, STAGES>
-                                             : (n_iter ? k_map_f16<N, 1, NT, MINB, STAGES> : k_map_f16<N, 0, NT, MINB, STAGES>);
+  void (*kern)(const MapArgs) = (n_iter & 1) ? k_map_f16<P, N, 2, NT, MINB, STAGES>
+                                             : (n_iter ? k_map_f16<P, N, 1, NT, MINB, STAGES> : k_map_f16<P, N, 0, NT, MINB, STAGES>);
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
@@ -523,15 +523,13 @@ int Engine::run(Plan& p)
 
   // tensor maps of the K-groups (TMA staging of the windowed MAP kernel): [2g] 3-plane box, [2g+1] 2-plane box
   const uint32_t seg_len = map_seg_len();
-  const bool     use_tmaps = opt_fast16;
+  const bool     use_tmaps = true;
   if (use_tmaps && !groups.empty()) {
     if (d_tmaps.reserve(groups.size() * 2 * sizeof(CUtensorMap)) || h_tmaps.reserve(groups.size() * 2 * sizeof(CUtensorMap)))
       return SRSLTE_B200_ERROR;
     CUtensorMap* hm = (CUtensorMap*)h_tmaps.ptr;
     for (size_t gi = 0; gi < groups.size(); gi++) {
       const KGroup& g = groups[gi];
-      if (g.cls >= 2)
-        continue; // the int8 classes run k_map_win (per-thread staging)
       for (uint32_t v = 0; v < 2; v++)
         if (encode_group_map(&hm[2 * gi + v], d_ws.ptr + g.ws_off, kWinClasses[g.cls].lanes, g.n_blocks, g.W, g.ps, seg_len, v == 0 ? 3 : 2))
           return SRSLTE_B200_ERROR;
@@ -627,19 +625,18 @@ int Engine::run(Plan& p)
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
         switch (opt_map_cfg & 0xff) {
-          case 1: e = c == 0 ? launch_map_f16<8, 256, 2, 2>(a, ns, n_it, stream) : launch_map_f16<16, 256, 2, 2>(a, ns, n_it, stream); break;
-          case 2: e = c == 0 ? launch_map_f16<8, 256, 1, 3>(a, ns, n_it, stream) : launch_map_f16<16, 256, 1, 3>(a, ns, n_it, stream); break;
-          default: e = c == 0 ? launch_map_f16<8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<16, 128, 3, 3>(a, ns, n_it, stream); break;
+          case 1: e = c == 0 ? launch_map_f16<Fast16, 8, 256, 2, 2>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 256, 2, 2>(a, ns, n_it, stream); break;
+          default: e = c == 0 ? launch_map_f16<Fast16, 8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 128, 3, 3>(a, ns, n_it, stream); break;
         }
         CUDA_OK(e);
         last_launches++;
         a.mode = 2;
       }
       switch (c) {
-        case 0: e = launch_map<Sat16, 8>(a, cls[c].n_slots, cls[c].max_w, stream); break;
-        case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break;
-        case 2: e = launch_map<Sat8, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break;
-        default: e = launch_map<Sat8, 32>(a, cls[c].n_slots, cls[c].max_w, stream); break;
+        case 0: e = launch_map<Sat16, 8>(a, cls[c].n_slots, cls[c].max_w, stream); break;  // exact replay of flagged blocks
+        case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break; // (or everything, fast16 off)
+        case 2: e = launch_map_f16<Sat8, 16, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream); break;
+        default: e = launch_map_f16<Sat8, 32, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream); break;
       }
       CUDA_OK(e);
       CUDA_OK(cudaEventRecord(e1, stream));

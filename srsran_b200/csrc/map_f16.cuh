@@ -102,11 +102,11 @@ struct F16Lay {
 };
 
 // MODE: 0 = DEC1 without a-priori input, 1 = DEC1 with a-priori input, 2 = DEC2
-template <int N, int MODE, int NT, int MINB, int STAGES>
+template <class P, int N, int MODE, int NT, int MINB, int STAGES>
 __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
 {
-  using P = Fast16;
   constexpr int  T = N / 2, G = 32 / T;
+  constexpr int  kNP = P::kNormPeriod; // normalisation cadence of the reference: 2 (int16, by state 0) or 1 (int8, by the max)
   constexpr bool kDec2 = MODE == 2, kApr = MODE == 1;
   using Lay = F16Lay<T, STAGES>;
   constexpr int kStages = STAGES;
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   const int j     = lane % T;
   const int cb    = slot < a.n_slots ? a.work[slot] : -1;
   bool      live  = cb >= 0;
-  uint32_t  d_W = 0, d_K = 0, d_ps = 0, d_qpp = 0, n_iter0 = 0;
+  uint32_t  d_W = 0, d_K = 0, d_ps = 0, d_qpp = 0, d_sat = 0, n_iter0 = 0;
   uint64_t  d_ws = 0;
   if (live) {
     const CbDev*   dp = a.cbs + cb;
@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
     d_K     = dp->K;
     d_ps    = dp->ps;
     d_qpp   = dp->qpp_off;
+    d_sat   = dp->sat_end;
     d_ws    = dp->ws_off;
     n_iter0 = sp->n_iter;
     if (sp->done || n_iter0 >= dp->max_iter)
@@ -262,12 +263,10 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       u32 x, y;
       row(tb, i, x, y);
       bwd_step<P>(st, x, y, P::add(x, y));
-      if ((i & 1) == 0) {
-        if (t < 4 || i < 6)
-          mon_b.track(st); // k < 38: the first two steps start from eight equal values (spread 0, covered by g)
-        if (i != 0 || t != 0)
-          P::normalize_now(st);
-      }
+      if (P::kMonitor && (i & 1) == 0 && (t < 4 || i < 6))
+        mon_b.track(st); // k < 38: the first two steps start from eight equal values (spread 0, covered by g)
+      if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+        P::normalize_now(st);
     }
   }
   // hand the estimate to the lane below; tail trellis for the last lane (win.h:580-612, 500-548)
@@ -296,7 +295,8 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       }
     }
   };
-  mon_b.track(st);
+  if (P::kMonitor)
+    mon_b.track(st);
   ck_store(nT, st);
   {
     int t = nT - 1;
@@ -309,11 +309,10 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         bwd_step<P>(st, x, y, P::add(x, y));
         if (i == 0)
           ck_store(t, st);
-        if ((i & 1) == 0) {
+        if (P::kMonitor && (i & 1) == 0)
           mon_b.track(st);
-          if (i != 0 || t != 0)
-            P::normalize_now(st);
-        }
+        if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+          P::normalize_now(st);
       }
       t--;
     }
@@ -326,11 +325,10 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         bwd_step<P>(st, x, y, P::add(x, y));
         if (i == 0)
           ck_store(t, st);
-        if ((i & 1) == 0) {
+        if (P::kMonitor && (i & 1) == 0)
           mon_b.track(st);
-          if (i != 0 || t != 0)
-            P::normalize_now(st);
-        }
+        if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+          P::normalize_now(st);
       }
     }
   }
@@ -339,8 +337,8 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
 
   // bound on every |branch metric| of this call: max|a-priori| + max|systematic| + max|parity|
   int*      gm = a.gmax + (size_t)(live ? cb : 0) * 4;
-  const int g  = kDec2 ? gm[3] + gm[2] : (kApr ? gm[3] : 0) + gm[0] + gm[1];
-  {
+  const int g  = !P::kMonitor ? 0 : kDec2 ? gm[3] + gm[2] : (kApr ? gm[3] : 0) + gm[0] + gm[1];
+  if (P::kMonitor) {
     const bool bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
     if (__any_sync(gmask, bad && live)) { // the whole code block is replayed with the exact policy (mode 2 launch)
       if (j == 0 && live && !(a.mode & 0xfe00))
@@ -365,12 +363,10 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         u32 x, y;
         row(tb, i, x, y);
         fwd_step<P>(st, x, y, P::add(x, y));
-        if ((kk & 1) == 0) {
-          if (kk > 2)
-            mon_a.track(st);
-          if (kk != 0)
-            P::normalize_now(st);
-        }
+        if (P::kMonitor && (kk & 1) == 0 && kk > 2)
+          mon_a.track(st);
+        if ((kNP == 1 || (kk & 1) == 0) && kk != 0)
+          P::normalize_now(st);
       }
     }
   }
@@ -388,7 +384,8 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   }
   // The first four steps (and the start state) are tracked by mon_h: the -INF entries of lane 0 widen the spread
   // only there (after three steps every state is reachable from state 0), and both monitors are checked below.
-  mon_h.track(st);
+  if (P::kMonitor)
+    mon_h.track(st);
 
   // ---- output pass
   u32* const     post  = (u32*)(ws + kPlPost * ps);
@@ -404,20 +401,27 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   auto out_step = [&](const u32* tb, int t, int i, const u32 (&b)[8], RangeMon& mon, bool norm) {
     u32 x, y;
     row(tb, i, x, y);
-    const u32 xy  = P::add(x, y);
-    const u32 llr = llr_factored<P>(al, b, x, y, xy, mon);
-    fwd_step<P>(al, x, y, xy);
-    if ((i & 1) == 0) {
-      mon.track(al);
-      if (norm)
-        P::normalize_now(al);
+    const u32 xy = P::add(x, y);
+    u32       llr;
+    if (P::kMonitor) { // wrapping arithmetic under the range monitor: factored form
+      llr = llr_factored<P>(al, b, x, y, xy, mon);
+      fwd_step<P>(al, x, y, xy);
+    } else { // saturating arithmetic: the operation order of the reference is part of the result
+      llr = fwd_step_llr<P>(al, b, x, y, xy, mon);
     }
+    if (P::kMonitor && (i & 1) == 0)
+      mon.track(al);
+    if ((kNP == 1 || (i & 1) == 0) && norm)
+      P::normalize_now(al);
     const u32 r = tb[Lay::kLutOff + i * T + j - lane];
     if (!kDec2) {
       // a-posteriori -> post (linear); extrinsic - a-priori -> app2[rev[.]]
-      const u32 e = kApr ? P::sub(llr, tb[2 * Lay::kPlaneWords + i * 32]) : llr;
-      ehi         = p_max(ehi, e);
-      elo         = p_min(elo, e);
+      const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
+      const u32      e  = kApr ? P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat) : llr;
+      if (P::kMonitor) {
+        ehi = p_max(ehi, e);
+        elo = p_min(elo, e);
+      }
       if (live && !(a.mode & 0x2000))
         post[(8 * t + i) * T + j] = llr;
       if (live && !(a.mode & 0x1000)) {
@@ -426,10 +430,12 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       }
     } else {
       // a-posteriori -> post[fwd[.]]; a-posteriori - own input -> a-priori[fwd[.]]
-      const u32 e = P::sub(llr, x);
-      ehi         = p_max(ehi, e);
-      elo         = p_min(elo, e);
       const uint32_t t0 = r & 0xffffu, t1 = r >> 16;
+      const u32      e  = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
+      if (P::kMonitor) {
+        ehi = p_max(ehi, e);
+        elo = p_min(elo, e);
+      }
       if (live && !(a.mode & 0x1000)) {
         ext[t0]    = (int16_t)lo16(e);
         ext[t1]    = (int16_t)hi16(e);
@@ -469,14 +475,14 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         for (int s = 0; s < 8; s++)
           bs[kk - 1][s] = st[s];
       }
-      if ((kk & 1) == 0)
+      if (kNP == 1 || (kk & 1) == 0)
         P::normalize_now(st);
     }
     // ---- steps 8t .. 8t+3 against beta_{8t+1} .. beta_{8t+4}
 #pragma unroll
     for (int i = 0; i < 4; i++)
       out_step(tb, t, i, bs[i], mon_a, i != 0 || t != 0);
-    if (t == 0) { // what was tracked so far belongs to the head monitor
+    if (P::kMonitor && t == 0) { // what was tracked so far belongs to the head monitor
       mon_h.hi = p_max(mon_h.hi, mon_a.hi);
       mon_h.lo = p_min(mon_h.lo, mon_a.lo);
       mon_a.hi = 0;
@@ -508,19 +514,19 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         u32 x, y;
         row(tb, kk, x, y);
         bwd_step<P>(b, x, y, P::add(x, y));
-        if (kk > i + 1 && (kk & 1) == 0)
+        if (kk > i + 1 && (kNP == 1 || (kk & 1) == 0))
           P::normalize_now(b);
       }
       out_step(tb, t, i, b, mon_a, true); // (t >= 5 here: a lane has at least 40 steps)
     }
   }
 
-  // max |extrinsic| handed to the next half-iteration (its a-priori / systematic input)
-  int ge = max(max(lo16(ehi), hi16(ehi)), max(-lo16(elo), -hi16(elo)));
+  if (P::kMonitor) {
+    // max |extrinsic| handed to the next half-iteration (its a-priori / systematic input)
+    int ge = max(max(lo16(ehi), hi16(ehi)), max(-lo16(elo), -hi16(elo)));
 #pragma unroll
-  for (int o = T / 2; o >= 1; o >>= 1)
-    ge = max(ge, __shfl_xor_sync(gmask, ge, o, T));
-  {
+    for (int o = T / 2; o >= 1; o >>= 1)
+      ge = max(ge, __shfl_xor_sync(gmask, ge, o, T));
     const bool bad = !fast16_alpha_ok(mon_a.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_a.spread_hi(), mon_b.spread_hi(), g) ||
                      !fast16_alpha_ok(mon_h.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_h.spread_hi(), mon_b.spread_hi(), g) ||
                      ((mon_a.ovf | mon_h.ovf) & 0x80008000u) != 0;
@@ -529,9 +535,9 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
         a.state[cb].redo = 1;
       return;
     }
+    if (j == 0 && live)
+      gm[3] = ge;
   }
-  if (j == 0 && live)
-    gm[3] = ge;
 }
 
 #endif // __CUDACC__
