@@ -437,6 +437,7 @@ int Engine::run(Plan& p)
   struct ClassRun {
     size_t off, winfo_off;
     int    n_slots, max_w;
+    bool   no_crc; // run_all semantics for every block of the class: only the last half-iteration's decisions are read
   } cls[4];
   struct KGroup { // code blocks of one size in one decoder class: consecutive slots, consecutive workspace
     int      cls, first_slot, n_blocks;
@@ -482,6 +483,10 @@ int Engine::run(Plan& p)
     cls[c].winfo_off = add_list(winfo);
     cls[c].n_slots   = (int)w.size();
     cls[c].max_w     = max_w;
+    cls[c].no_crc    = true;
+    for (int i : ids)
+      if (p.cbs[i].crc_poly != 0 || p.cbs[i].max_iter != p.iter0 + p.max_iter)
+        cls[c].no_crc = false;
   }
   // generic decoder: pairs of equal K
   std::vector<int> gen_pairs;
@@ -617,10 +622,12 @@ int Engine::run(Plan& p)
         return SRSLTE_B200_ERROR;
       CUDA_OK(cudaEventRecord(e0, stream));
       cudaError_t e;
+      // the a-posteriori plane is only read by the hard decision: skip writing it when no decision follows this launch
+      const int   skip_post = (cls[c].no_crc && it + 1 < p.max_iter) ? 0x2000 : 0;
       const bool  fast = opt_fast16 && c < 2;
       if (fast) {
         // native packed-instruction attempt with range monitoring, then exact replay of the flagged code blocks
-        a.mode = 1;
+        a.mode = 1 | skip_post;
         a.mode |= opt_map_cfg & 0xff00; // (measurement switches of k_map_f16)
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
@@ -635,8 +642,14 @@ int Engine::run(Plan& p)
       switch (c) {
         case 0: e = launch_map<Sat16, 8>(a, cls[c].n_slots, cls[c].max_w, stream); break;  // exact replay of flagged blocks
         case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break; // (or everything, fast16 off)
-        case 2: e = launch_map_f16<Sat8, 16, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream); break;
-        default: e = launch_map_f16<Sat8, 32, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream); break;
+        case 2:
+          a.mode |= skip_post;
+          e = launch_map_f16<Sat8, 16, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream);
+          break;
+        default:
+          a.mode |= skip_post;
+          e = launch_map_f16<Sat8, 32, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream);
+          break;
       }
       CUDA_OK(e);
       CUDA_OK(cudaEventRecord(e1, stream));

@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   if (P::kMonitor) {
     const bool bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
     if (__any_sync(gmask, bad && live)) { // the whole code block is replayed with the exact policy (mode 2 launch)
-      if (j == 0 && live && !(a.mode & 0xfe00))
+      if (j == 0 && live && !(a.mode & 0xde00))
         a.state[cb].redo = 1;
       live = false;
     }
@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
                      !fast16_alpha_ok(mon_h.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_h.spread_hi(), mon_b.spread_hi(), g) ||
                      ((mon_a.ovf | mon_h.ovf) & 0x80008000u) != 0;
     if (__any_sync(gmask, bad && live)) {
-      if (j == 0 && live && !(a.mode & 0xfe00))
+      if (j == 0 && live && !(a.mode & 0xde00))
         a.state[cb].redo = 1;
       return;
     }
