@@ -483,8 +483,10 @@ def run_ours(args):
     # ---- per-TTI latency (second half of the metric): ONE subframe's worth of work submitted from host buffers,
     #      submit -> results on the host, back to back on an otherwise idle GPU
     lat = []
-    n_lat = 300
-    if args.workload == "c1":
+    n_lat = 0 if args.no_latency else 300
+    if n_lat == 0:
+        tti_desc = "skipped (--no-latency)"
+    elif args.workload == "c1":
         tti_cb = 13
         tti_desc = "%d code blocks x K=6144 x 4 half-iterations (one 75 kbit subframe), host buffers in and out" % tti_cb
         for i in range(n_lat + 20):
@@ -503,8 +505,11 @@ def run_ours(args):
             t0 = time.perf_counter()
             ctx.decode_tbs(one, dt == np.int8, cfg["max_iter"], flags=0)
             lat.append(time.perf_counter() - t0)
-    lat = np.sort(np.array(lat[20:])) * 1e6
-    latency = {"tti": tti_desc, "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "max_us": float(lat[-1]), "n": int(len(lat))}
+    if n_lat:
+        lat = np.sort(np.array(lat[20:])) * 1e6
+        latency = {"tti": tti_desc, "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "max_us": float(lat[-1]), "n": int(len(lat))}
+    else:
+        latency = {"tti": tti_desc, "p50_us": None, "p99_us": None, "max_us": None, "n": 0}
     barrier()
 
     if args.workload != "c1":
@@ -587,6 +592,7 @@ def main():
     ap.add_argument("--ntb", type=int, default=1000, help="transport blocks per step per GPU (c2/c4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-latency", action="store_true", help="skip the per-TTI latency loop (keeps profiler launch lists short)")
     ap.add_argument("--engines", type=int, default=4, help="engines (streams) per GPU the batches / end-to-end chunks rotate over")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks one end-to-end step is split into")
     args = ap.parse_args()

@@ -14,7 +14,10 @@ KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "la
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__icc_request_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__icc_request_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tma.avg.pct_of_peak_sustained_active",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+        "smsp__warps_eligible.avg.per_cycle_active", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.per_cycle_active"]
 
 
 def main():
@@ -38,32 +41,42 @@ def main():
     rows = list(csv.reader(src.splitlines()))
     if len(rows) < 3:
         return
-    hdr = rows[1]
-    ix = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[2:] if len(r) >= len(hdr)]
-    stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-    tot, opc, ops = collections.Counter(), collections.Counter(), collections.Counter()
-    per = []
-    for r in data:
-        n = int(r[ix["# Samples"]] or 0)
-        ex = int(r[ix["Instructions Executed"]] or 0)
-        for s in stalls:
-            tot[s] += int(r[ix[s]] or 0)
-        t = r[ix["Source"]].split()
-        op = (t[1] if t and t[0].startswith("@") else (t[0] if t else "")).split(".")[0]
-        opc[op] += ex
-        ops[op] += n
-        per.append((n, r[ix["Source"]], ex))
+    # one section per profiled launch: a title row (kernel name), a header row (starts with "Address"), then data rows
+    sections, title = [], ""
+    for r in rows:
+        if r and r[0] == "Address":
+            sections.append({"title": title, "hdr": r, "data": []})
+        elif sections and len(r) >= len(sections[-1]["hdr"]):
+            sections[-1]["data"].append(r)
+        elif r:
+            title = r[1] if len(r) > 1 else r[0]
     with open(out + ".hotspots.txt", "w") as f:
-        f.write(rows[0][1] + "\n")
-        f.write("warp-level instructions executed: %d\n" % sum(opc.values()))
-        f.write("stall samples by reason: %s\n\n" % dict(tot.most_common()))
-        f.write("instruction class: executed (warp-level), stall samples\n")
-        for k, v in opc.most_common(24):
-            f.write("  %-12s %12d %8d\n" % (k, v, ops[k]))
-        f.write("\ntop stalled SASS lines: samples | executed | instruction\n")
-        for n, s, ex in sorted(per, key=lambda x: -x[0])[:30]:
-            f.write("  %6d %10d  %s\n" % (n, ex, s[:100]))
+        for sec in sections:
+            hdr, data = sec["hdr"], sec["data"]
+            ix = {h: i for i, h in enumerate(hdr)}
+            stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
+            tot, opc, ops = collections.Counter(), collections.Counter(), collections.Counter()
+            per = []
+            for r in data:
+                n = int(r[ix["# Samples"]] or 0)
+                ex = int(r[ix["Instructions Executed"]] or 0)
+                for st in stalls:
+                    tot[st] += int(r[ix[st]] or 0)
+                t = r[ix["Source"]].split()
+                op = (t[1] if t and t[0].startswith("@") else (t[0] if t else "")).split(".")[0]
+                opc[op] += ex
+                ops[op] += n
+                per.append((n, r[ix["Source"]], ex))
+            f.write(sec["title"] + "\n")
+            f.write("warp-level instructions executed: %d\n" % sum(opc.values()))
+            f.write("stall samples by reason: %s\n\n" % dict(tot.most_common()))
+            f.write("instruction class: executed (warp-level), stall samples\n")
+            for k, v in opc.most_common(24):
+                f.write("  %-12s %12d %8d\n" % (k, v, ops[k]))
+            f.write("\ntop stalled SASS lines: samples | executed | instruction\n")
+            for n, sline, ex in sorted(per, key=lambda x: -x[0])[:16]:
+                f.write("  %6d %10d  %s\n" % (n, ex, sline[:100]))
+            f.write("\n")
 
 
 if __name__ == "__main__":
