@@ -525,11 +525,12 @@ def run_ours(args):
     #      (one engine, batches back to back, CUDA events around every launch on the launching stream).
     rsteps = max(1, min(5, args.steps))
     ctx.timer_start()
-    r_map_ms, r_map_launches = 0.0, 0
+    r_map_ms, r_map_launches, r_gpu_ms = 0.0, 0, 0.0
     for i in range(rsteps):
         dev_submit(0)
         ctx.wait()
         r_map_ms += ctx.last_map_ms()
+        r_gpu_ms += ctx.last_gpu_ms()
         r_map_launches += ctx.last_map_launches()
     ms_single = ctx.timer_stop_ms() / rsteps
     # peak: issue rate of the packed instructions the kernel is made of, each measured on its own (VIADD.16x2, VIMNMX.S16x2,
@@ -547,7 +548,9 @@ def run_ours(args):
                 "traffic": None if traffic is None else traffic["bytes_per_cb"] * (units_per_step / K if args.workload == "c1" else cfg["C"] * ntb),
                 "traffic_source": None if traffic is None else traffic["source"],
                 "kernel": "k_map_f16", "launches": map_launches, "avg_launch_ms": 1e3 * map_s_per_launch,
-                "map_share_of_step": (r_map_ms / rsteps) / ms_single, "single_stream_mbps": units_per_step / (ms_single * 1e-3) / 1e6,
+                # share of the batch's device time (first kernel -> last kernel, CUDA events) spent in the MAP launches
+                "map_share_of_step": r_map_ms / r_gpu_ms if r_gpu_ms else None, "batch_device_ms": r_gpu_ms / rsteps,
+                "single_stream_mbps": units_per_step / (ms_single * 1e-3) / 1e6,
                 "peak_source": "live micro-benchmark (k_alu_probe): min over VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2 of the packed "
                                "instruction rate, x2 int16 lanes; algorithmic work = 82 (int8: 106) lane-ops per trellis step and half-iteration",
                 "probe_packed_tops": [x / 1e12 for x in probes],

@@ -160,7 +160,48 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
     // decoder's layout with consecutive threads writing consecutive elements (both sides coalesced)
     extern __shared__ __align__(16) int16_t s_in[];
     const uint32_t n_in = 3 * K + 12;
-    if (d.in_bits == 16 && d.bits == 16 && (((uintptr_t)in16) & 7u) == 0) {
+    const bool     vec  = d.in_bits == 16 && d.bits == 16 && (((uintptr_t)in16) & 7u) == 0;
+    if (vec && N && (W & 3u) == 0 && (blockDim.x % (N / 2)) == 0) {
+      // Fast transposition (the common case: int16 LLRs into an int16 windowed decoder).  The block is staged with one
+      // word of padding per decoder lane, so the N/2 threads that build the words (lane 2j, lane 2j+1) of one step read
+      // different banks; every thread then emits whole 32-bit words of all three planes with consecutive threads
+      // writing consecutive words.
+      const uint32_t LW = 3 * W, hw = N / 2, hsh = 31 - __clz(hw), nth = blockDim.x; // LW: int16 per lane region
+      {
+        const uint2* src = reinterpret_cast<const uint2*>(in16);
+        u32*         dst = reinterpret_cast<u32*>(s_in);
+        for (uint32_t i = threadIdx.x; i < 3 * K / 4; i += nth) {
+          const uint2    v  = __ldg(src + i);
+          const uint32_t e  = 4 * i, dl = e / LW; // 8-byte pieces never straddle two lane regions (LW % 4 == 0)
+          dst[e / 2 + dl]     = v.x;
+          dst[e / 2 + dl + 1] = v.y;
+        }
+      }
+      __syncthreads();
+      const uint32_t jj = threadIdx.x & (hw - 1);
+      const int16_t* la = s_in + (2 * jj) * (LW + 2);
+      const int16_t* lb = s_in + (2 * jj + 1) * (LW + 2);
+      u32*           q0 = reinterpret_cast<u32*>(p0);
+      u32*           q1 = reinterpret_cast<u32*>(p0 + kPlPar0 * (size_t)d.ps);
+      u32*           q2 = reinterpret_cast<u32*>(p0 + kPlPar1 * (size_t)d.ps);
+      u32            h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
+      for (uint32_t p = threadIdx.x >> hsh; p < W; p += nth >> hsh) {
+        const uint32_t w  = p * hw + jj;
+        const u32      v0 = (u32)(uint16_t)la[3 * p] | ((u32)(uint16_t)lb[3 * p] << 16);
+        const u32      v1 = (u32)(uint16_t)la[3 * p + 1] | ((u32)(uint16_t)lb[3 * p + 1] << 16);
+        const u32      v2 = (u32)(uint16_t)la[3 * p + 2] | ((u32)(uint16_t)lb[3 * p + 2] << 16);
+        q0[w] = v0;
+        q1[w] = v1;
+        q2[w] = v2;
+        h0 = p_max(h0, v0); l0 = p_min(l0, v0);
+        h1 = p_max(h1, v1); l1 = p_min(l1, v1);
+        h2 = p_max(h2, v2); l2 = p_min(l2, v2);
+      }
+      g0 = max(max(lo16(h0), hi16(h0)), max(-lo16(l0), -hi16(l0)));
+      g1 = max(max(lo16(h1), hi16(h1)), max(-lo16(l1), -hi16(l1)));
+      g2 = max(max(lo16(h2), hi16(h2)), max(-lo16(l2), -hi16(l2)));
+    } else {
+    if (vec) {
       // 8-byte vector loads (n_in is a multiple of 4)
       const uint2* src = reinterpret_cast<const uint2*>(in16);
       uint2*       dst = reinterpret_cast<uint2*>(s_in);
@@ -227,6 +268,7 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
         amax(g0, a); amax(g1, b); amax(g2, c);
       }
     }
+    } // (general path)
   }
   if (threadIdx.x < 12) { // (the shared-memory copy is not used here: generic inputs may not have filled it)
     const uint32_t tb = d.in_sb ? 3 * (K + kSbPadDev) : 3 * K;
