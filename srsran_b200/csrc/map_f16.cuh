@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   u32* const     post  = (u32*)(ws + kPlPost * ps);
   int16_t* const post16 = ws + kPlPost * ps;
   int16_t* const ext   = kDec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps; // extrinsic output, scattered through the QPP table
-  u32            ehi = 0, elo = 0;
+  u32            ehi = 0, elo = 0, e_even = 0;
   u32            al[8];
 #pragma unroll
   for (int s = 0; s < 8; s++)
@@ -413,29 +413,36 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       mon.track(al);
     if ((kNP == 1 || (i & 1) == 0) && norm)
       P::normalize_now(al);
-    const u32 r = tb[Lay::kLutOff + i * T + j - lane];
+    // the two scatter targets of this thread (QPP table word = two uint16 indices), read as halves: two LDS.U16 on the
+    // load/store pipe instead of LDS + LOP3 + SHF on the max-type integer pipe, which is the busiest one
+    const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tb + (Lay::kLutOff + i * T + j - lane));
+    const uint32_t  t0 = r16[0], t1 = r16[1];
+    // running max / min of the extrinsic values, two steps per VIMNMX3
+    auto track_e = [&](u32 e) {
+      if (P::kMonitor) {
+        if ((i & 1) == 0) {
+          e_even = e;
+        } else {
+          ehi = p_max3(ehi, e_even, e);
+          elo = p_min3(elo, e_even, e);
+        }
+      }
+    };
     if (!kDec2) {
       // a-posteriori -> post (linear); extrinsic - a-priori -> app2[rev[.]]
       const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
       const u32      e  = kApr ? P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat) : llr;
-      if (P::kMonitor) {
-        ehi = p_max(ehi, e);
-        elo = p_min(elo, e);
-      }
+      track_e(e);
       if (live && !(a.mode & 0x2000))
         post[(8 * t + i) * T + j] = llr;
       if (live && !(a.mode & 0x1000)) {
-        ext[r & 0xffffu]          = (int16_t)lo16(e);
-        ext[r >> 16]              = (int16_t)hi16(e);
+        ext[t0] = (int16_t)lo16(e);
+        ext[t1] = (int16_t)hi16(e);
       }
     } else {
       // a-posteriori -> post[fwd[.]]; a-posteriori - own input -> a-priori[fwd[.]]
-      const uint32_t t0 = r & 0xffffu, t1 = r >> 16;
-      const u32      e  = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
-      if (P::kMonitor) {
-        ehi = p_max(ehi, e);
-        elo = p_min(elo, e);
-      }
+      const u32 e = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
+      track_e(e);
       if (live && !(a.mode & 0x1000)) {
         ext[t0]    = (int16_t)lo16(e);
         ext[t1]    = (int16_t)hi16(e);
@@ -523,6 +530,8 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
 
   if (P::kMonitor) {
     // max |extrinsic| handed to the next half-iteration (its a-priori / systematic input)
+    ehi    = p_max(ehi, e_even); // (an odd number of steps leaves the last one pending; counting one twice is harmless)
+    elo    = p_min(elo, e_even);
     int ge = max(max(lo16(ehi), hi16(ehi)), max(-lo16(elo), -hi16(elo)));
 #pragma unroll
     for (int o = T / 2; o >= 1; o >>= 1)

@@ -292,6 +292,42 @@ def test_decode_tbs_batch_mixed(port, ctx):
     assert 0 in rets and -1 in rets
 
 
+@pytest.mark.parametrize("dtype,amp", [(np.int16, 100), (np.int8, 25)])
+def test_decode_tbs_all_sizes_one_batch(port, ctx, dtype, amp):
+    """config C3: ONE submit whose code blocks cover all 188 LTE sizes (single-CB transport blocks, tbs = K - 24), CRC
+    early stopping with iteration counts that differ per block (noise level varies), plus a few multi-CB blocks in
+    between -- every K is its own K-group / tensor map, every decoder class is present"""
+    rng = np.random.default_rng(1880 + (dtype == np.int8))
+    cases = []
+    for i, K in enumerate(all_K()):
+        tbs = K - 24
+        G = 2 * ((3 * K + 12) // 2 + (i % 5) * 40)  # around the mother code rate, sometimes with repetition
+        cases.append((tbs, 2, G, (0.45, 0.7, 0.95, 1.3)[i % 4]))
+        if i % 47 == 0:
+            cases.append((15264, 4, 20000, 0.5))
+    n = len(cases)
+    t = b.make_tbs(n)
+    llrs, outs = [], []
+    for i, (tbs, Qm, G, sigma) in enumerate(cases):
+        _, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, dtype, amp, sigma)
+        out = np.zeros(tbs // 8 + 22, np.uint8)
+        llrs.append(llr)
+        outs.append(out)
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = llr.ctypes.data, len(llr), tbs, Qm, 0, out.ctypes.data
+    ctx.decode_tbs(t, dtype == np.int8, 8)
+    its = set()
+    for i, (tbs, Qm, G, sigma) in enumerate(cases):
+        sbp = port.softbuffer_new()
+        rc, d, nit, avg, crc = port.decode_tb(sbp, tbs, Qm, 0, llrs[i], 8)
+        port.softbuffer_del(sbp)
+        C_ = t[i].nof_cb
+        nb = tbs // 8 + (3 if C_ == 1 else 6)
+        assert t[i].ret == rc and (outs[i][:nb] == d[:nb]).all(), (i, tbs)
+        assert list(t[i].cb_noi[:C_]) == nit[:C_].tolist(), (i, tbs)
+        its.update(nit[:C_].tolist())
+    assert len(its) >= 4  # iteration counts really vary inside the batch
+
+
 def test_decode_tb_invalid(ctx):
     t = b.make_tbs(3)
     out = np.zeros(20000, np.uint8)
