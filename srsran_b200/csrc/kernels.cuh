@@ -989,6 +989,41 @@ struct DecideArgs {
 // ballot per decoder lane turns 32 rows into 32 consecutive natural-order bits of that lane; the bit rows are then
 // cut into MSB-first bytes (bit n of the block is step n % W of lane n / W), the bytes go out coalesced and feed
 // the warp-parallel CRC.
+// Hard decisions of a windowed decoder: lane l of the warp loads row r0 + l (N int16 = NQ uint4) of the a-posteriori
+// plane, one ballot per decoder lane turns 32 rows into 32 consecutive bits of that lane.  The loads of the next 32 rows
+// are issued before the ballots of the current ones (the chain is otherwise one DRAM round trip per 32 rows).
+template <int NQ>
+__device__ __forceinline__ void decide_rows(const int16_t* post, uint32_t W, u32* bits, uint32_t wpr, int lane)
+{
+  constexpr uint32_t N = 8 * NQ;
+  uint4              cur[NQ], nxt[NQ];
+  auto load = [&](uint32_t r0, uint4 (&v)[NQ]) {
+    const uint32_t p = r0 + lane;
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+      v[q] = p < W ? *reinterpret_cast<const uint4*>(post + (size_t)p * N + 8 * q) : make_uint4(0, 0, 0, 0);
+  };
+  load(0, cur);
+  for (uint32_t r0 = 0; r0 < W; r0 += 32) {
+    if (r0 + 32 < W)
+      load(r0 + 32, nxt);
+#pragma unroll
+    for (int q = 0; q < NQ; q++) {
+      const u32 ww[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int32_t val = (e & 1) ? hi16(ww[e >> 1]) : lo16(ww[e >> 1]);
+        const u32     b   = __ballot_sync(0xffffffffu, val > 0);
+        if (lane == 0)
+          bits[(8 * q + e) * wpr + r0 / 32] = b;
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; q++)
+      cur[q] = nxt[q];
+  }
+}
+
 constexpr int kDecideWarps = 4;
 __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideArgs a)
 {
@@ -1030,25 +1065,16 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
     for (uint32_t i = lane; i < N * wpr; i += 32)
       bits[i] = 0;
     __syncwarp();
-    for (uint32_t r0 = 0; r0 < W; r0 += 32) {
+    if (N == 8)
+      decide_rows<1>(post, W, bits, wpr, lane);
+    else if (N == 16)
+      decide_rows<2>(post, W, bits, wpr, lane);
+    else if (N == 32)
+      decide_rows<4>(post, W, bits, wpr, lane);
+    for (uint32_t r0 = 0; r0 < W && N < 8; r0 += 32) {
       const uint32_t p     = r0 + lane;
       const bool     valid = p < W;
-      if (N >= 8) {
-        // row of N int16 = N/8 uint4
-        for (uint32_t q = 0; q < N / 8; q++) {
-          uint4 v = make_uint4(0, 0, 0, 0);
-          if (valid)
-            v = *reinterpret_cast<const uint4*>(post + (size_t)p * N + 8 * q);
-          const u32 ww[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-          for (int e = 0; e < 8; e++) {
-            const int32_t val = (e & 1) ? hi16(ww[e >> 1]) : lo16(ww[e >> 1]);
-            const u32     b   = __ballot_sync(0xffffffffu, val > 0);
-            if (lane == 0)
-              bits[(8 * q + e) * wpr + r0 / 32] = b;
-          }
-        }
-      } else {
+      {
         const int32_t val = valid ? (int32_t)post[p] : 0;
         const u32     b   = __ballot_sync(0xffffffffu, val > 0);
         if (lane == 0)
