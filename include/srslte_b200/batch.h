@@ -98,6 +98,34 @@ SRSLTE_B200_API int srslte_b200_tdec_batch_submit(srslte_b200_ctx_t* ctx, const 
 SRSLTE_B200_API int srslte_b200_decode_tbs_submit(srslte_b200_ctx_t* ctx, srslte_b200_tb_t* tbs, uint32_t nof_tb, int llr_is_8bit, uint32_t max_iterations, uint32_t flags);
 SRSLTE_B200_API int srslte_b200_wait(srslte_b200_ctx_t* ctx);
 
+/* ---- soft demodulation + descrambling on the device: the batched form of
+ * srslte_demod_soft_demodulate_s / _b (lib/src/phy/modem/demod_soft.c:896-945) followed by
+ * srslte_scrambling_s_offset / _sb_offset (lib/src/phy/scrambling/scrambling.c:43-53) -- the two steps between the
+ * equaliser and decode_tb in lib/src/phy/phch/pdsch.c:832-852.  Integer results are those of the reference's x86 (SSE)
+ * build, including the position-dependent rounding of its SIMD bodies and scalar tails.
+ *   symbols         cf_t[nof_symbols] (interleaved re, im floats) of one codeword
+ *   mod             srslte_mod_t: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM
+ *   scramble_bytes  srslte_sequence_t::c_bytes of the codeword (bit i of the sequence = bit 7-(i%8) of byte i/8,
+ *                   >= nof_symbols*Qm bits), or NULL for no descrambling
+ *   e_bits          out: int16 or int8 [nof_symbols * Qm], 4-byte aligned for full store width
+ * flags: SRSLTE_B200_IN_DEVICE  -> symbols and scramble_bytes are device pointers
+ *        SRSLTE_B200_OUT_DEVICE -> e_bits are device pointers and the call returns once the work is enqueued on the
+ *                                  context's stream (a following srslte_b200_decode_tbs*(..., SRSLTE_B200_IN_DEVICE) on the
+ *                                  same context consumes them in order); otherwise the call returns with e_bits filled. */
+typedef struct {
+  const void*    symbols;
+  uint32_t       nof_symbols;
+  uint32_t       mod;
+  const uint8_t* scramble_bytes;
+  void*          e_bits;
+} srslte_b200_demod_t;
+
+SRSLTE_B200_API int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const srslte_b200_demod_t* cws, uint32_t nof_cw, int llr_is_8bit, uint32_t flags);
+
+/* pseudo-random sequence of TS 36.211 7.2 packed like srslte_sequence_t::c_bytes (srslte_sequence_LTE_pr,
+ * lib/src/phy/common/sequence.c); out: (len + 7) / 8 bytes.  Host helper for callers that do not hold the sequence. */
+SRSLTE_B200_API void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out);
+
 /* device-resident HARQ soft buffers (srslte_softbuffer_rx_init / _reset / _free, softbuffer.c:41-155) */
 SRSLTE_B200_API int  srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer_t** sb, uint32_t max_cb);
 SRSLTE_B200_API void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb);

@@ -25,6 +25,9 @@ CRC8 = 0x19B
 
 # srslte_tdec_impl_type_t (turbodecoder_impl.h:28-38)
 TDEC_AUTO, TDEC_GENERIC, TDEC_SSE, TDEC_SSE_WINDOW, TDEC_NEON_WINDOW, TDEC_AVX_WINDOW, TDEC_SSE8_WINDOW, TDEC_AVX8_WINDOW = range(8)
+# srslte_mod_t (phy_common.h): bits per symbol
+MOD_BPSK, MOD_QPSK, MOD_16QAM, MOD_64QAM, MOD_256QAM = range(5)
+MOD_BITS = [1, 2, 4, 6, 8]
 
 
 def build(ref=True):
@@ -199,6 +202,26 @@ class Port:
         self.L.orc_softbuffer_get_crc(s, _p(crc), C.c_uint32(32))
         return rc, data, nit, avg.value, crc
 
+    # ---- soft demodulation + descrambling
+    def demod(self, mod, symbols, dtype):
+        """symbols: complex64[n]; returns int16/int8 [n * Qm] (srslte_demod_soft_demodulate_{s,b})"""
+        sym = np.ascontiguousarray(symbols, np.complex64).view(np.float32)
+        n = len(sym) // 2
+        out = np.zeros(n * MOD_BITS[mod], dtype)
+        f = self.L.orc_demod_s if dtype == np.int16 else self.L.orc_demod_b
+        assert f(C.c_int(mod), _p(sym), _p(out), C.c_int(n)) == 0
+        return out
+
+    def sequence_bytes(self, c_init, length):
+        out = np.zeros((length + 7) // 8, np.uint8)
+        self.L.orc_sequence_bytes(C.c_uint32(c_init), C.c_uint32(length), _p(out))
+        return out
+
+    def descramble(self, c_bytes, data):
+        d = data.copy()
+        (self.L.orc_descramble_s if d.dtype == np.int16 else self.L.orc_descramble_b)(_p(c_bytes), _p(d), C.c_int(len(d)))
+        return d
+
 
 class Ref:
     """The unmodified reference (srsLTE 20.10.1) through oracle/ref_shim.c"""
@@ -364,6 +387,28 @@ class Ref:
         return d
 
     # CPU baseline runners
+    # ---- soft demodulation + descrambling; the SSE bodies use aligned loads/stores
+    def demod(self, mod, symbols, dtype):
+        n = len(symbols)
+        sym = aligned_zeros(2 * n + 16, np.float32)
+        sym[:2 * n] = np.ascontiguousarray(symbols, np.complex64).view(np.float32)
+        out = aligned_zeros(n * MOD_BITS[mod] + 64, dtype)
+        f = self.L.ref_demod_s if dtype == np.int16 else self.L.ref_demod_b
+        assert f(C.c_int(mod), _p(sym), _p(out), C.c_int(n)) == 0
+        return out[:n * MOD_BITS[mod]].copy()
+
+    def sequence_bytes(self, c_init, length):
+        out = np.zeros((length + 7) // 8 + 16, np.uint8)
+        assert self.L.ref_sequence_bytes(C.c_uint32(c_init), C.c_uint32(length), _p(out)) == 0
+        return out[:(length + 7) // 8].copy()
+
+    def descramble(self, c_init, data):
+        d = aligned_zeros(len(data) + 64, data.dtype)
+        d[:len(data)] = data
+        f = self.L.ref_descramble_s if data.dtype == np.int16 else self.L.ref_descramble_b
+        assert f(C.c_uint32(c_init), _p(d), C.c_int(len(data))) == 0
+        return d[:len(data)].copy()
+
     def bench_c1(self, nthreads, llr, K, nof_iter, layout_sb=False, repeat=1):
         """llr: (ncb, stride) int16/int8.  Returns (seconds, out bytes (ncb, K/8))."""
         assert llr.ndim == 2 and llr.flags.c_contiguous

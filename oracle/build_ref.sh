@@ -33,6 +33,7 @@ src/phy/utils/vector.c src/phy/utils/vector_simd.c src/phy/utils/bit.c src/phy/u
 src/phy/channel/ch_awgn.c src/phy/channel/gauss.c
 src/phy/phch/sch.c src/phy/phch/uci.c src/phy/phch/cqi.c src/phy/phch/ra.c
 src/phy/common/phy_common.c src/phy/common/sequence.c
+src/phy/modem/demod_soft.c src/phy/scrambling/scrambling.c
 src/phy/fec/viterbi.c src/phy/fec/viterbi37_port.c src/phy/fec/viterbi37_sse.c src/phy/fec/viterbi37_avx2.c
 src/phy/fec/viterbi37_avx2_16bit.c src/phy/fec/parity.c src/phy/fec/rm_conv.c src/phy/fec/convcoder.c
 "

@@ -919,3 +919,253 @@ int orc_encode_tb(uint32_t tbs, uint32_t Qm, uint32_t rv, uint32_t nof_e_bits, c
   free(tb); free(cb); free(cbb); free(cw); free(tab);
   return 0;
 }
+
+/* ============================================================ soft demodulation + descrambling
+ *
+ * Restates src/phy/modem/demod_soft.c as built for x86 with SSE (LV_HAVE_SSE): srslte_demod_soft_demodulate_s (:896-919)
+ * and _b (:921-945).  The reference's results depend on WHERE a symbol sits: the SSE bodies convert with
+ * round-to-nearest and saturating packs and subtract integer thresholds, the scalar tails (the last n mod 4 / n mod 8
+ * symbols) truncate, wrap and subtract float thresholds.  Both are written down element-wise here. */
+#include <math.h>
+
+static int32_t orc_cvt_rne(float f) /* _mm_cvtps_epi32 */
+{
+  if (!(f >= -2147483648.0f && f < 2147483648.0f))
+    return INT32_MIN;
+  return (int32_t)lrintf(f); /* default rounding mode: to nearest even */
+}
+static int32_t orc_cvt_trunc(float f) /* _mm_cvttps_epi32 / cvttss2si */
+{
+  if (!(f > -2147483904.0f && f < 2147483648.0f))
+    return INT32_MIN;
+  return (int32_t)f;
+}
+static int32_t orc_cvt_trunc_d(double d) /* cvttsd2si */
+{
+  if (!(d > -2147483649.0 && d < 2147483648.0))
+    return INT32_MIN;
+  return (int32_t)d;
+}
+static int16_t orc_sat16(int32_t v) { return v > 32767 ? 32767 : (v < -32768 ? -32768 : (int16_t)v); } /* _mm_packs_epi32 */
+static int8_t  orc_sat8(int16_t v) { return v > 127 ? 127 : (v < -128 ? -128 : (int8_t)v); }             /* _mm_packs_epi16 */
+static int16_t orc_w16(int32_t v) { return (int16_t)(uint16_t)(uint32_t)v; }
+static int8_t  orc_w8(int32_t v) { return (int8_t)(uint8_t)(uint32_t)v; }
+static int16_t orc_abs16(int16_t v) { return v < 0 ? orc_w16(-(int32_t)v) : v; } /* _mm_abs_epi16: abs(-32768) = -32768 */
+static int8_t  orc_abs8(int8_t v) { return v < 0 ? orc_w8(-(int32_t)v) : v; }
+
+/* srslte_mod_t: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM (phy_common.h) */
+int orc_demod_s(int mod, const float* sym, int16_t* llr, int n)
+{
+  switch (mod) {
+    case 0: /* demod_bpsk_lte_s :118-123 */
+      for (int i = 0; i < n; i++) {
+        const float t = -100.0f * (sym[2 * i] + sym[2 * i + 1]);
+        llr[i]        = orc_w16(orc_cvt_trunc_d((double)t * M_SQRT1_2));
+      }
+      return 0;
+    case 1: { /* demod_qpsk_lte_s :137-140 -> srslte_vec_convert_fi_simd (vector_simd.c:436-472, AVX2: 16 values per trip) */
+      const float scale = (float)(-100 * M_SQRT2);
+      const int   len = 2 * n, nb = len >= 16 ? ((len - 16) / 16 + 1) * 16 : 0;
+      for (int e = 0; e < len; e++) {
+        const int32_t v = orc_cvt_trunc(sym[e] * scale);
+        llr[e]          = e < nb ? orc_sat16(v) : orc_w16(v);
+      }
+      return 0;
+    }
+    case 2: { /* demod_16qam_lte_s_sse :273-322 */
+      const int16_t off  = orc_w16(orc_cvt_trunc(2 * 400 / sqrtf(10)));
+      const float   thrf = 2 * 400 / sqrtf(10);
+      for (int i = 0; i < n; i++) {
+        const float re = sym[2 * i], im = sym[2 * i + 1];
+        if (i < 4 * (n / 4)) {
+          const int16_t vr = orc_sat16(orc_cvt_rne(re * -400.0f)), vi = orc_sat16(orc_cvt_rne(im * -400.0f));
+          llr[4 * i + 0] = vr;
+          llr[4 * i + 1] = vi;
+          llr[4 * i + 2] = orc_w16((int32_t)orc_abs16(vr) - off);
+          llr[4 * i + 3] = orc_w16((int32_t)orc_abs16(vi) - off);
+        } else {
+          const int16_t yre = orc_w16(orc_cvt_trunc(400.0f * re)), yim = orc_w16(orc_cvt_trunc(400.0f * im));
+          llr[4 * i + 0] = orc_w16(-(int32_t)yre);
+          llr[4 * i + 1] = orc_w16(-(int32_t)yim);
+          llr[4 * i + 2] = orc_w16(orc_cvt_trunc((float)abs((int)yre) - thrf));
+          llr[4 * i + 3] = orc_w16(orc_cvt_trunc((float)abs((int)yim) - thrf));
+        }
+      }
+      return 0;
+    }
+    case 3: { /* demod_64qam_lte_s_sse :594-669 */
+      const int16_t off1 = orc_w16(orc_cvt_trunc(4 * 700 / sqrtf(42))), off2 = orc_w16(orc_cvt_trunc(2 * 700 / sqrtf(42)));
+      for (int i = 0; i < n; i++) {
+        const float re = sym[2 * i], im = sym[2 * i + 1];
+        int16_t     vr, vi;
+        if (i < 4 * (n / 4)) {
+          vr = orc_sat16(orc_cvt_rne(re * -700.0f));
+          vi = orc_sat16(orc_cvt_rne(im * -700.0f));
+          llr[6 * i + 0] = vr;
+          llr[6 * i + 1] = vi;
+          llr[6 * i + 2] = orc_w16((int32_t)orc_abs16(vr) - off1);
+          llr[6 * i + 3] = orc_w16((int32_t)orc_abs16(vi) - off1);
+          llr[6 * i + 4] = orc_w16((int32_t)orc_abs16(llr[6 * i + 2]) - off2);
+          llr[6 * i + 5] = orc_w16((int32_t)orc_abs16(llr[6 * i + 3]) - off2);
+        } else {
+          vr = orc_w16(orc_cvt_trunc(700.0f * re));
+          vi = orc_w16(orc_cvt_trunc(700.0f * im));
+          llr[6 * i + 0] = orc_w16(-(int32_t)vr);
+          llr[6 * i + 1] = orc_w16(-(int32_t)vi);
+          llr[6 * i + 2] = orc_w16((int32_t)orc_w16(abs((int)vr)) - off1);
+          llr[6 * i + 3] = orc_w16((int32_t)orc_w16(abs((int)vi)) - off1);
+          llr[6 * i + 4] = orc_w16((int32_t)orc_w16(abs((int)llr[6 * i + 2])) - off2);
+          llr[6 * i + 5] = orc_w16((int32_t)orc_w16(abs((int)llr[6 * i + 3])) - off2);
+        }
+      }
+      return 0;
+    }
+    case 4: { /* demod_256qam_lte_s :849-869 */
+      const float c8 = 8.0f / sqrtf(170.0f), c4 = 4.0f / sqrtf(170.0f), c2 = 2.0f / sqrtf(170.0f);
+      for (int i = 0; i < n; i++) {
+        float re = -sym[2 * i], im = -sym[2 * i + 1];
+        llr[8 * i + 0] = orc_w16(orc_cvt_trunc(1000.0f * re));
+        llr[8 * i + 1] = orc_w16(orc_cvt_trunc(1000.0f * im));
+        re = fabsf(re) - c8;
+        im = fabsf(im) - c8;
+        llr[8 * i + 2] = orc_w16(orc_cvt_trunc(1000.0f * re));
+        llr[8 * i + 3] = orc_w16(orc_cvt_trunc(1000.0f * im));
+        re = fabsf(re) - c4;
+        im = fabsf(im) - c4;
+        llr[8 * i + 4] = orc_w16(orc_cvt_trunc(1000.0f * re));
+        llr[8 * i + 5] = orc_w16(orc_cvt_trunc(1000.0f * im));
+        re = fabsf(re) - c2;
+        im = fabsf(im) - c2;
+        llr[8 * i + 6] = orc_w16(orc_cvt_trunc(1000.0f * re));
+        llr[8 * i + 7] = orc_w16(orc_cvt_trunc(1000.0f * im));
+      }
+      return 0;
+    }
+  }
+  return -1;
+}
+
+int orc_demod_b(int mod, const float* sym, int8_t* llr, int n)
+{
+  switch (mod) {
+    case 0: /* demod_bpsk_lte_b :111-116 */
+      for (int i = 0; i < n; i++) {
+        const float t = -20.0f * (sym[2 * i] + sym[2 * i + 1]);
+        llr[i]        = orc_w8(orc_cvt_trunc_d((double)t * M_SQRT1_2));
+      }
+      return 0;
+    case 1: { /* demod_qpsk_lte_b :132-135 -> srslte_vec_convert_fb_simd (vector_simd.c:524-590, SSE: 16 values per trip) */
+      const float scale = (float)(-20 * M_SQRT2);
+      const int   len = 2 * n, nb = len >= 16 ? ((len - 16) / 16 + 1) * 16 : 0;
+      for (int e = 0; e < len; e++) {
+        const int32_t v = orc_cvt_trunc(sym[e] * scale);
+        llr[e]          = e < nb ? orc_sat8(orc_sat16(v)) : orc_w8(v);
+      }
+      return 0;
+    }
+    case 2: { /* demod_16qam_lte_b_sse :324-382 */
+      const int8_t off  = orc_w8(orc_cvt_trunc(2 * 30 / sqrtf(10)));
+      const float  thrf = 2 * 30 / sqrtf(10);
+      for (int i = 0; i < n; i++) {
+        const float re = sym[2 * i], im = sym[2 * i + 1];
+        if (i < 8 * (n / 8)) {
+          const int8_t vr = orc_sat8(orc_sat16(orc_cvt_rne(re * -30.0f))), vi = orc_sat8(orc_sat16(orc_cvt_rne(im * -30.0f)));
+          llr[4 * i + 0] = vr;
+          llr[4 * i + 1] = vi;
+          llr[4 * i + 2] = orc_w8((int32_t)orc_abs8(vr) - off);
+          llr[4 * i + 3] = orc_w8((int32_t)orc_abs8(vi) - off);
+        } else {
+          const int yre = orc_w8(orc_cvt_trunc(30.0f * re)), yim = orc_w8(orc_cvt_trunc(30.0f * im));
+          llr[4 * i + 0] = orc_w8(-yre);
+          llr[4 * i + 1] = orc_w8(-yim);
+          llr[4 * i + 2] = orc_w8(orc_cvt_trunc((float)abs(yre) - thrf));
+          llr[4 * i + 3] = orc_w8(orc_cvt_trunc((float)abs(yim) - thrf));
+        }
+      }
+      return 0;
+    }
+    case 3: { /* demod_64qam_lte_b_sse :671-755 */
+      const int8_t off1 = orc_w8(orc_cvt_trunc(4 * 40 / sqrtf(42))), off2 = orc_w8(orc_cvt_trunc(2 * 40 / sqrtf(42)));
+      for (int i = 0; i < n; i++) {
+        const float re = sym[2 * i], im = sym[2 * i + 1];
+        if (i < 8 * (n / 8)) {
+          const int8_t vr = orc_sat8(orc_sat16(orc_cvt_rne(re * -40.0f))), vi = orc_sat8(orc_sat16(orc_cvt_rne(im * -40.0f)));
+          llr[6 * i + 0] = vr;
+          llr[6 * i + 1] = vi;
+          llr[6 * i + 2] = orc_w8((int32_t)orc_abs8(vr) - off1);
+          llr[6 * i + 3] = orc_w8((int32_t)orc_abs8(vi) - off1);
+          llr[6 * i + 4] = orc_w8((int32_t)orc_abs8(llr[6 * i + 2]) - off2);
+          llr[6 * i + 5] = orc_w8((int32_t)orc_abs8(llr[6 * i + 3]) - off2);
+        } else {
+          const int8_t vr = orc_w8(orc_cvt_trunc(40.0f * re)), vi = orc_w8(orc_cvt_trunc(40.0f * im));
+          llr[6 * i + 0] = orc_w8(-(int32_t)vr);
+          llr[6 * i + 1] = orc_w8(-(int32_t)vi);
+          llr[6 * i + 2] = orc_w8((int32_t)orc_w8(abs((int)vr)) - off1);
+          llr[6 * i + 3] = orc_w8((int32_t)orc_w8(abs((int)vi)) - off1);
+          llr[6 * i + 4] = orc_w8((int32_t)orc_w8(abs((int)llr[6 * i + 2])) - off2);
+          llr[6 * i + 5] = orc_w8((int32_t)orc_w8(abs((int)llr[6 * i + 3])) - off2);
+        }
+      }
+      return 0;
+    }
+    case 4: { /* demod_256qam_lte_b :827-847 */
+      const float c8 = 8.0f / sqrtf(170.0f), c4 = 4.0f / sqrtf(170.0f), c2 = 2.0f / sqrtf(170.0f);
+      for (int i = 0; i < n; i++) {
+        float re = -sym[2 * i], im = -sym[2 * i + 1];
+        llr[8 * i + 0] = orc_w8(orc_cvt_trunc(50.0f * re));
+        llr[8 * i + 1] = orc_w8(orc_cvt_trunc(50.0f * im));
+        re = fabsf(re) - c8;
+        im = fabsf(im) - c8;
+        llr[8 * i + 2] = orc_w8(orc_cvt_trunc(50.0f * re));
+        llr[8 * i + 3] = orc_w8(orc_cvt_trunc(50.0f * im));
+        re = fabsf(re) - c4;
+        im = fabsf(im) - c4;
+        llr[8 * i + 4] = orc_w8(orc_cvt_trunc(50.0f * re));
+        llr[8 * i + 5] = orc_w8(orc_cvt_trunc(50.0f * im));
+        re = fabsf(re) - c2;
+        im = fabsf(im) - c2;
+        llr[8 * i + 6] = orc_w8(orc_cvt_trunc(50.0f * re));
+        llr[8 * i + 7] = orc_w8(orc_cvt_trunc(50.0f * im));
+      }
+      return 0;
+    }
+  }
+  return -1;
+}
+
+/* Pseudo-random sequence of TS 36.211 7.2 (src/phy/common/sequence.c: srslte_sequence_LTE_pr), packed as the
+ * reference's c_bytes (srslte_bit_pack_vector: first bit = MSB).  out: (len + 7) / 8 bytes. */
+void orc_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out)
+{
+  const uint32_t Nc = 1600;
+  uint8_t*       x1 = (uint8_t*)calloc(Nc + len + 31, 1);
+  uint8_t*       x2 = (uint8_t*)calloc(Nc + len + 31, 1);
+  x1[0] = 1;
+  for (int i = 0; i < 31; i++)
+    x2[i] = (c_init >> i) & 1u;
+  for (uint32_t n = 0; n + 31 < Nc + len + 31; n++) {
+    x1[n + 31] = x1[n + 3] ^ x1[n];
+    x2[n + 31] = x2[n + 3] ^ x2[n + 2] ^ x2[n + 1] ^ x2[n];
+  }
+  memset(out, 0, (len + 7) / 8);
+  for (uint32_t n = 0; n < len; n++)
+    if (x1[n + Nc] ^ x2[n + Nc])
+      out[n / 8] |= (uint8_t)(0x80u >> (n % 8));
+  free(x1);
+  free(x2);
+}
+
+/* srslte_scrambling_s_offset / _sb_offset (scrambling.c:43-53) with the sequence given as packed bytes:
+ * srslte_vec_neg_{sss,bbb} against c_short / c_char = +-1 -> wrapping negation where the sequence bit is 1 */
+void orc_descramble_s(const uint8_t* c_bytes, int16_t* data, int len)
+{
+  for (int i = 0; i < len; i++)
+    if (c_bytes[i / 8] & (0x80u >> (i % 8)))
+      data[i] = orc_w16(-(int32_t)data[i]);
+}
+void orc_descramble_b(const uint8_t* c_bytes, int8_t* data, int len)
+{
+  for (int i = 0; i < len; i++)
+    if (c_bytes[i / 8] & (0x80u >> (i % 8)))
+      data[i] = orc_w8(-(int32_t)data[i]);
+}

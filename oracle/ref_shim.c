@@ -11,6 +11,8 @@
  *   srslte_crc_*             lib/include/srslte/phy/fec/crc.h:48-74
  *   srslte_cbsegm*           lib/include/srslte/phy/fec/cbsegm.h:46-52
  *   srslte_dlsch_encode2 / srslte_dlsch_decode2   lib/src/phy/phch/sch.c:577,611
+ *   srslte_demod_soft_demodulate_{s,b}             lib/src/phy/modem/demod_soft.c:896-945
+ *   srslte_sequence_LTE_pr, srslte_scrambling_{s,sb}_offset   lib/src/phy/common/sequence.c, scrambling/scrambling.c:43-53
  *
  * Nothing in here re-implements reference arithmetic.
  */
@@ -31,6 +33,9 @@
 #include "srslte/phy/fec/turbodecoder.h"
 #include "srslte/phy/phch/pdsch_cfg.h"
 #include "srslte/phy/phch/sch.h"
+#include "srslte/phy/common/sequence.h"
+#include "srslte/phy/modem/demod_soft.h"
+#include "srslte/phy/scrambling/scrambling.h"
 
 static double now_s(void)
 {
@@ -504,4 +509,46 @@ double ref_bench_tb(int      nthreads,
   free(th);
   free(a);
   return t1 - t0;
+}
+
+
+/* ------------------------------------------------------------------ soft demodulation + descrambling */
+int ref_demod_s(int mod, const float* symbols, int16_t* llr, int nsymbols)
+{
+  return srslte_demod_soft_demodulate_s((srslte_mod_t)mod, (const cf_t*)symbols, llr, nsymbols);
+}
+int ref_demod_b(int mod, const float* symbols, int8_t* llr, int nsymbols)
+{
+  return srslte_demod_soft_demodulate_b((srslte_mod_t)mod, (const cf_t*)symbols, llr, nsymbols);
+}
+/* pseudo-random sequence of TS 36.211 7.2 as the reference stores it: packed bytes (c_bytes, MSB first) */
+int ref_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out)
+{
+  srslte_sequence_t seq;
+  memset(&seq, 0, sizeof(seq));
+  if (srslte_sequence_LTE_pr(&seq, len, c_init))
+    return -1;
+  memcpy(out, seq.c_bytes, (len + 7) / 8);
+  srslte_sequence_free(&seq);
+  return 0;
+}
+int ref_descramble_s(uint32_t c_init, int16_t* data, int len)
+{
+  srslte_sequence_t seq;
+  memset(&seq, 0, sizeof(seq));
+  if (srslte_sequence_LTE_pr(&seq, len, c_init))
+    return -1;
+  srslte_scrambling_s_offset(&seq, data, 0, len);
+  srslte_sequence_free(&seq);
+  return 0;
+}
+int ref_descramble_b(uint32_t c_init, int8_t* data, int len)
+{
+  srslte_sequence_t seq;
+  memset(&seq, 0, sizeof(seq));
+  if (srslte_sequence_LTE_pr(&seq, len, c_init))
+    return -1;
+  srslte_scrambling_sb_offset(&seq, data, 0, len);
+  srslte_sequence_free(&seq);
+  return 0;
 }

@@ -41,6 +41,13 @@ class Tb(C.Structure):  # srslte_b200_tb_t
                 ("cb_noi", C.c_uint8 * MAX_CODEBLOCKS), ("nof_cb", C.c_uint32)]
 
 
+class Demod(C.Structure):  # srslte_b200_demod_t
+    _fields_ = [("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("scramble_bytes", C.c_void_p), ("e_bits", C.c_void_p)]
+
+
+MOD_BITS = [1, 2, 4, 6, 8]  # bits per symbol of srslte_mod_t 0..4 (BPSK, QPSK, 16QAM, 64QAM, 256QAM)
+
+
 class CbSegm(C.Structure):  # srslte_cbsegm_t
     _fields_ = [(n, C.c_uint32) for n in ("F", "C", "K1", "K2", "K1_idx", "K2_idx", "C1", "C2", "tbs")]
 
@@ -86,6 +93,9 @@ def lib():
         for f in ("srslte_b200_decode_tbs", "srslte_b200_decode_tbs_submit"):
             getattr(L, f).argtypes = [C.c_void_p, C.POINTER(Tb), C.c_uint32, C.c_int, C.c_uint32, C.c_uint32]
         L.srslte_b200_wait.argtypes = [C.c_void_p]
+        L.srslte_b200_demod_descramble.argtypes = [C.c_void_p, C.POINTER(Demod), C.c_uint32, C.c_int, C.c_uint32]
+        L.srslte_b200_sequence_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
+        L.srslte_b200_sequence_bytes.restype = None
         L.srslte_b200_softbuffer_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]
         L.srslte_b200_softbuffer_reset.argtypes = [C.c_void_p]
         L.srslte_b200_softbuffer_free.argtypes = [C.c_void_p]
@@ -112,6 +122,17 @@ def lib():
         L.srslte_cbsegm_cbsize_isvalid.restype = C.c_bool
         _lib = L
     return _lib
+
+
+def sequence_bytes(c_init, length):
+    """TS 36.211 7.2 pseudo-random sequence packed like srslte_sequence_t::c_bytes (host helper of the library)"""
+    out = np.zeros((length + 7) // 8, np.uint8)
+    lib().srslte_b200_sequence_bytes(c_init, length, out.ctypes.data_as(C.c_void_p))
+    return out
+
+
+def make_demods(n):
+    return (Demod * n)()
 
 
 def _err(what, rc):
@@ -181,6 +202,32 @@ class Context:
         rc = lib().srslte_b200_memcpy_d2h(self.h, _ptr(arr), dptr, arr.nbytes)
         if rc:
             _err("d2h", rc)
+
+    # ---- soft demodulation + descrambling (srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset)
+    def demod_descramble(self, codewords, dtype):
+        """codewords: list of (complex64 symbols, mod, packed sequence bytes or None), host arrays.  Returns the list of
+        int16 / int8 LLR arrays (nof_symbols * Qm each)."""
+        n = len(codewords)
+        arr = (Demod * n)()
+        keep, outs = [], []
+        for i, (sym, mod, scr) in enumerate(codewords):
+            sym = np.ascontiguousarray(sym, np.complex64)
+            out = np.zeros(len(sym) * MOD_BITS[mod], dtype)
+            keep.append((sym, scr))
+            outs.append(out)
+            arr[i].symbols, arr[i].nof_symbols, arr[i].mod = sym.ctypes.data, len(sym), mod
+            arr[i].scramble_bytes = scr.ctypes.data if scr is not None else None
+            arr[i].e_bits = out.ctypes.data
+        rc = lib().srslte_b200_demod_descramble(self.h, arr, n, int(dtype == np.int8), 0)
+        if rc:
+            _err("srslte_b200_demod_descramble", rc)
+        return outs
+
+    def demod_descramble_raw(self, arr, is8, flags):
+        """arr: ctypes array of Demod with caller-managed (host or device) pointers"""
+        rc = lib().srslte_b200_demod_descramble(self.h, arr, len(arr), int(is8), flags)
+        if rc:
+            _err("srslte_b200_demod_descramble", rc)
 
     # ---- batch of code blocks (srslte_tdec_run_all semantics)
     def tdec_batch(self, llr, K, nof_iterations, input_sb=False, dec_type=TDEC_AUTO, out=None):

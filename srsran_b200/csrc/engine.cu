@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -203,6 +204,7 @@ Engine::~Engine()
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
+  d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); h_dm_desc.release(); h_dm_out.release();
   if (stream)
     cudaStreamDestroy(stream);
   delete plan_ptr;
@@ -1036,6 +1038,142 @@ int Engine::wait()
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- soft demodulation
+static DemodConst demod_constants()
+{
+  DemodConst c;
+  // the reference's expressions, evaluated the way its compiler evaluates them (float arithmetic, then conversion)
+  c.qpsk_scale_s = (float)(-100 * M_SQRT2);
+  c.qpsk_scale_b = (float)(-20 * M_SQRT2);
+  c.thr16_s      = 2 * 400 / sqrtf(10);
+  c.thr16_b      = 2 * 30 / sqrtf(10);
+  c.off16_s      = (int16_t)(2 * 400 / sqrtf(10));
+  c.off16_b      = (int8_t)(2 * 30 / sqrtf(10));
+  c.off64a_s     = (int16_t)(4 * 700 / sqrtf(42));
+  c.off64b_s     = (int16_t)(2 * 700 / sqrtf(42));
+  c.off64a_b     = (int8_t)(4 * 40 / sqrtf(42));
+  c.off64b_b     = (int8_t)(2 * 40 / sqrtf(42));
+  c.c8           = 8.0f / sqrtf(170.0f);
+  c.c4           = 4.0f / sqrtf(170.0f);
+  c.c2           = 2.0f / sqrtf(170.0f);
+  return c;
+}
+
+int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, int is8, uint32_t flags)
+{
+  if (!cws && nof_cw) {
+    set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  if (nof_cw == 0)
+    return 0;
+  CUDA_OK(cudaSetDevice(device));
+  const size_t esz = is8 ? 1 : 2;
+  // pass 1: validate, size the staging areas (every piece 16-byte aligned)
+  size_t   in_bytes = 0, out_bytes = 0;
+  uint32_t max_sym = 0;
+  auto     al16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  for (uint32_t i = 0; i < nof_cw; i++) {
+    const srslte_b200_demod_t& c = cws[i];
+    if (!c.symbols || !c.e_bits || c.mod > 4 || c.nof_symbols == 0) {
+      set_error("invalid codeword descriptor");
+      return SRSLTE_B200_ERROR_INVALID_INPUTS;
+    }
+    const uint32_t Qm = c.mod == 0 ? 1 : 2 * c.mod;
+    in_bytes += al16((size_t)c.nof_symbols * 8) + (c.scramble_bytes ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0);
+    out_bytes += al16((size_t)c.nof_symbols * Qm * esz);
+    max_sym = std::max(max_sym, c.nof_symbols);
+  }
+  const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
+  if ((!in_dev && d_dm_in.reserve(in_bytes + 64)) || (!out_dev && (d_dm_out.reserve(out_bytes + 64) || h_dm_out.reserve(out_bytes + 64))) ||
+      d_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || h_dm_desc.reserve(nof_cw * sizeof(DemodDev)))
+    return SRSLTE_B200_ERROR;
+  // pass 2: descriptors + uploads (adjacent host arrays go up in one copy)
+  DemodDev*      hd = (DemodDev*)h_dm_desc.ptr;
+  size_t         in_off = 0, out_off = 0;
+  const uint8_t* cp_src = nullptr;
+  size_t         cp_dst = 0, cp_bytes = 0;
+  auto           upload = [&](const void* src, size_t nb) -> const uint8_t* {
+    const uint8_t* dst = d_dm_in.ptr + in_off;
+    if (cp_bytes && (const uint8_t*)src == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
+      cp_bytes += nb;
+    } else {
+      if (cp_bytes)
+        cudaMemcpyAsync(d_dm_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream);
+      cp_src   = (const uint8_t*)src;
+      cp_dst   = in_off;
+      cp_bytes = nb;
+    }
+    in_off += nb;
+    if (nb % 16)
+      in_off = al16(in_off);
+    return dst;
+  };
+  for (uint32_t i = 0; i < nof_cw; i++) {
+    const srslte_b200_demod_t& c  = cws[i];
+    const uint32_t             Qm = c.mod == 0 ? 1 : 2 * c.mod;
+    DemodDev&                  d  = hd[i];
+    d.nsym = c.nof_symbols;
+    d.mod  = c.mod;
+    if (in_dev) {
+      d.sym = (const float*)c.symbols;
+      d.scr = c.scramble_bytes;
+    } else {
+      d.sym = (const float*)upload(c.symbols, (size_t)c.nof_symbols * 8);
+      d.scr = c.scramble_bytes ? upload(c.scramble_bytes, ((size_t)c.nof_symbols * Qm + 7) / 8) : nullptr;
+    }
+    if (out_dev) {
+      d.out = c.e_bits;
+    } else {
+      d.out = d_dm_out.ptr + out_off;
+      out_off += al16((size_t)c.nof_symbols * Qm * esz);
+    }
+  }
+  if (cp_bytes)
+    CUDA_OK(cudaMemcpyAsync(d_dm_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaMemcpyAsync(d_dm_desc.ptr, hd, nof_cw * sizeof(DemodDev), cudaMemcpyHostToDevice, stream));
+  static const DemodConst kc = demod_constants();
+  const dim3              grid(std::min<uint32_t>((max_sym + 255) / 256, 64), nof_cw);
+  if (is8)
+    k_demod_descramble<int8_t><<<grid, 256, 0, stream>>>((const DemodDev*)d_dm_desc.ptr, kc);
+  else
+    k_demod_descramble<int16_t><<<grid, 256, 0, stream>>>((const DemodDev*)d_dm_desc.ptr, kc);
+  CUDA_OK(cudaGetLastError());
+  last_launches++;
+  if (out_dev)
+    return 0; // stream-ordered with whatever is submitted next on this context
+  CUDA_OK(cudaMemcpyAsync(h_dm_out.ptr, d_dm_out.ptr, out_off, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  out_off = 0;
+  for (uint32_t i = 0; i < nof_cw; i++) {
+    const uint32_t Qm = cws[i].mod == 0 ? 1 : 2 * cws[i].mod;
+    const size_t   nb = (size_t)cws[i].nof_symbols * Qm * esz;
+    memcpy(cws[i].e_bits, h_dm_out.ptr + out_off, nb);
+    out_off += al16(nb);
+  }
+  return 0;
+}
+
+// TS 36.211 7.2: c(n) = x1(n + 1600) ^ x2(n + 1600), x1(n+31) = x1(n+3) ^ x1(n), x2(n+31) = x2(n+3) ^ x2(n+2) ^ x2(n+1) ^ x2(n)
+// (srslte_sequence_LTE_pr, lib/src/phy/common/sequence.c); bit-serial on two 31-bit registers
+void lte_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out)
+{
+  uint32_t x1 = 1, x2 = c_init & 0x7fffffffu;
+  auto     step = [&]() {
+    const uint32_t f1 = ((x1 >> 3) ^ x1) & 1u, f2 = ((x2 >> 3) ^ (x2 >> 2) ^ (x2 >> 1) ^ x2) & 1u;
+    x1 = (x1 >> 1) | (f1 << 30);
+    x2 = (x2 >> 1) | (f2 << 30);
+  };
+  for (uint32_t n = 0; n < 1600; n++)
+    step();
+  memset(out, 0, (len + 7) / 8);
+  for (uint32_t n = 0; n < len; n++) {
+    if ((x1 ^ x2) & 1u)
+      out[n / 8] |= (uint8_t)(0x80u >> (n % 8));
+    step();
+  }
+}
+
 // ------------------------------------------------------------------------------------------------- soft buffers
 int Engine::softbuffer_create(Softbuffer** out, uint32_t max_cb)
 {
@@ -1222,6 +1360,14 @@ int srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer
 }
 void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb) { b200::softbuffer_reset((b200::Softbuffer*)sb); }
 void srslte_b200_softbuffer_free(srslte_b200_softbuffer_t* sb) { b200::softbuffer_free((b200::Softbuffer*)sb); }
+
+int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const srslte_b200_demod_t* cws, uint32_t nof_cw, int llr_is_8bit, uint32_t flags)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->demod_descramble(cws, nof_cw, llr_is_8bit, flags);
+}
+void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out) { b200::lte_sequence_bytes(c_init, len, out); }
 
 // packed-instruction issue rate probe: returns operations per second over the whole GPU (each = one packed int16x2
 // instruction per thread) for op 0 VIADD.16x2, 1 VIMNMX.S16x2, 2 VIADDMNMX.S16x2, 3 VIMNMX3.S16x2, 4 __vaddss2

@@ -56,6 +56,7 @@ public:
   float timer_stop_ms(); // records the closing event, waits for it, returns the device time between the two
 
   int softbuffer_create(Softbuffer** out, uint32_t max_cb);
+  int demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, int is8, uint32_t flags);
   // host-pointer compatibility operations behind the drop-in srslte_* symbols (api.inc)
   int tdec_step(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, const void* input, uint32_t n_done, uint32_t n_more,
                 uint8_t* out);
@@ -98,6 +99,8 @@ public:
   uint32_t         last_redo = 0, last_half_iter = 0;
   PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc, h_tmaps;
   DevBuf<uint8_t>  d_tmaps;
+  DevBuf<uint8_t>  d_dm_in, d_dm_out, d_dm_desc; // soft-demodulation front end: staged symbols + sequences, LLRs, descriptors
+  PinBuf<uint8_t>  h_dm_desc, h_dm_out;
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
 

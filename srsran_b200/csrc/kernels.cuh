@@ -7,6 +7,7 @@
 //   k_decide_crc   tdec_*_decision_byte + srslte_crc_checksum_byte + early stop (win.h:925-993, crc.c:143-157,
 //                  sch.c:420-450)
 //   k_tb_finish    TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
+//   k_demod_descramble  srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset (demod_soft.c:896-945)
 #pragma once
 #include <cuda.h> // CUtensorMap (type only: the encoder is reached through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>
@@ -1128,6 +1129,160 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
       s->done   = 1;
     }
     s->crc = crc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ soft demodulation
+// srslte_demod_soft_demodulate_{s,b} (modem/demod_soft.c:896-945) + srslte_scrambling_{s,sb}_offset
+// (scrambling/scrambling.c:43-53), the two steps between the equaliser and decode_tb (phch/pdsch.c:832-852), fused:
+// one thread per symbol, Qm LLRs computed, descrambled and stored.  The reference's integer results depend on where a
+// symbol sits -- its SSE bodies (groups of 4 symbols for int16, 8 for int8; 16 values for the QPSK conversion) round
+// to nearest, pack with saturation and subtract integer thresholds; the scalar tails truncate, wrap and subtract float
+// thresholds -- so both forms are implemented and selected by the symbol index.  Conversions reproduce cvt(t)ps2dq
+// including its "integer indefinite" result for out-of-range inputs.
+struct DemodDev {
+  const float*   sym; // nsym complex values (re, im)
+  const uint8_t* scr; // packed scrambling sequence (first bit = MSB) or nullptr
+  void*          out; // nsym * Qm LLRs
+  uint32_t       nsym;
+  uint32_t       mod; // srslte_mod_t: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM
+};
+struct DemodConst { // thresholds evaluated on the host exactly as the reference's expressions are (float arithmetic)
+  float   qpsk_scale_s, qpsk_scale_b;
+  float   thr16_s, thr16_b; // 2 * SCALE / sqrtf(10)
+  int32_t off16_s, off16_b;
+  int32_t off64a_s, off64b_s, off64a_b, off64b_b; // 4 * SCALE / sqrtf(42), 2 * SCALE / sqrtf(42), truncated
+  float   c8, c4, c2; // 8, 4, 2 / sqrtf(170)
+};
+__device__ __forceinline__ int32_t cvt_rne(float f) { return f < 2147483648.0f ? __float2int_rn(f) : (int32_t)0x80000000; }
+__device__ __forceinline__ int32_t cvt_trunc(float f) { return f < 2147483648.0f ? __float2int_rz(f) : (int32_t)0x80000000; }
+__device__ __forceinline__ int32_t cvt_trunc_d(double d) { return d < 2147483648.0 ? __double2int_rz(d) : (int32_t)0x80000000; }
+template <typename T>
+__device__ __forceinline__ int32_t wrapT(int32_t v)
+{
+  return sizeof(T) == 2 ? (int32_t)(int16_t)(uint16_t)v : (int32_t)(int8_t)(uint8_t)v;
+}
+template <typename T>
+__device__ __forceinline__ int32_t satT(int32_t v) // _mm_packs_epi32 [+ _mm_packs_epi16]
+{
+  const int32_t s16 = min(max(v, -32768), 32767);
+  return sizeof(T) == 2 ? s16 : min(max(s16, -128), 127);
+}
+template <typename T>
+__device__ __forceinline__ int32_t absT(int32_t v) { return wrapT<T>(v < 0 ? -v : v); } // abs(-min) = -min, like pabsw/pabsb
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __restrict__ cws, const DemodConst c)
+{
+  constexpr bool S     = sizeof(T) == 2;
+  const DemodDev d     = cws[blockIdx.y];
+  const int      n     = (int)d.nsym;
+  const int      grp   = S ? 4 : 8;              // symbols per SSE trip of the 16QAM / 64QAM bodies
+  const int      n_sse = n / grp * grp;
+  const int      qlen = 2 * n, q_sse = qlen >= 16 ? ((qlen - 16) / 16 + 1) * 16 : 0; // values converted by the QPSK SIMD body
+  const int      Qm   = d.mod == 0 ? 1 : 2 * (int)d.mod;
+  T*             out  = (T*)d.out;
+  const bool     vec4 = (((uintptr_t)out) & 3u) == 0 && ((Qm * sizeof(T)) & 3u) == 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float2 sy = reinterpret_cast<const float2*>(d.sym)[i];
+    const float  re = sy.x, im = sy.y;
+    int32_t      v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    switch (d.mod) {
+      case 0: { // demod_bpsk_lte_{s,b}
+        const float t = __fmul_rn(S ? -100.0f : -20.0f, __fadd_rn(re, im));
+        v[0]          = wrapT<T>(cvt_trunc_d(__dmul_rn((double)t, 0.70710678118654752440)));
+        break;
+      }
+      case 1: { // srslte_vec_convert_f{i,b}: truncation; the SIMD body saturates, the tail wraps
+        const float sc = S ? c.qpsk_scale_s : c.qpsk_scale_b;
+        const int32_t a = cvt_trunc(__fmul_rn(re, sc)), b = cvt_trunc(__fmul_rn(im, sc));
+        v[0] = 2 * i < q_sse ? satT<T>(a) : wrapT<T>(a);
+        v[1] = 2 * i + 1 < q_sse ? satT<T>(b) : wrapT<T>(b);
+        break;
+      }
+      case 2: {
+        const float sc = S ? 400.0f : 30.0f;
+        if (i < n_sse) {
+          const int32_t off = S ? c.off16_s : c.off16_b;
+          v[0] = satT<T>(cvt_rne(__fmul_rn(re, -sc)));
+          v[1] = satT<T>(cvt_rne(__fmul_rn(im, -sc)));
+          v[2] = wrapT<T>(absT<T>(v[0]) - off);
+          v[3] = wrapT<T>(absT<T>(v[1]) - off);
+        } else {
+          const float   thr = S ? c.thr16_s : c.thr16_b;
+          const int32_t yre = wrapT<T>(cvt_trunc(__fmul_rn(sc, re))), yim = wrapT<T>(cvt_trunc(__fmul_rn(sc, im)));
+          v[0] = wrapT<T>(-yre);
+          v[1] = wrapT<T>(-yim);
+          v[2] = wrapT<T>(cvt_trunc(__fsub_rn((float)abs(yre), thr)));
+          v[3] = wrapT<T>(cvt_trunc(__fsub_rn((float)abs(yim), thr)));
+        }
+        break;
+      }
+      case 3: {
+        const float   sc = S ? 700.0f : 40.0f;
+        const int32_t o1 = S ? c.off64a_s : c.off64a_b, o2 = S ? c.off64b_s : c.off64b_b;
+        if (i < n_sse) {
+          v[0] = satT<T>(cvt_rne(__fmul_rn(re, -sc)));
+          v[1] = satT<T>(cvt_rne(__fmul_rn(im, -sc)));
+          v[2] = wrapT<T>(absT<T>(v[0]) - o1);
+          v[3] = wrapT<T>(absT<T>(v[1]) - o1);
+          v[4] = wrapT<T>(absT<T>(v[2]) - o2);
+          v[5] = wrapT<T>(absT<T>(v[3]) - o2);
+        } else {
+          const int32_t yre = wrapT<T>(cvt_trunc(__fmul_rn(sc, re))), yim = wrapT<T>(cvt_trunc(__fmul_rn(sc, im)));
+          v[0] = wrapT<T>(-yre);
+          v[1] = wrapT<T>(-yim);
+          v[2] = wrapT<T>(wrapT<T>(abs(yre)) - o1);
+          v[3] = wrapT<T>(wrapT<T>(abs(yim)) - o1);
+          v[4] = wrapT<T>(wrapT<T>(abs(v[2])) - o2);
+          v[5] = wrapT<T>(wrapT<T>(abs(v[3])) - o2);
+        }
+        break;
+      }
+      default: { // demod_256qam_lte_{s,b}: scalar float arithmetic, truncating conversions
+        const float sc = S ? 1000.0f : 50.0f;
+        float       r = -re, q = -im;
+        v[0] = wrapT<T>(cvt_trunc(__fmul_rn(sc, r)));
+        v[1] = wrapT<T>(cvt_trunc(__fmul_rn(sc, q)));
+        r = __fsub_rn(fabsf(r), c.c8);
+        q = __fsub_rn(fabsf(q), c.c8);
+        v[2] = wrapT<T>(cvt_trunc(__fmul_rn(sc, r)));
+        v[3] = wrapT<T>(cvt_trunc(__fmul_rn(sc, q)));
+        r = __fsub_rn(fabsf(r), c.c4);
+        q = __fsub_rn(fabsf(q), c.c4);
+        v[4] = wrapT<T>(cvt_trunc(__fmul_rn(sc, r)));
+        v[5] = wrapT<T>(cvt_trunc(__fmul_rn(sc, q)));
+        r = __fsub_rn(fabsf(r), c.c2);
+        q = __fsub_rn(fabsf(q), c.c2);
+        v[6] = wrapT<T>(cvt_trunc(__fmul_rn(sc, r)));
+        v[7] = wrapT<T>(cvt_trunc(__fmul_rn(sc, q)));
+        break;
+      }
+    }
+    // descrambling: wrapping negation where the sequence bit is 1 (srslte_vec_neg_* against c_short / c_char = +-1)
+    const uint32_t b0 = (uint32_t)i * (uint32_t)Qm;
+    if (d.scr) {
+      // 16 sequence bits starting at byte b0 / 8 (the second byte only when the symbol's bits reach into it)
+      const uint32_t win = ((uint32_t)d.scr[b0 >> 3] << 8) | (((b0 & 7u) + (uint32_t)Qm > 8u) ? (uint32_t)d.scr[(b0 >> 3) + 1] : 0u);
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < Qm && ((win >> (15 - (b0 & 7u) - k)) & 1u))
+          v[k] = wrapT<T>(-v[k]);
+    }
+    if (vec4) {
+      u32*      o  = reinterpret_cast<u32*>(out + b0);
+      const int nw = Qm * (int)sizeof(T) / 4;
+#pragma unroll
+      for (int w = 0; w < 4; w++)
+        if (w < nw)
+          o[w] = S ? pack16(v[2 * w], v[2 * w + 1])
+                   : ((u32)(uint8_t)v[4 * w] | ((u32)(uint8_t)v[4 * w + 1] << 8) | ((u32)(uint8_t)v[4 * w + 2] << 16) | ((u32)(uint8_t)v[4 * w + 3] << 24));
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; k++)
+        if (k < Qm)
+          out[b0 + k] = (T)v[k];
+    }
   }
 }
 

@@ -114,3 +114,30 @@ def awgn_llr(rng, bits, amp, sigma, dtype):
     x = amp * ((2.0 * bits.astype(np.float32) - 1.0) + sigma * rng.standard_normal(bits.shape, dtype=np.float32))
     info = np.iinfo(dtype)
     return np.clip(np.rint(x), info.min + 1, info.max).astype(dtype)
+
+
+# ---------------------------------------------------------------------------------------------- modulation mapper
+_AMP = {2: np.array([1, 3]), 3: np.array([3, 1, 5, 7]), 4: np.array([5, 7, 3, 1, 11, 9, 13, 15])}
+
+
+def lte_modulate(bits, mod):
+    """TS 36.211 7.1 modulation mapper: bits (one per element, length = nsym * Qm) -> complex64 symbols.
+    mod: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM (srslte_mod_t)."""
+    bits = np.asarray(bits, np.int64)
+    if mod == 0:
+        return ((1 - 2 * bits) * (1 + 1j) / np.sqrt(2)).astype(np.complex64)
+    Qm = 2 * mod
+    b_ = bits.reshape(-1, Qm)
+    if mod == 1:
+        return (((1 - 2 * b_[:, 0]) + 1j * (1 - 2 * b_[:, 1])) / np.sqrt(2)).astype(np.complex64)
+    h = Qm // 2 - 1  # amplitude bits per axis
+    norm = {2: np.sqrt(10), 3: np.sqrt(42), 4: np.sqrt(170)}[mod]
+    ii = np.zeros(len(b_), np.int64)
+    qq = np.zeros(len(b_), np.int64)
+    for k in range(h):
+        ii = 2 * ii + b_[:, 2 + 2 * k]
+        qq = 2 * qq + b_[:, 3 + 2 * k]
+    amp = _AMP[mod]
+    re = (1 - 2 * b_[:, 0]) * amp[ii]
+    im = (1 - 2 * b_[:, 1]) * amp[qq]
+    return ((re + 1j * im) / norm).astype(np.complex64)

@@ -12,6 +12,8 @@ Outputs (small, compressed):
   tests/golden/tables.npz    digests of every QPP table and rate-dematch table of the reference (188 K x layouts x rv)
   tests/golden/tdec.npz      decided bytes after every half-iteration + LLR snapshots for a set of (K, width, amplitude)
   tests/golden/tb.npz        transport-block decodes through the real sch.c (incl. HARQ retransmissions)
+  tests/golden/demod.npz     soft demodulation (all modulations, int16 / int8, lengths around the SIMD group sizes),
+                             pseudo-random sequences and descrambled outputs
 """
 import ctypes
 import hashlib
@@ -121,5 +123,36 @@ def main():
         print(f, os.path.getsize(os.path.join(HERE, f + ".npz")))
 
 
+def make_demod():
+    """tests/golden/demod.npz: the reference's soft demodulator / sequence generator / descrambler on fixed inputs"""
+    R = Ref()
+    rng = np.random.default_rng(2026)
+    out = {}
+    lens = (1, 7, 8, 9, 16, 17, 31, 100, 203)
+    amps = (0.3, 1.0, 3.0, 50.0, 400.0)
+    for n in lens:
+        for a, amp in enumerate(amps):
+            out["sym_%d_%d" % (n, a)] = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+    for mod in range(5):
+        for bits, dt in ((16, np.int16), (8, np.int8)):
+            for n in lens:
+                for a in range(len(amps)):
+                    out["llr_%d_%d_%d_%d" % (mod, bits, n, a)] = R.demod(mod, out["sym_%d_%d" % (n, a)], dt)
+    seqs = ((1, 104), (12345, 9000), (0x7fffffff, 11520), ((61 << 14) + (3 << 9) + 150, 2880))
+    out["seqs"] = np.array(seqs, np.int64)
+    for i, (c_init, L) in enumerate(seqs):
+        out["seq%d" % i] = R.sequence_bytes(c_init, L)[:L // 8]
+        for bits, dt in ((16, np.int16), (8, np.int8)):
+            d = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max + 1, L).astype(dt)
+            out["din%d_%d" % (i, bits)] = d
+            out["dout%d_%d" % (i, bits)] = R.descramble(c_init, d)
+    np.savez_compressed(os.path.join(HERE, "demod.npz"), **out)
+    print("demod", os.path.getsize(os.path.join(HERE, "demod.npz")))
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "demod":
+        make_demod()
+    else:
+        main()
+        make_demod()

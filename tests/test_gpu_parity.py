@@ -428,3 +428,70 @@ def test_drop_in_decode_tb_with_softbuffer(port):
         assert rcs[0] == -1 and rcs[-1] == 0, rcs
         sbg.free()
         port.softbuffer_del(sbp)
+
+
+# ----------------------------------------------------------------------------------------- soft demodulation
+@pytest.mark.parametrize("dtype", [np.int16, np.int8])
+def test_demod_descramble(port, ctx, dtype):
+    """k_demod_descramble against the oracle: every modulation, lengths around the reference's SIMD group sizes (its bodies
+    and tails round differently), amplitudes up to saturation, with and without descrambling, many codewords per call"""
+    rng = np.random.default_rng(31 + (dtype == np.int8))
+    cws, want = [], []
+    for mod in range(5):
+        for n in (1, 3, 4, 7, 8, 9, 15, 16, 17, 31, 33, 100, 1001, 15000):
+            amp = (0.3, 1.0, 3.0, 50.0, 400.0)[(n + mod) % 5]
+            sym = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+            nbits = n * b.MOD_BITS[mod]
+            scr = port.sequence_bytes(int(rng.integers(1, 2 ** 31)), nbits) if (n + mod) % 3 else None
+            cws.append((sym, mod, scr))
+            llr = port.demod(mod, sym, dtype)
+            want.append(port.descramble(scr, llr) if scr is not None else llr)
+    got = ctx.demod_descramble(cws, dtype)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert (g == w).all(), (i, cws[i][1], len(cws[i][0]))
+
+
+def test_sequence_bytes_helper(port):
+    for c_init, L in ((1, 100), (12345, 90000), (0x7fffffff, 115203), (777, 33)):
+        assert (b.sequence_bytes(c_init, L) == port.sequence_bytes(c_init, L)).all()
+
+
+@pytest.mark.parametrize("tbs,mod,dtype,sigma", [(75376, 3, np.int16, 0.08), (97896, 4, np.int8, 0.012), (15264, 2, np.int16, 0.15), (1000, 1, np.int8, 0.3)])
+def test_symbols_to_transport_block_on_device(port, ctx, tbs, mod, dtype, sigma):
+    """the chain of pdsch.c:832-859 on the device: equalised symbols -> soft demodulation -> descrambling -> decode_tb, LLRs
+    never leaving the GPU (demod with OUT_DEVICE, decode with IN_DEVICE), against the same chain through the oracle"""
+    from srsran_b200 import synth
+    rng = np.random.default_rng(tbs + mod)
+    Qm = b.MOD_BITS[mod]
+    nsym = {75376: 15000, 97896: 14400, 15264: 5000, 1000: 1440}[tbs]
+    G = nsym * Qm
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    e = port.encode_tb(tbs, Qm, 0, G, data)  # rate-matched bits (one per byte)
+    c_init = (0x1234 << 14) + (0 << 13) + (3 << 9) + 77
+    scr = port.sequence_bytes(c_init, G)
+    scr_bits = np.unpackbits(scr)[:G]
+    sym = synth.lte_modulate(e ^ scr_bits, mod)
+    sym = (sym + sigma * (rng.standard_normal(nsym) + 1j * rng.standard_normal(nsym))).astype(np.complex64)
+    # oracle chain
+    llr = port.descramble(scr, port.demod(mod, sym, dtype))
+    sbp = port.softbuffer_new()
+    rc, want, nit, avg, crc = port.decode_tb(sbp, tbs, Qm, 0, llr, 8)
+    port.softbuffer_del(sbp)
+    # device chain
+    d_e = ctx.device_alloc(G * np.dtype(dtype).itemsize + 64)
+    dm = b.make_demods(1)
+    dm[0].symbols, dm[0].nof_symbols, dm[0].mod, dm[0].scramble_bytes, dm[0].e_bits = sym.ctypes.data, nsym, mod, scr.ctypes.data, d_e
+    ctx.demod_descramble_raw(dm, dtype == np.int8, b.OUT_DEVICE)
+    d_out = ctx.device_alloc(tbs // 8 + 64)
+    t = b.make_tbs(1)
+    t[0].e_bits, t[0].nof_e_bits, t[0].tbs, t[0].Qm, t[0].rv, t[0].softbuffer, t[0].data = d_e, G, tbs, Qm, 0, None, d_out
+    ctx.decode_tbs(t, dtype == np.int8, 8, flags=b.IN_DEVICE | b.OUT_DEVICE)
+    out = np.zeros(tbs // 8 + 6, np.uint8)
+    ctx.d2h(out, d_out)
+    ctx.device_free(d_e)
+    ctx.device_free(d_out)
+    C_ = t[0].nof_cb
+    nb = tbs // 8 + (3 if C_ == 1 else 6)
+    assert t[0].ret == rc and (out[:nb] == want[:nb]).all()
+    assert rc == 0 and (out[:tbs // 8] == data).all()  # (the case is meant to decode)
+    assert list(t[0].cb_noi[:C_]) == nit[:C_].tolist()

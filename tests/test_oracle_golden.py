@@ -106,3 +106,23 @@ def test_transport_blocks_against_reference_outputs(port):
             if rc == 0:
                 assert (d[:tbs // 8] == t["data%d" % idx]).all()
         port.softbuffer_del(sb)
+
+
+def test_soft_demodulation_against_reference_outputs(port):
+    """srslte_demod_soft_demodulate_{s,b}, srslte_sequence_LTE_pr and srslte_scrambling_{s,sb}_offset of the
+    unmodified reference on fixed inputs (tests/golden/demod.npz)"""
+    g = np.load(os.path.join(G, "demod.npz"))
+    n_checked = 0
+    for key in g.files:
+        if not key.startswith("llr_"):
+            continue
+        _, mod, bits, n, a = key.split("_")
+        got = port.demod(int(mod), g["sym_%s_%s" % (n, a)], np.int16 if bits == "16" else np.int8)
+        assert (got == g[key]).all(), key
+        n_checked += 1
+    assert n_checked == 5 * 2 * 9 * 5
+    for i, (c_init, L) in enumerate(g["seqs"]):
+        cb = port.sequence_bytes(int(c_init), int(L))
+        assert (cb[:int(L) // 8] == g["seq%d" % i]).all()
+        for bits in (16, 8):
+            assert (port.descramble(cb, g["din%d_%d" % (i, bits)]) == g["dout%d_%d" % (i, bits)]).all()

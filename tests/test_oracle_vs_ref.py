@@ -169,3 +169,28 @@ def test_known_vector_vs_reference_encoder(ref):
     k = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat.npz"))
     got = ref.tcod_encode(k["known_data"])
     assert np.nonzero(got != k["known_data_encoded"])[0].tolist() == [1512]
+
+
+# ----------------------------------------------------------------------------------------- SURVEY 8f row 1
+@pytest.mark.parametrize("mod", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("dtype", [np.int16, np.int8])
+def test_soft_demodulation(port, ref, mod, dtype):
+    """srslte_demod_soft_demodulate_{s,b}: the restatement reproduces the reference's SSE bodies (round to nearest,
+    saturating packs, integer thresholds) AND its scalar tails (truncation, wrap, float thresholds) -- lengths around
+    the SIMD group sizes, amplitudes up to saturation"""
+    rng = np.random.default_rng(100 + mod)
+    for n in (1, 3, 4, 7, 8, 9, 15, 16, 17, 31, 32, 100, 1001, 15000):
+        for amp in (0.3, 1.0, 3.0, 50.0, 400.0):
+            sym = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+            assert (port.demod(mod, sym, dtype) == ref.demod(mod, sym, dtype)).all(), (n, amp)
+
+
+def test_sequence_and_descrambling(port, ref):
+    """srslte_sequence_LTE_pr (c_bytes) and srslte_scrambling_{s,sb}_offset"""
+    rng = np.random.default_rng(5)
+    for c_init, L in ((1, 104), (12345, 90000), (0x7fffffff, 115200), (777, 40), ((61 << 14) + (3 << 9) + 150, 28800)):
+        cb = port.sequence_bytes(c_init, L)
+        assert (cb[:L // 8] == ref.sequence_bytes(c_init, L)[:L // 8]).all()
+        for dtype in (np.int16, np.int8):
+            d = rng.integers(np.iinfo(dtype).min, np.iinfo(dtype).max + 1, L).astype(dtype)
+            assert (port.descramble(cb, d) == ref.descramble(c_init, d)).all()
