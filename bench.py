@@ -521,6 +521,36 @@ def run_ours(args):
         extra["avg_half_iterations"] = avg_it
         extra["tb_ok_fraction"] = n_ok / ntb
 
+        # ---- front end of the path: soft demodulation + descrambling of the same subframes' symbols on
+        #      the device (k_demod_descramble, HBM-bound): device-resident symbols in, LLRs out, CUDA-event timed
+        mod = {6: 3, 8: 4}[Qm]
+        nsym = G // Qm
+        sym = ((rng.standard_normal((ntb, nsym)) + 1j * rng.standard_normal((ntb, nsym))) * 0.7).astype(np.complex64)
+        scr = b.sequence_bytes(0x12345, G)
+        d_sym = ctx.device_alloc(sym.nbytes)
+        d_scr = ctx.device_alloc(len(scr) + 16)
+        d_e = ctx.device_alloc(ntb * G * esz)
+        ctx.h2d(d_sym, sym)
+        ctx.h2d(d_scr, scr)
+        dm = b.make_demods(ntb)
+        for i in range(ntb):
+            dm[i].symbols, dm[i].nof_symbols, dm[i].mod, dm[i].scramble_bytes, dm[i].e_bits = d_sym + i * nsym * 8, nsym, mod, d_scr, d_e + i * G * esz
+        for _ in range(3):
+            ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
+        reps = 10
+        ctx.timer_start()
+        for _ in range(reps):
+            ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
+        fe_ms = ctx.timer_stop_ms() / reps
+        fe_bytes = ntb * (nsym * 8 + G * esz + G / 8)
+        extra["front_end"] = {"kernel": "k_demod_descramble", "what": "%d codewords x %d symbols, %s, %s LLRs, device-resident" % (
+                                  ntb, nsym, {3: "64QAM", 4: "256QAM"}[mod], np.dtype(dt).name),
+                              "ms": fe_ms, "gsym_per_s": ntb * nsym / (fe_ms * 1e-3) / 1e9,
+                              "hbm": {"achieved_gbs": fe_bytes / (fe_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                                      "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
+        for p_ in (d_sym, d_scr, d_e):
+            ctx.device_free(p_)
+
     # ---- roofline of the dominant kernel (k_map_win): integer-ALU issue bound.  The kernel is timed on its own here
     #      (one engine, batches back to back, CUDA events around every launch on the launching stream).
     rsteps = max(1, min(5, args.steps))
