@@ -15,7 +15,10 @@ d_out = ctx.device_alloc(ncb * K // 8)
 ctx.h2d(d_llr, llr)
 ref = None
 for cfg in cfgs:
-    ctx.set_option("map_cfg", cfg)
+    try:
+        ctx.set_option("map_cfg", cfg)  # (an engine option of the experiment builds; the release engine has one geometry)
+    except Exception:
+        pass
     best = 1e9
     for _ in range(4):
         ctx.tdec_batch_device(d_llr, d_out, K, ncb, 3 * K + 12, 16, 4)

@@ -625,18 +625,15 @@ int Engine::run(Plan& p)
       CUDA_OK(cudaEventRecord(e0, stream));
       cudaError_t e;
       // the a-posteriori plane is only read by the hard decision: skip writing it when no decision follows this launch
-      const int   skip_post = (cls[c].no_crc && it + 1 < p.max_iter) ? 0x2000 : 0;
+      const int   skip_post = (cls[c].no_crc && it + 1 < p.max_iter) ? kMapSkipPost : 0;
       const bool  fast = opt_fast16 && c < 2;
       if (fast) {
         // native packed-instruction attempt with range monitoring, then exact replay of the flagged code blocks
         a.mode = 1 | skip_post;
-        a.mode |= opt_map_cfg & 0xff00; // (measurement switches of k_map_f16)
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
-        switch (opt_map_cfg & 0xff) {
-          case 1: e = c == 0 ? launch_map_f16<Fast16, 8, 256, 2, 2>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 256, 2, 2>(a, ns, n_it, stream); break;
-          default: e = c == 0 ? launch_map_f16<Fast16, 8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 128, 3, 3>(a, ns, n_it, stream); break;
-        }
+        // 128-thread CTAs, 3 per SM, 3 staging stages: the best of the geometries measured (profiles/README.md)
+        e = c == 0 ? launch_map_f16<Fast16, 8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 128, 3, 3>(a, ns, n_it, stream);
         CUDA_OK(e);
         last_launches++;
         a.mode = 2;
@@ -1435,10 +1432,6 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (!strcmp(name, "fast16")) {
     ctx->e->opt_fast16 = value != 0;
-    return 0;
-  }
-  if (!strcmp(name, "map_cfg")) {
-    ctx->e->opt_map_cfg = value;
     return 0;
   }
   return SRSLTE_B200_ERROR_INVALID_INPUTS;

@@ -92,7 +92,6 @@ public:
   DevBuf<int16_t>  d_ws, d_tails, d_sb;
   DevBuf<uint8_t>  d_cbout, d_in, d_tbout;
   DevBuf<int>      d_lists, d_gmax;
-  int              opt_map_cfg = 0;
   bool             opt_fast16 = true; // try the native packed-instruction path first (exact replay on range alarm)
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch;
   PinBuf<uint32_t> h_counters;

@@ -430,6 +430,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
 }
 
 // ------------------------------------------------------------------------------------------ windowed MAP
+constexpr int kMapSkipPost = 0x2000;
 struct MapArgs {
   const int*      work;    // code block per slot, -1 = padding (slots of one warp share K)
   int             n_slots;
@@ -439,7 +440,8 @@ struct MapArgs {
   const int16_t*  tails;
   const uint16_t* qpp;
   int*            gmax; // per CB: max|syst|, max|par0|, max|par1|, max|extrinsic handed to the next half-iteration|
-  int             mode; // 0: decode every active CB; 1: Fast16 attempt (flags redo); 2: replay only CBs flagged redo
+  int             mode; // 0: decode every active CB; 1: Fast16 attempt (flags redo); 2: replay only CBs flagged redo;
+                        // | kMapSkipPost: no hard decision follows this launch, the a-posteriori plane is not written
   u32*            ck_scratch; // global beta-checkpoint scratch: ck_slots x (grid threads) x 8 words
   int             ck_slots;
   const uint32_t* counters; // DecideArgs::counters

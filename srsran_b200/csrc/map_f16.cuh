@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   const int a0  = (W - kWinOverlap) >> 3;
   const int nAW = nT - a0;
   const int s1 = 5, s2 = s1 + nT, s3 = s2 + nAW, n_seq = s3 + nT;
-  const bool     hints     = (a.mode & 0x100) == 0; // (bit 8 of mode: L2 hints off, for A/B measurements)
+  const bool     write_post = (a.mode & kMapSkipPost) == 0; // the a-posteriori plane is only read by a hard decision
   const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
   auto bar_of = [&](int stage) -> unsigned { return sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * stage); };
   int wr_idx = 0, wr_stage = 0; // next tile of the sequence to request / its stage
@@ -198,19 +198,11 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       }
       const int      r1        = (8 * t + 8) < W ? 8 : W - 8 * t;
       const unsigned lut_bytes = (unsigned)r1 * T * 4u;
-      const bool dbg_nock = a.mode & 0x200, dbg_nolut = a.mode & 0x400; // (timing experiments only: results are wrong)
-      mbar_expect_tx(bar, aux ? kBoxBytes + (dbg_nolut ? 0u : lut_bytes) + (dbg_nock ? 0u : 1024u) : kBoxBytes);
-      if (hints)
-        tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, pol_first);
-      else
-        tma_tile4(dst, tmap, 0, blk0, 8 * t, plane0, bar);
-      if (aux && !dbg_nolut)
+      mbar_expect_tx(bar, aux ? kBoxBytes + lut_bytes + 1024u : kBoxBytes);
+      tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, pol_first);
+      if (aux) {
         bulk_g2s(dst + 4u * (unsigned)Lay::kLutOff, lut + (size_t)8 * t * T, lut_bytes, bar);
-      if (aux && !dbg_nock) {
-        if (hints)
-          bulk_g2s_hint(dst + 4u * (unsigned)Lay::kCkOff, ck_warp + (size_t)(t + 1) * ck_stride, 1024u, bar, pol_first);
-        else
-          bulk_g2s(dst + 4u * (unsigned)Lay::kCkOff, ck_warp + (size_t)(t + 1) * ck_stride, 1024u, bar);
+        bulk_g2s_hint(dst + 4u * (unsigned)Lay::kCkOff, ck_warp + (size_t)(t + 1) * ck_stride, 1024u, bar, pol_first);
       }
     }
     wr_idx++;
@@ -284,15 +276,10 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   }
   // ---- main pass with one checkpoint per tile: slot t = beta[8t] before normalisation, slot nT = beta[W]
   auto ck_store = [&](int sl, const u32 (&v)[8]) {
-    if (live && !(a.mode & 0x800)) {
+    if (live) {
       uint4* g = reinterpret_cast<uint4*>(ck_warp + (size_t)sl * ck_stride) + lane;
-      if (hints) {
-        stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), pol_last);
-        stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), pol_last);
-      } else {
-        g[0]  = make_uint4(v[0], v[1], v[2], v[3]);
-        g[32] = make_uint4(v[4], v[5], v[6], v[7]);
-      }
+      stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), pol_last);
+      stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), pol_last);
     }
   };
   if (P::kMonitor)
@@ -341,7 +328,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   if (P::kMonitor) {
     const bool bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
     if (__any_sync(gmask, bad && live)) { // the whole code block is replayed with the exact policy (mode 2 launch)
-      if (j == 0 && live && !(a.mode & 0xde00))
+      if (j == 0 && live)
         a.state[cb].redo = 1;
       live = false;
     }
@@ -433,9 +420,9 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
       const u32      e  = kApr ? P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat) : llr;
       track_e(e);
-      if (live && !(a.mode & 0x2000))
+      if (live && write_post)
         post[(8 * t + i) * T + j] = llr;
-      if (live && !(a.mode & 0x1000)) {
+      if (live) {
         ext[t0] = (int16_t)lo16(e);
         ext[t1] = (int16_t)hi16(e);
       }
@@ -443,11 +430,11 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
       // a-posteriori -> post[fwd[.]]; a-posteriori - own input -> a-priori[fwd[.]]
       const u32 e = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
       track_e(e);
-      if (live && !(a.mode & 0x1000)) {
+      if (live) {
         ext[t0]    = (int16_t)lo16(e);
         ext[t1]    = (int16_t)hi16(e);
       }
-      if (live && !(a.mode & 0x2000)) {
+      if (live && write_post) {
         post16[t0] = (int16_t)lo16(llr);
         post16[t1] = (int16_t)hi16(llr);
       }
@@ -540,7 +527,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
                      !fast16_alpha_ok(mon_h.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_h.spread_hi(), mon_b.spread_hi(), g) ||
                      ((mon_a.ovf | mon_h.ovf) & 0x80008000u) != 0;
     if (__any_sync(gmask, bad && live)) {
-      if (j == 0 && live && !(a.mode & 0xde00))
+      if (j == 0 && live)
         a.state[cb].redo = 1;
       return;
     }
