@@ -1,0 +1,64 @@
+"""One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
+k_prepare, k_map_f16 (Fast16 and Sat8, the three decoder modes), k_map_win<Sat16> (exact path), k_map_gen, k_decide_crc,
+k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import srsran_b200 as b  # noqa: E402
+
+rng = np.random.default_rng(1)
+ctx = b.Context(0)
+
+
+def cb_batch(ncb, K, nit, dtype=np.int16):
+    llr, _ = bench.make_c1(rng, ncb, K) if (K == 6144 and dtype == np.int16) else (None, None)
+    if llr is None:
+        llr = rng.integers(-60, 61, (ncb, 3 * K + 12)).astype(dtype)
+    d_llr = ctx.device_alloc(llr.nbytes)
+    d_out = ctx.device_alloc(ncb * K // 8 + 64)
+    ctx.h2d(d_llr, llr)
+    ctx.tdec_batch_device(d_llr, d_out, K, ncb, 3 * K + 12, 16 if dtype == np.int16 else 8, nit)
+
+
+def tb_batch(wl, ntb, max_iter):
+    cfg = bench.TB_CFG[wl]
+    tbs, Qm, G, dt = cfg["tbs"], cfg["Qm"], cfg["G"], cfg["dtype"]
+    llr, _ = bench.make_tb(rng, ntb, tbs, Qm, G, dt, cfg["amp"], cfg["sigma"])
+    esz = np.dtype(dt).itemsize
+    ostride = (tbs // 8 + 6 + 15) // 16 * 16
+    d_llr = ctx.device_alloc(llr.nbytes)
+    d_out = ctx.device_alloc(ntb * ostride)
+    ctx.h2d(d_llr, llr)
+    t = b.make_tbs(ntb)
+    for i in range(ntb):
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].softbuffer, t[i].data = d_llr + i * G * esz, G, tbs, Qm, 0, None, d_out + i * ostride
+    ctx.decode_tbs(t, dt == np.int8, max_iter, flags=b.IN_DEVICE | b.OUT_DEVICE)
+
+
+cb_batch(4736, 6144, 3)           # k_prepare, k_map_f16<Fast16,16,{0,2,1}>, k_decide_crc
+tb_batch("c2", 364, 3)            # k_dematch_prepare<short>, k_tb_finish
+tb_batch("c4", 296, 3)            # k_dematch_prepare<int8>, k_map_f16<Sat8,32,*>
+ctx.set_option("fast16", 0)
+cb_batch(1184, 6144, 2)           # k_map_win<Sat16,16> doing real work (the exact path)
+ctx.set_option("fast16", 1)
+cb_batch(2368, 512, 2)            # k_map_f16<Fast16,8,*>
+cb_batch(4096, 40, 2)             # k_map_gen
+for dt, mod in ((np.int16, 3), (np.int8, 4)):
+    n, nsym = 256, 15000
+    sym = ((rng.standard_normal((n, nsym)) + 1j * rng.standard_normal((n, nsym))) * 0.7).astype(np.complex64)
+    scr = b.sequence_bytes(0x12345, nsym * 8)
+    d_sym, d_scr = ctx.device_alloc(sym.nbytes), ctx.device_alloc(len(scr) + 16)
+    d_e = ctx.device_alloc(n * nsym * 8 * 2)
+    ctx.h2d(d_sym, sym)
+    ctx.h2d(d_scr, scr)
+    dm = b.make_demods(n)
+    Qm = b.MOD_BITS[mod]
+    for i in range(n):
+        dm[i].symbols, dm[i].nof_symbols, dm[i].mod, dm[i].scramble_bytes, dm[i].e_bits = d_sym + i * nsym * 8, nsym, mod, d_scr, d_e + i * nsym * Qm * np.dtype(dt).itemsize
+    ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
+ctx.wait()
+print("done")

@@ -78,6 +78,8 @@ struct Sat16 {
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   // max(a + b, c) with the reference's saturating add
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_max(p_add_sat(a, b), c); }
+  // max(a + b, c + d), both sums saturating
+  B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_max(p_add_sat(a, b), p_add_sat(c, d)); }
   static constexpr int kNormPeriod = 2;
   B200_HD static void normalize_now(u32 (&o)[8])
   {
@@ -113,6 +115,7 @@ struct Fast16 {
   B200_HD static u32 sub(u32 a, u32 b) { return p_sub_wrap(a, b); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_addmax(a, b, p_add_wrap(c, d)); }
   static constexpr int kNormPeriod = 2;
   B200_HD static void normalize_now(u32 (&o)[8])
   {
@@ -140,7 +143,12 @@ struct Sat8 {
   B200_HD static u32 add(u32 a, u32 b) { return p_min(p_addmax(a, b, 0xff80ff80u), 0x007f007fu); }
   B200_HD static u32 sub(u32 a, u32 b) { return clamp8(p_sub_wrap(a, b)); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
-  B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_max(add(a, b), c); }
+  // max(clamp8(a + b), c) for c already in [-128, 127] (every metric is): the lower clamp is absorbed by the max with c
+  // and the upper clamp commutes with it, so one fused add-max and one min give the same integers as add() + max()
+  B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_min(p_addmax(a, b, c), 0x007f007fu); }
+  // max(clamp8(a + b), clamp8(c + d)) = clamp8(max(a + b, c + d)) (the clamp is monotone; the int16 containers hold the
+  // unclamped sums exactly): one wrapping add on the add-type pipe, a fused add-max and one clamp
+  B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return clamp8(p_addmax(a, b, p_add_wrap(c, d))); }
   static constexpr int kNormPeriod = 1;
   B200_HD static void normalize_now(u32 (&o)[8])
   {
@@ -148,9 +156,11 @@ struct Sat8 {
     m     = p_max3(m, o[3], o[4]);
     m     = p_max3(m, o[5], o[6]);
     m     = p_max(m, o[7]);
+    // o[i] - m lies in [-255, 0]: only the lower bound of the saturating subtract can act
+    const u32 nm = p_sub_wrap(0u, m);
 #pragma unroll
     for (int i = 0; i < 8; i++)
-      o[i] = sub(o[i], m);
+      o[i] = p_addmax(o[i], nm, 0xff80ff80u);
   }
   // normalize_max, period 1 (turbodecoder_win.h:180-181, 483-490)
   B200_HD static void normalize(uint32_t k, u32 (&o)[8])
@@ -159,7 +169,8 @@ struct Sat8 {
       normalize_now(o);
   }
   // divide_output: per-element arithmetic >> 1 (turbodecoder_win.h:188-193, 811-813)
-  B200_HD static u32 out(u32 llr) { return pack16(lo16(llr) >> 1, hi16(llr) >> 1); }
+  // (both halves at once: bits 14..0 of each half come from the logical shift, the sign bit is put back)
+  B200_HD static u32 out(u32 llr) { return ((llr >> 1) & 0x7fff7fffu) | (llr & 0x80008000u); }
   // int16 z = x + y; z > 127 ? 127 : (int8_t) z   (saturates upwards only)
   B200_HD static int32_t tail_add(int32_t a, int32_t b)
   {

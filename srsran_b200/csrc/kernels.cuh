@@ -816,6 +816,7 @@ struct Wrap16 { // turbodecoder_gen.c: plain C int16 arithmetic
   B200_HD static u32 sub(u32 a, u32 b) { return p_sub_wrap(a, b); }
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_addmax(a, b, p_add_wrap(c, d)); }
   B200_HD static u32 out(u32 v) { return v; }
 };
 

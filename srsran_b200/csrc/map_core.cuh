@@ -24,10 +24,10 @@ B200_HD void bwd_step(u32 (&o)[8], u32 x, u32 y, u32 xy)
 {
   const u32 n0 = P::addmax(o[4], xy, o[0]);
   const u32 n1 = P::addmax(o[0], xy, o[4]);
-  const u32 n2 = P::addmax(o[5], y, P::add(o[1], x));
-  const u32 n3 = P::addmax(o[5], x, P::add(o[1], y));
-  const u32 n4 = P::addmax(o[6], x, P::add(o[2], y));
-  const u32 n5 = P::addmax(o[6], y, P::add(o[2], x));
+  const u32 n2 = P::addmax2(o[5], y, o[1], x);
+  const u32 n3 = P::addmax2(o[5], x, o[1], y);
+  const u32 n4 = P::addmax2(o[6], x, o[2], y);
+  const u32 n5 = P::addmax2(o[6], y, o[2], x);
   const u32 n6 = P::addmax(o[3], xy, o[7]);
   const u32 n7 = P::addmax(o[7], xy, o[3]);
   o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
@@ -38,12 +38,12 @@ template <class P>
 B200_HD void fwd_step(u32 (&o)[8], u32 x, u32 y, u32 xy)
 {
   const u32 n0 = P::addmax(o[1], xy, o[0]);
-  const u32 n1 = P::addmax(o[3], y, P::add(o[2], x));
-  const u32 n2 = P::addmax(o[4], y, P::add(o[5], x));
+  const u32 n1 = P::addmax2(o[3], y, o[2], x);
+  const u32 n2 = P::addmax2(o[4], y, o[5], x);
   const u32 n3 = P::addmax(o[6], xy, o[7]);
   const u32 n4 = P::addmax(o[0], xy, o[1]);
-  const u32 n5 = P::addmax(o[2], y, P::add(o[3], x));
-  const u32 n6 = P::addmax(o[5], y, P::add(o[4], x));
+  const u32 n5 = P::addmax2(o[2], y, o[3], x);
+  const u32 n6 = P::addmax2(o[5], y, o[4], x);
   const u32 n7 = P::addmax(o[7], xy, o[6]);
   o[0] = n0; o[1] = n1; o[2] = n2; o[3] = n3; o[4] = n4; o[5] = n5; o[6] = n6; o[7] = n7;
 }
