@@ -36,8 +36,8 @@ def main():
             ("lsu%", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"), ("L2hit%", "lts__t_sector_hit_rate.pct")]
     with open(out, "w") as f:
         f.write("# longest launch of every kernel in %s; DRAM GB/s = (dram__bytes_read.sum + dram__bytes_write.sum) / gpu__time_duration.sum, peak %.0f GB/s\n" % (rep, peak))
-        f.write("# issue%% = smsp__issue_active; alu%% / fma%% / lsu%% = sm__inst_executed_pipe_* (pct of peak sustained active; the packed int16x2 ops run on\n")
-        f.write("# two 16-lane pipes, see DESIGN 5.0: 50 %% here is a full integer pipe)\n")
+        f.write("# issue% = smsp__issue_active; alu% / fma% / lsu% = sm__inst_executed_pipe_* (pct of peak sustained active; the packed int16x2 ops run on\n")
+        f.write("# two 16-lane pipes, see DESIGN 5.0: 100 % of alu / fma = 0.5 warp-instructions per clock and sub-partition)\n")
         f.write("%-62s %9s %8s %8s %7s" % ("kernel", "time us", "rd MB", "wr MB", "GB/s") + " %6s" % "%peak" + "".join(" %8s" % c for c, _ in cols) + "\n")
         for name, (t, r) in sorted(best.items(), key=lambda kv: -kv[1][0]):
             rd = num(r[ix["dram__bytes_read.sum"]]) * scale.get(units[ix["dram__bytes_read.sum"]], 1.0) if "dram__bytes_read.sum" in ix else float("nan")
