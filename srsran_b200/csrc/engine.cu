@@ -381,20 +381,30 @@ static int encode_group_map(CUtensorMap* out, int16_t* base, uint32_t lanes, uin
   return 0;
 }
 
-template <class P, int N, int NT, int MINB, int STAGES>
-static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaStream_t st)
+template <class P, int N, int MODE, int NT, int MINB, int STAGES>
+static cudaError_t launch_map_f16_mode(MapArgs a, int n_slots, cudaStream_t st)
 {
   constexpr int T = N / 2, G = 32 / T;
   const int     warps  = (n_slots + G - 1) / G;
   const int     blocks = (warps + (NT / 32) - 1) / (NT / 32);
-  const size_t  smem   = (size_t)(NT / 32) * F16Lay<T, STAGES>::kWarpWords * 4;
-  void (*kern)(const MapArgs) = (n_iter & 1) ? k_map_f16<P, N, 2, NT, MINB, STAGES>
-                                             : (n_iter ? k_map_f16<P, N, 1, NT, MINB, STAGES> : k_map_f16<P, N, 0, NT, MINB, STAGES>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const size_t  smem   = (size_t)(NT / 32) * F16Lay<T, STAGES, MODE == 1 ? 3 : 2>::kWarpWords * 4;
+  auto          kern   = k_map_f16<P, N, MODE, NT, MINB, STAGES>;
+  cudaError_t   e      = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess)
     return e;
   kern<<<blocks, NT, smem, st>>>(a);
   return cudaGetLastError();
+}
+// Geometry: 128-thread CTAs, three per SM, three staging stages -- the best of the geometries measured
+// (profiles/README.md; four CTAs per SM fit for the two-plane variants but run no faster: DRAM pressure grows with them)
+template <class P, int N>
+static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaStream_t st)
+{
+  if (n_iter & 1)
+    return launch_map_f16_mode<P, N, 2, 128, 3, 3>(a, n_slots, st);
+  if (n_iter)
+    return launch_map_f16_mode<P, N, 1, 128, 3, 3>(a, n_slots, st);
+  return launch_map_f16_mode<P, N, 0, 128, 3, 3>(a, n_slots, st);
 }
 
 int Engine::run(Plan& p)
@@ -632,8 +642,7 @@ int Engine::run(Plan& p)
         a.mode = 1 | skip_post;
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
-        // 128-thread CTAs, 3 per SM, 3 staging stages: the best of the geometries measured (profiles/README.md)
-        e = c == 0 ? launch_map_f16<Fast16, 8, 128, 3, 3>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16, 128, 3, 3>(a, ns, n_it, stream);
+        e = c == 0 ? launch_map_f16<Fast16, 8>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16>(a, ns, n_it, stream);
         CUDA_OK(e);
         last_launches++;
         a.mode = 2;
@@ -643,11 +652,11 @@ int Engine::run(Plan& p)
         case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break; // (or everything, fast16 off)
         case 2:
           a.mode |= skip_post;
-          e = launch_map_f16<Sat8, 16, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream);
+          e = launch_map_f16<Sat8, 16>(a, cls[c].n_slots, p.iter0 + it, stream);
           break;
         default:
           a.mode |= skip_post;
-          e = launch_map_f16<Sat8, 32, 128, 3, 3>(a, cls[c].n_slots, p.iter0 + it, stream);
+          e = launch_map_f16<Sat8, 32>(a, cls[c].n_slots, p.iter0 + it, stream);
           break;
       }
       CUDA_OK(e);

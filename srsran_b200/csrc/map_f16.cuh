@@ -88,11 +88,11 @@ __device__ __forceinline__ void stg128_hint(void* p, uint4 v, uint64_t pol)
   asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
-template <int T, int STAGES>
+template <int T, int STAGES, int PLANES>
 struct F16Lay {
   static constexpr int kRows       = 8;                                  // trellis steps per tile
   static constexpr int kPlaneWords = kRows * 32;                         // one plane of a tile: 8 box rows of 32 words
-  static constexpr int kLutOff     = 3 * kPlaneWords;                    // QPP rows of the warp [8][T]
+  static constexpr int kLutOff     = PLANES * kPlaneWords;               // (2 input planes, 3 for DEC1 with a-priori) | QPP rows [8][T]
   static constexpr int kCkOff      = kLutOff + kRows * T;                // checkpoint [2 halves][32 lanes][4 words]
   static constexpr int kStageWords = (kCkOff + 256 + 31) / 32 * 32;      // stages stay 128-byte aligned
   static constexpr int kStages     = STAGES;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(NT, MINB) k_map_f16(const MapArgs a)
   constexpr int  T = N / 2, G = 32 / T;
   constexpr int  kNP = P::kNormPeriod; // normalisation cadence of the reference: 2 (int16, by state 0) or 1 (int8, by the max)
   constexpr bool kDec2 = MODE == 2, kApr = MODE == 1;
-  using Lay = F16Lay<T, STAGES>;
+  using Lay = F16Lay<T, STAGES, kApr ? 3 : 2>;
   constexpr int kStages = STAGES;
   extern __shared__ __align__(128) u32 smem_f[];
 
