@@ -126,6 +126,26 @@ SRSLTE_B200_API int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const s
  * lib/src/phy/common/sequence.c); out: (len + 7) / 8 bytes.  Host helper for callers that do not hold the sequence. */
 SRSLTE_B200_API void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out);
 
+/* ---- transmit mirror: the batched form of srslte_dlsch_encode2 / encode_tb_off (lib/src/phy/phch/sch.c:
+ * 235-349): TB CRC24A, code block segmentation, CB CRC24B, srslte_tcod_encode_lut (lib/src/phy/fec/turbocoder.c:190-372),
+ * srslte_rm_turbo_tx_lut (lib/src/phy/fec/rm_turbo.c:349-395).  Stateless: retransmissions (rv != 0) are re-encoded from
+ * the payload instead of being read back from a srslte_softbuffer_tx_t; the bits are the same.
+ *   data     tbs/8 payload bytes            e_bits  out: nof_e_bits packed bits (first bit = MSB of byte 0), 4-byte aligned,
+ *                                                    (nof_e_bits + 31) / 32 * 4 bytes are written
+ *   ret      0, or -1 (TBS needs filler bits / too many code blocks: the reference rejects those too), -2 (invalid)
+ * flags as for srslte_b200_demod_descramble. */
+typedef struct {
+  const uint8_t* data;
+  uint32_t       tbs;
+  uint32_t       Qm;
+  uint32_t       rv;
+  uint32_t       nof_e_bits;
+  uint8_t*       e_bits;
+  int32_t        ret;
+} srslte_b200_enc_t;
+
+SRSLTE_B200_API int srslte_b200_encode_tbs(srslte_b200_ctx_t* ctx, srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags);
+
 /* device-resident HARQ soft buffers (srslte_softbuffer_rx_init / _reset / _free, softbuffer.c:41-155) */
 SRSLTE_B200_API int  srslte_b200_softbuffer_create(srslte_b200_ctx_t* ctx, srslte_b200_softbuffer_t** sb, uint32_t max_cb);
 SRSLTE_B200_API void srslte_b200_softbuffer_reset(srslte_b200_softbuffer_t* sb);

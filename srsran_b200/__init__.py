@@ -41,6 +41,11 @@ class Tb(C.Structure):  # srslte_b200_tb_t
                 ("cb_noi", C.c_uint8 * MAX_CODEBLOCKS), ("nof_cb", C.c_uint32)]
 
 
+class Enc(C.Structure):  # srslte_b200_enc_t
+    _fields_ = [("data", C.c_void_p), ("tbs", C.c_uint32), ("Qm", C.c_uint32), ("rv", C.c_uint32), ("nof_e_bits", C.c_uint32),
+                ("e_bits", C.c_void_p), ("ret", C.c_int32)]
+
+
 class Demod(C.Structure):  # srslte_b200_demod_t
     _fields_ = [("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("scramble_bytes", C.c_void_p), ("e_bits", C.c_void_p)]
 
@@ -96,6 +101,7 @@ def lib():
         L.srslte_b200_demod_descramble.argtypes = [C.c_void_p, C.POINTER(Demod), C.c_uint32, C.c_int, C.c_uint32]
         L.srslte_b200_sequence_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.srslte_b200_sequence_bytes.restype = None
+        L.srslte_b200_encode_tbs.argtypes = [C.c_void_p, C.POINTER(Enc), C.c_uint32, C.c_uint32]
         L.srslte_b200_softbuffer_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]
         L.srslte_b200_softbuffer_reset.argtypes = [C.c_void_p]
         L.srslte_b200_softbuffer_free.argtypes = [C.c_void_p]
@@ -133,6 +139,10 @@ def sequence_bytes(c_init, length):
 
 def make_demods(n):
     return (Demod * n)()
+
+
+def make_encs(n):
+    return (Enc * n)()
 
 
 def _err(what, rc):
@@ -222,6 +232,28 @@ class Context:
         if rc:
             _err("srslte_b200_demod_descramble", rc)
         return outs
+
+    # ---- transmit mirror (srslte_dlsch_encode2 semantics, stateless)
+    def encode_tbs(self, blocks):
+        """blocks: list of (payload bytes uint8[tbs/8], tbs, Qm, rv, G).  Returns (list of packed e-bit arrays, list of ret)."""
+        n = len(blocks)
+        arr = (Enc * n)()
+        keep, outs = [], []
+        for i, (data, tbs, Qm, rv, G) in enumerate(blocks):
+            data = np.ascontiguousarray(data, np.uint8)
+            out = np.zeros((G + 31) // 32 * 4, np.uint8)
+            keep.append(data)
+            outs.append(out)
+            arr[i].data, arr[i].tbs, arr[i].Qm, arr[i].rv, arr[i].nof_e_bits, arr[i].e_bits = data.ctypes.data, tbs, Qm, rv, G, out.ctypes.data
+        rc = lib().srslte_b200_encode_tbs(self.h, arr, n, 0)
+        if rc:
+            _err("srslte_b200_encode_tbs", rc)
+        return [o[:(blocks[i][4] + 7) // 8] for i, o in enumerate(outs)], [arr[i].ret for i in range(n)]
+
+    def encode_tbs_raw(self, arr, flags):
+        rc = lib().srslte_b200_encode_tbs(self.h, arr, len(arr), flags)
+        if rc:
+            _err("srslte_b200_encode_tbs", rc)
 
     def demod_descramble_raw(self, arr, is8, flags):
         """arr: ctypes array of Demod with caller-managed (host or device) pointers"""

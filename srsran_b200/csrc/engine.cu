@@ -205,6 +205,7 @@ Engine::~Engine()
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
   d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); h_dm_desc.release(); h_dm_out.release();
+  d_enc_in.release(); d_enc_out.release(); d_enc_desc.release(); h_enc_desc.release(); h_enc_out.release();
   if (stream)
     cudaStreamDestroy(stream);
   delete plan_ptr;
@@ -1160,6 +1161,141 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- transmit mirror
+int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
+{
+  if (!tbs && nof_tb) {
+    set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  if (nof_tb == 0)
+    return 0;
+  CUDA_OK(cudaSetDevice(device));
+  const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
+  auto       al16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  std::vector<EncTbDev> htb;
+  std::vector<EncCbDev> hcb;
+  std::vector<int>      map(nof_tb, -1);
+  std::vector<size_t>   out_offs(nof_tb, 0);
+  size_t                in_bytes = 0, out_bytes = 0;
+  // pass 1: validate + segment (encode_tb_off: sch.c:247-266), size the staging areas
+  std::vector<CbSegm> segs(nof_tb);
+  for (uint32_t i = 0; i < nof_tb; i++) {
+    srslte_b200_enc_t& u = tbs[i];
+    u.ret = SRSLTE_B200_ERROR_INVALID_INPUTS;
+    if (!u.data || !u.e_bits || u.Qm == 0 || u.rv > 3 || u.tbs == 0 || u.tbs % 8 || u.nof_e_bits < u.Qm)
+      continue;
+    if (cb_segm(&segs[i], u.tbs) || segs[i].F || segs[i].C == 0 || segs[i].C > SRSLTE_B200_MAX_CODEBLOCKS) {
+      u.ret = SRSLTE_B200_ERROR;
+      continue;
+    }
+    map[i] = 0;
+    in_bytes += al16(u.tbs / 8);
+    out_bytes += al16(((size_t)u.nof_e_bits + 31) / 32 * 4);
+  }
+  if ((!in_dev && d_enc_in.reserve(in_bytes + 64)) || (!out_dev && (d_enc_out.reserve(out_bytes + 64) || h_enc_out.reserve(out_bytes + 64))))
+    return SRSLTE_B200_ERROR;
+  // pass 2: descriptors, uploads
+  size_t         in_off = 0, out_off = 0;
+  const uint8_t* cp_src = nullptr;
+  size_t         cp_dst = 0, cp_bytes = 0;
+  for (uint32_t i = 0; i < nof_tb; i++) {
+    if (map[i] < 0)
+      continue;
+    srslte_b200_enc_t& u = tbs[i];
+    const CbSegm&      s = segs[i];
+    EncTbDev           t;
+    memset(&t, 0, sizeof(t));
+    t.tbs = u.tbs;
+    crc24_xpows(u.tbs / 8, kCrc24A, t.crc_xp);
+    if (in_dev) {
+      t.data = u.data;
+    } else {
+      const size_t nb = u.tbs / 8;
+      if (cp_bytes && u.data == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
+        cp_bytes += nb;
+      } else {
+        if (cp_bytes)
+          CUDA_OK(cudaMemcpyAsync(d_enc_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+        cp_src   = u.data;
+        cp_dst   = in_off;
+        cp_bytes = nb;
+      }
+      t.data = d_enc_in.ptr + in_off;
+      in_off += nb;
+      if (nb % 16)
+        in_off = al16(in_off);
+    }
+    const size_t ob = ((size_t)u.nof_e_bits + 31) / 32 * 4;
+    if (out_dev) {
+      t.e_words = (uint32_t*)u.e_bits;
+      CUDA_OK(cudaMemsetAsync(u.e_bits, 0, ob, stream));
+    } else {
+      t.e_words   = (uint32_t*)(d_enc_out.ptr + out_off);
+      out_offs[i] = out_off;
+      out_off += al16(ob);
+    }
+    map[i] = (int)htb.size();
+    const uint32_t Gp = u.nof_e_bits / u.Qm, gamma = Gp % s.C;
+    uint32_t       rp = 0, wp = 0;
+    for (uint32_t c = 0; c < s.C; c++) {
+      const uint32_t K    = c < s.C2 ? s.K2 : s.K1; // the transmitter's order (sch.c:277-283)
+      const uint32_t rlen = s.C > 1 ? K - 24 : K;
+      const uint32_t n_e  = (c + gamma + 1 <= s.C) ? u.Qm * (Gp / s.C) : u.Qm * ((Gp + s.C - 1) / s.C); // sch.c:289-293
+      const int      ci   = cb_index(K);
+      EncCbDev       d;
+      memset(&d, 0, sizeof(d));
+      d.tb       = (uint32_t)htb.size();
+      d.K        = K;
+      d.rp_bytes = rp / 8;
+      d.last     = c + 1 == s.C;
+      d.nd_bytes = d.last ? rlen / 8 - 3 : rlen / 8;
+      d.cb_crc   = s.C > 1;
+      d.E        = n_e;
+      d.wp       = wp;
+      d.qpp_off  = qpp_off[0][ci];
+      d.rm_off   = rm_off[0][ci];
+      d.rm_start = rm_start[0][ci][u.rv];
+      if (d.cb_crc)
+        crc24_xpows(K / 8 - 3, kCrc24B, d.crc_xp);
+      hcb.push_back(d);
+      rp += rlen;
+      wp += n_e;
+    }
+    htb.push_back(t);
+  }
+  if (cp_bytes)
+    CUDA_OK(cudaMemcpyAsync(d_enc_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+  if (!htb.empty()) {
+    const size_t tb_b = htb.size() * sizeof(EncTbDev), cb_b = hcb.size() * sizeof(EncCbDev), cb_at = al16(tb_b);
+    if (d_enc_desc.reserve(cb_at + cb_b + 64) || h_enc_desc.reserve(cb_at + cb_b + 64))
+      return SRSLTE_B200_ERROR;
+    memcpy(h_enc_desc.ptr, htb.data(), tb_b);
+    memcpy(h_enc_desc.ptr + cb_at, hcb.data(), cb_b);
+    CUDA_OK(cudaMemcpyAsync(d_enc_desc.ptr, h_enc_desc.ptr, cb_at + cb_b, cudaMemcpyHostToDevice, stream));
+    if (!out_dev)
+      CUDA_OK(cudaMemsetAsync(d_enc_out.ptr, 0, out_off, stream));
+    EncTbDev* dtb = (EncTbDev*)d_enc_desc.ptr;
+    EncCbDev* dcb = (EncCbDev*)(d_enc_desc.ptr + cb_at);
+    k_enc_tb_crc<<<((int)htb.size() + 3) / 4, 128, 0, stream>>>(dtb, (int)htb.size());
+    const size_t smem = 768 + kMaxK + 3 * kMaxK + 12 + 16;
+    k_enc_cb<<<(int)hcb.size(), 256, smem, stream>>>(dcb, dtb, d_qpp.ptr, d_rm.ptr);
+    CUDA_OK(cudaGetLastError());
+    last_launches += 2;
+  }
+  for (uint32_t i = 0; i < nof_tb; i++)
+    if (map[i] >= 0)
+      tbs[i].ret = 0;
+  if (out_dev || htb.empty())
+    return 0; // stream-ordered with whatever is submitted next on this context
+  CUDA_OK(cudaMemcpyAsync(h_enc_out.ptr, d_enc_out.ptr, out_off, cudaMemcpyDeviceToHost, stream));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  for (uint32_t i = 0; i < nof_tb; i++)
+    if (map[i] >= 0)
+      memcpy(tbs[i].e_bits, h_enc_out.ptr + out_offs[i], ((size_t)tbs[i].nof_e_bits + 7) / 8);
+  return 0;
+}
+
 // TS 36.211 7.2: c(n) = x1(n + 1600) ^ x2(n + 1600), x1(n+31) = x1(n+3) ^ x1(n), x2(n+31) = x2(n+3) ^ x2(n+2) ^ x2(n+1) ^ x2(n)
 // (srslte_sequence_LTE_pr, lib/src/phy/common/sequence.c); bit-serial on two 31-bit registers
 void lte_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out)
@@ -1372,6 +1508,12 @@ int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const srslte_b200_demod
   if (!ctx)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   return ctx->e->demod_descramble(cws, nof_cw, llr_is_8bit, flags);
+}
+int srslte_b200_encode_tbs(srslte_b200_ctx_t* ctx, srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->encode_tbs(tbs, nof_tb, flags);
 }
 void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out) { b200::lte_sequence_bytes(c_init, len, out); }
 

@@ -57,6 +57,7 @@ public:
 
   int softbuffer_create(Softbuffer** out, uint32_t max_cb);
   int demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, int is8, uint32_t flags);
+  int encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags);
   // host-pointer compatibility operations behind the drop-in srslte_* symbols (api.inc)
   int tdec_step(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, const void* input, uint32_t n_done, uint32_t n_more,
                 uint8_t* out);
@@ -100,6 +101,8 @@ public:
   DevBuf<uint8_t>  d_tmaps;
   DevBuf<uint8_t>  d_dm_in, d_dm_out, d_dm_desc; // soft-demodulation front end: staged symbols + sequences, LLRs, descriptors
   PinBuf<uint8_t>  h_dm_desc, h_dm_out;
+  DevBuf<uint8_t>  d_enc_in, d_enc_out, d_enc_desc; // transmit mirror: payloads, packed e-bits, descriptors
+  PinBuf<uint8_t>  h_enc_desc, h_enc_out;
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
 

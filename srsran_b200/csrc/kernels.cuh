@@ -77,7 +77,8 @@ struct TbResult {
 // Planes of a code block's workspace (plane stride d.ps int16 each).  The order keeps the inputs of each constituent
 // decoder adjacent so one TMA box covers them: DEC1 reads {syst, par0, apr}, DEC2 reads {app2, par1}.
 constexpr int kPlSyst = 0, kPlPar0 = 1, kPlApr = 2, kPlApp2 = 3, kPlPar1 = 4, kPlPost = 5;
-constexpr uint32_t kSbPadDev = 32; // plane padding of the lane layout (rm_turbo.c:272)
+constexpr uint32_t kSbPadDev = 32;
+constexpr uint32_t kMaxKDev  = 6144; // plane padding of the lane layout (rm_turbo.c:272)
 
 __constant__ uint32_t c_crc_tab[2][256]; // [0] = CRC24A, [1] = CRC24B byte tables (crc.c:30-46)
 
@@ -1397,6 +1398,155 @@ __global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uin
   const uint32_t c = warp_crc24(nbytes, s_tab[tab], poly, xp.v, [&](uint32_t b) -> uint32_t { return data[b]; });
   if (threadIdx.x == 0)
     *out = c;
+}
+
+// ------------------------------------------------------------------------------------------ transmit mirror
+// encode_tb_off (phch/sch.c:235-349) = TB CRC24A, segmentation, CB CRC24B, srslte_tcod_encode_lut (fec/turbocoder.c:190-372)
+// and srslte_rm_turbo_tx_lut (fec/rm_turbo.c:349-395), for many transport blocks at once.
+struct EncTbDev {
+  const uint8_t* data;    // tbs/8 payload bytes
+  uint32_t*      e_words; // packed e-bits of the TB (first bit = MSB of byte 0), zero-filled before the launch, 4-byte aligned
+  uint32_t       tbs;
+  uint32_t       crc;     // CRC24A of the payload, written by k_enc_tb_crc
+  uint32_t       crc_xp[5];
+};
+struct EncCbDev {
+  uint32_t tb;        // owning transport block
+  uint32_t K;
+  uint32_t rp_bytes;  // offset of this block's payload in the TB
+  uint32_t nd_bytes;  // payload bytes taken from the TB data
+  uint32_t last;      // last block of the TB: the 3 TB CRC bytes follow the payload
+  uint32_t cb_crc;    // C > 1: CRC24B over payload (+ TB CRC) is appended
+  uint32_t E;         // rate-matched bits of this block
+  uint32_t wp;        // bit offset of this block in the TB's e-bit stream
+  uint32_t qpp_off;   // natural-order QPP table fwd[K] in the QPP pool
+  uint32_t rm_off;    // base rate-matching table (standard layout) in the rm pool
+  uint32_t rm_start;  // rank of the first transmitted entry for this rv
+  uint32_t crc_xp[5]; // CRC24B combination constants for (K - 24) / 8 bytes
+};
+
+__global__ void __launch_bounds__(128) k_enc_tb_crc(EncTbDev* __restrict__ tbs, int n_tb)
+{
+  __shared__ uint32_t s_tab[2][256];
+  load_crc_tables(s_tab);
+  __syncthreads();
+  const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
+  if (w >= n_tb)
+    return;
+  const EncTbDev t = tbs[w];
+  const uint32_t c = warp_crc24(t.tbs / 8, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return t.data[b]; });
+  if ((threadIdx.x & 31) == 0)
+    tbs[w].crc = c;
+}
+
+// recursive systematic convolutional encoder g0 = 1 + D^2 + D^3 (feedback), g1 = 1 + D + D^3: one step on the packed
+// state (bit 0 = newest register).  Returns the parity bit.
+__device__ __forceinline__ uint32_t rsc_step(uint32_t& st, uint32_t u)
+{
+  const uint32_t s0 = st & 1u, s1 = (st >> 1) & 1u, s2 = (st >> 2) & 1u;
+  const uint32_t fb = u ^ s1 ^ s2;
+  st                = ((st << 1) & 6u) | fb;
+  return fb ^ s0 ^ s2;
+}
+
+// One CTA per code block.  The two constituent encoders run chunk-parallel: every thread first encodes its chunk from the
+// zero state, the chunk start states follow from a 256-step scan with the (linear) zero-input transition of one chunk
+// length, then every thread encodes its chunk again from its true start state.
+__global__ void __launch_bounds__(256) k_enc_cb(const EncCbDev* __restrict__ cbs, const EncTbDev* __restrict__ tbs, const uint16_t* __restrict__ qpp,
+                                                const uint16_t* __restrict__ rm_pool)
+{
+  extern __shared__ __align__(16) uint8_t s_enc[];
+  __shared__ uint32_t s_tab[2][256];
+  __shared__ uint8_t  s_end[2][256], s_start[2][256], s_zi[8];
+  const EncCbDev d  = cbs[blockIdx.x];
+  const EncTbDev t  = tbs[d.tb];
+  const uint32_t K = d.K, nb = K / 8;
+  uint8_t*       bytes = s_enc;                      // K/8 block bytes (payload [+ TB CRC] [+ CB CRC])
+  uint8_t*       c     = s_enc + 768;                // K bits
+  uint8_t*       buf   = c + kMaxKDev;               // 3K + 12 coded bits in the decoder's input order
+  const int      tid = threadIdx.x;
+  load_crc_tables(s_tab);
+  for (uint32_t i = tid; i < d.nd_bytes; i += 256)
+    bytes[i] = t.data[d.rp_bytes + i];
+  if (d.last && tid < 3)
+    bytes[d.nd_bytes + tid] = (uint8_t)(t.crc >> (16 - 8 * tid));
+  __syncthreads();
+  if (d.cb_crc && tid < 32) {
+    const uint32_t crc = warp_crc24(nb - 3, s_tab[1], kCrc24B, d.crc_xp, [&](uint32_t b) -> uint32_t { return bytes[b]; });
+    if (tid < 3)
+      bytes[nb - 3 + tid] = (uint8_t)(crc >> (16 - 8 * tid));
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < K; i += 256)
+    c[i] = (bytes[i >> 3] >> (7 - (i & 7))) & 1u;
+  // zero-input transition of one chunk length
+  const uint32_t L = (K + 255) / 256, nc = (K + L - 1) / L;
+  if (tid < 8) {
+    uint32_t st = tid;
+    for (uint32_t i = 0; i < L; i++)
+      rsc_step(st, 0);
+    s_zi[tid] = (uint8_t)st;
+  }
+  __syncthreads();
+  const uint16_t* fwd = qpp + d.qpp_off;
+  const uint32_t  lo = tid * L, hi = min(K, lo + L);
+  // pass 1: chunk end states from the zero state (encoder 0: natural order, encoder 1: interleaved order)
+  if ((uint32_t)tid < nc) {
+    uint32_t s0 = 0, s1 = 0;
+    for (uint32_t i = lo; i < hi; i++) {
+      rsc_step(s0, c[i]);
+      rsc_step(s1, c[fwd[i]]);
+    }
+    s_end[0][tid] = (uint8_t)s0;
+    s_end[1][tid] = (uint8_t)s1;
+  }
+  __syncthreads();
+  if (tid == 0 || tid == 32) {
+    const int e  = tid >> 5;
+    uint32_t  st = 0;
+    for (uint32_t k = 0; k < nc; k++) {
+      s_start[e][k] = (uint8_t)st;
+      st            = s_zi[st] ^ s_end[e][k]; // linear: response to the start state + response to the input
+    }
+  }
+  __syncthreads();
+  // pass 2: parity bits; the last chunk continues into the trellis termination
+  if ((uint32_t)tid < nc) {
+    uint32_t s0 = s_start[0][tid], s1 = s_start[1][tid];
+    for (uint32_t i = lo; i < hi; i++) {
+      buf[3 * i]     = c[i];
+      buf[3 * i + 1] = (uint8_t)rsc_step(s0, c[i]);
+      buf[3 * i + 2] = (uint8_t)rsc_step(s1, c[fwd[i]]);
+    }
+    if ((uint32_t)tid == nc - 1) {
+      // tail: the input that drives the feedback to zero, and its parity; x z x z x z | x' z' x' z' x' z'
+      for (int k = 0; k < 3; k++) {
+        const uint32_t x0 = ((s0 >> 1) ^ (s0 >> 2)) & 1u, x1 = ((s1 >> 1) ^ (s1 >> 2)) & 1u;
+        buf[3 * K + 2 * k]         = (uint8_t)x0;
+        buf[3 * K + 2 * k + 1]     = (uint8_t)rsc_step(s0, x0);
+        buf[3 * K + 6 + 2 * k]     = (uint8_t)x1;
+        buf[3 * K + 6 + 2 * k + 1] = (uint8_t)rsc_step(s1, x1);
+      }
+    }
+  }
+  __syncthreads();
+  // rate matching (gather through the same table the receiver scatters with) + packing into the TB's e-bit words
+  const uint16_t* tab = rm_pool + d.rm_off;
+  const uint32_t  Lr = 3 * K + 12, w0 = d.wp >> 5, w1 = (d.wp + d.E + 31) >> 5;
+  for (uint32_t w = w0 + tid; w < w1; w += 256) {
+    uint32_t word = 0;
+    const uint32_t b_lo = max(w << 5, d.wp), b_hi = min((w + 1) << 5, d.wp + d.E);
+    uint32_t       pos = (b_lo - d.wp + d.rm_start) % Lr;
+    for (uint32_t bb = b_lo; bb < b_hi; bb++) {
+      const uint32_t bit = buf[tab[pos]];
+      pos                = pos + 1 == Lr ? 0 : pos + 1;
+      word |= bit << (8 * ((bb & 31) >> 3) + 7 - (bb & 7)); // first bit of the stream = MSB of byte 0
+    }
+    if (b_lo == (w << 5) && b_hi == ((w + 1) << 5))
+      t.e_words[w] = word; // interior word: owned by this block
+    else
+      atomicOr(&t.e_words[w], word); // shared with the neighbouring block
+  }
 }
 
 // ------------------------------------------------------------------------------------------ ALU roofline probe
