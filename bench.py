@@ -551,6 +551,26 @@ def run_ours(args):
         for p_ in (d_sym, d_scr, d_e):
             ctx.device_free(p_)
 
+        # ---- transmit mirror of the same transport blocks: payload bytes -> packed e-bits, device-resident
+        pay = rng.integers(0, 256, (ntb, tbs // 8), dtype=np.uint8)
+        ew = (G + 31) // 32 * 4
+        d_pay = ctx.device_alloc(pay.nbytes)
+        d_eb = ctx.device_alloc(ntb * ew)
+        ctx.h2d(d_pay, pay)
+        en = b.make_encs(ntb)
+        for i in range(ntb):
+            en[i].data, en[i].tbs, en[i].Qm, en[i].rv, en[i].nof_e_bits, en[i].e_bits = d_pay + i * (tbs // 8), tbs, Qm, 0, G, d_eb + i * ew
+        for _ in range(3):
+            ctx.encode_tbs_raw(en, b.IN_DEVICE | b.OUT_DEVICE)
+        ctx.timer_start()
+        for _ in range(reps):
+            ctx.encode_tbs_raw(en, b.IN_DEVICE | b.OUT_DEVICE)
+        tx_ms = ctx.timer_stop_ms() / reps
+        extra["tx_mirror"] = {"kernel": "k_enc_tb_crc + k_enc_cb", "what": "%d transport blocks of %d bits -> %d e-bits each, device-resident" % (ntb, tbs, G),
+                              "ms": tx_ms, "encoded_mbps": ntb * tbs / (tx_ms * 1e-3) / 1e6}
+        ctx.device_free(d_pay)
+        ctx.device_free(d_eb)
+
     # ---- roofline of the dominant kernel (k_map_win): integer-ALU issue bound.  The kernel is timed on its own here
     #      (one engine, batches back to back, CUDA events around every launch on the launching stream).
     rsteps = max(1, min(5, args.steps))

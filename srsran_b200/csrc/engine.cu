@@ -1206,7 +1206,8 @@ int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
     const CbSegm&      s = segs[i];
     EncTbDev           t;
     memset(&t, 0, sizeof(t));
-    t.tbs = u.tbs;
+    t.tbs     = u.tbs;
+    t.n_words = (u.nof_e_bits + 31) / 32;
     crc24_xpows(u.tbs / 8, kCrc24A, t.crc_xp);
     if (in_dev) {
       t.data = u.data;
@@ -1229,7 +1230,6 @@ int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
     const size_t ob = ((size_t)u.nof_e_bits + 31) / 32 * 4;
     if (out_dev) {
       t.e_words = (uint32_t*)u.e_bits;
-      CUDA_OK(cudaMemsetAsync(u.e_bits, 0, ob, stream));
     } else {
       t.e_words   = (uint32_t*)(d_enc_out.ptr + out_off);
       out_offs[i] = out_off;
@@ -1273,8 +1273,6 @@ int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
     memcpy(h_enc_desc.ptr, htb.data(), tb_b);
     memcpy(h_enc_desc.ptr + cb_at, hcb.data(), cb_b);
     CUDA_OK(cudaMemcpyAsync(d_enc_desc.ptr, h_enc_desc.ptr, cb_at + cb_b, cudaMemcpyHostToDevice, stream));
-    if (!out_dev)
-      CUDA_OK(cudaMemsetAsync(d_enc_out.ptr, 0, out_off, stream));
     EncTbDev* dtb = (EncTbDev*)d_enc_desc.ptr;
     EncCbDev* dcb = (EncCbDev*)(d_enc_desc.ptr + cb_at);
     k_enc_tb_crc<<<((int)htb.size() + 3) / 4, 128, 0, stream>>>(dtb, (int)htb.size());

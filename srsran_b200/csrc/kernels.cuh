@@ -1405,7 +1405,8 @@ __global__ void k_crc24_bytes(const uint8_t* data, uint32_t nbytes, int tab, uin
 // and srslte_rm_turbo_tx_lut (fec/rm_turbo.c:349-395), for many transport blocks at once.
 struct EncTbDev {
   const uint8_t* data;    // tbs/8 payload bytes
-  uint32_t*      e_words; // packed e-bits of the TB (first bit = MSB of byte 0), zero-filled before the launch, 4-byte aligned
+  uint32_t*      e_words; // packed e-bits of the TB (first bit = MSB of byte 0), 4-byte aligned; zero-filled by k_enc_tb_crc
+  uint32_t       n_words; // (nof_e_bits + 31) / 32
   uint32_t       tbs;
   uint32_t       crc;     // CRC24A of the payload, written by k_enc_tb_crc
   uint32_t       crc_xp[5];
@@ -1437,6 +1438,8 @@ __global__ void __launch_bounds__(128) k_enc_tb_crc(EncTbDev* __restrict__ tbs, 
   const uint32_t c = warp_crc24(t.tbs / 8, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return t.data[b]; });
   if ((threadIdx.x & 31) == 0)
     tbs[w].crc = c;
+  for (uint32_t i = threadIdx.x & 31; i < t.n_words; i += 32) // code blocks OR their boundary words into place
+    t.e_words[i] = 0;
 }
 
 // recursive systematic convolutional encoder g0 = 1 + D^2 + D^3 (feedback), g1 = 1 + D + D^3: one step on the packed
