@@ -1,6 +1,6 @@
 """One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
 k_prepare, k_map_f16 (Fast16 and Sat8, the three decoder modes), k_map_win<Sat16> (exact path), k_map_gen, k_decide_crc,
-k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8)."""
+k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8), k_enc_tb_crc, k_enc_cb."""
 import os
 import sys
 
@@ -60,5 +60,15 @@ for dt, mod in ((np.int16, 3), (np.int8, 4)):
     for i in range(n):
         dm[i].symbols, dm[i].nof_symbols, dm[i].mod, dm[i].scramble_bytes, dm[i].e_bits = d_sym + i * nsym * 8, nsym, mod, d_scr, d_e + i * nsym * Qm * np.dtype(dt).itemsize
     ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
+# transmit mirror: k_enc_tb_crc, k_enc_cb
+ntb, tbs, Qm, G = 364, 75376, 6, 90000
+pay = rng.integers(0, 256, (ntb, tbs // 8), dtype=np.uint8)
+ew = (G + 31) // 32 * 4
+d_pay, d_eb = ctx.device_alloc(pay.nbytes), ctx.device_alloc(ntb * ew)
+ctx.h2d(d_pay, pay)
+en = b.make_encs(ntb)
+for i in range(ntb):
+    en[i].data, en[i].tbs, en[i].Qm, en[i].rv, en[i].nof_e_bits, en[i].e_bits = d_pay + i * (tbs // 8), tbs, Qm, 0, G, d_eb + i * ew
+ctx.encode_tbs_raw(en, b.IN_DEVICE | b.OUT_DEVICE)
 ctx.wait()
 print("done")
