@@ -37,7 +37,7 @@ W16_OPS = 82.0   # algorithmic int16 lane-ops per trellis step per half-iteratio
 W8_OPS = 106.0
 # DRAM traffic of the dominant kernel per code block and launch (dram__bytes_read.sum + dram__bytes_write.sum of one
 # `ncu --set full` capture divided by the code blocks of that launch; see profiles/README.md for the capture)
-MAP_TRAFFIC_PER_CB = {"c1": {"bytes_per_cb": 102.5e3, "source": "profiles/r01_k_map_f16.metrics.txt: mean over the 4 half-iteration launches (DEC1 first 95.4, DEC2 96.0, DEC1 122.7 KB per code block)"}}
+MAP_TRAFFIC_PER_CB = {"c1": {"bytes_per_cb": 92.1e3, "source": "profiles/r01_k_map_f16.metrics.txt: mean over the 4 half-iteration launches of a batch (DEC1 first 82.2, DEC2 82.3, DEC1 109.4 KB per code block without the a-posteriori plane; the last DEC2 writes it: 94.3)"}}
 
 
 def load_peaks():
