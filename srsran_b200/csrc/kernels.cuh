@@ -1,13 +1,16 @@
 // Device kernels of the B200 LTE turbo-decode engine (sm_100a).  Included by engine.cu only.
 //
-//   k_dematch      srslte_rm_turbo_rx_lut[_8bit]          (rm_turbo.c:397-493)        HARQ combine + scatter
-//   k_prepare      extract_input / extract_input_tail_sb  (win.h:880-923, iter.h:59-69, gen.c:238-258)
-//   k_map_win      tdec_win*_dec + half-iteration glue    (win.h:551-868, iter.h:104-128)
-//   k_map_gen      tdec_gen_dec + glue                    (turbodecoder_gen.c:58-236)
-//   k_decide_crc   tdec_*_decision_byte + srslte_crc_checksum_byte + early stop (win.h:925-993, crc.c:143-157,
-//                  sch.c:420-450)
-//   k_tb_finish    TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
-//   k_demod_descramble  srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset (demod_soft.c:896-945)
+//   k_dematch_prepare  srslte_rm_turbo_rx_lut[_8bit] + input extraction  (rm_turbo.c:397-493, win.h:880-923)
+//   k_dematch          srslte_rm_turbo_rx_lut[_8bit] for the host-pointer compatibility symbol
+//   k_prepare          extract_input / extract_input_tail_sb  (win.h:880-923, iter.h:59-69, gen.c:238-258)
+//   k_map_f16          tdec_win*_dec + half-iteration glue, int16 (Fast16) and int8 (Sat8)  -> map_f16.cuh
+//   k_map_win          the same in exact saturating int16 (replay of blocks the Fast16 range monitor flags; fast16 off)
+//   k_map_gen          tdec_gen_dec + glue                    (turbodecoder_gen.c:58-236)
+//   k_decide_crc       tdec_*_decision_byte + srslte_crc_checksum_byte + early stop (win.h:925-993, crc.c:143-157,
+//                      sch.c:420-450)
+//   k_tb_finish        TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
+//   k_demod_descramble srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset (demod_soft.c:896-945)
+//   k_enc_tb_crc, k_enc_cb  encode_tb_off: CRC, turbo code, rate matching (sch.c:235-349, turbocoder.c, rm_turbo.c:349-395)
 #pragma once
 #include <cuda.h> // CUtensorMap (type only: the encoder is reached through cudaGetDriverEntryPoint)
 #include <cuda_runtime.h>

@@ -537,3 +537,20 @@ def test_encode_decode_round_trip_on_device(port, ctx):
     t[0].e_bits, t[0].nof_e_bits, t[0].tbs, t[0].Qm, t[0].rv, t[0].data = llr.ctypes.data, G, tbs, Qm, 0, o.ctypes.data
     ctx.decode_tbs(t, False, 4)
     assert t[0].ret == 0 and (o[:tbs // 8] == data).all()
+
+
+def test_front_end_and_encoder_reject_invalid_descriptors(ctx):
+    sym = np.zeros(16, np.complex64)
+    out = np.zeros(128, np.int16)
+    dm = b.make_demods(1)
+    dm[0].symbols, dm[0].nof_symbols, dm[0].mod, dm[0].scramble_bytes, dm[0].e_bits = sym.ctypes.data, 16, 7, None, out.ctypes.data
+    with pytest.raises(b.B200Error):
+        ctx.demod_descramble_raw(dm, False, 0)  # unknown modulation
+    dm[0].mod, dm[0].nof_symbols = 2, 0
+    with pytest.raises(b.B200Error):
+        ctx.demod_descramble_raw(dm, False, 0)  # empty codeword
+    # encoder: per-block return codes, the batch itself succeeds
+    data = np.zeros(1000 // 8, np.uint8)
+    _, rets = ctx.encode_tbs([(data, 1000, 2, 5, 2880), (data, 1000, 0, 0, 2880), (data, 1000, 2, 0, 2880)])
+    assert rets == [-2, -2, 0]
+    assert ctx.encode_tbs([]) == ([], [])
