@@ -646,10 +646,14 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-TTI latency loop (keeps profiler launch lists short)")
-    ap.add_argument("--engines", type=int, default=4, help="engines (streams) per GPU the batches / end-to-end chunks rotate over")
+    ap.add_argument("--engines", type=int, default=0,
+                    help="engines (streams) per GPU the batches / end-to-end chunks rotate over (default: 4 for c1, 6 for the early-stop workloads "
+                         "whose last half-iterations run nearly empty and overlap with other batches)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks one end-to-end step is split into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.engines <= 0:
+        args.engines = 4 if args.workload == "c1" else 6
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
