@@ -389,6 +389,30 @@ def test_fast16_amplitude_sweep(port, ctx):
             assert (got == want[None, :]).all(), (K, amp)
 
 
+def test_fast16_all_window_sizes_across_the_monitor_boundary(port, ctx):
+    """every windowed int16 size (partial top tiles for W % 8 != 0, 8- and 16-lane decoders), three amplitudes -- far
+    below, around and far above the range monitor's decision boundary, so that blocks of one batch take the fast path,
+    the exact replay, or both in different half-iterations -- random (non-codeword) LLRs, 5 half-iterations"""
+    rng = np.random.default_rng(1919)
+    replayed = clean = 0
+    for K in all_K():
+        N = lanes16(K)
+        if N == 0:
+            continue
+        for amp in (60, 900, 6000):
+            batch = np.stack([random_llr(rng, 3 * K + 12, amp, np.int16) for _ in range(3)])
+            got = ctx.tdec_batch(batch, K, 5, input_sb=False)
+            rep = ctx.last_replayed()
+            replayed += rep > 0
+            clean += rep == 0
+            hp = port.tdec_new(TDEC_AUTO, True)
+            for i in range(3):
+                rc, want = port.tdec_run_all(hp, batch[i], 5, K)
+                assert rc == 0 and (got[i] == want).all(), (K, amp, i, rep)
+            port.tdec_del(hp)
+    assert replayed > 50 and clean > 50
+
+
 def test_exact_path_full_suite_sample(port, ctx):
     """the exact-arithmetic kernels alone (fast16 = 0) on the transport-block path"""
     rng = np.random.default_rng(1818)
