@@ -616,7 +616,9 @@ int Engine::run(Plan& p)
         map_geometry<16>(cls[c].n_slots, &nt, &blocks);
       else
         map_geometry<32>(cls[c].n_slots, &nt, &blocks);
-      const size_t slots = (size_t)(cls[c].max_w + 3) / 4 + 1; // sized for the shortest segment length in use
+      // one 8-word checkpoint per thread and 8-step tile (+ the start state); both kernels round their thread count up to
+      // whole CTAs (128 threads for k_map_f16, 256 for k_map_win)
+      const size_t slots = (size_t)(cls[c].max_w + 7) / 8 + 2;
       need = std::max(need, slots * ((size_t)blocks * nt + 256) * 8);
     }
     if (need && d_ckscratch.reserve(need))
