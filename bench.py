@@ -551,6 +551,36 @@ def run_ours(args):
         for p_ in (d_sym, d_scr, d_e):
             ctx.device_free(p_)
 
+        # ---- PUSCH pre-steps: a 100-PRB 64QAM uplink subframe per transport block -- ACK / RI / CQI LLR
+        #      extraction + channel de-interleaving (k_ulsch_deinterleave, HBM-bound), device-resident, CUDA-event timed
+        if dt == np.int16:
+            ul_rows, ul_cols, ul_Qm, ul_q = 1200, 12, 6, (36, 20, 57)
+            ul_n = ul_rows * ul_cols * ul_Qm
+            qll = rng.integers(-2000, 2000, (min(ntb, 256), ul_n)).astype(np.int16)
+            d_ulq = ctx.device_alloc(ntb * ul_n * 2)
+            d_ulg = ctx.device_alloc(ntb * ul_n * 2)
+            for i in range(0, ntb, len(qll)):
+                k = min(len(qll), ntb - i)
+                ctx.h2d(d_ulq + i * ul_n * 2, qll[:k])
+            ul = b.make_ulschs(ntb)
+            for i in range(ntb):
+                ul[i].q_bits, ul[i].Qm, ul[i].H_prime_total, ul[i].N_pusch_symbs, ul[i].g_bits = d_ulq + i * ul_n * 2, ul_Qm, ul_rows * ul_cols, ul_cols, d_ulg + i * ul_n * 2
+                ul[i].Q_prime_ack, ul[i].Q_prime_ri, ul[i].Q_prime_cqi = ul_q
+            for _ in range(3):
+                ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
+            ctx.timer_start()
+            for _ in range(10):
+                ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
+            ul_ms = ctx.timer_stop_ms() / 10
+            ul_bytes = ntb * (2 * ul_n * 2 - ul_q[1] * ul_Qm * 2)
+            extra["ul_pre"] = {"kernel": "k_ulsch_deinterleave", "what": "%d subframes x %d x %d symbols, 64QAM, Q'(ack, ri, cqi) = %s, device-resident" % (
+                                   ntb, ul_rows, ul_cols, list(ul_q)),
+                               "ms": ul_ms, "gllr_per_s": ntb * ul_n / (ul_ms * 1e-3) / 1e9,
+                               "hbm": {"achieved_gbs": ul_bytes / (ul_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                                       "frac": ul_bytes / (ul_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
+            ctx.device_free(d_ulq)
+            ctx.device_free(d_ulg)
+
         # ---- transmit mirror of the same transport blocks: payload bytes -> packed e-bits, device-resident
         pay = rng.integers(0, 256, (ntb, tbs // 8), dtype=np.uint8)
         ew = (G + 31) // 32 * 4

@@ -126,6 +126,43 @@ SRSLTE_B200_API int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const s
  * lib/src/phy/common/sequence.c); out: (len + 7) / 8 bytes.  Host helper for callers that do not hold the sequence. */
 SRSLTE_B200_API void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, uint8_t* out);
 
+/* ---- PUSCH pre-steps: the data movement srslte_ulsch_decode (lib/src/phy/phch/sch.c:1105-1180) performs
+ * between the descrambler and decode_tb, batched over transport blocks:
+ *   - the LLRs at the HARQ-ACK and RI resource elements (uci_ulsch_interleave_{ack,ri}_gen, lib/src/phy/phch/uci.c:551-605)
+ *     are gathered for the host's UCI decoders, in the order srslte_uci_decode_ack_ri reads them (uci.c:843-857);
+ *   - the ACK positions are zeroed (sch.c:1067-1070) -- here on the way through, q_bits itself is left untouched;
+ *   - ulsch_deinterleave (sch.c:992-1019, table of ulsch_interleave_gen :658-679): the channel de-interleaver of
+ *     TS 36.212 5.2.2.8 with the RI positions skipped, INCLUDING the reference's side effect that, when RI is present,
+ *     g_bits[0] receives the LLR of the last RI position (every RI position is sent to index 0);
+ *   - the CQI LLRs at the front of g_bits are handed back; UL-SCH data starts at g_bits + Q_prime_cqi * Qm and holds
+ *     (H_prime_total - Q_prime_ri - Q_prime_cqi) * Qm e-bits -- the e_bits / nof_e_bits of srslte_b200_decode_tbs.
+ * The Q' values come from the reference's own host code (Q_prime_ri_ack uci.c:606-630, Q_prime_cqi uci.c:329-345); the
+ * UCI payload decoders stay there too and consume ack_llr / ri_llr / cqi_llr.
+ *   q_bits          int16[H_prime_total * Qm], 4-byte aligned when a device pointer
+ *   Qm              2, 4, 6 (8 accepted)       N_pusch_symbs  cfg->grant.nof_symb (12, 11 with SRS; 10, 9 extended CP)
+ *   g_bits          out: int16[(H_prime_total - Q_prime_ri) * Qm] written, 4-byte aligned when a device pointer
+ *   ack_llr, ri_llr, cqi_llr   HOST arrays of Q' * Qm int16 each, or NULL; when any is given the call returns after the
+ *                   stream has drained (the values are needed before the UCI decoders can run)
+ * flags: SRSLTE_B200_IN_DEVICE -> q_bits are device pointers; SRSLTE_B200_OUT_DEVICE -> g_bits are device pointers and stay
+ * stream-ordered with a following srslte_b200_decode_tbs*(..., SRSLTE_B200_IN_DEVICE) on the same context.
+ * Returns SRSLTE_B200_ERROR_INVALID_INPUTS for geometries the reference cannot index (H' not a multiple of N_pusch_symbs,
+ * more than four ACK or RI symbols per row of the interleaver matrix, UCI columns beyond N_pusch_symbs). */
+typedef struct {
+  const int16_t* q_bits;
+  uint32_t       Qm;
+  uint32_t       H_prime_total;
+  uint32_t       N_pusch_symbs;
+  uint32_t       Q_prime_ack;
+  uint32_t       Q_prime_ri;
+  uint32_t       Q_prime_cqi;
+  int16_t*       g_bits;
+  int16_t*       ack_llr;
+  int16_t*       ri_llr;
+  int16_t*       cqi_llr;
+} srslte_b200_ulsch_t;
+
+SRSLTE_B200_API int srslte_b200_ulsch_deinterleave(srslte_b200_ctx_t* ctx, const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, uint32_t flags);
+
 /* ---- transmit mirror: the batched form of srslte_dlsch_encode2 / encode_tb_off (lib/src/phy/phch/sch.c:
  * 235-349): TB CRC24A, code block segmentation, CB CRC24B, srslte_tcod_encode_lut (lib/src/phy/fec/turbocoder.c:190-372),
  * srslte_rm_turbo_tx_lut (lib/src/phy/fec/rm_turbo.c:349-395).  Stateless: retransmissions (rv != 0) are re-encoded from

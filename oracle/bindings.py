@@ -222,6 +222,35 @@ class Port:
         (self.L.orc_descramble_s if d.dtype == np.int16 else self.L.orc_descramble_b)(_p(c_bytes), _p(d), C.c_int(len(d)))
         return d
 
+    # ---- PUSCH pre-steps
+    def ulsch_qprime(self, K_segm, L_prb, nof_symb, nof_ack, ri_len, cqi_len, I_ack, I_ri, I_cqi):
+        """(Q'_ack, Q'_ri, Q'_cqi) as srslte_ulsch_decode derives them for a grant that carries UL-SCH data (sch.c:1021-1180)"""
+        L = self.L
+        L.orc_beta_offset.restype = C.c_float
+        L.orc_qprime_ri_ack.restype = C.c_uint32
+        L.orc_qprime_cqi.restype = C.c_uint32
+        u = C.c_uint32
+        beta = lambda w, i: C.c_float(L.orc_beta_offset(C.c_int(w), u(i)))
+        qa = L.orc_qprime_ri_ack(u(K_segm), u(L_prb), u(nof_symb), u(nof_ack), u(cqi_len), beta(0, I_ack)) if nof_ack else 0
+        qr = L.orc_qprime_ri_ack(u(K_segm), u(L_prb), u(nof_symb), u(ri_len), u(cqi_len), beta(1, I_ri)) if ri_len else 0
+        qc = L.orc_qprime_cqi(u(K_segm), u(L_prb), u(nof_symb), u(cqi_len), beta(2, I_cqi), u(qr)) if cqi_len else 0
+        return qa, qr, qc
+
+    def ulsch_uci_position(self, is_ri, idx, Qm, H_prime_total, N_pusch_symbs):
+        self.L.orc_ulsch_uci_position.restype = C.c_int64
+        return self.L.orc_ulsch_uci_position(C.c_int(int(is_ri)), C.c_uint32(idx), C.c_uint32(Qm), C.c_uint32(H_prime_total), C.c_uint32(N_pusch_symbs))
+
+    def ulsch_deinterleave(self, q_bits, Qm, N_pusch_symbs, Q_prime_ack, Q_prime_ri, g_fill=0):
+        """q_bits int16[H' * Qm].  Returns (rc, g_bits, ack_llr, ri_llr, q_bits after the ACK positions were zeroed)"""
+        q = _i16(q_bits).copy()
+        H = len(q) // Qm
+        g = np.full(len(q), g_fill, np.int16)
+        ack = np.zeros(max(Q_prime_ack * Qm, 1), np.int16)
+        ri = np.zeros(max(Q_prime_ri * Qm, 1), np.int16)
+        rc = self.L.orc_ulsch_deinterleave(_p(q), C.c_uint32(Qm), C.c_uint32(H), C.c_uint32(N_pusch_symbs), C.c_uint32(Q_prime_ack),
+                                           C.c_uint32(Q_prime_ri), _p(g), _p(ack), _p(ri))
+        return rc, g, ack[:Q_prime_ack * Qm], ri[:Q_prime_ri * Qm], q
+
 
 class Ref:
     """The unmodified reference (srsLTE 20.10.1) through oracle/ref_shim.c"""
@@ -385,6 +414,35 @@ class Ref:
         rc = self.L.ref_sch_get_softbuffer(s, C.c_uint32(cb), _p(d), C.c_uint32(n))
         assert rc == 0
         return d
+
+    # ---- PUSCH through the real srslte_ulsch_encode / srslte_ulsch_decode (sch.c:1105-1330)
+    @staticmethod
+    def _ul_params(tbs, Qm, L_prb, nof_symb, rv, nof_ack, ri_len, cqi, I_ack, I_ri, I_cqi):
+        return np.array([tbs, Qm, L_prb, nof_symb, rv, nof_ack, ri_len, cqi, I_ack, I_ri, I_cqi], np.uint32)
+
+    def ulsch_encode(self, s, params, uci_seed, data):
+        p = self._ul_params(*params)
+        nb_q = int(p[2]) * 12 * int(p[3]) * int(p[1])
+        d = np.zeros(int(p[0]) // 8 + 16, np.uint8)
+        d[: int(p[0]) // 8] = _u8(data)[: int(p[0]) // 8]
+        q = np.zeros(nb_q // 8 + 64, np.uint8)
+        rc = self.L.ref_ulsch_encode(s, _p(p), C.c_uint32(uci_seed), _p(d), _p(q))
+        assert rc >= 0, rc
+        return np.unpackbits(q)[:nb_q]
+
+    def ulsch_decode(self, s, params, q_llr, c_seq_bits, g_fill=0):
+        """Returns (rc, data, g_bits, q_llr after the call, out[9] = ret, ack[0..3], ack.valid, ri, cqi crc, wideband cqi)"""
+        p = self._ul_params(*params)
+        q = aligned_zeros(len(q_llr) + 64, np.int16)
+        q[:len(q_llr)] = q_llr
+        g = aligned_zeros(len(q_llr) + 64, np.int16)
+        g[:] = g_fill
+        c = np.zeros(len(q_llr) + 64, np.uint8)
+        c[:len(q_llr)] = c_seq_bits
+        data = np.zeros(int(p[0]) // 8 + 8 + 768, np.uint8)
+        out = np.zeros(16, np.int32)
+        rc = self.L.ref_ulsch_decode(s, _p(p), _p(q), _p(c), _p(g), _p(data), _p(out))
+        return rc, data, g[:len(q_llr)].copy(), q[:len(q_llr)].copy(), out
 
     # CPU baseline runners
     # ---- soft demodulation + descrambling (SURVEY 8f row 1); the SSE bodies use aligned loads/stores

@@ -1169,3 +1169,109 @@ void orc_descramble_b(const uint8_t* c_bytes, int8_t* data, int len)
     if (c_bytes[i / 8] & (0x80u >> (i % 8)))
       data[i] = orc_w8(-(int32_t)data[i]);
 }
+
+/* ============================================================ PUSCH pre-steps
+ * What srslte_ulsch_decode (src/phy/phch/sch.c:1105-1180) does between the descrambler and decode_tb: locate the
+ * HARQ-ACK and RI resource elements, take their LLRs out, zero the ACK ones, de-interleave the rest (TS 36.212
+ * 5.2.2.8) and offset past the CQI.  The UCI payload decoders themselves (srslte_uci_decode_ack_ri's correlators,
+ * the CQI block/Viterbi decoders) are control-plane code and stay in the reference. */
+
+/* 36.213 Tables 8.6.3-1/-2/-3 as the reference holds them (sch.c:42-87); out-of-range indexes fall back like there */
+float orc_beta_offset(int which, uint32_t idx)
+{
+  static const float harq[16] = {2.0, 2.5, 3.125, 4.0, 5.0, 6.250, 8.0, 10.0, 12.625, 15.875, 20.0, 31.0, 50.0, 80.0, 126.0, -1.0};
+  static const float ri[16]   = {1.25, 1.625, 2.0, 2.5, 3.125, 4.0, 5.0, 6.25, 8.0, 10.0, 12.625, 15.875, 20.0, -1.0, -1.0, -1.0};
+  static const float cqi[16]  = {-1.0, -1.0, 1.125, 1.25, 1.375, 1.625, 1.750, 2.0, 2.25, 2.5, 2.875, 3.125, 3.5, 4.0, 5.0, 6.25};
+  switch (which) {
+    case 0: return idx < 15 ? harq[idx] : harq[0];
+    case 1: return idx < 13 ? ri[idx] : ri[0];
+    default: return (idx > 1 && idx < 16) ? cqi[idx] : cqi[2];
+  }
+}
+
+/* Q_prime_ri_ack (src/phy/phch/uci.c:606-630): coded symbols of an O-bit ACK or RI; K_segm = C1*K1 + C2*K2 (sch.c:1123) */
+uint32_t orc_qprime_ri_ack(uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, uint32_t O, uint32_t O_cqi, float beta)
+{
+  uint32_t K = K_segm;
+  if (K == 0)
+    K = O_cqi <= 11 ? O_cqi : O_cqi + 8;
+  float    f = (float)O * L_prb * 12 * nof_symb * beta / K;
+  uint32_t x = (uint32_t)ceilf(f);
+  uint32_t m = 4 * L_prb * 12;
+  return x < m ? x : m;
+}
+
+/* Q_prime_cqi (uci.c:329-345) */
+uint32_t orc_qprime_cqi(uint32_t K_segm, uint32_t L_prb, uint32_t nof_symb, uint32_t O, float beta, uint32_t Q_prime_ri)
+{
+  uint32_t L = O < 11 ? 0 : 8;
+  uint32_t x = 999999;
+  if (K_segm > 0)
+    x = (uint32_t)ceilf((float)(O + L) * L_prb * 12 * nof_symb * beta / K_segm);
+  uint32_t m = L_prb * 12 * nof_symb - Q_prime_ri;
+  return x < m ? x : m;
+}
+
+/* uci_ulsch_interleave_ack_gen / _ri_gen (uci.c:551-605): first of the Qm positions of coded symbol idx, or -1 where
+ * the reference logs an error (the symbol would sit above the first row) */
+int64_t orc_ulsch_uci_position(int is_ri, uint32_t idx, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs)
+{
+  static const uint32_t ack_norm[4] = {2, 3, 8, 9}, ack_ext[4] = {1, 2, 6, 7};
+  static const uint32_t ri_norm[4] = {1, 4, 7, 10}, ri_ext[4] = {0, 3, 5, 8};
+  uint32_t rows = H_prime_total / N_pusch_symbs;
+  if (rows < 1 + idx / 4)
+    return -1;
+  uint32_t row    = rows - 1 - idx / 4;
+  uint32_t colidx = (3 * idx) % 4;
+  uint32_t col    = N_pusch_symbs > 10 ? (is_ri ? ri_norm : ack_norm)[colidx] : (is_ri ? ri_ext : ack_ext)[colidx];
+  return (int64_t)row * Qm + (int64_t)rows * col * Qm;
+}
+
+/* The data movement of srslte_ulsch_decode, in its order:
+ *   1. ACK LLRs are read at their positions (uci.c:846-857) and the positions zeroed in q_bits (sch.c:1067-1070);
+ *   2. RI LLRs are read at theirs (they stay in q_bits);
+ *   3. ulsch_deinterleave (sch.c:992-1019): the table of ulsch_interleave_gen (:658-679) numbers the positions that
+ *      hold no RI row by row, column by column, and sends every RI position to index 0; srslte_vec_lut_sis
+ *      (utils/vector.c:136-141) then stores g[lut[i]] = q[i] for i ascending -- so with RI present g[0] ends up
+ *      holding the LLR of the LAST RI position, not the first data/CQI LLR (reference behaviour, kept).
+ * q_bits is modified like the reference modifies it; g_bits receives (H' - Q'_ri) * Qm values, the tail is untouched.
+ * Returns 0, or -1 for geometries the reference cannot index (see orc_ulsch_uci_position). */
+int orc_ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total, uint32_t N_pusch_symbs, uint32_t Q_prime_ack,
+                           uint32_t Q_prime_ri, int16_t* g_bits, int16_t* ack_llr, int16_t* ri_llr)
+{
+  if (Qm == 0 || N_pusch_symbs == 0 || H_prime_total < N_pusch_symbs || H_prime_total % N_pusch_symbs)
+    return -1;
+  const uint32_t rows = H_prime_total / N_pusch_symbs, cols = N_pusch_symbs, nof_bits = H_prime_total * Qm;
+  if (Q_prime_ack > 4 * rows || Q_prime_ri > 4 * rows)
+    return -1;
+  for (uint32_t i = 0; i < Q_prime_ack; i++) {
+    int64_t p = orc_ulsch_uci_position(0, i, Qm, H_prime_total, N_pusch_symbs);
+    for (uint32_t k = 0; k < Qm; k++) {
+      if (ack_llr)
+        ack_llr[i * Qm + k] = q_bits[p + k];
+      q_bits[p + k] = 0;
+    }
+  }
+  uint8_t* ri_present = (uint8_t*)calloc(nof_bits, 1);
+  for (uint32_t i = 0; i < Q_prime_ri; i++) {
+    int64_t p = orc_ulsch_uci_position(1, i, Qm, H_prime_total, N_pusch_symbs);
+    for (uint32_t k = 0; k < Qm; k++) {
+      if (ri_llr)
+        ri_llr[i * Qm + k] = q_bits[p + k];
+      ri_present[p + k] = 1;
+    }
+  }
+  uint32_t* lut = (uint32_t*)malloc(sizeof(uint32_t) * nof_bits);
+  uint32_t  idx = 0;
+  for (uint32_t j = 0; j < rows; j++)
+    for (uint32_t i = 0; i < cols; i++)
+      for (uint32_t k = 0; k < Qm; k++) {
+        uint32_t p = j * Qm + i * rows * Qm + k;
+        lut[p]     = ri_present[p] ? 0 : idx++;
+      }
+  for (uint32_t i = 0; i < nof_bits; i++)
+    g_bits[lut[i]] = q_bits[i];
+  free(lut);
+  free(ri_present);
+  return 0;
+}

@@ -12,6 +12,7 @@
  *   srslte_cbsegm*           lib/include/srslte/phy/fec/cbsegm.h:46-52
  *   srslte_dlsch_encode2 / srslte_dlsch_decode2   lib/src/phy/phch/sch.c:577,611
  *   srslte_demod_soft_demodulate_{s,b}             lib/src/phy/modem/demod_soft.c:896-945
+ *   srslte_ulsch_encode / srslte_ulsch_decode      lib/src/phy/phch/sch.c:1105-1330
  *   srslte_sequence_LTE_pr, srslte_scrambling_{s,sb}_offset   lib/src/phy/common/sequence.c, scrambling/scrambling.c:43-53
  *
  * Nothing in here re-implements reference arithmetic.
@@ -551,4 +552,86 @@ int ref_descramble_b(uint32_t c_init, int8_t* data, int len)
   srslte_scrambling_sb_offset(&seq, data, 0, len);
   srslte_sequence_free(&seq);
   return 0;
+}
+
+/* ------------------------------------------------------------------ PUSCH: srslte_ulsch_encode / srslte_ulsch_decode
+ * p = {tbs, Qm, L_prb, nof_symb, rv, nof_ack, ri_len, cqi (0 none, 1 wideband 4 bit, 2 higher-layer subband N=9 22 bit),
+ *      I_offset_ack, I_offset_ri, I_offset_cqi}; nb_q = L_prb * 12 * nof_symb * Qm */
+#include "srslte/phy/phch/pusch_cfg.h"
+static void fill_ul_cfg(ref_sch_t* s, srslte_pusch_cfg_t* cfg, const uint32_t* p, int tx)
+{
+  memset(cfg, 0, sizeof(*cfg));
+  cfg->grant.L_prb       = p[2];
+  cfg->grant.nof_symb    = p[3];
+  cfg->grant.nof_re      = p[2] * 12 * p[3];
+  cfg->grant.tb.enabled  = true;
+  cfg->grant.tb.tbs      = (int)p[0];
+  cfg->grant.tb.rv       = (int)p[4];
+  cfg->grant.tb.mod      = mod_from_qm(p[1]);
+  cfg->grant.tb.nof_bits = cfg->grant.nof_re * p[1];
+  cfg->uci_cfg.ack[0].nof_acks = p[5];
+  cfg->uci_cfg.cqi.ri_len      = p[6];
+  if (p[7]) {
+    cfg->uci_cfg.cqi.data_enable = true;
+    cfg->uci_cfg.cqi.type        = p[7] == 1 ? SRSLTE_CQI_TYPE_WIDEBAND : SRSLTE_CQI_TYPE_SUBBAND_HL;
+    cfg->uci_cfg.cqi.N           = 9;
+  }
+  cfg->uci_offset.I_offset_ack = p[8];
+  cfg->uci_offset.I_offset_ri  = p[9];
+  cfg->uci_offset.I_offset_cqi = p[10];
+  if (tx)
+    cfg->softbuffers.tx = &s->tx;
+  else
+    cfg->softbuffers.rx = &s->rx;
+}
+static void fill_uci_value(srslte_uci_value_t* v, const uint32_t* p, uint32_t seed)
+{
+  memset(v, 0, sizeof(*v));
+  for (uint32_t i = 0; i < p[5] && i < SRSLTE_UCI_MAX_ACK_BITS; i++)
+    v->ack.ack_value[i] = (seed >> i) & 1u;
+  v->ri = (seed >> 7) & 1u;
+  if (p[7] == 1) {
+    v->cqi.wideband.wideband_cqi = (seed >> 8) & 15u;
+  } else if (p[7] == 2) {
+    v->cqi.subband_hl.wideband_cqi_cw0     = (seed >> 8) & 15u;
+    v->cqi.subband_hl.subband_diff_cqi_cw0 = (seed * 2654435761u) & 0x3FFFFu;
+  }
+}
+/* data: tbs/8 bytes; q_bytes out: nb_q/8 packed bits of the interleaved, UCI-multiplexed codeword (before scrambling) */
+int ref_ulsch_encode(void* ss, const uint32_t* p, uint32_t uci_seed, uint8_t* data, uint8_t* q_bytes)
+{
+  ref_sch_t*         s = ss;
+  srslte_pusch_cfg_t cfg;
+  srslte_uci_value_t uci;
+  fill_ul_cfg(s, &cfg, p, 1);
+  fill_uci_value(&uci, p, uci_seed);
+  if (p[4] == 0)
+    srslte_softbuffer_tx_reset_tbs(&s->tx, p[0]);
+  uint32_t nb_q   = cfg.grant.tb.nof_bits;
+  uint8_t* g_bits = srslte_vec_u8_malloc(nb_q / 8 + 64);
+  memset(g_bits, 0, nb_q / 8 + 64);
+  memset(q_bytes, 0, nb_q / 8);
+  int r = srslte_ulsch_encode(&s->sch, &cfg, data, &uci, g_bits, q_bytes);
+  free(g_bits);
+  return r;
+}
+/* q_llr: int16[nb_q] descrambled LLRs, modified in place as the reference does; c_seq: nb_q unpacked scrambling bits;
+ * g_bits out: int16[nb_q] (pre-filled by the caller; the reference leaves the last Q'_ri*Qm untouched);
+ * out = {ret, ack_value[0..3], ack.valid, ri, cqi.data_crc, first cqi field} */
+int ref_ulsch_decode(void* ss, const uint32_t* p, int16_t* q_llr, uint8_t* c_seq, int16_t* g_bits, uint8_t* data, int32_t* out)
+{
+  ref_sch_t*         s = ss;
+  srslte_pusch_cfg_t cfg;
+  srslte_uci_value_t uci;
+  fill_ul_cfg(s, &cfg, p, 0);
+  memset(&uci, 0, sizeof(uci));
+  int r  = srslte_ulsch_decode(&s->sch, &cfg, q_llr, g_bits, c_seq, data, &uci);
+  out[0] = r;
+  for (int i = 0; i < 4; i++)
+    out[1 + i] = uci.ack.ack_value[i];
+  out[5] = uci.ack.valid;
+  out[6] = uci.ri;
+  out[7] = uci.cqi.data_crc;
+  out[8] = p[7] == 2 ? uci.cqi.subband_hl.wideband_cqi_cw0 : uci.cqi.wideband.wideband_cqi;
+  return r;
 }

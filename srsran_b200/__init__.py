@@ -50,6 +50,12 @@ class Demod(C.Structure):  # srslte_b200_demod_t
     _fields_ = [("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("scramble_bytes", C.c_void_p), ("e_bits", C.c_void_p)]
 
 
+class Ulsch(C.Structure):  # srslte_b200_ulsch_t
+    _fields_ = [("q_bits", C.c_void_p), ("Qm", C.c_uint32), ("H_prime_total", C.c_uint32), ("N_pusch_symbs", C.c_uint32),
+                ("Q_prime_ack", C.c_uint32), ("Q_prime_ri", C.c_uint32), ("Q_prime_cqi", C.c_uint32), ("g_bits", C.c_void_p),
+                ("ack_llr", C.c_void_p), ("ri_llr", C.c_void_p), ("cqi_llr", C.c_void_p)]
+
+
 MOD_BITS = [1, 2, 4, 6, 8]  # bits per symbol of srslte_mod_t 0..4 (BPSK, QPSK, 16QAM, 64QAM, 256QAM)
 
 
@@ -102,6 +108,7 @@ def lib():
         L.srslte_b200_sequence_bytes.argtypes = [C.c_uint32, C.c_uint32, C.c_void_p]
         L.srslte_b200_sequence_bytes.restype = None
         L.srslte_b200_encode_tbs.argtypes = [C.c_void_p, C.POINTER(Enc), C.c_uint32, C.c_uint32]
+        L.srslte_b200_ulsch_deinterleave.argtypes = [C.c_void_p, C.POINTER(Ulsch), C.c_uint32, C.c_uint32]
         L.srslte_b200_softbuffer_create.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32]
         L.srslte_b200_softbuffer_reset.argtypes = [C.c_void_p]
         L.srslte_b200_softbuffer_free.argtypes = [C.c_void_p]
@@ -143,6 +150,10 @@ def make_demods(n):
 
 def make_encs(n):
     return (Enc * n)()
+
+
+def make_ulschs(n):
+    return (Ulsch * n)()
 
 
 def _err(what, rc):
@@ -232,6 +243,35 @@ class Context:
         if rc:
             _err("srslte_b200_demod_descramble", rc)
         return outs
+
+    # ---- PUSCH pre-steps (the data movement of srslte_ulsch_decode before decode_tb)
+    def ulsch_deinterleave(self, blocks, uci=True):
+        """blocks: list of (q_bits int16[H' * Qm], Qm, N_pusch_symbs, Q'_ack, Q'_ri, Q'_cqi), host arrays.  Returns a list of
+        (g_bits int16[(H' - Q'_ri) * Qm], ack_llr, ri_llr, cqi_llr)."""
+        n = len(blocks)
+        arr = (Ulsch * n)()
+        keep, outs = [], []
+        for i, (q, Qm, nsym, qa, qr, qc) in enumerate(blocks):
+            q = np.ascontiguousarray(q, np.int16)
+            H = len(q) // Qm
+            o = (np.zeros((H - qr) * Qm, np.int16), np.zeros(qa * Qm, np.int16), np.zeros(qr * Qm, np.int16), np.zeros(qc * Qm, np.int16))
+            keep.append(q)
+            outs.append(o)
+            a = arr[i]
+            a.q_bits, a.Qm, a.H_prime_total, a.N_pusch_symbs, a.Q_prime_ack, a.Q_prime_ri, a.Q_prime_cqi = q.ctypes.data, Qm, H, nsym, qa, qr, qc
+            a.g_bits = o[0].ctypes.data
+            if uci:
+                a.ack_llr, a.ri_llr, a.cqi_llr = o[1].ctypes.data, o[2].ctypes.data, o[3].ctypes.data
+        rc = lib().srslte_b200_ulsch_deinterleave(self.h, arr, n, 0)
+        if rc:
+            _err("srslte_b200_ulsch_deinterleave", rc)
+        return outs
+
+    def ulsch_deinterleave_raw(self, arr, flags):
+        """arr: ctypes array of Ulsch with caller-managed (host or device) pointers"""
+        rc = lib().srslte_b200_ulsch_deinterleave(self.h, arr, len(arr), flags)
+        if rc:
+            _err("srslte_b200_ulsch_deinterleave", rc)
 
     # ---- transmit mirror (srslte_dlsch_encode2 semantics, stateless)
     def encode_tbs(self, blocks):

@@ -179,6 +179,7 @@ int Engine::create(Engine** out, int device)
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventCreate(&e->ev_end));
+  CUDA_OK(cudaEventCreateWithFlags(&e->ev_desc, cudaEventDisableTiming));
   int rc = e->build_tables();
   if (rc) {
     delete e;
@@ -197,6 +198,8 @@ Engine::~Engine()
     cudaEventDestroy(ev);
   if (ev_begin)
     cudaEventDestroy(ev_begin);
+  if (ev_desc)
+    cudaEventDestroy(ev_desc);
   if (ev_end)
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
@@ -206,6 +209,7 @@ Engine::~Engine()
   h_tmaps.release(); d_tmaps.release();
   d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); h_dm_desc.release(); h_dm_out.release();
   d_enc_in.release(); d_enc_out.release(); d_enc_desc.release(); h_enc_desc.release(); h_enc_out.release();
+  d_ul_in.release(); d_ul_out.release(); d_ul_uci.release(); d_ul_desc.release(); h_ul_out.release(); h_ul_uci.release(); h_ul_desc.release();
   if (stream)
     cudaStreamDestroy(stream);
   delete plan_ptr;
@@ -1098,6 +1102,7 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
       d_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || h_dm_desc.reserve(nof_cw * sizeof(DemodDev)))
     return SRSLTE_B200_ERROR;
   // pass 2: descriptors + uploads (adjacent host arrays go up in one copy)
+  CUDA_OK(cudaEventSynchronize(ev_desc)); // a previous device-to-device call may still be reading the pinned descriptors
   DemodDev*      hd = (DemodDev*)h_dm_desc.ptr;
   size_t         in_off = 0, out_off = 0;
   const uint8_t* cp_src = nullptr;
@@ -1141,6 +1146,7 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   if (cp_bytes)
     CUDA_OK(cudaMemcpyAsync(d_dm_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
   CUDA_OK(cudaMemcpyAsync(d_dm_desc.ptr, hd, nof_cw * sizeof(DemodDev), cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaEventRecord(ev_desc, stream));
   static const DemodConst kc = demod_constants();
   const dim3              grid(std::min<uint32_t>((max_sym + 255) / 256, 64), nof_cw);
   if (is8)
@@ -1159,6 +1165,152 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
     const size_t   nb = (size_t)cws[i].nof_symbols * Qm * esz;
     memcpy(cws[i].e_bits, h_dm_out.ptr + out_off, nb);
     out_off += al16(nb);
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------- PUSCH pre-steps
+int Engine::ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, uint32_t flags)
+{
+  if (!tbs && nof_tb) {
+    set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  if (nof_tb == 0)
+    return 0;
+  CUDA_OK(cudaSetDevice(device));
+  const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
+  auto           al16 = [](size_t v) { return (v + 15) / 16 * 16; };
+  size_t         in_bytes = 0, out_bytes = 0, uci_bytes = 0;
+  bool           want_uci = false;
+  for (uint32_t i = 0; i < nof_tb; i++) {
+    const srslte_b200_ulsch_t& u = tbs[i];
+    bool ok = u.q_bits && u.g_bits && u.Qm >= 2 && u.Qm <= 2 * kUlMaxW && u.Qm % 2 == 0 && u.N_pusch_symbs >= 1 &&
+              u.N_pusch_symbs <= (uint32_t)kUlMaxCols && u.H_prime_total >= u.N_pusch_symbs && u.H_prime_total % u.N_pusch_symbs == 0 &&
+              u.H_prime_total <= (1u << 24);
+    if (ok) {
+      const uint32_t rows = u.H_prime_total / u.N_pusch_symbs;
+      const uint32_t ack_last = u.N_pusch_symbs > 10 ? 9 : 7, ri_last = u.N_pusch_symbs > 10 ? 10 : 8;
+      ok = u.Q_prime_ack <= 4 * rows && u.Q_prime_ri <= 4 * rows && (u.Q_prime_ack == 0 || ack_last < u.N_pusch_symbs) &&
+           (u.Q_prime_ri == 0 || ri_last < u.N_pusch_symbs) && (uint64_t)u.Q_prime_ri + u.Q_prime_cqi <= u.H_prime_total;
+      if ((in_dev && ((uintptr_t)u.q_bits & 3u)) || (out_dev && ((uintptr_t)u.g_bits & 3u)))
+        ok = false;
+    }
+    if (!ok) {
+      set_error("invalid UL-SCH descriptor");
+      return SRSLTE_B200_ERROR_INVALID_INPUTS;
+    }
+    in_bytes += al16((size_t)u.H_prime_total * u.Qm * 2);
+    out_bytes += al16((size_t)(u.H_prime_total - u.Q_prime_ri) * u.Qm * 2);
+    if (u.ack_llr || u.ri_llr || u.cqi_llr) {
+      want_uci = true;
+      uci_bytes += al16((size_t)(u.Q_prime_ack + u.Q_prime_ri + u.Q_prime_cqi) * u.Qm * 2);
+    }
+  }
+  if ((!in_dev && d_ul_in.reserve(in_bytes + 64)) || (!out_dev && (d_ul_out.reserve(out_bytes + 64) || h_ul_out.reserve(out_bytes + 64))) ||
+      (want_uci && (d_ul_uci.reserve(uci_bytes + 64) || h_ul_uci.reserve(uci_bytes + 64))) || d_ul_desc.reserve(nof_tb * sizeof(UlschDev)) ||
+      h_ul_desc.reserve(nof_tb * sizeof(UlschDev)))
+    return SRSLTE_B200_ERROR;
+  CUDA_OK(cudaEventSynchronize(ev_desc)); // a previous device-to-device call may still be reading the pinned descriptors
+  UlschDev*      hd = (UlschDev*)h_ul_desc.ptr;
+  // the kernel is specialised on the words per symbol: descriptors are grouped by Qm, one launch per group
+  uint32_t       grp_n[kUlMaxW + 1] = {0}, grp_at[kUlMaxW + 2] = {0}, grp_rows[kUlMaxW + 1] = {0};
+  for (uint32_t i = 0; i < nof_tb; i++)
+    grp_n[tbs[i].Qm / 2]++;
+  for (int w = 1; w <= kUlMaxW; w++)
+    grp_at[w + 1] = grp_at[w] + grp_n[w];
+  size_t         in_off = 0, out_off = 0, uci_off = 0;
+  const uint8_t* cp_src = nullptr; // adjacent host arrays go up in one copy
+  size_t         cp_dst = 0, cp_bytes = 0;
+  for (uint32_t i = 0; i < nof_tb; i++) {
+    const srslte_b200_ulsch_t& u = tbs[i];
+    UlschDev&                  d = hd[grp_at[u.Qm / 2]++];
+    const size_t               nb = (size_t)u.H_prime_total * u.Qm * 2;
+    grp_rows[u.Qm / 2] = std::max(grp_rows[u.Qm / 2], u.H_prime_total / u.N_pusch_symbs);
+    d.W     = u.Qm / 2;
+    d.cols  = u.N_pusch_symbs;
+    d.rows  = u.H_prime_total / u.N_pusch_symbs;
+    d.q_ack = u.Q_prime_ack;
+    d.q_ri  = u.Q_prime_ri;
+    d.q_cqi = u.Q_prime_cqi;
+    d.ack_cols = u.N_pusch_symbs > 10 ? kUlAckNorm : kUlAckExt;
+    d.ri_cols  = u.N_pusch_symbs > 10 ? kUlRiNorm : kUlRiExt;
+    d.clobber  = -1;
+    for (uint32_t r = 0; r < u.Q_prime_ri; r++)
+      d.clobber = std::max<int32_t>(d.clobber, (int32_t)ul_uci_element(d.ri_cols, r, d.rows, u.Qm, u.Qm - 1));
+    if (in_dev) {
+      d.q = (const u32*)u.q_bits;
+    } else {
+      d.q = (const u32*)(d_ul_in.ptr + in_off);
+      if (cp_bytes && (const uint8_t*)u.q_bits == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
+        cp_bytes += nb;
+      } else {
+        if (cp_bytes)
+          cudaMemcpyAsync(d_ul_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream);
+        cp_src   = (const uint8_t*)u.q_bits;
+        cp_dst   = in_off;
+        cp_bytes = nb;
+      }
+      in_off += nb;
+      if (nb % 16)
+        in_off = al16(in_off);
+    }
+    if (out_dev) {
+      d.g = (u32*)u.g_bits;
+    } else {
+      d.g = (u32*)(d_ul_out.ptr + out_off);
+      out_off += al16((size_t)(u.H_prime_total - u.Q_prime_ri) * u.Qm * 2);
+    }
+    if (u.ack_llr || u.ri_llr || u.cqi_llr) {
+      d.uci = (int16_t*)(d_ul_uci.ptr + uci_off);
+      uci_off += al16((size_t)(u.Q_prime_ack + u.Q_prime_ri + u.Q_prime_cqi) * u.Qm * 2);
+    } else {
+      d.uci = nullptr;
+    }
+  }
+  if (cp_bytes)
+    CUDA_OK(cudaMemcpyAsync(d_ul_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaMemcpyAsync(d_ul_desc.ptr, hd, nof_tb * sizeof(UlschDev), cudaMemcpyHostToDevice, stream));
+  CUDA_OK(cudaEventRecord(ev_desc, stream));
+  for (int w = 1; w <= kUlMaxW; w++) {
+    if (!grp_n[w])
+      continue;
+    const dim3      grid(std::min<uint32_t>((grp_rows[w] + kUlRows - 1) / kUlRows, 64), grp_n[w]);
+    const UlschDev* dd = (const UlschDev*)d_ul_desc.ptr + (grp_at[w] - grp_n[w]); // grp_at[w] has advanced to the group's end
+    switch (w) {
+      case 1: k_ulsch_deinterleave<1><<<grid, 256, 0, stream>>>(dd); break;
+      case 2: k_ulsch_deinterleave<2><<<grid, 256, 0, stream>>>(dd); break;
+      case 3: k_ulsch_deinterleave<3><<<grid, 256, 0, stream>>>(dd); break;
+      default: k_ulsch_deinterleave<4><<<grid, 256, 0, stream>>>(dd); break;
+    }
+    CUDA_OK(cudaGetLastError());
+    last_launches++;
+  }
+  if (want_uci)
+    CUDA_OK(cudaMemcpyAsync(h_ul_uci.ptr, d_ul_uci.ptr, uci_off, cudaMemcpyDeviceToHost, stream));
+  if (!out_dev)
+    CUDA_OK(cudaMemcpyAsync(h_ul_out.ptr, d_ul_out.ptr, out_off, cudaMemcpyDeviceToHost, stream));
+  if (out_dev && !want_uci)
+    return 0; // stream-ordered with whatever is submitted next on this context
+  CUDA_OK(cudaStreamSynchronize(stream));
+  out_off = uci_off = 0;
+  for (uint32_t i = 0; i < nof_tb; i++) {
+    const srslte_b200_ulsch_t& u = tbs[i];
+    if (!out_dev) {
+      const size_t nb = (size_t)(u.H_prime_total - u.Q_prime_ri) * u.Qm * 2;
+      memcpy(u.g_bits, h_ul_out.ptr + out_off, nb);
+      out_off += al16(nb);
+    }
+    if (u.ack_llr || u.ri_llr || u.cqi_llr) {
+      const int16_t* p = (const int16_t*)(h_ul_uci.ptr + uci_off);
+      if (u.ack_llr)
+        memcpy(u.ack_llr, p, (size_t)u.Q_prime_ack * u.Qm * 2);
+      if (u.ri_llr)
+        memcpy(u.ri_llr, p + (size_t)u.Q_prime_ack * u.Qm, (size_t)u.Q_prime_ri * u.Qm * 2);
+      if (u.cqi_llr)
+        memcpy(u.cqi_llr, p + (size_t)(u.Q_prime_ack + u.Q_prime_ri) * u.Qm, (size_t)u.Q_prime_cqi * u.Qm * 2);
+      uci_off += al16((size_t)(u.Q_prime_ack + u.Q_prime_ri + u.Q_prime_cqi) * u.Qm * 2);
+    }
   }
   return 0;
 }
@@ -1272,9 +1424,11 @@ int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
     const size_t tb_b = htb.size() * sizeof(EncTbDev), cb_b = hcb.size() * sizeof(EncCbDev), cb_at = al16(tb_b);
     if (d_enc_desc.reserve(cb_at + cb_b + 64) || h_enc_desc.reserve(cb_at + cb_b + 64))
       return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaEventSynchronize(ev_desc));
     memcpy(h_enc_desc.ptr, htb.data(), tb_b);
     memcpy(h_enc_desc.ptr + cb_at, hcb.data(), cb_b);
     CUDA_OK(cudaMemcpyAsync(d_enc_desc.ptr, h_enc_desc.ptr, cb_at + cb_b, cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaEventRecord(ev_desc, stream));
     EncTbDev* dtb = (EncTbDev*)d_enc_desc.ptr;
     EncCbDev* dcb = (EncCbDev*)(d_enc_desc.ptr + cb_at);
     k_enc_tb_crc<<<((int)htb.size() + 3) / 4, 128, 0, stream>>>(dtb, (int)htb.size());
@@ -1508,6 +1662,12 @@ int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const srslte_b200_demod
   if (!ctx)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   return ctx->e->demod_descramble(cws, nof_cw, llr_is_8bit, flags);
+}
+int srslte_b200_ulsch_deinterleave(srslte_b200_ctx_t* ctx, const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, uint32_t flags)
+{
+  if (!ctx)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->ulsch_deinterleave(tbs, nof_tb, flags);
 }
 int srslte_b200_encode_tbs(srslte_b200_ctx_t* ctx, srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
 {

@@ -58,6 +58,7 @@ public:
   int softbuffer_create(Softbuffer** out, uint32_t max_cb);
   int demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, int is8, uint32_t flags);
   int encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags);
+  int ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, uint32_t flags);
   // host-pointer compatibility operations behind the drop-in srslte_* symbols (api.inc)
   int tdec_step(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, const void* input, uint32_t n_done, uint32_t n_more,
                 uint8_t* out);
@@ -103,6 +104,8 @@ public:
   PinBuf<uint8_t>  h_dm_desc, h_dm_out;
   DevBuf<uint8_t>  d_enc_in, d_enc_out, d_enc_desc; // transmit mirror: payloads, packed e-bits, descriptors
   PinBuf<uint8_t>  h_enc_desc, h_enc_out;
+  DevBuf<uint8_t>  d_ul_in, d_ul_out, d_ul_uci, d_ul_desc; // PUSCH pre-steps: staged q_bits, g_bits, ACK/RI/CQI LLRs, descriptors
+  PinBuf<uint8_t>  h_ul_out, h_ul_uci, h_ul_desc;
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
 
@@ -113,6 +116,7 @@ private:
   int finish_timing();
 
   cudaEvent_t              ev_begin = nullptr, ev_end = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  cudaEvent_t              ev_desc = nullptr; // last upload of a front-end descriptor array from its pinned staging buffer
   std::vector<cudaEvent_t> map_events;
   size_t                   n_map_events_used = 0;
 

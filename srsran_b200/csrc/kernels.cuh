@@ -10,6 +10,7 @@
 //                      sch.c:420-450)
 //   k_tb_finish        TB assembly, CRC24A, HARQ bookkeeping  (sch.c:462-486, 546-552)
 //   k_demod_descramble srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset (demod_soft.c:896-945)
+//   k_ulsch_deinterleave  ulsch_deinterleave + ACK/RI/CQI LLR extraction of srslte_ulsch_decode (sch.c:992-1019, 1021-1180)
 //   k_enc_tb_crc, k_enc_cb  encode_tb_off: CRC, turbo code, rate matching (sch.c:235-349, turbocoder.c, rm_turbo.c:349-395)
 #pragma once
 #include <cuda.h> // CUtensorMap (type only: the encoder is reached through cudaGetDriverEntryPoint)
@@ -17,6 +18,7 @@
 #include <stdint.h>
 
 #include "map_core.cuh"
+#include "ulsch_core.cuh"
 
 namespace b200 {
 
@@ -1593,6 +1595,102 @@ __global__ void __launch_bounds__(256) k_alu_probe(u32* out, int iters, u32 seed
   for (int i = 0; i < 8; i++)
     r ^= a[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+// ------------------------------------------------------------------------------------------ PUSCH pre-steps
+// The data movement of srslte_ulsch_decode (phch/sch.c:1105-1180) between the descrambler and decode_tb; geometry and
+// index arithmetic in ulsch_core.cuh.  A CTA moves a tile of kUlRows rows of the interleaver matrix through shared
+// memory: per column one contiguous run of q_bits in (coalesced, half a column run per warp and trip), one contiguous
+// run of g_bits out.  W (words per symbol) is a template parameter so that the index splits are constant divisions;
+// tiles above the bottom rows that hold ACK / RI symbols -- all but the last one or two -- take a path without the
+// per-symbol checks.
+template <int W>
+__global__ void __launch_bounds__(256, 5) k_ulsch_deinterleave(const UlschDev* __restrict__ tbs)
+{
+  constexpr uint32_t cs = (kUlRows + 1) * W; // column stride = W mod 32 banks: a row's symbols land in consecutive banks
+  __shared__ u32 s_tile[kUlMaxCols * cs];
+  const UlschDev d = tbs[blockIdx.y];
+  const uint32_t rows = d.rows, cols = d.cols;
+  const uint32_t inv_cols  = 65536u / cols + 1;                            // sym / cols == sym * inv_cols >> 16 for sym < 896
+  const uint32_t uci_rows  = max((d.q_ack + 3) / 4, (d.q_ri + 3) / 4);     // bottom rows that hold ACK or RI symbols
+  const uint32_t cqi_words = d.uci ? d.q_cqi * W : 0u;
+  const int16_t* qe  = reinterpret_cast<const int16_t*>(d.q);
+  u32*           cqi = d.uci ? reinterpret_cast<u32*>(d.uci + 2 * W * (d.q_ack + d.q_ri)) : nullptr;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (uint32_t j0 = blockIdx.x * kUlRows; j0 < rows; j0 += gridDim.x * kUlRows) {
+    const uint32_t rt = min((uint32_t)kUlRows, rows - j0), run = rt * W, half = run / 2;
+    const bool     plain = j0 + rt + uci_rows <= rows; // no ACK / RI symbol in this tile
+    __syncthreads();
+    if (rt == kUlRows && (plain || d.q_ack == 0)) {
+      // full tile without ACK symbols: every thread issues all of its loads (cols * W / 4 words) before the first use
+      constexpr uint32_t kRun = kUlRows * W, kTrips = (kUlMaxCols * kRun + 255) / 256;
+      u32                v[kTrips];
+#pragma unroll
+      for (uint32_t k = 0; k < kTrips; k++) {
+        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRun, x = idx - c * kRun;
+        if (c < cols)
+          v[k] = d.q[((size_t)c * rows + j0) * W + x];
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < kTrips; k++) {
+        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRun, x = idx - c * kRun;
+        if (c < cols)
+          s_tile[c * cs + x] = v[k];
+      }
+    } else {
+      for (uint32_t u = warp; u < 2 * cols; u += 8) { // one half of a column's run per warp and trip
+        const uint32_t c = u >> 1, x0 = (u & 1) ? half : 0u, x1 = (u & 1) ? run : half;
+        const u32*     src = d.q + ((size_t)c * rows + j0) * W;
+        for (uint32_t x = x0 + lane; x < x1; x += 32) { // ACK symbols are zeroed before the de-interleaver sees them (sch.c:1067-1070)
+          const uint32_t m = rows - 1 - (j0 + x / W);
+          s_tile[c * cs + x] = ul_holds(ul_row_count(m, d.q_ack), d.ack_cols, c) ? 0u : src[x];
+        }
+      }
+    }
+    __syncthreads();
+    const uint32_t n_out = cols * run;
+    if (plain) {
+      u32* dst = d.g + (size_t)j0 * cols * W;
+#pragma unroll 4
+      for (uint32_t idx = threadIdx.x; idx < n_out; idx += 256) {
+        const uint32_t sym = idx / W, w = idx - sym * W;
+        const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
+        u32            v  = s_tile[c * cs + jr * W + w];
+        if (j0 == 0) { // the head of g_bits: the reference's clobbered first LLR, and the CQI LLRs (sch.c:1152-1171)
+          if (idx == 0 && d.clobber > 0)
+            v = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
+          if (idx < cqi_words)
+            cqi[idx] = v;
+        }
+        dst[idx] = v;
+      }
+    } else {
+      for (uint32_t idx = threadIdx.x; idx < n_out; idx += 256) {
+        const uint32_t sym = idx / W, w = idx - sym * W;
+        const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
+        const uint32_t m    = rows - 1 - (j0 + jr);
+        const uint32_t n_ri = ul_row_count(m, d.q_ri);
+        if (ul_holds(n_ri, d.ri_cols, c))
+          continue;
+        const uint32_t o = ((j0 + jr) * cols + c - ul_ri_before(m, n_ri, d.q_ri, d.ri_cols, c)) * W + w;
+        u32            v = s_tile[c * cs + jr * W + w];
+        if (o == 0 && d.clobber > (int32_t)(((size_t)c * rows + j0 + jr) * 2 * W)) // the later store to index 0 wins
+          v = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
+        d.g[o] = v;
+        if (o < cqi_words)
+          cqi[o] = v;
+      }
+    }
+  }
+  // LLRs at the ACK and RI positions, in the order srslte_uci_decode_ack_ri walks them (uci.c:843-857)
+  if (blockIdx.x == 0 && d.uci) {
+    constexpr uint32_t Qm = 2 * W;
+    for (uint32_t idx = threadIdx.x; idx < (d.q_ack + d.q_ri) * Qm; idx += blockDim.x) {
+      const uint32_t r0 = idx / Qm, k = idx - r0 * Qm;
+      const bool     ri = r0 >= d.q_ack;
+      d.uci[idx] = qe[ul_uci_element(ri ? d.ri_cols : d.ack_cols, ri ? r0 - d.q_ack : r0, rows, Qm, k)];
+    }
+  }
 }
 
 } // namespace b200

@@ -14,6 +14,9 @@ Outputs (small, compressed):
   tests/golden/tb.npz        transport-block decodes through the real sch.c (incl. HARQ retransmissions)
   tests/golden/demod.npz     soft demodulation (all modulations, int16 / int8, lengths around the SIMD group sizes),
                              pseudo-random sequences and descrambled outputs
+  tests/golden/ulsch.npz     PUSCH: input LLRs of srslte_ulsch_decode for the grants of tests/util.py UL_GRANTS[:10] (made by
+                             srslte_ulsch_encode + AWGN) and what the call leaves behind: g_bits (digest of the UL-SCH part,
+                             the CQI part in full), q_bits (digest), return code, decoded bytes
 """
 import ctypes
 import hashlib
@@ -28,7 +31,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from oracle.bindings import CRC8, CRC16, CRC24A, CRC24B, Port, Ref, aligned_zeros  # noqa: E402
-from util import all_K, bpsk_awgn_llr, lanes8, lanes16, random_llr  # noqa: E402
+from util import UL_GRANTS, all_K, bpsk_awgn_llr, lanes8, lanes16, random_llr, ul_params, ul_qprime  # noqa: E402
 
 REF_SRC = os.environ.get("SRSLTE_REFERENCE", "/root/reference")
 
@@ -150,9 +153,40 @@ def make_demod():
     print("demod", os.path.getsize(os.path.join(HERE, "demod.npz")))
 
 
+def make_ulsch():
+    """tests/golden/ulsch.npz: the reference's srslte_ulsch_encode -> AWGN -> srslte_ulsch_decode on fixed inputs"""
+    R, P = Ref(), Port()
+    rng = np.random.default_rng(36212)
+    out = {}
+    for i, grant in enumerate(UL_GRANTS[:10]):
+        tbs, Qm, L_prb, nof_symb = grant[:4]
+        params = ul_params(grant)
+        s = R.sch_new(False, 8, 100)
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        q_tx = R.ulsch_encode(s, params, int(rng.integers(0, 1 << 20)), data)
+        llr = bpsk_awgn_llr(rng, q_tx, 100, 0.35, np.int16)
+        c_seq = rng.integers(0, 2, len(llr), dtype=np.uint8)
+        R.sch_reset_rx(s, tbs)
+        rc, d, g, q_after, uci = R.ulsch_decode(s, params, llr, c_seq, g_fill=777)
+        qa, qr, qc = ul_qprime(P, grant) # the reference does not report them; the fixture's g_bits only match if they are right
+        out["llr%d" % i] = llr
+        out["qprime%d" % i] = np.array([qa, qr, qc], np.uint32)
+        out["g_front%d" % i] = g[:qc * Qm]
+        out["g_data%d" % i] = digest(g[qc * Qm:])
+        out["q_after%d" % i] = digest(q_after)
+        out["rc%d" % i] = np.array([rc], np.int32)
+        out["data%d" % i] = d[:tbs // 8]
+        R.sch_del(s)
+    np.savez_compressed(os.path.join(HERE, "ulsch.npz"), **out)
+    print("ulsch", os.path.getsize(os.path.join(HERE, "ulsch.npz")))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "demod":
         make_demod()
+    elif len(sys.argv) > 1 and sys.argv[1] == "ulsch":
+        make_ulsch()
     else:
         main()
         make_demod()
+        make_ulsch()

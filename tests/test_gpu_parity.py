@@ -2,6 +2,7 @@
 same seeded inputs.  Bit-exact: decided bytes after every half-iteration, CRC outcomes, iteration counts,
 soft-buffer contents.  Marked gpu: run on the B200 box."""
 import ctypes as C
+import os
 
 import numpy as np
 import pytest
@@ -578,3 +579,144 @@ def test_front_end_and_encoder_reject_invalid_descriptors(ctx):
     _, rets = ctx.encode_tbs([(data, 1000, 2, 5, 2880), (data, 1000, 0, 0, 2880), (data, 1000, 2, 0, 2880)])
     assert rets == [-2, -2, 0]
     assert ctx.encode_tbs([]) == ([], [])
+
+
+# ----------------------------------------------------------------------------------------- PUSCH pre-steps
+def _ul_check(port, ctx, blocks):
+    got = ctx.ulsch_deinterleave(blocks)
+    for i, (q, Qm, nsym, qa, qr, qc) in enumerate(blocks):
+        rc, g, ack, ri, _ = port.ulsch_deinterleave(q, Qm, nsym, qa, qr)
+        assert rc == 0
+        n = (len(q) // Qm - qr) * Qm
+        assert (got[i][0] == g[:n]).all(), (i, Qm, nsym, qa, qr, qc, int(np.argmax(got[i][0] != g[:n])))
+        assert (got[i][1] == ack).all() and (got[i][2] == ri).all() and (got[i][3] == g[:qc * Qm]).all(), (i, Qm, nsym, qa, qr, qc)
+    return got
+
+
+def test_ulsch_deinterleave(port, ctx):
+    """k_ulsch_deinterleave against the oracle, many transport blocks per call: every Qm, normal / extended CP with and without
+    SRS, matrices from one row to 1320 rows (110 PRB), no UCI, ACK only, RI only, both, up to the four-per-row maximum, CQI
+    regions that do and do not cover the clobbered g_bits[0]; full-range int16 inputs"""
+    rng = np.random.default_rng(3621)
+    blocks = []
+    for Qm in (2, 4, 6, 8):
+        for nsym in (12, 11, 10, 9):
+            for rows in (1, 2, 3, 12, 63, 64, 65, 300, 1200, 1320):
+                if rows > 300 and (Qm == 8 or nsym in (11, 9)):
+                    continue
+                H = rows * nsym
+                for qa, qr in ((0, 0), (1, 0), (0, 1), (3, 2), (4 * rows, 4 * rows), (min(4 * rows, 37), min(4 * rows, 5)), (min(4 * rows, 6), min(4 * rows, 41))):
+                    qc = int(rng.integers(0, min(H - qr, 200) + 1)) if (rows + qa) % 2 else 0
+                    blocks.append((rng.integers(-32768, 32768, H * Qm).astype(np.int16), Qm, nsym, qa, qr, qc))
+    for nsym in (1, 7, 14):  # no UCI columns needed
+        blocks.append((rng.integers(-32768, 32768, nsym * 50 * 4).astype(np.int16), 4, nsym, 0, 0, 3))
+    assert len(blocks) > 500
+    _ul_check(port, ctx, blocks[:1])
+    _ul_check(port, ctx, blocks)
+    # without the UCI outputs the call is a pure de-interleave
+    got = ctx.ulsch_deinterleave(blocks[5:40], uci=False)
+    for (q, Qm, nsym, qa, qr, qc), g in zip(blocks[5:40], got):
+        assert (g[0] == port.ulsch_deinterleave(q, Qm, nsym, qa, qr)[1][:len(g[0])]).all()
+
+
+def test_pusch_golden_on_device(ctx):
+    """the fixtures recorded from the UNMODIFIED srslte_ulsch_decode (tests/golden/ulsch.npz): device de-interleave + device
+    decode_tb reproduce its g_bits (digest), CQI LLRs, return code and decoded bytes"""
+    import hashlib
+    from util import UL_GRANTS
+    u = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ulsch.npz"))
+    dig = lambda a: np.frombuffer(hashlib.sha256(np.ascontiguousarray(a).tobytes()).digest()[:8], np.uint64)[0]
+    blocks = []
+    for i, grant in enumerate(UL_GRANTS[:10]):
+        qa, qr, qc = u["qprime%d" % i].tolist()
+        blocks.append((u["llr%d" % i], grant[1], grant[3], qa, qr, qc))
+    got = ctx.ulsch_deinterleave(blocks)
+    t = b.make_tbs(len(blocks))
+    outs = []
+    for i, (grant, (q, Qm, nsym, qa, qr, qc)) in enumerate(zip(UL_GRANTS, blocks)):
+        g = got[i][0]
+        # (the fixture covers the reference's whole g_bits array: its last Q'_ri * Qm elements are never written, fill 777)
+        assert dig(np.concatenate([g[qc * Qm:], np.full(qr * Qm, 777, np.int16)])) == u["g_data%d" % i], i
+        front = got[i][3].copy()
+        if grant[6] == 1 and len(front) > 32:  # the reference's short-CQI decoder folds the copies in place (uci.c:379-385)
+            for k in range(1, len(front) // 32):
+                front[:32] += front[32 * k:32 * k + 32]
+            k = len(front) // 32
+            front[:len(front) % 32] += front[32 * k:]
+        assert (front == u["g_front%d" % i]).all(), i
+        e = np.ascontiguousarray(g[qc * Qm:])
+        o = np.zeros(grant[0] // 8 + 22, np.uint8)
+        outs.append((e, o))
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = e.ctypes.data, len(e), grant[0], Qm, 0, o.ctypes.data
+    ctx.decode_tbs(t, False, 8)
+    for i, grant in enumerate(UL_GRANTS[:10]):
+        assert t[i].ret == int(u["rc%d" % i][0]), i
+        assert (outs[i][1][:grant[0] // 8] == u["data%d" % i]).all(), i
+
+
+def test_pusch_symbols_to_transport_block_on_device(port, ctx):
+    """the receive chain of pusch.c / srslte_ulsch_decode on the device for a 100-PRB 64QAM subframe carrying ACK, RI and CQI:
+    symbols -> soft demodulation + descrambling -> UCI extraction + de-interleaving -> decode_tb, LLRs never leaving the GPU,
+    against the same chain through the oracle"""
+    from srsran_b200 import synth
+    rng = np.random.default_rng(1105)
+    tbs, mod, Qm, L_prb, nsym = 75376, 3, 6, 100, 12
+    rows, H = L_prb * 12, L_prb * 12 * nsym
+    qa, qr, qc = 36, 20, 57
+    G = (H - qr - qc) * Qm
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    g_tx = np.concatenate([rng.integers(0, 2, qc * Qm, dtype=np.uint8), port.encode_tb(tbs, Qm, 0, G, data)])
+    # channel interleaver of TS 36.212 5.2.2.8: row by row over the positions that hold no RI, then ACK overwrites
+    pos = (np.arange(rows)[:, None, None] * Qm + np.arange(nsym)[None, :, None] * rows * Qm + np.arange(Qm)[None, None, :]).reshape(-1)
+    ri_pos = np.concatenate([port.ulsch_uci_position(True, i, Qm, H, nsym) + np.arange(Qm) for i in range(qr)])
+    ack_pos = np.concatenate([port.ulsch_uci_position(False, i, Qm, H, nsym) + np.arange(Qm) for i in range(qa)])
+    q_tx = np.zeros(H * Qm, np.uint8)
+    q_tx[pos[~np.isin(pos, ri_pos)]] = g_tx
+    q_tx[ri_pos] = rng.integers(0, 2, len(ri_pos), dtype=np.uint8)
+    q_tx[ack_pos] = rng.integers(0, 2, len(ack_pos), dtype=np.uint8)
+    scr = port.sequence_bytes((0x46 << 14) + (5 << 9) + 1, H * Qm)
+    sym = synth.lte_modulate(q_tx ^ np.unpackbits(scr)[:H * Qm], mod)
+    sym = (sym + 0.07 * (rng.standard_normal(H) + 1j * rng.standard_normal(H))).astype(np.complex64)
+    # oracle chain
+    q_llr = port.descramble(scr, port.demod(mod, sym, np.int16))
+    rc0, g, ack, ri, _ = port.ulsch_deinterleave(q_llr, Qm, nsym, qa, qr)
+    sbp = port.softbuffer_new()
+    rc, want, nit, avg, crc = port.decode_tb(sbp, tbs, Qm, 0, g[qc * Qm:qc * Qm + G].copy(), 8)
+    port.softbuffer_del(sbp)
+    assert rc0 == 0 and rc == 0 and (want[:tbs // 8] == data).all()
+    # device chain
+    d_q, d_g, d_out = ctx.device_alloc(H * Qm * 2 + 64), ctx.device_alloc(H * Qm * 2 + 64), ctx.device_alloc(tbs // 8 + 64)
+    dm = b.make_demods(1)
+    dm[0].symbols, dm[0].nof_symbols, dm[0].mod, dm[0].scramble_bytes, dm[0].e_bits = sym.ctypes.data, H, mod, scr.ctypes.data, d_q
+    ctx.demod_descramble_raw(dm, False, b.OUT_DEVICE)
+    ul = b.make_ulschs(1)
+    a_l, r_l, c_l = np.zeros(qa * Qm, np.int16), np.zeros(qr * Qm, np.int16), np.zeros(qc * Qm, np.int16)
+    ul[0].q_bits, ul[0].Qm, ul[0].H_prime_total, ul[0].N_pusch_symbs, ul[0].g_bits = d_q, Qm, H, nsym, d_g
+    ul[0].Q_prime_ack, ul[0].Q_prime_ri, ul[0].Q_prime_cqi = qa, qr, qc
+    ul[0].ack_llr, ul[0].ri_llr, ul[0].cqi_llr = a_l.ctypes.data, r_l.ctypes.data, c_l.ctypes.data
+    ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
+    assert (a_l == ack).all() and (r_l == ri).all() and (c_l == g[:qc * Qm]).all()
+    t = b.make_tbs(1)
+    t[0].e_bits, t[0].nof_e_bits, t[0].tbs, t[0].Qm, t[0].rv, t[0].softbuffer, t[0].data = d_g + qc * Qm * 2, G, tbs, Qm, 0, None, d_out
+    ctx.decode_tbs(t, False, 8, flags=b.IN_DEVICE | b.OUT_DEVICE)
+    out = np.zeros(tbs // 8 + 6, np.uint8)
+    ctx.d2h(out, d_out)
+    for p in (d_q, d_g, d_out):
+        ctx.device_free(p)
+    assert t[0].ret == 0 and (out == want[:tbs // 8 + 6]).all() and (out[:tbs // 8] == data).all()
+    assert list(t[0].cb_noi[:13]) == nit[:13].tolist()
+
+
+def test_ulsch_rejects_invalid_descriptors(ctx):
+    q, g = np.zeros(12 * 8 * 2, np.int16), np.zeros(12 * 8 * 2, np.int16)
+    def call(Qm=2, H=96, nsym=12, qa=0, qr=0, qc=0, qp=q.ctypes.data, gp=g.ctypes.data):
+        ul = b.make_ulschs(1)
+        ul[0].q_bits, ul[0].Qm, ul[0].H_prime_total, ul[0].N_pusch_symbs, ul[0].g_bits = qp, Qm, H, nsym, gp
+        ul[0].Q_prime_ack, ul[0].Q_prime_ri, ul[0].Q_prime_cqi = qa, qr, qc
+        ctx.ulsch_deinterleave_raw(ul, 0)
+    call()
+    for bad in (dict(Qm=3), dict(Qm=0), dict(Qm=10), dict(H=95), dict(nsym=0), dict(nsym=15, H=90), dict(qa=33), dict(qr=33), dict(qr=8, qc=89), dict(qp=None),
+                dict(gp=None), dict(nsym=8, qr=1), dict(nsym=6, H=96, qa=1)):
+        with pytest.raises(b.B200Error):
+            call(**bad)
+    assert ctx.ulsch_deinterleave([]) == []

@@ -111,3 +111,36 @@ def test_glue_sub_semantics(emul):
     assert un(emul.emul_glue_sub(8, pk(100, -100), pk(-100, 100), 1, 1)) == (127, -128)
     assert un(emul.emul_glue_sub(8, pk(100, -100), pk(-100, 100), 0, 0)) == (200 - 256, -200 + 256)
     assert un(emul.emul_glue_sub(8, pk(100, -100), pk(-100, 100), 1, 0)) == (127, 56)
+
+
+# ----------------------------------------------------------------------------------------- k_ulsch_deinterleave
+def test_ulsch_kernel_index_arithmetic(port):
+    """The tile loops of k_ulsch_deinterleave with the index functions of srsran_b200/csrc/ulsch_core.cuh (compiled here with
+    g++, tests/host_emul/emul_ulsch.cpp) against the oracle's restatement of srslte_ulsch_decode's data movement"""
+    src, so = os.path.join(HERE, "host_emul", "emul_ulsch.cpp"), os.path.join(HERE, "host_emul", "libemul_ulsch.so")
+    deps = [src, os.path.join(CSRC, "ulsch_core.cuh"), os.path.join(CSRC, "arith.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-o", so, src])
+    L = C.CDLL(so)
+    rng = np.random.default_rng(992)
+    n = 0
+    for Qm in (2, 4, 6, 8):
+        for nsym in (12, 11, 10, 9):
+            for rows in (1, 2, 3, 12, 63, 64, 65, 129, 300, 1200):
+                if rows > 300 and Qm != 6:
+                    continue
+                H = rows * nsym
+                for qa, qr in ((0, 0), (1, 0), (0, 1), (3, 2), (4 * rows, 4 * rows), (min(4 * rows, 37), min(4 * rows, 5)), (min(4 * rows, 6), min(4 * rows, 41))):
+                    qc = int(rng.integers(0, min(H - qr, 200) + 1)) if (rows + qa) % 2 else 0
+                    q = rng.integers(-32768, 32768, H * Qm).astype(np.int16)
+                    g = np.full(H * Qm, 777, np.int16)
+                    uci = np.zeros((qa + qr + qc) * Qm + 2, np.int16)
+                    grid = int(rng.integers(1, 4))
+                    L.emul_ulsch(_p(q), C.c_uint32(Qm), C.c_uint32(H), C.c_uint32(nsym), C.c_uint32(qa), C.c_uint32(qr), C.c_uint32(qc), _p(g), _p(uci),
+                                 C.c_uint32(grid))
+                    rc, g_o, ack, ri, _ = port.ulsch_deinterleave(q, Qm, nsym, qa, qr, g_fill=777)
+                    assert rc == 0 and (g == g_o).all(), (Qm, nsym, rows, qa, qr, qc)
+                    assert (uci[:qa * Qm] == ack).all() and (uci[qa * Qm:(qa + qr) * Qm] == ri).all()
+                    assert (uci[(qa + qr) * Qm:(qa + qr + qc) * Qm] == g_o[:qc * Qm]).all()
+                    n += 1
+    assert n > 700

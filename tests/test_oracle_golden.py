@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 from oracle.bindings import CRC8, CRC16, CRC24A, CRC24B
-from util import all_K, lanes8, lanes16
+from util import UL_GRANTS, all_K, lanes8, lanes16, ul_qprime
 
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -126,3 +126,34 @@ def test_soft_demodulation_against_reference_outputs(port):
         assert (cb[:int(L) // 8] == g["seq%d" % i]).all()
         for bits in (16, 8):
             assert (port.descramble(cb, g["din%d_%d" % (i, bits)]) == g["dout%d_%d" % (i, bits)]).all()
+
+
+def test_ulsch_pre_steps_against_reference_outputs(port):
+    """what the unmodified srslte_ulsch_decode leaves in g_bits / q_bits for fixed input LLRs
+    (tests/golden/ulsch.npz): ACK zeroing, RI-skipping de-interleaver with its g_bits[0] side effect, CQI offset; and the
+    transport block decoded from the restated g_bits."""
+    u = np.load(os.path.join(G, "ulsch.npz"))
+    for i, grant in enumerate(UL_GRANTS[:10]):
+        tbs, Qm, L_prb, nof_symb = grant[:4]
+        llr = u["llr%d" % i]
+        qa, qr, qc = ul_qprime(port, grant)
+        assert [qa, qr, qc] == u["qprime%d" % i].tolist()
+        rc, g, ack, ri, q2 = port.ulsch_deinterleave(llr, Qm, nof_symb, qa, qr, g_fill=777)
+        assert rc == 0
+        assert digest(g[qc * Qm:]) == u["g_data%d" % i] and digest(q2) == u["q_after%d" % i], i
+        front = g[:qc * Qm].copy()
+        if grant[6] == 1 and len(front) > 32: # decode_cqi_short folds the copies onto the first 32 in place (uci.c:379-385)
+            for k in range(1, len(front) // 32):
+                front[:32] += front[32 * k:32 * k + 32]
+            k = len(front) // 32
+            front[:len(front) % 32] += front[32 * k:]
+        assert (front == u["g_front%d" % i]).all(), i
+        G_bits = (len(llr) // Qm - qr - qc) * Qm
+        sb = port.softbuffer_new()
+        rc_p, d, _, _, _ = port.decode_tb(sb, tbs, Qm, 0, g[qc * Qm:qc * Qm + G_bits].copy(), 8)
+        port.softbuffer_del(sb)
+        assert rc_p == int(u["rc%d" % i][0]) and (d[:tbs // 8] == u["data%d" % i]).all(), i
+    # geometries the reference cannot index
+    z = np.zeros(12 * 4 * 2, np.int16)
+    assert port.ulsch_deinterleave(z, 2, 12, 17, 0)[0] == -1 and port.ulsch_deinterleave(z, 2, 12, 0, 17)[0] == -1
+    assert port.ulsch_deinterleave(z[:-2], 2, 12, 0, 0)[0] == -1

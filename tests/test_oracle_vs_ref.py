@@ -5,7 +5,7 @@ import pytest
 
 from oracle.bindings import (CRC8, CRC16, CRC24A, CRC24B, TDEC_AUTO, TDEC_AVX8_WINDOW, TDEC_AVX_WINDOW, TDEC_GENERIC, TDEC_SSE8_WINDOW,
                              TDEC_SSE_WINDOW, aligned_zeros)
-from util import all_K, bpsk_awgn_llr, random_llr
+from util import all_K, bpsk_awgn_llr, random_llr, UL_GRANTS, ul_params, ul_qprime
 
 
 def test_segmentation_and_dispatch(port, ref):
@@ -194,3 +194,60 @@ def test_sequence_and_descrambling(port, ref):
         for dtype in (np.int16, np.int8):
             d = rng.integers(np.iinfo(dtype).min, np.iinfo(dtype).max + 1, L).astype(dtype)
             assert (port.descramble(cb, d) == ref.descramble(c_init, d)).all()
+
+
+# ----------------------------------------------------------------------------------------- SURVEY 8f rank 2
+@pytest.mark.parametrize("grant", UL_GRANTS)
+def test_ulsch_pre_steps(port, ref, grant):
+    """The real srslte_ulsch_encode -> AWGN -> srslte_ulsch_decode (sch.c:1105-1330) against the restatement of its data
+    movement: g_bits after the call (incl. the RI-clobbered g_bits[0] and the untouched tail), q_bits after the call (ACK
+    positions zeroed) -- which also pins the Q' formulas and the ACK / RI positions -- and the transport block decoded
+    from the restated g_bits."""
+    tbs, Qm, L_prb, nof_symb = grant[:4]
+    rng = np.random.default_rng(tbs + 7 * nof_symb + grant[4])
+    params = ul_params(grant)
+    s = ref.sch_new(False, 8, 100)
+    data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+    q_tx = ref.ulsch_encode(s, params, int(rng.integers(0, 1 << 20)), data)
+    nb_q = L_prb * 12 * nof_symb * Qm
+    assert len(q_tx) == nb_q
+    c_seq = rng.integers(0, 2, nb_q, dtype=np.uint8)
+    llr = bpsk_awgn_llr(rng, q_tx, 100, 0.35, np.int16)
+    ref.sch_reset_rx(s, tbs)
+    rc_ref, d_ref, g_ref, q_after, out = ref.ulsch_decode(s, params, llr, c_seq, g_fill=777)
+    qa, qr, qc = ul_qprime(port, grant)
+    assert (qa > 0) == (grant[4] > 0) and (qr > 0) == (grant[5] > 0) and (qc > 0) == (grant[6] > 0)
+    rc, g, ack, ri, q2 = port.ulsch_deinterleave(llr, Qm, nof_symb, qa, qr, g_fill=777)
+    assert rc == 0
+    assert (q2 == q_after).all()
+    Qc = qc * Qm
+    assert (g[Qc:] == g_ref[Qc:]).all()
+    if qr:
+        assert (g[-qr * Qm:] == 777).all()
+    # the CQI LLRs at the front: the reference's short-CQI decoder folds them onto the first 32 in place (decode_cqi_short,
+    # uci.c:379-385) after the de-interleaver wrote them; its long-CQI decoder only reads them
+    front = g[:Qc].copy()
+    if grant[6] == 1 and Qc > 32:
+        for i in range(1, Qc // 32):
+            front[:32] += front[32 * i:32 * i + 32]
+        i = max(Qc // 32, 1)
+        front[:Qc % 32] += front[32 * i:32 * i + Qc % 32]
+    assert (front == g_ref[:Qc]).all()
+    if qr and not qc:
+        assert g[0] == llr[max(port.ulsch_uci_position(True, i, Qm, nb_q // Qm, nof_symb) for i in range(qr)) + Qm - 1]
+    for i in range(qa):
+        p = port.ulsch_uci_position(False, i, Qm, nb_q // Qm, nof_symb)
+        assert (ack[i * Qm:(i + 1) * Qm] == llr[p:p + Qm]).all() and (q2[p:p + Qm] == 0).all()
+    for i in range(qr):
+        p = port.ulsch_uci_position(True, i, Qm, nb_q // Qm, nof_symb)
+        assert (ri[i * Qm:(i + 1) * Qm] == llr[p:p + Qm]).all()
+    # the transport block from the restated g_bits through the restated decode_tb
+    G = (nb_q // Qm - qr - qc) * Qm
+    sb = port.softbuffer_new()
+    rc_p, d_p, _, _, _ = port.decode_tb(sb, tbs, Qm, 0, g[qc * Qm:qc * Qm + G].copy(), 8)
+    port.softbuffer_del(sb)
+    assert rc_p == rc_ref
+    assert (d_p[:tbs // 8] == d_ref[:tbs // 8]).all()
+    if grant != UL_GRANTS[8]: # that one loses a third of its resource elements to a 126x ACK offset and does not decode
+        assert rc_ref == 0 and (d_p[:tbs // 8] == data).all()
+    ref.sch_del(s)

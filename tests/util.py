@@ -37,3 +37,36 @@ def std_to_sb(llr_std, K, N):
         out[s * (K + SB_PAD) + j] = llr_std[3 * n + s]
     out[3 * (K + SB_PAD):] = llr_std[3 * K:]
     return out
+
+
+# ---- PUSCH grants used by the UL pre-step tests: (tbs, Qm, L_prb, nof_symb, nof_ack, ri_len, cqi kind, I_ack, I_ri, I_cqi);
+# cqi kind 0 none / 1 wideband (4 bits) / 2 higher-layer subband N=9 (22 bits).  They cover QPSK/16QAM/64QAM, normal and
+# extended CP with and without SRS (12 / 11 / 10 / 9 symbols), 1, 2 and >2 ACK bits, RI, short and long CQI.
+UL_GRANTS = [
+    (2216, 2, 10, 12, 0, 0, 0, 9, 6, 6),
+    (2216, 2, 10, 12, 1, 0, 0, 9, 6, 6),
+    (5160, 2, 25, 12, 1, 1, 1, 9, 6, 6),
+    (3624, 2, 25, 10, 3, 1, 1, 10, 8, 7),
+    (3624, 2, 25, 9, 2, 1, 2, 9, 6, 6),
+    (9912, 4, 25, 12, 2, 1, 1, 11, 12, 15),
+    (9912, 4, 25, 11, 2, 1, 2, 0, 0, 2),
+    (1000, 4, 3, 11, 1, 1, 0, 9, 6, 6),
+    (1000, 2, 6, 12, 4, 1, 1, 14, 12, 12),
+    (15264, 6, 25, 12, 2, 1, 2, 9, 6, 6),
+    (36696, 6, 50, 12, 2, 1, 2, 9, 6, 6),
+    (75376, 6, 100, 12, 1, 1, 1, 9, 6, 6),
+]
+UL_CQI_LEN = {0: 0, 1: 4, 2: 22}
+
+
+def ul_params(grant, rv=0):
+    tbs, Qm, L_prb, nof_symb, nof_ack, ri_len, cqi, I_ack, I_ri, I_cqi = grant
+    return (tbs, Qm, L_prb, nof_symb, rv, nof_ack, ri_len, cqi, I_ack, I_ri, I_cqi)
+
+
+def ul_qprime(port, grant):
+    """(Q'_ack, Q'_ri, Q'_cqi) of a grant through the oracle's restatement of uci.c:329-345, 606-630"""
+    tbs, Qm, L_prb, nof_symb, nof_ack, ri_len, cqi, I_ack, I_ri, I_cqi = grant
+    _, seg = port.cbsegm(tbs)
+    K_segm = seg["C1"] * seg["K1"] + seg["C2"] * seg["K2"]
+    return port.ulsch_qprime(K_segm, L_prb, nof_symb, nof_ack, ri_len, UL_CQI_LEN[cqi], I_ack, I_ri, I_cqi)
