@@ -1233,11 +1233,7 @@ int Engine::ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, 
     d.q_ack = u.Q_prime_ack;
     d.q_ri  = u.Q_prime_ri;
     d.q_cqi = u.Q_prime_cqi;
-    d.ack_cols = u.N_pusch_symbs > 10 ? kUlAckNorm : kUlAckExt;
-    d.ri_cols  = u.N_pusch_symbs > 10 ? kUlRiNorm : kUlRiExt;
-    d.clobber  = -1;
-    for (uint32_t r = 0; r < u.Q_prime_ri; r++)
-      d.clobber = std::max<int32_t>(d.clobber, (int32_t)ul_uci_element(d.ri_cols, r, d.rows, u.Qm, u.Qm - 1));
+    ul_finish_descriptor(d, u.N_pusch_symbs);
     if (in_dev) {
       d.q = (const u32*)u.q_bits;
     } else {

@@ -1600,86 +1600,108 @@ __global__ void __launch_bounds__(256) k_alu_probe(u32* out, int iters, u32 seed
 // ------------------------------------------------------------------------------------------ PUSCH pre-steps
 // The data movement of srslte_ulsch_decode (phch/sch.c:1105-1180) between the descrambler and decode_tb; geometry and
 // index arithmetic in ulsch_core.cuh.  A CTA moves a tile of kUlRows rows of the interleaver matrix through shared
-// memory: per column one contiguous run of q_bits in (coalesced, half a column run per warp and trip), one contiguous
-// run of g_bits out.  W (words per symbol) is a template parameter so that the index splits are constant divisions;
-// tiles above the bottom rows that hold ACK / RI symbols -- all but the last one or two -- take a path without the
-// per-symbol checks.
+// memory: per column one contiguous run of q_bits in, one contiguous run of g_bits out.  The kernel is HBM-bound work
+// whose enemy is the index arithmetic per 32-bit word, so: W (words per symbol) is a template parameter; full tiles
+// load with 128-bit accesses, all of a thread's loads in flight before the first use; the ACK symbols (bottom rows) are
+// zeroed in shared memory; all rows above the RI symbols are stored with a thread mapping whose (column, word) is
+// fixed per thread (only the row advances), and only the few bottom rows that hold RI symbols take the per-word path.
 template <int W>
-__global__ void __launch_bounds__(256, 5) k_ulsch_deinterleave(const UlschDev* __restrict__ tbs)
+__global__ void __launch_bounds__(256, 4) k_ulsch_deinterleave(const UlschDev* __restrict__ tbs)
 {
-  constexpr uint32_t cs = (kUlRows + 1) * W; // column stride = W mod 32 banks: a row's symbols land in consecutive banks
-  __shared__ u32 s_tile[kUlMaxCols * cs];
+  constexpr uint32_t cs = kUlRows * W + 4; // column stride: 16-byte aligned columns, 4 banks apart
+  __shared__ __align__(16) u32 s_tile[kUlMaxCols * cs];
   const UlschDev d = tbs[blockIdx.y];
-  const uint32_t rows = d.rows, cols = d.cols;
-  const uint32_t inv_cols  = 65536u / cols + 1;                            // sym / cols == sym * inv_cols >> 16 for sym < 896
-  const uint32_t uci_rows  = max((d.q_ack + 3) / 4, (d.q_ri + 3) / 4);     // bottom rows that hold ACK or RI symbols
+  const uint32_t rows = d.rows, cols = d.cols, rw = cols * W;
+  const uint32_t inv_cols  = d.inv_cols;                 // sym / cols == sym * inv_cols >> 16 for the symbols of a tile
+  const uint32_t ack_rows  = (d.q_ack + 3) / 4, ri_rows = (d.q_ri + 3) / 4; // bottom rows that hold ACK / RI symbols
   const uint32_t cqi_words = d.uci ? d.q_cqi * W : 0u;
+  const bool     vec = ((rows * W) & 3u) == 0 && (reinterpret_cast<uintptr_t>(d.q) & 15u) == 0;
   const int16_t* qe  = reinterpret_cast<const int16_t*>(d.q);
   u32*           cqi = d.uci ? reinterpret_cast<u32*>(d.uci + 2 * W * (d.q_ack + d.q_ri)) : nullptr;
   const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (uint32_t j0 = blockIdx.x * kUlRows; j0 < rows; j0 += gridDim.x * kUlRows) {
     const uint32_t rt = min((uint32_t)kUlRows, rows - j0), run = rt * W, half = run / 2;
-    const bool     plain = j0 + rt + uci_rows <= rows; // no ACK / RI symbol in this tile
     __syncthreads();
-    if (rt == kUlRows && (plain || d.q_ack == 0)) {
-      // full tile without ACK symbols: every thread issues all of its loads (cols * W / 4 words) before the first use
-      constexpr uint32_t kRun = kUlRows * W, kTrips = (kUlMaxCols * kRun + 255) / 256;
-      u32                v[kTrips];
+    // ---- in: per column one contiguous run of q_bits
+    if (rt == kUlRows && vec) {
+      constexpr uint32_t kRunV = kUlRows * W / 4, kTrips = (kUlMaxCols * kRunV + 255) / 256;
+      uint4              v[kTrips];
 #pragma unroll
       for (uint32_t k = 0; k < kTrips; k++) {
-        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRun, x = idx - c * kRun;
+        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRunV, xv = idx - c * kRunV;
         if (c < cols)
-          v[k] = d.q[((size_t)c * rows + j0) * W + x];
+          v[k] = *reinterpret_cast<const uint4*>(d.q + ((size_t)c * rows + j0) * W + 4 * xv);
       }
 #pragma unroll
       for (uint32_t k = 0; k < kTrips; k++) {
-        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRun, x = idx - c * kRun;
+        const uint32_t idx = threadIdx.x + 256 * k, c = idx / kRunV, xv = idx - c * kRunV;
         if (c < cols)
-          s_tile[c * cs + x] = v[k];
+          *reinterpret_cast<uint4*>(&s_tile[c * cs + 4 * xv]) = v[k];
       }
     } else {
       for (uint32_t u = warp; u < 2 * cols; u += 8) { // one half of a column's run per warp and trip
         const uint32_t c = u >> 1, x0 = (u & 1) ? half : 0u, x1 = (u & 1) ? run : half;
         const u32*     src = d.q + ((size_t)c * rows + j0) * W;
-        for (uint32_t x = x0 + lane; x < x1; x += 32) { // ACK symbols are zeroed before the de-interleaver sees them (sch.c:1067-1070)
-          const uint32_t m = rows - 1 - (j0 + x / W);
-          s_tile[c * cs + x] = ul_holds(ul_row_count(m, d.q_ack), d.ack_cols, c) ? 0u : src[x];
-        }
+#pragma unroll 4
+        for (uint32_t x = x0 + lane; x < x1; x += 32)
+          s_tile[c * cs + x] = src[x];
       }
     }
     __syncthreads();
-    const uint32_t n_out = cols * run;
-    if (plain) {
-      u32* dst = d.g + (size_t)j0 * cols * W;
+    if (j0 + rt + ack_rows > rows) { // ACK symbols are zeroed before the de-interleaver sees them (sch.c:1067-1070)
+      for (uint32_t idx = threadIdx.x; idx < d.q_ack * W; idx += 256) {
+        const uint32_t r = idx / W, w = idx - r * W, j = rows - 1 - r / 4;
+        if (j >= j0 && j < j0 + rt)
+          s_tile[ul_col(d.ack_cols, r) * cs + (j - j0) * W + w] = 0;
+      }
+      __syncthreads();
+    }
+    // ---- out: the rows above the RI symbols leave as one contiguous run; (column, word) of a thread never change,
+    //      its row advances by rpp
+    const uint32_t n_plain = j0 + rt + ri_rows <= rows ? rt : (j0 + ri_rows >= rows ? 0u : rows - ri_rows - j0);
+    const size_t   base = (size_t)j0 * rw;
+    {
+      u32*           dst = d.g + base;
+      const uint32_t rpp = d.rpp;
+      if (threadIdx.x < rpp * rw) {
+        const uint32_t r0 = (threadIdx.x * d.inv_rw) >> 16, t = threadIdx.x - r0 * rw, c = t / W, w = t - c * W;
+        const u32*     sp = s_tile + c * cs + r0 * W + w;
+        u32*           gp = dst + threadIdx.x;
 #pragma unroll 4
-      for (uint32_t idx = threadIdx.x; idx < n_out; idx += 256) {
-        const uint32_t sym = idx / W, w = idx - sym * W;
-        const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
-        u32            v  = s_tile[c * cs + jr * W + w];
-        if (j0 == 0) { // the head of g_bits: the reference's clobbered first LLR, and the CQI LLRs (sch.c:1152-1171)
-          if (idx == 0 && d.clobber > 0)
-            v = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
-          if (idx < cqi_words)
-            cqi[idx] = v;
+        for (uint32_t jr = r0; jr < n_plain; jr += rpp, sp += rpp * W, gp += rpp * rw)
+          *gp = *sp;
+      }
+      if (n_plain && (base < cqi_words || (j0 == 0 && d.clobber > 0))) {
+        // the head of g_bits: the reference's clobbered first LLR, and the CQI LLRs (sch.c:1152-1171)
+        const uint32_t n_fix = (uint32_t)min((size_t)n_plain * rw, max((size_t)cqi_words, base + 1) - base);
+        for (uint32_t idx = threadIdx.x; idx < n_fix; idx += 256) {
+          const uint32_t sym = idx / W, w = idx - sym * W;
+          const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
+          u32            v  = s_tile[c * cs + jr * W + w];
+          if (base + idx == 0 && d.clobber > 0) {
+            v      = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
+            dst[0] = v; // same thread as the plain store above (thread 0), program order
+          }
+          if (base + idx < cqi_words)
+            cqi[base + idx] = v;
         }
-        dst[idx] = v;
       }
-    } else {
-      for (uint32_t idx = threadIdx.x; idx < n_out; idx += 256) {
-        const uint32_t sym = idx / W, w = idx - sym * W;
-        const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
-        const uint32_t m    = rows - 1 - (j0 + jr);
-        const uint32_t n_ri = ul_row_count(m, d.q_ri);
-        if (ul_holds(n_ri, d.ri_cols, c))
-          continue;
-        const uint32_t o = ((j0 + jr) * cols + c - ul_ri_before(m, n_ri, d.q_ri, d.ri_cols, c)) * W + w;
-        u32            v = s_tile[c * cs + jr * W + w];
-        if (o == 0 && d.clobber > (int32_t)(((size_t)c * rows + j0 + jr) * 2 * W)) // the later store to index 0 wins
-          v = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
-        d.g[o] = v;
-        if (o < cqi_words)
-          cqi[o] = v;
-      }
+    }
+    // ---- out: the bottom rows, RI symbols skipped (ulsch_interleave_gen, sch.c:658-679)
+    for (uint32_t idx = n_plain * rw + threadIdx.x; idx < rt * rw; idx += 256) {
+      const uint32_t sym = idx / W, w = idx - sym * W;
+      const uint32_t jr = (sym * inv_cols) >> 16, c = sym - jr * cols;
+      const uint32_t m    = rows - 1 - (j0 + jr);
+      const uint32_t n_ri = ul_row_count(m, d.q_ri);
+      if (ul_holds(n_ri, d.ri_cols, c))
+        continue;
+      const uint32_t o = ((j0 + jr) * cols + c - ul_ri_before(m, n_ri, d.q_ri, d.ri_cols, c)) * W + w;
+      u32            v = s_tile[c * cs + jr * W + w];
+      if (o == 0 && d.clobber > (int32_t)(((size_t)c * rows + j0 + jr) * 2 * W)) // the later store to index 0 wins
+        v = (v & 0xffff0000u) | (uint16_t)qe[d.clobber];
+      d.g[o] = v;
+      if (o < cqi_words)
+        cqi[o] = v;
     }
   }
   // LLRs at the ACK and RI positions, in the order srslte_uci_decode_ack_ri walks them (uci.c:843-857)

@@ -19,10 +19,12 @@ struct UlschDev {
   uint32_t   W, rows, cols;
   uint32_t   q_ack, q_ri, q_cqi;
   uint32_t   ack_cols, ri_cols; // the four columns of each set, one per byte, indexed by (3r) % 4
+  uint32_t   inv_cols, inv_rw, rpp; // host-computed: 65536 / cols + 1, 65536 / (cols * W) + 1 (exact quotients by multiply
+                                // and shift for the operand ranges of a tile), 256 / (cols * W) rows per store pass
   int32_t    clobber;           // element of q_bits that the reference leaves in g_bits[0] (its table sends every RI
                                 // position to index 0 and the last store wins, sch.c:670-671 + vector.c:136-141), or -1
 };
-constexpr int kUlRows    = 64; // rows of the matrix per tile
+constexpr int kUlRows    = 128; // rows of the matrix per tile
 constexpr int kUlMaxCols = 14;
 constexpr int kUlMaxW    = 4;
 
@@ -54,6 +56,21 @@ B200_HD uint32_t ul_ri_before(uint32_t m, uint32_t n_ri, uint32_t q_ri, uint32_t
 B200_HD size_t ul_uci_element(uint32_t colset, uint32_t r, uint32_t rows, uint32_t Qm, uint32_t k)
 {
   return ((size_t)ul_col(colset, r) * rows + (rows - 1 - r / 4)) * Qm + k;
+}
+
+// fills the derived fields of a descriptor whose W, rows, cols, q_ack, q_ri are set (host side)
+inline void ul_finish_descriptor(UlschDev& d, uint32_t N_pusch_symbs)
+{
+  d.ack_cols = N_pusch_symbs > 10 ? kUlAckNorm : kUlAckExt;
+  d.ri_cols  = N_pusch_symbs > 10 ? kUlRiNorm : kUlRiExt;
+  d.inv_cols = 65536u / d.cols + 1;
+  d.inv_rw   = 65536u / (d.cols * d.W) + 1;
+  d.rpp      = 256u / (d.cols * d.W);
+  d.clobber  = -1;
+  for (uint32_t r = 0; r < d.q_ri; r++) {
+    const int32_t e = (int32_t)ul_uci_element(d.ri_cols, r, d.rows, 2 * d.W, 2 * d.W - 1);
+    d.clobber       = e > d.clobber ? e : d.clobber;
+  }
 }
 
 } // namespace b200

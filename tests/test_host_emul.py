@@ -131,8 +131,10 @@ def test_ulsch_kernel_index_arithmetic(port):
                     continue
                 H = rows * nsym
                 for qa, qr in ((0, 0), (1, 0), (0, 1), (3, 2), (4 * rows, 4 * rows), (min(4 * rows, 37), min(4 * rows, 5)), (min(4 * rows, 6), min(4 * rows, 41))):
-                    qc = int(rng.integers(0, min(H - qr, 200) + 1)) if (rows + qa) % 2 else 0
-                    q = rng.integers(-32768, 32768, H * Qm).astype(np.int16)
+                    qc = int(rng.integers(0, min(H - qr, 200 if rows < 300 else 3000) + 1)) if (rows + qa) % 2 else 0
+                    qbuf = rng.integers(-32768, 32768, H * Qm + 16).astype(np.int16)
+                    off = (-qbuf.ctypes.data % 16) // 2 + (2 if n % 3 == 0 else 0)  # 16-byte aligned (128-bit path) or not
+                    q = qbuf[off:off + H * Qm]
                     g = np.full(H * Qm, 777, np.int16)
                     uci = np.zeros((qa + qr + qc) * Qm + 2, np.int16)
                     grid = int(rng.integers(1, 4))
