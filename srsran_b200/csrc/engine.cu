@@ -1084,7 +1084,6 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   const size_t esz = is8 ? 1 : 2;
   // pass 1: validate, size the staging areas (every piece 16-byte aligned)
   size_t   in_bytes = 0, out_bytes = 0;
-  uint32_t max_sym = 0;
   auto     al16 = [](size_t v) { return (v + 15) / 16 * 16; };
   for (uint32_t i = 0; i < nof_cw; i++) {
     const srslte_b200_demod_t& c = cws[i];
@@ -1095,7 +1094,6 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
     const uint32_t Qm = c.mod == 0 ? 1 : 2 * c.mod;
     in_bytes += al16((size_t)c.nof_symbols * 8) + (c.scramble_bytes ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0);
     out_bytes += al16((size_t)c.nof_symbols * Qm * esz);
-    max_sym = std::max(max_sym, c.nof_symbols);
   }
   const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
   if ((!in_dev && d_dm_in.reserve(in_bytes + 64)) || (!out_dev && (d_dm_out.reserve(out_bytes + 64) || h_dm_out.reserve(out_bytes + 64))) ||
@@ -1104,6 +1102,12 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   // pass 2: descriptors + uploads (adjacent host arrays go up in one copy)
   CUDA_OK(cudaEventSynchronize(ev_desc)); // a previous device-to-device call may still be reading the pinned descriptors
   DemodDev*      hd = (DemodDev*)h_dm_desc.ptr;
+  // the kernel is specialised on the modulation: descriptors are grouped by it, one launch per group
+  uint32_t       grp_n[5] = {0}, grp_at[6] = {0}, grp_sym[5] = {0};
+  for (uint32_t i = 0; i < nof_cw; i++)
+    grp_n[cws[i].mod]++;
+  for (int m = 0; m < 5; m++)
+    grp_at[m + 1] = grp_at[m] + grp_n[m];
   size_t         in_off = 0, out_off = 0;
   const uint8_t* cp_src = nullptr;
   size_t         cp_dst = 0, cp_bytes = 0;
@@ -1126,7 +1130,8 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   for (uint32_t i = 0; i < nof_cw; i++) {
     const srslte_b200_demod_t& c  = cws[i];
     const uint32_t             Qm = c.mod == 0 ? 1 : 2 * c.mod;
-    DemodDev&                  d  = hd[i];
+    DemodDev&                  d  = hd[grp_at[c.mod]++];
+    grp_sym[c.mod] = std::max(grp_sym[c.mod], c.nof_symbols);
     d.nsym = c.nof_symbols;
     d.mod  = c.mod;
     if (in_dev) {
@@ -1148,13 +1153,29 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   CUDA_OK(cudaMemcpyAsync(d_dm_desc.ptr, hd, nof_cw * sizeof(DemodDev), cudaMemcpyHostToDevice, stream));
   CUDA_OK(cudaEventRecord(ev_desc, stream));
   static const DemodConst kc = demod_constants();
-  const dim3              grid(std::min<uint32_t>((max_sym + 255) / 256, 64), nof_cw);
-  if (is8)
-    k_demod_descramble<int8_t><<<grid, 256, 0, stream>>>((const DemodDev*)d_dm_desc.ptr, kc);
-  else
-    k_demod_descramble<int16_t><<<grid, 256, 0, stream>>>((const DemodDev*)d_dm_desc.ptr, kc);
-  CUDA_OK(cudaGetLastError());
-  last_launches++;
+  for (int m = 0; m < 5; m++) {
+    if (!grp_n[m])
+      continue;
+    const dim3      grid(std::min<uint32_t>((grp_sym[m] + kDemodU * 256 - 1) / (kDemodU * 256), 64), grp_n[m]);
+    const DemodDev* dd = (const DemodDev*)d_dm_desc.ptr + (grp_at[m] - grp_n[m]); // grp_at[m] has advanced to the group's end
+#define B200_DEMOD_LAUNCH(M)                                              \
+  case M:                                                                 \
+    if (is8)                                                              \
+      k_demod_descramble<int8_t, M><<<grid, 256, 0, stream>>>(dd, kc);    \
+    else                                                                  \
+      k_demod_descramble<int16_t, M><<<grid, 256, 0, stream>>>(dd, kc);   \
+    break;
+    switch (m) {
+      B200_DEMOD_LAUNCH(0)
+      B200_DEMOD_LAUNCH(1)
+      B200_DEMOD_LAUNCH(2)
+      B200_DEMOD_LAUNCH(3)
+      B200_DEMOD_LAUNCH(4)
+    }
+#undef B200_DEMOD_LAUNCH
+    CUDA_OK(cudaGetLastError());
+    last_launches++;
+  }
   if (out_dev)
     return 0; // stream-ordered with whatever is submitted next on this context
   CUDA_OK(cudaMemcpyAsync(h_dm_out.ptr, d_dm_out.ptr, out_off, cudaMemcpyDeviceToHost, stream));

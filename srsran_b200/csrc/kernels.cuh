@@ -1180,7 +1180,8 @@ __device__ __forceinline__ int32_t satT(int32_t v) // _mm_packs_epi32 [+ _mm_pac
 template <typename T>
 __device__ __forceinline__ int32_t absT(int32_t v) { return wrapT<T>(v < 0 ? -v : v); } // abs(-min) = -min, like pabsw/pabsb
 
-template <typename T>
+constexpr int kDemodU = 4;
+template <typename T, int MOD> // one instantiation per modulation (the host groups the codewords): no per-symbol switch
 __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __restrict__ cws, const DemodConst c)
 {
   constexpr bool S     = sizeof(T) == 2;
@@ -1189,14 +1190,32 @@ __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __rest
   const int      grp   = S ? 4 : 8;              // symbols per SSE trip of the 16QAM / 64QAM bodies
   const int      n_sse = n / grp * grp;
   const int      qlen = 2 * n, q_sse = qlen >= 16 ? ((qlen - 16) / 16 + 1) * 16 : 0; // values converted by the QPSK SIMD body
-  const int      Qm   = d.mod == 0 ? 1 : 2 * (int)d.mod;
+  constexpr int  Qm   = MOD == 0 ? 1 : 2 * MOD;
   T*             out  = (T*)d.out;
   const bool     vec4 = (((uintptr_t)out) & 3u) == 0 && ((Qm * sizeof(T)) & 3u) == 0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float2 sy = reinterpret_cast<const float2*>(d.sym)[i];
-    const float  re = sy.x, im = sy.y;
+  // kDemodU symbols per thread and trip, their loads (symbol + sequence bytes) issued before the first use
+  for (int i0 = blockIdx.x * (kDemodU * 256) + threadIdx.x; i0 < n; i0 += gridDim.x * (kDemodU * 256)) {
+    float2   sy_u[kDemodU];
+    uint32_t win_u[kDemodU];
+#pragma unroll
+    for (int u = 0; u < kDemodU; u++) {
+      const int i = i0 + u * 256;
+      if (i < n) {
+        sy_u[u] = reinterpret_cast<const float2*>(d.sym)[i];
+        if (d.scr) { // 16 sequence bits starting at byte b0 / 8 (the second byte only when the symbol's bits reach into it)
+          const uint32_t b0 = (uint32_t)i * (uint32_t)Qm;
+          win_u[u] = ((uint32_t)d.scr[b0 >> 3] << 8) | (((b0 & 7u) + (uint32_t)Qm > 8u) ? (uint32_t)d.scr[(b0 >> 3) + 1] : 0u);
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kDemodU; u++) {
+    const int i = i0 + u * 256;
+    if (i >= n)
+      break;
+    const float  re = sy_u[u].x, im = sy_u[u].y;
     int32_t      v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    switch (d.mod) {
+    switch (MOD) {
       case 0: { // demod_bpsk_lte_{s,b}
         const float t = __fmul_rn(S ? -100.0f : -20.0f, __fadd_rn(re, im));
         v[0]          = wrapT<T>(cvt_trunc_d(__dmul_rn((double)t, 0.70710678118654752440)));
@@ -1271,8 +1290,7 @@ __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __rest
     // descrambling: wrapping negation where the sequence bit is 1 (srslte_vec_neg_* against c_short / c_char = +-1)
     const uint32_t b0 = (uint32_t)i * (uint32_t)Qm;
     if (d.scr) {
-      // 16 sequence bits starting at byte b0 / 8 (the second byte only when the symbol's bits reach into it)
-      const uint32_t win = ((uint32_t)d.scr[b0 >> 3] << 8) | (((b0 & 7u) + (uint32_t)Qm > 8u) ? (uint32_t)d.scr[(b0 >> 3) + 1] : 0u);
+      const uint32_t win = win_u[u];
 #pragma unroll
       for (int k = 0; k < 8; k++)
         if (k < Qm && ((win >> (15 - (b0 & 7u) - k)) & 1u))
@@ -1291,6 +1309,7 @@ __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __rest
       for (int k = 0; k < 8; k++)
         if (k < Qm)
           out[b0 + k] = (T)v[k];
+    }
     }
   }
 }
