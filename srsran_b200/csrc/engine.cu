@@ -820,6 +820,7 @@ struct Softbuffer {
   uint8_t* data;  // max_cb x 768
   uint8_t* crc;   // max_cb flags (device)
   std::vector<uint8_t> crc_host;
+  std::vector<uint8_t> zero_pending; // per code block: reset since its last use -- the next de-matching starts from zeros
   bool     tb_crc;
 };
 
@@ -971,7 +972,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
       d.rm_start = rm_start[li][ci][u.rv];
       if (sb) {
         d.in_ptr = (void*)(sb->buf + (size_t)c * kSoftbufElems);
-        d.fresh  = 0;
+        d.fresh  = sb->zero_pending[c] ? 2 : 0; // 2: clear, combine AND keep (srslte_softbuffer_rx_reset* since the last use)
+        sb->zero_pending[c] = 0;
         d.skip   = sb->crc_host[c] ? 1 : 0; // sch.c:385
       } else {
         d.in_ptr = nullptr; // one-shot decode: the combined soft bits never leave the SM (k_dematch_prepare)
@@ -1498,6 +1500,7 @@ int Engine::softbuffer_create(Softbuffer** out, uint32_t max_cb)
   s->max_cb     = max_cb;
   s->tb_crc     = false;
   s->crc_host.assign(max_cb, 0);
+  s->zero_pending.assign(max_cb, 0);
   const size_t bytes = (size_t)max_cb * (kSoftbufElems * 2 + 768 + 1) + 256;
   uint8_t*     base  = nullptr;
   cudaError_t  e     = cudaMalloc((void**)&base, bytes);
@@ -1520,9 +1523,10 @@ void softbuffer_reset(Softbuffer* s)
   if (!s)
     return;
   cudaSetDevice(s->eng->device);
-  const size_t bytes = (size_t)s->max_cb * (kSoftbufElems * 2 + 768 + 1);
-  cudaMemsetAsync(s->buf, 0, bytes, s->eng->stream);
-  cudaStreamSynchronize(s->eng->stream);
+  // lazy: no device work and no synchronisation here -- the next de-matching of each code block starts from zeros in
+  // shared memory and writes the combined soft bits back (CbDev::fresh == 2); the saved bytes / flags of a code block
+  // are only read after a later call has written them
+  std::fill(s->zero_pending.begin(), s->zero_pending.end(), 1);
   std::fill(s->crc_host.begin(), s->crc_host.end(), 0);
   s->tb_crc = false;
 }

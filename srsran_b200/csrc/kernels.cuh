@@ -48,7 +48,8 @@ struct CbDev {
   uint32_t rm_start; // rank of the first transmitted entry for this rv
   uint32_t tb;       // owning transport block
   uint32_t cb_in_tb;
-  uint32_t fresh;    // soft buffer must be cleared before combining (new transmission)
+  uint32_t fresh;    // soft buffer must be cleared before combining (new transmission): 1 = one-shot, nothing kept;
+                     // 2 = caller-owned HARQ buffer that was reset since its last use (cleared, combined, written back)
 };
 
 struct CbState {
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
 // soft buffer of the block is assembled in shared memory (zero-filled for a new transmission, loaded for a
 // retransmission), the e-bits are accumulated into it (same gather form as k_dematch), and the result leaves the
 // SM as the decoder's three int16 planes + tails + per-plane max|LLR|; it is written back to the HARQ soft buffer
-// only when the caller keeps one (d.fresh == 0 means a caller-owned buffer).
+// only when the caller keeps one (d.fresh != 1 means a caller-owned buffer).
 template <typename T>
 __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list,
                                                          const uint16_t* __restrict__ rm_pool, int16_t* __restrict__ ws,
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     }
   }
   __syncthreads();
-  if (!d.fresh) {
+  if (d.fresh != 1) {
     for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
       gsb[i] = sb[i];
   }

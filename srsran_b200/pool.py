@@ -1,0 +1,154 @@
+"""Pooled vRAN receive path over the C ABI (BASELINE config 5): the subframes of many cells decoded by the GPUs
+of one box.  Host-side orchestration only -- every computation is a call into libsrslte_fec_b200.so.
+
+Sharding: a cell belongs to ONE rank (``owner_of``), so the HARQ soft buffers of its (direction, HARQ process) pairs
+stay resident in the HBM of the GPU that decodes it; code blocks and subframes are independent, so there is no
+collective on the data path (reference: one srslte_sch_t + srslte_softbuffer_rx_t per PHY worker and carrier,
+lib/src/phy/phch/sch.c:363-570, srsenb/src/phy/cc_worker.cc).
+
+Per rank two engines run side by side: downlink-shaped transport blocks (rate-matched e-bits as PDSCH delivers them,
+decode_tb sch.c:503-570) on one, uplink subframes (descrambled q_bits -> UCI extraction + channel de-interleaving ->
+decode_tb, srslte_ulsch_decode sch.c:1105-1180) on the other, so that the uplink pre-step overlaps the downlink decode.
+"""
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import IN_DEVICE, OUT_DEVICE, B200Error, Context, Ulsch, make_tbs
+
+
+def owner_of(cell: int, world: int) -> int:
+    """rank that owns a cell: stable per cell, so HARQ state never moves between GPUs"""
+    return cell % world
+
+
+def partition(jobs, rank: int, world: int):
+    """the jobs of one rank, in submission order"""
+    return [j for j in jobs if owner_of(j.cell, world) == rank]
+
+
+@dataclass
+class Job:
+    cell: int
+    tti: int
+    kind: str                    # "dl": llr = rate-matched e-bits; "ul": llr = descrambled q_bits of the PUSCH subframe
+    pid: int                     # HARQ process
+    rv: int
+    new_data: bool               # first transmission of a transport block: the process's soft buffer is reset
+    tbs: int
+    Qm: int
+    llr: np.ndarray              # int16, host
+    n_pusch_symbs: int = 12      # "ul" only
+    q_prime: Tuple[int, int, int] = (0, 0, 0)  # "ul" only: coded symbols of ACK, RI, CQI
+
+
+@dataclass
+class Result:
+    ret: int = 0
+    data: Optional[np.ndarray] = None
+    avg_iterations: float = 0.0
+    cb_noi: list = field(default_factory=list)
+    cb_crc: list = field(default_factory=list)
+    ack_llr: Optional[np.ndarray] = None
+    ri_llr: Optional[np.ndarray] = None
+    cqi_llr: Optional[np.ndarray] = None
+
+
+class CellPool:
+    """The cells one rank owns: two engines on its GPU and the device-resident HARQ soft buffers of its cells."""
+
+    def __init__(self, rank=0, world=1, device=0, max_iterations=8):
+        self.rank, self.world, self.max_iterations = rank, world, max_iterations
+        self.dl = Context(device)
+        self.ul = Context(device)
+        self._harq = {}
+        self._g_dev, self._g_cap = None, 0
+
+    def close(self):
+        for kind, sb in self._harq.values():
+            (self.dl if kind == "dl" else self.ul).softbuffer_free(sb)
+        self._harq = {}
+        if self._g_dev:
+            self.ul.device_free(self._g_dev)
+            self._g_dev = None
+        self.dl.close()
+        self.ul.close()
+
+    def owns(self, cell):
+        return owner_of(cell, self.world) == self.rank
+
+    def _softbuffer(self, job):
+        key = (job.cell, job.kind, job.pid)
+        if key not in self._harq:
+            self._harq[key] = (job.kind, (self.dl if job.kind == "dl" else self.ul).softbuffer_create())
+        sb = self._harq[key][1]
+        if job.new_data:
+            (self.dl if job.kind == "dl" else self.ul).softbuffer_reset(sb)
+        return sb
+
+    def decode(self, jobs):
+        """Decode one batch of jobs (all owned by this rank; at most one job per (cell, kind, pid)).  Returns a Result per job."""
+        seen = set()
+        for j in jobs:
+            if not self.owns(j.cell):
+                raise B200Error("cell %d belongs to rank %d, not %d" % (j.cell, owner_of(j.cell, self.world), self.rank))
+            if (j.cell, j.kind, j.pid) in seen:
+                raise B200Error("two jobs of one HARQ process in a batch: their order would matter")
+            seen.add((j.cell, j.kind, j.pid))
+        res = [Result() for _ in jobs]
+        dl = [i for i, j in enumerate(jobs) if j.kind == "dl"]
+        ul = [i for i, j in enumerate(jobs) if j.kind == "ul"]
+        keep = []
+        # ---- downlink-shaped blocks: one asynchronous batch on the first engine
+        t_dl = make_tbs(len(dl))
+        for k, i in enumerate(dl):
+            j = jobs[i]
+            llr = np.ascontiguousarray(j.llr, np.int16)
+            res[i].data = np.zeros(j.tbs // 8 + 8, np.uint8)
+            keep.append(llr)
+            t = t_dl[k]
+            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = llr.ctypes.data, len(llr), j.tbs, j.Qm, j.rv, self._softbuffer(j), res[i].data.ctypes.data
+        if dl:
+            self.dl.decode_tbs(t_dl, False, self.max_iterations, submit_only=True)
+        # ---- uplink subframes: UCI extraction + de-interleaving into device memory, then decode from there
+        t_ul = make_tbs(len(ul))
+        if ul:
+            need = sum(len(jobs[i].llr) * 2 + 64 for i in ul)
+            if need > self._g_cap:
+                if self._g_dev:
+                    self.ul.device_free(self._g_dev)
+                self._g_dev, self._g_cap = self.ul.device_alloc(need), need
+            arr = (Ulsch * len(ul))()
+            off = 0
+            for k, i in enumerate(ul):
+                j = jobs[i]
+                q = np.ascontiguousarray(j.llr, np.int16)
+                qa, qr, qc = j.q_prime
+                H = len(q) // j.Qm
+                r = res[i]
+                r.ack_llr, r.ri_llr, r.cqi_llr = np.zeros(qa * j.Qm, np.int16), np.zeros(qr * j.Qm, np.int16), np.zeros(qc * j.Qm, np.int16)
+                r.data = np.zeros(j.tbs // 8 + 8, np.uint8)
+                keep.append(q)
+                a = arr[k]
+                a.q_bits, a.Qm, a.H_prime_total, a.N_pusch_symbs, a.g_bits = q.ctypes.data, j.Qm, H, j.n_pusch_symbs, self._g_dev + off
+                a.Q_prime_ack, a.Q_prime_ri, a.Q_prime_cqi = qa, qr, qc
+                a.ack_llr, a.ri_llr, a.cqi_llr = r.ack_llr.ctypes.data, r.ri_llr.ctypes.data, r.cqi_llr.ctypes.data
+                t = t_ul[k]
+                t.e_bits, t.nof_e_bits = self._g_dev + off + qc * j.Qm * 2, (H - qr - qc) * j.Qm  # sch.c:1174-1177
+                t.tbs, t.Qm, t.rv, t.softbuffer, t.data = j.tbs, j.Qm, j.rv, self._softbuffer(j), r.data.ctypes.data
+                off += (len(q) * 2 + 63) // 64 * 64
+            self.ul.ulsch_deinterleave_raw(arr, OUT_DEVICE)
+            self.ul.decode_tbs(t_ul, False, self.max_iterations, flags=IN_DEVICE, submit_only=True)
+        if dl:
+            self.dl.wait()
+        if ul:
+            self.ul.wait()
+        for ts, idx in ((t_dl, dl), (t_ul, ul)):
+            for k, i in enumerate(idx):
+                t, r = ts[k], res[i]
+                r.ret, r.avg_iterations = t.ret, t.avg_iterations
+                r.cb_noi, r.cb_crc = list(t.cb_noi[:t.nof_cb]), list(t.cb_crc[:t.nof_cb])
+        del keep
+        return res

@@ -20,6 +20,10 @@ def test_two_rank_aggregation(tmp_path):
         assert abs(x["ms"] - 20.0) < 1e-9 and abs(x["total"] - 15000) < 1e-9
         assert abs(x["value"] - 15000 / 20e-3 / 1e6) < 1e-12
     assert r[0]["sample"] != r[1]["sample"]  # independent shards
+    # pooled cells: the two ranks' job lists are disjoint, cover all 240 jobs, and a cell never changes rank (HARQ affinity)
+    j0, j1 = [tuple(x) for x in r[0]["jobs"]], [tuple(x) for x in r[1]["jobs"]]
+    assert len(j0) + len(j1) == 240 and not set(j0) & set(j1) and len(set(j0) | set(j1)) == 240
+    assert not {c for c, _, _ in j0} & {c for c, _, _ in j1}
 
 
 def test_reference_arm_other_ranks_exit_quietly():

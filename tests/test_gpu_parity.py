@@ -659,6 +659,7 @@ def test_pusch_symbols_to_transport_block_on_device(port, ctx):
     symbols -> soft demodulation + descrambling -> UCI extraction + de-interleaving -> decode_tb, LLRs never leaving the GPU,
     against the same chain through the oracle"""
     from srsran_b200 import synth
+    from util import ul_interleave_tx
     rng = np.random.default_rng(1105)
     tbs, mod, Qm, L_prb, nsym = 75376, 3, 6, 100, 12
     rows, H = L_prb * 12, L_prb * 12 * nsym
@@ -666,14 +667,7 @@ def test_pusch_symbols_to_transport_block_on_device(port, ctx):
     G = (H - qr - qc) * Qm
     data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
     g_tx = np.concatenate([rng.integers(0, 2, qc * Qm, dtype=np.uint8), port.encode_tb(tbs, Qm, 0, G, data)])
-    # channel interleaver of TS 36.212 5.2.2.8: row by row over the positions that hold no RI, then ACK overwrites
-    pos = (np.arange(rows)[:, None, None] * Qm + np.arange(nsym)[None, :, None] * rows * Qm + np.arange(Qm)[None, None, :]).reshape(-1)
-    ri_pos = np.concatenate([port.ulsch_uci_position(True, i, Qm, H, nsym) + np.arange(Qm) for i in range(qr)])
-    ack_pos = np.concatenate([port.ulsch_uci_position(False, i, Qm, H, nsym) + np.arange(Qm) for i in range(qa)])
-    q_tx = np.zeros(H * Qm, np.uint8)
-    q_tx[pos[~np.isin(pos, ri_pos)]] = g_tx
-    q_tx[ri_pos] = rng.integers(0, 2, len(ri_pos), dtype=np.uint8)
-    q_tx[ack_pos] = rng.integers(0, 2, len(ack_pos), dtype=np.uint8)
+    q_tx = ul_interleave_tx(port, rng, g_tx, Qm, rows, nsym, qa, qr)
     scr = port.sequence_bytes((0x46 << 14) + (5 << 9) + 1, H * Qm)
     sym = synth.lte_modulate(q_tx ^ np.unpackbits(scr)[:H * Qm], mod)
     sym = (sym + 0.07 * (rng.standard_normal(H) + 1j * rng.standard_normal(H))).astype(np.complex64)
@@ -720,3 +714,94 @@ def test_ulsch_rejects_invalid_descriptors(ctx):
         with pytest.raises(b.B200Error):
             call(**bad)
     assert ctx.ulsch_deinterleave([]) == []
+
+
+# ----------------------------------------------------------------------------------------- BASELINE config 5 / SURVEY 8e: pooled cells
+def test_pooled_cells_with_harq(port):
+    """srsran_b200.pool.CellPool: downlink-shaped and uplink subframes of several cells over a run of TTIs, cells sharded over
+    two ranks (both on this GPU), HARQ processes with device-resident soft buffers -- failed transport blocks are
+    retransmitted with the next redundancy version into the same process -- against the oracle walking the same job
+    sequence with its own soft buffers"""
+    from srsran_b200.pool import CellPool, Job, owner_of, partition
+    from util import ul_interleave_tx
+    rng = np.random.default_rng(2005)
+    world = 2
+    pools = [CellPool(rank=r, world=world, device=0) for r in range(world)]
+    grants = {  # per cell: (dl: tbs, Qm, G, sigma), (ul: tbs, Qm, L_prb, nsym, q_prime, sigma)
+        0: ((15264, 4, 20000, 0.74), (9912, 4, 25, 12, (23, 8, 10), 0.62)),
+        1: ((75376, 6, 90000, 0.93), (5160, 2, 25, 12, (12, 4, 5), 1.05)),
+        2: ((2216, 2, 7000, 1.45), (75376, 6, 100, 12, (36, 20, 57), 0.83)),
+        3: ((31704, 6, 40000, 0.80), (3624, 2, 25, 10, (28, 3, 5), 0.95)),
+    }
+    rvs = (0, 2, 3, 1)
+    state = {}   # (cell, kind, pid) -> [data, transmissions so far]
+    orc_sb = {}
+    n_retx = n_fail_first = n_jobs = 0
+    for tti in range(10):
+        jobs = []
+        for cell, (gdl, gul) in grants.items():
+            for kind in ("dl", "ul"):
+                pid = tti % 4
+                key = (cell, kind, pid)
+                st = state.get(key)
+                tbs = gdl[0] if kind == "dl" else gul[0]
+                if st is None:
+                    st = state[key] = [rng.integers(0, 256, tbs // 8, dtype=np.uint8), 0]
+                data, ntx = st
+                rv = rvs[ntx]
+                if kind == "dl":
+                    _, Qm, G, sigma = gdl
+                    llr = bpsk_awgn_llr(rng, port.encode_tb(tbs, Qm, rv, G, data), 100, sigma, np.int16)
+                    jobs.append(Job(cell, tti, "dl", pid, rv, ntx == 0, tbs, Qm, llr))
+                else:
+                    _, Qm, L_prb, nsym, (qa, qr, qc), sigma = gul
+                    rows = L_prb * 12
+                    G = (rows * nsym - qr - qc) * Qm
+                    g_tx = np.concatenate([rng.integers(0, 2, qc * Qm, dtype=np.uint8), port.encode_tb(tbs, Qm, rv, G, data)])
+                    llr = bpsk_awgn_llr(rng, ul_interleave_tx(port, rng, g_tx, Qm, rows, nsym, qa, qr), 100, sigma, np.int16)
+                    jobs.append(Job(cell, tti, "ul", pid, rv, ntx == 0, tbs, Qm, llr, nsym, (qa, qr, qc)))
+        # every rank decodes its own cells; together they cover the batch exactly once
+        parts = [partition(jobs, r, world) for r in range(world)]
+        assert sorted(id(j) for p in parts for j in p) == sorted(id(j) for j in jobs)
+        results = {}
+        for r in range(world):
+            assert all(owner_of(j.cell, world) == r for j in parts[r])
+            for j, res in zip(parts[r], pools[r].decode(parts[r])):
+                results[id(j)] = res
+        for j in jobs:
+            key = (j.cell, j.kind, j.pid)
+            res = results[id(j)]
+            if key not in orc_sb:
+                orc_sb[key] = port.softbuffer_new()
+            if j.new_data:
+                port.softbuffer_reset(orc_sb[key])
+            e = j.llr
+            if j.kind == "ul":
+                qa, qr, qc = j.q_prime
+                rc0, g, ack, ri, _ = port.ulsch_deinterleave(j.llr, j.Qm, j.n_pusch_symbs, qa, qr)
+                assert rc0 == 0 and (res.ack_llr == ack).all() and (res.ri_llr == ri).all() and (res.cqi_llr == g[:qc * j.Qm]).all()
+                e = g[qc * j.Qm:(len(j.llr) // j.Qm - qr) * j.Qm].copy()
+            rc, want, nit, avg, crc = port.decode_tb(orc_sb[key], j.tbs, j.Qm, j.rv, e, 8)
+            C_ = len(res.cb_noi)
+            assert res.ret == rc, (tti, key, res.ret, rc)
+            assert (res.data[:j.tbs // 8 + 3] == want[:j.tbs // 8 + 3]).all(), (tti, key)
+            assert res.cb_noi == nit[:C_].tolist() and res.cb_crc == crc[:C_].tolist(), (tti, key)
+            assert abs(res.avg_iterations - avg) < 1e-6
+            n_jobs += 1
+            st = state[key]
+            if rc == 0:
+                assert (res.data[:j.tbs // 8] == st[0]).all()
+                del state[key]
+            else:
+                n_fail_first += st[1] == 0
+                st[1] += 1
+                n_retx += 1
+                if st[1] == 4:
+                    del state[key]
+    assert n_jobs == 80 and n_fail_first >= 8 and n_retx >= 8, (n_jobs, n_fail_first, n_retx)  # the run really exercises HARQ combining
+    with pytest.raises(b.B200Error):
+        pools[0].decode([Job(1, 0, "dl", 0, 0, True, 2216, 2, np.zeros(7000, np.int16))])  # cell 1 belongs to rank 1
+    for sb in orc_sb.values():
+        port.softbuffer_del(sb)
+    for p in pools:
+        p.close()

@@ -70,3 +70,18 @@ def ul_qprime(port, grant):
     _, seg = port.cbsegm(tbs)
     K_segm = seg["C1"] * seg["K1"] + seg["C2"] * seg["K2"]
     return port.ulsch_qprime(K_segm, L_prb, nof_symb, nof_ack, ri_len, UL_CQI_LEN[cqi], I_ack, I_ri, I_cqi)
+
+
+def ul_interleave_tx(port, rng, g_tx, Qm, rows, nsym, qa, qr):
+    """Transmit side of the UL-SCH channel interleaver (TS 36.212 5.2.2.8) for the tests: g_tx (CQI + UL-SCH bits, one per
+    element) is written row by row over the positions that hold no RI, RI positions and then ACK positions get random bits.
+    Positions come from the oracle's restatement of uci.c:551-605.  Returns the H' * Qm interleaved bits."""
+    H = rows * nsym
+    pos = (np.arange(rows)[:, None, None] * Qm + np.arange(nsym)[None, :, None] * rows * Qm + np.arange(Qm)[None, None, :]).reshape(-1)
+    ri_pos = np.concatenate([port.ulsch_uci_position(True, i, Qm, H, nsym) + np.arange(Qm) for i in range(qr)]) if qr else np.zeros(0, np.int64)
+    ack_pos = np.concatenate([port.ulsch_uci_position(False, i, Qm, H, nsym) + np.arange(Qm) for i in range(qa)]) if qa else np.zeros(0, np.int64)
+    q_tx = np.zeros(H * Qm, np.uint8)
+    q_tx[pos[~np.isin(pos, ri_pos)]] = g_tx
+    q_tx[ri_pos] = rng.integers(0, 2, len(ri_pos), dtype=np.uint8)
+    q_tx[ack_pos] = rng.integers(0, 2, len(ack_pos), dtype=np.uint8)
+    return q_tx
