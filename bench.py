@@ -664,13 +664,122 @@ def run_ours(args):
     return 0
 
 
+# ----------------------------------------------------------------------------------------------- pooled cells (config 5)
+def run_c5(args):
+    """BASELINE config 5: the subframes of `--cells` cells, one downlink-shaped transport block (C2 shape) and one uplink
+    subframe (100 PRB 64QAM with ACK, RI and CQI) per cell and TTI, sharded over the ranks by cell (HARQ affinity),
+    decoded through srsran_b200.pool.CellPool from pinned host buffers.  A tenth of the downlink HARQ processes
+    alternate between a first transmission that fails and the retransmission that combines with it."""
+    rank, world, local, barrier, vmax, vsum = dist_setup(args.gpus)
+    import srsran_b200 as b
+    from srsran_b200 import synth
+    from srsran_b200.pool import CellPool, Job, owner_of
+    rng = np.random.default_rng(shard_seed(rank))
+    # two pools per GPU, each with half of the rank's cells: while one pool's batch decodes, the other's is copied and planned
+    pools = [CellPool(rank, world, local) for _ in range(2)]
+    cells = [c for c in range(args.cells) if owner_of(c, world) == rank]
+    tbs, Qm, G = 75376, 6, 90000
+    rows, nsym, qp = 1200, 12, (36, 20, 57)
+    n_q = rows * nsym * Qm
+    G_ul = (rows * nsym - qp[1] - qp[2]) * Qm
+    base = 8
+    data = rng.integers(0, 256, (base, tbs // 8), dtype=np.uint8)
+    pin_dl = b.PinnedArray((base, G), np.int16)
+    pin_hard = b.PinnedArray((2, G), np.int16)
+    pin_ul = b.PinnedArray((base, n_q), np.int16)
+    pin_dl.array[:] = synth.awgn_llr(rng, synth.encode_tbs(data, tbs, Qm, G, 0), 100.0, 0.44, np.int16)
+    pin_hard.array[0] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 0), 100.0, 0.95, np.int16)[0]
+    pin_hard.array[1] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 2), 100.0, 0.95, np.int16)[0]
+    g_tx = np.concatenate([rng.integers(0, 2, (base, qp[2] * Qm), dtype=np.uint8), synth.encode_tbs(data, tbs, Qm, G_ul, 0)], axis=1)
+    pin_ul.array[:] = synth.awgn_llr(rng, synth.ul_interleave(rng, g_tx, Qm, rows, nsym, qp[0], qp[1]), 100.0, 0.33, np.int16)
+    n_pid = 8
+    batches = []  # [pool][phase] -> (jobs, prepared batch)
+    for pi, pool in enumerate(pools):
+        per_phase = []
+        for phase in range(2):  # the hard processes alternate: first transmission (fails) / retransmission (combines)
+            jobs = []
+            for c in cells[pi::2]:
+                for pid in range(n_pid):
+                    k = (c * n_pid + pid) % base
+                    if (c * n_pid + pid) % 10 == 3:
+                        jobs.append(Job(c, pid, "dl", pid, 2 * phase, phase == 0, tbs, Qm, pin_hard.ptr + phase * G * 2, n_llr=G))
+                    else:
+                        jobs.append(Job(c, pid, "dl", pid, 0, True, tbs, Qm, pin_dl.ptr + k * G * 2, n_llr=G))
+                    jobs.append(Job(c, pid, "ul", pid, 0, True, tbs, Qm, pin_ul.ptr + k * n_q * 2, nsym, qp, n_llr=n_q))
+            per_phase.append((jobs, pool.prepare(jobs)))
+        batches.append(per_phase)
+    sampler = ClockSampler(local)
+    sampler.start()
+    in_flight = [None, None]
+    tally = [0, 0]  # decoded bits, kernel launches
+
+    def retire(pi):
+        bt = in_flight[pi]
+        if bt is None:
+            return
+        pools[pi].wait(bt, collect=False)
+        tally[0] += tbs * (sum(1 for k in range(len(bt.dl)) if bt.t_dl[k].ret == 0) + sum(1 for k in range(len(bt.ul)) if bt.t_ul[k].ret == 0))
+        tally[1] += pools[pi].dl.last_launches() + pools[pi].ul.last_launches()
+        in_flight[pi] = None
+
+    def step(i):
+        for pi in range(2):
+            retire(pi)
+            if batches[pi][0][0]:
+                in_flight[pi] = batches[pi][i % 2][1]
+                pools[pi].submit(in_flight[pi])
+
+    for i in range(2 * max(1, args.warmup // 2)):
+        step(i)
+    retire(0)
+    retire(1)
+    barrier()
+    sampler.mark()
+    tally[0] = tally[1] = 0
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    retire(0)
+    retire(1)
+    bits, launches = tally
+    dt = vmax(time.perf_counter() - t0)
+    clocks = sampler.stop()
+    barrier()
+    total = vsum(bits)
+    my_jobs = batches[0][0][0] + batches[1][0][0]
+    n_jobs = vsum(len(my_jobs))
+    if rank == 0:
+        val = total / dt / 1e6
+        h2d = sum((j.n_llr * 2) for j in my_jobs)
+        line = {"metric": "turbo_decoded_mbps", "value": val, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16",
+                "data": "synthetic",
+                "config": {"workload": "c5-pooled: %d cells x %d TTIs per step (one 75376-bit downlink-shaped block + one 100-PRB 64QAM uplink subframe with "
+                                       "ACK/RI/CQI per cell and TTI), cells sharded over %d rank(s), device-resident HARQ soft buffers, 10%% of the downlink "
+                                       "processes alternate failing first transmission / combining retransmission" % (args.cells, n_pid, world),
+                           "l2": "inputs of a step (%d MB over all ranks) larger than the 126 MB L2" % (n_jobs * G * 2 // 1000000),
+                           "parallelism": "cells sharded x%d, no collective" % world, "note": "host-fed only: value == e2e (wall clock, max over ranks)"},
+                "clocks": clocks, "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my_jobs) * (tbs // 8 + 6)},
+                "gpu_launches": int(launches), "decoded_tb_fraction": total / (n_jobs * tbs * args.steps)}
+        print(json.dumps(line))
+    for pi, pool in enumerate(pools):
+        for _, bt in batches[pi]:
+            pool.release(bt)
+        pool.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c4"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c4", "c5"])
+    ap.add_argument("--cells", type=int, default=20, help="cells of the pooled workload (c5), sharded over the ranks")
     ap.add_argument("--ncb", type=int, default=18944, help="code blocks per step per GPU (c1); 18944 = 4 full waves of 148 CTAs x 32 blocks")
     ap.add_argument("--ntb", type=int, default=1000, help="transport blocks per step per GPU (c2/c4)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
@@ -686,6 +795,8 @@ def main():
         args.engines = 4 if args.workload == "c1" else 6
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "c5":
+        return run_c5(args)
     return run_ours(args)
 
 

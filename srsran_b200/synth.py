@@ -141,3 +141,29 @@ def lte_modulate(bits, mod):
     re = (1 - 2 * b_[:, 0]) * amp[ii]
     im = (1 - 2 * b_[:, 1]) * amp[qq]
     return ((re + 1j * im) / norm).astype(np.complex64)
+
+
+# ---------------------------------------------------------------------------------------------- PUSCH multiplexing (inputs only)
+def ul_uci_positions(is_ri, n, Qm, H_prime_total, n_pusch_symbs):
+    """first q_bits position of coded ACK / RI symbols 0..n-1 (TS 36.212 5.2.2.8; reference: uci.c:551-605)"""
+    rows = H_prime_total // n_pusch_symbs
+    norm = n_pusch_symbs > 10
+    cols = np.array(([1, 4, 7, 10] if norm else [0, 3, 5, 8]) if is_ri else ([2, 3, 8, 9] if norm else [1, 2, 6, 7]))
+    r = np.arange(n)
+    return (rows - 1 - r // 4) * Qm + rows * cols[(3 * r) % 4] * Qm
+
+
+def ul_interleave(rng, g_bits, Qm, rows, n_pusch_symbs, q_ack, q_ri):
+    """UL-SCH channel interleaver, transmit side: g_bits (CQI + UL-SCH bits, (M, n)) row by row over the positions without RI;
+    RI and then ACK positions carry random bits.  Returns (M, rows * n_pusch_symbs * Qm) bits in transmission order."""
+    g_bits = np.atleast_2d(g_bits)
+    H = rows * n_pusch_symbs
+    k = np.arange(Qm)
+    pos = (np.arange(rows)[:, None, None] * Qm + np.arange(n_pusch_symbs)[None, :, None] * rows * Qm + k[None, None, :]).reshape(-1)
+    ri_pos = (ul_uci_positions(True, q_ri, Qm, H, n_pusch_symbs)[:, None] + k).reshape(-1)
+    ack_pos = (ul_uci_positions(False, q_ack, Qm, H, n_pusch_symbs)[:, None] + k).reshape(-1)
+    q = np.zeros((g_bits.shape[0], H * Qm), np.uint8)
+    q[:, pos[~np.isin(pos, ri_pos)]] = g_bits
+    q[:, ri_pos] = rng.integers(0, 2, (g_bits.shape[0], len(ri_pos)), dtype=np.uint8)
+    q[:, ack_pos] = rng.integers(0, 2, (g_bits.shape[0], len(ack_pos)), dtype=np.uint8)
+    return q
