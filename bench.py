@@ -688,8 +688,8 @@ def run_c5(args):
     pin_hard = b.PinnedArray((2, G), np.int16)
     pin_ul = b.PinnedArray((base, n_q), np.int16)
     pin_dl.array[:] = synth.awgn_llr(rng, synth.encode_tbs(data, tbs, Qm, G, 0), 100.0, 0.40, np.int16)
-    pin_hard.array[0] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 0), 100.0, 0.95, np.int16)[0]
-    pin_hard.array[1] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 2), 100.0, 0.95, np.int16)[0]
+    pin_hard.array[0] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 0), 100.0, 0.56, np.int16)[0]
+    pin_hard.array[1] = synth.awgn_llr(rng, synth.encode_tbs(data[:1], tbs, Qm, G, 2), 100.0, 0.56, np.int16)[0]
     g_tx = np.concatenate([rng.integers(0, 2, (base, qp[2] * Qm), dtype=np.uint8), synth.encode_tbs(data, tbs, Qm, G_ul, 0)], axis=1)
     pin_ul.array[:] = synth.awgn_llr(rng, synth.ul_interleave(rng, g_tx, Qm, rows, nsym, qp[0], qp[1]), 100.0, 0.30, np.int16)
     n_pid = 8

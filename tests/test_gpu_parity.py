@@ -805,3 +805,33 @@ def test_pooled_cells_with_harq(port):
         port.softbuffer_del(sb)
     for p in pools:
         p.close()
+
+
+def test_ulsch_deinterleave_device_buffers_stay_in_bounds(port, ctx):
+    """device-resident in and out (SRSLTE_B200_IN_DEVICE | OUT_DEVICE) with sentinel-filled guard bands around every g_bits
+    array and after the unwritten RI tail: nothing outside [0, (H' - Q'_ri) * Qm) is touched"""
+    rng = np.random.default_rng(77)
+    geo = [(6, 12, 1200, 36, 20, 57), (6, 12, 1200, 0, 0, 0), (2, 10, 300, 28, 3, 5), (4, 11, 36, 7, 2, 0), (4, 12, 129, 516, 516, 40), (2, 9, 1, 4, 4, 0),
+           (8, 12, 65, 3, 9, 700), (6, 12, 128, 1, 1, 1), (2, 12, 127, 0, 5, 0)]
+    guard = 256  # int16 elements
+    ul = b.make_ulschs(len(geo))
+    bufs = []
+    for i, (Qm, nsym, rows, qa, qr, qc) in enumerate(geo):
+        n = rows * nsym * Qm
+        q = rng.integers(-32768, 32768, n).astype(np.int16)
+        d_q = ctx.device_alloc(n * 2 + 64)
+        d_g = ctx.device_alloc((n + 2 * guard) * 2)
+        ctx.h2d(d_q, q)
+        ctx.h2d(d_g, np.full(n + 2 * guard, 31111, np.int16))
+        ul[i].q_bits, ul[i].Qm, ul[i].H_prime_total, ul[i].N_pusch_symbs, ul[i].g_bits = d_q, Qm, rows * nsym, nsym, d_g + guard * 2
+        ul[i].Q_prime_ack, ul[i].Q_prime_ri, ul[i].Q_prime_cqi = qa, qr, qc
+        bufs.append((q, d_q, d_g, n))
+    ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
+    for (Qm, nsym, rows, qa, qr, qc), (q, d_q, d_g, n) in zip(geo, bufs):
+        out = np.zeros(n + 2 * guard, np.int16)
+        ctx.d2h(out, d_g)  # (memcpy_d2h drains the context's stream first)
+        rc, g, _, _, _ = port.ulsch_deinterleave(q, Qm, nsym, qa, qr, g_fill=31111)
+        assert rc == 0 and (out[guard:guard + n] == g).all(), (Qm, nsym, rows, qa, qr, qc)
+        assert (out[:guard] == 31111).all() and (out[guard + n:] == 31111).all()
+        ctx.device_free(d_q)
+        ctx.device_free(d_g)

@@ -135,13 +135,15 @@ def test_ulsch_kernel_index_arithmetic(port):
                     qbuf = rng.integers(-32768, 32768, H * Qm + 16).astype(np.int16)
                     off = (-qbuf.ctypes.data % 16) // 2 + (2 if n % 3 == 0 else 0)  # 16-byte aligned (128-bit path) or not
                     q = qbuf[off:off + H * Qm]
-                    g = np.full(H * Qm, 777, np.int16)
-                    uci = np.zeros((qa + qr + qc) * Qm + 2, np.int16)
+                    gbuf = np.full(H * Qm + 128, 777, np.int16)  # guard bands on both sides: a stray store would show
+                    g = gbuf[64:64 + H * Qm]
+                    uci = np.full((qa + qr + qc) * Qm + 64, 555, np.int16)
                     grid = int(rng.integers(1, 4))
                     L.emul_ulsch(_p(q), C.c_uint32(Qm), C.c_uint32(H), C.c_uint32(nsym), C.c_uint32(qa), C.c_uint32(qr), C.c_uint32(qc), _p(g), _p(uci),
                                  C.c_uint32(grid))
                     rc, g_o, ack, ri, _ = port.ulsch_deinterleave(q, Qm, nsym, qa, qr, g_fill=777)
                     assert rc == 0 and (g == g_o).all(), (Qm, nsym, rows, qa, qr, qc)
+                    assert (gbuf[:64] == 777).all() and (gbuf[64 + H * Qm:] == 777).all() and (uci[(qa + qr + qc) * Qm:] == 555).all()
                     assert (uci[:qa * Qm] == ack).all() and (uci[qa * Qm:(qa + qr) * Qm] == ri).all()
                     assert (uci[(qa + qr) * Qm:(qa + qr + qc) * Qm] == g_o[:qc * Qm]).all()
                     n += 1
