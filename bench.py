@@ -329,7 +329,7 @@ def run_ours(args):
         K, nit = 6144, 4
         ncb = args.ncb
         stride = 3 * K + 12
-        pin_in = b.PinnedArray((ncb, stride), np.int16)
+        pin_in = b.PinnedArray((ncb, stride), np.int16, write_combined=args.wc_inputs)
         pin_out = b.PinnedArray((ncb, K // 8), np.uint8)
         llr, _ = make_c1(rng, ncb, K, host_out=pin_in.array)
         d_llr = ctx.device_alloc(llr.nbytes)
@@ -363,7 +363,7 @@ def run_ours(args):
                 e.tdec_batch_submit(pin_in.array[lo:hi].ctypes.data, pin_out.array[lo:hi].ctypes.data, K, hi - lo, stride, 16, nit)
 
         def cpu_base():
-            return cpu_baseline_c1(llr[:min(ncb, 2048)], K, nit, args.cpu_seconds)
+            return cpu_baseline_c1(np.array(llr[:min(ncb, 2048)]), K, nit, args.cpu_seconds)  # (a copy in ordinary memory)
     else:
         cfg = TB_CFG[args.workload]
         ntb = args.ntb
@@ -788,6 +788,7 @@ def main():
     ap.add_argument("--engines", type=int, default=0,
                     help="engines (streams) per GPU the batches / end-to-end chunks rotate over (default: 4 for c1, 6 for the early-stop workloads "
                          "whose last half-iterations run nearly empty and overlap with other batches)")
+    ap.add_argument("--wc-inputs", type=int, default=0, help="c1: allocate the host LLR staging buffer write-combined (srslte_b200_host_alloc_wc)")
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks one end-to-end step is split into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

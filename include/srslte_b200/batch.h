@@ -40,6 +40,9 @@ SRSLTE_B200_API const char* srslte_b200_last_error(void);
 
 /* Pinned host memory helpers (page-locked buffers make the H2D/D2H copies asynchronous). */
 SRSLTE_B200_API void* srslte_b200_host_alloc(uint64_t bytes);
+/* write-combined page-locked memory for INPUT staging (LLRs the host only writes, sequentially): the device reads it
+ * without snooping the CPU caches; CPU reads from it are very slow.  Free with srslte_b200_host_free. */
+SRSLTE_B200_API void* srslte_b200_host_alloc_wc(uint64_t bytes);
 SRSLTE_B200_API void  srslte_b200_host_free(void* p);
 SRSLTE_B200_API void* srslte_b200_device_alloc(uint64_t bytes);
 SRSLTE_B200_API void  srslte_b200_device_free(void* p);

@@ -91,6 +91,8 @@ def lib():
         L.srslte_b200_last_error.restype = C.c_char_p
         L.srslte_b200_host_alloc.restype = C.c_void_p
         L.srslte_b200_host_alloc.argtypes = [C.c_uint64]
+        L.srslte_b200_host_alloc_wc.restype = C.c_void_p
+        L.srslte_b200_host_alloc_wc.argtypes = [C.c_uint64]
         L.srslte_b200_host_free.argtypes = [C.c_void_p]
         L.srslte_b200_device_alloc.restype = C.c_void_p
         L.srslte_b200_device_alloc.argtypes = [C.c_uint64]
@@ -167,9 +169,9 @@ def _ptr(a):
 class PinnedArray:
     """numpy view over page-locked host memory (srslte_b200_host_alloc)"""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
         self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
-        self.ptr = lib().srslte_b200_host_alloc(max(self.nbytes, 16))
+        self.ptr = (lib().srslte_b200_host_alloc_wc if write_combined else lib().srslte_b200_host_alloc)(max(self.nbytes, 16))
         if not self.ptr:
             raise B200Error("pinned host allocation failed")
         buf = (C.c_uint8 * max(self.nbytes, 16)).from_address(self.ptr)

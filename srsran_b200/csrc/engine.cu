@@ -1603,6 +1603,13 @@ void* srslte_b200_host_alloc(uint64_t bytes)
     return nullptr;
   return p;
 }
+void* srslte_b200_host_alloc_wc(uint64_t bytes)
+{
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess)
+    return nullptr;
+  return p;
+}
 void  srslte_b200_host_free(void* p) { cudaFreeHost(p); }
 void* srslte_b200_device_alloc(uint64_t bytes)
 {
