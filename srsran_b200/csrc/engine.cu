@@ -176,6 +176,8 @@ int Engine::create(Engine** out, int device)
   e->plan_ptr = new Plan();
   if (const char* ev = getenv("SRSLTE_B200_FAST16"))
     e->opt_fast16 = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_LATENCY"))
+    e->opt_latency = atoi(ev) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventCreate(&e->ev_end));
@@ -400,6 +402,20 @@ static cudaError_t launch_map_f16_mode(MapArgs a, int n_slots, cudaStream_t st)
   kern<<<blocks, NT, smem, st>>>(a);
   return cudaGetLastError();
 }
+// Latency-shaped launch (map_lat.cuh): one 4-warp CTA per group of G slots; a.ck_slots = vectors per pass and CTA
+template <class P, int N>
+static cudaError_t launch_map_lat(MapArgs a, int n_slots, uint32_t n_iter, cudaStream_t st)
+{
+  constexpr int T = N / 2, G = 32 / T;
+  const int     groups = (n_slots + G - 1) / G;
+  const size_t  smem   = (size_t)4 * LatLay<T>::kWarpWords * 4;
+  void (*kern)(MapArgs) = (n_iter & 1) ? k_map_lat<P, N, 2> : (n_iter ? k_map_lat<P, N, 1> : k_map_lat<P, N, 0>);
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess)
+    return e;
+  kern<<<groups, 128, smem, st>>>(a);
+  return cudaGetLastError();
+}
 // Geometry: 128-thread CTAs, three per SM, three staging stages -- the best of the geometries measured
 // (profiles/README.md; four CTAs per SM fit for the two-plane variants but run no faster: DRAM pressure grows with them)
 template <class P, int N>
@@ -608,6 +624,7 @@ int Engine::run(Plan& p)
   CUDA_OK(cudaGetLastError());
 
   // ---- global scratch for the beta checkpoints of the windowed kernels
+  bool lat16 = false;
   {
     size_t need = 0;
     for (int c = 0; c < 4; c++) {
@@ -624,6 +641,12 @@ int Engine::run(Plan& p)
       // whole CTAs (128 threads for k_map_f16, 256 for k_map_win)
       const size_t slots = (size_t)(cls[c].max_w + 7) / 8 + 2;
       need = std::max(need, slots * ((size_t)blocks * nt + 256) * 8);
+      // latency-shaped kernel (int16, 16 lanes): when the groups of the class leave most SMs empty, one 4-warp CTA per group
+      // with every beta and alpha vector in scratch (2 x (W + 2) KB per group)
+      const int groups = (cls[c].n_slots + 3) / 4;
+      lat16 = c == 1 && opt_fast16 && opt_latency && groups <= num_sms;
+      if (lat16)
+        need = std::max(need, (size_t)groups * 2 * (size_t)(cls[c].max_w + 2) * 256);
     }
     if (need && d_ckscratch.reserve(need))
       return SRSLTE_B200_ERROR;
@@ -649,7 +672,13 @@ int Engine::run(Plan& p)
         a.mode = 1 | skip_post;
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
-        e = c == 0 ? launch_map_f16<Fast16, 8>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16>(a, ns, n_it, stream);
+        if (c == 1 && lat16) {
+          a.ck_slots = cls[c].max_w + 2;
+          e = launch_map_lat<Fast16, 16>(a, ns, n_it, stream);
+          a.ck_slots = 0;
+        } else {
+          e = c == 0 ? launch_map_f16<Fast16, 8>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16>(a, ns, n_it, stream);
+        }
         CUDA_OK(e);
         last_launches++;
         a.mode = 2;
@@ -1771,6 +1800,10 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (!strcmp(name, "fast16")) {
     ctx->e->opt_fast16 = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "latency")) {
+    ctx->e->opt_latency = value != 0;
     return 0;
   }
   return SRSLTE_B200_ERROR_INVALID_INPUTS;

@@ -95,6 +95,7 @@ public:
   DevBuf<uint8_t>  d_cbout, d_in, d_tbout;
   DevBuf<int>      d_lists, d_gmax;
   bool             opt_fast16 = true; // try the native packed-instruction path first (exact replay on range alarm)
+  bool             opt_latency = true; // small batches: the 4-warp latency-shaped MAP kernel (map_lat.cuh) instead of one warp per group
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch;
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;

@@ -4,6 +4,8 @@
 //   k_dematch          srslte_rm_turbo_rx_lut[_8bit] for the host-pointer compatibility symbol
 //   k_prepare          extract_input / extract_input_tail_sb  (win.h:880-923, iter.h:59-69, gen.c:238-258)
 //   k_map_f16          tdec_win*_dec + half-iteration glue, int16 (Fast16) and int8 (Sat8)  -> map_f16.cuh
+//   k_map_lat          the same integers as k_map_f16 for single-subframe batches: beta and alpha passes on two warps at once,
+//                      LLRs + glue spread over four  -> map_lat.cuh
 //   k_map_win          the same in exact saturating int16 (replay of blocks the Fast16 range monitor flags; fast16 off)
 //   k_map_gen          tdec_gen_dec + glue                    (turbodecoder_gen.c:58-236)
 //   k_decide_crc       tdec_*_decision_byte + srslte_crc_checksum_byte + early stop (win.h:925-993, crc.c:143-157,
@@ -789,6 +791,7 @@ __device__ __forceinline__ void tma_tile4(unsigned dst_s, const CUtensorMap* tm,
 
 } // namespace b200
 #include "map_f16.cuh"
+#include "map_lat.cuh"
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------ generic MAP
