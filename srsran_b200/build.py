@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsrslte_fec_b200.so")
 SOURCES = ["engine.cu", "lte_tables.cpp"]
-DEPS = ["engine.cu", "engine.h", "kernels.cuh", "map_core.cuh", "map_f16.cuh", "arith.cuh", "api.inc", "lte_tables.cpp", "lte_tables.h",
-        "lte_qpp_table.h", "../../include/srslte_b200/batch.h", "../../include/srslte_b200/fec.h"]
+DEPS = sorted(f for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc", ".cpp"))) + \
+    ["../../include/srslte_b200/batch.h", "../../include/srslte_b200/fec.h"]  # every source and header: a stale library is worse than a slow build
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-fvisibility=hidden",
          "-shared", "-cudart", "static"]

@@ -332,6 +332,24 @@ static void map_geometry(int n_slots, int* nt, int* blocks)
   *blocks = (warps + (*nt / 32) - 1) / (*nt / 32);
 }
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (kernel, device) instead of before every launch: the call sits
+// on the host-side critical path of small batches
+static cudaError_t smem_attr_once(const void* kern, int smem)
+{
+  static std::mutex                              mu;
+  static std::vector<std::pair<const void*, int>> done;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  for (auto& d : done)
+    if (d.first == kern && d.second == dev)
+      return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e == cudaSuccess)
+    done.emplace_back(kern, dev);
+  return e;
+}
+
 template <class P, int N, int L = kSegLen, int NT = kMapThreads, int MINB = 1>
 static cudaError_t launch_map(MapArgs a, int n_slots, int max_w, cudaStream_t st)
 {
@@ -343,7 +361,7 @@ static cudaError_t launch_map(MapArgs a, int n_slots, int max_w, cudaStream_t st
   // checkpoint, per thread
   const size_t smem = (size_t)NT * 3 * (L * 4 + 8) * 4; // StagedSrc::kStages buffers
   auto         kern = k_map_win<P, N, L, NT, MINB>;
-  cudaError_t  e    = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t  e    = smem_attr_once((const void*)kern, (int)smem);
   if (e != cudaSuccess)
     return e;
   kern<<<blocks, NT, smem, st>>>(a);
@@ -396,7 +414,7 @@ static cudaError_t launch_map_f16_mode(MapArgs a, int n_slots, cudaStream_t st)
   const int     blocks = (warps + (NT / 32) - 1) / (NT / 32);
   const size_t  smem   = (size_t)(NT / 32) * F16Lay<T, STAGES, MODE == 1 ? 3 : 2>::kWarpWords * 4;
   auto          kern   = k_map_f16<P, N, MODE, NT, MINB, STAGES>;
-  cudaError_t   e      = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t   e      = smem_attr_once((const void*)kern, (int)smem);
   if (e != cudaSuccess)
     return e;
   kern<<<blocks, NT, smem, st>>>(a);
@@ -410,7 +428,7 @@ static cudaError_t launch_map_lat(MapArgs a, int n_slots, uint32_t n_iter, cudaS
   const int     groups = (n_slots + G - 1) / G;
   const size_t  smem   = (size_t)4 * LatLay<T>::kWarpWords * 4;
   void (*kern)(MapArgs) = (n_iter & 1) ? k_map_lat<P, N, 2> : (n_iter ? k_map_lat<P, N, 1> : k_map_lat<P, N, 0>);
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = smem_attr_once((const void*)kern, (int)smem);
   if (e != cudaSuccess)
     return e;
   kern<<<groups, 128, smem, st>>>(a);
@@ -604,20 +622,20 @@ int Engine::run(Plan& p)
   const size_t sb_smem = (3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t);
   if (!dm16.empty()) {
     auto kern = k_dematch_prepare<int16_t>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
     kern<<<(int)dm16.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
     last_launches++;
   }
   if (!dm8.empty()) {
     auto kern = k_dematch_prepare<int8_t>;
-    CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sb_smem));
+    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
     kern<<<(int)dm8.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
     last_launches++;
   }
   if (!plain.empty() && p.prepare) {
     // staging of one code block (3K+12 LLRs) + one padded plane for the transposition into the lane layout
     const size_t prep_smem = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
-    CUDA_OK(cudaFuncSetAttribute(k_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)prep_smem));
+    CUDA_OK(smem_attr_once((const void*)k_prepare, (int)prep_smem));
     k_prepare<<<(int)plain.size(), 256, prep_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
     last_launches++;
   }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
   const int nT  = (W + 7) >> 3;
   const int a0  = (W - kWinOverlap) >> 3;
   const int nAW = nT - a0;
-  const uint64_t pol_first = l2_policy_evict_first(), pol_last = l2_policy_evict_last();
+  const uint64_t pol_first = l2_policy_evict_first();
   auto bar_of = [&](int stage) -> unsigned { return sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * stage); };
   unsigned rd_phase = 0; // bit s = parity the consumer waits for on barrier s (carried over from phase 1 to phase 2)
   auto row = [&](const u32* tb, int i, u32& x, u32& y) {
@@ -117,8 +117,8 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
   auto vec_store = [&](u32* base, int p, const u32 (&v)[8]) {
     if (live) {
       uint4* g = reinterpret_cast<uint4*>(base + (size_t)p * 256) + lane;
-      stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), pol_last);
-      stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), pol_last);
+      g[0]  = make_uint4(v[0], v[1], v[2], v[3]);
+      g[32] = make_uint4(v[4], v[5], v[6], v[7]);
     }
   };
 
