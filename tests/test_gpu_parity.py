@@ -835,3 +835,40 @@ def test_ulsch_deinterleave_device_buffers_stay_in_bounds(port, ctx):
         assert (out[:guard] == 31111).all() and (out[guard + n:] == 31111).all()
         ctx.device_free(d_q)
         ctx.device_free(d_g)
+
+
+# ----------------------------------------------------------------------------------------- both MAP kernels on the same inputs
+def test_latency_option_both_kernels(port, ctx):
+    """Small batches run the latency-shaped k_map_lat by default, so the throughput kernel k_map_f16 would lose its
+    small-case coverage: every case here is decoded twice, with the option "latency" off (k_map_f16) and on (k_map_lat), and
+    both must equal the oracle -- code-block batches of every 16-lane size class incl. partial top tiles (K = 5824, 816,
+    1008) and saturating amplitudes (exact replay), and transport blocks with CRC early stop and HARQ combining."""
+    rng = np.random.default_rng(4848)
+    cb_cases = []
+    for K, amp, nit in ((6144, 300, 4), (6144, 30000, 5), (5824, 2000, 6), (816, 5000, 4), (1008, 700, 5), (2048, 100, 4), (4160, 900, 3), (3136, 32767, 4)):
+        llr = np.stack([random_llr(rng, 3 * (K + 32) + 12, amp, np.int16) for _ in range(5)])
+        hp = port.tdec_new(TDEC_AUTO, False)
+        want = [port.tdec_run_all(hp, llr[i], nit, K)[1] for i in range(5)]
+        port.tdec_del(hp)
+        cb_cases.append((K, nit, llr, want))
+    tb_cases = []
+    for tbs, Qm, G, sigma in ((75376, 6, 90000, 0.46), (75376, 6, 90000, 0.95), (15264, 4, 20000, 0.75), (31704, 6, 40000, 0.5)):
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        tb_cases.append((tbs, Qm, G, [(rv, _tb_inputs(port, rng, tbs, Qm, G, rv, np.int16, 100, sigma, data)[1]) for rv in (0, 2)]))
+    try:
+        for lat in (0, 1):
+            ctx.set_option("latency", lat)
+            for K, nit, llr, want in cb_cases:
+                got = ctx.tdec_batch(llr, K, nit, input_sb=True)
+                for i in range(5):
+                    assert (got[i] == want[i]).all(), (lat, K, i)
+            for tbs, Qm, G, txs in tb_cases:
+                sbp, sbg = port.softbuffer_new(), ctx.softbuffer_create()
+                for rv, llr in txs:
+                    _decode_both(port, ctx, tbs, Qm, rv, llr, 8, sbp, sbg)
+                port.softbuffer_del(sbp)
+                ctx.softbuffer_free(sbg)
+    finally:
+        ctx.set_option("latency", 1)
+    with pytest.raises(b.B200Error):
+        ctx.set_option("no-such-option", 1)
