@@ -642,7 +642,7 @@ int Engine::run(Plan& p)
   CUDA_OK(cudaGetLastError());
 
   // ---- global scratch for the beta checkpoints of the windowed kernels
-  bool lat16 = false;
+  bool cls_lat[4] = {false, false, false, false};
   {
     size_t need = 0;
     for (int c = 0; c < 4; c++) {
@@ -661,9 +661,9 @@ int Engine::run(Plan& p)
       need = std::max(need, slots * ((size_t)blocks * nt + 256) * 8);
       // latency-shaped kernel (int16, 16 lanes): when the groups of the class leave most SMs empty, one 4-warp CTA per group
       // with every beta and alpha vector in scratch (2 x (W + 2) KB per group)
-      const int groups = (cls[c].n_slots + 3) / 4;
-      lat16 = c == 1 && opt_fast16 && opt_latency && groups <= num_sms;
-      if (lat16)
+      const int gsz = 64 / kWinClasses[c].lanes, groups = (cls[c].n_slots + gsz - 1) / gsz;
+      cls_lat[c] = opt_latency && (c >= 2 || opt_fast16) && groups <= num_sms;
+      if (cls_lat[c])
         need = std::max(need, (size_t)groups * 2 * (size_t)(cls[c].max_w + 2) * 256);
     }
     if (need && d_ckscratch.reserve(need))
@@ -690,9 +690,9 @@ int Engine::run(Plan& p)
         a.mode = 1 | skip_post;
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
-        if (c == 1 && lat16) {
+        if (cls_lat[c]) {
           a.ck_slots = cls[c].max_w + 2;
-          e = launch_map_lat<Fast16, 16>(a, ns, n_it, stream);
+          e = c == 0 ? launch_map_lat<Fast16, 8>(a, ns, n_it, stream) : launch_map_lat<Fast16, 16>(a, ns, n_it, stream);
           a.ck_slots = 0;
         } else {
           e = c == 0 ? launch_map_f16<Fast16, 8>(a, ns, n_it, stream) : launch_map_f16<Fast16, 16>(a, ns, n_it, stream);
@@ -706,11 +706,13 @@ int Engine::run(Plan& p)
         case 1: e = launch_map<Sat16, 16>(a, cls[c].n_slots, cls[c].max_w, stream); break; // (or everything, fast16 off)
         case 2:
           a.mode |= skip_post;
-          e = launch_map_f16<Sat8, 16>(a, cls[c].n_slots, p.iter0 + it, stream);
+          a.ck_slots = cls_lat[c] ? cls[c].max_w + 2 : 0;
+          e = cls_lat[c] ? launch_map_lat<Sat8, 16>(a, cls[c].n_slots, p.iter0 + it, stream) : launch_map_f16<Sat8, 16>(a, cls[c].n_slots, p.iter0 + it, stream);
           break;
         default:
           a.mode |= skip_post;
-          e = launch_map_f16<Sat8, 32>(a, cls[c].n_slots, p.iter0 + it, stream);
+          a.ck_slots = cls_lat[c] ? cls[c].max_w + 2 : 0;
+          e = cls_lat[c] ? launch_map_lat<Sat8, 32>(a, cls[c].n_slots, p.iter0 + it, stream) : launch_map_f16<Sat8, 32>(a, cls[c].n_slots, p.iter0 + it, stream);
           break;
       }
       CUDA_OK(e);

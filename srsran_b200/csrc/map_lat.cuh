@@ -11,8 +11,8 @@
 //             (win.h:769-813, iter.h:104-128) of different steps are independent: the four warps take the 8-step tiles
 //             round robin.
 //
-// Arithmetic, normalisation points, range-monitor tracking points and the soundness conditions are those of k_map_f16
-// (Fast16; map_core.cuh): the alpha / beta vectors are simply stored instead of being consumed in place.
+// Arithmetic (Fast16 under the range monitor, or the saturating int8 policy Sat8), normalisation points, tracking points
+// and the soundness conditions are those of k_map_f16 (map_core.cuh): the alpha / beta vectors are simply stored instead of being consumed in place.
 // Scratch per CTA: beta [0..W] then alpha [0..W-1], 1 KB per vector ([2 halves][32 lanes][4 words]), L2-resident.
 #pragma once
 #include "map_f16.cuh"
@@ -44,7 +44,6 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
   constexpr int  kNP = P::kNormPeriod;
   constexpr bool kDec2 = MODE == 2, kApr = MODE == 1;
   using Lay = LatLay<T>;
-  static_assert(P::kMonitor, "the latency-shaped kernel is built for the monitored wrapping arithmetic (Fast16)");
   extern __shared__ __align__(128) u32 smem_f[];
   __shared__ u32 s_mon[32][6]; // alpha pass: mon_a.hi, mon_a.lo, mon_h.hi, mon_h.lo; [4] beta verdict, [5] unused
   __shared__ u32 s_out[4][32][3]; // phase 2, per warp: LLR-subtraction overflow bits, max / min extrinsic
@@ -178,7 +177,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           u32 x, y;
           row(tb, i, x, y);
           bwd_step<P>(st, x, y, P::add(x, y));
-          if ((i & 1) == 0 && (t < 4 || i < 6))
+          if (P::kMonitor && (i & 1) == 0 && (t < 4 || i < 6))
             mon_b.track(st);
           if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
             P::normalize_now(st);
@@ -196,7 +195,8 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
         for (int s = 0; s < 8; s++)
           st[s] = (st[s] & 0xffffu) | ((u32)(uint16_t)tt[s] << 16);
       }
-      mon_b.track(st);
+      if (P::kMonitor)
+        mon_b.track(st);
       vec_store(be_g, W, st);
       // ---- backward main pass: beta[p] stored before normalisation, as the LLR consumes it
       int t = nT - 1;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           row(tb, i, x, y);
           bwd_step<P>(st, x, y, P::add(x, y));
           vec_store(be_g, 8 * t + i, st);
-          if ((i & 1) == 0)
+          if (P::kMonitor && (i & 1) == 0)
             mon_b.track(st);
           if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
             P::normalize_now(st);
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           row(tb, i, x, y);
           bwd_step<P>(st, x, y, P::add(x, y));
           vec_store(be_g, 8 * t + i, st);
-          if ((i & 1) == 0)
+          if (P::kMonitor && (i & 1) == 0)
             mon_b.track(st);
           if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
             P::normalize_now(st);
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           u32 x, y;
           row(tb, i, x, y);
           fwd_step<P>(st, x, y, P::add(x, y));
-          if ((kk & 1) == 0 && kk > 2)
+          if (P::kMonitor && (kk & 1) == 0 && kk > 2)
             mon_a.track(st);
           if ((kNP == 1 || (kk & 1) == 0) && kk != 0)
             P::normalize_now(st);
@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
         for (int s = 1; s < 8; s++)
           st[s] = (st[s] & 0xffff0000u) | (u32)(uint16_t)(-P::kInf);
       }
-      mon_h.track(st);
+      if (P::kMonitor)
+        mon_h.track(st);
       // ---- alpha recursion: alpha before step p stored; tracking and normalisation points of k_map_f16's output pass
       const int n_full = W >> 3;
       for (int t = 0; t < n_full; t++) {
@@ -269,11 +270,11 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           u32 x, y;
           row(tb, i, x, y);
           fwd_step<P>(st, x, y, P::add(x, y));
-          if ((i & 1) == 0)
+          if (P::kMonitor && (i & 1) == 0)
             mon_a.track(st);
           if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
             P::normalize_now(st);
-          if (t == 0 && i == 3) { // what was tracked so far belongs to the head monitor
+          if (P::kMonitor && t == 0 && i == 3) { // what was tracked so far belongs to the head monitor
             mon_h.hi = p_max(mon_h.hi, mon_a.hi);
             mon_h.lo = p_min(mon_h.lo, mon_a.lo);
             mon_a.hi = 0;
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
           u32 x, y;
           row(tb, i, x, y);
           fwd_step<P>(st, x, y, P::add(x, y));
-          if ((i & 1) == 0)
+          if (P::kMonitor && (i & 1) == 0)
             mon_a.track(st);
           if (kNP == 1 || (i & 1) == 0)
             P::normalize_now(st);
@@ -300,8 +301,11 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
     asm volatile("fence.proxy.async.global;\n" ::: "memory");
     __threadfence_block();
     if (role == 0) {
-      g = kDec2 ? gm[3] + gm[2] : (kApr ? gm[3] : 0) + gm[0] + gm[1];
-      const bool bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
+      bool bad = false;
+      if (P::kMonitor) {
+        g   = kDec2 ? gm[3] + gm[2] : (kApr ? gm[3] : 0) + gm[0] + gm[1];
+        bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
+      }
       s_mon[lane][4] = __any_sync(gmask, bad && live) ? 1u : 0u;
     } else {
       s_mon[lane][0] = mon_a.hi;
@@ -363,7 +367,11 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
         vec_load(tb, Lay::kBeOff, i, b);
         row(tb, i, x, y);
         const u32 xy  = P::add(x, y);
-        const u32 llr = llr_factored<P>(al, b, x, y, xy, mon_l);
+        u32 llr;
+        if (P::kMonitor) // wrapping arithmetic under the range monitor: factored form
+          llr = llr_factored<P>(al, b, x, y, xy, mon_l);
+        else // saturating arithmetic: the operation order of the reference is part of the result (the state update is discarded)
+          llr = fwd_step_llr<P>(al, b, x, y, xy, mon_l);
         const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tb + (Lay::kLutOff + i * T + j - lane));
         const uint32_t  t0 = r16[0], t1 = r16[1];
         u32 e;
@@ -396,7 +404,7 @@ __global__ void __launch_bounds__(128, 1) k_map_lat(const MapArgs a)
   s_out[role][lane][1] = ehi;
   s_out[role][lane][2] = elo;
   __syncthreads();
-  if (role == 0) {
+  if (role == 0 && P::kMonitor) {
     u32 ovf = 0;
 #pragma unroll
     for (int r = 0; r < 4; r++) {
