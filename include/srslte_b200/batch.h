@@ -201,6 +201,9 @@ SRSLTE_B200_API uint32_t srslte_b200_last_map_launches(srslte_b200_ctx_t* ctx);
 /* options: "fast16" (default 1): int16 windowed decoders first try the native packed-instruction path (VIADD.16x2 /
  * VIMNMX.S16x2 / VIADDMNMX.S16x2) under a range monitor and replay with the exact saturating arithmetic whenever
  * a saturation cannot be ruled out; 0 forces the exact arithmetic everywhere.  Results are identical either way. */
+/*          "latency" (default 1): batches that leave at most one group of code blocks per SM (one subframe or a few) run
+ * the latency-shaped MAP kernel (backward and forward recursions on two warps at once, LLRs spread over four); 0 keeps the
+ * throughput kernel for every batch size.  Results are identical either way. */
 SRSLTE_B200_API int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value);
 /* statistics of the last completed batch: (code block x half-iteration) units run, and how many were replayed */
 SRSLTE_B200_API uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx);
