@@ -1,6 +1,7 @@
 """One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
 k_prepare, k_map_f16 (Fast16 and Sat8, the three decoder modes), k_map_win<Sat16> (exact path), k_map_gen, k_decide_crc,
-k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8), k_enc_tb_crc, k_enc_cb."""
+k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8), k_ulsch_deinterleave, k_map_lat (one subframe),
+k_enc_tb_crc, k_enc_cb."""
 import os
 import sys
 
@@ -60,6 +61,19 @@ for dt, mod in ((np.int16, 3), (np.int8, 4)):
     for i in range(n):
         dm[i].symbols, dm[i].nof_symbols, dm[i].mod, dm[i].scramble_bytes, dm[i].e_bits = d_sym + i * nsym * 8, nsym, mod, d_scr, d_e + i * nsym * Qm * np.dtype(dt).itemsize
     ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
+# PUSCH pre-steps: k_ulsch_deinterleave<3> (100 PRB, 64QAM, ACK + RI + CQI)
+ntb_ul, n_ul = 256, 1200 * 12 * 6
+q_ul = rng.integers(-2000, 2000, (ntb_ul, n_ul)).astype(np.int16)
+d_q, d_g = ctx.device_alloc(q_ul.nbytes), ctx.device_alloc(q_ul.nbytes)
+ctx.h2d(d_q, q_ul)
+ul = b.make_ulschs(ntb_ul)
+for i in range(ntb_ul):
+    ul[i].q_bits, ul[i].Qm, ul[i].H_prime_total, ul[i].N_pusch_symbs, ul[i].g_bits = d_q + i * n_ul * 2, 6, 14400, 12, d_g + i * n_ul * 2
+    ul[i].Q_prime_ack, ul[i].Q_prime_ri, ul[i].Q_prime_cqi = 36, 20, 57
+ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
+# one subframe at a time: k_map_lat<Fast16,16,*> (13 blocks of K = 6144) and k_map_lat<Sat8,32,*> (one 97896-bit block)
+cb_batch(13, 6144, 3)
+tb_batch("c4", 1, 3)
 # transmit mirror: k_enc_tb_crc, k_enc_cb
 ntb, tbs, Qm, G = 364, 75376, 6, 90000
 pay = rng.integers(0, 256, (ntb, tbs // 8), dtype=np.uint8)
