@@ -94,6 +94,35 @@ static void crc24_xpows(uint32_t nbytes, uint32_t poly, uint32_t out[5])
   cache[key] = e;
 }
 
+// the same constants for the fused kernel's per-block CRC: `lanes` chunks of ceil(nbytes / lanes) bytes (group_crc24)
+static void crc24_xq(uint32_t nbytes, uint32_t lanes, uint32_t poly, uint32_t out[4])
+{
+  struct Entry {
+    uint32_t v[4];
+  };
+  static thread_local std::map<uint64_t, Entry> cache;
+  const uint64_t key = ((uint64_t)poly << 32) | ((uint64_t)lanes << 24) | nbytes;
+  auto           it  = cache.find(key);
+  if (it != cache.end()) {
+    memcpy(out, it->second.v, sizeof(it->second.v));
+    return;
+  }
+  const uint32_t cb = (nbytes + lanes - 1) / lanes;
+  uint32_t       xp = 1;
+  for (uint32_t q = 0; q < 8 * cb; q++) {
+    xp <<= 1;
+    if (xp & 0x1000000u)
+      xp ^= poly;
+  }
+  xp &= 0xffffffu;
+  Entry e;
+  for (int l = 0; l < 4; l++) {
+    out[l] = e.v[l] = xp;
+    xp     = crc24_mulmod_host(xp, xp, poly);
+  }
+  cache[key] = e;
+}
+
 template <typename T>
 int DevBuf<T>::reserve(size_t n)
 {
@@ -178,6 +207,8 @@ int Engine::create(Engine** out, int device)
     e->opt_fast16 = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_LATENCY"))
     e->opt_latency = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_FUSED"))
+    e->opt_fused = atoi(ev) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventCreate(&e->ev_end));
@@ -205,7 +236,7 @@ Engine::~Engine()
   if (ev_end)
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
-  d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
+  d_crctab.release(); d_parked.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
@@ -229,8 +260,13 @@ int Engine::build_tables()
       if (lanes > 1 && (K % lanes != 0 || K / lanes < (uint32_t)kWinOverlap))
         continue;
       qpp_off[li][ci] = (uint32_t)qpp.size();
-      qpp.resize(qpp.size() + 2 * K);
-      qpp_tables(K, lanes, &qpp[qpp_off[li][ci]], &qpp[qpp_off[li][ci] + K]);
+      qpp.resize(qpp.size() + 3 * K);
+      uint16_t* fwd = &qpp[qpp_off[li][ci]];
+      qpp_tables(K, lanes, fwd, fwd + K);
+      // nat[i]: natural bit index of the element fwd[i] points at (DEC2's hard decisions go straight to the natural-order
+      // bit string of the fused kernel)
+      for (uint32_t i = 0; i < K; i++)
+        fwd[2 * K + i] = (uint16_t)(lanes > 1 ? from_lane(fwd[i], K, lanes) : fwd[i]);
     }
   }
   // rate de-matching base tables for layout {standard, 8, 16, 32 lanes}
@@ -260,6 +296,9 @@ int Engine::build_tables()
   crc24_table(kCrc24A, tab[0]);
   crc24_table(kCrc24B, tab[1]);
   CUDA_OK(cudaMemcpyToSymbol(c_crc_tab, tab, sizeof(tab)));
+  if (d_crctab.reserve(512))
+    return SRSLTE_B200_ERROR;
+  CUDA_OK(cudaMemcpy(d_crctab.ptr, tab, sizeof(tab), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -311,6 +350,17 @@ void Engine::fill_geometry(CbDev* d, uint32_t K, const DecSel& s)
   d->qpp_off   = qpp_off[lanes_idx(s.lanes)][ci];
   d->sat_end   = s.bits == 8 ? (K / 32) * 32 : 0;
   d->in_sb     = s.in_sb ? 1 : 0;
+}
+
+// CRC constants of a code block for both decision paths (k_decide_crc: 32 chunks; k_map_fused: one chunk per lane of the block)
+static void fill_crc(CbDev* d, uint32_t poly)
+{
+  d->crc_poly = poly;
+  if (!poly)
+    return;
+  crc24_xpows(d->K / 8, poly, d->crc_xp);
+  if (d->N)
+    crc24_xq(d->K / 8, d->N / 2, poly, d->crc_xq);
 }
 
 // ------------------------------------------------------------------------------------------------- batch run
@@ -446,6 +496,49 @@ static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaS
   return launch_map_f16_mode<P, N, 0, 128, 3, 3>(a, n_slots, st);
 }
 
+// Persistent fused launch (map_fused.cuh): one CTA per SM, up to 12 warps; every warp fetches groups until the list is dry.
+struct FusedGeom {
+  int grid, warps, warp_words, bits_words;
+};
+template <int N>
+static FusedGeom fused_geometry(int n_groups, int max_k, int num_sms)
+{
+  constexpr int T = N / 2, G = 32 / T;
+  FusedGeom     g;
+  g.bits_words = (max_k + 31) / 32;
+  g.warp_words = (FusedLay<T>::kFixedWords + G * g.bits_words + 31) / 32 * 32;
+  int warps    = std::min(12, std::max(1, (n_groups + num_sms - 1) / num_sms));
+  while (warps > 1 && (size_t)warps * g.warp_words * 4 > 232448)
+    warps--;
+  g.warps = warps;
+  g.grid  = std::min(num_sms, (n_groups + warps - 1) / warps);
+  return g;
+}
+template <class P, int N>
+static cudaError_t launch_fused(FusedArgs a, const FusedGeom& g, cudaStream_t st)
+{
+  a.warp_words = g.warp_words;
+  a.bits_words = g.bits_words;
+  const size_t smem = (size_t)g.warps * g.warp_words * 4;
+  auto         kern = k_map_fused<P, N>;
+  static std::mutex mu; // the attribute is raised to the largest size seen per (kernel, device)
+  static std::map<std::pair<const void*, int>, size_t> done;
+  {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& have = done[std::make_pair((const void*)kern, dev)];
+    if (smem > have) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess)
+        return e;
+      have = smem;
+    }
+  }
+  kern<<<g.grid, g.warps * 32, smem, st>>>(a);
+  return cudaGetLastError();
+}
+
 int Engine::run(Plan& p)
 {
   CUDA_OK(cudaSetDevice(device));
@@ -484,10 +577,10 @@ int Engine::run(Plan& p)
     else
       plain.push_back(i);
   }
-  const size_t off_active = add_list(active), off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
+  const size_t off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
   struct ClassRun {
     size_t off, winfo_off;
-    int    n_slots, max_w;
+    int    n_slots, max_w, max_k;
     bool   no_crc; // run_all semantics for every block of the class: only the last half-iteration's decisions are read
   } cls[4];
   struct KGroup { // code blocks of one size in one decoder class: consecutive slots, consecutive workspace
@@ -534,6 +627,7 @@ int Engine::run(Plan& p)
     cls[c].winfo_off = add_list(winfo);
     cls[c].n_slots   = (int)w.size();
     cls[c].max_w     = max_w;
+    cls[c].max_k     = ids.empty() ? 0 : (int)p.cbs[ids[0]].K; // (sorted by K, longest first)
     cls[c].no_crc    = true;
     for (int i : ids)
       if (p.cbs[i].crc_poly != 0 || p.cbs[i].max_iter != p.iter0 + p.max_iter)
@@ -567,6 +661,28 @@ int Engine::run(Plan& p)
   }
   const size_t off_gen = add_list(gen_pairs);
   const int    n_pairs = (int)gen_pairs.size() / 2;
+
+  // ---- which kernel runs a class: the latency-shaped per-half-iteration kernel when its groups leave most SMs empty (one
+  //      subframe or a few), else ONE persistent fused launch for all half-iterations
+  bool cls_lat[4] = {false, false, false, false}, cls_fused[4] = {false, false, false, false};
+  std::vector<int> old_path; // blocks decided by k_decide_crc after every half-iteration: latency classes + generic decoder
+  for (int c = 0; c < 4; c++) {
+    if (!cls[c].n_slots)
+      continue;
+    const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
+    cls_lat[c]   = opt_latency && (c >= 2 || opt_fast16) && n_groups <= num_sms;
+    cls_fused[c] = !cls_lat[c] && opt_fused;
+  }
+  for (int i : active) {
+    const CbDev& d = p.cbs[i];
+    int          c = -1;
+    for (int k = 0; k < 4; k++)
+      if (d.N == kWinClasses[k].lanes && d.bits == kWinClasses[k].bits)
+        c = k;
+    if (c < 0 || !cls_fused[c])
+      old_path.push_back(i);
+  }
+  const size_t off_old = add_list(old_path);
 
   // ---- device buffers
   if (d_gmax.reserve((size_t)n_cb * 4) || d_cbs.reserve(n_cb) || d_state.reserve(n_cb) || d_ws.reserve(ws_elems) || d_tails.reserve((size_t)n_cb * 12) ||
@@ -611,7 +727,8 @@ int Engine::run(Plan& p)
     CUDA_OK(cudaMemcpyAsync(d_tbs.ptr, hp, p.tbs.size() * sizeof(TbDev), cudaMemcpyHostToDevice, stream));
   }
 
-  const size_t n_counters = 4 + (size_t)p.max_iter + 1;
+  const size_t ctr_fetch0 = 4 + (size_t)p.max_iter + 1; // group fetch counters of the fused launches (two per class)
+  const size_t n_counters = ctr_fetch0 + 8;
   if (d_counters.reserve(n_counters) || h_counters.reserve(4))
     return SRSLTE_B200_ERROR;
   CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, n_counters * sizeof(uint32_t), stream));
@@ -642,12 +759,21 @@ int Engine::run(Plan& p)
   CUDA_OK(cudaGetLastError());
 
   // ---- global scratch for the beta checkpoints of the windowed kernels
-  bool cls_lat[4] = {false, false, false, false};
+  FusedGeom fgeo[4];
   {
     size_t need = 0;
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots)
         continue;
+      const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
+      if (cls_fused[c]) {
+        // one checkpoint (256 words per warp) per 8-step tile + the start state, per RESIDENT warp
+        fgeo[c] = kWinClasses[c].lanes == 8 ? fused_geometry<8>(n_groups, cls[c].max_k, num_sms)
+                                            : kWinClasses[c].lanes == 16 ? fused_geometry<16>(n_groups, cls[c].max_k, num_sms)
+                                                                         : fused_geometry<32>(n_groups, cls[c].max_k, num_sms);
+        need = std::max(need, (size_t)fgeo[c].grid * fgeo[c].warps * (((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+        continue;
+      }
       int nt, blocks;
       if (kWinClasses[c].lanes == 8)
         map_geometry<8>(cls[c].n_slots, &nt, &blocks);
@@ -659,21 +785,76 @@ int Engine::run(Plan& p)
       // whole CTAs (128 threads for k_map_f16, 256 for k_map_win)
       const size_t slots = (size_t)(cls[c].max_w + 7) / 8 + 2;
       need = std::max(need, slots * ((size_t)blocks * nt + 256) * 8);
-      // latency-shaped kernel (int16, 16 lanes): when the groups of the class leave most SMs empty, one 4-warp CTA per group
-      // with every beta and alpha vector in scratch (2 x (W + 2) KB per group)
-      const int gsz = 64 / kWinClasses[c].lanes, groups = (cls[c].n_slots + gsz - 1) / gsz;
-      cls_lat[c] = opt_latency && (c >= 2 || opt_fast16) && groups <= num_sms;
+      // latency-shaped kernel: one 4-warp CTA per group with every beta and alpha vector in scratch (2 x (W + 2) KB per group)
       if (cls_lat[c])
-        need = std::max(need, (size_t)groups * 2 * (size_t)(cls[c].max_w + 2) * 256);
+        need = std::max(need, (size_t)n_groups * 2 * (size_t)(cls[c].max_w + 2) * 256);
     }
     if (need && d_ckscratch.reserve(need))
       return SRSLTE_B200_ERROR;
   }
 
-  // ---- half-iterations
-  for (uint32_t it = 0; it < p.max_iter && !active.empty(); it++) {
+  // ---- fused classes: every half-iteration, the hard decisions, the CRC and the early stop in one persistent launch;
+  //      int16 classes run the native packed arithmetic under the range monitor first, then the exact-arithmetic kernel
+  //      finishes the blocks the monitor parked (it returns at once when nothing was parked)
+  for (int c = 0; c < 4; c++) {
+    if (!cls_fused[c])
+      continue;
+    const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
+    if (d_parked.reserve((size_t)n_groups + 1))
+      return SRSLTE_B200_ERROR;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.work       = d_lists.ptr + cls[c].off;
+    a.n_groups   = n_groups;
+    a.cbs        = d_cbs.ptr;
+    a.state      = d_state.ptr;
+    a.ws         = d_ws.ptr;
+    a.tails      = d_tails.ptr;
+    a.qpp        = d_qpp.ptr;
+    a.gmax       = d_gmax.ptr;
+    a.ck_scratch = d_ckscratch.ptr;
+    a.ck_words   = (uint32_t)((((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+    a.counters   = d_counters.ptr;
+    a.parked     = d_parked.ptr;
+    a.winfo      = d_lists.ptr + cls[c].winfo_off;
+    a.tmaps      = (const CUtensorMap*)d_tmaps.ptr;
+    a.cb_out     = d_cbout.ptr;
+    a.crc_tab    = d_crctab.ptr;
+    cudaEvent_t e0, e1;
+    if (map_event_pair(&e0, &e1))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaEventRecord(e0, stream));
+    cudaError_t e = cudaSuccess;
+    if (c < 2) {
+      if (opt_fast16) {
+        CUDA_OK(cudaMemsetAsync(d_counters.ptr + 2, 0, sizeof(uint32_t), stream)); // parked groups of THIS class
+        a.mode      = 1;
+        a.ctr_fetch = (int)ctr_fetch0 + 2 * c;
+        e = c == 0 ? launch_fused<Fast16, 8>(a, fgeo[c], stream) : launch_fused<Fast16, 16>(a, fgeo[c], stream);
+        CUDA_OK(e);
+        last_launches++;
+        last_map_launches++;
+        a.mode = 2;
+      } else {
+        a.mode = 0;
+      }
+      a.ctr_fetch = (int)ctr_fetch0 + 2 * c + 1;
+      e = c == 0 ? launch_fused<Sat16, 8>(a, fgeo[c], stream) : launch_fused<Sat16, 16>(a, fgeo[c], stream);
+    } else {
+      a.mode      = 0;
+      a.ctr_fetch = (int)ctr_fetch0 + 2 * c;
+      e = c == 2 ? launch_fused<Sat8, 16>(a, fgeo[c], stream) : launch_fused<Sat8, 32>(a, fgeo[c], stream);
+    }
+    CUDA_OK(e);
+    CUDA_OK(cudaEventRecord(e1, stream));
+    last_launches++;
+    last_map_launches++;
+  }
+
+  // ---- per-half-iteration path: latency-shaped classes and the generic decoder
+  for (uint32_t it = 0; it < p.max_iter && !old_path.empty(); it++) {
     for (int c = 0; c < 4; c++) {
-      if (!cls[c].n_slots)
+      if (!cls[c].n_slots || cls_fused[c])
         continue;
       MapArgs a{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 0, d_ckscratch.ptr, 0, d_counters.ptr, (int)it,
                 d_lists.ptr + cls[c].winfo_off, (const CUtensorMap*)d_tmaps.ptr};
@@ -726,8 +907,8 @@ int Engine::run(Plan& p)
       CUDA_OK(cudaGetLastError());
       last_launches++;
     }
-    DecideArgs da{d_lists.ptr + off_active, (int)active.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
-    k_decide_crc<<<((int)active.size() + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
+    DecideArgs da{d_lists.ptr + off_old, (int)old_path.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
+    k_decide_crc<<<((int)old_path.size() + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
   }
@@ -986,7 +1167,6 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     u.nof_cb  = s.C;
 
     const uint32_t Gp = u.nof_e_bits / u.Qm, gamma = Gp % s.C, n_e = u.Qm * (Gp / s.C);
-    uint32_t       xp_cache[5];
     crc24_xpows(u.tbs / 8, kCrc24A, td.crc_xp);
     for (uint32_t c = 0; c < s.C; c++) {
       const uint32_t K = c < s.C1 ? s.K1 : s.K2;
@@ -998,10 +1178,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
       memset(&d, 0, sizeof(d));
       fill_geometry(&d, K, sel);
       d.max_iter = max_iterations;
-      d.crc_poly = s.C > 1 ? kCrc24B : kCrc24A;
-      if (c == 0 || K != (c - 1 < s.C1 ? s.K1 : s.K2))
-        crc24_xpows(K / 8, d.crc_poly, xp_cache);
-      memcpy(d.crc_xp, xp_cache, sizeof(xp_cache));
+      fill_crc(&d, s.C > 1 ? kCrc24B : kCrc24A);
       d.in_bits  = is8 ? 8 : 16;
       d.dematch  = 1;
       d.tb       = (uint32_t)plan.tbs.size();
@@ -1820,6 +1997,10 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   if (!strcmp(name, "fast16")) {
     ctx->e->opt_fast16 = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "fused")) {
+    ctx->e->opt_fused = value != 0;
     return 0;
   }
   if (!strcmp(name, "latency")) {

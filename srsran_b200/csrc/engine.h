@@ -96,7 +96,9 @@ public:
   DevBuf<int>      d_lists, d_gmax;
   bool             opt_fast16 = true; // try the native packed-instruction path first (exact replay on range alarm)
   bool             opt_latency = true; // small batches: the 4-warp latency-shaped MAP kernel (map_lat.cuh) instead of one warp per group
-  DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch;
+  DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch, d_crctab;
+  DevBuf<int>      d_parked; // fused kernel: groups whose blocks the Fast16 monitor parked for the exact-arithmetic launch
+  bool             opt_fused = true; // large batches: one persistent launch per decoder class (map_fused.cuh)
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;
   PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc, h_tmaps;

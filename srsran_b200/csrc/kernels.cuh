@@ -38,6 +38,7 @@ struct CbDev {
   uint32_t out_off;  // byte offset of this CB's K/8 decided bytes in the CB output pool
   uint32_t sat_end;  // 8-bit glue: elements below this index use the saturating subtract
   uint32_t crc_xp[5]; // CRC chunk-combination constants for K/8 bytes under crc_poly (warp_crc24)
+  uint32_t crc_xq[4]; // the same for chunks of ceil(K/8 / (N/2)) bytes: the block's own lanes compute the CRC (group_crc24)
   // input description for k_prepare / k_dematch
   void*       in_ptr; // decoder input: HARQ soft buffer of this CB, or the caller's LLRs (device memory)
   const void* e_ptr;  // rate-matched e-bits of this CB (device memory), dematch only
@@ -792,6 +793,10 @@ __device__ __forceinline__ void tma_tile4(unsigned dst_s, const CUtensorMap* tm,
 } // namespace b200
 #include "map_f16.cuh"
 #include "map_lat.cuh"
+namespace b200 {
+__device__ __forceinline__ uint32_t crc24_mulmod(uint32_t a, uint32_t b, uint32_t poly);
+}
+#include "map_fused.cuh"
 namespace b200 {
 
 // ------------------------------------------------------------------------------------------ generic MAP

@@ -1,0 +1,707 @@
+// k_map_fused -- the persistent per-code-block pipeline: ALL half-iterations of a group of code blocks in one launch.
+//
+// Replaces the reference's per-code-block loop (lib/src/phy/phch/sch.c:420-450: srslte_tdec_iteration -> hard decision ->
+// srslte_crc_checksum_byte -> stop on CRC == 0 or at the iteration limit; srslte_tdec_run_all, turbodecoder.c:537-578, is the
+// same loop without the CRC) around the windowed max-log-MAP of include/srslte/phy/fec/turbodecoder_win.h:551-868 and the
+// half-iteration glue of turbodecoder_iter.h:104-128.
+//
+// One WARP owns a group of G = 64/N code blocks of equal K (one thread = two adjacent sub-block lanes of one block, int16x2)
+// from its first half-iteration to its last:
+//
+//     fetch group (atomic counter; groups are sorted by K, longest first)
+//     repeat   DEC1 | DEC2 half-iteration: beta warm-up, beta pass (one checkpoint per 8-step tile), alpha warm-up, alpha
+//                pass with the a-posteriori LLRs, the glue (extrinsic scatter through the QPP rows) and the HARD DECISIONS
+//                packed as bits into a K-bit string per block in shared memory
+//              CRC24 of the decided bytes by the block's own T lanes, early stop per block, decided bytes written once
+//     until    every block of the group passed its CRC or reached its iteration limit
+//
+// so a batch costs ONE launch per decoder class instead of 2 x max_iterations launches, the a-posteriori plane and the
+// decision kernel's read-back of it are gone, and there is no wave quantisation: the grid is one CTA of 12 warps per SM and a
+// warp that finishes a group takes the next one.  Staging (TMA tensor tiles, three stages, one mbarrier per warp and
+// stage), the checkpoint/recompute schedule, the factored LLR and the Fast16 range monitor are those of DESIGN.md 5.1 / 5.2.
+// A block the monitor flags is PARKED (its inputs of that half-iteration are intact): the same kernel compiled with the
+// exact saturating policy (Sat16) takes the parked groups in a second launch and finishes them.
+#pragma once
+#include "map_f16.cuh"
+
+namespace b200 {
+
+#if defined(__CUDACC__)
+
+struct FusedArgs {
+  const int*         work;      // code block per slot, -1 = padding; the G slots of a group share K
+  int                n_groups;
+  const CbDev*       cbs;
+  CbState*           state;
+  int16_t*           ws;
+  const int16_t*     tails;
+  const uint16_t*    qpp;       // per (K, lanes): fwd[K] | rev[K] | nat[K]
+  int*               gmax;
+  u32*               ck_scratch; // resident warps x ck_words: beta checkpoints of the half-iteration in flight
+  uint32_t           ck_words;
+  uint32_t*          counters;  // [0] half-iterations run with the exact policy after parking, [1] half-iterations run,
+                                // [2] groups parked by the Fast16 launch, [ctr_fetch] group fetch counter of this launch
+  int                ctr_fetch;
+  int*               parked;    // group ids holding parked blocks (written by mode 1, consumed by mode 2)
+  int                mode;      // 0: every active block; 1: Fast16 attempt, flagged blocks are parked; 2: parked blocks only
+  const int*         winfo;     // per group {index of its K-group's pair of tensor maps, block coordinate of its first slot}
+  const CUtensorMap* tmaps;     // per K-group: [2g] box of 3 planes, [2g+1] box of 2 planes
+  uint8_t*           cb_out;
+  const uint32_t*    crc_tab;   // [2][256]: CRC24A, CRC24B byte tables (global memory copy, read through L1)
+  int                warp_words; // shared memory words per warp (FusedLay<T>::kFixedWords + G * bits words per block)
+  int                bits_words; // words of the K-bit decision string per block (max over the class)
+};
+
+template <int T>
+struct FusedLay {
+  static constexpr int kRows       = 8;
+  static constexpr int kPlaneWords = kRows * 32;
+  static constexpr int kLutWords   = kRows * T;
+  // stage: planes | QPP rows (| natural-index rows, DEC2 only) | checkpoint.  DEC1 with a-priori input stages 3 planes + 1
+  // table, DEC2 2 planes + 2 tables; the checkpoint sits behind the larger of the two
+  static constexpr int kCkOff      = 3 * kPlaneWords + kLutWords;
+  static constexpr int kStageWords = (kCkOff + 256 + 31) / 32 * 32;
+  static constexpr int kStages     = 3;
+  static constexpr int kYOff       = kStages * kStageWords;  // beta spill [3][2 halves][32 lanes][4 words]
+  static constexpr int kBarOff     = kYOff + 3 * 256;        // kStages mbarriers
+  static constexpr int kBitsOff    = kBarOff + 8;            // decision bits: G blocks x bits_words
+  static constexpr int kFixedWords = kBitsOff;
+};
+
+// CRC24 of the decided bytes of one code block by the block's own T lanes (T = 4, 8, 16 consecutive lanes of the warp).
+// bits: the block's K decisions, natural bit n at word n / 32, bit n % 32; byte b of the message holds bits 8b..8b+7, first
+// bit = MSB (turbodecoder_win.h:925-993).  Each lane runs the reference's byte recurrence (crc.h:56-63) over one chunk of
+// ceil(nbytes / T) bytes (the message is virtually left-padded with zero bytes, which do not change a zero-initialised CRC);
+// chunks are combined with crc(A || B) = crc(A) x^(8|B|) + crc(B) mod g, xq[l] = x^(8 * chunk * 2^l) mod g from the host.
+template <int T>
+__device__ __forceinline__ uint32_t group_crc24(const u32* bits, uint32_t nbytes, const uint32_t* __restrict__ tab, uint32_t poly, const uint32_t* xq,
+                                                int j, unsigned gmask)
+{
+  const uint32_t cbk = (nbytes + T - 1) / T, pad = T * cbk - nbytes;
+  uint32_t       crc = 0;
+  for (uint32_t q = 0; q < cbk; q++) {
+    const uint32_t pos = (uint32_t)j * cbk + q;
+    if (pos >= pad) {
+      const uint32_t b    = pos - pad;
+      const uint32_t byte = __brev((bits[b >> 2] >> (8u * (b & 3u))) & 0xffu) >> 24;
+      crc                 = ((crc << 8) ^ __ldg(tab + (((crc >> 16) & 0xffu) ^ byte))) & 0xffffffu;
+    }
+  }
+#pragma unroll
+  for (int lv = 0; (1 << lv) < T; lv++) {
+    const int      l     = 1 << lv;
+    const uint32_t other = __shfl_down_sync(gmask, crc, l, T);
+    if ((j & (2 * l - 1)) == 0)
+      crc = crc24_mulmod(crc, xq[lv], poly) ^ other;
+  }
+  return __shfl_sync(gmask, crc, 0, T);
+}
+
+// per-warp state that lives across half-iterations and groups
+template <int T>
+struct FusedWarp {
+  u32*     sm;        // this warp's shared memory
+  unsigned sm_s;
+  int      lane, j;
+  unsigned gmask;
+  int      wr_stage, rd_stage;
+  unsigned rd_phase;
+  uint64_t pol_first, pol_last;
+  u32*     ck_warp;   // checkpoint scratch of this resident warp: slot s at ck_warp + 256 s
+  u32*     bits;      // decision bits of this thread's block
+};
+
+// ONE half-iteration of the group.  MODE: 0 = DEC1 without a-priori input, 1 = DEC1, 2 = DEC2.  BITS: the hard decisions of
+// this half-iteration are needed (a CRC check or the end of the run follows).
+// Returns true for the threads of blocks whose Fast16 range monitor cannot rule a saturation out.
+template <class P, int N, int MODE, bool BITS>
+__device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs& a, const CUtensorMap* tmap, int blk0, int W, int K, const uint16_t* q,
+                                           int16_t* ws, size_t ps, const int16_t* tl, int g_in, uint32_t d_sat, bool live, int& ge_out)
+{
+  constexpr int  T = N / 2;
+  constexpr int  kNP = P::kNormPeriod;
+  constexpr bool kDec2 = MODE == 2, kApr = MODE == 1;
+  using Lay = FusedLay<T>;
+  constexpr int      kStages   = Lay::kStages;
+  constexpr int      kPlanes   = kApr ? 3 : 2;
+  constexpr int      kLutOff   = kPlanes * Lay::kPlaneWords;
+  constexpr int      kNatOff   = kLutOff + Lay::kLutWords;
+  constexpr int      plane0    = kDec2 ? kPlApp2 : kPlSyst;
+  constexpr unsigned kBoxBytes = (unsigned)kPlanes * Lay::kRows * 128u;
+  const int      lane = w.lane, j = w.j;
+  const unsigned gmask = w.gmask;
+  const u32*     my   = w.sm + lane; // a box row holds one word per lane
+  const u32*     lut  = (const u32*)(kDec2 ? q : q + K);     // rev[] pairs for DEC1, fwd[] pairs for DEC2
+  const u32*     natl = (const u32*)(q + 2 * (size_t)K);     // natural bit index of fwd[]'s targets (DEC2 decisions)
+
+  // tile sequence: beta warm-up (tiles 4..0), beta main (top..0), alpha warm-up (a0..top), alpha main (0..top)
+  const int nT  = (W + 7) >> 3;
+  const int a0  = (W - kWinOverlap) >> 3;
+  const int nAW = nT - a0;
+  const int s1 = 5, s2 = s1 + nT, s3 = s2 + nAW, n_seq = s3 + nT;
+  auto bar_of = [&](int stage) -> unsigned { return w.sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * stage); };
+  int  wr_idx = 0;
+  auto issue = [&]() {
+    __syncwarp(); // every lane is done with the stage about to be refilled
+    if (wr_idx < n_seq) {
+      if (lane == 0) {
+        const unsigned bar = bar_of(w.wr_stage);
+        const unsigned dst = w.sm_s + 4u * (unsigned)(w.wr_stage * Lay::kStageWords);
+        int            t;
+        bool           aux = false;
+        if (wr_idx < s1)
+          t = 4 - wr_idx;
+        else if (wr_idx < s2)
+          t = nT - 1 - (wr_idx - s1);
+        else if (wr_idx < s3)
+          t = a0 + (wr_idx - s2);
+        else {
+          t   = wr_idx - s3;
+          aux = true;
+        }
+        const int      r1        = (8 * t + 8) < W ? 8 : W - 8 * t;
+        const unsigned lut_bytes = (unsigned)r1 * T * 4u;
+        const unsigned n_lut     = (kDec2 && BITS) ? 2u : 1u;
+        mbar_expect_tx(bar, aux ? kBoxBytes + n_lut * lut_bytes + 1024u : kBoxBytes);
+        tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, w.pol_first);
+        if (aux) {
+          bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)8 * t * T, lut_bytes, bar);
+          if (kDec2 && BITS)
+            bulk_g2s(dst + 4u * (unsigned)kNatOff, natl + (size_t)8 * t * T, lut_bytes, bar);
+          bulk_g2s_hint(dst + 4u * (unsigned)Lay::kCkOff, w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar, w.pol_first);
+        }
+      }
+      wr_idx++;
+      w.wr_stage = w.wr_stage + 1 == kStages ? 0 : w.wr_stage + 1;
+    }
+  };
+  auto acquire = [&]() -> const u32* {
+    issue();
+    mbar_wait(bar_of(w.rd_stage), (w.rd_phase >> w.rd_stage) & 1u);
+    w.rd_phase ^= 1u << w.rd_stage;
+    const u32* tb = my + w.rd_stage * Lay::kStageWords;
+    w.rd_stage    = w.rd_stage + 1 == kStages ? 0 : w.rd_stage + 1;
+    return tb;
+  };
+  auto row = [&](const u32* tb, int i, u32& x, u32& y) {
+    const u32 vin = tb[i * 32];
+    y             = tb[Lay::kPlaneWords + i * 32];
+    x             = kApr ? P::add(tb[2 * Lay::kPlaneWords + i * 32], vin) : vin;
+  };
+
+#pragma unroll
+  for (int i = 0; i < kStages - 1; i++)
+    issue();
+
+  RangeMon mon_b, mon_a, mon_h;
+  mon_b.reset();
+  mon_a.reset();
+  mon_h.reset();
+  u32 st[8];
+
+  // =============================================================== backward
+  // ---- warm-up: steps 39..0 of the lane's own sub-block from the all-"unknown" state (win.h:622-630)
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    st[s] = splat16(-P::kInf);
+  for (int t = 4; t >= 0; t--) {
+    const u32* tb = acquire();
+#pragma unroll
+    for (int i = 7; i >= 0; i--) {
+      u32 x, y;
+      row(tb, i, x, y);
+      bwd_step<P>(st, x, y, P::add(x, y));
+      if (P::kMonitor && (i & 1) == 0 && (t < 4 || i < 6))
+        mon_b.track(st); // k < 38: the first two steps start from eight equal values (spread 0, covered by g)
+      if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+        P::normalize_now(st);
+    }
+  }
+  // hand the estimate to the lane below; tail trellis for the last lane (win.h:580-612, 500-548)
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const u32 nx = __shfl_down_sync(gmask, st[s], 1, T);
+    st[s]        = shift_down_lanes(st[s], nx);
+  }
+  if (j == T - 1) {
+    int32_t tt[8];
+    tail_trellis<P>(kDec2 ? tl + 6 : tl, kDec2 ? tl + 9 : tl + 3, tt);
+#pragma unroll
+    for (int s = 0; s < 8; s++)
+      st[s] = (st[s] & 0xffffu) | ((u32)(uint16_t)tt[s] << 16);
+  }
+  // ---- main pass with one checkpoint per tile: slot t = beta[8t] before normalisation, slot nT = beta[W]
+  // (every lane stores, ghosts too: the scratch belongs to the warp and nobody else reads it)
+  auto ck_store = [&](int sl, const u32 (&v)[8]) {
+    uint4* g = reinterpret_cast<uint4*>(w.ck_warp + (size_t)sl * 256) + lane;
+    stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), w.pol_last);
+    stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), w.pol_last);
+  };
+  if (P::kMonitor)
+    mon_b.track(st);
+  ck_store(nT, st);
+  {
+    int t = nT - 1;
+    if (W & 7) { // partial top tile: guarded, rolled
+      const u32* tb = acquire();
+#pragma unroll 1
+      for (int i = (W & 7) - 1; i >= 0; i--) {
+        u32 x, y;
+        row(tb, i, x, y);
+        bwd_step<P>(st, x, y, P::add(x, y));
+        if (i == 0)
+          ck_store(t, st);
+        if (P::kMonitor && (i & 1) == 0)
+          mon_b.track(st);
+        if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+          P::normalize_now(st);
+      }
+      t--;
+    }
+    for (; t >= 0; t--) {
+      const u32* tb = acquire();
+#pragma unroll
+      for (int i = 7; i >= 0; i--) {
+        u32 x, y;
+        row(tb, i, x, y);
+        bwd_step<P>(st, x, y, P::add(x, y));
+        if (i == 0)
+          ck_store(t, st);
+        if (P::kMonitor && (i & 1) == 0)
+          mon_b.track(st);
+        if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+          P::normalize_now(st);
+      }
+    }
+  }
+  // the checkpoints were written through the generic proxy and come back through the async proxy
+  asm volatile("fence.proxy.async.global;\n" ::: "memory");
+
+  // bound on every |branch metric| of this call: max|a-priori| + max|systematic| + max|parity| (g_in, from the caller)
+  const int g = g_in;
+  bool      flagged = false;
+  if (P::kMonitor) {
+    const bool bad = !fast16_beta_ok(mon_b.spread_lo(), g) || !fast16_beta_ok(mon_b.spread_hi(), g);
+    if (__any_sync(gmask, bad && live)) {
+      flagged = live;
+      live    = false;
+    }
+  }
+
+  // =============================================================== forward
+  // ---- warm-up: steps W-40..W-1 of the lane's own sub-block (win.h:747-756); normalisation follows the loop counter
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    st[s] = splat16(-P::kInf);
+  {
+    int kk = 0; // loop counter of the pass
+    for (int t = a0; t < nT; t++) {
+      const u32* tb = acquire();
+      const int  i0 = t == a0 ? (W - kWinOverlap) - 8 * a0 : 0;
+      const int  i1 = (8 * t + 8) <= W ? 8 : W - 8 * t;
+#pragma unroll 1
+      for (int i = i0; i < i1; i++, kk++) {
+        u32 x, y;
+        row(tb, i, x, y);
+        fwd_step<P>(st, x, y, P::add(x, y));
+        if (P::kMonitor && (kk & 1) == 0 && kk > 2)
+          mon_a.track(st);
+        if ((kNP == 1 || (kk & 1) == 0) && kk != 0)
+          P::normalize_now(st);
+      }
+    }
+  }
+  // hand the estimate to the lane above; lane 0 starts from the known state [0, -INF x 7]
+#pragma unroll
+  for (int s = 0; s < 8; s++) {
+    const u32 pv = __shfl_up_sync(gmask, st[s], 1, T);
+    st[s]        = shift_up_lanes(pv, st[s]);
+  }
+  if (j == 0) {
+    st[0] = st[0] & 0xffff0000u;
+#pragma unroll
+    for (int s = 1; s < 8; s++)
+      st[s] = (st[s] & 0xffff0000u) | (u32)(uint16_t)(-P::kInf);
+  }
+  // The first four steps (and the start state) are tracked by mon_h
+  if (P::kMonitor)
+    mon_h.track(st);
+
+  // ---- output pass
+  // extrinsic output, scattered through the QPP rows
+  char* const ext = reinterpret_cast<char*>(kDec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps);
+  u32         ehi = 0, elo = 0, e_even = 0;
+  u32         al[8];
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    al[s] = st[s];
+  u32       acc = 0;                                  // DEC1 decisions of up to 16 steps, both lanes, first step = MSB
+  int       acc_n = 0;
+  char* const bits_c = reinterpret_cast<char*>(w.bits);
+  // flush the accumulated DEC1 decisions of steps [p_end - acc_n, p_end) into the natural-order bit string
+  auto flush_bits = [&](int p_end) {
+    if (acc_n == 0)
+      return;
+    if (live) {
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const u32      v  = h ? (acc >> 16) : (acc & 0xffffu);
+        const u32      r  = __brev(v) >> (32 - acc_n);                  // first step at bit 0
+        const uint32_t n0 = (uint32_t)(2 * j + h) * (uint32_t)W + (uint32_t)(p_end - acc_n);
+        const uint32_t sh = n0 & 31u;
+        atomicOr(w.bits + (n0 >> 5), r << sh);
+        if (sh + (uint32_t)acc_n > 32u)
+          atomicOr(w.bits + (n0 >> 5) + 1, r >> (32u - sh));
+      }
+    }
+    acc   = 0;
+    acc_n = 0;
+  };
+
+  auto out_step = [&](const u32* tb, int t, int i, const u32 (&b)[8], RangeMon& mon, bool norm) {
+    u32 x, y;
+    row(tb, i, x, y);
+    const u32 xy = P::add(x, y);
+    u32       llr;
+    if (P::kMonitor) { // wrapping arithmetic under the range monitor: factored form
+      llr = llr_factored<P>(al, b, x, y, xy, mon);
+      fwd_step<P>(al, x, y, xy);
+    } else { // saturating arithmetic: the operation order of the reference is part of the result
+      llr = fwd_step_llr<P>(al, b, x, y, xy, mon);
+    }
+    if (P::kMonitor && (i & 1) == 0)
+      mon.track(al);
+    if ((kNP == 1 || (i & 1) == 0) && norm)
+      P::normalize_now(al);
+    const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tb + (kLutOff + i * T + j - lane));
+    const uint32_t  t0 = r16[0], t1 = r16[1];
+    auto track_e = [&](u32 e) {
+      if (P::kMonitor) {
+        if ((i & 1) == 0) {
+          e_even = e;
+        } else {
+          ehi = p_max3(ehi, e_even, e);
+          elo = p_min3(elo, e_even, e);
+        }
+      }
+    };
+    // hard decisions (llr > 0), one bit per int16 half: 1 where positive
+    const u32 dbit = BITS ? __vimin_s16x2_relu(llr, 0x00010001u) : 0u;
+    u32       e;
+    if (!kDec2) {
+      // extrinsic - a-priori -> app2[rev[.]]; decisions stay in this thread's lanes: accumulate, flush every 16 steps
+      const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
+      e = kApr ? P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat) : llr;
+      if (BITS) {
+        acc = acc * 2u + dbit;
+        acc_n++;
+      }
+    } else {
+      // a-posteriori - own input -> a-priori[fwd[.]]; decisions belong to natural positions nat[.]
+      e = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
+      if (BITS) {
+        const uint16_t* n16 = reinterpret_cast<const uint16_t*>(tb + (kNatOff + i * T + j - lane));
+        const uint32_t  n0 = n16[0], n1 = n16[1];
+        if (live) {
+          atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
+          atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
+        }
+      }
+    }
+    track_e(e);
+    if (live) {
+      *reinterpret_cast<int16_t*>(ext + 2u * t0) = (int16_t)lo16(e);
+      *reinterpret_cast<int16_t*>(ext + 2u * t1) = (int16_t)hi16(e);
+    }
+  };
+  auto ck_load = [&](const u32* tb, u32 (&v)[8]) { // checkpoint of the tile: [half][lane][4 words]
+    const uint4* c = reinterpret_cast<const uint4*>(tb - lane + Lay::kCkOff) + lane;
+    const uint4  lo = c[0], hi = c[32];
+    v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
+    v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
+  };
+  uint4* const ysp = reinterpret_cast<uint4*>(w.sm + Lay::kYOff) + lane; // beta spill: entry y at ysp[64 y], ysp[64 y + 32]
+
+  const int n_full = W >> 3;
+  for (int t = 0; t < n_full; t++) {
+    const u32* tb = acquire();
+    u32        bs[4][8];
+    // ---- recompute beta_{8t+7} .. beta_{8t+1} from the checkpoint beta_{8t+8}
+    ck_load(tb, st);
+    if (8 * (t + 1) < W)
+      P::normalize_now(st); // the recursion continued from the normalised value; beta[W] itself was never normalised
+#pragma unroll
+    for (int kk = 7; kk >= 1; kk--) {
+      u32 x, y;
+      row(tb, kk, x, y);
+      bwd_step<P>(st, x, y, P::add(x, y));
+      if (kk >= 5) {
+        ysp[64 * (kk - 5)]      = make_uint4(st[0], st[1], st[2], st[3]);
+        ysp[64 * (kk - 5) + 32] = make_uint4(st[4], st[5], st[6], st[7]);
+      } else {
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          bs[kk - 1][s] = st[s];
+      }
+      if (kNP == 1 || (kk & 1) == 0)
+        P::normalize_now(st);
+    }
+    // ---- steps 8t .. 8t+3 against beta_{8t+1} .. beta_{8t+4}
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+      out_step(tb, t, i, bs[i], mon_a, i != 0 || t != 0);
+    if (P::kMonitor && t == 0) { // what was tracked so far belongs to the head monitor
+      mon_h.hi = p_max(mon_h.hi, mon_a.hi);
+      mon_h.lo = p_min(mon_h.lo, mon_a.lo);
+      mon_a.hi = 0;
+      mon_a.lo = 0;
+    }
+    // ---- steps 8t+4 .. 8t+7 against beta_{8t+5} .. beta_{8t+7} (spilled by this lane) and the checkpoint beta_{8t+8}
+#pragma unroll
+    for (int y = 0; y < 3; y++) {
+      const uint4 lo = ysp[64 * y], hi = ysp[64 * y + 32];
+      bs[y][0] = lo.x; bs[y][1] = lo.y; bs[y][2] = lo.z; bs[y][3] = lo.w;
+      bs[y][4] = hi.x; bs[y][5] = hi.y; bs[y][6] = hi.z; bs[y][7] = hi.w;
+    }
+    ck_load(tb, bs[3]);
+#pragma unroll
+    for (int i = 4; i < 8; i++)
+      out_step(tb, t, i, bs[i - 4], mon_a, true);
+    if (BITS && !kDec2 && (t & 1))
+      flush_bits(8 * t + 8);
+  }
+  if (W & 7) {
+    // partial top tile, guarded: beta_{p+1} of each step is recomputed from the checkpoint beta[W] (at most 6 steps)
+    const int  t  = n_full;
+    const int  nv = W & 7;
+    const u32* tb = acquire();
+#pragma unroll 1
+    for (int i = 0; i < nv; i++) {
+      u32 b[8];
+      ck_load(tb, b);
+#pragma unroll 1
+      for (int kk = nv - 1; kk > i; kk--) { // -> beta_{8t+kk}, normalised on the way except the one that is used
+        u32 x, y;
+        row(tb, kk, x, y);
+        bwd_step<P>(b, x, y, P::add(x, y));
+        if (kk > i + 1 && (kNP == 1 || (kk & 1) == 0))
+          P::normalize_now(b);
+      }
+      out_step(tb, t, i, b, mon_a, true); // (t >= 5 here: a lane has at least 40 steps)
+    }
+  }
+  if (BITS && !kDec2)
+    flush_bits(W);
+
+  ge_out = 0;
+  if (P::kMonitor) {
+    // max |extrinsic| handed to the next half-iteration (its a-priori / systematic input)
+    ehi    = p_max(ehi, e_even); // (an odd number of steps leaves the last one pending; counting one twice is harmless)
+    elo    = p_min(elo, e_even);
+    int ge = max(max(lo16(ehi), hi16(ehi)), max(-lo16(elo), -hi16(elo)));
+#pragma unroll
+    for (int o = T / 2; o >= 1; o >>= 1)
+      ge = max(ge, __shfl_xor_sync(gmask, ge, o, T));
+    ge_out = ge;
+    const bool bad = !fast16_alpha_ok(mon_a.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_a.spread_hi(), mon_b.spread_hi(), g) ||
+                     !fast16_alpha_ok(mon_h.spread_lo(), mon_b.spread_lo(), g) || !fast16_alpha_ok(mon_h.spread_hi(), mon_b.spread_hi(), g) ||
+                     ((mon_a.ovf | mon_h.ovf) & 0x80008000u) != 0;
+    if (__any_sync(gmask, bad && live))
+      flagged = flagged || live;
+  }
+  // the extrinsic values were written through the generic proxy; the next half-iteration's tiles read them through the
+  // async proxy
+  asm volatile("fence.proxy.async.global;\n" ::: "memory");
+  return flagged;
+}
+
+template <class P, int N>
+__global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
+{
+  constexpr int T = N / 2, G = 32 / T;
+  using Lay = FusedLay<T>;
+  extern __shared__ __align__(128) u32 smem_f[];
+  const int lane = threadIdx.x & 31;
+  const int wib  = threadIdx.x >> 5;
+
+  FusedWarp<T> w;
+  w.sm        = smem_f + (size_t)wib * a.warp_words;
+  w.sm_s      = (unsigned)__cvta_generic_to_shared(w.sm);
+  w.lane      = lane;
+  w.j         = lane % T;
+  w.gmask     = (T == 32) ? 0xffffffffu : (((1u << T) - 1u) << (lane / T * T));
+  w.wr_stage  = 0;
+  w.rd_stage  = 0;
+  w.rd_phase  = 0;
+  w.pol_first = l2_policy_evict_first();
+  w.pol_last  = l2_policy_evict_last();
+  w.ck_warp   = a.ck_scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + wib) * a.ck_words;
+  w.bits      = w.sm + Lay::kBitsOff + (lane / T) * a.bits_words;
+  const int j = w.j;
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < Lay::kStages; i++)
+      mbar_init(w.sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * i), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncwarp();
+
+  const int n_groups = a.mode == 2 ? (int)a.counters[2] : a.n_groups;
+  for (;;) {
+    int gi = 0;
+    if (lane == 0)
+      gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
+    gi = __shfl_sync(0xffffffffu, gi, 0);
+    if (gi >= n_groups)
+      break;
+    const int grp  = a.mode == 2 ? a.parked[gi] : gi;
+    const int slot = grp * G + lane / T;
+    const int cb   = a.work[slot];
+    bool      live = cb >= 0;
+    uint32_t  d_W = 0, d_K = 0, d_ps = 0, d_qpp = 0, d_sat = 0, n_iter0 = 0, max_iter = 0, crc_poly = 0, out_off = 0;
+    uint32_t  xq[4] = {0, 0, 0, 0};
+    uint64_t  d_ws = 0;
+    if (live) {
+      const CbDev*   dp = a.cbs + cb;
+      const CbState* sp = a.state + cb;
+      d_W      = dp->W;
+      d_K      = dp->K;
+      d_ps     = dp->ps;
+      d_qpp    = dp->qpp_off;
+      d_sat    = dp->sat_end;
+      d_ws     = dp->ws_off;
+      max_iter = dp->max_iter;
+      crc_poly = dp->crc_poly;
+      out_off  = dp->out_off;
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        xq[i] = dp->crc_xq[i];
+      n_iter0 = sp->n_iter;
+      if (sp->done || n_iter0 >= max_iter || (a.mode == 2 && !sp->redo))
+        live = false;
+    }
+    const unsigned live_mask = __ballot_sync(0xffffffffu, live);
+    if (live_mask == 0)
+      continue;
+    const int leader = __ffs(live_mask) - 1;
+    const int W      = __shfl_sync(0xffffffffu, (int)d_W, leader);
+    const int K      = __shfl_sync(0xffffffffu, (int)d_K, leader);
+    const int qoff   = __shfl_sync(0xffffffffu, (int)d_qpp, leader);
+    if (live && (int)d_W != W)
+      __trap(); // host planning never mixes sizes in a group
+    int16_t*        ws = a.ws + d_ws;
+    const size_t    ps = d_ps;
+    const int16_t*  tl = a.tails + (size_t)(live ? cb : 0) * 12;
+    const uint16_t* q  = a.qpp + qoff;
+    int*            gm = a.gmax + (size_t)(live ? cb : 0) * 4;
+    // max |LLR| of the three input planes and of the extrinsic values handed to the next half-iteration (Fast16 monitor)
+    const int g_syst = P::kMonitor ? gm[0] : 0, g_par0 = P::kMonitor ? gm[1] : 0, g_par1 = P::kMonitor ? gm[2] : 0;
+    int       g_ext = P::kMonitor ? gm[3] : 0;
+    const CUtensorMap* tmap3 = a.tmaps + 2 * a.winfo[2 * grp];
+    const int          blk0  = a.winfo[2 * grp + 1];
+    const uint32_t     nwords = (uint32_t)K >> 5, nbytes = (uint32_t)K >> 3;
+    bool               parked_any = false;
+
+    // The blocks of a group normally sit at the same half-iteration; blocks parked at different half-iterations (exact
+    // launch) are taken in cohorts of equal count, because the constituent decoder is a property of the warp's code path
+    bool pending = live;
+    for (;;) {
+    const unsigned pmask = __ballot_sync(0xffffffffu, pending);
+    if (pmask == 0)
+      break;
+    int niter = __shfl_sync(0xffffffffu, (int)n_iter0, __ffs(pmask) - 1);
+    live      = pending && (int)n_iter0 == niter;
+    pending   = pending && !live;
+    const int niter_first = niter;
+    while (true) {
+      // decisions are needed when a CRC check follows this half-iteration or the run ends with it
+      const bool want_bits = __any_sync(0xffffffffu, live && (crc_poly != 0 || (uint32_t)niter + 1 >= max_iter));
+      if (want_bits) {
+        for (uint32_t i = j; i < (uint32_t)a.bits_words; i += T)
+          w.bits[i] = 0;
+        __syncwarp();
+      }
+      bool flagged;
+      int  ge = 0;
+      if (niter & 1) {
+        const int g = g_ext + g_par1;
+        flagged = want_bits ? fused_half<P, N, 2, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
+                            : fused_half<P, N, 2, false>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
+      } else if (niter) {
+        const int g = g_ext + g_syst + g_par0;
+        flagged = want_bits ? fused_half<P, N, 1, true>(w, a, tmap3, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
+                            : fused_half<P, N, 1, false>(w, a, tmap3, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
+      } else {
+        const int g = g_syst + g_par0;
+        flagged = want_bits ? fused_half<P, N, 0, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
+                            : fused_half<P, N, 0, false>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
+      }
+      g_ext = ge;
+      __syncwarp(); // the decision bits of every lane are in shared memory
+      if (P::kMonitor && flagged) {
+        // park: the half-iteration is replayed (and the block finished) by the exact-arithmetic launch
+        if (j == 0) {
+          a.state[cb].n_iter = (uint32_t)niter;
+          a.state[cb].redo   = 1;
+          if (niter > niter_first)
+            atomicAdd(&a.counters[1], (uint32_t)(niter - niter_first));
+        }
+        live = false;
+      }
+      parked_any = parked_any || __any_sync(0xffffffffu, P::kMonitor && flagged);
+      niter++;
+      if (live && j == 0 && P::kMonitor)
+        gm[3] = ge;
+      const bool need = live && (crc_poly != 0 || (uint32_t)niter >= max_iter);
+      uint32_t   crc  = 1;
+      if (__any_sync(0xffffffffu, need && crc_poly != 0)) { // (every lane takes part: ghosts compute a value nobody uses)
+        const bool     is_a = crc_poly == kCrc24A;
+        const uint32_t c    = group_crc24<T>(w.bits, nbytes, a.crc_tab + (is_a ? 0 : 256), is_a ? kCrc24A : kCrc24B, xq, j, w.gmask);
+        if (need && crc_poly != 0)
+          crc = c;
+      }
+      const bool ok  = need && crc_poly != 0 && crc == 0; // early stop (sch.c:441-450)
+      const bool fin = live && (ok || (uint32_t)niter >= max_iter);
+      if (fin) {
+        // decided bytes, first bit of the block = MSB of byte 0
+        uint8_t* ob = a.cb_out + out_off;
+        if (((out_off | nbytes) & 3u) == 0) {
+          u32* o32 = reinterpret_cast<u32*>(ob);
+          for (uint32_t i = j; i < nwords; i += T)
+            o32[i] = __byte_perm(__brev(w.bits[i]), 0, 0x0123);
+        } else {
+          for (uint32_t i = j; i < nbytes; i += T)
+            ob[i] = (uint8_t)(__brev((w.bits[i >> 2] >> (8u * (i & 3u))) & 0xffu) >> 24);
+        }
+        if (j == 0) {
+          CbState* s = a.state + cb;
+          s->n_iter  = (uint32_t)niter;
+          s->crc     = crc;
+          if (ok) {
+            s->crc_ok = 1;
+            s->done   = 1;
+          }
+          const uint32_t ran = (uint32_t)(niter - niter_first);
+          atomicAdd(&a.counters[1], ran);
+          if (a.mode == 2) {
+            s->redo = 0;
+            s->n_redo += ran;
+            atomicAdd(&a.counters[0], ran);
+          }
+        }
+        live = false;
+      }
+      if (!__any_sync(0xffffffffu, live))
+        break;
+    }
+    }
+    if (a.mode == 1 && parked_any && lane == 0) {
+      const uint32_t at = atomicAdd(&a.counters[2], 1u);
+      a.parked[at]      = grp;
+    }
+  }
+}
+
+#endif // __CUDACC__
+
+} // namespace b200

@@ -872,3 +872,103 @@ def test_latency_option_both_kernels(port, ctx):
         ctx.set_option("latency", 1)
     with pytest.raises(b.B200Error):
         ctx.set_option("no-such-option", 1)
+
+
+# ----------------------------------------------------------------------------------------- the fused persistent kernel at the benchmarked scale
+def _scale_batch(rng, port, K, n_base, amps, dtype, sb):
+    """n_base distinct AWGN code words (amplitude cycles over `amps`, so some blocks trip the Fast16 range monitor)"""
+    N = (lanes16(K) if dtype == np.int16 else lanes8(K)) if sb else 0
+    rows = []
+    for i in range(n_base):
+        bits = rng.integers(0, 2, K, dtype=np.uint8)
+        llr = bpsk_awgn_llr(rng, port.tcod_encode(bits), amps[i % len(amps)], 0.75 + 0.5 * (i % 7) / 6, dtype)
+        rows.append(std_to_sb(llr, K, N) if N else llr)
+    return np.stack(rows)
+
+
+def _spread(n, n_base):
+    """which distinct block sits at batch position i: every base block appears in many groups, warps and waves"""
+    i = np.arange(n)
+    return (i * 7 + i // n_base) % n_base
+
+
+@pytest.mark.parametrize("K,dtype,ncb,nit,amps,sb", [
+    (6144, np.int16, 8000, 4, (100, 100, 100, 260, 2500), False),   # the benchmark's shape: several waves of 12-warp CTAs, some blocks parked
+    (6144, np.int16, 4100, 8, (100, 180, 300), True),
+    (5824, np.int16, 8000, 5, (100, 100, 400), True),               # partial top tile (W = 364)
+    (6144, np.int8, 4000, 6, (20, 45, 127), True),                  # Sat8, 32 lanes
+    (2048, np.int8, 5000, 5, (25, 127), True),                      # Sat8, 16 lanes
+    (512, np.int16, 6000, 6, (100, 900), True),                     # 8-lane class, 8 blocks per warp
+    (1008, np.int16, 3000, 7, (100, 3000), False),                  # W = 63: odd, every flush of the decision bits unaligned
+])
+def test_fused_kernel_at_scale(port, K, dtype, ncb, nit, amps, sb):
+    """k_map_fused (NOT the latency-shaped kernel small batches get) at the size the benchmark runs it: thousands of blocks
+    of one size on two engines that decode concurrently; every block of the batch is compared with the oracle's result for
+    its distinct input (duplicates at different slots, warps and waves must decode identically)."""
+    rng = np.random.default_rng(K + ncb + nit)
+    n_base = 56
+    base = _scale_batch(rng, port, K, n_base, amps, dtype, sb)
+    hp = port.tdec_new(TDEC_AUTO, not sb)
+    want = np.stack([port.tdec_run_all(hp, base[i], nit, K)[1] for i in range(n_base)])
+    port.tdec_del(hp)
+    idx = _spread(ncb, n_base)
+    batch = np.ascontiguousarray(base[idx])
+    ctxs = [b.Context(0), b.Context(0)]
+    outs = [np.zeros((ncb, K // 8), np.uint8) for _ in ctxs]
+    try:
+        for c, o in zip(ctxs, outs):  # both submitted before either is waited for
+            c.tdec_batch_submit(batch.ctypes.data, o.ctypes.data, K, ncb, batch.shape[1], 16 if dtype == np.int16 else 8, nit, input_sb=sb)
+        for c in ctxs:
+            c.wait()
+            assert c.last_half_iterations() == ncb * nit
+            assert c.last_map_launches() <= 2  # one persistent launch (+ the exact-arithmetic launch for parked blocks)
+        for o in outs:
+            bad = np.nonzero((o != want[idx]).any(axis=1))[0]
+            assert len(bad) == 0, "K=%d: %d of %d blocks differ from the oracle, first at %d (base %d)" % (K, len(bad), ncb, bad[0], idx[bad[0]])
+        if dtype == np.int16 and max(amps) > 1000:
+            assert 0 < ctxs[0].last_replayed() < ncb * nit  # some blocks really took the parked / exact path
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_fused_kernel_transport_blocks_at_scale(port):
+    """the transport-block path through k_map_fused: 360 blocks of 75376 bits (13 x K=5824) + 300 of 97896 bits in int8 on a
+    second engine at the same time, noise levels spread so that code blocks stop after 1..8 half-iterations or never; return
+    codes, bytes, per-block CRC flags and half-iteration counts of EVERY transport block against the oracle"""
+    rng = np.random.default_rng(2602)
+    jobs = []
+    for tbs, Qm, G, dtype, amp, sigmas, ntb in ((75376, 6, 90000, np.int16, 100, (0.3, 0.44, 0.5, 0.56, 0.62, 0.9), 360),
+                                                (97896, 8, 115200, np.int8, 20, (0.3, 0.40, 0.47, 0.55), 300)):
+        base, want = [], []
+        for i, sg in enumerate(sigmas * 2):
+            _, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, dtype, amp, sg)
+            sbp = port.softbuffer_new()
+            want.append(port.decode_tb(sbp, tbs, Qm, 0, llr, 8))
+            port.softbuffer_del(sbp)
+            base.append(llr)
+        idx = _spread(ntb, len(base))
+        t = b.make_tbs(ntb)
+        outs = np.zeros((ntb, tbs // 8 + 22), np.uint8)
+        for i in range(ntb):
+            t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = base[idx[i]].ctypes.data, G, tbs, Qm, 0, outs[i].ctypes.data
+        jobs.append((b.Context(0), t, dtype == np.int8, tbs, idx, base, want, outs))
+    try:
+        for c, t, is8, *_ in jobs:
+            c.decode_tbs(t, is8, 8, submit_only=True)
+        for c, t, is8, tbs, idx, base, want, outs in jobs:
+            c.wait()
+            seen = set()
+            for i in range(len(t)):
+                rc, d, nit, avg, crc = want[idx[i]]
+                C_ = t[i].nof_cb
+                nb = tbs // 8 + 6
+                assert t[i].ret == rc, (tbs, i)
+                assert (outs[i][:nb] == d[:nb]).all(), (tbs, i)
+                assert list(t[i].cb_noi[:C_]) == nit[:C_].tolist(), (tbs, i)
+                assert list(t[i].cb_crc[:C_]) == crc[:C_].tolist(), (tbs, i)
+                seen.update(nit[:C_].tolist())
+            assert len(seen) >= 4 and c.last_map_launches() <= 2
+    finally:
+        for j in jobs:
+            j[0].close()
