@@ -209,6 +209,8 @@ int Engine::create(Engine** out, int device)
     e->opt_latency = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED"))
     e->opt_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
+    e->opt_fused_warps = atoi(ev);
   CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreate(&e->ev_begin));
   CUDA_OK(cudaEventCreate(&e->ev_end));
@@ -260,13 +262,22 @@ int Engine::build_tables()
       if (lanes > 1 && (K % lanes != 0 || K / lanes < (uint32_t)kWinOverlap))
         continue;
       qpp_off[li][ci] = (uint32_t)qpp.size();
-      qpp.resize(qpp.size() + 3 * K);
+      // fwd[K] | rev[K] | (windowed decoders) one record per 8-step tile for the fused kernel's DEC2 pass: the tile's 8 rows of
+      // fwd[], then the NATURAL bit index of each of those targets (DEC2's hard decisions go straight to the natural-order
+      // bit string); a partial top tile is padded with zeros
+      const uint32_t W = lanes > 1 ? K / lanes : 0, nT = (W + 7) / 8;
+      qpp.resize(qpp.size() + 2 * K + (size_t)nT * 16 * lanes);
       uint16_t* fwd = &qpp[qpp_off[li][ci]];
       qpp_tables(K, lanes, fwd, fwd + K);
-      // nat[i]: natural bit index of the element fwd[i] points at (DEC2's hard decisions go straight to the natural-order
-      // bit string of the fused kernel)
-      for (uint32_t i = 0; i < K; i++)
-        fwd[2 * K + i] = (uint16_t)(lanes > 1 ? from_lane(fwd[i], K, lanes) : fwd[i]);
+      uint16_t* fn = fwd + 2 * K;
+      for (uint32_t t = 0; t < nT; t++)
+        for (uint32_t r = 0; r < 8; r++)
+          for (uint32_t l = 0; l < lanes; l++) {
+            const uint32_t row = 8 * t + r;
+            const uint16_t f   = row < W ? fwd[row * lanes + l] : (uint16_t)0;
+            fn[(size_t)t * 16 * lanes + r * lanes + l]             = f;
+            fn[(size_t)t * 16 * lanes + 8 * lanes + r * lanes + l] = (uint16_t)(row < W ? from_lane(f, K, lanes) : 0);
+          }
     }
   }
   // rate de-matching base tables for layout {standard, 8, 16, 32 lanes}
@@ -501,17 +512,18 @@ struct FusedGeom {
   int grid, warps, warp_words, bits_words;
 };
 template <int N>
-static FusedGeom fused_geometry(int n_groups, int max_k, int num_sms)
+static FusedGeom fused_geometry(int n_groups, int max_k, int num_sms, int warps_per_cta)
 {
   constexpr int T = N / 2, G = 32 / T;
   FusedGeom     g;
   g.bits_words = (max_k + 31) / 32;
   g.warp_words = (FusedLay<T>::kFixedWords + G * g.bits_words + 31) / 32 * 32;
-  int warps    = std::min(12, std::max(1, (n_groups + num_sms - 1) / num_sms));
-  while (warps > 1 && (size_t)warps * g.warp_words * 4 > 232448)
-    warps--;
-  g.warps = warps;
-  g.grid  = std::min(num_sms, (n_groups + warps - 1) / warps);
+  // one warp per CTA, 12 CTAs per SM: a warp that finds the list dry exits and frees its registers and shared memory for
+  // the next kernel in flight (another engine's batch) instead of waiting for the slowest warp of a larger CTA
+  g.warps = std::max(1, std::min(12, warps_per_cta));
+  while (g.warps > 1 && (size_t)g.warps * g.warp_words * 4 > 232448)
+    g.warps--;
+  g.grid = std::min((12 / g.warps) * num_sms, (n_groups + g.warps - 1) / g.warps);
   return g;
 }
 template <class P, int N>
@@ -768,10 +780,11 @@ int Engine::run(Plan& p)
       const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
       if (cls_fused[c]) {
         // one checkpoint (256 words per warp) per 8-step tile + the start state, per RESIDENT warp
-        fgeo[c] = kWinClasses[c].lanes == 8 ? fused_geometry<8>(n_groups, cls[c].max_k, num_sms)
-                                            : kWinClasses[c].lanes == 16 ? fused_geometry<16>(n_groups, cls[c].max_k, num_sms)
-                                                                         : fused_geometry<32>(n_groups, cls[c].max_k, num_sms);
-        need = std::max(need, (size_t)fgeo[c].grid * fgeo[c].warps * (((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+        fgeo[c] = kWinClasses[c].lanes == 8 ? fused_geometry<8>(n_groups, cls[c].max_k, num_sms, opt_fused_warps)
+                                            : kWinClasses[c].lanes == 16 ? fused_geometry<16>(n_groups, cls[c].max_k, num_sms, opt_fused_warps)
+                                                                         : fused_geometry<32>(n_groups, cls[c].max_k, num_sms, opt_fused_warps);
+        // ... and a dump area of one plane for the extrinsic values of ghost lanes
+        need = std::max(need, (size_t)fgeo[c].grid * fgeo[c].warps * ((((size_t)cls[c].max_w + 7) / 8 + 2) * 256 + ((size_t)cls[c].max_k / 2 + 31) / 32 * 32));
         continue;
       }
       int nt, blocks;
@@ -813,7 +826,8 @@ int Engine::run(Plan& p)
     a.qpp        = d_qpp.ptr;
     a.gmax       = d_gmax.ptr;
     a.ck_scratch = d_ckscratch.ptr;
-    a.ck_words   = (uint32_t)((((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+    a.dump_off   = (uint32_t)((((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+    a.ck_words   = a.dump_off + (uint32_t)(((size_t)cls[c].max_k / 2 + 31) / 32 * 32);
     a.counters   = d_counters.ptr;
     a.parked     = d_parked.ptr;
     a.winfo      = d_lists.ptr + cls[c].winfo_off;

@@ -35,7 +35,7 @@ struct FusedArgs {
   CbState*           state;
   int16_t*           ws;
   const int16_t*     tails;
-  const uint16_t*    qpp;       // per (K, lanes): fwd[K] | rev[K] | nat[K]
+  const uint16_t*    qpp;       // per (K, lanes): fwd[K] | rev[K] | per 8-step tile: fwd rows, natural bit index of their targets
   int*               gmax;
   u32*               ck_scratch; // resident warps x ck_words: beta checkpoints of the half-iteration in flight
   uint32_t           ck_words;
@@ -50,6 +50,7 @@ struct FusedArgs {
   const uint32_t*    crc_tab;   // [2][256]: CRC24A, CRC24B byte tables (global memory copy, read through L1)
   int                warp_words; // shared memory words per warp (FusedLay<T>::kFixedWords + G * bits words per block)
   int                bits_words; // words of the K-bit decision string per block (max over the class)
+  uint32_t           dump_off;   // word offset, inside a warp's ck_scratch share, of the area ghost lanes scatter into
 };
 
 template <int T>
@@ -57,12 +58,13 @@ struct FusedLay {
   static constexpr int kRows       = 8;
   static constexpr int kPlaneWords = kRows * 32;
   static constexpr int kLutWords   = kRows * T;
-  // stage: planes | QPP rows (| natural-index rows, DEC2 only) | checkpoint.  DEC1 with a-priori input stages 3 planes + 1
-  // table, DEC2 2 planes + 2 tables; the checkpoint sits behind the larger of the two
-  static constexpr int kCkOff      = 3 * kPlaneWords + kLutWords;
-  static constexpr int kStageWords = (kCkOff + 256 + 31) / 32 * 32;
+  // stage: planes | QPP rows (| natural-index rows, DEC2 only).  DEC1 with a-priori input stages 3 planes + 1 table, DEC2
+  // 2 planes + 2 tables.  The beta checkpoint of an alpha tile is requested one tile later than its planes and lands in a
+  // ring of two (it only has to arrive before its tile is consumed; the third copy of it was 1 KB of shared memory per warp)
+  static constexpr int kStageWords = (3 * kPlaneWords + kLutWords + 31) / 32 * 32;
   static constexpr int kStages     = 3;
-  static constexpr int kYOff       = kStages * kStageWords;  // beta spill [3][2 halves][32 lanes][4 words]
+  static constexpr int kCkRing     = kStages * kStageWords;  // [2][2 halves][32 lanes][4 words]
+  static constexpr int kYOff       = kCkRing + 2 * 256;      // beta spill [3][2 halves][32 lanes][4 words]
   static constexpr int kBarOff     = kYOff + 3 * 256;        // kStages mbarriers
   static constexpr int kBitsOff    = kBarOff + 8;            // decision bits: G blocks x bits_words
   static constexpr int kFixedWords = kBitsOff;
@@ -111,28 +113,43 @@ struct FusedWarp {
   u32*     bits;      // decision bits of this thread's block
 };
 
-// ONE half-iteration of the group.  MODE: 0 = DEC1 without a-priori input, 1 = DEC1, 2 = DEC2.  BITS: the hard decisions of
-// this half-iteration are needed (a CRC check or the end of the run follows).
+// ONE half-iteration of the group.  kDec2: constituent decoder 2 (inputs app2 | par1, outputs scattered through fwd[]), else
+// decoder 1 (inputs syst | par0 | a-priori, outputs scattered through rev[]).  Only two bodies exist per kernel -- the code of
+// one body is ~50 KB and twelve warps of an SM sit in different phases, so every extra specialisation costs instruction-
+// cache misses (a six-body build ran the int8 kernel at a 59 % instruction-cache hit rate):
+//   has_apr  DEC1 only: false for the first half-iteration, whose tiles carry two planes; the a-priori slice of the staging
+//            area is zeroed instead, and x = 0 + systematic, e = llr - 0 are the reference's values
+//   bits     the hard decisions of this half-iteration are needed (a CRC check or the end of the run follows)
 // Returns true for the threads of blocks whose Fast16 range monitor cannot rule a saturation out.
-template <class P, int N, int MODE, bool BITS>
+template <class P, int N, bool kDec2>
 __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs& a, const CUtensorMap* tmap, int blk0, int W, int K, const uint16_t* q,
-                                           int16_t* ws, size_t ps, const int16_t* tl, int g_in, uint32_t d_sat, bool live, int& ge_out)
+                                           int16_t* ws, size_t ps, const int16_t* tl, int g_in, uint32_t d_sat, bool live, int& ge_out, bool has_apr,
+                                           bool bits)
 {
   constexpr int  T = N / 2;
   constexpr int  kNP = P::kNormPeriod;
-  constexpr bool kDec2 = MODE == 2, kApr = MODE == 1;
   using Lay = FusedLay<T>;
   constexpr int      kStages   = Lay::kStages;
-  constexpr int      kPlanes   = kApr ? 3 : 2;
-  constexpr int      kLutOff   = kPlanes * Lay::kPlaneWords;
+  constexpr int      kLutOff   = (kDec2 ? 2 : 3) * Lay::kPlaneWords;
   constexpr int      kNatOff   = kLutOff + Lay::kLutWords;
   constexpr int      plane0    = kDec2 ? kPlApp2 : kPlSyst;
-  constexpr unsigned kBoxBytes = (unsigned)kPlanes * Lay::kRows * 128u;
+  const unsigned     kBoxBytes = (unsigned)((!kDec2 && has_apr) ? 3 : 2) * Lay::kRows * 128u;
   const int      lane = w.lane, j = w.j;
   const unsigned gmask = w.gmask;
   const u32*     my   = w.sm + lane; // a box row holds one word per lane
-  const u32*     lut  = (const u32*)(kDec2 ? q : q + K);     // rev[] pairs for DEC1, fwd[] pairs for DEC2
-  const u32*     natl = (const u32*)(q + 2 * (size_t)K);     // natural bit index of fwd[]'s targets (DEC2 decisions)
+  // QPP rows of a tile: rev[] pairs for DEC1; for DEC2 one record per tile, fwd[] pairs then the natural bit index of their
+  // targets (the hard decisions of DEC2 go straight to the natural-order bit string)
+  const u32*     lut  = (const u32*)(kDec2 ? q + 2 * (size_t)K : q + K);
+
+  if (!kDec2 && !has_apr) {
+    // first half-iteration: no a-priori input.  The third plane of every stage is not written by the two-plane tiles
+#pragma unroll
+    for (int sidx = 0; sidx < kStages; sidx++)
+#pragma unroll
+      for (int i = 0; i < Lay::kRows; i++)
+        w.sm[sidx * Lay::kStageWords + 2 * Lay::kPlaneWords + i * 32 + lane] = 0;
+    asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+  }
 
   // tile sequence: beta warm-up (tiles 4..0), beta main (top..0), alpha warm-up (a0..top), alpha main (0..top)
   const int nT  = (W + 7) >> 3;
@@ -142,7 +159,13 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   auto bar_of = [&](int stage) -> unsigned { return w.sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * stage); };
   int  wr_idx = 0;
   auto issue = [&]() {
-    __syncwarp(); // every lane is done with the stage about to be refilled
+    __syncwarp(); // every lane is done with the stage (and the checkpoint slot) about to be refilled
+    if (lane == 0 && wr_idx > s3 && wr_idx <= n_seq) {
+      // checkpoint beta[8(t+1)] of the alpha tile whose planes the PREVIOUS call requested: same mbarrier, ring slot t & 1
+      const int      t     = wr_idx - 1 - s3;
+      const int      stage = w.wr_stage == 0 ? kStages - 1 : w.wr_stage - 1;
+      bulk_g2s_hint(w.sm_s + 4u * (unsigned)(Lay::kCkRing + (t & 1) * 256), w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar_of(stage), w.pol_first);
+    }
     if (wr_idx < n_seq) {
       if (lane == 0) {
         const unsigned bar = bar_of(w.wr_stage);
@@ -159,20 +182,17 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
           t   = wr_idx - s3;
           aux = true;
         }
-        const int      r1        = (8 * t + 8) < W ? 8 : W - 8 * t;
-        const unsigned lut_bytes = (unsigned)r1 * T * 4u;
-        const unsigned n_lut     = (kDec2 && BITS) ? 2u : 1u;
-        mbar_expect_tx(bar, aux ? kBoxBytes + n_lut * lut_bytes + 1024u : kBoxBytes);
+        // (the tables are padded to whole tiles: a partial top tile copies rows nobody reads)
+        const unsigned lut_bytes = (kDec2 && bits) ? 2u * Lay::kLutWords * 4u : Lay::kLutWords * 4u;
+        mbar_expect_tx(bar, aux ? kBoxBytes + lut_bytes + 1024u : kBoxBytes);
         tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, w.pol_first);
-        if (aux) {
-          bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)8 * t * T, lut_bytes, bar);
-          if (kDec2 && BITS)
-            bulk_g2s(dst + 4u * (unsigned)kNatOff, natl + (size_t)8 * t * T, lut_bytes, bar);
-          bulk_g2s_hint(dst + 4u * (unsigned)Lay::kCkOff, w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar, w.pol_first);
-        }
+        if (aux)
+          bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)t * (kDec2 ? 2 : 1) * Lay::kLutWords, lut_bytes, bar);
       }
       wr_idx++;
       w.wr_stage = w.wr_stage + 1 == kStages ? 0 : w.wr_stage + 1;
+    } else if (wr_idx == n_seq) {
+      wr_idx++; // (the last checkpoint has just been requested)
     }
   };
   auto acquire = [&]() -> const u32* {
@@ -186,7 +206,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   auto row = [&](const u32* tb, int i, u32& x, u32& y) {
     const u32 vin = tb[i * 32];
     y             = tb[Lay::kPlaneWords + i * 32];
-    x             = kApr ? P::add(tb[2 * Lay::kPlaneWords + i * 32], vin) : vin;
+    x             = kDec2 ? vin : P::add(tb[2 * Lay::kPlaneWords + i * 32], vin); // (first half-iteration: the a-priori slice is zero)
   };
 
 #pragma unroll
@@ -329,7 +349,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
 
   // ---- output pass
   // extrinsic output, scattered through the QPP rows
-  char* const ext = reinterpret_cast<char*>(kDec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps);
+  // (ghost lanes -- blocks of the group that are finished or parked -- run the same instruction stream without a branch:
+  //  their extrinsic values go to the warp's dump area, their decision bits to their own unused bit string)
+  char* const ext = live ? reinterpret_cast<char*>(kDec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps) : reinterpret_cast<char*>(w.ck_warp + a.dump_off);
   u32         ehi = 0, elo = 0, e_even = 0;
   u32         al[8];
 #pragma unroll
@@ -342,7 +364,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   auto flush_bits = [&](int p_end) {
     if (acc_n == 0)
       return;
-    if (live) {
+    {
 #pragma unroll
       for (int h = 0; h < 2; h++) {
         const u32      v  = h ? (acc >> 16) : (acc & 0xffffu);
@@ -385,37 +407,32 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         }
       }
     };
-    // hard decisions (llr > 0), one bit per int16 half: 1 where positive
-    const u32 dbit = BITS ? __vimin_s16x2_relu(llr, 0x00010001u) : 0u;
-    u32       e;
+    u32 e;
     if (!kDec2) {
       // extrinsic - a-priori -> app2[rev[.]]; decisions stay in this thread's lanes: accumulate, flush every 16 steps
       const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
-      e = kApr ? P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat) : llr;
-      if (BITS) {
-        acc = acc * 2u + dbit;
+      e = P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat);
+      if (bits) {
+        acc = acc * 2u + __vimin_s16x2_relu(llr, 0x00010001u); // hard decisions (llr > 0), one bit per int16 half
         acc_n++;
       }
     } else {
       // a-posteriori - own input -> a-priori[fwd[.]]; decisions belong to natural positions nat[.]
       e = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
-      if (BITS) {
+      if (bits) {
+        const u32       dbit = __vimin_s16x2_relu(llr, 0x00010001u);
         const uint16_t* n16 = reinterpret_cast<const uint16_t*>(tb + (kNatOff + i * T + j - lane));
         const uint32_t  n0 = n16[0], n1 = n16[1];
-        if (live) {
-          atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
-          atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
-        }
+        atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
+        atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
       }
     }
     track_e(e);
-    if (live) {
-      *reinterpret_cast<int16_t*>(ext + 2u * t0) = (int16_t)lo16(e);
-      *reinterpret_cast<int16_t*>(ext + 2u * t1) = (int16_t)hi16(e);
-    }
+    *reinterpret_cast<int16_t*>(ext + 2u * t0) = (int16_t)lo16(e);
+    *reinterpret_cast<int16_t*>(ext + 2u * t1) = (int16_t)hi16(e);
   };
-  auto ck_load = [&](const u32* tb, u32 (&v)[8]) { // checkpoint of the tile: [half][lane][4 words]
-    const uint4* c = reinterpret_cast<const uint4*>(tb - lane + Lay::kCkOff) + lane;
+  auto ck_load = [&](int t, u32 (&v)[8]) { // checkpoint of alpha tile t: [half][lane][4 words]
+    const uint4* c = reinterpret_cast<const uint4*>(w.sm + Lay::kCkRing + (t & 1) * 256) + lane;
     const uint4  lo = c[0], hi = c[32];
     v[0] = lo.x; v[1] = lo.y; v[2] = lo.z; v[3] = lo.w;
     v[4] = hi.x; v[5] = hi.y; v[6] = hi.z; v[7] = hi.w;
@@ -427,7 +444,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     const u32* tb = acquire();
     u32        bs[4][8];
     // ---- recompute beta_{8t+7} .. beta_{8t+1} from the checkpoint beta_{8t+8}
-    ck_load(tb, st);
+    ck_load(t, st);
     if (8 * (t + 1) < W)
       P::normalize_now(st); // the recursion continued from the normalised value; beta[W] itself was never normalised
 #pragma unroll
@@ -463,12 +480,12 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       bs[y][0] = lo.x; bs[y][1] = lo.y; bs[y][2] = lo.z; bs[y][3] = lo.w;
       bs[y][4] = hi.x; bs[y][5] = hi.y; bs[y][6] = hi.z; bs[y][7] = hi.w;
     }
-    ck_load(tb, bs[3]);
+    ck_load(t, bs[3]);
 #pragma unroll
     for (int i = 4; i < 8; i++)
       out_step(tb, t, i, bs[i - 4], mon_a, true);
-    if (BITS && !kDec2 && (t & 1))
-      flush_bits(8 * t + 8);
+    if (!kDec2 && (t & 1))
+      flush_bits(8 * t + 8); // (nothing accumulated when the decisions are not needed)
   }
   if (W & 7) {
     // partial top tile, guarded: beta_{p+1} of each step is recomputed from the checkpoint beta[W] (at most 6 steps)
@@ -478,7 +495,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
 #pragma unroll 1
     for (int i = 0; i < nv; i++) {
       u32 b[8];
-      ck_load(tb, b);
+      ck_load(t, b);
 #pragma unroll 1
       for (int kk = nv - 1; kk > i; kk--) { // -> beta_{8t+kk}, normalised on the way except the one that is used
         u32 x, y;
@@ -490,7 +507,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       out_step(tb, t, i, b, mon_a, true); // (t >= 5 here: a lane has at least 40 steps)
     }
   }
-  if (BITS && !kDec2)
+  if (!kDec2)
     flush_bits(W);
 
   ge_out = 0;
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
   const int wib  = threadIdx.x >> 5;
 
   FusedWarp<T> w;
-  w.sm        = smem_f + (size_t)wib * a.warp_words;
+  w.sm        = smem_f + (size_t)wib * a.warp_words; // (one warp per CTA: a finished warp hands its share of the SM back)
   w.sm_s      = (unsigned)__cvta_generic_to_shared(w.sm);
   w.lane      = lane;
   w.j         = lane % T;
@@ -623,19 +640,11 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
       }
       bool flagged;
       int  ge = 0;
-      if (niter & 1) {
-        const int g = g_ext + g_par1;
-        flagged = want_bits ? fused_half<P, N, 2, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
-                            : fused_half<P, N, 2, false>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
-      } else if (niter) {
-        const int g = g_ext + g_syst + g_par0;
-        flagged = want_bits ? fused_half<P, N, 1, true>(w, a, tmap3, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
-                            : fused_half<P, N, 1, false>(w, a, tmap3, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
-      } else {
-        const int g = g_syst + g_par0;
-        flagged = want_bits ? fused_half<P, N, 0, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge)
-                            : fused_half<P, N, 0, false>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge);
-      }
+      if (niter & 1)
+        flagged = fused_half<P, N, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g_ext + g_par1, d_sat, live, ge, false, want_bits);
+      else
+        flagged = fused_half<P, N, false>(w, a, niter ? tmap3 : tmap3 + 1, blk0, W, K, q, ws, ps, tl, (niter ? g_ext : 0) + g_syst + g_par0, d_sat, live, ge,
+                                          niter != 0, want_bits);
       g_ext = ge;
       __syncwarp(); // the decision bits of every lane are in shared memory
       if (P::kMonitor && flagged) {
