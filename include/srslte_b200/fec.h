@@ -67,6 +67,19 @@ SRSLTE_API uint32_t srslte_crc_checksum_byte(srslte_crc_t* h, uint8_t* data, int
 SRSLTE_API uint32_t srslte_crc_checksum(srslte_crc_t* h, uint8_t* data, int len);                     /* crc.c:102 */
 SRSLTE_API uint32_t srslte_crc_attach_byte(srslte_crc_t* h, uint8_t* data, int len);                  /* crc.c:159 */
 SRSLTE_API uint32_t srslte_crc_attach(srslte_crc_t* h, uint8_t* data, int len);                       /* crc.c:172 */
+/* crc.h:56-70: the two header-only helpers of the reference.  They stay host code here as they are there: their one caller
+ * is the TRANSMIT-side encoder srslte_tcod_encode_lut (turbocoder.c:190-196), which is outside the replaced path and keeps
+ * running on the CPU; they only touch the srslte_crc_t fields kept above (table, order, crcinit, crcmask). */
+static inline void srslte_crc_checksum_put_byte(srslte_crc_t* h, uint8_t byte)
+{
+  const uint64_t c  = h->crcinit;
+  const uint64_t ix = ((c >> (h->order - 8)) & 0xff) ^ byte; /* polynomial order 8, 16, 24 or 32 */
+  h->crcinit        = (c << 8) ^ h->table[ix];
+}
+static inline uint64_t srslte_crc_checksum_get(srslte_crc_t* h)
+{
+  return h->crcinit & h->crcmask;
+}
 
 /* ---------------------------------------------------------------- turbodecoder_impl.h:28-38 */
 typedef enum SRSLTE_API {
@@ -116,20 +129,38 @@ SRSLTE_API int  srslte_rm_turbo_rx_lut(int16_t* input, int16_t* output, uint32_t
 SRSLTE_API int  srslte_rm_turbo_rx_lut_(int16_t* input, int16_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx, bool enable_input_tdec); /* :410 */
 SRSLTE_API int  srslte_rm_turbo_rx_lut_8bit(int8_t* input, int8_t* output, uint32_t in_len, uint32_t cb_idx, uint32_t rv_idx);    /* :456 */
 
-/* ---------------------------------------------------------------- softbuffer.h:37-60 (receive side)
- * The HARQ soft buffer lives in GPU memory; the host struct keeps the reference's bookkeeping fields. */
+/* ---------------------------------------------------------------- softbuffer.h:37-60
+ * Field names and order of the reference are kept, so decode_tb_cb (sch.c:363-488), which dereferences buffer_f[] and
+ * data[] (sch.c:404,409,422,424,466,481), recompiles unchanged: buffer_f[i] (SOFTBUFFER_SIZE int16) and data[i] (768 bytes)
+ * are ordinary HOST arrays that the per-code-block symbols above read and write.  The batched path (srslte_b200_decode_tb,
+ * batch.h) keeps the HARQ state of the same soft buffer in GPU memory behind b200_softbuffer and never touches the host
+ * arrays; a soft buffer must be driven through ONE of the two paths between resets. */
 #define SOFTBUFFER_SIZE 18600
 typedef struct SRSLTE_API {
-  uint32_t max_cb;
-  void*    b200_softbuffer; /* device-resident buffer_f[] / data[] (softbuffer.h:39-40) */
-  bool*    cb_crc;
-  bool     tb_crc;
+  uint32_t  max_cb;
+  int16_t** buffer_f;
+  uint8_t** data;
+  bool*     cb_crc;
+  bool      tb_crc;
+  void*     b200_softbuffer; /* device-resident HARQ state of the batched path */
+  bool      b200_host_dirty; /* the per-code-block path wrote into buffer_f[] since the last reset */
 } srslte_softbuffer_rx_t;
 SRSLTE_API int  srslte_softbuffer_rx_init(srslte_softbuffer_rx_t* q, uint32_t nof_prb);       /* softbuffer.c:41 */
 SRSLTE_API void srslte_softbuffer_rx_reset(srslte_softbuffer_rx_t* p);                        /* :128 */
 SRSLTE_API void srslte_softbuffer_rx_reset_tbs(srslte_softbuffer_rx_t* q, uint32_t tbs);      /* :122 */
 SRSLTE_API void srslte_softbuffer_rx_reset_cb(srslte_softbuffer_rx_t* q, uint32_t nof_cb);    /* :133 */
 SRSLTE_API void srslte_softbuffer_rx_free(srslte_softbuffer_rx_t* p);                         /* :97  */
+/* transmit-side soft buffer (softbuffer.h:45-48, softbuffer.c:157-245): host memory management only, kept so that a build
+ * that drops the reference's softbuffer.c still links its CPU encoder (encode_tb_off, sch.c:235-349) */
+typedef struct SRSLTE_API {
+  uint32_t  max_cb;
+  uint8_t** buffer_b;
+} srslte_softbuffer_tx_t;
+SRSLTE_API int  srslte_softbuffer_tx_init(srslte_softbuffer_tx_t* q, uint32_t nof_prb);       /* softbuffer.c:157 */
+SRSLTE_API void srslte_softbuffer_tx_reset(srslte_softbuffer_tx_t* p);                        /* :209 */
+SRSLTE_API void srslte_softbuffer_tx_reset_tbs(srslte_softbuffer_tx_t* q, uint32_t tbs);      /* :203 */
+SRSLTE_API void srslte_softbuffer_tx_reset_cb(srslte_softbuffer_tx_t* q, uint32_t nof_cb);    /* :214 */
+SRSLTE_API void srslte_softbuffer_tx_free(srslte_softbuffer_tx_t* p);                         /* :190 */
 
 /* ---------------------------------------------------------------- sch.c:503-570 decode_tb as one call
  * What decode_tb (static in sch.c) becomes: same arguments (q's relevant state passed explicitly), same return

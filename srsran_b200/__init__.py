@@ -73,8 +73,6 @@ class Tdec(C.Structure):  # srslte_tdec_t
                 ("current_long_cb", C.c_uint32), ("current_cbidx", C.c_int), ("n_iter", C.c_int)]
 
 
-class SoftbufferRx(C.Structure):  # srslte_softbuffer_rx_t
-    _fields_ = [("max_cb", C.c_uint32), ("b200_softbuffer", C.c_void_p), ("cb_crc", C.POINTER(C.c_bool)), ("tb_crc", C.c_bool)]
 
 
 _lib = None
@@ -499,8 +497,9 @@ class SoftbufferRx:
 SoftbufferRx_t = SoftbufferRx  # placeholder, replaced below
 
 
-class _SoftbufferRxStruct(C.Structure):  # srslte_softbuffer_rx_t
-    _fields_ = [("max_cb", C.c_uint32), ("b200_softbuffer", C.c_void_p), ("cb_crc", C.POINTER(C.c_bool)), ("tb_crc", C.c_bool)]
+class _SoftbufferRxStruct(C.Structure):  # srslte_softbuffer_rx_t (the reference's fields, then the device handle)
+    _fields_ = [("max_cb", C.c_uint32), ("buffer_f", C.POINTER(C.POINTER(C.c_int16))), ("data", C.POINTER(C.POINTER(C.c_uint8))),
+                ("cb_crc", C.POINTER(C.c_bool)), ("tb_crc", C.c_bool), ("b200_softbuffer", C.c_void_p), ("b200_host_dirty", C.c_bool)]
 
 
 SoftbufferRx_t = _SoftbufferRxStruct

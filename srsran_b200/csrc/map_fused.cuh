@@ -58,10 +58,10 @@ struct FusedLay {
   static constexpr int kRows       = 8;
   static constexpr int kPlaneWords = kRows * 32;
   static constexpr int kLutWords   = kRows * T;
-  // stage: planes | QPP rows (| natural-index rows, DEC2 only).  DEC1 with a-priori input stages 3 planes + 1 table, DEC2
-  // 2 planes + 2 tables.  The beta checkpoint of an alpha tile is requested one tile later than its planes and lands in a
+  // stage: three plane slices | QPP rows | natural-index rows (decoder 2 only).  Decoder 1 with a-priori input stages 3
+  // planes, every other half-iteration 2 (the third slice is zeroed).  The beta checkpoint of an alpha tile is requested one tile later than its planes and lands in a
   // ring of two (it only has to arrive before its tile is consumed; the third copy of it was 1 KB of shared memory per warp)
-  static constexpr int kStageWords = (3 * kPlaneWords + kLutWords + 31) / 32 * 32;
+  static constexpr int kStageWords = (3 * kPlaneWords + 2 * kLutWords + 31) / 32 * 32;
   static constexpr int kStages     = 3;
   static constexpr int kCkRing     = kStages * kStageWords;  // [2][2 halves][32 lanes][4 words]
   static constexpr int kYOff       = kCkRing + 2 * 256;      // beta spill [3][2 halves][32 lanes][4 words]
@@ -113,36 +113,45 @@ struct FusedWarp {
   u32*     bits;      // decision bits of this thread's block
 };
 
-// ONE half-iteration of the group.  kDec2: constituent decoder 2 (inputs app2 | par1, outputs scattered through fwd[]), else
-// decoder 1 (inputs syst | par0 | a-priori, outputs scattered through rev[]).  Only two bodies exist per kernel -- the code of
-// one body is ~50 KB and twelve warps of an SM sit in different phases, so every extra specialisation costs instruction-
-// cache misses (a six-body build ran the int8 kernel at a 59 % instruction-cache hit rate):
-//   has_apr  DEC1 only: false for the first half-iteration, whose tiles carry two planes; the a-priori slice of the staging
-//            area is zeroed instead, and x = 0 + systematic, e = llr - 0 are the reference's values
+// ONE half-iteration of the group -- ONE code body for both constituent decoders.  The instruction cache behind an SM's
+// twelve warps is 32 KB (L1.5) and the warps sit in different phases of different half-iterations: a build with one
+// specialised body per (decoder, a-priori, decisions) combination ran the int8 kernel at a 59 % instruction-cache hit rate
+// and 5 stall cycles per instruction waiting for instructions.  So everything that differs between the decoders is data:
+//   dec2     decoder 2: inputs app2 | par1, extrinsic = a-posteriori - own input scattered through fwd[] into the a-priori
+//            plane, decisions at natural positions nat[.]; else decoder 1: inputs syst | par0 | a-priori, extrinsic =
+//            a-posteriori - a-priori scattered through rev[] into app2, decisions in this thread's own lanes
+//   apr3     the tiles carry three planes (decoder 1 with a-priori input).  Otherwise they carry two and the a-priori slice
+//            of every stage is zeroed once: x = 0 + input and e = llr - 0 are then the reference's values
 //   bits     the hard decisions of this half-iteration are needed (a CRC check or the end of the run follows)
+// and the unrolled bodies are shared: the two beta passes (warm-up, main) run the same 8-step tile, the alpha tile is two
+// trips through one 4-step body.
 // Returns true for the threads of blocks whose Fast16 range monitor cannot rule a saturation out.
-template <class P, int N, bool kDec2>
+// DEC: -1 = the decoder is a runtime property (one body: the int8 and exact-int16 kernels, whose code is large); 0 / 1 = this
+// instance is decoder 1 / decoder 2 (the Fast16 kernel affords two bodies: 2 x 25 KB of hot loops still hit the instruction
+// cache at 97 %, and decoder 2 then skips the add of its zero a-priori slice)
+template <class P, int N, int DEC>
 __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs& a, const CUtensorMap* tmap, int blk0, int W, int K, const uint16_t* q,
-                                           int16_t* ws, size_t ps, const int16_t* tl, int g_in, uint32_t d_sat, bool live, int& ge_out, bool has_apr,
-                                           bool bits)
+                                           int16_t* ws, size_t ps, const int16_t* tl, int g_in, uint32_t d_sat, bool live, int& ge_out, bool dec2_rt,
+                                           bool apr3, bool bits)
 {
+  const bool dec2 = DEC < 0 ? dec2_rt : DEC == 1;
   constexpr int  T = N / 2;
   constexpr int  kNP = P::kNormPeriod;
   using Lay = FusedLay<T>;
-  constexpr int      kStages   = Lay::kStages;
-  constexpr int      kLutOff   = (kDec2 ? 2 : 3) * Lay::kPlaneWords;
-  constexpr int      kNatOff   = kLutOff + Lay::kLutWords;
-  constexpr int      plane0    = kDec2 ? kPlApp2 : kPlSyst;
-  const unsigned     kBoxBytes = (unsigned)((!kDec2 && has_apr) ? 3 : 2) * Lay::kRows * 128u;
+  constexpr int  kStages = Lay::kStages;
+  constexpr int  kLutOff = 3 * Lay::kPlaneWords;
+  const int      plane0    = dec2 ? kPlApp2 : kPlSyst;
+  const unsigned kBoxBytes = (apr3 ? 3u : 2u) * Lay::kRows * 128u;
   const int      lane = w.lane, j = w.j;
   const unsigned gmask = w.gmask;
   const u32*     my   = w.sm + lane; // a box row holds one word per lane
-  // QPP rows of a tile: rev[] pairs for DEC1; for DEC2 one record per tile, fwd[] pairs then the natural bit index of their
-  // targets (the hard decisions of DEC2 go straight to the natural-order bit string)
-  const u32*     lut  = (const u32*)(kDec2 ? q + 2 * (size_t)K : q + K);
+  // QPP rows of a tile: rev[] pairs for decoder 1; for decoder 2 one record per tile, fwd[] pairs then the natural bit index
+  // of their targets
+  const u32*     lut        = (const u32*)(dec2 ? q + 2 * (size_t)K : q + K);
+  const unsigned lut_stride = dec2 ? 2u * Lay::kLutWords : (unsigned)Lay::kLutWords;
+  const unsigned lut_bytes  = (dec2 && bits) ? 2u * Lay::kLutWords * 4u : Lay::kLutWords * 4u;
 
-  if (!kDec2 && !has_apr) {
-    // first half-iteration: no a-priori input.  The third plane of every stage is not written by the two-plane tiles
+  if (!apr3) {
 #pragma unroll
     for (int sidx = 0; sidx < kStages; sidx++)
 #pragma unroll
@@ -162,8 +171,8 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     __syncwarp(); // every lane is done with the stage (and the checkpoint slot) about to be refilled
     if (lane == 0 && wr_idx > s3 && wr_idx <= n_seq) {
       // checkpoint beta[8(t+1)] of the alpha tile whose planes the PREVIOUS call requested: same mbarrier, ring slot t & 1
-      const int      t     = wr_idx - 1 - s3;
-      const int      stage = w.wr_stage == 0 ? kStages - 1 : w.wr_stage - 1;
+      const int t     = wr_idx - 1 - s3;
+      const int stage = w.wr_stage == 0 ? kStages - 1 : w.wr_stage - 1;
       bulk_g2s_hint(w.sm_s + 4u * (unsigned)(Lay::kCkRing + (t & 1) * 256), w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar_of(stage), w.pol_first);
     }
     if (wr_idx < n_seq) {
@@ -183,11 +192,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
           aux = true;
         }
         // (the tables are padded to whole tiles: a partial top tile copies rows nobody reads)
-        const unsigned lut_bytes = (kDec2 && bits) ? 2u * Lay::kLutWords * 4u : Lay::kLutWords * 4u;
         mbar_expect_tx(bar, aux ? kBoxBytes + lut_bytes + 1024u : kBoxBytes);
         tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, w.pol_first);
         if (aux)
-          bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)t * (kDec2 ? 2 : 1) * Lay::kLutWords, lut_bytes, bar);
+          bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)t * lut_stride, lut_bytes, bar);
       }
       wr_idx++;
       w.wr_stage = w.wr_stage + 1 == kStages ? 0 : w.wr_stage + 1;
@@ -203,10 +211,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     w.rd_stage    = w.rd_stage + 1 == kStages ? 0 : w.rd_stage + 1;
     return tb;
   };
+  // x (input + a-priori) and y (parity) of box row i
   auto row = [&](const u32* tb, int i, u32& x, u32& y) {
-    const u32 vin = tb[i * 32];
-    y             = tb[Lay::kPlaneWords + i * 32];
-    x             = kDec2 ? vin : P::add(tb[2 * Lay::kPlaneWords + i * 32], vin); // (first half-iteration: the a-priori slice is zero)
+    y = tb[Lay::kPlaneWords + i * 32];
+    x = DEC == 1 ? tb[i * 32] : P::add(tb[2 * Lay::kPlaneWords + i * 32], tb[i * 32]);
   };
 
 #pragma unroll
@@ -220,64 +228,57 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   u32 st[8];
 
   // =============================================================== backward
-  // ---- warm-up: steps 39..0 of the lane's own sub-block from the all-"unknown" state (win.h:622-630)
-#pragma unroll
-  for (int s = 0; s < 8; s++)
-    st[s] = splat16(-P::kInf);
-  for (int t = 4; t >= 0; t--) {
-    const u32* tb = acquire();
-#pragma unroll
-    for (int i = 7; i >= 0; i--) {
-      u32 x, y;
-      row(tb, i, x, y);
-      bwd_step<P>(st, x, y, P::add(x, y));
-      if (P::kMonitor && (i & 1) == 0 && (t < 4 || i < 6))
-        mon_b.track(st); // k < 38: the first two steps start from eight equal values (spread 0, covered by g)
-      if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
-        P::normalize_now(st);
-    }
-  }
-  // hand the estimate to the lane below; tail trellis for the last lane (win.h:580-612, 500-548)
-#pragma unroll
-  for (int s = 0; s < 8; s++) {
-    const u32 nx = __shfl_down_sync(gmask, st[s], 1, T);
-    st[s]        = shift_down_lanes(st[s], nx);
-  }
-  if (j == T - 1) {
-    int32_t tt[8];
-    tail_trellis<P>(kDec2 ? tl + 6 : tl, kDec2 ? tl + 9 : tl + 3, tt);
-#pragma unroll
-    for (int s = 0; s < 8; s++)
-      st[s] = (st[s] & 0xffffu) | ((u32)(uint16_t)tt[s] << 16);
-  }
-  // ---- main pass with one checkpoint per tile: slot t = beta[8t] before normalisation, slot nT = beta[W]
-  // (every lane stores, ghosts too: the scratch belongs to the warp and nobody else reads it)
+  // pass 0: warm-up, steps 39..0 of the lane's own sub-block from the all-"unknown" state (win.h:622-630)
+  // pass 1: main pass from the neighbour's estimate / the tail trellis, one checkpoint per tile: slot t = beta[8t] before
+  //         normalisation, slot nT = beta[W]  (every lane stores, ghosts too: the scratch belongs to the warp)
   auto ck_store = [&](int sl, const u32 (&v)[8]) {
     uint4* g = reinterpret_cast<uint4*>(w.ck_warp + (size_t)sl * 256) + lane;
     stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), w.pol_last);
     stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), w.pol_last);
   };
-  if (P::kMonitor)
-    mon_b.track(st);
-  ck_store(nT, st);
-  {
-    int t = nT - 1;
-    if (W & 7) { // partial top tile: guarded, rolled
-      const u32* tb = acquire();
+#pragma unroll
+  for (int s = 0; s < 8; s++)
+    st[s] = splat16(-P::kInf);
 #pragma unroll 1
-      for (int i = (W & 7) - 1; i >= 0; i--) {
-        u32 x, y;
-        row(tb, i, x, y);
-        bwd_step<P>(st, x, y, P::add(x, y));
-        if (i == 0)
-          ck_store(t, st);
-        if (P::kMonitor && (i & 1) == 0)
-          mon_b.track(st);
-        if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
-          P::normalize_now(st);
+  for (int pass = 0; pass < 2; pass++) {
+    int t = 4;
+    if (pass == 1) {
+      // hand the estimate to the lane below; tail trellis for the last lane (win.h:580-612, 500-548)
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        const u32 nx = __shfl_down_sync(gmask, st[s], 1, T);
+        st[s]        = shift_down_lanes(st[s], nx);
       }
-      t--;
+      if (j == T - 1) {
+        int32_t tt[8];
+        tail_trellis<P>(dec2 ? tl + 6 : tl, dec2 ? tl + 9 : tl + 3, tt);
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          st[s] = (st[s] & 0xffffu) | ((u32)(uint16_t)tt[s] << 16);
+      }
+      if (P::kMonitor)
+        mon_b.track(st);
+      ck_store(nT, st);
+      t = nT - 1;
+      if (W & 7) { // partial top tile: guarded, rolled
+        const u32* tb = acquire();
+#pragma unroll 1
+        for (int i = (W & 7) - 1; i >= 0; i--) {
+          u32 x, y;
+          row(tb, i, x, y);
+          bwd_step<P>(st, x, y, P::add(x, y));
+          if (i == 0)
+            ck_store(t, st);
+          if (P::kMonitor && (i & 1) == 0)
+            mon_b.track(st);
+          if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
+            P::normalize_now(st);
+        }
+        t--;
+      }
     }
+    const bool main_pass = pass == 1;
+#pragma unroll 1
     for (; t >= 0; t--) {
       const u32* tb = acquire();
 #pragma unroll
@@ -285,9 +286,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         u32 x, y;
         row(tb, i, x, y);
         bwd_step<P>(st, x, y, P::add(x, y));
-        if (i == 0)
+        if (i == 0 && main_pass)
           ck_store(t, st);
-        if (P::kMonitor && (i & 1) == 0)
+        // warm-up, k = 38 (t = 4, i = 6): the first two steps start from eight equal values (spread 0, covered by g)
+        if (P::kMonitor && (i & 1) == 0 && (i != 6 || main_pass || t < 4))
           mon_b.track(st);
         if ((kNP == 1 || (i & 1) == 0) && (i != 0 || t != 0))
           P::normalize_now(st);
@@ -315,6 +317,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     st[s] = splat16(-P::kInf);
   {
     int kk = 0; // loop counter of the pass
+#pragma unroll 1
     for (int t = a0; t < nT; t++) {
       const u32* tb = acquire();
       const int  i0 = t == a0 ? (W - kWinOverlap) - 8 * a0 : 0;
@@ -348,41 +351,45 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     mon_h.track(st);
 
   // ---- output pass
-  // extrinsic output, scattered through the QPP rows
   // (ghost lanes -- blocks of the group that are finished or parked -- run the same instruction stream without a branch:
   //  their extrinsic values go to the warp's dump area, their decision bits to their own unused bit string)
-  char* const ext = live ? reinterpret_cast<char*>(kDec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps) : reinterpret_cast<char*>(w.ck_warp + a.dump_off);
+  char* const ext = live ? reinterpret_cast<char*>(dec2 ? ws + kPlApr * ps : ws + kPlApp2 * ps) : reinterpret_cast<char*>(w.ck_warp + a.dump_off);
   u32         ehi = 0, elo = 0, e_even = 0;
   u32         al[8];
 #pragma unroll
   for (int s = 0; s < 8; s++)
     al[s] = st[s];
-  u32       acc = 0;                                  // DEC1 decisions of up to 16 steps, both lanes, first step = MSB
-  int       acc_n = 0;
+  u32         acc = 0; // decoder 1: decisions of up to 16 steps, both lanes, first step = MSB
+  int         acc_n = 0;
   char* const bits_c = reinterpret_cast<char*>(w.bits);
-  // flush the accumulated DEC1 decisions of steps [p_end - acc_n, p_end) into the natural-order bit string
+  // (the flags go through an empty asm in every tile so that the compiler cannot unswitch the loop into one copy per flag
+  //  combination: code size is what this body is about)
+  int         flags = (dec2 ? 1 : 0) | (bits && !dec2 ? 2 : 0) | (bits && dec2 ? 4 : 0);
+  bool        bits1 = false, bits2 = false, d2 = false;
+  // flush the accumulated decisions of steps [p_end - acc_n, p_end) into the natural-order bit string
   auto flush_bits = [&](int p_end) {
     if (acc_n == 0)
       return;
-    {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const u32      v  = h ? (acc >> 16) : (acc & 0xffffu);
-        const u32      r  = __brev(v) >> (32 - acc_n);                  // first step at bit 0
-        const uint32_t n0 = (uint32_t)(2 * j + h) * (uint32_t)W + (uint32_t)(p_end - acc_n);
-        const uint32_t sh = n0 & 31u;
-        atomicOr(w.bits + (n0 >> 5), r << sh);
-        if (sh + (uint32_t)acc_n > 32u)
-          atomicOr(w.bits + (n0 >> 5) + 1, r >> (32u - sh));
-      }
+    for (int h = 0; h < 2; h++) {
+      const u32      v  = h ? (acc >> 16) : (acc & 0xffffu);
+      const u32      r  = __brev(v) >> (32 - acc_n); // first step at bit 0
+      const uint32_t n0 = (uint32_t)(2 * j + h) * (uint32_t)W + (uint32_t)(p_end - acc_n);
+      const uint32_t sh = n0 & 31u;
+      atomicOr(w.bits + (n0 >> 5), r << sh);
+      if (sh + (uint32_t)acc_n > 32u)
+        atomicOr(w.bits + (n0 >> 5) + 1, r >> (32u - sh));
     }
     acc   = 0;
     acc_n = 0;
   };
 
-  auto out_step = [&](const u32* tb, int t, int i, const u32 (&b)[8], RangeMon& mon, bool norm) {
+  // one forward step with output: LLR against b = beta_{p+1}, state update, glue epilogue (iter.h:107-127).
+  // tp / tq: this lane's view of the staged plane rows / table rows at row 0 of the step's half tile; p: trellis step;
+  // i: step within the half tile (compile-time; its parity is the step's)
+  auto out_step = [&](const u32* tp, const u32* tq, int p, int i, const u32 (&b)[8], RangeMon& mon, bool norm) {
     u32 x, y;
-    row(tb, i, x, y);
+    row(tp, i, x, y);
     const u32 xy = P::add(x, y);
     u32       llr;
     if (P::kMonitor) { // wrapping arithmetic under the range monitor: factored form
@@ -395,39 +402,39 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       mon.track(al);
     if ((kNP == 1 || (i & 1) == 0) && norm)
       P::normalize_now(al);
-    const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tb + (kLutOff + i * T + j - lane));
+    const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tq + i * T);
     const uint32_t  t0 = r16[0], t1 = r16[1];
-    auto track_e = [&](u32 e) {
-      if (P::kMonitor) {
-        if ((i & 1) == 0) {
-          e_even = e;
-        } else {
-          ehi = p_max3(ehi, e_even, e);
-          elo = p_min3(elo, e_even, e);
-        }
-      }
-    };
-    u32 e;
-    if (!kDec2) {
-      // extrinsic - a-priori -> app2[rev[.]]; decisions stay in this thread's lanes: accumulate, flush every 16 steps
-      const uint32_t w2 = 2u * (uint32_t)((8 * t + i) * T + j);
-      e = P::glue_sub(llr, tb[2 * Lay::kPlaneWords + i * 32], w2 < d_sat, w2 + 1 < d_sat);
-      if (bits) {
-        acc = acc * 2u + __vimin_s16x2_relu(llr, 0x00010001u); // hard decisions (llr > 0), one bit per int16 half
-        acc_n++;
-      }
+    // decoder 1: extrinsic - a-priori -> app2[rev[.]]; decoder 2: a-posteriori - own input -> a-priori[fwd[.]]
+    // (decoder 2 has a zero a-priori slice, so x is its own input)
+    const u32 sub = d2 ? x : tp[2 * Lay::kPlaneWords + i * 32];
+    u32       e;
+    if (P::kBits == 8) { // srslte_vec_sub_bbb saturates below an element index that depends on the build (arith.cuh)
+      const uint32_t w2 = 2u * (uint32_t)(p * T + j);
+      e = P::glue_sub(llr, sub, (d2 ? t0 : w2) < d_sat, (d2 ? t1 : w2 + 1) < d_sat);
     } else {
-      // a-posteriori - own input -> a-priori[fwd[.]]; decisions belong to natural positions nat[.]
-      e = P::glue_sub(llr, x, t0 < d_sat, t1 < d_sat);
-      if (bits) {
-        const u32       dbit = __vimin_s16x2_relu(llr, 0x00010001u);
-        const uint16_t* n16 = reinterpret_cast<const uint16_t*>(tb + (kNatOff + i * T + j - lane));
-        const uint32_t  n0 = n16[0], n1 = n16[1];
-        atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
-        atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
+      e = P::glue_sub(llr, sub, false, false);
+    }
+    if (P::kMonitor) { // running max / min of the extrinsic values, two steps per VIMNMX3
+      if ((i & 1) == 0) {
+        e_even = e;
+      } else {
+        ehi = p_max3(ehi, e_even, e);
+        elo = p_min3(elo, e_even, e);
       }
     }
-    track_e(e);
+    if (bits1) {
+      // decisions stay in this thread's lanes: accumulate (llr > 0 -> 1, one bit per int16 half), flush every 16 steps
+      acc = acc * 2u + __vimin_s16x2_relu(llr, 0x00010001u);
+      acc_n++;
+    }
+    if (bits2) {
+      // decisions belong to natural positions nat[.]
+      const u32       dbit = __vimin_s16x2_relu(llr, 0x00010001u);
+      const uint16_t* n16 = reinterpret_cast<const uint16_t*>(tq + Lay::kLutWords + i * T);
+      const uint32_t  n0 = n16[0], n1 = n16[1];
+      atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
+      atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
+    }
     *reinterpret_cast<int16_t*>(ext + 2u * t0) = (int16_t)lo16(e);
     *reinterpret_cast<int16_t*>(ext + 2u * t1) = (int16_t)hi16(e);
   };
@@ -440,10 +447,16 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   uint4* const ysp = reinterpret_cast<uint4*>(w.sm + Lay::kYOff) + lane; // beta spill: entry y at ysp[64 y], ysp[64 y + 32]
 
   const int n_full = W >> 3;
+#pragma unroll 1
   for (int t = 0; t < n_full; t++) {
+    asm volatile("" : "+r"(flags));
+    d2    = flags & 1;
+    bits1 = flags & 2;
+    bits2 = flags & 4;
     const u32* tb = acquire();
     u32        bs[4][8];
-    // ---- recompute beta_{8t+7} .. beta_{8t+1} from the checkpoint beta_{8t+8}
+    // ---- recompute beta_{8t+7} .. beta_{8t+1} from the checkpoint beta_{8t+8}: the upper three go to shared memory, the
+    //      lower four stay in registers
     ck_load(t, st);
     if (8 * (t + 1) < W)
       P::normalize_now(st); // the recursion continued from the normalised value; beta[W] itself was never normalised
@@ -463,35 +476,42 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       if (kNP == 1 || (kk & 1) == 0)
         P::normalize_now(st);
     }
-    // ---- steps 8t .. 8t+3 against beta_{8t+1} .. beta_{8t+4}
+    // ---- two trips through one 4-step body: steps 8t .. 8t+3 against beta_{8t+1} .. beta_{8t+4} (registers), then steps
+    //      8t+4 .. 8t+7 against beta_{8t+5} .. beta_{8t+7} (spilled by this lane) and the checkpoint beta_{8t+8}
+#pragma unroll 1
+    for (int half = 0; half < 2; half++) {
+      if (half) {
 #pragma unroll
-    for (int i = 0; i < 4; i++)
-      out_step(tb, t, i, bs[i], mon_a, i != 0 || t != 0);
-    if (P::kMonitor && t == 0) { // what was tracked so far belongs to the head monitor
-      mon_h.hi = p_max(mon_h.hi, mon_a.hi);
-      mon_h.lo = p_min(mon_h.lo, mon_a.lo);
-      mon_a.hi = 0;
-      mon_a.lo = 0;
+        for (int y = 0; y < 3; y++) {
+          const uint4 lo = ysp[64 * y], hi = ysp[64 * y + 32];
+          bs[y][0] = lo.x; bs[y][1] = lo.y; bs[y][2] = lo.z; bs[y][3] = lo.w;
+          bs[y][4] = hi.x; bs[y][5] = hi.y; bs[y][6] = hi.z; bs[y][7] = hi.w;
+        }
+        ck_load(t, bs[3]);
+      }
+      const u32* tp = tb + half * 4 * 32;                               // plane rows 4 half .. 4 half + 3
+      const u32* tq = tb - lane + kLutOff + j + half * 4 * T;           // table rows of the same steps
+#pragma unroll
+      for (int i = 0; i < 4; i++)
+        out_step(tp, tq, 8 * t + 4 * half + i, i, bs[i], mon_a, (i | half | t) != 0);
+      if (P::kMonitor && t == 0 && half == 0) { // what was tracked so far belongs to the head monitor
+        mon_h.hi = p_max(mon_h.hi, mon_a.hi);
+        mon_h.lo = p_min(mon_h.lo, mon_a.lo);
+        mon_a.hi = 0;
+        mon_a.lo = 0;
+      }
     }
-    // ---- steps 8t+4 .. 8t+7 against beta_{8t+5} .. beta_{8t+7} (spilled by this lane) and the checkpoint beta_{8t+8}
-#pragma unroll
-    for (int y = 0; y < 3; y++) {
-      const uint4 lo = ysp[64 * y], hi = ysp[64 * y + 32];
-      bs[y][0] = lo.x; bs[y][1] = lo.y; bs[y][2] = lo.z; bs[y][3] = lo.w;
-      bs[y][4] = hi.x; bs[y][5] = hi.y; bs[y][6] = hi.z; bs[y][7] = hi.w;
-    }
-    ck_load(t, bs[3]);
-#pragma unroll
-    for (int i = 4; i < 8; i++)
-      out_step(tb, t, i, bs[i - 4], mon_a, true);
-    if (!kDec2 && (t & 1))
-      flush_bits(8 * t + 8); // (nothing accumulated when the decisions are not needed)
+    if (t & 1)
+      flush_bits(8 * t + 8); // (nothing accumulated unless decoder 1 needs its decisions)
   }
   if (W & 7) {
     // partial top tile, guarded: beta_{p+1} of each step is recomputed from the checkpoint beta[W] (at most 6 steps)
     const int  t  = n_full;
     const int  nv = W & 7;
     const u32* tb = acquire();
+    d2    = flags & 1;
+    bits1 = flags & 2;
+    bits2 = flags & 4;
 #pragma unroll 1
     for (int i = 0; i < nv; i++) {
       u32 b[8];
@@ -504,11 +524,18 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         if (kk > i + 1 && (kNP == 1 || (kk & 1) == 0))
           P::normalize_now(b);
       }
-      out_step(tb, t, i, b, mon_a, true); // (t >= 5 here: a lane has at least 40 steps)
+      // (t >= 5 here: a lane has at least 40 steps.)  A runtime row index: the step parity that drives the normalisation
+      // cadence and the monitor is i's, passed as the compile-time 0 / 1 of the two branches
+      const int  r0 = i & ~1;
+      const u32* tp = tb + r0 * 32;
+      const u32* tq = tb - lane + kLutOff + j + r0 * T;
+      if (i & 1)
+        out_step(tp, tq, 8 * t + i, 1, b, mon_a, true);
+      else
+        out_step(tp, tq, 8 * t + i, 0, b, mon_a, true);
     }
   }
-  if (!kDec2)
-    flush_bits(W);
+  flush_bits(W);
 
   ge_out = 0;
   if (P::kMonitor) {
@@ -640,11 +667,18 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
       }
       bool flagged;
       int  ge = 0;
-      if (niter & 1)
-        flagged = fused_half<P, N, true>(w, a, tmap3 + 1, blk0, W, K, q, ws, ps, tl, g_ext + g_par1, d_sat, live, ge, false, want_bits);
-      else
-        flagged = fused_half<P, N, false>(w, a, niter ? tmap3 : tmap3 + 1, blk0, W, K, q, ws, ps, tl, (niter ? g_ext : 0) + g_syst + g_par0, d_sat, live, ge,
-                                          niter != 0, want_bits);
+      {
+        // one call site, runtime flags: the body must exist once (see fused_half)
+        const bool dec2 = niter & 1, apr3 = !dec2 && niter != 0;
+        const int  g    = dec2 ? g_ext + g_par1 : (apr3 ? g_ext : 0) + g_syst + g_par0;
+        const CUtensorMap* tm = apr3 ? tmap3 : tmap3 + 1;
+        if (!P::kMonitor)
+          flagged = fused_half<P, N, -1>(w, a, tm, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge, dec2, apr3, want_bits);
+        else if (dec2)
+          flagged = fused_half<P, N, 1>(w, a, tm, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge, true, false, want_bits);
+        else
+          flagged = fused_half<P, N, 0>(w, a, tm, blk0, W, K, q, ws, ps, tl, g, d_sat, live, ge, false, apr3, want_bits);
+      }
       g_ext = ge;
       __syncwarp(); // the decision bits of every lane are in shared memory
       if (P::kMonitor && flagged) {
