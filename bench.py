@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- turbo-decoded Mbit/s on the B200 LTE turbo-decode engine (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c4] [--ncb N]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c1|c2|c3|c4|c5]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
 
@@ -10,15 +10,21 @@ A "step" is one pass of the hot path over one batch of synthetic input:
      half-iterations each (srslte_tdec_run_all semantics, no early stop), decided bytes out.
   c2: NTB transport blocks of TBS 75376 (13 x K=5824, 64QAM-sized G=90000 e-bits, rv 0): rate de-matching +
      decode with CRC early stopping (max 8 half-iterations) + TB CRC, through the batched decode_tb entry.
-  c4: same with int8 LLRs, TBS 97896 (16 x K=6144, G=115200).
+  c3: one batch over ALL 188 LTE code block sizes (single-block transport blocks, tbs = K - 24), noise levels mixed so
+     that the half-iteration counts vary from 1 to 8 inside the batch, CRC early stopping.
+  c4: as c2 with int8 LLRs, TBS 97896 (16 x K=6144, G=115200).
+  c5: pooled cells (downlink-shaped blocks + PUSCH subframes with HARQ state), sharded over the ranks by cell.
 
 `value` is whole-job decoded information Mbit/s with the inputs already resident in HBM; `e2e` is the same metric
 through the C ABI with pinned HOST buffers (H2D of the LLRs and D2H of the bytes inside the timed region).
+The default run measures c1 and adds a compact `configs` block with c2, c3, c4 and c5 measured in the same process.
+Every timed batch shape is verified: a sample of its outputs is compared with the oracle outside the timed region
+(`verified`); a mismatch makes the run fail.
 For N > 1 launch with torchrun (one rank per GPU): work is sharded by batch (weak scaling), no collective on the
 data path; the timed region is bracketed by a barrier and the maximum over ranks is taken.
 
---impl reference times the reference's own CPU implementation (oracle/_ref, all host cores) on a bounded sample
-of the same workload.
+--impl reference times the reference's own CPU implementation (oracle/_ref, all host cores, pinned threads) on a
+bounded sample of the same workload.
 """
 import argparse
 import json
@@ -35,9 +41,10 @@ sys.path.insert(0, ROOT)
 
 W16_OPS = 82.0   # algorithmic int16 lane-ops per trellis step per half-iteration
 W8_OPS = 106.0
-# DRAM traffic of the dominant kernel per code block and launch (dram__bytes_read.sum + dram__bytes_write.sum of one
-# `ncu --set full` capture divided by the code blocks of that launch; see profiles/README.md for the capture)
-MAP_TRAFFIC_PER_CB = {"c1": {"bytes_per_cb": 92.1e3, "source": "profiles/r01_k_map_f16.metrics.txt: mean over the 4 half-iteration launches of a batch (DEC1 first 82.2, DEC2 82.3, DEC1 109.4 KB per code block without the a-posteriori plane; the last DEC2 writes it: 94.3)"}}
+# DRAM traffic of the dominant kernel per code block and HALF-ITERATION (dram__bytes_read.sum + dram__bytes_write.sum of one
+# `ncu --set full` capture of k_map_fused divided by the block x half-iteration units of that launch; profiles/README.md)
+MAP_TRAFFIC = {"bytes_per_cb_half_iteration": 83.9e3,
+               "source": "profiles/r02_k_map_fused_c1.metrics.txt: 6.36 GB read + written by one launch = 18 944 code blocks x 4 half-iterations"}
 
 
 def load_peaks():
@@ -49,18 +56,22 @@ def load_peaks():
 
 
 class ClockSampler:
-    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    """ONE nvidia-smi process (rank 0) samples clocks / throttle reasons of every GPU of the job during the timed regions"""
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
-    def __init__(self, index):
-        self.index = index
+    def __init__(self, n_gpus, enabled=True):
+        self.n_gpus = n_gpus
         self.lines = []
         self.proc = None
+        self.enabled = enabled
+        self.t_mark = 0.0
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "25"],
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -72,29 +83,29 @@ class ClockSampler:
             self.lines.append((time.perf_counter(), line.strip()))
 
     def mark(self):
-        """start of the timed region: wait (bounded) until nvidia-smi has produced its first sample"""
+        """start of a timed region: wait (bounded) until nvidia-smi has produced its first sample"""
+        if not self.enabled:
+            return
         t0 = time.perf_counter()
         while self.proc and not self.lines and time.perf_counter() - t0 < 3.0:
             time.sleep(0.05)
         self.t_mark = time.perf_counter()
 
-    def stop(self):
+    def snapshot(self):
+        """clocks over the samples since mark()"""
+        if not self.enabled:
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
-        t_end = time.perf_counter()
-        t_mark = getattr(self, "t_mark", 0.0)
-        rows = [ln for (t, ln) in self.lines if t >= t_mark - 0.05] or [ln for (t, ln) in self.lines[-2:]]
+        rows = [ln for (t, ln) in self.lines if t >= self.t_mark - 0.05] or [ln for (t, ln) in self.lines[-2 * self.n_gpus:]]
         for ln in rows:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
             try:
+                if int(f[0]) >= self.n_gpus:
+                    continue
                 sm.append(float(f[1]))
                 mx.append(float(f[2]))
             except ValueError:
@@ -103,7 +114,28 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "gpus_sampled": self.n_gpus}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+
+def pin_rank_threads(local, world_local):
+    """give each rank of the box its own slice of the host cores (the planner, the copies' submission and the waits of a
+    rank then do not migrate over the cores of the others)"""
+    try:
+        cpus = sorted(os.sched_getaffinity(0))
+        per = len(cpus) // max(1, world_local)
+        if per >= 1 and world_local > 1:
+            os.sched_setaffinity(0, set(cpus[local * per:(local + 1) * per]))
+        return per if world_local > 1 else len(cpus)
+    except Exception:
+        return os.cpu_count() or 1
 
 
 def dist_setup(n_gpus, backend=None):
@@ -115,8 +147,11 @@ def dist_setup(n_gpus, backend=None):
     import torch
     import torch.distributed as dist
     backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
+    if backend == "nccl" and not os.environ.get("NCCL_DEBUG"):
+        # communicator set-up lines for whoever reads the log (rank / nranks / device), on stderr: stdout carries the JSON line
+        os.environ["NCCL_DEBUG"] = "INFO"
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     if backend == "nccl":
@@ -186,15 +221,54 @@ def make_tb(rng, ntb, tbs, Qm, G, dtype, amp, sigma, base=8, host_out=None):
 
 TB_CFG = {"c2": dict(tbs=75376, Qm=6, G=90000, dtype=np.int16, amp=100.0, sigma=0.44, max_iter=8, C=13, K=5824),
           "c4": dict(tbs=97896, Qm=8, G=115200, dtype=np.int8, amp=20.0, sigma=0.40, max_iter=8, C=16, K=6144)}
+C3_SIGMAS = (0.45, 0.6, 0.75, 0.9, 1.05, 1.3)
+
+
+def all_K():
+    return list(range(40, 513, 8)) + list(range(528, 1025, 16)) + list(range(1056, 2049, 32)) + list(range(2112, 6145, 64))
+
+
+def c3_specs(per_k):
+    """(tbs, Qm, G, sigma index) of every transport block of a c3 batch: per_k blocks of every LTE size, sizes interleaved"""
+    specs = []
+    for r in range(per_k):
+        for i, K in enumerate(all_K()):
+            specs.append((K - 24, 2, 2 * ((3 * K + 12) // 2), (i + r) % len(C3_SIGMAS)))
+    return specs
+
+
+def make_c3(rng, specs, flat):
+    """fills `flat` (int16) with the e-bits of every block; returns the element offsets.  Two distinct payloads per size."""
+    from srsran_b200 import synth
+    enc = {}
+    off = np.zeros(len(specs), np.uint64)
+    at = 0
+    for i, (tbs, Qm, G, si) in enumerate(specs):
+        if tbs not in enc:
+            enc[tbs] = synth.encode_tbs(rng.integers(0, 256, (2, tbs // 8), dtype=np.uint8), tbs, Qm, G, 0)
+        r = (i // 188) & 1
+        flat[at:at + G] = synth.awgn_llr(rng, enc[tbs][r:r + 1], 100.0, C3_SIGMAS[si], np.int16)[0]
+        off[i] = at
+        at += (G + 7) // 8 * 8
+    return off
+
+
+def c3_elems(specs):
+    return sum((G + 7) // 8 * 8 for (_, _, G, _) in specs)
+
+
+def get_ref(fast=True):
+    from oracle.bindings import Ref
+    return Ref(fast=fast) if Ref.available() else None
 
 
 def cpu_baseline_c1(llr, K, nof_iter, budget_s):
     """reference (or port) on the host cores over a bounded sample of the same code blocks"""
-    from oracle.bindings import Port, Ref
+    from oracle.bindings import Port
     cores = os.cpu_count() or 1
     sample = np.ascontiguousarray(llr)
-    if Ref.available():
-        R = Ref()
+    R = get_ref()
+    if R is not None:
         t1, _ = R.bench_c1(cores, sample, K, nof_iter, layout_sb=False)  # warm-up + calibration
         rep = max(1, int(budget_s / max(t1, 1e-3)))
         t_tot, _ = R.bench_c1(cores, sample, K, nof_iter, layout_sb=False, repeat=rep)
@@ -202,8 +276,11 @@ def cpu_baseline_c1(llr, K, nof_iter, budget_s):
             rep = max(1, int(rep * budget_s / max(t_tot, 1e-3)))
             t_tot, _ = R.bench_c1(cores, sample, K, nof_iter, layout_sb=False, repeat=rep)
         n_tot = rep * len(sample)
-        return {"value": n_tot * K / t_tot / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "reference",
-                "sample": "%d x K=%d code blocks x %d half-iterations, srslte_tdec_run_all (AUTO->avx16), %.1f s" % (n_tot, K, nof_iter, t_tot)}
+        lat = np.sort(R.latency_c1(sample, K, nof_iter, 13, 60)[10:])
+        return {"value": n_tot * K / t_tot / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "reference", "flags": R.flags, "threads": "pinned, one per core",
+                "sample": "%d x K=%d code blocks x %d half-iterations, srslte_tdec_run_all (AUTO->avx16), %.1f s" % (n_tot, K, nof_iter, t_tot),
+                "latency_one_core": {"tti": "13 code blocks x K=%d x %d half-iterations on one pinned core" % (K, nof_iter),
+                                     "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "n": int(len(lat))}}
     P = Port()
     h = P.tdec_new(0, True)
     t0 = time.perf_counter()
@@ -216,31 +293,40 @@ def cpu_baseline_c1(llr, K, nof_iter, budget_s):
     return {"value": n * K / t / 1e6, "unit": "Mbit/s", "cores": 1, "kind": "port", "sample": "%d x K=%d code blocks, scalar oracle port, %.1f s" % (n, K, t)}
 
 
-def cpu_baseline_tb(llr, cfg, budget_s):
-    from oracle.bindings import Port, Ref
+def cpu_baseline_tb(flat, off, specs, is8, max_iter, budget_s, uniform_llr=None):
+    """the reference's srslte_dlsch_decode2 on all host cores (pinned threads) over a bounded sample of the same transport
+    blocks; for uniform batches also the per-call latency of one block on one pinned core"""
+    from oracle.bindings import Port
     cores = os.cpu_count() or 1
-    if Ref.available():
-        R = Ref()
-        t1, _, _, _ = R.bench_tb(cores, llr, cfg["tbs"], cfg["Qm"], 0, cfg["max_iter"])  # warm-up + calibration
+    tbs = np.array([s[0] for s in specs], np.uint32)
+    Qm = np.array([s[1] for s in specs], np.uint32)
+    G = np.array([s[2] for s in specs], np.uint32)
+    bits = int(tbs.sum())
+    R = get_ref()
+    if R is not None:
+        t1, _, _, _ = R.bench_tb_mixed(cores, flat, off, tbs, Qm, G, max_iter)  # warm-up + calibration
         rep = max(1, int(budget_s / max(t1, 1e-3)))
-        t_tot, _, rc, avg = R.bench_tb(cores, llr, cfg["tbs"], cfg["Qm"], 0, cfg["max_iter"], repeat=rep)
-        if t_tot < 0.6 * budget_s:
-            rep = max(1, int(rep * budget_s / max(t_tot, 1e-3)))
-            t_tot, _, rc, avg = R.bench_tb(cores, llr, cfg["tbs"], cfg["Qm"], 0, cfg["max_iter"], repeat=rep)
-        n_tot = rep * len(llr)
-        it = [float(avg.mean())]
-        return {"value": n_tot * cfg["tbs"] / t_tot / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "reference",
-                "sample": "%d TBs of %d bits, srslte_dlsch_decode2, %.2f avg half-iterations, %.1f s" % (n_tot, cfg["tbs"], float(np.mean(it)), t_tot)}
+        t_tot, _, rc, avg = R.bench_tb_mixed(cores, flat, off, tbs, Qm, G, max_iter, repeat=rep)
+        out = {"value": rep * bits / t_tot / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "reference", "flags": R.flags, "threads": "pinned, one per core",
+               "sample": "%d transport blocks (%d distinct), srslte_dlsch_decode2, %.2f avg half-iterations, %.1f s" % (
+                   rep * len(specs), len(specs), float(avg.mean()), t_tot)}
+        if uniform_llr is not None:
+            lat = np.sort(R.latency_tb(uniform_llr, int(tbs[0]), int(Qm[0]), max_iter, 60)[10:])
+            out["latency_one_core"] = {"tti": "1 transport block of %d bits, srslte_dlsch_decode2 on one pinned core" % int(tbs[0]),
+                                       "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "n": int(len(lat))}
+        return out
     P = Port()
     sb = P.softbuffer_new()
     t0 = time.perf_counter()
-    n = 0
+    n = nb = 0
     while time.perf_counter() - t0 < budget_s:
+        i = n % len(specs)
         P.softbuffer_reset(sb)
-        P.decode_tb(sb, cfg["tbs"], cfg["Qm"], 0, llr[n % len(llr)], cfg["max_iter"])
+        P.decode_tb(sb, int(tbs[i]), int(Qm[i]), 0, flat[int(off[i]):int(off[i]) + int(G[i])], max_iter)
+        nb += int(tbs[i])
         n += 1
     t = time.perf_counter() - t0
-    return {"value": n * cfg["tbs"] / t / 1e6, "unit": "Mbit/s", "cores": 1, "kind": "port", "sample": "%d TBs, scalar oracle port, %.1f s" % (n, t)}
+    return {"value": nb / t / 1e6, "unit": "Mbit/s", "cores": 1, "kind": "port", "sample": "%d TBs, scalar oracle port, %.1f s" % (n, t)}
 
 
 # ----------------------------------------------------------------------------------------------- reference arm
@@ -249,10 +335,11 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if world > 1 and rank != 0:
         return 0
-    from oracle.bindings import Ref, Port
+    from oracle.bindings import Port
     rng = np.random.default_rng(1234)
     cores = os.cpu_count() or 1
-    have_ref = Ref.available()
+    R = get_ref()
+    have_ref = R is not None
     if args.workload == "c1":
         K, nit = 6144, 4
         ncb = 1024 * cores if have_ref else 8
@@ -268,29 +355,41 @@ def run_reference(args):
             return time.perf_counter() - t0
         workload = "c1: K=6144 x 4 half-iterations, int16, %d code blocks per step (bounded sample)" % ncb
     else:
-        cfg = TB_CFG[args.workload]
-        ntb = 64 * cores if have_ref else 1
-        llr, _ = make_tb(rng, ntb, cfg["tbs"], cfg["Qm"], cfg["G"], cfg["dtype"], cfg["amp"], cfg["sigma"])
-        units = ntb * cfg["tbs"]
+        if args.workload == "c3":
+            specs = c3_specs(2 if have_ref else 1)
+            flat = np.zeros(c3_elems(specs), np.int16)
+            off = make_c3(rng, specs, flat)
+            is8, max_iter = False, 8
+        else:
+            cfg = TB_CFG["c2" if args.workload == "c5" else args.workload]
+            ntb = 64 * cores if have_ref else 1
+            llr2, _ = make_tb(rng, ntb, cfg["tbs"], cfg["Qm"], cfg["G"], cfg["dtype"], cfg["amp"], cfg["sigma"])
+            specs = [(cfg["tbs"], cfg["Qm"], cfg["G"], 0)] * ntb
+            flat = llr2.reshape(-1)
+            off = np.arange(ntb, dtype=np.uint64) * np.uint64(cfg["G"])
+            is8, max_iter = cfg["dtype"] == np.int8, cfg["max_iter"]
+        tbs_a = np.array([s[0] for s in specs], np.uint32)
+        Qm_a = np.array([s[1] for s in specs], np.uint32)
+        G_a = np.array([s[2] for s in specs], np.uint32)
+        units = int(tbs_a.sum())
 
         def step():
             if have_ref:
-                return R.bench_tb(cores, llr, cfg["tbs"], cfg["Qm"], 0, cfg["max_iter"])[0]
+                return R.bench_tb_mixed(cores, flat, off, tbs_a, Qm_a, G_a, max_iter)[0]
             t0 = time.perf_counter()
-            for i in range(ntb):
+            for i in range(len(specs)):
                 P.softbuffer_reset(sb)
-                P.decode_tb(sb, cfg["tbs"], cfg["Qm"], 0, llr[i], cfg["max_iter"])
+                P.decode_tb(sb, int(tbs_a[i]), int(Qm_a[i]), 0, flat[int(off[i]):int(off[i]) + int(G_a[i])], max_iter)
             return time.perf_counter() - t0
-        workload = "%s: TBS %d, %d TBs per step (bounded sample)" % (args.workload, cfg["tbs"], ntb)
-    if have_ref:
-        R = Ref()
-    else:
+        workload = "%s: %d transport blocks per step (bounded sample), srslte_dlsch_decode2" % (args.workload, len(specs))
+    if not have_ref:
         P = Port()
         h = P.tdec_new(0, True)
         sb = P.softbuffer_new()
     for _ in range(args.warmup):
         step()
-    t = sum(step() for _ in range(args.steps))
+    times = [step() for _ in range(args.steps)]
+    t = sum(times)
     val = units * args.steps / t / 1e6
     kind = "reference" if have_ref else "port"
     used = cores if have_ref else 1
@@ -299,108 +398,210 @@ def run_reference(args):
             "dtype": "int8" if args.workload == "c4" else "int16", "data": "synthetic",
             "config": {"workload": workload, "l2": "n/a (CPU)"},
             "cpu_baseline": {"value": val, "unit": "Mbit/s", "cores": used, "kind": kind,
-                             "sample": "the reference's own AVX2 decoder (oracle/_ref) on %d host threads" % used if have_ref else "scalar oracle port, 1 thread"},
+                             "flags": R.flags if have_ref else "-O2", "threads": "pinned, one per core" if have_ref else "1",
+                             "sample": "the reference's own AVX2 decoder (oracle/_ref) on %d pinned host threads" % used if have_ref else "scalar oracle port, 1 thread",
+                             # run-to-run spread of the host measurement (a shared VM): slowest and fastest timed step
+                             "step_value_min_max": [units / max(times) / 1e6, units / min(times) / 1e6]},
             "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line))
     return 0
 
 
 # ----------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    rank, world, local, barrier, vmax, vsum = dist_setup(args.gpus)
+class Env:
+    pass
+
+
+def verify_cb(ctx, llr_host, d_out, K, ncb, nit, n_sample, rng):
+    """compare a random sample of the code blocks of a timed batch (device output buffer) with the oracle"""
+    from oracle.bindings import Port, aligned_zeros
+    out = np.zeros((ncb, K // 8), np.uint8)
+    ctx.d2h(out, d_out)
+    buf = aligned_zeros(llr_host.shape[1], llr_host.dtype)  # (the reference's AVX loads want 32-byte aligned input)
+    idx = np.sort(rng.choice(ncb, size=min(n_sample, ncb), replace=False))
+    R = get_ref(fast=False)
+    P = R if R is not None else Port()
+    h = P.tdec_new(0, True)
+    bad = 0
+    for i in idx:
+        buf[:] = llr_host[i]
+        rc, want = P.tdec_run_all(h, buf, nit, K)
+        bad += int((out[i] != want).any())
+    P.tdec_del(h)
+    return {"n": int(len(idx)), "mismatches": int(bad), "against": "reference (oracle/_ref)" if R is not None else "oracle port", "what": "decided bytes"}, out
+
+
+def verify_tbs(tb_arr, outs, flat, off, specs, max_iter, idx):
+    """transport blocks idx of a timed batch against the oracle: return code, bytes, per-code-block half-iteration counts"""
+    from oracle.bindings import Port
+    P = Port()
+    bad = 0
+    for i in idx:
+        tbs, Qm, G, _ = specs[i]
+        sb = P.softbuffer_new()
+        rc, d, nit, avg, crc = P.decode_tb(sb, tbs, Qm, 0, np.ascontiguousarray(flat[int(off[i]):int(off[i]) + G]), max_iter)
+        P.softbuffer_del(sb)
+        C_ = tb_arr[i].nof_cb
+        nb = tbs // 8 + 3
+        ok = tb_arr[i].ret == rc and (outs[i][:nb] == d[:nb]).all() and list(tb_arr[i].cb_noi[:C_]) == nit[:C_].tolist()
+        bad += int(not ok)
+    return {"n": int(len(idx)), "mismatches": int(bad), "against": "oracle port (pinned to the reference)", "what": "return code, transport block bytes, cb_noi"}
+
+
+def h2d_probe(env, b, ctx, mb=256, reps=6):
+    """plain concurrent host-to-device copy bandwidth of the job: every rank copies a page-locked buffer at the same time"""
+    n = mb << 20
+    pin = b.PinnedArray((n,), np.uint8)
+    d = ctx.device_alloc(n)
+    ctx.h2d(d, pin.array)
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ctx.h2d(d, pin.array)
+    dt = env.vmax(time.perf_counter() - t0)
+    ctx.device_free(d)
+    pin.free()
+    return env.world * reps * n / dt / 1e9
+
+
+def alu_peak(env, ctx):
+    """integer roofline denominator: packed-instruction issue rate measured live, x2 int16 lanes"""
+    if getattr(env, "probe", None) is None:
+        probes = [ctx.alu_probe(op) for op in range(4)]
+        env.probe = (min(probes), probes, ctx.alu_probe(4))
+    return env.probe
+
+
+def measure_batched(env, args, wl, steps, warmup, quick):
+    """c1 / c2 / c3 / c4 on this rank's GPU.  Returns the result dictionary of the workload."""
     import srsran_b200 as b
-    from srsran_b200 import synth  # noqa: F401
-    peaks, peak_src = load_peaks()
-    ctx = b.Context(local)
-    # engines (= streams) of this GPU: batches rotate over them, so the latency-bound tail of one batch (last wave, code
-    # blocks that need all their iterations) overlaps the head of the next; the end-to-end loop also overlaps the
-    # H2D copy and host-side planning of one chunk with the decode of the previous ones
-    n_eng = max(2, args.engines)
-    all_ctx = [ctx] + [b.Context(local) for _ in range(n_eng - 1)]
-    ctx2 = all_ctx[1]
-    e2e_ctx = all_ctx
-    rng = np.random.default_rng(shard_seed(rank))
-    sampler = ClockSampler(local)
+    rank, world, local = env.rank, env.world, env.local
+    barrier, vmax, vsum = env.barrier, env.vmax, env.vsum
+    peaks, peak_src = env.peaks, env.peak_src
+    n_eng = max(2, args.engines if args.engines > 0 else (4 if wl == "c1" else 6))
+    all_ctx = [b.Context(local) for _ in range(n_eng)]
+    ctx = all_ctx[0]
+    rng = np.random.default_rng(shard_seed(rank) + {"c1": 0, "c2": 100, "c3": 200, "c4": 300}[wl])
     launches = 0
     extra = {}
     replay = [0, 0]  # (code block x half-iteration) units replayed with the exact arithmetic, units run
+    frees, pins = [], []
 
-    if args.workload == "c1":
+    def dalloc(n):
+        p_ = ctx.device_alloc(n)
+        frees.append(p_)
+        return p_
+
+    if wl == "c1":
         K, nit = 6144, 4
         ncb = args.ncb
         stride = 3 * K + 12
         pin_in = b.PinnedArray((ncb, stride), np.int16, write_combined=args.wc_inputs)
         pin_out = b.PinnedArray((ncb, K // 8), np.uint8)
+        pins += [pin_in, pin_out]
         llr, _ = make_c1(rng, ncb, K, host_out=pin_in.array)
-        d_llr = ctx.device_alloc(llr.nbytes)
-        d_out = ctx.device_alloc(ncb * K // 8)
+        d_llr = dalloc(llr.nbytes)
         ctx.h2d(d_llr, llr)
         units_per_step = ncb * K
-        algo_ops_per_step = W16_OPS * K * nit * ncb
         algo_bytes_per_step = ncb * (stride * 2 + K // 8)
         h2d_b, d2h_b = llr.nbytes, ncb * K // 8
         workload = "c1-batched: %d code blocks x K=6144 x 4 half-iterations, int16 LLRs (standard order), no early stop" % ncb
-
-        engines = [(ctx, d_out)] + [(c, ctx.device_alloc(ncb * K // 8)) for c in all_ctx[1:]]
+        dtype_name = "int16"
+        engines = [(c, dalloc(ncb * K // 8)) for c in all_ctx]
 
         def dev_submit(i):
             e, o = engines[i % n_eng]
-            e.wait()  # the batch this engine ran two steps ago
+            e.wait()  # the batch this engine ran n_eng steps ago
             e.tdec_batch_device(d_llr, o, K, ncb, stride, 16, nit, input_sb=False, submit_only=True)
 
         chunks = args.e2e_chunks
         per = (ncb + chunks - 1) // chunks
 
         def e2e_step():
-            # (the engines keep streaming across steps; e2e_drain() closes the timed region)
-            cs = e2e_ctx
             for c in range(chunks):
                 lo, hi = c * per, min(ncb, (c + 1) * per)
                 if lo >= hi:
                     break
-                e = cs[c % len(cs)]
+                e = all_ctx[c % n_eng]
                 e.wait()
                 e.tdec_batch_submit(pin_in.array[lo:hi].ctypes.data, pin_out.array[lo:hi].ctypes.data, K, hi - lo, stride, 16, nit)
 
-        def cpu_base():
-            return cpu_baseline_c1(np.array(llr[:min(ncb, 2048)]), K, nit, args.cpu_seconds)  # (a copy in ordinary memory)
-    else:
-        cfg = TB_CFG[args.workload]
-        ntb = args.ntb
-        tbs, Qm, G, dt = cfg["tbs"], cfg["Qm"], cfg["G"], cfg["dtype"]
-        pin_in = b.PinnedArray((ntb, G), dt)
-        ostride = (tbs // 8 + 6 + 15) // 16 * 16
-        pin_out = b.PinnedArray((ntb, ostride), np.uint8)
-        llr, data = make_tb(rng, ntb, tbs, Qm, G, dt, cfg["amp"], cfg["sigma"], host_out=pin_in.array)
-        d_llr = ctx.device_alloc(llr.nbytes)
-        d_out = ctx.device_alloc(ntb * ostride)
-        ctx.h2d(d_llr, llr)
-        esz = np.dtype(dt).itemsize
-        tb_dev = b.make_tbs(ntb)
-        for i in range(ntb):
-            t = tb_dev[i]
-            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = d_llr + i * G * esz, G, tbs, Qm, 0, None, d_out + i * ostride
-        units_per_step = ntb * tbs
-        h2d_b, d2h_b = llr.nbytes, ntb * (tbs // 8 + 6)
-        workload = "%s: %d TBs x TBS %d (%d x K=%d), %s e-bits, rate de-matching + <=%d half-iterations with CRC early stop" % (
-            args.workload, ntb, tbs, cfg["C"], cfg["K"], np.dtype(dt).name, cfg["max_iter"])
+        def verify():
+            v, out_dev = verify_cb(ctx, llr, engines[0][1], K, ncb, nit, 96 if not quick else 64, rng)
+            # the end-to-end path wrote pin_out: same blocks, same answer
+            v["e2e_equals_device_path"] = bool((out_dev == pin_out.array).all())
+            if not v["e2e_equals_device_path"]:
+                v["mismatches"] += 1
+            return v
 
-        engines = [(ctx, tb_dev)]
-        for c in all_ctx[1:]:
-            d_o = ctx.device_alloc(ntb * ostride)
+        def cpu_base():
+            return cpu_baseline_c1(np.array(llr[:min(ncb, 2048)]), K, nit, args.cpu_seconds if not quick else 3.0)
+
+        tti_cb = 13
+        tti_desc = "%d code blocks x K=6144 x 4 half-iterations (one 75 kbit subframe), host buffers in and out" % tti_cb
+
+        def latency_once(i):
+            lo = (i * tti_cb) % (ncb - tti_cb)
+            ctx.tdec_batch_submit(pin_in.array[lo:lo + tti_cb].ctypes.data, pin_out.array[lo:lo + tti_cb].ctypes.data, K, tti_cb, stride, 16, nit)
+            ctx.wait()
+
+        def algo_ops():
+            return W16_OPS * K * nit * ncb
+    else:
+        if wl == "c3":
+            specs = c3_specs(args.c3_per_k if not quick else min(args.c3_per_k, 32))
+            dt, max_iter, is8 = np.int16, 8, False
+            n_el = c3_elems(specs)
+            pin_in = b.PinnedArray((n_el,), dt)
+            off = make_c3(rng, specs, pin_in.array)
+            workload = "c3-mixed: %d single-block transport blocks over all 188 LTE sizes K=40..6144 (%d per size), int16 e-bits, noise sigma %s, " \
+                       "rate de-matching + <=8 half-iterations with CRC early stop" % (len(specs), len(specs) // 188, list(C3_SIGMAS))
+            uniform = None
+        else:
+            cfg = TB_CFG[wl]
+            ntb_ = args.ntb
+            dt, max_iter, is8 = cfg["dtype"], cfg["max_iter"], cfg["dtype"] == np.int8
+            specs = [(cfg["tbs"], cfg["Qm"], cfg["G"], 0)] * ntb_
+            pin_in = b.PinnedArray((ntb_ * cfg["G"],), dt)
+            make_tb(rng, ntb_, cfg["tbs"], cfg["Qm"], cfg["G"], dt, cfg["amp"], cfg["sigma"], host_out=pin_in.array.reshape(ntb_, cfg["G"]))
+            off = np.arange(ntb_, dtype=np.uint64) * np.uint64(cfg["G"])
+            workload = "%s: %d TBs x TBS %d (%d x K=%d), %s e-bits, rate de-matching + <=%d half-iterations with CRC early stop" % (
+                wl, ntb_, cfg["tbs"], cfg["C"], cfg["K"], np.dtype(dt).name, max_iter)
+            uniform = pin_in.array.reshape(ntb_, cfg["G"])
+        pins.append(pin_in)
+        flat = pin_in.array
+        ntb = len(specs)
+        esz = np.dtype(dt).itemsize
+        dtype_name = np.dtype(dt).name
+        ostr = np.array([(s[0] // 8 + 6 + 15) // 16 * 16 for s in specs], np.int64)
+        ooff = np.concatenate([[0], np.cumsum(ostr)[:-1]])
+        pin_out = b.PinnedArray((int(ostr.sum()),), np.uint8)
+        pins.append(pin_out)
+        d_llr = dalloc(flat.nbytes)
+        ctx.h2d(d_llr, flat)
+        units_per_step = sum(s[0] for s in specs)
+        h2d_b, d2h_b = flat.nbytes, sum(s[0] // 8 + 6 for s in specs)
+        algo_bytes_per_step = sum(s[2] * esz + s[0] // 8 for s in specs)
+
+        def fill(arr, lo, hi, in_base, out_base):
+            for i in range(lo, hi):
+                t = arr[i - lo]
+                t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer = in_base + int(off[i]) * esz, specs[i][2], specs[i][0], specs[i][1], 0, None
+                t.data = out_base + int(ooff[i])
+
+        engines = []
+        for c in all_ctx:
+            d_o = dalloc(int(ostr.sum()))
             tbd = b.make_tbs(ntb)
-            for i in range(ntb):
-                t = tbd[i]
-                t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = d_llr + i * G * esz, G, tbs, Qm, 0, None, d_o + i * ostride
-            engines.append((c, tbd))
+            fill(tbd, 0, ntb, d_llr, d_o)
+            engines.append((c, tbd, d_o))
+        tb_dev = engines[0][1]
 
         def dev_submit(i):
-            e, t = engines[i % n_eng]
+            e, t, _ = engines[i % n_eng]
             e.wait()
-            e.decode_tbs(t, dt == np.int8, cfg["max_iter"], flags=b.IN_DEVICE | b.OUT_DEVICE, submit_only=True)
+            e.decode_tbs(t, is8, max_iter, flags=b.IN_DEVICE | b.OUT_DEVICE, submit_only=True)
 
-        # end to end: the TTIs of a step go down in 4 chunks that alternate between the two engines, so the H2D copy
-        # of one chunk overlaps the decode of the previous one
         n_chunks = args.e2e_chunks
         per = (ntb + n_chunks - 1) // n_chunks
         host_chunks = []
@@ -409,201 +610,178 @@ def run_ours(args):
             if lo >= hi:
                 break
             arr = b.make_tbs(hi - lo)
-            for i in range(lo, hi):
-                t = arr[i - lo]
-                t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = pin_in.ptr + i * G * esz, G, tbs, Qm, 0, None, pin_out.ptr + i * ostride
-            host_chunks.append(arr)
+            fill(arr, lo, hi, pin_in.ptr, pin_out.ptr)
+            host_chunks.append((lo, arr))
 
         def e2e_step():
-            cs = e2e_ctx
-            for c, arr in enumerate(host_chunks):
-                e = cs[c % len(cs)]
+            for c, (lo, arr) in enumerate(host_chunks):
+                e = all_ctx[c % n_eng]
                 e.wait()
-                e.decode_tbs(arr, dt == np.int8, cfg["max_iter"], flags=0, submit_only=True)
+                e.decode_tbs(arr, is8, max_iter, flags=0, submit_only=True)
+
+        def verify():
+            n_s = min(ntb, (24 if wl != "c3" else 376) if not quick else (12 if wl != "c3" else 188))
+            idx = np.sort(rng.choice(ntb, size=n_s, replace=False)) if wl != "c3" else np.arange(0, ntb, max(1, ntb // n_s))[:n_s]
+            # device-resident path: outputs of engine 0's last batch
+            dev_out = np.zeros(int(ostr.sum()), np.uint8)
+            ctx.d2h(dev_out, engines[0][2])
+            outs = {int(i): dev_out[int(ooff[i]):int(ooff[i]) + int(ostr[i])] for i in idx}
+            v = verify_tbs(tb_dev, outs, flat, off, specs, max_iter, [int(i) for i in idx])
+            # end-to-end path: the host output buffer and the descriptor arrays of its chunks say the same for EVERY block
+            bad = 0
+            for lo, arr in host_chunks:
+                for k in range(len(arr)):
+                    i = lo + k
+                    nb = specs[i][0] // 8 + 3
+                    o = int(ooff[i])
+                    if arr[k].ret != tb_dev[i].ret or list(arr[k].cb_noi) != list(tb_dev[i].cb_noi) or not (pin_out.array[o:o + nb] == dev_out[o:o + nb]).all():
+                        bad += 1
+            v["e2e_equals_device_path"] = bad == 0
+            if bad:
+                v["mismatches"] += 1
+            return v
 
         def cpu_base():
-            return cpu_baseline_tb(llr[:min(ntb, 64)], cfg, args.cpu_seconds)
+            n_s = min(ntb, 64 if wl != "c3" else 376)
+            sel = list(range(n_s)) if wl != "c3" else list(range(0, ntb, max(1, ntb // n_s)))[:n_s]
+            sub_specs = [specs[i] for i in sel]
+            sub_off = np.zeros(len(sel), np.uint64)
+            sub = np.zeros(sum((s[2] + 7) // 8 * 8 for s in sub_specs), dt)
+            at = 0
+            for k, i in enumerate(sel):
+                G = specs[i][2]
+                sub[at:at + G] = flat[int(off[i]):int(off[i]) + G]
+                sub_off[k] = at
+                at += (G + 7) // 8 * 8
+            uni = np.ascontiguousarray(uniform[:16]) if uniform is not None else None
+            return cpu_baseline_tb(sub, sub_off, sub_specs, is8, max_iter, args.cpu_seconds if not quick else 3.0, uniform_llr=uni)
 
-    # ---- device-resident throughput (`value`): two engines (streams) of this GPU alternate batches, so the tail of
-    #      one batch (last wave / code blocks that need all their iterations) overlaps the head of the next
+        if wl == "c3":
+            tti_desc = "13 transport blocks of mixed sizes (every 14th size), host buffers in and out"
+            lat_sets = []
+            for s0 in range(8):
+                ids = [(s0 + 14 * k) % ntb for k in range(13)]
+                arr = b.make_tbs(13)
+                for k, i in enumerate(ids):
+                    t = arr[k]
+                    t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer = pin_in.ptr + int(off[i]) * esz, specs[i][2], specs[i][0], specs[i][1], 0, None
+                    t.data = pin_out.ptr + int(ooff[i])
+                lat_sets.append(arr)
+
+            def latency_once(i):
+                ctx.decode_tbs(lat_sets[i % len(lat_sets)], is8, max_iter, flags=0)
+        else:
+            tti_desc = "1 transport block of %d bits (%d code blocks), <=%d half-iterations with CRC early stop, host buffers in and out" % (
+                specs[0][0], TB_CFG[wl]["C"], max_iter)
+            one = b.make_tbs(1)
+
+            def latency_once(i):
+                k = i % ntb
+                fill(one, k, k + 1, pin_in.ptr, pin_out.ptr)
+                ctx.decode_tbs(one, is8, max_iter, flags=0)
+
+        Ks = {}
+
+        def algo_ops():
+            # W x K x half-iterations actually run, per code block (results of engine 0's last batch)
+            tot = 0.0
+            for i in range(ntb):
+                t = tb_dev[i]
+                tbs = specs[i][0]
+                if tbs not in Ks:
+                    _, seg = b.cbsegm(tbs)
+                    Ks[tbs] = (seg["C1"], seg["K1"], seg["K2"])
+                C1, K1, K2 = Ks[tbs]
+                for c in range(t.nof_cb):
+                    tot += (W8_OPS if is8 else W16_OPS) * (K1 if c < C1 else K2) * t.cb_noi[c]
+            return tot
+
+    # ---- device-resident throughput (`value`): the engines (streams) of this GPU take the batches in turn, so the tail of
+    #      one batch (code blocks that need all their iterations) overlaps the head of the next
     def stats(e):
         replay[0] += e.last_replayed()
         replay[1] += e.last_half_iterations()
-        return e.last_launches(), e.last_map_ms(), e.last_map_launches()
+        return e.last_launches()
 
-    sampler.start()
-    for i in range(max(args.warmup, n_eng)):
+    for i in range(max(warmup, n_eng)):
         dev_submit(i)
     for c in all_ctx:
         c.wait()
     replay[0] = replay[1] = 0
     barrier()
-    sampler.mark()
+    env.sampler.mark()
     ctx.timer_start()
-    map_ms, map_launches = 0.0, 0
-    for i in range(args.steps):
+    for i in range(steps):
         e = engines[i % n_eng][0]
         if i >= n_eng:
             e.wait()
-            l, mm, ml = stats(e)
-            launches += l
-            map_ms += mm
-            map_launches += ml
+            launches += stats(e)
         dev_submit(i)
-    for i in range(max(0, args.steps - n_eng), args.steps): # the batches still in flight, oldest first
+    for i in range(max(0, steps - n_eng), steps):  # the batches still in flight, oldest first
         e = engines[i % n_eng][0]
         e.wait()
-        l, mm, ml = stats(e)
-        launches += l
-        map_ms += mm
-        map_launches += ml
+        launches += stats(e)
     ms = ctx.timer_stop_ms()
     extra["exact_replay_fraction"] = replay[0] / max(1, replay[1])
     barrier()
-    value, ms, total_units = aggregate(units_per_step, args.steps, ms, vmax, vsum)
+    value, ms, total_units = aggregate(units_per_step, steps, ms, vmax, vsum)
+    clocks_value = env.sampler.snapshot()
+
+    # sustained: the same loop for about --sustain-seconds of device time (the K timed steps above are tens of milliseconds)
+    sustained = None
+    if not quick and args.sustain_seconds > 0:
+        n_s = max(steps, int(args.sustain_seconds * 1e3 / max(ms / steps, 1e-3)))
+        barrier()
+        env.sampler.mark()
+        ctx.timer_start()
+        for i in range(n_s):
+            dev_submit(i)
+        for c in all_ctx:
+            c.wait()
+        ms_s = vmax(ctx.timer_stop_ms())
+        sustained = {"steps": n_s, "seconds": ms_s * 1e-3, "value": vsum(units_per_step) * n_s / (ms_s * 1e-3) / 1e6, "unit": "Mbit/s", "clocks": env.sampler.snapshot()}
+        barrier()
 
     # ---- end to end through the C ABI with host buffers
     def e2e_drain():
-        for e in e2e_ctx:
+        for e in all_ctx:
             e.wait()
 
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, warmup // 2)):
         e2e_step()
     e2e_drain()
     barrier()
+    env.sampler.mark()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(steps):
         e2e_step()
     e2e_drain()
     e2e_s = vmax(time.perf_counter() - t0)
-    clocks = sampler.stop()  # samples cover the device-resident and the end-to-end timed regions
+    clocks_e2e = env.sampler.snapshot()
     barrier()
     e2e_value = total_units / e2e_s / 1e6
 
+    # ---- verification of what was timed (outside the timed regions): device-resident outputs and end-to-end outputs
+    verified = verify()
+
     # ---- per-TTI latency (second half of the metric): ONE subframe's worth of work submitted from host buffers,
     #      submit -> results on the host, back to back on an otherwise idle GPU
-    lat = []
-    n_lat = 0 if args.no_latency else 300
-    if n_lat == 0:
-        tti_desc = "skipped (--no-latency)"
-    elif args.workload == "c1":
-        tti_cb = 13
-        tti_desc = "%d code blocks x K=6144 x 4 half-iterations (one 75 kbit subframe), host buffers in and out" % tti_cb
-        for i in range(n_lat + 20):
-            lo = (i * tti_cb) % (ncb - tti_cb)
-            t0 = time.perf_counter()
-            ctx.tdec_batch_submit(pin_in.array[lo:lo + tti_cb].ctypes.data, pin_out.array[lo:lo + tti_cb].ctypes.data, K, tti_cb, stride, 16, nit)
-            ctx.wait()
-            lat.append(time.perf_counter() - t0)
-    else:
-        tti_desc = "1 transport block of %d bits (%d code blocks), <=%d half-iterations with CRC early stop, host buffers in and out" % (tbs, cfg["C"], cfg["max_iter"])
-        one = b.make_tbs(1)
-        for i in range(n_lat + 20):
-            k = i % ntb
-            t = one[0]
-            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = pin_in.ptr + k * G * esz, G, tbs, Qm, 0, None, pin_out.ptr + k * ostride
-            t0 = time.perf_counter()
-            ctx.decode_tbs(one, dt == np.int8, cfg["max_iter"], flags=0)
-            lat.append(time.perf_counter() - t0)
+    n_lat = 0 if args.no_latency else (300 if not quick else 120)
     if n_lat:
+        lat = []
+        for i in range(n_lat + 20):
+            t0 = time.perf_counter()
+            latency_once(i)
+            lat.append(time.perf_counter() - t0)
         lat = np.sort(np.array(lat[20:])) * 1e6
         latency = {"tti": tti_desc, "p50_us": float(lat[len(lat) // 2]), "p99_us": float(lat[int(len(lat) * 0.99)]), "max_us": float(lat[-1]), "n": int(len(lat))}
     else:
-        latency = {"tti": tti_desc, "p50_us": None, "p99_us": None, "max_us": None, "n": 0}
+        latency = {"tti": "skipped (--no-latency)", "p50_us": None, "p99_us": None, "max_us": None, "n": 0}
     barrier()
 
-    if args.workload != "c1":
-        avg_it = float(np.mean([tb_dev[i].avg_iterations for i in range(ntb)]))
-        K, nit = cfg["K"], avg_it
-        algo_ops_per_step = (W8_OPS if cfg["dtype"] == np.int8 else W16_OPS) * K * avg_it * cfg["C"] * ntb
-        algo_bytes_per_step = ntb * (G * esz + tbs // 8)
-        n_ok = sum(1 for i in range(ntb) if tb_dev[i].ret == 0)
-        extra["avg_half_iterations"] = avg_it
-        extra["tb_ok_fraction"] = n_ok / ntb
-
-        # ---- front end of the path: soft demodulation + descrambling of the same subframes' symbols on
-        #      the device (k_demod_descramble, HBM-bound): device-resident symbols in, LLRs out, CUDA-event timed
-        mod = {6: 3, 8: 4}[Qm]
-        nsym = G // Qm
-        sym = ((rng.standard_normal((ntb, nsym)) + 1j * rng.standard_normal((ntb, nsym))) * 0.7).astype(np.complex64)
-        scr = b.sequence_bytes(0x12345, G)
-        d_sym = ctx.device_alloc(sym.nbytes)
-        d_scr = ctx.device_alloc(len(scr) + 16)
-        d_e = ctx.device_alloc(ntb * G * esz)
-        ctx.h2d(d_sym, sym)
-        ctx.h2d(d_scr, scr)
-        dm = b.make_demods(ntb)
-        for i in range(ntb):
-            dm[i].symbols, dm[i].nof_symbols, dm[i].mod, dm[i].scramble_bytes, dm[i].e_bits = d_sym + i * nsym * 8, nsym, mod, d_scr, d_e + i * G * esz
-        for _ in range(3):
-            ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
-        reps = 10
-        ctx.timer_start()
-        for _ in range(reps):
-            ctx.demod_descramble_raw(dm, dt == np.int8, b.IN_DEVICE | b.OUT_DEVICE)
-        fe_ms = ctx.timer_stop_ms() / reps
-        fe_bytes = ntb * (nsym * 8 + G * esz + G / 8)
-        extra["front_end"] = {"kernel": "k_demod_descramble", "what": "%d codewords x %d symbols, %s, %s LLRs, device-resident" % (
-                                  ntb, nsym, {3: "64QAM", 4: "256QAM"}[mod], np.dtype(dt).name),
-                              "ms": fe_ms, "gsym_per_s": ntb * nsym / (fe_ms * 1e-3) / 1e9,
-                              "hbm": {"achieved_gbs": fe_bytes / (fe_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                                      "frac": fe_bytes / (fe_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
-        for p_ in (d_sym, d_scr, d_e):
-            ctx.device_free(p_)
-
-        # ---- PUSCH pre-steps: a 100-PRB 64QAM uplink subframe per transport block -- ACK / RI / CQI LLR
-        #      extraction + channel de-interleaving (k_ulsch_deinterleave, HBM-bound), device-resident, CUDA-event timed
-        if dt == np.int16:
-            ul_rows, ul_cols, ul_Qm, ul_q = 1200, 12, 6, (36, 20, 57)
-            ul_n = ul_rows * ul_cols * ul_Qm
-            qll = rng.integers(-2000, 2000, (min(ntb, 256), ul_n)).astype(np.int16)
-            d_ulq = ctx.device_alloc(ntb * ul_n * 2)
-            d_ulg = ctx.device_alloc(ntb * ul_n * 2)
-            for i in range(0, ntb, len(qll)):
-                k = min(len(qll), ntb - i)
-                ctx.h2d(d_ulq + i * ul_n * 2, qll[:k])
-            ul = b.make_ulschs(ntb)
-            for i in range(ntb):
-                ul[i].q_bits, ul[i].Qm, ul[i].H_prime_total, ul[i].N_pusch_symbs, ul[i].g_bits = d_ulq + i * ul_n * 2, ul_Qm, ul_rows * ul_cols, ul_cols, d_ulg + i * ul_n * 2
-                ul[i].Q_prime_ack, ul[i].Q_prime_ri, ul[i].Q_prime_cqi = ul_q
-            for _ in range(3):
-                ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
-            ctx.timer_start()
-            for _ in range(10):
-                ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
-            ul_ms = ctx.timer_stop_ms() / 10
-            ul_bytes = ntb * (2 * ul_n * 2 - ul_q[1] * ul_Qm * 2)
-            extra["ul_pre"] = {"kernel": "k_ulsch_deinterleave", "what": "%d subframes x %d x %d symbols, 64QAM, Q'(ack, ri, cqi) = %s, device-resident" % (
-                                   ntb, ul_rows, ul_cols, list(ul_q)),
-                               "ms": ul_ms, "gllr_per_s": ntb * ul_n / (ul_ms * 1e-3) / 1e9,
-                               "hbm": {"achieved_gbs": ul_bytes / (ul_ms * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                                       "frac": ul_bytes / (ul_ms * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0)}}
-            ctx.device_free(d_ulq)
-            ctx.device_free(d_ulg)
-
-        # ---- transmit mirror of the same transport blocks: payload bytes -> packed e-bits, device-resident
-        pay = rng.integers(0, 256, (ntb, tbs // 8), dtype=np.uint8)
-        ew = (G + 31) // 32 * 4
-        d_pay = ctx.device_alloc(pay.nbytes)
-        d_eb = ctx.device_alloc(ntb * ew)
-        ctx.h2d(d_pay, pay)
-        en = b.make_encs(ntb)
-        for i in range(ntb):
-            en[i].data, en[i].tbs, en[i].Qm, en[i].rv, en[i].nof_e_bits, en[i].e_bits = d_pay + i * (tbs // 8), tbs, Qm, 0, G, d_eb + i * ew
-        for _ in range(3):
-            ctx.encode_tbs_raw(en, b.IN_DEVICE | b.OUT_DEVICE)
-        ctx.timer_start()
-        for _ in range(reps):
-            ctx.encode_tbs_raw(en, b.IN_DEVICE | b.OUT_DEVICE)
-        tx_ms = ctx.timer_stop_ms() / reps
-        extra["tx_mirror"] = {"kernel": "k_enc_tb_crc + k_enc_cb", "what": "%d transport blocks of %d bits -> %d e-bits each, device-resident" % (ntb, tbs, G),
-                              "ms": tx_ms, "encoded_mbps": ntb * tbs / (tx_ms * 1e-3) / 1e6}
-        ctx.device_free(d_pay)
-        ctx.device_free(d_eb)
-
-    # ---- roofline of the dominant kernel (k_map_win): integer-ALU issue bound.  The kernel is timed on its own here
-    #      (one engine, batches back to back, CUDA events around every launch on the launching stream).
-    rsteps = max(1, min(5, args.steps))
+    # ---- roofline of the dominant kernel: integer-ALU issue bound.  The kernel is timed on its own here (one engine,
+    #      batches back to back, CUDA events around the launches on the launching stream).
+    rsteps = max(1, min(5, steps))
     ctx.timer_start()
     r_map_ms, r_map_launches, r_gpu_ms = 0.0, 0, 0.0
     for i in range(rsteps):
@@ -613,33 +791,35 @@ def run_ours(args):
         r_gpu_ms += ctx.last_gpu_ms()
         r_map_launches += ctx.last_map_launches()
     ms_single = ctx.timer_stop_ms() / rsteps
-    # peak: issue rate of the packed instructions the kernel is made of, each measured on its own (VIADD.16x2, VIMNMX.S16x2,
-    # VIADDMNMX.S16x2, VIMNMX3.S16x2 all sustain 0.5 warp-instructions/clk/SM sub-partition on B200: 16-lane integer pipe)
-    probes = [ctx.alu_probe(op) for op in range(4)]
-    probe = min(probes)                # packed int16x2 instructions / s
-    probe_sat = ctx.alu_probe(4)
-    peak_lane_ops = 2.0 * probe        # one algorithmic operation per int16 lane and instruction
-    # the dominant kernel is the persistent k_map_fused: ONE launch runs all half-iterations of a batch (a second, exact-
-    # arithmetic launch follows and returns at once unless the range monitor parked blocks); `achieved` is the batch's
-    # algorithmic work over the event-timed duration of those launches
-    map_s_per_launch = (r_map_ms * 1e-3) / max(1, rsteps)
-    ach_lane_ops = (algo_ops_per_step / map_s_per_launch) if r_map_ms > 0 else 0.0
-    map_ms, map_launches = r_map_ms, r_map_launches
-    traffic = MAP_TRAFFIC_PER_CB.get(args.workload)
-    roofline = {"bound": "int_alu", "achieved": ach_lane_ops / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s (int16)",
-                "frac": ach_lane_ops / peak_lane_ops if peak_lane_ops else None,
-                "traffic": None if traffic is None else traffic["bytes_per_cb"] * (units_per_step / K if args.workload == "c1" else cfg["C"] * ntb),
-                "traffic_source": None if traffic is None else traffic["source"],
-                "kernel": "k_map_fused", "launches": map_launches, "avg_launch_ms": 1e3 * map_s_per_launch,
-                # share of the batch's device time (first kernel -> last kernel, CUDA events) spent in the MAP launches
+    ops = algo_ops()
+    if wl != "c1":
+        its = [tb_dev[i].avg_iterations for i in range(ntb)]
+        extra["avg_half_iterations"] = float(np.mean(its))
+        extra["tb_ok_fraction"] = sum(1 for i in range(ntb) if tb_dev[i].ret == 0) / ntb
+        cb_its = sum(sum(tb_dev[i].cb_noi[:tb_dev[i].nof_cb]) for i in range(ntb))
+        if wl == "c3":
+            hist = np.bincount([tb_dev[i].cb_noi[0] for i in range(ntb)], minlength=9)[:9]
+            extra["half_iteration_histogram"] = [int(x) for x in hist]
+    else:
+        cb_its = ncb * nit
+    probe, probes, probe_sat = alu_peak(env, ctx)
+    peak_lane_ops = 2.0 * probe
+    map_s = (r_map_ms * 1e-3) / rsteps
+    ach = ops / map_s if map_s > 0 else 0.0
+    roofline = {"bound": "int_alu", "achieved": ach / 1e12, "peak": peak_lane_ops / 1e12, "unit": "Tlane-op/s (int16)",
+                "frac": ach / peak_lane_ops if peak_lane_ops else None,
+                # whole step (driver-visible): algorithmic work of a step over the step time of the multi-engine loop
+                "frac_of_step": (ops / ((ms / steps) * 1e-3)) / peak_lane_ops if peak_lane_ops else None,
+                "traffic": MAP_TRAFFIC["bytes_per_cb_half_iteration"] * cb_its, "traffic_source": MAP_TRAFFIC["source"],
+                "kernel": "k_map_fused", "launches_per_batch": r_map_launches / rsteps, "kernel_ms_per_batch": 1e3 * map_s,
                 "map_share_of_step": r_map_ms / r_gpu_ms if r_gpu_ms else None, "batch_device_ms": r_gpu_ms / rsteps,
                 "single_stream_mbps": units_per_step / (ms_single * 1e-3) / 1e6,
                 "peak_source": "live micro-benchmark (k_alu_probe): min over VIADD.16x2 / VIMNMX.S16x2 / VIADDMNMX.S16x2 / VIMNMX3.S16x2 of the packed "
-                               "instruction rate, x2 int16 lanes; algorithmic work = 82 (int8: 106) lane-ops per trellis step and half-iteration",
+                               "instruction rate, x2 int16 lanes; algorithmic work = 82 (int8: 106) lane-ops per trellis step and half-iteration "
+                               "actually run",
                 "probe_packed_tops": [x / 1e12 for x in probes],
-                "peak_with_saturating_emulation": 2.0 * probe_sat / 1e12,
-                "hbm": {"achieved_gbs": algo_bytes_per_step / ((ms / args.steps) * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
-                        "frac": algo_bytes_per_step / ((ms / args.steps) * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src}}
+                "hbm": {"achieved_gbs": algo_bytes_per_step / ((ms / steps) * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"),
+                        "frac": algo_bytes_per_step / ((ms / steps) * 1e-3) / 1e9 / peaks.get("hbm_gbs", 6650.0), "peak_source": peak_src}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -648,36 +828,34 @@ def run_ours(args):
         except Exception as ex:  # the baseline is reporting only; never fail the GPU measurement on it
             cpu = {"value": None, "unit": "Mbit/s", "cores": 0, "kind": "unavailable", "sample": str(ex)}
 
-    if rank == 0:
-        line = {"metric": "turbo_decoded_mbps", "value": value, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int8" if args.workload == "c4" else "int16", "data": "synthetic",
-                "config": {"workload": workload, "l2": "inputs (%.0f MB per GPU per step) larger than the 126 MB L2" % (h2d_b / 1e6),
-                           "parallelism": "batch-sharded x%d, no collective" % world, "engines_per_gpu": n_eng, "e2e_chunks_per_step": args.e2e_chunks},
-                "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d_b * world), "d2h_bytes_per_step": int(d2h_b * world)},
-                "gpu_launches": int(launches * world), "latency": latency, "roofline": roofline}
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
-        line.update(extra)
-        print(json.dumps(line))
-    if world > 1:
-        import torch.distributed as dist
-        dist.destroy_process_group()
-    return 0
+    res = {"value": value, "ms_per_step": ms / steps, "dtype": dtype_name, "workload": workload, "engines": n_eng, "h2d_b": h2d_b,
+           "e2e": {"value": e2e_value, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d_b * world), "d2h_bytes_per_step": int(d2h_b * world),
+                   "h2d_gbs": h2d_b * world * steps / e2e_s / 1e9},
+           "gpu_launches": int(launches * world), "latency": latency, "roofline": roofline, "verified": verified,
+           "clocks": clocks_value, "clocks_e2e": clocks_e2e, "cpu_baseline": cpu, "sustained": sustained, "extra": extra}
+    for c in all_ctx[1:]:
+        c.close()
+    for p_ in frees:
+        ctx.device_free(p_)
+    for p_ in pins:
+        p_.free()
+    ctx.close()
+    return res
 
 
 # ----------------------------------------------------------------------------------------------- pooled cells (config 5)
-def run_c5(args):
+def measure_c5(env, args, steps, warmup, quick):
     """BASELINE config 5: the subframes of `--cells` cells, one downlink-shaped transport block (C2 shape) and one uplink
     subframe (100 PRB 64QAM with ACK, RI and CQI) per cell and TTI, sharded over the ranks by cell (HARQ affinity),
     decoded through srsran_b200.pool.CellPool from pinned host buffers.  A tenth of the downlink HARQ processes
     alternate between a first transmission that fails and the retransmission that combines with it."""
-    rank, world, local, barrier, vmax, vsum = dist_setup(args.gpus)
+    import ctypes as C
     import srsran_b200 as b
     from srsran_b200 import synth
     from srsran_b200.pool import CellPool, Job, owner_of
-    rng = np.random.default_rng(shard_seed(rank))
+    rank, world, local = env.rank, env.world, env.local
+    barrier, vmax, vsum = env.barrier, env.vmax, env.vsum
+    rng = np.random.default_rng(shard_seed(rank) + 500)
     # two pools per GPU, each with half of the rank's cells: while one pool's batch decodes, the other's is copied and planned
     pools = [CellPool(rank, world, local) for _ in range(2)]
     cells = [c for c in range(args.cells) if owner_of(c, world) == rank]
@@ -711,8 +889,6 @@ def run_c5(args):
                     jobs.append(Job(c, pid, "ul", pid, 0, True, tbs, Qm, pin_ul.ptr + k * n_q * 2, nsym, qp, n_llr=n_q))
             per_phase.append((jobs, pool.prepare(jobs)))
         batches.append(per_phase)
-    sampler = ClockSampler(local)
-    sampler.start()
     in_flight = [None, None]
     tally = [0, 0]  # decoded bits, kernel launches
 
@@ -732,47 +908,154 @@ def run_c5(args):
                 in_flight[pi] = batches[pi][i % 2][1]
                 pools[pi].submit(in_flight[pi])
 
-    for i in range(2 * max(1, args.warmup // 2)):
+    n_warm = 2 * max(1, warmup // 2)
+    for i in range(n_warm):
         step(i)
     retire(0)
     retire(1)
     barrier()
-    sampler.mark()
+    env.sampler.mark()
     tally[0] = tally[1] = 0
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         step(i)
     retire(0)
     retire(1)
     bits, launches = tally
     dt = vmax(time.perf_counter() - t0)
-    clocks = sampler.stop()
+    clocks = env.sampler.snapshot()
     barrier()
+    # ---- verification: one more (untimed) step of phase 0 -- every job of that phase is a first transmission, so the oracle
+    #      needs no history -- and a sample of its jobs against the oracle
+    from oracle.bindings import Port
+    P = Port()
+    n_ver = bad = 0
+    for pi in range(2):
+        jobs, bt = batches[pi][0]
+        if not jobs:
+            continue
+        pools[pi].submit(bt)
+        res = pools[pi].wait(bt, collect=True)
+        pick = list(range(0, len(jobs), max(1, len(jobs) // (6 if not quick else 3))))[:6]
+        for i in pick:
+            j = jobs[i]
+            e = np.ctypeslib.as_array((C.c_int16 * j.n_llr).from_address(j.llr)).copy()
+            if j.kind == "ul":
+                qa, qr, qc = j.q_prime
+                rc0, g, ack, ri, _ = P.ulsch_deinterleave(e, j.Qm, j.n_pusch_symbs, qa, qr)
+                e = g[qc * j.Qm:(j.n_llr // j.Qm - qr) * j.Qm].copy()
+            sb = P.softbuffer_new()
+            rc, want, nit, avg, crc = P.decode_tb(sb, j.tbs, j.Qm, j.rv, e, 8)
+            P.softbuffer_del(sb)
+            ok = res[i].ret == rc and (res[i].data[:j.tbs // 8 + 3] == want[:j.tbs // 8 + 3]).all() and res[i].cb_noi == nit[:len(res[i].cb_noi)].tolist()
+            n_ver += 1
+            bad += int(not ok)
+    verified = {"n": n_ver, "mismatches": bad, "against": "oracle port (pinned to the reference)", "what": "return code, transport block bytes, cb_noi (DL and UL jobs)"}
     total = vsum(bits)
     my_jobs = batches[0][0][0] + batches[1][0][0]
     n_jobs = vsum(len(my_jobs))
-    if rank == 0:
-        val = total / dt / 1e6
-        h2d = sum((j.n_llr * 2) for j in my_jobs)
-        line = {"metric": "turbo_decoded_mbps", "value": val, "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "int16",
-                "data": "synthetic",
-                "config": {"workload": "c5-pooled: %d cells x %d TTIs per step (one 75376-bit downlink-shaped block + one 100-PRB 64QAM uplink subframe with "
-                                       "ACK/RI/CQI per cell and TTI), cells sharded over %d rank(s), device-resident HARQ soft buffers, 10%% of the downlink "
-                                       "processes alternate failing first transmission / combining retransmission" % (args.cells, n_pid, world),
-                           "l2": "inputs of a step (%d MB over all ranks) larger than the 126 MB L2" % (n_jobs * G * 2 // 1000000),
-                           "parallelism": "cells sharded x%d, no collective" % world, "note": "host-fed only: value == e2e (wall clock, max over ranks)"},
-                "clocks": clocks, "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": len(my_jobs) * (tbs // 8 + 6)},
-                "gpu_launches": int(launches), "decoded_tb_fraction": total / (n_jobs * tbs * args.steps)}
-        print(json.dumps(line))
+    val = total / dt / 1e6
+    h2d = vsum(sum((j.n_llr * 2) for j in my_jobs))
+    res = {"value": val, "ms_per_step": 1e3 * dt / steps, "dtype": "int16", "scaling": "strong",
+           "workload": "c5-pooled: %d cells x %d TTIs per step (one 75376-bit downlink-shaped block + one 100-PRB 64QAM uplink subframe with "
+                       "ACK/RI/CQI per cell and TTI), cells sharded over %d rank(s), device-resident HARQ soft buffers, 10%% of the downlink "
+                       "processes alternate failing first transmission / combining retransmission" % (args.cells, n_pid, world),
+           "note": "host-fed only: value == e2e (wall clock, max over ranks)",
+           "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_jobs * (tbs // 8 + 6)),
+                   "h2d_gbs": h2d * steps / dt / 1e9},
+           "gpu_launches": int(vsum(launches)), "decoded_tb_fraction": total / (n_jobs * tbs * steps), "verified": verified, "clocks": clocks,
+           "latency": None, "roofline": None, "cpu_baseline": None, "sustained": None, "extra": {}, "engines": 4}
     for pi, pool in enumerate(pools):
         for _, bt in batches[pi]:
             pool.release(bt)
         pool.close()
+    for p_ in (pin_dl, pin_hard, pin_ul):
+        p_.free()
+    return res
+
+
+def compact(r):
+    """one line of the `configs` block"""
+    out = {"workload": r["workload"], "value": r["value"], "unit": "Mbit/s", "ms_per_step": r["ms_per_step"], "e2e": r["e2e"]["value"],
+           "verified": r["verified"]}
+    if r.get("roofline"):
+        out["roofline_frac"] = r["roofline"]["frac"]
+        out["kernel_ms_per_batch"] = r["roofline"]["kernel_ms_per_batch"]
+        out["map_share_of_step"] = r["roofline"]["map_share_of_step"]
+    if r.get("latency"):
+        out["latency"] = {k: r["latency"][k] for k in ("tti", "p50_us", "p99_us")}
+    if r.get("cpu_baseline"):
+        c = r["cpu_baseline"]
+        out["cpu_baseline"] = {k: c.get(k) for k in ("value", "cores", "kind", "sample", "latency_one_core")}
+    for k in ("avg_half_iterations", "tb_ok_fraction", "exact_replay_fraction", "half_iteration_histogram"):
+        if k in r.get("extra", {}):
+            out[k] = r["extra"][k]
+    if "decoded_tb_fraction" in r:
+        out["decoded_tb_fraction"] = r["decoded_tb_fraction"]
+    return out
+
+
+def run_ours(args):
+    rank, world, local, barrier, vmax, vsum = dist_setup(args.gpus)
+    import srsran_b200 as b
+    env = Env()
+    env.rank, env.world, env.local, env.barrier, env.vmax, env.vsum = rank, world, local, barrier, vmax, vsum
+    env.peaks, env.peak_src = load_peaks()
+    env.probe = None
+    env.cores_per_rank = pin_rank_threads(local, int(os.environ.get("LOCAL_WORLD_SIZE", world)))
+    env.sampler = ClockSampler(world, enabled=(rank == 0))
+    env.sampler.start()
+
+    def measure(wl, steps, warmup, quick):
+        if wl == "c5":
+            return measure_c5(env, args, steps, warmup, quick)
+        return measure_batched(env, args, wl, steps, warmup, quick)
+
+    main_r = measure(args.workload, args.steps, args.warmup, False)
+    # plain concurrent host-to-device bandwidth of the job (what `e2e` is bounded by: 36.9 KB of LLRs per 6144 decoded bits)
+    pctx = b.Context(local)
+    h2d_gbs = h2d_probe(env, b, pctx)
+    pctx.close()
+    configs = {}
+    if args.workload == "c1" and not args.no_configs:
+        for wl in ("c2", "c3", "c4", "c5"):
+            try:
+                configs[wl] = compact(measure(wl, max(4, min(args.steps, args.config_steps)), 3, True))
+            except Exception as ex:  # a secondary configuration must not take the headline down; it is reported as failed
+                if world > 1:
+                    raise  # (the ranks would lose step with each other)
+                configs[wl] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+    env.sampler.stop()
+
+    bad = main_r["verified"]["mismatches"] + sum((c.get("verified") or {}).get("mismatches", 0) for c in configs.values())
+    if rank == 0:
+        line = {"metric": "turbo_decoded_mbps", "value": main_r["value"], "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": main_r.get("scaling", "weak"), "vs_baseline": None,
+                "dtype": main_r["dtype"], "data": "synthetic",
+                "config": {"workload": main_r["workload"],
+                           "l2": ("inputs (%.0f MB per GPU per step) larger than the 126 MB L2" % (main_r["h2d_b"] / 1e6)) if "h2d_b" in main_r else
+                                 "inputs of a step larger than the 126 MB L2",
+                           "parallelism": "batch-sharded x%d, no collective" % world, "engines_per_gpu": main_r["engines"], "e2e_chunks_per_step": args.e2e_chunks,
+                           "host_cores_per_rank": env.cores_per_rank},
+                "clocks": main_r["clocks"],
+                "e2e": dict(main_r["e2e"], h2d_probe_gbs=h2d_gbs, h2d_frac_of_probe=(main_r["e2e"]["h2d_gbs"] / h2d_gbs if h2d_gbs else None)),
+                "gpu_launches": main_r["gpu_launches"], "latency": main_r["latency"], "roofline": main_r["roofline"], "verified": main_r["verified"]}
+        if main_r.get("clocks_e2e"):
+            line["clocks_e2e"] = main_r["clocks_e2e"]
+        if main_r.get("sustained"):
+            line["sustained"] = main_r["sustained"]
+        if main_r.get("cpu_baseline") is not None:
+            line["cpu_baseline"] = main_r["cpu_baseline"]
+        if "decoded_tb_fraction" in main_r:
+            line["decoded_tb_fraction"] = main_r["decoded_tb_fraction"]
+        line.update(main_r.get("extra", {}))
+        if configs:
+            line["configs"] = configs
+        print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
-    return 0
+    return 1 if bad else 0
 
 
 def main():
@@ -781,13 +1064,17 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c4", "c5"])
+    ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cells", type=int, default=20, help="cells of the pooled workload (c5), sharded over the ranks")
-    ap.add_argument("--ncb", type=int, default=18944, help="code blocks per step per GPU (c1); 18944 = 4 full waves of 148 CTAs x 32 blocks")
+    ap.add_argument("--ncb", type=int, default=18944, help="code blocks per step per GPU (c1)")
     ap.add_argument("--ntb", type=int, default=1000, help="transport blocks per step per GPU (c2/c4)")
+    ap.add_argument("--c3-per-k", type=int, default=64, help="transport blocks per LTE code block size and step per GPU (c3)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-TTI latency loop (keeps profiler launch lists short)")
+    ap.add_argument("--no-configs", action="store_true", help="c1 only: skip the compact c2 / c3 / c4 / c5 block")
+    ap.add_argument("--config-steps", type=int, default=8, help="timed steps of each configuration of the compact block")
+    ap.add_argument("--sustain-seconds", type=float, default=1.5, help="extra device-resident loop of about this long (0: skip)")
     ap.add_argument("--engines", type=int, default=0,
                     help="engines (streams) per GPU the batches / end-to-end chunks rotate over (default: 4 for c1, 6 for the early-stop workloads "
                          "whose last half-iterations run nearly empty and overlap with other batches)")
@@ -795,12 +1082,8 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=4, help="chunks one end-to-end step is split into")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    if args.engines <= 0:
-        args.engines = 4 if args.workload == "c1" else 6
     if args.impl == "reference":
         return run_reference(args)
-    if args.workload == "c5":
-        return run_c5(args)
     return run_ours(args)
 
 

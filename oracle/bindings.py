@@ -17,6 +17,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_SO = os.path.join(HERE, "liboracle.so")
 REF_SO = os.path.join(HERE, "_ref", "libsrslte_ref.so")
+REF_FAST_SO = os.path.join(HERE, "_ref", "libsrslte_ref_fast.so")
 
 CRC24A = 0x1864CFB
 CRC24B = 0x1800063
@@ -259,10 +260,16 @@ class Ref:
     def available():
         return os.path.exists(REF_SO)
 
-    def __init__(self):
-        if not os.path.exists(REF_SO):
+    def __init__(self, fast=False):
+        """fast=True: the build with the reference's release flags (-Ofast -funroll-loops), for bench.py's CPU baseline only"""
+        so = REF_SO
+        if fast and os.path.exists(REF_FAST_SO):
+            so = REF_FAST_SO
+        if not os.path.exists(so):
             raise RuntimeError("reference library not built: run oracle/build_ref.sh where /root/reference exists")
-        L = self.L = C.CDLL(REF_SO)
+        self.flags = "-Ofast -funroll-loops -mavx2 -mfma" if so == REF_FAST_SO else "-O3 -mavx2 -mfma"
+        L = self.L = C.CDLL(so)
+        L.ref_bench_tb_mixed.restype = C.c_double
         L.ref_tdec_new.restype = C.c_void_p
         L.ref_sch_new.restype = C.c_void_p
         L.ref_crc_byte.restype = C.c_uint32
@@ -475,6 +482,36 @@ class Ref:
         t = self.L.ref_bench_c1(C.c_int(nthreads), _p(llr), C.c_uint32(stride), C.c_uint32(ncb), C.c_uint32(K), C.c_uint32(nof_iter),
                                 C.c_int(int(llr.dtype == np.int8)), C.c_int(int(layout_sb)), _p(out), C.c_uint32(repeat))
         return t, out
+
+    def bench_tb_mixed(self, nthreads, llr_flat, off, tbs, Qm, G, max_iter, repeat=1):
+        """transport blocks of different sizes: llr_flat holds all e-bits, off[i] the element offset of block i.
+        Returns (seconds, data (ntb, stride), rc, avg_iter)."""
+        ntb = len(tbs)
+        off = np.ascontiguousarray(off, np.uint64)
+        tbs, Qm, G = (np.ascontiguousarray(x, np.uint32) for x in (tbs, Qm, G))
+        stride = int(tbs.max()) // 8 + 8 + 768
+        out = np.zeros((ntb, stride), np.uint8)
+        rc = np.zeros(ntb, np.int32)
+        avg = np.zeros(ntb, np.float32)
+        t = self.L.ref_bench_tb_mixed(C.c_int(nthreads), _p(llr_flat), _p(off), _p(tbs), _p(Qm), _p(G), C.c_uint32(ntb), C.c_uint32(max_iter),
+                                      C.c_int(int(llr_flat.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg), C.c_uint32(repeat))
+        return t, out, rc, avg
+
+    def latency_tb(self, llr, tbs, Qm, max_iter, n_calls):
+        """per-call wall time (us) of srslte_dlsch_decode2 for one transport block on one pinned core"""
+        ntb, G = llr.shape
+        lat = np.zeros(n_calls, np.float64)
+        self.L.ref_latency_tb(_p(llr), C.c_uint32(ntb), C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(G), C.c_uint32(max_iter),
+                              C.c_int(int(llr.dtype == np.int8)), C.c_uint32(n_calls), _p(lat))
+        return lat
+
+    def latency_c1(self, llr, K, nof_iter, cbs_per_tti, n_calls):
+        """per-call wall time (us) of cbs_per_tti x srslte_tdec_run_all on one pinned core"""
+        ncb, stride = llr.shape
+        lat = np.zeros(n_calls, np.float64)
+        self.L.ref_latency_c1(_p(llr), C.c_uint32(stride), C.c_uint32(ncb), C.c_uint32(K), C.c_uint32(nof_iter), C.c_uint32(cbs_per_tti),
+                              C.c_uint32(n_calls), _p(lat))
+        return lat
 
     def bench_tb(self, nthreads, llr, tbs, Qm, rv, max_iter, repeat=1):
         """llr: (ntb, G) int16/int8.  Returns (seconds, data (ntb, stride), rc (ntb,), avg_iter (ntb,))."""

@@ -53,3 +53,21 @@ OBJS="$OBJS $o"
 gcc $CFLAGS -c "$HERE/ref_shim.c" -o "$OUT/obj/ref_shim.o"
 g++ -shared -o "$OUT/libsrslte_ref.so" $OBJS "$OUT/obj/ref_shim.o" -lm -lpthread
 echo "built $OUT/libsrslte_ref.so"
+
+# Second build for bench.py's CPU baseline only: the reference's RELEASE optimisation flags (CMakeLists.txt:394-417:
+# -Ofast -funroll-loops -mfpmath=sse on top of the ISA flags; -march=native is left out because the library is built here and
+# runs on the GPU box's host CPU).  The parity tests keep using the -O3 build above.
+FFLAGS="-Ofast -funroll-loops -mfpmath=sse -std=gnu99 -fPIC -mavx2 -mfma -msse4.1 -DLV_HAVE_SSE -DLV_HAVE_AVX -DLV_HAVE_AVX2 -DLV_HAVE_FMA \
+ -I$OUT/inc -I$R/include -fno-strict-aliasing -w"
+mkdir -p "$OUT/objf"
+FOBJS=""
+for f in $CFILES; do
+  o="$OUT/objf/$(echo "$f" | tr '/' '_' | sed 's/\.c$/.o/')"
+  if [ ! -f "$o" ] || [ "$R/$f" -nt "$o" ]; then
+    gcc $FFLAGS -c "$R/$f" -o "$o"
+  fi
+  FOBJS="$FOBJS $o"
+done
+gcc $FFLAGS -c "$HERE/ref_shim.c" -o "$OUT/objf/ref_shim.o"
+g++ -shared -o "$OUT/libsrslte_ref_fast.so" $FOBJS "$OUT/obj/random.o" "$OUT/objf/ref_shim.o" -lm -lpthread
+echo "built $OUT/libsrslte_ref_fast.so"

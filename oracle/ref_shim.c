@@ -17,7 +17,9 @@
  *
  * Nothing in here re-implements reference arithmetic.
  */
+#define _GNU_SOURCE
 #include <pthread.h>
+#include <sched.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -43,6 +45,28 @@ static double now_s(void)
   struct timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+/* pin the calling thread to the t-th CPU of the process's affinity mask (pinned threads) */
+static void pin_to_cpu(int t)
+{
+  cpu_set_t all, one;
+  if (sched_getaffinity(0, sizeof(all), &all) != 0)
+    return;
+  int n = CPU_COUNT(&all);
+  if (n <= 0)
+    return;
+  int want = t % n, seen = 0;
+  for (int c = 0; c < CPU_SETSIZE; c++) {
+    if (!CPU_ISSET(c, &all))
+      continue;
+    if (seen++ == want) {
+      CPU_ZERO(&one);
+      CPU_SET(c, &one);
+      pthread_setaffinity_np(pthread_self(), sizeof(one), &one);
+      return;
+    }
+  }
 }
 
 int ref_init(void)
@@ -362,6 +386,7 @@ static void* c1_worker(void* p)
 {
   c1_arg_t*   a = p;
   ref_tdec_t* h = g_c1_dec[a->tid][a->layout_sb ? 1 : 0];
+  pin_to_cpu(a->tid);
   pthread_barrier_wait(a->bar);
   a->t0 = now_s();
   for (uint32_t r = 0; r < a->repeat; r++) {
@@ -452,6 +477,7 @@ static void* tb_worker(void* p)
 {
   tb_arg_t*  a = p;
   ref_sch_t* s = g_workers[a->tid];
+  pin_to_cpu(a->tid);
   pthread_barrier_wait(a->bar);
   a->t0 = now_s();
   for (uint32_t r = 0; r < a->repeat; r++) {
@@ -512,6 +538,116 @@ double ref_bench_tb(int      nthreads,
   return t1 - t0;
 }
 
+
+/* --------------------------------------------- mixed-size transport blocks (BASELINE config 3) */
+typedef struct {
+  int             tid, nthreads;
+  uint32_t        ntb, max_iter, repeat;
+  int             is8;
+  void*           llr;     /* all e-bits, one array */
+  const uint64_t* off;     /* element offset of TB i in llr */
+  const uint32_t *tbs, *Qm, *G;
+  uint8_t*        out;     /* ntb x out_stride */
+  uint32_t        out_stride;
+  int*            rc;
+  float*          avg_iter;
+  pthread_barrier_t* bar;
+  double          t0, t1;
+} mix_arg_t;
+
+static void* mix_worker(void* p)
+{
+  mix_arg_t* a = p;
+  ref_sch_t* s = g_workers[a->tid];
+  pin_to_cpu(a->tid);
+  pthread_barrier_wait(a->bar);
+  a->t0 = now_s();
+  for (uint32_t r = 0; r < a->repeat; r++) {
+    for (uint32_t tb = a->tid; tb < a->ntb; tb += a->nthreads) {
+      srslte_softbuffer_rx_reset_tbs(&s->rx, a->tbs[tb]);
+      void* llr = a->is8 ? (void*)((int8_t*)a->llr + a->off[tb]) : (void*)((int16_t*)a->llr + a->off[tb]);
+      srslte_pdsch_cfg_t cfg;
+      fill_cfg(s, &cfg, a->tbs[tb], a->Qm[tb], a->G[tb], 0, 0);
+      a->rc[tb]       = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, a->out + (size_t)tb * a->out_stride, 0, 1);
+      a->avg_iter[tb] = srslte_sch_last_noi(&s->sch);
+    }
+  }
+  a->t1 = now_s();
+  return NULL;
+}
+
+/* Decode ntb transport blocks of DIFFERENT sizes (new transmissions, rv 0) with srslte_dlsch_decode2 on nthreads pinned
+ * threads; returns wall seconds. */
+double ref_bench_tb_mixed(int nthreads, void* llr, const uint64_t* off, const uint32_t* tbs, const uint32_t* Qm, const uint32_t* G, uint32_t ntb,
+                          uint32_t max_iter, int is8, uint8_t* out, uint32_t out_stride, int* rc, float* avg_iter, uint32_t repeat)
+{
+  srslte_rm_turbo_gentables();
+  if (nthreads > MAX_WORKERS)
+    nthreads = MAX_WORKERS;
+  for (int t = 0; t < nthreads; t++)
+    get_worker(t, is8, max_iter);
+  pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
+  mix_arg_t*        a  = calloc(nthreads, sizeof(mix_arg_t));
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    a[t] = (mix_arg_t){t, nthreads, ntb, max_iter, repeat ? repeat : 1, is8, llr, off, tbs, Qm, G, out, out_stride, rc, avg_iter, &bar, 0, 0};
+    pthread_create(&th[t], NULL, mix_worker, &a[t]);
+  }
+  double t0 = 1e300, t1 = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    if (a[t].t0 < t0)
+      t0 = a[t].t0;
+    if (a[t].t1 > t1)
+      t1 = a[t].t1;
+  }
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(a);
+  return t1 - t0;
+}
+
+/* --------------------------------------------- per-TTI latency on ONE pinned core (us per TTI, p50 / p99;
+ * the reference times the same call, lib/src/phy/phch/pdsch.c:921-924, 1061-1065).  lat_us[i] = wall time of call i. */
+int ref_latency_tb(void* llr, uint32_t ntb, uint32_t tbs, uint32_t Qm, uint32_t G, uint32_t max_iter, int is8, uint32_t n_calls, double* lat_us)
+{
+  srslte_rm_turbo_gentables();
+  ref_sch_t* s = get_worker(0, is8, max_iter);
+  uint8_t*   out = calloc(tbs / 8 + 8 + 768, 1);
+  pin_to_cpu(0);
+  for (uint32_t i = 0; i < n_calls; i++) {
+    uint32_t tb = i % ntb;
+    void*    l  = is8 ? (void*)((int8_t*)llr + (size_t)tb * G) : (void*)((int16_t*)llr + (size_t)tb * G);
+    double   t0 = now_s();
+    srslte_softbuffer_rx_reset_tbs(&s->rx, tbs);
+    srslte_pdsch_cfg_t cfg;
+    fill_cfg(s, &cfg, tbs, Qm, G, 0, 0);
+    srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)l, out, 0, 1);
+    lat_us[i] = 1e6 * (now_s() - t0);
+  }
+  free(out);
+  return 0;
+}
+/* one "TTI" of the code-block workload: cbs_per_tti blocks of size K through srslte_tdec_run_all, one pinned core */
+int ref_latency_c1(void* llr, uint32_t stride, uint32_t ncb, uint32_t K, uint32_t nof_iter, uint32_t cbs_per_tti, uint32_t n_calls, double* lat_us)
+{
+  if (!g_c1_dec[0][0])
+    g_c1_dec[0][0] = ref_tdec_new(6144, SRSLTE_TDEC_AUTO, 1);
+  ref_tdec_t* h   = g_c1_dec[0][0];
+  uint8_t*    out = calloc(K / 8 + 16, 1);
+  pin_to_cpu(0);
+  for (uint32_t i = 0; i < n_calls; i++) {
+    double t0 = now_s();
+    for (uint32_t c = 0; c < cbs_per_tti; c++) {
+      uint32_t cb = (i * cbs_per_tti + c) % ncb;
+      srslte_tdec_run_all(&h->td, (int16_t*)llr + (size_t)cb * stride, out, nof_iter, K);
+    }
+    lat_us[i] = 1e6 * (now_s() - t0);
+  }
+  free(out);
+  return 0;
+}
 
 /* ------------------------------------------------------------------ soft demodulation + descrambling */
 int ref_demod_s(int mod, const float* symbols, int16_t* llr, int nsymbols)

@@ -9,6 +9,7 @@
 #include <cstring>
 #include <map>
 #include <mutex>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -39,6 +40,9 @@ struct Plan {
   uint32_t           cb_out_bytes = 0;
 };
 
+struct LaunchState;
+static LaunchState* new_launch_state();
+static void         delete_launch_state(LaunchState* p);
 static int lanes_idx(uint32_t lanes) { return lanes == 8 ? 1 : lanes == 16 ? 2 : lanes == 32 ? 3 : 0; }
 
 // byte table of crc.c:30-46 for a 24-bit polynomial
@@ -203,6 +207,7 @@ int Engine::create(Engine** out, int device)
   e->device   = device;
   e->num_sms  = prop.multiProcessorCount;
   e->plan_ptr = new Plan();
+  e->ls_ptr   = new_launch_state();
   if (const char* ev = getenv("SRSLTE_B200_FAST16"))
     e->opt_fast16 = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_LATENCY"))
@@ -211,10 +216,18 @@ int Engine::create(Engine** out, int device)
     e->opt_fused = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
     e->opt_fused_warps = atoi(ev);
-  CUDA_OK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
-  CUDA_OK(cudaEventCreate(&e->ev_begin));
-  CUDA_OK(cudaEventCreate(&e->ev_end));
-  CUDA_OK(cudaEventCreateWithFlags(&e->ev_desc, cudaEventDisableTiming));
+  cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+  if (ce == cudaSuccess)
+    ce = cudaEventCreate(&e->ev_begin);
+  if (ce == cudaSuccess)
+    ce = cudaEventCreate(&e->ev_end);
+  if (ce == cudaSuccess)
+    ce = cudaEventCreateWithFlags(&e->ev_desc, cudaEventDisableTiming);
+  if (ce != cudaSuccess) {
+    set_error(std::string("engine set-up: ") + cudaGetErrorString(ce));
+    delete e; // (the destructor copes with the members that were not created)
+    return SRSLTE_B200_ERROR;
+  }
   int rc = e->build_tables();
   if (rc) {
     delete e;
@@ -248,6 +261,7 @@ Engine::~Engine()
   if (stream)
     cudaStreamDestroy(stream);
   delete plan_ptr;
+  delete_launch_state(ls_ptr);
 }
 
 int Engine::build_tables()
@@ -434,15 +448,14 @@ typedef CUresult (*TmapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, 
                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static TmapEncodeFn tmap_encoder()
 {
-  static TmapEncodeFn fn = nullptr;
-  static bool         tried = false;
-  if (!tried) {
-    tried = true;
+  static TmapEncodeFn   fn = nullptr;
+  static std::once_flag once; // engines are created from several threads
+  std::call_once(once, [] {
     cudaDriverEntryPointQueryResult qr;
     void*                           p = nullptr;
     if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
       fn = (TmapEncodeFn)p;
-  }
+  });
   return fn;
 }
 // workspace of one K-group as the tensor (T words | block | row | plane); box = (T, G, L, planes)
@@ -511,6 +524,26 @@ static cudaError_t launch_map_f16(MapArgs a, int n_slots, uint32_t n_iter, cudaS
 struct FusedGeom {
   int grid, warps, warp_words, bits_words;
 };
+struct ClassRun {
+  size_t off, winfo_off;
+  int    n_slots, max_w, max_k;
+  bool   no_crc; // run_all semantics for every block of the class: only the last half-iteration's decisions are read
+};
+// Everything the kernel launches of a batch need once its descriptors, work lists and tensor maps sit in device memory.
+// A batch that repeats the previous one on this engine (same shapes, same buffers: a receiver's steady state, the
+// benchmark's steps) is launched again from this record without re-planning or re-uploading anything.
+struct LaunchState {
+  bool      valid = false;
+  int       n_cb = 0, n_dm16 = 0, n_dm8 = 0, n_plain = 0, n_pairs = 0, gen_threads = 0, n_old = 0, n_tbs = 0;
+  size_t    off_dm16 = 0, off_dm8 = 0, off_plain = 0, off_gen = 0, off_old = 0, ctr_fetch0 = 0, n_counters = 0;
+  uint32_t  max_iter = 0, iter0 = 0;
+  bool      prepare = true;
+  ClassRun  cls[4];
+  bool      cls_lat[4], cls_fused[4];
+  FusedGeom fgeo[4];
+};
+static LaunchState* new_launch_state() { return new LaunchState(); }
+static void         delete_launch_state(LaunchState* p) { delete p; }
 template <int N>
 static FusedGeom fused_geometry(int n_groups, int max_k, int num_sms, int warps_per_cta)
 {
@@ -553,13 +586,22 @@ static cudaError_t launch_fused(FusedArgs a, const FusedGeom& g, cudaStream_t st
 
 int Engine::run(Plan& p)
 {
+  cache_key.clear(); // (callers whose batches are reusable set it again after a successful run)
+  int rc = build_plan(p);
+  return rc ? rc : launch_plan();
+}
+
+// Host planning of a batch: work lists, workspace layout, tensor maps; uploads them.  Fills *ls_ptr.
+int Engine::build_plan(Plan& p)
+{
   CUDA_OK(cudaSetDevice(device));
   const int n_cb = (int)p.cbs.size();
-  last_launches = 0;
-  last_map_launches = 0;
-  n_map_events_used = 0;
-  if (n_cb == 0)
+  ls_ptr->valid = false;
+  if (n_cb == 0) {
+    *ls_ptr = LaunchState();
+    ls_ptr->valid = true;
     return 0;
+  }
 
   // ---- workspace layout + output slots
   // (workspace offsets are assigned below in work-list order: the slots of a warp are adjacent in memory)
@@ -590,11 +632,9 @@ int Engine::run(Plan& p)
       plain.push_back(i);
   }
   const size_t off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
-  struct ClassRun {
-    size_t off, winfo_off;
-    int    n_slots, max_w, max_k;
-    bool   no_crc; // run_all semantics for every block of the class: only the last half-iteration's decisions are read
-  } cls[4];
+  LaunchState& L   = *ls_ptr;
+  L                = LaunchState();
+  ClassRun(&cls)[4] = L.cls;
   struct KGroup { // code blocks of one size in one decoder class: consecutive slots, consecutive workspace
     int      cls, first_slot, n_blocks;
     uint32_t W, ps;
@@ -676,7 +716,10 @@ int Engine::run(Plan& p)
 
   // ---- which kernel runs a class: the latency-shaped per-half-iteration kernel when its groups leave most SMs empty (one
   //      subframe or a few), else ONE persistent fused launch for all half-iterations
-  bool cls_lat[4] = {false, false, false, false}, cls_fused[4] = {false, false, false, false};
+  bool(&cls_lat)[4] = L.cls_lat;
+  bool(&cls_fused)[4] = L.cls_fused;
+  for (int c = 0; c < 4; c++)
+    cls_lat[c] = cls_fused[c] = false;
   std::vector<int> old_path; // blocks decided by k_decide_crc after every half-iteration: latency classes + generic decoder
   for (int c = 0; c < 4; c++) {
     if (!cls[c].n_slots)
@@ -739,39 +782,8 @@ int Engine::run(Plan& p)
     CUDA_OK(cudaMemcpyAsync(d_tbs.ptr, hp, p.tbs.size() * sizeof(TbDev), cudaMemcpyHostToDevice, stream));
   }
 
-  const size_t ctr_fetch0 = 4 + (size_t)p.max_iter + 1; // group fetch counters of the fused launches (two per class)
-  const size_t n_counters = ctr_fetch0 + 8;
-  if (d_counters.reserve(n_counters) || h_counters.reserve(4))
-    return SRSLTE_B200_ERROR;
-  CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, n_counters * sizeof(uint32_t), stream));
-  CUDA_OK(cudaEventRecord(ev_begin, stream));
-
-  // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
-  //      directly supplied LLRs: extraction only
-  const size_t sb_smem = (3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t);
-  if (!dm16.empty()) {
-    auto kern = k_dematch_prepare<int16_t>;
-    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
-    kern<<<(int)dm16.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
-    last_launches++;
-  }
-  if (!dm8.empty()) {
-    auto kern = k_dematch_prepare<int8_t>;
-    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
-    kern<<<(int)dm8.size(), 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
-    last_launches++;
-  }
-  if (!plain.empty() && p.prepare) {
-    // staging of one code block (3K+12 LLRs) + one padded plane for the transposition into the lane layout
-    const size_t prep_smem = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
-    CUDA_OK(smem_attr_once((const void*)k_prepare, (int)prep_smem));
-    k_prepare<<<(int)plain.size(), 256, prep_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
-    last_launches++;
-  }
-  CUDA_OK(cudaGetLastError());
-
   // ---- global scratch for the beta checkpoints of the windowed kernels
-  FusedGeom fgeo[4];
+  FusedGeom(&fgeo)[4] = L.fgeo;
   {
     size_t need = 0;
     for (int c = 0; c < 4; c++) {
@@ -805,6 +817,66 @@ int Engine::run(Plan& p)
     if (need && d_ckscratch.reserve(need))
       return SRSLTE_B200_ERROR;
   }
+
+  const size_t ctr_fetch0 = 4 + (size_t)p.max_iter + 1; // group fetch counters of the fused launches (two per class)
+  const size_t n_counters = ctr_fetch0 + 8;
+  if (d_counters.reserve(n_counters) || h_counters.reserve(4))
+    return SRSLTE_B200_ERROR;
+  L.n_cb = n_cb; L.n_dm16 = (int)dm16.size(); L.n_dm8 = (int)dm8.size(); L.n_plain = (int)plain.size(); L.n_pairs = n_pairs;
+  L.gen_threads = gen_threads; L.n_old = (int)old_path.size(); L.n_tbs = (int)p.tbs.size();
+  L.off_dm16 = off_dm16; L.off_dm8 = off_dm8; L.off_plain = off_plain; L.off_gen = off_gen; L.off_old = off_old;
+  L.ctr_fetch0 = ctr_fetch0; L.n_counters = n_counters; L.max_iter = p.max_iter; L.iter0 = p.iter0; L.prepare = p.prepare;
+  L.valid = true;
+  return 0;
+}
+
+// Enqueue the kernels of the batch described by *ls_ptr (device-resident descriptors, work lists, tensor maps).
+int Engine::launch_plan()
+{
+  CUDA_OK(cudaSetDevice(device));
+  const LaunchState& L = *ls_ptr;
+  last_launches = 0;
+  last_map_launches = 0;
+  n_map_events_used = 0;
+  if (!L.valid || L.n_cb == 0)
+    return 0;
+  const ClassRun(&cls)[4] = L.cls;
+  const bool(&cls_lat)[4] = L.cls_lat;
+  const bool(&cls_fused)[4] = L.cls_fused;
+  const FusedGeom(&fgeo)[4] = L.fgeo;
+  const size_t off_dm16 = L.off_dm16, off_dm8 = L.off_dm8, off_plain = L.off_plain, off_gen = L.off_gen, off_old = L.off_old;
+  const size_t ctr_fetch0 = L.ctr_fetch0, n_counters = L.n_counters;
+  const int    n_pairs = L.n_pairs, gen_threads = L.gen_threads;
+  struct {
+    uint32_t max_iter, iter0;
+    bool     prepare;
+  } p{L.max_iter, L.iter0, L.prepare};
+  CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, n_counters * sizeof(uint32_t), stream));
+  CUDA_OK(cudaEventRecord(ev_begin, stream));
+
+  // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
+  //      directly supplied LLRs: extraction only
+  const size_t sb_smem = (3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t);
+  if (L.n_dm16 > 0) {
+    auto kern = k_dematch_prepare<int16_t>;
+    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
+    kern<<<L.n_dm16, 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm16, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
+    last_launches++;
+  }
+  if (L.n_dm8 > 0) {
+    auto kern = k_dematch_prepare<int8_t>;
+    CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));
+    kern<<<L.n_dm8, 256, sb_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_dm8, d_rm.ptr, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr);
+    last_launches++;
+  }
+  if (L.n_plain > 0 && p.prepare) {
+    // staging of one code block (3K+12 LLRs) + one padded plane for the transposition into the lane layout
+    const size_t prep_smem = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
+    CUDA_OK(smem_attr_once((const void*)k_prepare, (int)prep_smem));
+    k_prepare<<<L.n_plain, 256, prep_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
+    last_launches++;
+  }
+  CUDA_OK(cudaGetLastError());
 
   // ---- fused classes: every half-iteration, the hard decisions, the CRC and the early stop in one persistent launch;
   //      int16 classes run the native packed arithmetic under the range monitor first, then the exact-arithmetic kernel
@@ -866,7 +938,7 @@ int Engine::run(Plan& p)
   }
 
   // ---- per-half-iteration path: latency-shaped classes and the generic decoder
-  for (uint32_t it = 0; it < p.max_iter && !old_path.empty(); it++) {
+  for (uint32_t it = 0; it < p.max_iter && L.n_old > 0; it++) {
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots || cls_fused[c])
         continue;
@@ -921,16 +993,16 @@ int Engine::run(Plan& p)
       CUDA_OK(cudaGetLastError());
       last_launches++;
     }
-    DecideArgs da{d_lists.ptr + off_old, (int)old_path.size(), d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
-    k_decide_crc<<<((int)old_path.size() + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
+    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
+    k_decide_crc<<<(L.n_old + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
   }
 
   // ---- transport block assembly + CRC24A + HARQ bookkeeping
-  if (!p.tbs.empty()) {
-    TbArgs ta{d_tbs.ptr, (int)p.tbs.size(), d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr};
-    k_tb_finish<<<(int)p.tbs.size(), kTbThreads, 0, stream>>>(ta);
+  if (L.n_tbs > 0) {
+    TbArgs ta{d_tbs.ptr, L.n_tbs, d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr};
+    k_tb_finish<<<L.n_tbs, kTbThreads, 0, stream>>>(ta);
     CUDA_OK(cudaGetLastError());
     last_launches++;
   }
@@ -991,6 +1063,27 @@ int Engine::finish_timing()
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------- plan reuse
+// identity of a batch for the plan cache: every input the planner reads, byte for byte
+struct KeyBuilder {
+  std::vector<uint8_t> k;
+  template <class T>
+  void put(const T& v)
+  {
+    const uint8_t* p = reinterpret_cast<const uint8_t*>(&v);
+    k.insert(k.end(), p, p + sizeof(T));
+  }
+};
+static bool host_ptr_is_pinned(const void* p)
+{
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 // ------------------------------------------------------------------------------------------------- CB batch
 int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, uint8_t* out, uint32_t flags)
 {
@@ -1000,6 +1093,12 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   }
   if (!cfg || !llr || !out || (cfg->llr_bits != 16 && cfg->llr_bits != 8)) {
     set_error("invalid arguments");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  if (cfg->nof_cb == 0)
+    return 0; // an empty batch is done
+  if (cfg->nof_cb > (1u << 24) || cfg->llr_stride > (1u << 20)) {
+    set_error("batch too large");
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   }
   CUDA_OK(cudaSetDevice(device));
@@ -1025,25 +1124,41 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
     CUDA_OK(cudaMemcpyAsync(d_in.ptr, llr, bytes, cudaMemcpyHostToDevice, stream));
     d_llr = d_in.ptr;
   }
-  *plan_ptr  = Plan();
-  Plan& plan = *plan_ptr;
-  plan.max_iter = std::max(1u, cfg->nof_iterations);
-  plan.cbs.resize(cfg->nof_cb);
-  for (uint32_t i = 0; i < cfg->nof_cb; i++) {
-    CbDev& d = plan.cbs[i];
-    memset(&d, 0, sizeof(d));
-    fill_geometry(&d, cfg->K, sel);
-    d.max_iter = plan.max_iter;
-    d.crc_poly = 0;
-    d.in_ptr   = (void*)((const uint8_t*)d_llr + (size_t)i * cfg->llr_stride * esz);
-    d.in_bits  = (uint8_t)cfg->llr_bits;
+  KeyBuilder kb;
+  kb.put('C');
+  kb.put(*cfg);
+  kb.put(flags);
+  kb.put(d_llr);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps);
+  if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
+    // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
+    rc = launch_plan();
+  } else {
+    *plan_ptr  = Plan();
+    Plan& plan = *plan_ptr;
+    plan.max_iter = std::max(1u, cfg->nof_iterations);
+    plan.cbs.resize(cfg->nof_cb);
+    for (uint32_t i = 0; i < cfg->nof_cb; i++) {
+      CbDev& d = plan.cbs[i];
+      memset(&d, 0, sizeof(d));
+      fill_geometry(&d, cfg->K, sel);
+      d.max_iter = plan.max_iter;
+      d.crc_poly = 0;
+      d.in_ptr   = (void*)((const uint8_t*)d_llr + (size_t)i * cfg->llr_stride * esz);
+      d.in_bits  = (uint8_t)cfg->llr_bits;
+    }
+    rc = run(plan);
+    if (!rc)
+      cache_key = kb.k;
   }
-  rc = run(plan);
   if (rc)
     return rc;
   const size_t ob = (size_t)cfg->nof_cb * (cfg->K / 8);
   if (flags & SRSLTE_B200_OUT_DEVICE) {
     CUDA_OK(cudaMemcpyAsync(out, d_cbout.ptr, ob, cudaMemcpyDeviceToDevice, stream));
+    cb_out_host = nullptr;
+  } else if (host_ptr_is_pinned(out)) {
+    CUDA_OK(cudaMemcpyAsync(out, d_cbout.ptr, ob, cudaMemcpyDeviceToHost, stream)); // page-locked caller buffer: no staging copy
     cb_out_host = nullptr;
   } else {
     if (h_stage_out.reserve(ob + 64))
@@ -1079,18 +1194,52 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   }
   CUDA_OK(cudaSetDevice(device));
-  *plan_ptr  = Plan();
+  max_iterations = std::max(1u, max_iterations); // decode_tb_cb's loop is a do-while: one half-iteration always runs (sch.c:420-450)
+  // ---- plan reuse: one-shot transport blocks (no HARQ soft buffer, whose reset / CRC state changes from call to call) that
+  //      repeat the previous batch on this engine descriptor for descriptor
+  KeyBuilder kb;
+  bool       reusable = true;
+  kb.put('T');
+  kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps);
+  for (uint32_t t = 0; t < nof_tb; t++) {
+    const srslte_b200_tb_t& u = tbs[t];
+    if (u.softbuffer)
+      reusable = false;
+    kb.put(u.e_bits); kb.put(u.nof_e_bits); kb.put(u.tbs); kb.put(u.Qm); kb.put(u.rv); kb.put(u.data);
+  }
   Plan& plan = *plan_ptr;
+  tb_user   = tbs;
+  tb_user_n = nof_tb;
+  tb_flags  = flags;
+  if (reusable && ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
+    for (uint32_t t = 0; t < nof_tb; t++) {
+      srslte_b200_tb_t& u = tbs[t];
+      u.ret            = tb_map[t] < 0 ? tb_invalid_ret[t] : SRSLTE_B200_ERROR_INVALID_INPUTS;
+      u.avg_iterations = 0;
+      u.nof_cb         = tb_map[t] < 0 ? 0 : plan.tbs[tb_map[t]].C;
+      memset(u.cb_crc, 0, sizeof(u.cb_crc));
+      memset(u.cb_noi, 0, sizeof(u.cb_noi));
+    }
+    for (const auto& c : tb_h2d)
+      CUDA_OK(cudaMemcpyAsync(d_in.ptr + c.dst, c.src, c.bytes, cudaMemcpyHostToDevice, stream));
+    int rc = launch_plan();
+    if (rc)
+      return rc;
+    return finish_tb_submit(flags);
+  }
+  plan          = Plan();
   plan.max_iter = max_iterations;
-  tb_user       = tbs;
-  tb_user_n     = nof_tb;
-  tb_flags      = flags;
   tb_map.clear();
+  tb_h2d.clear();
+  tb_invalid_ret.assign(nof_tb, 0);
   const size_t esz = is8 ? 1 : 2;
 
   // pass 1: validate, segment, size the pools
   size_t in_bytes = 0, out_bytes = 0, scratch_cb = 0;
   std::vector<CbSegm> segs(nof_tb);
+  std::set<const void*> seen_sb;
+  std::vector<std::pair<Softbuffer*, uint32_t>> reset_done;
   for (uint32_t t = 0; t < nof_tb; t++) {
     srslte_b200_tb_t& u = tbs[t];
     u.ret = SRSLTE_B200_ERROR_INVALID_INPUTS;
@@ -1112,12 +1261,21 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     }
     if (s.F || s.C > SRSLTE_B200_MAX_CODEBLOCKS || (u.softbuffer && s.C > ((Softbuffer*)u.softbuffer)->max_cb))
       continue; // sch.c:519-530
+    if (u.softbuffer) {
+      // a soft buffer belongs to the engine that created it, and two transport blocks of one batch would race on it
+      if (((Softbuffer*)u.softbuffer)->eng != this || !seen_sb.insert(u.softbuffer).second) {
+        set_error("soft buffer of another context, or used by two transport blocks of one batch");
+        return SRSLTE_B200_ERROR_INVALID_INPUTS;
+      }
+    }
     tb_map[t] = 0;
     in_bytes += ((size_t)u.nof_e_bits * esz + 15) / 16 * 16;
     out_bytes += ((size_t)u.tbs / 8 + 6 + 15) / 16 * 16;
     if (!u.softbuffer)
       scratch_cb += s.C;
   }
+  for (uint32_t t = 0; t < nof_tb; t++)
+    tb_invalid_ret[t] = tbs[t].ret;
   if (!(flags & SRSLTE_B200_IN_DEVICE)) {
     if (d_in.reserve(in_bytes + 64))
       return SRSLTE_B200_ERROR;
@@ -1143,13 +1301,16 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     if (flags & SRSLTE_B200_IN_DEVICE) {
       e_dev = (const uint8_t*)u.e_bits;
     } else {
-      // host LLRs: adjacent transport blocks of one caller buffer are uploaded with a single copy
+      // host LLRs: transport blocks that sit in one caller buffer at the spacing they get on the device (packed, each block
+      // 16-byte aligned) are uploaded with a single copy
       const size_t nb = (size_t)u.nof_e_bits * esz;
-      if (cp_bytes && (const uint8_t*)u.e_bits == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
-        cp_bytes += nb;
+      if (cp_bytes && (const uint8_t*)u.e_bits == cp_src + (in_off - cp_dst)) {
+        cp_bytes = in_off - cp_dst + nb;
       } else {
-        if (cp_bytes)
+        if (cp_bytes) {
           CUDA_OK(cudaMemcpyAsync(d_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+          tb_h2d.push_back(H2dCopy{cp_src, cp_dst, cp_bytes});
+        }
         cp_src   = (const uint8_t*)u.e_bits;
         cp_dst   = in_off;
         cp_bytes = nb;
@@ -1213,7 +1374,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
       if (sb) {
         d.in_ptr = (void*)(sb->buf + (size_t)c * kSoftbufElems);
         d.fresh  = sb->zero_pending[c] ? 2 : 0; // 2: clear, combine AND keep (srslte_softbuffer_rx_reset* since the last use)
-        sb->zero_pending[c] = 0;
+        if (sb->zero_pending[c])
+          reset_done.emplace_back(sb, c); // (committed once the batch is enqueued: a failed submit must not lose the reset)
         d.skip   = sb->crc_host[c] ? 1 : 0; // sch.c:385
       } else {
         d.in_ptr = nullptr; // one-shot decode: the combined soft bits never leave the SM (k_dematch_prepare)
@@ -1225,18 +1387,32 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
     }
     plan.tbs.push_back(td);
   }
-  if (cp_bytes)
+  if (cp_bytes) {
     CUDA_OK(cudaMemcpyAsync(d_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
+    tb_h2d.push_back(H2dCopy{cp_src, cp_dst, cp_bytes});
+  }
+  tb_out_total = out_off;
   int rc = run(plan);
   if (rc)
     return rc;
+  for (auto& r : reset_done)
+    r.first->zero_pending[r.second] = 0;
+  if (reusable)
+    cache_key = kb.k;
+  return finish_tb_submit(flags);
+}
+
+// results of a transport-block batch back to the host (stream-ordered behind its kernels)
+int Engine::finish_tb_submit(uint32_t flags)
+{
+  Plan& plan = *plan_ptr;
   if (!plan.tbs.empty()) {
     if (h_res.reserve(plan.tbs.size()) || h_state.reserve(plan.cbs.size()))
       return SRSLTE_B200_ERROR;
     CUDA_OK(cudaMemcpyAsync(h_res.ptr, d_res.ptr, plan.tbs.size() * sizeof(TbResult), cudaMemcpyDeviceToHost, stream));
     CUDA_OK(cudaMemcpyAsync(h_state.ptr, d_state.ptr, plan.cbs.size() * sizeof(CbState), cudaMemcpyDeviceToHost, stream));
     if (!(flags & SRSLTE_B200_OUT_DEVICE))
-      CUDA_OK(cudaMemcpyAsync(h_stage_out.ptr, d_tbout.ptr, out_off, cudaMemcpyDeviceToHost, stream));
+      CUDA_OK(cudaMemcpyAsync(h_stage_out.ptr, d_tbout.ptr, tb_out_total, cudaMemcpyDeviceToHost, stream));
   }
   pending = PENDING_TB;
   return 0;
@@ -1338,6 +1514,7 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
     out_bytes += al16((size_t)c.nof_symbols * Qm * esz);
   }
   const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
+  CUDA_OK(cudaEventSynchronize(ev_desc)); // an earlier call's descriptor upload may still read the pinned buffer reserve() can free
   if ((!in_dev && d_dm_in.reserve(in_bytes + 64)) || (!out_dev && (d_dm_out.reserve(out_bytes + 64) || h_dm_out.reserve(out_bytes + 64))) ||
       d_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || h_dm_desc.reserve(nof_cw * sizeof(DemodDev)))
     return SRSLTE_B200_ERROR;
@@ -1470,6 +1647,7 @@ int Engine::ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, 
       uci_bytes += al16((size_t)(u.Q_prime_ack + u.Q_prime_ri + u.Q_prime_cqi) * u.Qm * 2);
     }
   }
+  CUDA_OK(cudaEventSynchronize(ev_desc)); // an earlier call's descriptor upload may still read the pinned buffer reserve() can free
   if ((!in_dev && d_ul_in.reserve(in_bytes + 64)) || (!out_dev && (d_ul_out.reserve(out_bytes + 64) || h_ul_out.reserve(out_bytes + 64))) ||
       (want_uci && (d_ul_uci.reserve(uci_bytes + 64) || h_ul_uci.reserve(uci_bytes + 64))) || d_ul_desc.reserve(nof_tb * sizeof(UlschDev)) ||
       h_ul_desc.reserve(nof_tb * sizeof(UlschDev)))
@@ -1681,6 +1859,7 @@ int Engine::encode_tbs(srslte_b200_enc_t* tbs, uint32_t nof_tb, uint32_t flags)
     CUDA_OK(cudaMemcpyAsync(d_enc_in.ptr + cp_dst, cp_src, cp_bytes, cudaMemcpyHostToDevice, stream));
   if (!htb.empty()) {
     const size_t tb_b = htb.size() * sizeof(EncTbDev), cb_b = hcb.size() * sizeof(EncCbDev), cb_at = al16(tb_b);
+    CUDA_OK(cudaEventSynchronize(ev_desc)); // (before reserve() can free the pinned buffer an earlier upload reads)
     if (d_enc_desc.reserve(cb_at + cb_b + 64) || h_enc_desc.reserve(cb_at + cb_b + 64))
       return SRSLTE_B200_ERROR;
     CUDA_OK(cudaEventSynchronize(ev_desc));

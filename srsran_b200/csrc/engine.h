@@ -42,6 +42,7 @@ struct DecSel {
 };
 
 struct Plan; // defined in engine.cu (needs the device descriptor types)
+struct LaunchState;
 
 class Engine
 {
@@ -68,7 +69,9 @@ public:
   // single code block sessions used by the srslte_tdec_* drop-in symbols (api.cu)
   int select_decoder(uint32_t K, uint32_t in_bits, uint32_t dec_type, bool force_not_sb, DecSel* s);
   void fill_geometry(CbDev* d, uint32_t K, const DecSel& s);
-  int run(Plan& p);
+  int run(Plan& p);        // build_plan + launch_plan
+  int build_plan(Plan& p);
+  int launch_plan();
   uint32_t map_seg_len() const; // trellis steps per beta segment of the MAP kernel variant in use
 
   int          device  = 0;
@@ -127,11 +130,21 @@ private:
   enum { PENDING_NONE = 0, PENDING_CB, PENDING_TB };
   int               pending = PENDING_NONE;
   Plan*             plan_ptr = nullptr;
+  LaunchState*      ls_ptr   = nullptr;
+  std::vector<uint8_t> cache_key; // identity of the batch *ls_ptr / *plan_ptr describe (empty: not reusable)
   uint8_t*          cb_out_host  = nullptr;
   size_t            cb_out_bytes = 0;
   srslte_b200_tb_t* tb_user   = nullptr;
   uint32_t          tb_user_n = 0;
   uint32_t          tb_flags  = 0;
+  struct H2dCopy {
+    const uint8_t* src;
+    size_t         dst, bytes;
+  };
+  std::vector<H2dCopy> tb_h2d;         // host-to-device copies of the batch's e-bits (replayed when the plan is reused)
+  std::vector<int32_t> tb_invalid_ret; // return codes of the transport blocks the planner rejected
+  size_t               tb_out_total = 0;
+  int                  finish_tb_submit(uint32_t flags);
   std::vector<int>    tb_map;
   std::vector<size_t> tb_out_off;
 };
