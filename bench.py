@@ -148,15 +148,27 @@ def dist_setup(n_gpus, backend=None):
     import torch.distributed as dist
     backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
     if backend == "nccl" and not os.environ.get("NCCL_DEBUG"):
-        # communicator set-up lines for whoever reads the log (rank / nranks / device), on stderr: stdout carries the JSON line
+        # communicator set-up lines (rank / nranks / device / transport) for whoever reads the log
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     if backend == "nccl":
         torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL logs to stdout, which carries the JSON line: the set-up (incl. the first collective, which creates the
+        # communicator) runs with stdout pointed at stderr
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            t_ = torch.zeros(1, device="cuda")
+            dist.all_reduce(t_)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         dev = "cuda"
     else:
         dist.init_process_group(backend)

@@ -209,6 +209,12 @@ SRSLTE_B200_API int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* n
 SRSLTE_B200_API uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx);
 SRSLTE_B200_API uint32_t srslte_b200_last_replayed(srslte_b200_ctx_t* ctx);
 
+/* test hook: one int16 LLR plane (in the decoder's lane layout, row = trellis step) of code block `cb` of the LAST completed
+ * batch of this context -- plane 2: the a-priori input of constituent decoder 1 (what turbodecoder_iter.h:107-109 leaves in
+ * app1 after its subtraction), plane 3: the input of decoder 2 (app2 of iter.h:117-121); 0 / 1 / 4: systematic / parity 0 /
+ * parity 1 as extracted.  The parity tests compare them with the oracle's arrays after every half-iteration. */
+SRSLTE_B200_API int srslte_b200_debug_read_plane(srslte_b200_ctx_t* ctx, uint32_t cb, uint32_t plane, int16_t* out, uint32_t n);
+
 /* host-side tables as the engine uploads them: QPP permutation (tc_interl_lte.c:69-109) in the index space of a
  * `lanes`-lane layout (lanes <= 1: natural order), and the rate de-matching table of one rv
  * (rm_turbo.c:177-251 [+ :263-277 when lanes > 0]): table[i] = buffer position of the i-th received e-bit */

@@ -57,10 +57,12 @@ typedef struct SRSLTE_API {
   uint64_t crchighbit;
   uint32_t srslte_crc_out;
 } srslte_crc_t; /* field layout kept: crc.h:36-44 */
+#ifndef SRSLTE_LTE_CRC24A
 #define SRSLTE_LTE_CRC24A 0x1864CFB /* phy_common.h:71-74 */
-#define SRSLTE_LTE_CRC24B 0x1800063
+#define SRSLTE_LTE_CRC24B 0X1800063
 #define SRSLTE_LTE_CRC16 0x11021
 #define SRSLTE_LTE_CRC8 0x19B
+#endif
 SRSLTE_API int      srslte_crc_init(srslte_crc_t* h, uint32_t srslte_crc_poly, int srslte_crc_order); /* crc.c:73 */
 SRSLTE_API int      srslte_crc_set_init(srslte_crc_t* h, uint64_t init_value);                        /* crc.c:61 */
 SRSLTE_API uint32_t srslte_crc_checksum_byte(srslte_crc_t* h, uint8_t* data, int len);                /* crc.c:143 */
@@ -97,6 +99,8 @@ typedef enum SRSLTE_API {
 /* ---------------------------------------------------------------- turbodecoder.h:63-121
  * The reference embeds this struct by value (sch.h:68, pssch.h:85) and no caller touches its fields; the fields
  * that describe host scratch memory are replaced by an opaque engine handle. */
+#define SRSLTE_TCOD_RATE 3        /* turbodecoder.h:41-47 */
+#define SRSLTE_TCOD_TOTALTAIL 12
 #define SRSLTE_TCOD_MAX_LEN_CB 6144
 #define SRSLTE_TDEC_EXPECT_INPUT_SB 1
 typedef struct SRSLTE_API {

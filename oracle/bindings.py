@@ -36,6 +36,8 @@ def build(ref=True):
     subprocess.check_call(["make", "-C", HERE, "liboracle.so"], stdout=subprocess.DEVNULL)
     if ref and os.path.isdir(os.environ.get("SRSLTE_REFERENCE", "/root/reference")):
         subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
+        if os.path.exists(os.path.join(os.path.dirname(HERE), "srsran_b200", "libsrslte_fec_b200.so")):
+            subprocess.check_call([os.path.join(HERE, "build_opt_a.sh")], stdout=subprocess.DEVNULL)
 
 
 def aligned_zeros(n, dtype, align=64):
@@ -525,3 +527,47 @@ class Ref:
                                 C.c_uint32(max_iter), C.c_int(int(llr.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg),
                                 C.c_uint32(repeat))
         return t, out, rc, avg
+
+
+OPT_A_SO = os.path.join(HERE, "_ref", "libsch_on_b200.so")
+
+
+class OptA:
+    """The reference's UNMODIFIED sch.c (decode_tb_cb's per-code-block loop) linked against the B200 library instead of the
+    reference's decoder, rate de-matcher, CRC, segmentation and soft buffer (oracle/build_opt_a.sh; INTEGRATION.md option A)."""
+
+    @staticmethod
+    def available():
+        return os.path.exists(OPT_A_SO)
+
+    def __init__(self, llr_is_8bit=False, max_iter=8):
+        L = self.L = C.CDLL(OPT_A_SO)
+        L.opta_new.restype = C.c_void_p
+        self.h = C.c_void_p(L.opta_new(C.c_int(int(llr_is_8bit)), C.c_uint32(max_iter)))
+        if not self.h:
+            raise RuntimeError("srslte_sch_init failed on the B200 library")
+
+    def close(self):
+        if self.h:
+            self.L.opta_del(self.h)
+            self.h = None
+
+    def reset_rx(self, tbs):
+        self.L.opta_reset_rx(self.h, C.c_uint32(tbs))
+
+    def encode(self, tbs, Qm, G, rv, data):
+        d = np.zeros(tbs // 8 + 16, np.uint8)  # (encode_tb appends the 3 CRC24A bytes to the caller's buffer, sch.c:216)
+        d[:tbs // 8] = data
+        e = np.zeros((G + 7) // 8 + 64, np.uint8)
+        rc = self.L.opta_encode(self.h, C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(G), C.c_uint32(rv), _p(d), _p(e))
+        assert rc == 0
+        return np.unpackbits(e)[:G]
+
+    def decode(self, tbs, Qm, rv, llr):
+        out = np.zeros(tbs // 8 + 8 + 768, np.uint8)
+        avg = C.c_float(0)
+        crc = np.zeros(32, np.uint8)
+        llr = np.ascontiguousarray(llr)
+        rc = self.L.opta_decode(self.h, C.c_uint32(tbs), C.c_uint32(Qm), C.c_uint32(len(llr)), C.c_uint32(rv), _p(llr), _p(out), C.byref(avg), _p(crc),
+                                C.c_uint32(32))
+        return rc, out, avg.value, crc

@@ -358,6 +358,16 @@ class Context:
         if rc:
             _err("srslte_b200_set_option(%s)" % name, rc)
 
+    def debug_read_plane(self, cb, plane, n):
+        """int16 LLR plane of a code block of the last completed batch (test hook, see batch.h)"""
+        out = np.zeros(n, np.int16)
+        f = lib().srslte_b200_debug_read_plane
+        f.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]
+        rc = f(self.h, cb, plane, _ptr(out), n)
+        if rc:
+            _err("srslte_b200_debug_read_plane", rc)
+        return out
+
     def last_replayed(self):
         return lib().srslte_b200_last_replayed(self.h)
 

@@ -1013,6 +1013,20 @@ int Engine::launch_plan()
 
 uint32_t Engine::map_seg_len() const { return 8; }
 
+// test hook: one LLR plane of a code block of the last completed batch (the engine's workspace keeps it until the next batch)
+int Engine::debug_read_plane(uint32_t cb, uint32_t plane, int16_t* out, uint32_t n)
+{
+  const Plan& p = *plan_ptr;
+  if (pending != PENDING_NONE || cb >= p.cbs.size() || plane > 4 || n > p.cbs[cb].ps) {
+    set_error("debug_read_plane: no such block / plane, or a batch is still outstanding");
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  }
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  CUDA_OK(cudaMemcpy(out, d_ws.ptr + p.cbs[cb].ws_off + (size_t)plane * p.cbs[cb].ps, (size_t)n * sizeof(int16_t), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int Engine::timer_start()
 {
   CUDA_OK(cudaSetDevice(device));
@@ -2183,6 +2197,13 @@ int srslte_b200_timer_start(srslte_b200_ctx_t* ctx)
   return ctx->e->timer_start();
 }
 float srslte_b200_timer_stop_ms(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->timer_stop_ms() : -1.f; }
+
+int srslte_b200_debug_read_plane(srslte_b200_ctx_t* ctx, uint32_t cb, uint32_t plane, int16_t* out, uint32_t n)
+{
+  if (!ctx || !out)
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  return ctx->e->debug_read_plane(cb, plane, out, n);
+}
 
 int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
 {

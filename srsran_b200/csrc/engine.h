@@ -72,6 +72,7 @@ public:
   int run(Plan& p);        // build_plan + launch_plan
   int build_plan(Plan& p);
   int launch_plan();
+  int      debug_read_plane(uint32_t cb, uint32_t plane, int16_t* out, uint32_t n);
   uint32_t map_seg_len() const; // trellis steps per beta segment of the MAP kernel variant in use
 
   int          device  = 0;

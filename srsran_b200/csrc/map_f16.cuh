@@ -88,6 +88,11 @@ __device__ __forceinline__ void stg128_hint(void* p, uint4 v, uint64_t pol)
   asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;\n" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
 }
 
+__device__ __forceinline__ void stg16_hint(void* p, uint16_t v, uint64_t pol)
+{
+  asm volatile("st.global.L2::cache_hint.b16 [%0], %1, %2;\n" ::"l"(p), "h"(v), "l"(pol) : "memory");
+}
+
 template <int T, int STAGES, int PLANES>
 struct F16Lay {
   static constexpr int kRows       = 8;                                  // trellis steps per tile

@@ -22,6 +22,8 @@
 // A block the monitor flags is PARKED (its inputs of that half-iteration are intact): the same kernel compiled with the
 // exact saturating policy (Sat16) takes the parked groups in a second launch and finishes them.
 #pragma once
+#include <type_traits>
+
 #include "map_f16.cuh"
 
 namespace b200 {
@@ -167,9 +169,13 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   const int s1 = 5, s2 = s1 + nT, s3 = s2 + nAW, n_seq = s3 + nT;
   auto bar_of = [&](int stage) -> unsigned { return w.sm_s + 4u * (unsigned)(Lay::kBarOff + 2 * stage); };
   int  wr_idx = 0;
-  auto issue = [&]() {
+  // kAux = false_type: the caller knows that the tile requested now is not an alpha-main tile (both beta passes: the
+  // request runs two tiles ahead of the consumer, so they only ever request beta and alpha warm-up tiles) -- no table rows,
+  // no checkpoint, a third of the code
+  auto issue = [&](auto kAux) {
+    constexpr bool aux_possible = decltype(kAux)::value;
     __syncwarp(); // every lane is done with the stage (and the checkpoint slot) about to be refilled
-    if (lane == 0 && wr_idx > s3 && wr_idx <= n_seq) {
+    if (aux_possible && lane == 0 && wr_idx > s3 && wr_idx <= n_seq) {
       // checkpoint beta[8(t+1)] of the alpha tile whose planes the PREVIOUS call requested: same mbarrier, ring slot t & 1
       const int t     = wr_idx - 1 - s3;
       const int stage = w.wr_stage == 0 ? kStages - 1 : w.wr_stage - 1;
@@ -185,7 +191,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
           t = 4 - wr_idx;
         else if (wr_idx < s2)
           t = nT - 1 - (wr_idx - s1);
-        else if (wr_idx < s3)
+        else if (!aux_possible || wr_idx < s3)
           t = a0 + (wr_idx - s2);
         else {
           t   = wr_idx - s3;
@@ -194,23 +200,25 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         // (the tables are padded to whole tiles: a partial top tile copies rows nobody reads)
         mbar_expect_tx(bar, aux ? kBoxBytes + lut_bytes + 1024u : kBoxBytes);
         tma_tile4_hint(dst, tmap, 0, blk0, 8 * t, plane0, bar, w.pol_first);
-        if (aux)
+        if (aux_possible && aux)
           bulk_g2s(dst + 4u * (unsigned)kLutOff, lut + (size_t)t * lut_stride, lut_bytes, bar);
       }
       wr_idx++;
       w.wr_stage = w.wr_stage + 1 == kStages ? 0 : w.wr_stage + 1;
-    } else if (wr_idx == n_seq) {
+    } else if (aux_possible && wr_idx == n_seq) {
       wr_idx++; // (the last checkpoint has just been requested)
     }
   };
-  auto acquire = [&]() -> const u32* {
-    issue();
+  auto acquire = [&](auto kAux) -> const u32* {
+    issue(kAux);
     mbar_wait(bar_of(w.rd_stage), (w.rd_phase >> w.rd_stage) & 1u);
     w.rd_phase ^= 1u << w.rd_stage;
     const u32* tb = my + w.rd_stage * Lay::kStageWords;
     w.rd_stage    = w.rd_stage + 1 == kStages ? 0 : w.rd_stage + 1;
     return tb;
   };
+  constexpr std::false_type kBeta{};  // requests made while a beta pass consumes
+  constexpr std::true_type  kAlpha{}; // requests made while an alpha pass consumes
   // x (input + a-priori) and y (parity) of box row i
   auto row = [&](const u32* tb, int i, u32& x, u32& y) {
     y = tb[Lay::kPlaneWords + i * 32];
@@ -219,7 +227,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
 
 #pragma unroll
   for (int i = 0; i < kStages - 1; i++)
-    issue();
+    issue(kBeta);
 
   RangeMon mon_b, mon_a, mon_h;
   mon_b.reset();
@@ -261,7 +269,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       ck_store(nT, st);
       t = nT - 1;
       if (W & 7) { // partial top tile: guarded, rolled
-        const u32* tb = acquire();
+        const u32* tb = acquire(kBeta);
 #pragma unroll 1
         for (int i = (W & 7) - 1; i >= 0; i--) {
           u32 x, y;
@@ -280,7 +288,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     const bool main_pass = pass == 1;
 #pragma unroll 1
     for (; t >= 0; t--) {
-      const u32* tb = acquire();
+      const u32* tb = acquire(kBeta);
 #pragma unroll
       for (int i = 7; i >= 0; i--) {
         u32 x, y;
@@ -319,7 +327,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     int kk = 0; // loop counter of the pass
 #pragma unroll 1
     for (int t = a0; t < nT; t++) {
-      const u32* tb = acquire();
+      const u32* tb = acquire(kAlpha);
       const int  i0 = t == a0 ? (W - kWinOverlap) - 8 * a0 : 0;
       const int  i1 = (8 * t + 8) <= W ? 8 : W - 8 * t;
 #pragma unroll 1
@@ -435,8 +443,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
       atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
     }
-    *reinterpret_cast<int16_t*>(ext + 2u * t0) = (int16_t)lo16(e);
-    *reinterpret_cast<int16_t*>(ext + 2u * t1) = (int16_t)hi16(e);
+    // (streamed: the extrinsic plane is read again a whole half-iteration later, by which time 85 MB of them are in flight;
+    //  the checkpoints, which come back within the same half-iteration, get the L2 instead)
+    stg16_hint(ext + 2u * t0, (uint16_t)(e & 0xffffu), w.pol_first);
+    stg16_hint(ext + 2u * t1, (uint16_t)(e >> 16), w.pol_first);
   };
   auto ck_load = [&](int t, u32 (&v)[8]) { // checkpoint of alpha tile t: [half][lane][4 words]
     const uint4* c = reinterpret_cast<const uint4*>(w.sm + Lay::kCkRing + (t & 1) * 256) + lane;
@@ -450,10 +460,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
 #pragma unroll 1
   for (int t = 0; t < n_full; t++) {
     asm volatile("" : "+r"(flags));
-    d2    = flags & 1;
-    bits1 = flags & 2;
-    bits2 = flags & 4;
-    const u32* tb = acquire();
+    d2    = DEC < 0 ? (flags & 1) != 0 : DEC == 1;
+    bits1 = DEC != 1 && (flags & 2);
+    bits2 = DEC != 0 && (flags & 4);
+    const u32* tb = acquire(kAlpha);
     u32        bs[4][8];
     // ---- recompute beta_{8t+7} .. beta_{8t+1} from the checkpoint beta_{8t+8}: the upper three go to shared memory, the
     //      lower four stay in registers
@@ -508,10 +518,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     // partial top tile, guarded: beta_{p+1} of each step is recomputed from the checkpoint beta[W] (at most 6 steps)
     const int  t  = n_full;
     const int  nv = W & 7;
-    const u32* tb = acquire();
-    d2    = flags & 1;
-    bits1 = flags & 2;
-    bits2 = flags & 4;
+    const u32* tb = acquire(kAlpha);
+    d2    = DEC < 0 ? (flags & 1) != 0 : DEC == 1;
+    bits1 = DEC != 1 && (flags & 2);
+    bits2 = DEC != 0 && (flags & 4);
 #pragma unroll 1
     for (int i = 0; i < nv; i++) {
       u32 b[8];
@@ -592,10 +602,12 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
 
   const int n_groups = a.mode == 2 ? (int)a.counters[2] : a.n_groups;
   for (;;) {
+    // (warp-wide reductions instead of shuffles wherever a value is the same for every lane: their results live in the
+    //  uniform datapath, so the tile bookkeeping and the operands of the bulk copies need no per-lane code)
     int gi = 0;
     if (lane == 0)
       gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
-    gi = __shfl_sync(0xffffffffu, gi, 0);
+    gi = (int)__reduce_add_sync(0xffffffffu, (unsigned)gi);
     if (gi >= n_groups)
       break;
     const int grp  = a.mode == 2 ? a.parked[gi] : gi;
@@ -627,10 +639,11 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
     const unsigned live_mask = __ballot_sync(0xffffffffu, live);
     if (live_mask == 0)
       continue;
-    const int leader = __ffs(live_mask) - 1;
-    const int W      = __shfl_sync(0xffffffffu, (int)d_W, leader);
-    const int K      = __shfl_sync(0xffffffffu, (int)d_K, leader);
-    const int qoff   = __shfl_sync(0xffffffffu, (int)d_qpp, leader);
+    // geometry of the group: the first slot of a group is never padding and every block of a group has the same size
+    const CbDev* d0   = a.cbs + a.work[grp * G];
+    const int    W    = d0->W;
+    const int    K    = (int)d0->K;
+    const int    qoff = (int)d0->qpp_off;
     if (live && (int)d_W != W)
       __trap(); // host planning never mixes sizes in a group
     int16_t*        ws = a.ws + d_ws;
@@ -653,7 +666,7 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
     const unsigned pmask = __ballot_sync(0xffffffffu, pending);
     if (pmask == 0)
       break;
-    int niter = __shfl_sync(0xffffffffu, (int)n_iter0, __ffs(pmask) - 1);
+    int niter = (int)__reduce_min_sync(0xffffffffu, pending ? n_iter0 : 0xffffffffu);
     live      = pending && (int)n_iter0 == niter;
     pending   = pending && !live;
     const int niter_first = niter;

@@ -120,3 +120,29 @@ def test_c_host_example_runs(tmp_path):
     p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert p.returncode == 0, p.stdout + p.stderr
     assert "batched decode_tb: ok" in p.stdout and "decode_tb_cb loop with srslte_* symbols: ok" in p.stdout
+
+
+def test_reference_call_sites_compile_against_fec_h():
+    """The reference's UNMODIFIED sch.c and pssch.c (every caller of the replaced symbols) type-check against
+    include/srslte_b200/fec.h: tests/shim_include replaces srslte/phy/fec/{crc,turbodecoder,softbuffer,cbsegm}.h, everything
+    else comes from the reference's own include tree.  Implicit declarations, incompatible pointers and int conversions are
+    errors, so a missing symbol or a changed signature fails here."""
+    ref = os.environ.get("SRSLTE_REFERENCE", "/root/reference")
+    if not os.path.isdir(os.path.join(ref, "lib", "src", "phy", "phch")):
+        pytest.skip("reference tree not present")
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    with tempfile.TemporaryDirectory() as tmp:
+        os.makedirs(os.path.join(tmp, "srslte"))
+        src = open(os.path.join(ref, "lib", "include", "srslte", "version.h.in")).read()
+        for k, v in (("MAJOR", "20"), ("MINOR", "10"), ("PATCH", "1"), ("STRING", "20.10.1")):
+            src = src.replace("@SRSLTE_VERSION_%s@" % k, v)
+        open(os.path.join(tmp, "srslte", "version.h"), "w").write(src)
+        for f in ("sch.c", "pssch.c"):
+            cmd = ["gcc", "-std=gnu99", "-fsyntax-only", "-w", "-Werror=implicit-function-declaration", "-Werror=incompatible-pointer-types",
+                   "-Werror=int-conversion", "-mavx2", "-mfma", "-DLV_HAVE_SSE", "-DLV_HAVE_AVX", "-DLV_HAVE_AVX2",
+                   "-I" + os.path.join(root, "tests", "shim_include"), "-I" + os.path.join(root, "include"), "-I" + tmp,
+                   "-I" + os.path.join(ref, "lib", "include"), os.path.join(ref, "lib", "src", "phy", "phch", f)]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            assert r.returncode == 0, r.stderr[-2000:]

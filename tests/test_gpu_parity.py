@@ -972,3 +972,107 @@ def test_fused_kernel_transport_blocks_at_scale(port):
     finally:
         for j in jobs:
             j[0].close()
+
+
+# ----------------------------------------------------------------------------------------- intermediate LLRs, not only decided bytes
+def _expected_planes(port, h, K, N, n_done, bits):
+    """what the engine's a-priori (plane 2) / decoder-2 input (plane 3) planes must hold after n_done half-iterations, from the
+    oracle's arrays: the glue subtractions of turbodecoder_iter.h:107-109 / 117-119 are fused into the kernels' epilogues"""
+    app1 = port.tdec_get_llr(h, 0, K).astype(np.int64)
+    ext1 = port.tdec_get_llr(h, 2, K).astype(np.int64)
+    fwd, rev = b.qpp_table(K, N)
+
+    def sub(a, c):
+        d = a - c
+        if bits == 16:
+            return ((d + 32768) % 65536 - 32768).astype(np.int16)  # srslte_vec_sub_sss wraps
+        sat = np.clip(d, -128, 127)
+        wrap = (d + 128) % 256 - 128
+        idx = np.arange(K)
+        return np.where(idx < (K // 32) * 32, sat, wrap).astype(np.int16)  # srslte_vec_sub_bbb, AVX2 build (SURVEY 8a-3)
+    if n_done % 2 == 1:
+        e = sub(ext1, app1) if n_done > 1 else ext1.astype(np.int16)  # iter.h:117-119, then app2[rev[i]] = ext1[i]
+        want = np.zeros(K, np.int16)
+        want[rev] = e
+        return 3, want
+    return 2, sub(app1, ext1)  # iter.h:107-109 (the subtraction the next DEC1 would perform)
+
+
+@pytest.mark.parametrize("K,dtype,ncb,amp", [(6144, np.int16, 700, 100), (6144, np.int16, 9, 100), (5824, np.int16, 640, 150), (1008, np.int16, 1300, 120),
+                                              (512, np.int16, 1400, 100), (6144, np.int8, 400, 25), (2048, np.int8, 900, 30)])
+def test_intermediate_llrs_match_the_oracle(port, ctx, K, dtype, ncb, amp):
+    """LLR-for-LLR: after n = 1..5 half-iterations the extrinsic planes in the engine's workspace equal what the oracle's
+    arrays say, for blocks at the start, the middle and the end of large batches (k_map_fused) and of a small one (k_map_lat)"""
+    rng = np.random.default_rng(K + ncb)
+    bits = 16 if dtype == np.int16 else 8
+    N = lanes16(K) if bits == 16 else lanes8(K)
+    base = [std_to_sb(bpsk_awgn_llr(rng, port.tcod_encode(rng.integers(0, 2, K, dtype=np.uint8)), amp, 0.8 + 0.1 * i, dtype), K, N) for i in range(3)]
+    batch = np.ascontiguousarray(np.stack([base[i % 3] for i in range(ncb)]))
+    probe = sorted({0, 1, 2, ncb // 2, ncb - 3, ncb - 2, ncb - 1})
+    for n in (1, 2, 3, 4, 5):
+        ctx.tdec_batch(batch, K, n, input_sb=True)
+        hs = []
+        for i in range(3):
+            h = port.tdec_new(TDEC_AUTO, False)
+            port.tdec_run_all(h, base[i], n, K)
+            hs.append(h)
+        for cb in probe:
+            plane, want = _expected_planes(port, hs[cb % 3], K, N, n, bits)
+            got = ctx.debug_read_plane(cb, plane, K)
+            assert (got == want).all(), "K=%d bits=%d n=%d block %d: %d LLRs differ" % (K, bits, n, cb, int((got != want).sum()))
+        for h in hs:
+            port.tdec_del(h)
+
+
+def test_int8_full_scale_every_windowed_size(port, ctx):
+    """int8 LLRs over the whole +-127 range on EVERY size the int8 decoders take in lane layout (K >= 408: widened 8-lane,
+    16-lane and 32-lane decoders), 4 half-iterations, decided bytes after the run; batches large enough for k_map_fused on the
+    16- and 32-lane classes every few sizes, small ones (k_map_lat) in between"""
+    rng = np.random.default_rng(8127)
+    for n, K in enumerate(k for k in all_K() if k >= 408):
+        N = lanes8(K)
+        ncb = 1300 if n % 6 == 0 else 5
+        base = [random_llr(rng, 3 * (K + 32) + 12, 127, np.int8) for _ in range(2)]
+        batch = np.ascontiguousarray(np.stack([base[i % 2] for i in range(ncb)]))
+        got = ctx.tdec_batch(batch, K, 4, input_sb=True)
+        hp = port.tdec_new(TDEC_AUTO, False)
+        want = [port.tdec_run_all(hp, base[i], 4, K)[1] for i in range(2)]
+        port.tdec_del(hp)
+        for i in range(ncb):
+            assert (got[i] == want[i % 2]).all(), (K, N, i)
+
+
+# ----------------------------------------------------------------------------------------- INTEGRATION.md option A, for real
+def test_unmodified_sch_c_on_the_b200_library(port):
+    """The reference's UNMODIFIED lib/src/phy/phch/sch.c -- srslte_dlsch_decode2 -> decode_tb -> decode_tb_cb with its per-code-
+    block loop over srslte_rm_turbo_rx_lut[_8bit], srslte_tdec_new_cb / srslte_tdec_iteration[_8bit] and
+    srslte_crc_checksum_byte, its softbuffer->buffer_f[] / data[] accesses and its HARQ bookkeeping -- compiled against
+    include/srslte_b200/fec.h and linked against libsrslte_fec_b200.so in place of the reference's FEC objects
+    (oracle/build_opt_a.sh).  Return codes, bytes, CRC flags and average iteration counts equal the oracle's, incl. a HARQ
+    retransmission that combines in the HOST soft buffer the reference's loop keeps."""
+    from oracle.bindings import OptA
+    if not OptA.available():
+        pytest.skip("oracle/_ref/libsch_on_b200.so not built (oracle/build_opt_a.sh needs /root/reference)")
+    rng = np.random.default_rng(31337)
+    for tbs, Qm, G, is8, amp, sigma, rvs in ((15264, 4, 20000, False, 200, 0.55, (0,)), (15264, 4, 20000, False, 200, 0.78, (0, 2, 3)),
+                                              (6120, 2, 14400, True, 30, 0.8, (0,)), (75376, 6, 90000, False, 100, 0.46, (0,))):
+        s = OptA(is8, 8)
+        sb = port.softbuffer_new()
+        s.reset_rx(tbs)
+        data = rng.integers(0, 256, tbs // 8, dtype=np.uint8)
+        for rv in rvs:
+            s.encode(tbs, Qm, G, 0, data)
+            e = s.encode(tbs, Qm, G, rv, data)  # the reference's CPU encoder (CRC attach through the library's symbols)
+            assert (e == port.encode_tb(tbs, Qm, rv, G, data)).all()
+            llr = bpsk_awgn_llr(rng, e, amp, sigma, np.int8 if is8 else np.int16)
+            rc, d, avg, crc = s.decode(tbs, Qm, rv, llr)
+            rc_p, d_p, nit_p, avg_p, crc_p = port.decode_tb(sb, tbs, Qm, rv, llr, 8)
+            C_ = port.cbsegm(tbs)[1]["C"]
+            assert rc == rc_p, (tbs, rv, rc, rc_p)
+            assert (d[:tbs // 8 + 3] == d_p[:tbs // 8 + 3]).all() and abs(avg - avg_p) < 1e-6, (tbs, rv)
+            assert crc[:C_].tolist() == crc_p[:C_].tolist()
+            if rc == 0:
+                assert (d[:tbs // 8] == data).all()
+                break
+        s.close()
+        port.softbuffer_del(sb)

@@ -117,6 +117,14 @@ def test_decoder_llr_exact(port, ref, case):
     _tdec(port, ref, K, np.int16 if bits == 16 else np.int8, amp, nit)
 
 
+@pytest.mark.parametrize("bits,amp", [(16, 700), (16, 32767), (8, 40), (8, 127)])
+def test_decoder_llr_exact_all_sizes(port, ref, bits, amp):
+    """the oracle's decoders pinned LLR-for-LLR against the reference on EVERY one of the 188 LTE sizes (AUTO dispatch:
+    generic, 8-, 16- and 32-lane windowed decoders), moderate and full-scale amplitudes, 3 half-iterations each"""
+    for K in all_K():
+        _tdec(port, ref, K, np.int16 if bits == 16 else np.int8, amp, 3)
+
+
 @pytest.mark.parametrize("K,dec,fnsb", [(6144, TDEC_AVX_WINDOW, True), (504, TDEC_SSE_WINDOW, True), (504, TDEC_GENERIC, True), (6144, TDEC_GENERIC, False),
                                         (1024, TDEC_SSE_WINDOW, False), (6144, TDEC_AVX8_WINDOW, True), (1024, TDEC_SSE8_WINDOW, True), (504, TDEC_AUTO, True),
                                         (6144, TDEC_AUTO, True), (40, TDEC_AUTO, True)])
