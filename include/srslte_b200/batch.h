@@ -121,6 +121,10 @@ typedef struct {
   uint32_t       mod;
   const uint8_t* scramble_bytes;
   void*          e_bits;
+  const float*   csi; /* channel state information per symbol (q->csi[cw] of pdsch.c) or NULL: when given, csi_correction
+                       * (lib/src/phy/phch/pdsch.c:628-741, what cfg->csi_enable turns on) runs between the demodulator and the
+                       * descrambler, with the integer results of the reference's x86 build; a host pointer unless
+                       * SRSLTE_B200_IN_DEVICE */
 } srslte_b200_demod_t;
 
 SRSLTE_B200_API int srslte_b200_demod_descramble(srslte_b200_ctx_t* ctx, const srslte_b200_demod_t* cws, uint32_t nof_cw, int llr_is_8bit, uint32_t flags);

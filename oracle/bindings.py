@@ -215,6 +215,13 @@ class Port:
         assert f(C.c_int(mod), _p(sym), _p(out), C.c_int(n)) == 0
         return out
 
+    def csi_correction(self, csi, e, mod):
+        """csi_correction (pdsch.c:628-741) on a copy of e (int16 / int8 soft bits of one codeword)"""
+        out = np.ascontiguousarray(e).copy()
+        c = np.ascontiguousarray(csi, np.float32)
+        self.L.orc_csi_correction(_p(c), _p(out), C.c_uint32(len(out)), C.c_int(mod), C.c_int(int(out.dtype == np.int8)))
+        return out
+
     def sequence_bytes(self, c_init, length):
         out = np.zeros((length + 7) // 8, np.uint8)
         self.L.orc_sequence_bytes(C.c_uint32(c_init), C.c_uint32(length), _p(out))
@@ -463,6 +470,16 @@ class Ref:
         f = self.L.ref_demod_s if dtype == np.int16 else self.L.ref_demod_b
         assert f(C.c_int(mod), _p(sym), _p(out), C.c_int(n)) == 0
         return out[:n * MOD_BITS[mod]].copy()
+
+    def csi_correction(self, csi, e, mod):
+        """the reference's static csi_correction (pdsch.c:628-741) through oracle/ref_csi_shim.c, on a copy of e"""
+        L = C.CDLL(os.path.join(HERE, "_ref", "libsrslte_ref_csi.so"))
+        out = aligned_zeros(len(e) + 64, e.dtype)
+        out[:len(e)] = e
+        c = aligned_zeros(len(csi) + 16, np.float32)
+        c[:len(csi)] = csi
+        L.ref_csi_correction(_p(c), _p(out), C.c_uint32(len(e)), C.c_int(mod), C.c_int(int(e.dtype == np.int8)))
+        return out[:len(e)].copy()
 
     def sequence_bytes(self, c_init, length):
         out = np.zeros((length + 7) // 8 + 16, np.uint8)

@@ -54,6 +54,14 @@ gcc $CFLAGS -c "$HERE/ref_shim.c" -o "$OUT/obj/ref_shim.o"
 g++ -shared -o "$OUT/libsrslte_ref.so" $OBJS "$OUT/obj/ref_shim.o" -lm -lpthread
 echo "built $OUT/libsrslte_ref.so"
 
+# csi_correction is static in pdsch.c: a shim that includes the source file, everything else garbage-collected at link time
+echo '{ global: ref_csi_correction; local: *; };' > "$OUT/obj/csi.map"
+gcc $CFLAGS -ffunction-sections -fdata-sections -DREF_PDSCH_C="\"$R/src/phy/phch/pdsch.c\"" -c "$HERE/ref_csi_shim.c" -o "$OUT/obj/ref_csi_shim.o"
+gcc -shared -o "$OUT/libsrslte_ref_csi.so" "$OUT/obj/ref_csi_shim.o" "$OUT/obj/src_phy_utils_vector.o" "$OUT/obj/src_phy_utils_vector_simd.o" \
+  "$OUT/obj/src_phy_utils_bit.o" "$OUT/obj/src_phy_utils_debug.o" "$OUT/obj/src_phy_utils_phy_logger.o" \
+  -Wl,--gc-sections -Wl,--version-script="$OUT/obj/csi.map" -Wl,--no-undefined -lm
+echo "built $OUT/libsrslte_ref_csi.so"
+
 # Second build for bench.py's CPU baseline only: the reference's RELEASE optimisation flags (CMakeLists.txt:394-417:
 # -Ofast -funroll-loops -mfpmath=sse on top of the ISA flags; -march=native is left out because the library is built here and
 # runs on the GPU box's host CPU).  The parity tests keep using the -O3 build above.

@@ -1275,3 +1275,88 @@ int orc_ulsch_deinterleave(int16_t* q_bits, uint32_t Qm, uint32_t H_prime_total,
   free(ri_present);
   return 0;
 }
+
+/* ================================================================== csi_correction (lib/src/phy/phch/pdsch.c:628-741)
+ * Scales the soft bits of a codeword by the channel state information of their resource element, between the soft
+ * demodulator and the descrambler (pdsch.c:843-846, only when cfg->csi_enable).  Restated with the reference's quirks:
+ *  - int16, SSE bodies: e = (e * c16) >> 16 with c16 = sat16(rne(csi * (32767 / csi_max))) -- _mm_cvtps_pi16 + _mm_mulhi_pi16,
+ *    i.e. HALF the scale of the scalar tail;
+ *  - QPSK body (groups of 4 soft bits = two symbols, :676-686): _mm_blend_ps(csi1, csi2, 3) takes elements 0,1 from csi2, so
+ *    the two symbols of a pair use EACH OTHER's csi;
+ *  - 64QAM body (groups of 12 = two symbols, :697-711): soft bits 4,5 of the first symbol use the second symbol's csi and soft
+ *    bits 0,1 of the second symbol the first one's;
+ *  - scalar tails and the whole int8 path: e = (T)((float)e * (csi / csi_max)), truncation;
+ *  - BPSK has no SSE body.
+ * mod: srslte_mod_t 0..4; nof_bits = symbols * Qm. */
+static int16_t orc_csi_c16(float csi, float scale)
+{
+  int32_t v = orc_cvt_rne(csi * scale); /* cvtps2pi: round to nearest even */
+  return (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v)); /* packssdw */
+}
+void orc_csi_correction(const float* csi, void* e, uint32_t nof_bits, int mod, int is8)
+{
+  const uint32_t qm = mod == 0 ? 1 : 2 * (uint32_t)mod, nsym = nof_bits / qm;
+  /* srslte_vec_max_fi: index of the maximum (the value is what matters) */
+  float csi_max = 1.0f;
+  if (nsym > 0) {
+    csi_max = csi[0];
+    for (uint32_t i = 1; i < nsym; i++)
+      if (csi[i] > csi_max)
+        csi_max = csi[i];
+  }
+  if (is8) {
+    int8_t* eb = e;
+    for (uint32_t i = 0; i < nsym; i++) {
+      const float c = csi[i] / csi_max;
+      for (uint32_t k = 0; k < qm; k++)
+        eb[qm * i + k] = (int8_t)(int32_t)((float)eb[qm * i + k] * c);
+    }
+    return;
+  }
+  int16_t*    es    = e;
+  const float scale = (float)32767 / csi_max;
+  uint32_t    i     = 0; /* soft-bit index while in the SSE bodies */
+#define ORC_MULHI(x, c) ((int16_t)(((int32_t)(x) * (int32_t)(c)) >> 16))
+  switch (mod) {
+    case 1:
+      for (; i + 3 < nof_bits; i += 4) {
+        const int16_t c0 = orc_csi_c16(csi[i / 2], scale), c1 = orc_csi_c16(csi[i / 2 + 1], scale);
+        es[i] = ORC_MULHI(es[i], c1); es[i + 1] = ORC_MULHI(es[i + 1], c1);
+        es[i + 2] = ORC_MULHI(es[i + 2], c0); es[i + 3] = ORC_MULHI(es[i + 3], c0);
+      }
+      break;
+    case 2:
+      for (; i + 3 < nof_bits; i += 4) {
+        const int16_t c = orc_csi_c16(csi[i / 4], scale);
+        for (int k = 0; k < 4; k++)
+          es[i + k] = ORC_MULHI(es[i + k], c);
+      }
+      break;
+    case 3:
+      for (; i + 11 < nof_bits; i += 12) {
+        const int16_t c0 = orc_csi_c16(csi[i / 6], scale), c1 = orc_csi_c16(csi[i / 6 + 1], scale);
+        for (int k = 0; k < 4; k++)
+          es[i + k] = ORC_MULHI(es[i + k], c0);
+        es[i + 4] = ORC_MULHI(es[i + 4], c1); es[i + 5] = ORC_MULHI(es[i + 5], c1);
+        es[i + 6] = ORC_MULHI(es[i + 6], c0); es[i + 7] = ORC_MULHI(es[i + 7], c0);
+        for (int k = 8; k < 12; k++)
+          es[i + k] = ORC_MULHI(es[i + k], c1);
+      }
+      break;
+    case 4:
+      for (; i + 7 < nof_bits; i += 8) {
+        const int16_t c = orc_csi_c16(csi[i / 8], scale);
+        for (int k = 0; k < 8; k++)
+          es[i + k] = ORC_MULHI(es[i + k], c);
+      }
+      break;
+    default:
+      break;
+  }
+#undef ORC_MULHI
+  for (uint32_t s = i / qm; s < nsym; s++) {
+    const float c = csi[s] / csi_max;
+    for (uint32_t k = 0; k < qm; k++)
+      es[qm * s + k] = (int16_t)(int32_t)((float)es[qm * s + k] * c);
+  }
+}

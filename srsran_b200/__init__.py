@@ -47,7 +47,8 @@ class Enc(C.Structure):  # srslte_b200_enc_t
 
 
 class Demod(C.Structure):  # srslte_b200_demod_t
-    _fields_ = [("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("scramble_bytes", C.c_void_p), ("e_bits", C.c_void_p)]
+    _fields_ = [("symbols", C.c_void_p), ("nof_symbols", C.c_uint32), ("mod", C.c_uint32), ("scramble_bytes", C.c_void_p), ("e_bits", C.c_void_p),
+                ("csi", C.c_void_p)]
 
 
 class Ulsch(C.Structure):  # srslte_b200_ulsch_t
@@ -226,18 +227,21 @@ class Context:
 
     # ---- soft demodulation + descrambling (srslte_demod_soft_demodulate_{s,b} + srslte_scrambling_{s,sb}_offset)
     def demod_descramble(self, codewords, dtype):
-        """codewords: list of (complex64 symbols, mod, packed sequence bytes or None), host arrays.  Returns the list of
-        int16 / int8 LLR arrays (nof_symbols * Qm each)."""
+        """codewords: list of (complex64 symbols, mod, packed sequence bytes or None[, float32 csi or None]), host arrays.
+        Returns the list of int16 / int8 LLR arrays (nof_symbols * Qm each)."""
         n = len(codewords)
         arr = (Demod * n)()
         keep, outs = [], []
-        for i, (sym, mod, scr) in enumerate(codewords):
+        for i, cw in enumerate(codewords):
+            sym, mod, scr = cw[:3]
+            csi = np.ascontiguousarray(cw[3], np.float32) if len(cw) > 3 and cw[3] is not None else None
             sym = np.ascontiguousarray(sym, np.complex64)
             out = np.zeros(len(sym) * MOD_BITS[mod], dtype)
-            keep.append((sym, scr))
+            keep.append((sym, scr, csi))
             outs.append(out)
             arr[i].symbols, arr[i].nof_symbols, arr[i].mod = sym.ctypes.data, len(sym), mod
             arr[i].scramble_bytes = scr.ctypes.data if scr is not None else None
+            arr[i].csi = csi.ctypes.data if csi is not None else None
             arr[i].e_bits = out.ctypes.data
         rc = lib().srslte_b200_demod_descramble(self.h, arr, n, int(dtype == np.int8), 0)
         if rc:

@@ -255,7 +255,7 @@ Engine::~Engine()
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
-  d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); h_dm_desc.release(); h_dm_out.release();
+  d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); d_dm_csimax.release(); h_dm_desc.release(); h_dm_out.release();
   d_enc_in.release(); d_enc_out.release(); d_enc_desc.release(); h_enc_desc.release(); h_enc_out.release();
   d_ul_in.release(); d_ul_out.release(); d_ul_uci.release(); d_ul_desc.release(); h_ul_out.release(); h_ul_uci.release(); h_ul_desc.release();
   if (stream)
@@ -1524,13 +1524,14 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
       return SRSLTE_B200_ERROR_INVALID_INPUTS;
     }
     const uint32_t Qm = c.mod == 0 ? 1 : 2 * c.mod;
-    in_bytes += al16((size_t)c.nof_symbols * 8) + (c.scramble_bytes ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0);
+    in_bytes += al16((size_t)c.nof_symbols * 8) + (c.scramble_bytes ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0) +
+                (c.csi ? al16((size_t)c.nof_symbols * 4) : 0);
     out_bytes += al16((size_t)c.nof_symbols * Qm * esz);
   }
   const bool in_dev = flags & SRSLTE_B200_IN_DEVICE, out_dev = flags & SRSLTE_B200_OUT_DEVICE;
   CUDA_OK(cudaEventSynchronize(ev_desc)); // an earlier call's descriptor upload may still read the pinned buffer reserve() can free
   if ((!in_dev && d_dm_in.reserve(in_bytes + 64)) || (!out_dev && (d_dm_out.reserve(out_bytes + 64) || h_dm_out.reserve(out_bytes + 64))) ||
-      d_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || h_dm_desc.reserve(nof_cw * sizeof(DemodDev)))
+      d_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || h_dm_desc.reserve(nof_cw * sizeof(DemodDev)) || d_dm_csimax.reserve(nof_cw))
     return SRSLTE_B200_ERROR;
   // pass 2: descriptors + uploads (adjacent host arrays go up in one copy)
   CUDA_OK(cudaEventSynchronize(ev_desc)); // a previous device-to-device call may still be reading the pinned descriptors
@@ -1544,6 +1545,7 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   size_t         in_off = 0, out_off = 0;
   const uint8_t* cp_src = nullptr;
   size_t         cp_dst = 0, cp_bytes = 0;
+  bool           any_csi = false;
   auto           upload = [&](const void* src, size_t nb) -> const uint8_t* {
     const uint8_t* dst = d_dm_in.ptr + in_off;
     if (cp_bytes && (const uint8_t*)src == cp_src + cp_bytes && in_off == cp_dst + cp_bytes) {
@@ -1570,10 +1572,14 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
     if (in_dev) {
       d.sym = (const float*)c.symbols;
       d.scr = c.scramble_bytes;
+      d.csi = c.csi;
     } else {
       d.sym = (const float*)upload(c.symbols, (size_t)c.nof_symbols * 8);
       d.scr = c.scramble_bytes ? upload(c.scramble_bytes, ((size_t)c.nof_symbols * Qm + 7) / 8) : nullptr;
+      d.csi = c.csi ? (const float*)upload(c.csi, (size_t)c.nof_symbols * 4) : nullptr;
     }
+    d.csi_max = d_dm_csimax.ptr + i;
+    any_csi   = any_csi || c.csi != nullptr;
     if (out_dev) {
       d.out = c.e_bits;
     } else {
@@ -1586,6 +1592,10 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
   CUDA_OK(cudaMemcpyAsync(d_dm_desc.ptr, hd, nof_cw * sizeof(DemodDev), cudaMemcpyHostToDevice, stream));
   CUDA_OK(cudaEventRecord(ev_desc, stream));
   static const DemodConst kc = demod_constants();
+  if (any_csi) {
+    k_csi_max<<<nof_cw, 256, 0, stream>>>((const DemodDev*)d_dm_desc.ptr);
+    CUDA_OK(cudaGetLastError());
+  }
   for (int m = 0; m < 5; m++) {
     if (!grp_n[m])
       continue;

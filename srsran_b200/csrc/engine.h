@@ -110,6 +110,7 @@ public:
   DevBuf<uint8_t>  d_tmaps;
   DevBuf<uint8_t>  d_dm_in, d_dm_out, d_dm_desc; // soft-demodulation front end: staged symbols + sequences, LLRs, descriptors
   PinBuf<uint8_t>  h_dm_desc, h_dm_out;
+  DevBuf<float>    d_dm_csimax; // per codeword: max of its channel state information (csi_correction)
   DevBuf<uint8_t>  d_enc_in, d_enc_out, d_enc_desc; // transmit mirror: payloads, packed e-bits, descriptors
   PinBuf<uint8_t>  h_enc_desc, h_enc_out;
   DevBuf<uint8_t>  d_ul_in, d_ul_out, d_ul_uci, d_ul_desc; // PUSCH pre-steps: staged q_bits, g_bits, ACK/RI/CQI LLRs, descriptors

@@ -1164,6 +1164,8 @@ struct DemodDev {
   void*          out; // nsym * Qm LLRs
   uint32_t       nsym;
   uint32_t       mod; // srslte_mod_t: 0 BPSK, 1 QPSK, 2 16QAM, 3 64QAM, 4 256QAM
+  const float*   csi;     // channel state information per symbol (csi_correction, pdsch.c:628-741) or nullptr
+  float*         csi_max; // its maximum over the codeword, written by k_csi_max
 };
 struct DemodConst { // thresholds evaluated on the host exactly as the reference's expressions are (float arithmetic)
   float   qpsk_scale_s, qpsk_scale_b;
@@ -1190,6 +1192,29 @@ template <typename T>
 __device__ __forceinline__ int32_t absT(int32_t v) { return wrapT<T>(v < 0 ? -v : v); } // abs(-min) = -min, like pabsw/pabsb
 
 constexpr int kDemodU = 4;
+// csi_max = csi[srslte_vec_max_fi(csi, nsym)] of every codeword that carries channel state information (pdsch.c:651-655)
+__global__ void __launch_bounds__(256) k_csi_max(const DemodDev* __restrict__ cws)
+{
+  __shared__ float s_m[8];
+  const DemodDev d = cws[blockIdx.x];
+  if (!d.csi)
+    return;
+  float m = d.csi[0];
+  for (uint32_t i = threadIdx.x; i < d.nsym; i += blockDim.x)
+    m = fmaxf(m, d.csi[i]);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1)
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0)
+    s_m[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; w++)
+      m = fmaxf(m, s_m[w]);
+    *d.csi_max = m;
+  }
+}
+
 template <typename T, int MOD> // one instantiation per modulation (the host groups the codewords): no per-symbol switch
 __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __restrict__ cws, const DemodConst c)
 {
@@ -1294,6 +1319,38 @@ __global__ void __launch_bounds__(256) k_demod_descramble(const DemodDev* __rest
         v[6] = wrapT<T>(cvt_trunc(__fmul_rn(sc, r)));
         v[7] = wrapT<T>(cvt_trunc(__fmul_rn(sc, q)));
         break;
+      }
+    }
+    // csi_correction (pdsch.c:628-741), between the demodulator and the descrambler: soft bits scaled by the channel state
+    // information of their resource element, with the arithmetic of the reference's x86 build (see oracle.c:orc_csi_correction):
+    // SSE bodies e = (e * sat16(rne(csi * (32767 / max)))) >> 16 -- and in the QPSK / 64QAM bodies the two symbols of a pair
+    // swap (part of) their csi (_mm_blend_ps operand order) --, scalar tails and the int8 path e = (T)((float)e * (csi / max))
+    if (d.csi) {
+      const float    cmax = *d.csi_max;
+      const uint32_t NB   = (uint32_t)n * (uint32_t)Qm;
+      // symbols covered by the SSE body of this modulation (int16 only)
+      const uint32_t body = !S ? 0u : MOD == 1 ? 2u * (NB / 4u) : MOD == 2 ? NB / 4u : MOD == 3 ? 2u * (NB / 12u) : MOD == 4 ? NB / 8u : 0u;
+      if ((uint32_t)i < body) {
+        const float scale = __fdiv_rn(32767.0f, cmax);
+        auto        c16   = [&](float cs) -> int32_t { return min(max(cvt_rne(__fmul_rn(cs, scale)), -32768), 32767); };
+        const int32_t own = c16(d.csi[i]);
+        const int32_t oth = (MOD == 1 || MOD == 3) ? c16(d.csi[i ^ 1]) : own;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < Qm) {
+            int32_t cc = own;
+            if (MOD == 1)
+              cc = oth;
+            if (MOD == 3 && (((i & 1) == 0 && k >= 4) || ((i & 1) == 1 && k < 2)))
+              cc = oth;
+            v[k] = (v[k] * cc) >> 16; // _mm_mulhi_pi16
+          }
+      } else {
+        const float cs = __fdiv_rn(d.csi[i], cmax);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+          if (k < Qm)
+            v[k] = wrapT<T>(cvt_trunc(__fmul_rn((float)v[k], cs)));
       }
     }
     // descrambling: wrapping negation where the sequence bit is 1 (srslte_vec_neg_* against c_short / c_char = +-1)

@@ -1076,3 +1076,27 @@ def test_unmodified_sch_c_on_the_b200_library(port):
                 break
         s.close()
         port.softbuffer_del(sb)
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int8])
+def test_demod_with_csi_correction(port, ctx, dtype):
+    """the whole front end of pdsch.c:832-852 with csi_enable: soft demodulation -> csi_correction (pdsch.c:628-741) ->
+    descrambling in one kernel, against the oracle's three functions in sequence (each pinned to the reference): every
+    modulation, lengths around the SSE group sizes of all three steps, codewords with and without csi in one call"""
+    rng = np.random.default_rng(741 + (dtype == np.int8))
+    cws, want = [], []
+    for mod in range(5):
+        for n in (2, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 33, 100, 1001, 15000):
+            amp = (0.3, 1.0, 3.0, 50.0)[(n + mod) % 4]
+            sym = ((rng.standard_normal(n) + 1j * rng.standard_normal(n)) * amp).astype(np.complex64)
+            nbits = n * b.MOD_BITS[mod]
+            scr = port.sequence_bytes(int(rng.integers(1, 2 ** 31)), nbits) if (n + mod) % 3 else None
+            csi = (rng.random(n).astype(np.float32) * 1.3 + 0.02) if (n + mod) % 4 else None
+            cws.append((sym, mod, scr, csi))
+            llr = port.demod(mod, sym, dtype)
+            if csi is not None:
+                llr = port.csi_correction(csi, llr, mod)
+            want.append(port.descramble(scr, llr) if scr is not None else llr)
+    got = ctx.demod_descramble(cws, dtype)
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert (g == w).all(), (i, cws[i][1], len(cws[i][0]), int(np.argmax(g != w)))

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from oracle.bindings import (CRC8, CRC16, CRC24A, CRC24B, TDEC_AUTO, TDEC_AVX8_WINDOW, TDEC_AVX_WINDOW, TDEC_GENERIC, TDEC_SSE8_WINDOW,
-                             TDEC_SSE_WINDOW, aligned_zeros)
+                             TDEC_SSE_WINDOW, MOD_BITS, aligned_zeros)
 from util import all_K, bpsk_awgn_llr, random_llr, UL_GRANTS, ul_params, ul_qprime
 
 
@@ -259,3 +259,24 @@ def test_ulsch_pre_steps(port, ref, grant):
     if grant != UL_GRANTS[8]: # that one loses a third of its resource elements to a 126x ACK offset and does not decode
         assert rc_ref == 0 and (d_p[:tbs // 8] == data).all()
     ref.sch_del(s)
+
+
+@pytest.mark.parametrize("dtype", [np.int16, np.int8])
+def test_csi_correction(port, ref, dtype):
+    """SURVEY 8f row 1, third item: csi_correction (pdsch.c:628-741, static -- run through oracle/ref_csi_shim.c): every
+    modulation, lengths around its SSE group sizes, full-range soft bits, csi values incl. equal maxima and a zero"""
+    rng = np.random.default_rng(628 + (dtype == np.int8))
+    info = np.iinfo(dtype)
+    for mod in range(5):
+        qm = MOD_BITS[mod]
+        # (the reference's loop bounds `i < nof_bits - 3` / `- 11` are unsigned: a one-symbol QPSK / 64QAM codeword runs off its
+        #  arrays there; real grants have hundreds of symbols, so n starts at 2)
+        for n in (2, 3, 4, 5, 7, 8, 9, 16, 17, 31, 100, 1001, 14400):
+            csi = rng.random(n).astype(np.float32) * (1.7 if n % 2 else 0.4) + 0.01
+            if n > 4:
+                csi[3] = csi.max()  # the maximum twice
+                csi[1] = 0.0
+            e = rng.integers(info.min, info.max + 1, n * qm).astype(dtype)
+            want = ref.csi_correction(csi, e, mod)
+            got = port.csi_correction(csi, e, mod)
+            assert (got == want).all(), (mod, n, int(np.argmax(got != want)))
