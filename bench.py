@@ -484,6 +484,116 @@ def alu_peak(env, ctx):
     return env.probe
 
 
+SYM_CFG = {"c2": dict(mod=3, sigma=0.075), "c4": dict(mod=4, sigma=0.024)}
+
+
+def e2e_symbols(env, args, b, all_ctx, wl, steps, warmup, quick, rng):
+    """symbols (host, pinned) -> H2D -> k_demod_descramble -> decode_tb (device-resident soft bits) -> bytes D2H, chunks rotating
+    over the engines; verified against the oracle's demodulator + descrambler + decode_tb; the reference's same chain on the
+    host cores beside it"""
+    from srsran_b200 import synth
+    cfg, sc = TB_CFG[wl], SYM_CFG[wl]
+    tbs, Qm, G, dt, max_iter = cfg["tbs"], cfg["Qm"], cfg["G"], cfg["dtype"], cfg["max_iter"]
+    is8 = dt == np.int8
+    esz = np.dtype(dt).itemsize
+    ntb, nsym, mod = args.ntb, G // Qm, sc["mod"]
+    c_init = (0x1234 << 14) + (3 << 9) + 77
+    scr = b.sequence_bytes(c_init, G)
+    scr_bits = np.unpackbits(scr)[:G]
+    base = 8
+    data = rng.integers(0, 256, (base, tbs // 8), dtype=np.uint8)
+    e = synth.encode_tbs(data, tbs, Qm, G, 0)
+    sym_base = np.stack([synth.lte_modulate(e[i] ^ scr_bits, mod) for i in range(base)])
+    pin_sym = b.PinnedArray((ntb, nsym), np.complex64)
+    for i in range(0, ntb, 64):
+        n = min(64, ntb - i)
+        noise = (rng.standard_normal((n, nsym)) + 1j * rng.standard_normal((n, nsym))) * sc["sigma"]
+        pin_sym.array[i:i + n] = (sym_base[np.arange(i, i + n) % base] + noise).astype(np.complex64)
+    d_scr = all_ctx[0].device_alloc(len(scr) + 64)  # the scrambling sequence of the RNTI: uploaded once
+    all_ctx[0].h2d(d_scr, scr)
+    ostride = (tbs // 8 + 6 + 15) // 16 * 16
+    pin_out = b.PinnedArray((ntb, ostride), np.uint8)
+    ctx = all_ctx[0]
+    d_e = ctx.device_alloc(ntb * G * esz + 64)
+    n_eng = len(all_ctx)
+    n_chunks = args.e2e_chunks
+    per = (ntb + n_chunks - 1) // n_chunks
+    chunks = []
+    for c in range(n_chunks):
+        lo, hi = c * per, min(ntb, (c + 1) * per)
+        if lo >= hi:
+            break
+        dm = b.make_demods(hi - lo)
+        tb = b.make_tbs(hi - lo)
+        for i in range(lo, hi):
+            d = dm[i - lo]
+            d.symbols, d.nof_symbols, d.mod, d.scramble_bytes, d.e_bits = pin_sym.ptr + i * nsym * 8, nsym, mod, d_scr, d_e + i * G * esz
+            t = tb[i - lo]
+            t.e_bits, t.nof_e_bits, t.tbs, t.Qm, t.rv, t.softbuffer, t.data = d_e + i * G * esz, G, tbs, Qm, 0, None, pin_out.ptr + i * ostride
+        chunks.append((lo, dm, tb))
+
+    def step():
+        for c, (lo, dm, tb) in enumerate(chunks):
+            e_ = all_ctx[c % n_eng]
+            e_.wait()
+            e_.demod_descramble_raw(dm, is8, b.OUT_DEVICE | b.SEQ_DEVICE)        # H2D of the symbols + k_demod_descramble, enqueued
+            e_.decode_tbs(tb, is8, max_iter, flags=b.IN_DEVICE, submit_only=True)  # soft bits never leave the device
+
+    for _ in range(max(1, warmup // 2)):
+        step()
+    for e_ in all_ctx:
+        e_.wait()
+    env.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    for e_ in all_ctx:
+        e_.wait()
+    dt_s = env.vmax(time.perf_counter() - t0)
+    env.barrier()
+    total = env.vsum(ntb * tbs) * steps
+    # verification: a sample of the blocks against the oracle's chain
+    from oracle.bindings import Port
+    P = Port()
+    idx = np.sort(rng.choice(ntb, size=min(ntb, 8 if not quick else 4), replace=False))
+    bad = 0
+    tb_of = {}
+    for lo, dm, tb in chunks:
+        for k in range(len(tb)):
+            tb_of[lo + k] = tb[k]
+    for i in idx:
+        llr = P.descramble(scr, P.demod(mod, np.array(pin_sym.array[i]), dt))
+        sb = P.softbuffer_new()
+        rc, d_, nit, avg, crc = P.decode_tb(sb, tbs, Qm, 0, llr, max_iter)
+        P.softbuffer_del(sb)
+        t = tb_of[int(i)]
+        ok = t.ret == rc and (pin_out.array[i][:tbs // 8 + 3] == d_[:tbs // 8 + 3]).all() and list(t.cb_noi[:t.nof_cb]) == nit[:t.nof_cb].tolist()
+        bad += int(not ok)
+    n_ok = sum(1 for t in tb_of.values() if t.ret == 0)
+    h2d = ntb * nsym * 8
+    res = {"value": total / dt_s / 1e6, "unit": "Mbit/s", "what": "equalised symbols (%s, %d per block, AWGN sigma %.3f) in host memory -> H2D -> "
+           "k_demod_descramble -> decode_tb on device-resident soft bits -> bytes D2H" % ({3: "64QAM", 4: "256QAM"}[mod], nsym, sc["sigma"]),
+           "h2d_bytes_per_step": int(h2d * env.world), "h2d_gbs": h2d * env.world * steps / dt_s / 1e9,
+           "avg_half_iterations": float(np.mean([t.avg_iterations for t in tb_of.values()])), "tb_ok_fraction": n_ok / ntb,
+           "verified": {"n": int(len(idx)), "mismatches": int(bad), "against": "oracle demodulator + descrambler + decode_tb", "what": "return code, bytes, cb_noi"}}
+    if env.rank == 0 and env.world == 1 and not args.no_cpu:
+        R = get_ref()
+        if R is not None:
+            cores = os.cpu_count() or 1
+            sub = np.array(pin_sym.array[:min(ntb, 4 * cores)])
+            t1, _, _ = R.bench_tb_symbols(cores, sub, mod, tbs, c_init, max_iter, is8)
+            rep = max(1, int((args.cpu_seconds / 3 if not quick else 1.5) / max(t1, 1e-3)))
+            t_tot, rc_, avg_ = R.bench_tb_symbols(cores, sub, mod, tbs, c_init, max_iter, is8, repeat=rep)
+            res["cpu_baseline"] = {"value": rep * len(sub) * tbs / t_tot / 1e6, "unit": "Mbit/s", "cores": cores, "kind": "reference", "flags": R.flags,
+                                   "sample": "%d blocks: srslte_demod_soft_demodulate + srslte_scrambling + srslte_dlsch_decode2 per block, %.2f avg "
+                                             "half-iterations, %.1f s" % (rep * len(sub), float(avg_.mean()), t_tot)}
+    ctx.device_free(d_e)
+    ctx.device_free(d_scr)
+    for p_ in (pin_sym, pin_out):
+        p_.free()
+    return res
+
+
 def measure_batched(env, args, wl, steps, warmup, quick):
     """c1 / c2 / c3 / c4 on this rank's GPU.  Returns the result dictionary of the workload."""
     import srsran_b200 as b
@@ -776,6 +886,11 @@ def measure_batched(env, args, wl, steps, warmup, quick):
     # ---- verification of what was timed (outside the timed regions): device-resident outputs and end-to-end outputs
     verified = verify()
 
+    # ---- end to end from equalised SYMBOLS (c2 / c4): what a receiver that also runs the soft demodulator on the device ships
+    #      over the host link -- 8 B per resource element instead of Qm soft bits -- then k_demod_descramble -> decode on the GPU
+    if wl in ("c2", "c4") and not args.no_symbols:
+        extra["e2e_symbols"] = e2e_symbols(env, args, b, all_ctx, wl, steps, warmup, quick, rng)
+
     # ---- per-TTI latency (second half of the metric): ONE subframe's worth of work submitted from host buffers,
     #      submit -> results on the host, back to back on an otherwise idle GPU
     n_lat = 0 if args.no_latency else (300 if not quick else 120)
@@ -999,7 +1114,7 @@ def compact(r):
     if r.get("cpu_baseline"):
         c = r["cpu_baseline"]
         out["cpu_baseline"] = {k: c.get(k) for k in ("value", "cores", "kind", "sample", "latency_one_core")}
-    for k in ("avg_half_iterations", "tb_ok_fraction", "exact_replay_fraction", "half_iteration_histogram"):
+    for k in ("avg_half_iterations", "tb_ok_fraction", "exact_replay_fraction", "half_iteration_histogram", "e2e_symbols"):
         if k in r.get("extra", {}):
             out[k] = r["extra"][k]
     if "decoded_tb_fraction" in r:
@@ -1040,6 +1155,7 @@ def run_ours(args):
     env.sampler.stop()
 
     bad = main_r["verified"]["mismatches"] + sum((c.get("verified") or {}).get("mismatches", 0) for c in configs.values())
+    bad += sum(((c.get("e2e_symbols") or {}).get("verified") or {}).get("mismatches", 0) for c in list(configs.values()) + [main_r.get("extra", {})])
     if rank == 0:
         line = {"metric": "turbo_decoded_mbps", "value": main_r["value"], "unit": "Mbit/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": main_r["ms_per_step"], "higher_is_better": True, "scaling": main_r.get("scaling", "weak"), "vs_baseline": None,
@@ -1084,6 +1200,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-TTI latency loop (keeps profiler launch lists short)")
+    ap.add_argument("--no-symbols", action="store_true", help="c2 / c4: skip the symbols-in end-to-end section")
     ap.add_argument("--no-configs", action="store_true", help="c1 only: skip the compact c2 / c3 / c4 / c5 block")
     ap.add_argument("--config-steps", type=int, default=8, help="timed steps of each configuration of the compact block")
     ap.add_argument("--sustain-seconds", type=float, default=1.5, help="extra device-resident loop of about this long (0: skip)")

@@ -28,6 +28,8 @@ extern "C" {
 /* flags for the batch calls */
 #define SRSLTE_B200_IN_DEVICE 1u  /* LLR / e_bits pointers are device pointers (already resident in HBM) */
 #define SRSLTE_B200_OUT_DEVICE 2u /* output byte pointers are device pointers */
+#define SRSLTE_B200_SEQ_DEVICE 4u /* srslte_b200_demod_descramble: the scrambling sequences are device pointers (a receiver uploads
+                                   * the sequences of its RNTIs once) while the symbols still come from the host */
 
 typedef struct srslte_b200_ctx srslte_b200_ctx_t;             /* one engine instance = one GPU + one stream */
 typedef struct srslte_b200_softbuffer srslte_b200_softbuffer_t; /* device-resident srslte_softbuffer_rx_t */

@@ -516,6 +516,21 @@ class Ref:
                                       C.c_int(int(llr_flat.dtype == np.int8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg), C.c_uint32(repeat))
         return t, out, rc, avg
 
+    def bench_tb_symbols(self, nthreads, sym, mod, tbs, c_init, max_iter, is8, repeat=1):
+        """sym: (ntb, nsym) complex64 equalised symbols; per block: soft demodulation + descrambling + srslte_dlsch_decode2.
+        Returns (seconds, rc, avg_iter)."""
+        ntb, nsym = sym.shape
+        s = aligned_zeros(ntb * nsym * 2 + 16, np.float32)
+        s[:ntb * nsym * 2] = np.ascontiguousarray(sym, np.complex64).view(np.float32).reshape(-1)
+        stride = tbs // 8 + 8 + 768
+        out = np.zeros((ntb, stride), np.uint8)
+        rc = np.zeros(ntb, np.int32)
+        avg = np.zeros(ntb, np.float32)
+        self.L.ref_bench_tb_symbols.restype = C.c_double
+        t = self.L.ref_bench_tb_symbols(C.c_int(nthreads), _p(s), C.c_uint32(ntb), C.c_uint32(nsym), C.c_uint32(mod), C.c_uint32(tbs), C.c_uint32(c_init),
+                                        C.c_uint32(max_iter), C.c_int(int(is8)), _p(out), C.c_uint32(stride), _p(rc), _p(avg), C.c_uint32(repeat))
+        return t, rc, avg
+
     def latency_tb(self, llr, tbs, Qm, max_iter, n_calls):
         """per-call wall time (us) of srslte_dlsch_decode2 for one transport block on one pinned core"""
         ntb, G = llr.shape

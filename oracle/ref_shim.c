@@ -608,6 +608,89 @@ double ref_bench_tb_mixed(int nthreads, void* llr, const uint64_t* off, const ui
   return t1 - t0;
 }
 
+/* --------------------------------------------- symbols in: soft demodulation + descrambling + decode per transport block
+ * (the chain of lib/src/phy/phch/pdsch.c:832-859 without the equaliser), all host threads, pinned */
+typedef struct {
+  int          tid, nthreads;
+  uint32_t     ntb, tbs, mod, Qm, nsym, max_iter, repeat, c_init;
+  int          is8;
+  const float* sym; /* ntb x nsym complex */
+  uint8_t*     out;
+  uint32_t     out_stride;
+  int*         rc;
+  float*       avg_iter;
+  pthread_barrier_t* bar;
+  double       t0, t1;
+} symb_arg_t;
+
+static void* symb_worker(void* p)
+{
+  symb_arg_t* a = p;
+  ref_sch_t*  s = g_workers[a->tid];
+  const uint32_t G = a->nsym * a->Qm;
+  srslte_sequence_t seq;
+  memset(&seq, 0, sizeof(seq));
+  srslte_sequence_LTE_pr(&seq, G, a->c_init);
+  void* llr = NULL;
+  if (posix_memalign(&llr, 64, (size_t)G * 2 + 64))
+    return NULL;
+  pin_to_cpu(a->tid);
+  pthread_barrier_wait(a->bar);
+  a->t0 = now_s();
+  for (uint32_t r = 0; r < a->repeat; r++) {
+    for (uint32_t tb = a->tid; tb < a->ntb; tb += a->nthreads) {
+      const cf_t* sy = (const cf_t*)(a->sym + (size_t)tb * a->nsym * 2);
+      if (a->is8) {
+        srslte_demod_soft_demodulate_b((srslte_mod_t)a->mod, sy, (int8_t*)llr, (int)a->nsym);
+        srslte_scrambling_sb_offset(&seq, (int8_t*)llr, 0, (int)G);
+      } else {
+        srslte_demod_soft_demodulate_s((srslte_mod_t)a->mod, sy, (int16_t*)llr, (int)a->nsym);
+        srslte_scrambling_s_offset(&seq, (int16_t*)llr, 0, (int)G);
+      }
+      srslte_softbuffer_rx_reset_tbs(&s->rx, a->tbs);
+      srslte_pdsch_cfg_t cfg;
+      fill_cfg(s, &cfg, a->tbs, a->Qm, G, 0, 0);
+      a->rc[tb]       = srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)llr, a->out + (size_t)tb * a->out_stride, 0, 1);
+      a->avg_iter[tb] = srslte_sch_last_noi(&s->sch);
+    }
+  }
+  a->t1 = now_s();
+  free(llr);
+  srslte_sequence_free(&seq);
+  return NULL;
+}
+
+double ref_bench_tb_symbols(int nthreads, const float* sym, uint32_t ntb, uint32_t nsym, uint32_t mod, uint32_t tbs, uint32_t c_init, uint32_t max_iter,
+                            int is8, uint8_t* out, uint32_t out_stride, int* rc, float* avg_iter, uint32_t repeat)
+{
+  srslte_rm_turbo_gentables();
+  if (nthreads > MAX_WORKERS)
+    nthreads = MAX_WORKERS;
+  for (int t = 0; t < nthreads; t++)
+    get_worker(t, is8, max_iter);
+  const uint32_t Qm = mod == 0 ? 1 : 2 * mod;
+  pthread_t*        th = calloc(nthreads, sizeof(pthread_t));
+  symb_arg_t*       a  = calloc(nthreads, sizeof(symb_arg_t));
+  pthread_barrier_t bar;
+  pthread_barrier_init(&bar, NULL, nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    a[t] = (symb_arg_t){t, nthreads, ntb, tbs, mod, Qm, nsym, max_iter, repeat ? repeat : 1, c_init, is8, sym, out, out_stride, rc, avg_iter, &bar, 0, 0};
+    pthread_create(&th[t], NULL, symb_worker, &a[t]);
+  }
+  double t0 = 1e300, t1 = 0;
+  for (int t = 0; t < nthreads; t++) {
+    pthread_join(th[t], NULL);
+    if (a[t].t0 < t0)
+      t0 = a[t].t0;
+    if (a[t].t1 > t1)
+      t1 = a[t].t1;
+  }
+  pthread_barrier_destroy(&bar);
+  free(th);
+  free(a);
+  return t1 - t0;
+}
+
 /* --------------------------------------------- per-TTI latency on ONE pinned core (us per TTI, p50 / p99;
  * the reference times the same call, lib/src/phy/phch/pdsch.c:921-924, 1061-1065).  lat_us[i] = wall time of call i. */
 int ref_latency_tb(void* llr, uint32_t ntb, uint32_t tbs, uint32_t Qm, uint32_t G, uint32_t max_iter, int is8, uint32_t n_calls, double* lat_us)

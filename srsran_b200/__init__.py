@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("SRSLTE_B200_LIB", os.path.join(HERE, "libsrslte_fec_b
 
 IN_DEVICE = 1
 OUT_DEVICE = 2
+SEQ_DEVICE = 4
 MAX_CODEBLOCKS = 32
 
 TDEC_AUTO, TDEC_GENERIC, TDEC_SSE, TDEC_SSE_WINDOW, TDEC_NEON_WINDOW, TDEC_AVX_WINDOW, TDEC_SSE8_WINDOW, TDEC_AVX8_WINDOW = range(8)

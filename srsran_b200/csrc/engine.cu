@@ -1524,7 +1524,7 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
       return SRSLTE_B200_ERROR_INVALID_INPUTS;
     }
     const uint32_t Qm = c.mod == 0 ? 1 : 2 * c.mod;
-    in_bytes += al16((size_t)c.nof_symbols * 8) + (c.scramble_bytes ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0) +
+    in_bytes += al16((size_t)c.nof_symbols * 8) + ((c.scramble_bytes && !(flags & SRSLTE_B200_SEQ_DEVICE)) ? al16(((size_t)c.nof_symbols * Qm + 7) / 8) : 0) +
                 (c.csi ? al16((size_t)c.nof_symbols * 4) : 0);
     out_bytes += al16((size_t)c.nof_symbols * Qm * esz);
   }
@@ -1575,7 +1575,8 @@ int Engine::demod_descramble(const srslte_b200_demod_t* cws, uint32_t nof_cw, in
       d.csi = c.csi;
     } else {
       d.sym = (const float*)upload(c.symbols, (size_t)c.nof_symbols * 8);
-      d.scr = c.scramble_bytes ? upload(c.scramble_bytes, ((size_t)c.nof_symbols * Qm + 7) / 8) : nullptr;
+      d.scr = !c.scramble_bytes ? nullptr
+                                : (flags & SRSLTE_B200_SEQ_DEVICE) ? c.scramble_bytes : upload(c.scramble_bytes, ((size_t)c.nof_symbols * Qm + 7) / 8);
       d.csi = c.csi ? (const float*)upload(c.csi, (size_t)c.nof_symbols * 4) : nullptr;
     }
     d.csi_max = d_dm_csimax.ptr + i;
