@@ -144,13 +144,14 @@ def dist_setup(n_gpus, backend=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     if world <= 1:
         return 0, 1, 0, (lambda: None), (lambda x: x), (lambda x: x)
-    import torch
-    import torch.distributed as dist
     backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
     if backend == "nccl" and not os.environ.get("NCCL_DEBUG"):
-        # communicator set-up lines (rank / nranks / device / transport) for whoever reads the log
+        # communicator set-up lines (rank / nranks / device / transport) for whoever reads the log; set before torch is
+        # imported: NCCL reads its debug level once
         os.environ["NCCL_DEBUG"] = "INFO"
         os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+    import torch
+    import torch.distributed as dist
     rank = int(os.environ["RANK"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     if backend == "nccl":

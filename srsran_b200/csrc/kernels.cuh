@@ -878,22 +878,37 @@ __global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
   };
   u32*      beta = a.beta + t;
   const int nt   = a.n_threads;
-  u32       o[8];
+  // The recursions are a serial chain in registers, but nothing they READ depends on them: the rows of a chunk of kGenU
+  // trellis steps (and, in the forward pass, the stored beta vectors) are loaded before the chunk's first step, so the chain
+  // never waits for memory (a batch brings a few dozen warps at most: one load round trip per step was the whole run time)
+  constexpr int kGenU = 8;
+  u32           o[8];
   o[0] = 0;
 #pragma unroll
   for (int i = 1; i < 8; i++)
     o[i] = splat16(-Wrap16::kInf);
-  for (int k = (int)K + 2; k >= 0; k--) { // map_gen_beta, gen.c:71-111
-    u32 x, y, ap;
-    ldx((uint32_t)k, x, y, ap);
-    bwd_step<Wrap16>(o, x, y, p_add_wrap(x, y));
-    if (k >= 1 && k <= (int)K) {
+  for (int k0 = (int)K + 2; k0 >= 0; k0 -= kGenU) { // map_gen_beta, gen.c:71-111: k = K+2 .. 0
+    u32 xs[kGenU], ys[kGenU];
 #pragma unroll
-      for (int s = 0; s < 8; s++)
-        beta[((size_t)k * 8 + s) * nt] = o[s];
+    for (int u = 0; u < kGenU; u++) {
+      u32 ap;
+      if (k0 - u >= 0)
+        ldx((uint32_t)(k0 - u), xs[u], ys[u], ap);
     }
-    if ((uint32_t)k < K)
-      gen_norm((uint32_t)k, o);
+#pragma unroll
+    for (int u = 0; u < kGenU; u++) {
+      const int k = k0 - u;
+      if (k < 0)
+        break;
+      bwd_step<Wrap16>(o, xs[u], ys[u], p_add_wrap(xs[u], ys[u]));
+      if (k >= 1 && k <= (int)K) {
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          beta[((size_t)k * 8 + s) * nt] = o[s];
+      }
+      if ((uint32_t)k < K)
+        gen_norm((uint32_t)k, o);
+    }
   }
   o[0] = 0;
 #pragma unroll
@@ -901,38 +916,52 @@ __global__ void __launch_bounds__(64) k_map_gen(const GenArgs a)
     o[i] = splat16(-Wrap16::kInf);
   const uint16_t* q0 = a.qpp + d0.qpp_off;
   const uint16_t* q1 = a.qpp + d1.qpp_off;
-  for (uint32_t k = 1; k <= K; k++) { // map_gen_alpha, gen.c:135-197
-    u32 x, y, ap;
-    ldx(k - 1, x, y, ap);
-    u32 b[8];
+  constexpr int   kGenA = 4;
+  for (uint32_t k0 = 1; k0 <= K; k0 += kGenA) { // map_gen_alpha, gen.c:135-197: k = 1 .. K
+    u32 xs[kGenA], ys[kGenA], aps[kGenA], bv[kGenA][8];
+    uint32_t f0[kGenA], f1[kGenA];
 #pragma unroll
-    for (int s = 0; s < 8; s++)
-      b[s] = beta[((size_t)k * 8 + s) * nt];
-    RangeMon  nomon;
-    const u32 llr = fwd_step_llr<Wrap16>(o, b, x, y, p_add_wrap(x, y), nomon);
-    gen_norm(k, o);
-    const uint32_t i = k - 1;
-    // glue (iter.h:107-127), per half
-    if (act0) {
-      const int32_t l = lo16(llr);
-      if (!dec2_0) {
-        w0[kPlPost * ps0 + i]             = (int16_t)l;
-        w0[kPlApp2 * ps0 + q0[K + i]]     = (int16_t)(l - lo16(ap)); // app2[rev[i]] = ext1[i] - app1[i]
-      } else {
-        const uint32_t f = q0[i];
-        w0[kPlPost * ps0 + f]  = (int16_t)l;
-        w0[kPlApr * ps0 + f]  = (int16_t)(l - (int32_t)in0[i]);      // app1[fwd[i]] = ext2[i] - app2[i]
+    for (int u = 0; u < kGenA; u++) {
+      const uint32_t k = k0 + u;
+      if (k <= K) {
+        ldx(k - 1, xs[u], ys[u], aps[u]);
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+          bv[u][s] = beta[((size_t)k * 8 + s) * nt];
+        // scatter targets of the glue: rev[i] for decoder 1, fwd[i] for decoder 2 (per half)
+        f0[u] = dec2_0 ? q0[k - 1] : q0[K + k - 1];
+        f1[u] = dec2_1 ? q1[k - 1] : q1[K + k - 1];
       }
     }
-    if (act1) {
-      const int32_t l = hi16(llr);
-      if (!dec2_1) {
-        w1[kPlPost * ps1 + i]         = (int16_t)l;
-        w1[kPlApp2 * ps1 + q1[K + i]] = (int16_t)(l - hi16(ap));
-      } else {
-        const uint32_t f = q1[i];
-        w1[kPlPost * ps1 + f]  = (int16_t)l;
-        w1[kPlApr * ps1 + f]  = (int16_t)(l - (int32_t)in1[i]);
+#pragma unroll
+    for (int u = 0; u < kGenA; u++) {
+      const uint32_t k = k0 + u;
+      if (k > K)
+        break;
+      RangeMon  nomon;
+      const u32 llr = fwd_step_llr<Wrap16>(o, bv[u], xs[u], ys[u], p_add_wrap(xs[u], ys[u]), nomon);
+      gen_norm(k, o);
+      const uint32_t i = k - 1;
+      // glue (iter.h:107-127), per half
+      if (act0) {
+        const int32_t l = lo16(llr);
+        if (!dec2_0) {
+          w0[kPlPost * ps0 + i]     = (int16_t)l;
+          w0[kPlApp2 * ps0 + f0[u]] = (int16_t)(l - lo16(aps[u])); // app2[rev[i]] = ext1[i] - app1[i]
+        } else {
+          w0[kPlPost * ps0 + f0[u]] = (int16_t)l;
+          w0[kPlApr * ps0 + f0[u]]  = (int16_t)(l - lo16(xs[u]));  // app1[fwd[i]] = ext2[i] - app2[i] (decoder 2: x is its own input)
+        }
+      }
+      if (act1) {
+        const int32_t l = hi16(llr);
+        if (!dec2_1) {
+          w1[kPlPost * ps1 + i]     = (int16_t)l;
+          w1[kPlApp2 * ps1 + f1[u]] = (int16_t)(l - hi16(aps[u]));
+        } else {
+          w1[kPlPost * ps1 + f1[u]] = (int16_t)l;
+          w1[kPlApr * ps1 + f1[u]]  = (int16_t)(l - hi16(xs[u]));
+        }
       }
     }
   }
