@@ -1,7 +1,7 @@
 """One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
-k_prepare, k_map_f16 (Fast16 and Sat8, the three decoder modes), k_map_win<Sat16> (exact path), k_map_gen, k_decide_crc,
-k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8), k_ulsch_deinterleave, k_map_lat (one subframe),
-k_enc_tb_crc, k_enc_cb."""
+k_prepare, k_map_fused (Fast16 8 / 16 lanes, Sat8 16 / 32 lanes, Sat16 = the exact path), k_map_gen, k_decide_crc,
+k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8, with and without csi), k_csi_max,
+k_ulsch_deinterleave, k_map_lat + k_map_win (one subframe: the per-half-iteration path), k_enc_tb_crc, k_enc_cb."""
 import os
 import sys
 
@@ -40,14 +40,15 @@ def tb_batch(wl, ntb, max_iter):
     ctx.decode_tbs(t, dt == np.int8, max_iter, flags=b.IN_DEVICE | b.OUT_DEVICE)
 
 
-cb_batch(4736, 6144, 3)           # k_prepare, k_map_f16<Fast16,16,{0,2,1}>, k_decide_crc
-tb_batch("c2", 364, 3)            # k_dematch_prepare<short>, k_tb_finish
-tb_batch("c4", 296, 3)            # k_dematch_prepare<int8>, k_map_f16<Sat8,32,*>
+cb_batch(7104, 6144, 4)           # k_prepare, k_map_fused<Fast16,16> (+ the empty exact-arithmetic launch)
+tb_batch("c2", 500, 8)            # k_dematch_prepare<short>, k_map_fused<Fast16,16> with decisions + CRC, k_tb_finish
+tb_batch("c4", 400, 8)            # k_dematch_prepare<int8>, k_map_fused<Sat8,32>
+cb_batch(4000, 2048, 3, np.int8)  # k_map_fused<Sat8,16>
 ctx.set_option("fast16", 0)
-cb_batch(1184, 6144, 2)           # k_map_win<Sat16,16> doing real work (the exact path)
+cb_batch(2368, 6144, 2)           # k_map_fused<Sat16,16> doing real work (the exact path)
 ctx.set_option("fast16", 1)
-cb_batch(2368, 512, 2)            # k_map_f16<Fast16,8,*>
-cb_batch(4096, 40, 2)             # k_map_gen
+cb_batch(9472, 512, 3)            # k_map_fused<Fast16,8>
+cb_batch(4096, 40, 2)             # k_map_gen, k_decide_crc
 for dt, mod in ((np.int16, 3), (np.int8, 4)):
     n, nsym = 256, 15000
     sym = ((rng.standard_normal((n, nsym)) + 1j * rng.standard_normal((n, nsym))) * 0.7).astype(np.complex64)
