@@ -357,16 +357,17 @@ def run_reference(args):
         K, nit = 6144, 4
         ncb = 1024 * cores if have_ref else 8
         llr, _ = make_c1(rng, ncb, K)
-        units = ncb * K
+        rep = 4 if have_ref else 1   # a step of ~0.25 s: thread start-up and scheduling noise of a 60 ms step cost the reference 30 %
+        units = ncb * K * rep
 
         def step():
             if have_ref:
-                return R.bench_c1(cores, llr, K, nit, layout_sb=False)[0]
+                return R.bench_c1(cores, llr, K, nit, layout_sb=False, repeat=rep)[0]
             t0 = time.perf_counter()
             for i in range(ncb):
                 P.tdec_run_all(h, llr[i], nit, K)
             return time.perf_counter() - t0
-        workload = "c1: K=6144 x 4 half-iterations, int16, %d code blocks per step (bounded sample)" % ncb
+        workload = "c1: K=6144 x 4 half-iterations, int16, %d code blocks per step (bounded sample)" % (ncb * rep)
     else:
         if args.workload == "c3":
             specs = c3_specs(2 if have_ref else 1)

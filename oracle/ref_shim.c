@@ -69,6 +69,10 @@ static void pin_to_cpu(int t)
   }
 }
 
+/* the latency probes pin the CALLING thread; its mask (which threads created later inherit) is put back afterwards */
+static int  save_affinity(cpu_set_t* m) { return pthread_getaffinity_np(pthread_self(), sizeof(*m), m); }
+static void restore_affinity(const cpu_set_t* m, int have) { if (have == 0) pthread_setaffinity_np(pthread_self(), sizeof(*m), m); }
+
 int ref_init(void)
 {
   srslte_rm_turbo_gentables();
@@ -698,6 +702,8 @@ int ref_latency_tb(void* llr, uint32_t ntb, uint32_t tbs, uint32_t Qm, uint32_t 
   srslte_rm_turbo_gentables();
   ref_sch_t* s = get_worker(0, is8, max_iter);
   uint8_t*   out = calloc(tbs / 8 + 8 + 768, 1);
+  cpu_set_t  saved;
+  const int  have = save_affinity(&saved);
   pin_to_cpu(0);
   for (uint32_t i = 0; i < n_calls; i++) {
     uint32_t tb = i % ntb;
@@ -709,6 +715,7 @@ int ref_latency_tb(void* llr, uint32_t ntb, uint32_t tbs, uint32_t Qm, uint32_t 
     srslte_dlsch_decode2(&s->sch, &cfg, (int16_t*)l, out, 0, 1);
     lat_us[i] = 1e6 * (now_s() - t0);
   }
+  restore_affinity(&saved, have);
   free(out);
   return 0;
 }
@@ -719,6 +726,8 @@ int ref_latency_c1(void* llr, uint32_t stride, uint32_t ncb, uint32_t K, uint32_
     g_c1_dec[0][0] = ref_tdec_new(6144, SRSLTE_TDEC_AUTO, 1);
   ref_tdec_t* h   = g_c1_dec[0][0];
   uint8_t*    out = calloc(K / 8 + 16, 1);
+  cpu_set_t   saved;
+  const int   have = save_affinity(&saved);
   pin_to_cpu(0);
   for (uint32_t i = 0; i < n_calls; i++) {
     double t0 = now_s();
@@ -728,6 +737,7 @@ int ref_latency_c1(void* llr, uint32_t stride, uint32_t ncb, uint32_t K, uint32_
     }
     lat_us[i] = 1e6 * (now_s() - t0);
   }
+  restore_affinity(&saved, have);
   free(out);
   return 0;
 }

@@ -551,8 +551,9 @@ static FusedGeom fused_geometry(int n_groups, int max_k, int num_sms, int warps_
   FusedGeom     g;
   g.bits_words = (max_k + 31) / 32;
   g.warp_words = (FusedLay<T>::kFixedWords + G * g.bits_words + 31) / 32 * 32;
-  // one warp per CTA, 12 CTAs per SM: a warp that finds the list dry exits and frees its registers and shared memory for
-  // the next kernel in flight (another engine's batch) instead of waiting for the slowest warp of a larger CTA
+  // 12 resident warps per SM (registers and the warps' staging memory allow no more) as 12 / warps_per_cta CTAs: small CTAs
+  // hand their share of the SM back as soon as their own warps find the list dry, large ones keep the instruction stream
+  // of an SM more coherent (measured: 4 warps without CRC checks, 12 with them -- Engine::opt_fused_warps)
   g.warps = std::max(1, std::min(12, warps_per_cta));
   while (g.warps > 1 && (size_t)g.warps * g.warp_words * 4 > 232448)
     g.warps--;

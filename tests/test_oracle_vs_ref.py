@@ -280,3 +280,18 @@ def test_csi_correction(port, ref, dtype):
             want = ref.csi_correction(csi, e, mod)
             got = port.csi_correction(csi, e, mod)
             assert (got == want).all(), (mod, n, int(np.argmax(got != want)))
+
+
+def test_latency_probes_leave_the_thread_affinity_alone(ref):
+    """the per-TTI latency probes pin the calling thread to one core; threads created afterwards inherit the caller's mask,
+    so a probe that does not put it back serialises every later multi-threaded measurement on one core"""
+    import os
+    before = os.sched_getaffinity(0)
+    llr = aligned_zeros(2 * 1568, np.int16).reshape(2, 1568)   # row stride a multiple of 32 bytes
+    llr[:] = np.random.default_rng(5).integers(-60, 60, llr.shape)
+    lat = ref.latency_c1(llr, 512, 2, 2, 3)
+    assert len(lat) == 3 and (lat > 0).all()
+    assert os.sched_getaffinity(0) == before
+    tb = np.random.default_rng(6).integers(-60, 60, (1, 1200)).astype(np.int16)
+    lat = ref.latency_tb(tb, 1000, 2, 4, 3)
+    assert len(lat) == 3 and os.sched_getaffinity(0) == before
