@@ -355,9 +355,11 @@ def run_reference(args):
     have_ref = R is not None
     if args.workload == "c1":
         K, nit = 6144, 4
-        ncb = 1024 * cores if have_ref else 8
+        # the sample of the cpu_baseline leg (128 distinct blocks per thread, cache-friendly: the reference at its best), a step
+        # of ~0.2 s: thread start-up and scheduling noise of a 60 ms step cost the reference 30 %
+        ncb = 128 * cores if have_ref else 8
         llr, _ = make_c1(rng, ncb, K)
-        rep = 4 if have_ref else 1   # a step of ~0.25 s: thread start-up and scheduling noise of a 60 ms step cost the reference 30 %
+        rep = 32 if have_ref else 1
         units = ncb * K * rep
 
         def step():
@@ -462,17 +464,21 @@ def verify_tbs(tb_arr, outs, flat, off, specs, max_iter, idx):
     return {"n": int(len(idx)), "mismatches": int(bad), "against": "oracle port (pinned to the reference)", "what": "return code, transport block bytes, cb_noi"}
 
 
-def h2d_probe(env, b, ctx, mb=256, reps=6):
-    """plain concurrent host-to-device copy bandwidth of the job: every rank copies a page-locked buffer at the same time"""
+def h2d_probe(env, b, ctx, mb=256, reps=6, trials=3):
+    """plain concurrent host-to-device copy bandwidth of the job: every rank copies a page-locked buffer at the same time
+    (best of a few trials: a single 30 ms trial on a shared host is off by 15 % now and then)"""
     n = mb << 20
     pin = b.PinnedArray((n,), np.uint8)
     d = ctx.device_alloc(n)
     ctx.h2d(d, pin.array)
-    env.barrier()
-    t0 = time.perf_counter()
-    for _ in range(reps):
-        ctx.h2d(d, pin.array)
-    dt = env.vmax(time.perf_counter() - t0)
+    dt = None
+    for _ in range(trials):
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            ctx.h2d(d, pin.array)
+        t = env.vmax(time.perf_counter() - t0)
+        dt = t if dt is None else min(dt, t)
     ctx.device_free(d)
     pin.free()
     return env.world * reps * n / dt / 1e9
