@@ -216,6 +216,8 @@ int Engine::create(Engine** out, int device)
     e->opt_fused = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
     e->opt_fused_warps = atoi(ev);
+  if (const char* ev = getenv("SRSLTE_B200_FUSED_SLICE"))
+    e->opt_fused_slice = atoi(ev);
   cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess)
     ce = cudaEventCreate(&e->ev_begin);
@@ -251,7 +253,7 @@ Engine::~Engine()
   if (ev_end)
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
-  d_crctab.release(); d_parked.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
+  d_crctab.release(); d_parked.release(); d_queue.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
@@ -823,7 +825,7 @@ int Engine::build_plan(Plan& p)
   }
 
   const size_t ctr_fetch0 = 4 + (size_t)p.max_iter + 1; // group fetch counters of the fused launches (two per class)
-  const size_t n_counters = ctr_fetch0 + 8;
+  const size_t n_counters = ctr_fetch0 + 24; // + a hand-back counter and a credit counter per fetch counter (time-sliced classes)
   if (d_counters.reserve(n_counters) || h_counters.reserve(4))
     return SRSLTE_B200_ERROR;
   L.n_cb = n_cb; L.n_dm16 = (int)dm16.size(); L.n_dm8 = (int)dm8.size(); L.n_plain = (int)plain.size(); L.n_pairs = n_pairs;
@@ -893,6 +895,18 @@ int Engine::launch_plan()
       return SRSLTE_B200_ERROR;
     FusedArgs a;
     memset(&a, 0, sizeof(a));
+    // classes with CRC early stop are time-sliced (map_fused.cuh): the blocks that need every iteration would otherwise
+    // start their long run whenever their group happens to be fetched, and the batch ends with a few warps working
+    const bool sliced = !cls[c].no_crc && opt_fused_slice > 0 && p.max_iter > 1;
+    if (sliced) {
+      a.queue_cap = n_groups * (int)p.max_iter;
+      if (d_queue.reserve((size_t)a.queue_cap + n_groups))
+        return SRSLTE_B200_ERROR;
+      CUDA_OK(cudaMemsetAsync(d_queue.ptr, 0xff, ((size_t)a.queue_cap + n_groups) * sizeof(int), stream));
+      a.queue       = d_queue.ptr;
+      a.slice_first = std::max(1, opt_fused_slice / 10);
+      a.slice_next  = std::max(1, opt_fused_slice % 10);
+    }
     a.work       = d_lists.ptr + cls[c].off;
     a.n_groups   = n_groups;
     a.cbs        = d_cbs.ptr;
@@ -920,6 +934,8 @@ int Engine::launch_plan()
         CUDA_OK(cudaMemsetAsync(d_counters.ptr + 2, 0, sizeof(uint32_t), stream)); // parked groups of THIS class
         a.mode      = 1;
         a.ctr_fetch = (int)ctr_fetch0 + 2 * c;
+        a.ctr_tail  = a.ctr_fetch + 8;
+      a.ctr_avail = a.ctr_fetch + 16;
         e = c == 0 ? launch_fused<Fast16, 8>(a, fgeo[c], stream) : launch_fused<Fast16, 16>(a, fgeo[c], stream);
         CUDA_OK(e);
         last_launches++;
@@ -929,10 +945,14 @@ int Engine::launch_plan()
         a.mode = 0;
       }
       a.ctr_fetch = (int)ctr_fetch0 + 2 * c + 1;
+      a.ctr_tail  = a.ctr_fetch + 8;
+      a.ctr_avail = a.ctr_fetch + 16;
       e = c == 0 ? launch_fused<Sat16, 8>(a, fgeo[c], stream) : launch_fused<Sat16, 16>(a, fgeo[c], stream);
     } else {
       a.mode      = 0;
       a.ctr_fetch = (int)ctr_fetch0 + 2 * c;
+      a.ctr_tail  = a.ctr_fetch + 8;
+      a.ctr_avail = a.ctr_fetch + 16;
       e = c == 2 ? launch_fused<Sat8, 16>(a, fgeo[c], stream) : launch_fused<Sat8, 32>(a, fgeo[c], stream);
     }
     CUDA_OK(e);
@@ -1147,7 +1167,7 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   kb.put(*cfg);
   kb.put(flags);
   kb.put(d_llr);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice);
   if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
     // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
     rc = launch_plan();
@@ -1219,7 +1239,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
   bool       reusable = true;
   kb.put('T');
   kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice);
   for (uint32_t t = 0; t < nof_tb; t++) {
     const srslte_b200_tb_t& u = tbs[t];
     if (u.softbuffer)
@@ -2230,6 +2250,12 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
   }
   if (!strcmp(name, "fused")) {
     ctx->e->opt_fused = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "fused_slice")) {
+    if (value < 0 || value > 99)
+      return SRSLTE_B200_ERROR_INVALID_INPUTS;
+    ctx->e->opt_fused_slice = value;
     return 0;
   }
   if (!strcmp(name, "latency")) {

@@ -102,7 +102,9 @@ public:
   bool             opt_latency = true; // small batches: the 4-warp latency-shaped MAP kernel (map_lat.cuh) instead of one warp per group
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch, d_crctab;
   DevBuf<int>      d_parked; // fused kernel: groups whose blocks the Fast16 monitor parked for the exact-arithmetic launch
+  DevBuf<int>      d_queue;  // fused kernel, time-sliced classes: groups handed back by their warp + one parked-list flag per group
   int              opt_fused_warps = 0;  // warps per CTA of the fused kernel (0: chosen per batch)
+  int              opt_fused_slice = 21; // classes with CRC early stop: half-iterations per visit of a group, 10 x first + later (0: a group stays with its warp)
   bool             opt_fused = true; // large batches: one persistent launch per decoder class (map_fused.cuh)
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;

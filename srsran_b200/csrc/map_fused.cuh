@@ -45,6 +45,15 @@ struct FusedArgs {
                                 // [2] groups parked by the Fast16 launch, [ctr_fetch] group fetch counter of this launch
   int                ctr_fetch;
   int*               parked;    // group ids holding parked blocks (written by mode 1, consumed by mode 2)
+  // time slicing (batches with CRC early stop, modes 0 / 1): a warp runs a group for slice_first (first visit) / slice_next
+  // half-iterations and, when other groups are waiting, hands the unfinished group back through queue[] instead of keeping
+  // it: every group advances at the same pace, so the blocks that need all their iterations do not start them late, and a
+  // warp is never idle while work is waiting.  slice_first == 0: a group stays with its warp until it is finished
+  int*               queue;     // [n_groups * max_iter] handed-back group ids (-1 = not yet published) | [n_groups] "already on the parked list" flags
+  int                queue_cap;
+  int                slice_first, slice_next;
+  int                ctr_tail;  // counters[ctr_tail]: number of groups handed back so far
+  int                ctr_avail; // counters[ctr_avail] (signed) + n_groups: entries not yet claimed
   int                mode;      // 0: every active block; 1: Fast16 attempt, flagged blocks are parked; 2: parked blocks only
   const int*         winfo;     // per group {index of its K-group's pair of tensor maps, block coordinate of its first slot}
   const CUtensorMap* tmaps;     // per K-group: [2g] box of 3 planes, [2g+1] box of 2 planes
@@ -600,16 +609,48 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
   }
   __syncwarp();
 
-  const int n_groups = a.mode == 2 ? (int)a.counters[2] : a.n_groups;
+  const int  n_groups = a.mode == 2 ? (int)a.counters[2] : a.n_groups;
+  const bool sliced   = a.slice_first > 0 && a.mode != 2;
   for (;;) {
     // (warp-wide reductions instead of shuffles wherever a value is the same for every lane: their results live in the
     //  uniform datapath, so the tile bookkeeping and the operands of the bulk copies need no per-lane code)
     int gi = 0;
-    if (lane == 0)
-      gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
-    gi = (int)__reduce_add_sync(0xffffffffu, (unsigned)gi);
-    if (gi >= n_groups)
-      break;
+    if (!sliced) {
+      if (lane == 0)
+        gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
+      gi = (int)__reduce_add_sync(0xffffffffu, (unsigned)gi);
+      if (gi >= n_groups)
+        break;
+    } else {
+      // tickets 0 .. n_groups-1 are the groups themselves, ticket n_groups + i is the i-th group handed back.  A ticket is
+      // only taken against a credit (counters[ctr_avail] + n_groups = entries nobody has claimed yet), so no entry is left
+      // behind by a warp that finds nothing and exits; every step is one fetch-add (a compare-and-swap loop on one address
+      // with 1776 warps ending their slices together is quadratic: measured 7x slower than no slicing at all)
+      if (lane == 0) {
+        int* avail = reinterpret_cast<int*>(a.counters + a.ctr_avail);
+        if (atomicAdd(avail, -1) + n_groups <= 0) {
+          atomicAdd(avail, 1);
+          gi = -1;
+        } else {
+          gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
+        }
+        if (gi >= n_groups) {
+          volatile int* slot_q = a.queue + (gi - n_groups);
+          int           v;
+          while ((v = *slot_q) < 0)
+            __nanosleep(64);
+          gi = v | 0x40000000;
+        }
+      }
+      gi = (int)__reduce_add_sync(0xffffffffu, (unsigned)gi);
+      if (gi < 0)
+        break;
+      if (gi & 0x40000000) {
+        gi &= 0x3fffffff;
+        __threadfence(); // acquire: the state and the extrinsic planes the previous owner wrote
+        asm volatile("fence.proxy.async.global;\n" ::: "memory");
+      }
+    }
     const int grp  = a.mode == 2 ? a.parked[gi] : gi;
     const int slot = grp * G + lane / T;
     const int cb   = a.work[slot];
@@ -633,7 +674,8 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
       for (int i = 0; i < 4; i++)
         xq[i] = dp->crc_xq[i];
       n_iter0 = sp->n_iter;
-      if (sp->done || n_iter0 >= max_iter || (a.mode == 2 && !sp->redo))
+      // (mode 1 comes back to a group it handed back: the blocks it parked meanwhile wait for the exact launch)
+      if (sp->done || n_iter0 >= max_iter || (a.mode == 2 && !sp->redo) || (a.mode == 1 && sp->redo))
         live = false;
     }
     const unsigned live_mask = __ballot_sync(0xffffffffu, live);
@@ -661,7 +703,7 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
 
     // The blocks of a group normally sit at the same half-iteration; blocks parked at different half-iterations (exact
     // launch) are taken in cohorts of equal count, because the constituent decoder is a property of the warp's code path
-    bool pending = live;
+    bool pending = live, handed_back = false;
     for (;;) {
     const unsigned pmask = __ballot_sync(0xffffffffu, pending);
     if (pmask == 0)
@@ -669,7 +711,8 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
     int niter = (int)__reduce_min_sync(0xffffffffu, pending ? n_iter0 : 0xffffffffu);
     live      = pending && (int)n_iter0 == niter;
     pending   = pending && !live;
-    const int niter_first = niter;
+    int       niter_first = niter;
+    int       budget      = niter == 0 ? a.slice_first : a.slice_next;
     while (true) {
       // decisions are needed when a CRC check follows this half-iteration or the run ends with it
       const bool want_bits = __any_sync(0xffffffffu, live && (crc_poly != 0 || (uint32_t)niter + 1 >= max_iter));
@@ -749,11 +792,41 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
       }
       if (!__any_sync(0xffffffffu, live))
         break;
+      if (sliced && --budget <= 0) {
+        // end of the slice: keep the group if nobody is waiting, else hand it back and take the oldest waiting one
+        int waiting = 0;
+        if (lane == 0)
+          waiting = *(volatile int*)(a.counters + a.ctr_avail) + n_groups > 0;
+        if (__reduce_add_sync(0xffffffffu, (unsigned)waiting) == 0) {
+          budget = a.slice_next;
+          continue;
+        }
+        if (live && j == 0) {
+          a.state[cb].n_iter = (uint32_t)niter;
+          atomicAdd(&a.counters[1], (uint32_t)(niter - niter_first));
+        }
+        handed_back = true;
+        pending     = false;
+        break;
+      }
     }
     }
     if (a.mode == 1 && parked_any && lane == 0) {
-      const uint32_t at = atomicAdd(&a.counters[2], 1u);
-      a.parked[at]      = grp;
+      // (a sliced group can park blocks in several of its slices: one list entry per group)
+      if (!sliced || atomicExch(&a.queue[a.queue_cap + grp], 0) == -1) {
+        const uint32_t at = atomicAdd(&a.counters[2], 1u);
+        a.parked[at]      = grp;
+      }
+    }
+    if (handed_back) {
+      __threadfence(); // release: this lane's extrinsic values and state
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t at = atomicAdd(&a.counters[a.ctr_tail], 1u);
+        *(volatile int*)(a.queue + at) = grp;
+        __threadfence();
+        atomicAdd(reinterpret_cast<int*>(a.counters + a.ctr_avail), 1); // the credit follows the entry
+      }
     }
   }
 }
