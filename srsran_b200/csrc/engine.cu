@@ -218,6 +218,10 @@ int Engine::create(Engine** out, int device)
     e->opt_fused_warps = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_FUSED_SLICE"))
     e->opt_fused_slice = atoi(ev);
+  if (const char* ev = getenv("SRSLTE_B200_SCAN"))
+    e->opt_scan = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_SCAN_FUSED"))
+    e->opt_scan_fused = atoi(ev) != 0;
   cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
   if (ce == cudaSuccess)
     ce = cudaEventCreate(&e->ev_begin);
@@ -253,7 +257,7 @@ Engine::~Engine()
   if (ev_end)
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
-  d_crctab.release(); d_parked.release(); d_queue.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
+  d_crctab.release(); d_parked.release(); d_queue.release(); d_scan.release(); d_scanacc.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
   d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
@@ -510,6 +514,19 @@ static cudaError_t launch_map_lat(MapArgs a, int n_slots, uint32_t n_iter, cudaS
   kern<<<groups, 128, smem, st>>>(a);
   return cudaGetLastError();
 }
+// Time-parallel pair (map_scan.cuh) for one half-iteration of a class of a few groups
+template <int N>
+static cudaError_t launch_scan(const ScanArgs& sa, int n_slots, uint32_t n_iter, cudaStream_t st)
+{
+  constexpr int G = 64 / N;
+  const int     groups = (n_slots + G - 1) / G;
+  const int     mode   = (n_iter & 1) ? 2 : (n_iter ? 1 : 0);
+  void (*kmat)(ScanArgs) = mode == 2 ? k_scan_mat<N, 2> : (mode == 1 ? k_scan_mat<N, 1> : k_scan_mat<N, 0>);
+  void (*kout)(ScanArgs) = mode == 2 ? k_scan_out<N, 2> : (mode == 1 ? k_scan_out<N, 1> : k_scan_out<N, 0>);
+  kmat<<<groups * (4 * sa.lay.n_chunks + 2), kScanThreads, 0, st>>>(sa);
+  kout<<<groups * sa.lay.n_tiles, 32, (size_t)kScanTileSlots * 32 * 16, st>>>(sa);
+  return cudaGetLastError();
+}
 // Geometry: 128-thread CTAs, three per SM, three staging stages -- the best of the geometries measured
 // (profiles/README.md; four CTAs per SM fit for the two-plane variants but run no faster: DRAM pressure grows with them)
 template <class P, int N>
@@ -541,7 +558,9 @@ struct LaunchState {
   uint32_t  max_iter = 0, iter0 = 0;
   bool      prepare = true;
   ClassRun  cls[4];
-  bool      cls_lat[4], cls_fused[4];
+  bool      cls_lat[4], cls_fused[4], cls_scan[4];
+  ScanLay   scan_lay[4];
+  int       scan_fused_cls = -1, scan_cpg = 0; // the batch is ONE run_all class small enough for k_scan_fused (cooperative launch)
   FusedGeom fgeo[4];
 };
 static LaunchState* new_launch_state() { return new LaunchState(); }
@@ -722,7 +741,7 @@ int Engine::build_plan(Plan& p)
   bool(&cls_lat)[4] = L.cls_lat;
   bool(&cls_fused)[4] = L.cls_fused;
   for (int c = 0; c < 4; c++)
-    cls_lat[c] = cls_fused[c] = false;
+    cls_lat[c] = cls_fused[c] = L.cls_scan[c] = false;
   std::vector<int> old_path; // blocks decided by k_decide_crc after every half-iteration: latency classes + generic decoder
   for (int c = 0; c < 4; c++) {
     if (!cls[c].n_slots)
@@ -730,6 +749,46 @@ int Engine::build_plan(Plan& p)
     const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
     cls_lat[c]   = opt_latency && (c >= 2 || opt_fast16) && n_groups <= num_sms;
     cls_fused[c] = !cls_lat[c] && opt_fused;
+    // a subframe or two of int16 blocks: the time-parallel kernels (map_scan.cuh) instead of k_map_lat's serial recursions
+    L.cls_scan[c] = cls_lat[c] && c < 2 && opt_fast16 && opt_scan && n_groups <= kScanMaxGroups && cls[c].max_w >= kScanMinW && cls[c].max_w <= kScanMaxW;
+    if (L.cls_scan[c]) {
+      L.scan_lay[c].n_tiles  = (cls[c].max_w + 7) / 8;
+      L.scan_lay[c].n_chunks = (cls[c].max_w + kScanChunk - 1) / kScanChunk;
+      if (d_scan.reserve((size_t)n_groups * L.scan_lay[c].words()) || d_scanacc.reserve((size_t)2 * kScanMaxGroups * kScanAcc * 32))
+        return SRSLTE_B200_ERROR;
+    }
+  }
+  // one cooperative launch for all half-iterations when the batch is a single run_all class of the time-parallel kernels
+  L.scan_fused_cls = -1;
+  {
+    int n_active = 0, only = -1;
+    for (int c = 0; c < 4; c++)
+      if (cls[c].n_slots) {
+        n_active++;
+        only = c;
+      }
+    if (n_active == 1 && n_pairs == 0 && L.cls_scan[only] && cls[only].no_crc && opt_scan_fused) {
+      static int max_ctas[2] = {-1, -1}; // co-resident CTAs per SM of the kernel (the cooperative launch needs the whole grid resident)
+      if (max_ctas[only] < 0) {
+        int nb = 0;
+        const size_t smem = (size_t)kScanTileWarps * kScanTileSlots * 32 * 16;
+        cudaError_t e = smem_attr_once(only == 0 ? (const void*)k_scan_fused<8> : (const void*)k_scan_fused<16>, (int)smem);
+        if (e == cudaSuccess)
+          e = only == 0 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_fused<8>, kScanThreads, smem)
+                        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_scan_fused<16>, kScanThreads, smem);
+        max_ctas[only] = e == cudaSuccess ? nb : 0;
+      }
+      const int n_groups = cls[only].n_slots / (64 / kWinClasses[only].lanes);
+      const int items    = 4 * L.scan_lay[only].n_chunks + 2;
+      const int cpg      = std::min(items, max_ctas[only] * num_sms / std::max(1, n_groups));
+      if (cpg >= 4) {
+        L.scan_fused_cls = only;
+        L.scan_cpg       = cpg;
+      }
+    }
+    for (int c = 0; c < 4; c++)
+      if (c != L.scan_fused_cls && !opt_scan_launch)
+        L.cls_scan[c] = false;
   }
   for (int i : active) {
     const CbDev& d = p.cbs[i];
@@ -793,6 +852,10 @@ int Engine::build_plan(Plan& p)
       if (!cls[c].n_slots)
         continue;
       const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
+      if (L.scan_fused_cls == c) { // its parked blocks are finished by k_map_fused<Sat16> (mode 2)
+        fgeo[c] = c == 0 ? fused_geometry<8>(n_groups, cls[c].max_k, num_sms, 4) : fused_geometry<16>(n_groups, cls[c].max_k, num_sms, 4);
+        need    = std::max(need, (size_t)fgeo[c].grid * fgeo[c].warps * ((((size_t)cls[c].max_w + 7) / 8 + 2) * 256 + ((size_t)cls[c].max_k / 2 + 31) / 32 * 32));
+      }
       if (cls_fused[c]) {
         // one checkpoint (256 words per warp) per 8-step tile + the start state, per RESIDENT warp
         // CTA size (measured, profiles/README.md): batches without early stop run 5 % faster as three 4-warp CTAs per SM;
@@ -825,7 +888,7 @@ int Engine::build_plan(Plan& p)
   }
 
   const size_t ctr_fetch0 = 4 + (size_t)p.max_iter + 1; // group fetch counters of the fused launches (two per class)
-  const size_t n_counters = ctr_fetch0 + 24; // + a hand-back counter and a credit counter per fetch counter (time-sliced classes)
+  const size_t n_counters = ctr_fetch0 + 24 + 4 * kScanMaxGroups * 2; // ... + arrival counters of the time-parallel kernels (two classes) // + a hand-back counter and a credit counter per fetch counter (time-sliced classes)
   if (d_counters.reserve(n_counters) || h_counters.reserve(4))
     return SRSLTE_B200_ERROR;
   L.n_cb = n_cb; L.n_dm16 = (int)dm16.size(); L.n_dm8 = (int)dm8.size(); L.n_plain = (int)plain.size(); L.n_pairs = n_pairs;
@@ -858,6 +921,8 @@ int Engine::launch_plan()
     bool     prepare;
   } p{L.max_iter, L.iter0, L.prepare};
   CUDA_OK(cudaMemsetAsync(d_counters.ptr, 0, n_counters * sizeof(uint32_t), stream));
+  if (L.cls_scan[0] || L.cls_scan[1])
+    CUDA_OK(cudaMemsetAsync(d_scanacc.ptr, 0, (size_t)2 * kScanMaxGroups * kScanAcc * 32 * sizeof(int32_t), stream));
   CUDA_OK(cudaEventRecord(ev_begin, stream));
 
   // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
@@ -961,8 +1026,73 @@ int Engine::launch_plan()
     last_map_launches++;
   }
 
+  // ---- a subframe or two of one int16 run_all class: every half-iteration in ONE cooperative launch of the time-parallel
+  //      kernel (map_scan.cuh), the exact kernel for the blocks it parked, one decision launch
+  const bool scan_fused = L.scan_fused_cls >= 0;
+  if (scan_fused) {
+    const int c = L.scan_fused_cls;
+    const int gsz = 64 / kWinClasses[c].lanes, n_groups = cls[c].n_slots / gsz;
+    if (d_parked.reserve((size_t)n_groups + 1))
+      return SRSLTE_B200_ERROR;
+    cudaEvent_t e0, e1;
+    if (map_event_pair(&e0, &e1))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaEventRecord(e0, stream));
+    ScanArgs sa;
+    memset(&sa, 0, sizeof(sa));
+    sa.m = MapArgs{d_lists.ptr + cls[c].off, cls[c].n_slots, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_gmax.ptr, 1, d_ckscratch.ptr, 0, d_counters.ptr, 0,
+                   d_lists.ptr + cls[c].winfo_off, (const CUtensorMap*)d_tmaps.ptr};
+    sa.scratch     = d_scan.ptr;
+    sa.lay         = L.scan_lay[c];
+    sa.group_words = sa.lay.words();
+    sa.arrive      = d_counters.ptr + ctr_fetch0 + 24 + 4 * kScanMaxGroups * c;
+    sa.acc         = d_scanacc.ptr + (size_t)c * kScanMaxGroups * kScanAcc * 32;
+    sa.n_half      = (int)p.max_iter;
+    sa.parked      = d_parked.ptr;
+    sa.n_parked    = d_counters.ptr + 2;
+    void* kargs[] = {&sa};
+    const void* kern = c == 0 ? (const void*)k_scan_fused<8> : (const void*)k_scan_fused<16>;
+    CUDA_OK(cudaLaunchCooperativeKernel(kern, dim3(n_groups * L.scan_cpg), dim3(kScanThreads), kargs, (size_t)kScanTileWarps * kScanTileSlots * 32 * 16, stream));
+    last_launches++;
+    last_map_launches++;
+    FusedArgs a;
+    memset(&a, 0, sizeof(a));
+    a.work       = d_lists.ptr + cls[c].off;
+    a.n_groups   = n_groups;
+    a.cbs        = d_cbs.ptr;
+    a.state      = d_state.ptr;
+    a.ws         = d_ws.ptr;
+    a.tails      = d_tails.ptr;
+    a.qpp        = d_qpp.ptr;
+    a.gmax       = d_gmax.ptr;
+    a.ck_scratch = d_ckscratch.ptr;
+    a.dump_off   = (uint32_t)((((size_t)cls[c].max_w + 7) / 8 + 2) * 256);
+    a.ck_words   = a.dump_off + (uint32_t)(((size_t)cls[c].max_k / 2 + 31) / 32 * 32);
+    a.counters   = d_counters.ptr;
+    a.parked     = d_parked.ptr;
+    a.winfo      = d_lists.ptr + cls[c].winfo_off;
+    a.tmaps      = (const CUtensorMap*)d_tmaps.ptr;
+    a.cb_out     = d_cbout.ptr;
+    a.crc_tab    = d_crctab.ptr;
+    a.mode       = 2;
+    a.ctr_fetch  = (int)ctr_fetch0 + 2 * c + 1;
+    a.ctr_tail   = a.ctr_fetch + 8;
+    a.ctr_avail  = a.ctr_fetch + 16;
+    {
+      const cudaError_t fe = c == 0 ? launch_fused<Sat16, 8>(a, fgeo[c], stream) : launch_fused<Sat16, 16>(a, fgeo[c], stream);
+      CUDA_OK(fe);
+    }
+    CUDA_OK(cudaEventRecord(e1, stream));
+    last_launches++;
+    last_map_launches++;
+    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, 0};
+    k_decide_crc<<<(L.n_old + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
+    CUDA_OK(cudaGetLastError());
+    last_launches++;
+  }
+
   // ---- per-half-iteration path: latency-shaped classes and the generic decoder
-  for (uint32_t it = 0; it < p.max_iter && L.n_old > 0; it++) {
+  for (uint32_t it = 0; it < p.max_iter && L.n_old > 0 && !scan_fused; it++) {
     for (int c = 0; c < 4; c++) {
       if (!cls[c].n_slots || cls_fused[c])
         continue;
@@ -981,7 +1111,18 @@ int Engine::launch_plan()
         a.mode = 1 | skip_post;
         const uint32_t n_it = p.iter0 + it;
         const int      ns   = cls[c].n_slots;
-        if (cls_lat[c]) {
+        if (L.cls_scan[c]) {
+          ScanArgs sa;
+          sa.m           = a;
+          sa.scratch     = d_scan.ptr;
+          sa.lay         = L.scan_lay[c];
+          sa.group_words = sa.lay.words();
+          sa.arrive      = d_counters.ptr + ctr_fetch0 + 24 + 4 * kScanMaxGroups * c;
+          sa.launch_no   = (int)it;
+          sa.acc         = d_scanacc.ptr + (size_t)c * kScanMaxGroups * kScanAcc * 32;
+          e = c == 0 ? launch_scan<8>(sa, ns, n_it, stream) : launch_scan<16>(sa, ns, n_it, stream);
+          last_launches++;
+        } else if (cls_lat[c]) {
           a.ck_slots = cls[c].max_w + 2;
           e = c == 0 ? launch_map_lat<Fast16, 8>(a, ns, n_it, stream) : launch_map_lat<Fast16, 16>(a, ns, n_it, stream);
           a.ck_slots = 0;
@@ -1167,7 +1308,7 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   kb.put(*cfg);
   kb.put(flags);
   kb.put(d_llr);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch);
   if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
     // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
     rc = launch_plan();
@@ -1239,7 +1380,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
   bool       reusable = true;
   kb.put('T');
   kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch);
   for (uint32_t t = 0; t < nof_tb; t++) {
     const srslte_b200_tb_t& u = tbs[t];
     if (u.softbuffer)
@@ -2250,6 +2391,18 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
   }
   if (!strcmp(name, "fused")) {
     ctx->e->opt_fused = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "scan")) {
+    ctx->e->opt_scan = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "scan_launch")) {
+    ctx->e->opt_scan_launch = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "scan_fused")) {
+    ctx->e->opt_scan_fused = value != 0;
     return 0;
   }
   if (!strcmp(name, "fused_slice")) {

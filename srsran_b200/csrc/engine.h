@@ -102,6 +102,11 @@ public:
   bool             opt_latency = true; // small batches: the 4-warp latency-shaped MAP kernel (map_lat.cuh) instead of one warp per group
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch, d_crctab;
   DevBuf<int>      d_parked; // fused kernel: groups whose blocks the Fast16 monitor parked for the exact-arithmetic launch
+  DevBuf<int32_t>  d_scanacc; // ... and the range-monitor accumulators of their groups
+  DevBuf<int32_t>  d_scan;   // time-parallel latency kernels (map_scan.cuh): transfer matrices, boundary states, monitor records
+  bool             opt_scan_launch = false; // the per-half-iteration pair k_scan_mat + k_scan_out where k_scan_fused does not apply (transport blocks): off, k_map_lat's fewer launches win there
+  bool             opt_scan_fused = true; // ... and, for a batch that is one run_all class, all half-iterations in ONE cooperative launch (k_scan_fused)
+  bool             opt_scan = true;  // int16 classes of at most kScanMaxGroups groups: k_scan_mat + k_scan_out instead of k_map_lat
   DevBuf<int>      d_queue;  // fused kernel, time-sliced classes: groups handed back by their warp + one parked-list flag per group
   int              opt_fused_warps = 0;  // warps per CTA of the fused kernel (0: chosen per batch)
   int              opt_fused_slice = 21; // classes with CRC early stop: half-iterations per visit of a group, 10 x first + later (0: a group stays with its warp)

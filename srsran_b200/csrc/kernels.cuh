@@ -793,6 +793,7 @@ __device__ __forceinline__ void tma_tile4(unsigned dst_s, const CUtensorMap* tm,
 } // namespace b200
 #include "map_f16.cuh"
 #include "map_lat.cuh"
+#include "map_scan.cuh"
 namespace b200 {
 __device__ __forceinline__ uint32_t crc24_mulmod(uint32_t a, uint32_t b, uint32_t poly);
 }

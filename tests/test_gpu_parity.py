@@ -1024,6 +1024,46 @@ def test_intermediate_llrs_match_the_oracle(port, ctx, K, dtype, ncb, amp):
             port.tdec_del(h)
 
 
+@pytest.mark.parametrize("K,ncb,amps", [(6144, 13, (100,)), (5824, 13, (100, 900)), (6144, 26, (300, 3000, 12000)), (4096, 9, (100, 20000)), (3136, 5, (700,)),
+                                        (3072, 32, (100, 5000)), (6144, 1, (32767,))])
+def test_time_parallel_latency_kernels(port, ctx, K, ncb, amps):
+    """A subframe or two of int16 blocks runs the time-parallel kernels of map_scan.cuh: the cooperative k_scan_fused (default),
+    the per-half-iteration pair k_scan_mat + k_scan_out (option scan_launch) -- both against k_map_lat (option scan off) and the
+    oracle: decided bytes after 1..7 half-iterations and the extrinsic planes LLR for LLR.  Amplitudes are mixed inside a
+    group so that the range monitor parks some blocks and not others, at different half-iterations (exact kernel takes over)."""
+    rng = np.random.default_rng(K + ncb)
+    N = lanes16(K)
+    base = [std_to_sb(bpsk_awgn_llr(rng, port.tcod_encode(rng.integers(0, 2, K, dtype=np.uint8)), amps[i % len(amps)], 0.7 + 0.1 * (i % 3), np.int16), K, N)
+            for i in range(min(ncb, 5))]
+    batch = np.ascontiguousarray(np.stack([base[i % len(base)] for i in range(ncb)]))
+    try:
+        for n in (1, 2, 4, 5, 7):
+            hs, want = [], []
+            for b0 in base:
+                h = port.tdec_new(TDEC_AUTO, False)
+                want.append(port.tdec_run_all(h, b0, n, K)[1])
+                hs.append(h)
+            for scan, launch, fused in ((0, 0, 0), (1, 0, 1), (1, 1, 0)):
+                ctx.set_option("scan", scan)
+                ctx.set_option("scan_launch", launch)
+                ctx.set_option("scan_fused", fused)
+                got = ctx.tdec_batch(batch, K, n, input_sb=True)
+                if scan and fused and ncb <= 32 and K >= 16 * 192:
+                    assert ctx.last_map_launches() == 2, "k_scan_fused + the exact kernel for parked blocks"
+                for i in range(ncb):
+                    assert (got[i] == want[i % len(base)]).all(), (K, n, scan, launch, fused, i)
+                for cb in sorted({0, ncb // 2, ncb - 1}):
+                    plane, exp = _expected_planes(port, hs[cb % len(base)], K, N, n, 16)
+                    llr = ctx.debug_read_plane(cb, plane, K)
+                    assert (llr == exp).all(), "K=%d n=%d scan=%d/%d/%d block %d: %d LLRs differ" % (K, n, scan, launch, fused, cb, int((llr != exp).sum()))
+            for h in hs:
+                port.tdec_del(h)
+    finally:
+        ctx.set_option("scan", 1)
+        ctx.set_option("scan_launch", 0)
+        ctx.set_option("scan_fused", 1)
+
+
 def test_int8_full_scale_every_windowed_size(port, ctx):
     """int8 LLRs over the whole +-127 range on EVERY size the int8 decoders take in lane layout (K >= 408: widened 8-lane,
     16-lane and 32-lane decoders), 4 half-iterations, decided bytes after the run; batches large enough for k_map_fused on the
