@@ -637,8 +637,13 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
         if (gi >= n_groups) {
           volatile int* slot_q = a.queue + (gi - n_groups);
           int           v;
-          while ((v = *slot_q) < 0)
+          // (the entry is being published by the warp that took the matching credit: a few instructions away.  Bounded, so
+          //  that a logic error is a trap and an error code instead of a hung GPU)
+          for (uint32_t spins = 0; (v = *slot_q) < 0; spins++) {
             __nanosleep(64);
+            if (spins > (1u << 22))
+              __trap();
+          }
           gi = v | 0x40000000;
         }
       }

@@ -916,8 +916,13 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_fused(const ScanArgs s
       if (tid == 0)
         atomicAdd(bar + 2 * which + 1, 1u);
     } else if (tid == 0) {
-      while (*(volatile uint32_t*)(bar + 2 * which + 1) < epoch)
+      // (every CTA of the grid is resident -- cooperative launch -- so the release always comes; bounded all the same: a
+      //  logic error must be a trap and an error code, not a hung GPU)
+      for (uint32_t spins = 0; *(volatile uint32_t*)(bar + 2 * which + 1) < epoch; spins++) {
         __nanosleep(32);
+        if (spins > (1u << 24))
+          __trap();
+      }
     }
     __syncthreads();
     __threadfence();
@@ -995,6 +1000,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_scan_fused(const ScanArgs s
           has_parked = true;
         else
           s->n_iter = a.cbs[ge.cb].max_iter - 1;
+        // half-iterations this kernel ran for the block (MapArgs::counters[1]; the decision kernel counts the last one, the
+        // exact kernel its own)
+        const uint32_t ran = s->n_iter - (uint32_t)niter0;
+        if (ran)
+          atomicAdd(const_cast<uint32_t*>(a.counters) + 1, ran);
       }
       if (__any_sync(0xffffffffu, has_parked) && lane == 0) {
         const uint32_t at = atomicAdd(sa.n_parked, 1u);
