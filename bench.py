@@ -145,11 +145,11 @@ def dist_setup(n_gpus, backend=None):
     if world <= 1:
         return 0, 1, 0, (lambda: None), (lambda x: x), (lambda x: x)
     backend = backend or os.environ.get("BENCH_BACKEND", "nccl")
-    if backend == "nccl" and not os.environ.get("NCCL_DEBUG"):
+    if backend == "nccl" and os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
         # communicator set-up lines (rank / nranks / device / transport) for whoever reads the log; set before torch is
-        # imported: NCCL reads its debug level once
+        # imported: NCCL reads its debug level once.  (The image presets NCCL_DEBUG=VERSION: an unset-only default never fired.)
         os.environ["NCCL_DEBUG"] = "INFO"
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT,ENV")
     import torch
     import torch.distributed as dist
     rank = int(os.environ["RANK"])
@@ -163,9 +163,11 @@ def dist_setup(n_gpus, backend=None):
         os.dup2(2, 1)
         try:
             dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-            t_ = torch.zeros(1, device="cuda")
+            t_ = torch.ones(1, device="cuda")
             dist.all_reduce(t_)
             torch.cuda.synchronize()
+            sys.stderr.write("[bench] rank %s of %s: %s (cuda:%s), NCCL %s, all_reduce of ones = %s\n" % (
+                rank, world, torch.cuda.get_device_name(local), local, ".".join(map(str, torch.cuda.nccl.version())), float(t_.item())))
         finally:
             sys.stdout.flush()
             os.dup2(saved, 1)
@@ -1190,6 +1192,9 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
+        # NCCL's tear-down lines (NCCL_DEBUG=INFO logs to stdout) must not follow the JSON line on stdout
+        sys.stdout.flush()
+        os.dup2(2, 1)
         dist.destroy_process_group()
     return 1 if bad else 0
 
