@@ -216,6 +216,8 @@ int Engine::create(Engine** out, int device)
     e->opt_fused = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
     e->opt_fused_warps = atoi(ev);
+  if (const char* ev = getenv("SRSLTE_B200_L2_PERSIST"))
+    e->opt_l2_persist = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_FUSED_SLICE"))
     e->opt_fused_slice = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_SCAN"))
@@ -989,6 +991,25 @@ int Engine::launch_plan()
     a.tmaps      = (const CUtensorMap*)d_tmaps.ptr;
     a.cb_out     = d_cbout.ptr;
     a.crc_tab    = d_crctab.ptr;
+    a.ck_policy  = opt_l2_persist == 2 ? 1 : 0;
+    if (opt_l2_persist) {
+      // experiment (profiles/README.md): keep the checkpoints of the half-iteration in flight in L2 with a persisting window
+      static int max_persist = -1, max_window = 0;
+      if (max_persist < 0) {
+        cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, device);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, device);
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+      }
+      const size_t bytes = std::min((size_t)fgeo[c].grid * fgeo[c].warps * a.ck_words * 4, (size_t)max_window);
+      cudaStreamAttrValue v;
+      memset(&v, 0, sizeof(v));
+      v.accessPolicyWindow.base_ptr  = d_ckscratch.ptr;
+      v.accessPolicyWindow.num_bytes = bytes;
+      v.accessPolicyWindow.hitRatio  = bytes ? std::min(1.0f, (float)max_persist / (float)bytes) : 0.f;
+      v.accessPolicyWindow.hitProp   = cudaAccessPropertyPersisting;
+      v.accessPolicyWindow.missProp  = cudaAccessPropertyStreaming;
+      CUDA_OK(cudaStreamSetAttribute(stream, cudaStreamAttributeAccessPolicyWindow, &v));
+    }
     cudaEvent_t e0, e1;
     if (map_event_pair(&e0, &e1))
       return SRSLTE_B200_ERROR;

@@ -109,6 +109,7 @@ public:
   bool             opt_scan = true;  // int16 classes of at most kScanMaxGroups groups: k_scan_mat + k_scan_out instead of k_map_lat
   DevBuf<int>      d_queue;  // fused kernel, time-sliced classes: groups handed back by their warp + one parked-list flag per group
   int              opt_fused_warps = 0;  // warps per CTA of the fused kernel (0: chosen per batch)
+  int              opt_l2_persist = 0;   // experiment: 1 = L2 access policy window (persisting) over the checkpoint scratch, 2 = and no per-instruction hints on them
   int              opt_fused_slice = 21; // classes with CRC early stop: half-iterations per visit of a group, 10 x first + later (0: a group stays with its warp)
   bool             opt_fused = true; // large batches: one persistent launch per decoder class (map_fused.cuh)
   PinBuf<uint32_t> h_counters;

@@ -70,6 +70,12 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint64_t l2_policy_evict_normal()
+{
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;\n" : "=l"(p));
+  return p;
+}
 __device__ __forceinline__ void tma_tile4_hint(unsigned dst_s, const CUtensorMap* tm, int c0, int c1, int c2, int c3, unsigned bar_s, uint64_t pol)
 {
   asm volatile(

@@ -62,6 +62,7 @@ struct FusedArgs {
   int                warp_words; // shared memory words per warp (FusedLay<T>::kFixedWords + G * bits words per block)
   int                bits_words; // words of the K-bit decision string per block (max over the class)
   uint32_t           dump_off;   // word offset, inside a warp's ck_scratch share, of the area ghost lanes scatter into
+  int                ck_policy;  // beta checkpoints: 0 = stored evict_last / read back evict_first; 1 = no eviction hint (the stream's access policy window decides)
 };
 
 template <int T>
@@ -119,7 +120,7 @@ struct FusedWarp {
   unsigned gmask;
   int      wr_stage, rd_stage;
   unsigned rd_phase;
-  uint64_t pol_first, pol_last;
+  uint64_t pol_first, pol_last, pol_ck_st, pol_ck_ld;
   u32*     ck_warp;   // checkpoint scratch of this resident warp: slot s at ck_warp + 256 s
   u32*     bits;      // decision bits of this thread's block
 };
@@ -188,7 +189,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       // checkpoint beta[8(t+1)] of the alpha tile whose planes the PREVIOUS call requested: same mbarrier, ring slot t & 1
       const int t     = wr_idx - 1 - s3;
       const int stage = w.wr_stage == 0 ? kStages - 1 : w.wr_stage - 1;
-      bulk_g2s_hint(w.sm_s + 4u * (unsigned)(Lay::kCkRing + (t & 1) * 256), w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar_of(stage), w.pol_first);
+      bulk_g2s_hint(w.sm_s + 4u * (unsigned)(Lay::kCkRing + (t & 1) * 256), w.ck_warp + (size_t)(t + 1) * 256, 1024u, bar_of(stage), w.pol_ck_ld);
     }
     if (wr_idx < n_seq) {
       if (lane == 0) {
@@ -250,8 +251,8 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   //         normalisation, slot nT = beta[W]  (every lane stores, ghosts too: the scratch belongs to the warp)
   auto ck_store = [&](int sl, const u32 (&v)[8]) {
     uint4* g = reinterpret_cast<uint4*>(w.ck_warp + (size_t)sl * 256) + lane;
-    stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), w.pol_last);
-    stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), w.pol_last);
+    stg128_hint(g, make_uint4(v[0], v[1], v[2], v[3]), w.pol_ck_st);
+    stg128_hint(g + 32, make_uint4(v[4], v[5], v[6], v[7]), w.pol_ck_st);
   };
 #pragma unroll
   for (int s = 0; s < 8; s++)
@@ -598,6 +599,8 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
   w.rd_phase  = 0;
   w.pol_first = l2_policy_evict_first();
   w.pol_last  = l2_policy_evict_last();
+  w.pol_ck_st = a.ck_policy ? l2_policy_evict_normal() : w.pol_last;
+  w.pol_ck_ld = a.ck_policy ? l2_policy_evict_normal() : w.pol_first;
   w.ck_warp   = a.ck_scratch + (size_t)(blockIdx.x * (blockDim.x >> 5) + wib) * a.ck_words;
   w.bits      = w.sm + Lay::kBitsOff + (lane / T) * a.bits_words;
   const int j = w.j;
