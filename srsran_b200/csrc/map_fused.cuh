@@ -418,7 +418,14 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     }
     if (P::kMonitor && (i & 1) == 0)
       mon.track(al);
-    if ((kNP == 1 || (i & 1) == 0) && norm)
+    if (P::kMonitor && i == 0) {
+      // (step 0 of a half tile normalises in every tile but the very first: without a branch -- subtracting zero leaves the
+      //  metrics as they are -- the two paths need no register moves to meet again)
+      const u32 n0 = norm ? al[0] : 0u;
+#pragma unroll
+      for (int s = 0; s < 8; s++)
+        al[s] = p_sub_wrap(al[s], n0);
+    } else if ((kNP == 1 || (i & 1) == 0) && norm)
       P::normalize_now(al);
     const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tq + i * T);
     const uint32_t  t0 = r16[0], t1 = r16[1];
