@@ -70,6 +70,12 @@ __device__ __forceinline__ uint64_t l2_policy_evict_last()
   asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;\n" : "=l"(p));
   return p;
 }
+__device__ __forceinline__ uint32_t lds_u16(unsigned addr_s)
+{
+  unsigned short v;
+  asm volatile("ld.shared.u16 %0, [%1];\n" : "=h"(v) : "r"(addr_s));
+  return v;
+}
 __device__ __forceinline__ uint64_t l2_policy_evict_normal()
 {
   uint64_t p;

@@ -427,8 +427,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         al[s] = p_sub_wrap(al[s], n0);
     } else if ((kNP == 1 || (i & 1) == 0) && norm)
       P::normalize_now(al);
-    const uint16_t* r16 = reinterpret_cast<const uint16_t*>(tq + i * T);
-    const uint32_t  t0 = r16[0], t1 = r16[1];
+    // (two 16-bit loads, not one word taken apart with LOP3 + PRMT: the load / store unit has room, the max-type pipe does not)
+    const unsigned  tq_s = (unsigned)__cvta_generic_to_shared(tq + i * T);
+    const uint32_t  t0 = lds_u16(tq_s), t1 = lds_u16(tq_s + 2u);
     // decoder 1: extrinsic - a-priori -> app2[rev[.]]; decoder 2: a-posteriori - own input -> a-priori[fwd[.]]
     // (decoder 2 has a zero a-priori slice, so x is its own input)
     const u32 sub = d2 ? x : tp[2 * Lay::kPlaneWords + i * 32];
@@ -455,8 +456,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     if (bits2) {
       // decisions belong to natural positions nat[.]
       const u32       dbit = __vimin_s16x2_relu(llr, 0x00010001u);
-      const uint16_t* n16 = reinterpret_cast<const uint16_t*>(tq + Lay::kLutWords + i * T);
-      const uint32_t  n0 = n16[0], n1 = n16[1];
+      const uint32_t  n0 = lds_u16(tq_s + 4u * (unsigned)Lay::kLutWords), n1 = lds_u16(tq_s + 4u * (unsigned)Lay::kLutWords + 2u);
       atomicOr(reinterpret_cast<u32*>(bits_c + ((n0 >> 5) << 2)), __funnelshift_l(0u, dbit & 1u, n0));
       atomicOr(reinterpret_cast<u32*>(bits_c + ((n1 >> 5) << 2)), __funnelshift_l(0u, dbit >> 16, n1));
     }
