@@ -929,7 +929,7 @@ int Engine::launch_plan()
 
   // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
   //      directly supplied LLRs: extraction only
-  const size_t sb_smem = (3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t);
+  const size_t sb_smem = ((3 * (kMaxK + kSbPad) + 12) * sizeof(int16_t) + 127) / 128 * 128; // (whole lines: the kernel swizzles within them)
   if (L.n_dm16 > 0) {
     auto kern = k_dematch_prepare<int16_t>;
     CUDA_OK(smem_attr_once((const void*)kern, (int)sb_smem));

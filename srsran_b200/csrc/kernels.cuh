@@ -305,6 +305,17 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
 // retransmission), the e-bits are accumulated into it (same gather form as k_dematch), and the result leaves the
 // SM as the decoder's three int16 planes + tails + per-plane max|LLR|; it is written back to the HARQ soft buffer
 // only when the caller keeps one (d.fresh != 1 means a caller-owned buffer).
+// Shared-memory index of soft-buffer element i.  The sub-block interleaver hands consecutive e-bits to positions 32 trellis
+// steps apart, i.e. a power-of-two stride in the lane layout: un-swizzled, the 32 lanes of a warp hit one or two banks
+// (10-16-way conflicts on both the load and the store of the accumulation, measured on the tables).  XOR-ing the bank bits
+// with higher index bits spreads them (2-2.5-way); element pairs (int16) / quads (int8) stay together in their word.
+template <typename T>
+__device__ __forceinline__ uint32_t sb_swz(uint32_t i)
+{
+  constexpr int  kShift = sizeof(T) == 2 ? 1 : 2;
+  const uint32_t h = i >> (5 + kShift);
+  return i ^ (((h ^ (h >> 5) ^ (h >> 10)) & 31u) << kShift);
+}
 template <typename T>
 __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list,
                                                          const uint16_t* __restrict__ rm_pool, int16_t* __restrict__ ws,
@@ -330,12 +341,12 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
   }
   if (d.fresh) {
     uint4*         z  = reinterpret_cast<uint4*>(s_raw);
-    const uint32_t nz = (n_sb * sizeof(T) + 15) / 16;
+    const uint32_t nz = ((n_sb * sizeof(T) + 127) / 128) * 8; // (whole 128-byte lines: the swizzle permutes within them)
     for (uint32_t i = threadIdx.x; i < nz; i += blockDim.x)
       z[i] = make_uint4(0, 0, 0, 0);
   } else {
     for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
-      sb[i] = gsb[i];
+      sb[sb_swz<T>(i)] = gsb[i];
   }
   __syncthreads();
   const T*        in  = (const T*)d.e_ptr;
@@ -366,14 +377,15 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
         uint32_t acc = (uint32_t)v[u];
         for (uint32_t r = i + L; r < d.E; r += L) // repetitions (E > 3K+12): same soft bit received again
           acc += (uint32_t)(int32_t)in[r];
-        sb[o[u]] = (T)(uint32_t)((uint32_t)(int32_t)sb[o[u]] + acc); // wraps in the width of the soft buffer
+        const uint32_t at = sb_swz<T>(o[u]);
+        sb[at] = (T)(uint32_t)((uint32_t)(int32_t)sb[at] + acc); // wraps in the width of the soft buffer
       }
     }
   }
   __syncthreads();
   if (d.fresh != 1) {
     for (uint32_t i = threadIdx.x; i < n_sb; i += blockDim.x)
-      gsb[i] = sb[i];
+      gsb[i] = sb[sb_swz<T>(i)];
   }
   // decoder planes (int16 containers), tails, max |LLR| per plane
   int16_t* p0 = ws + d.ws_off;
@@ -385,12 +397,11 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     u32* q2 = reinterpret_cast<u32*>(p0 + kPlPar1 * (size_t)d.ps);
     if (sizeof(T) == 2) {
       // int16 soft buffer: the planes are already pairs of adjacent lanes, copy them as 32-bit words
-      const u32* s0 = reinterpret_cast<const u32*>(sb);
-      const u32* s1 = reinterpret_cast<const u32*>(sb + (K + kSbPadDev));
-      const u32* s2 = reinterpret_cast<const u32*>(sb + 2 * (K + kSbPadDev));
-      u32        h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
+      const u32*     sw = reinterpret_cast<const u32*>(sb);
+      const uint32_t o1 = K + kSbPadDev, o2 = 2 * (K + kSbPadDev);
+      u32            h0 = 0, l0 = 0, h1 = 0, l1 = 0, h2 = 0, l2 = 0;
       for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
-        const u32 a = s0[h], b = s1[h], c = s2[h];
+        const u32 a = sw[sb_swz<T>(2 * h) >> 1], b = sw[sb_swz<T>(o1 + 2 * h) >> 1], c = sw[sb_swz<T>(o2 + 2 * h) >> 1];
         q0[h] = a;
         q1[h] = b;
         q2[h] = c;
@@ -404,8 +415,9 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     } else {
       for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
         const uint32_t j  = 2 * h;
-        const int32_t  a0 = sb[j], a1 = sb[j + 1], b0 = sb[K + kSbPadDev + j], b1 = sb[K + kSbPadDev + j + 1];
-        const int32_t  c0 = sb[2 * (K + kSbPadDev) + j], c1 = sb[2 * (K + kSbPadDev) + j + 1];
+        auto at = [&](uint32_t i) -> int32_t { return sb[sb_swz<T>(i)]; };
+        const int32_t  a0 = at(j), a1 = at(j + 1), b0 = at(K + kSbPadDev + j), b1 = at(K + kSbPadDev + j + 1);
+        const int32_t  c0 = at(2 * (K + kSbPadDev) + j), c1 = at(2 * (K + kSbPadDev) + j + 1);
         q0[h] = pack16(a0, a1);
         q1[h] = pack16(b0, b1);
         q2[h] = pack16(c0, c1);
@@ -416,7 +428,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
   } else {
     for (uint32_t n = threadIdx.x; n < K; n += blockDim.x) {
       const uint32_t j = N ? (n % W) * N + n / W : n;
-      const int32_t  a = sb[3 * n], b = sb[3 * n + 1], c = sb[3 * n + 2];
+      const int32_t  a = sb[sb_swz<T>(3 * n)], b = sb[sb_swz<T>(3 * n + 1)], c = sb[sb_swz<T>(3 * n + 2)];
       p0[j]            = (int16_t)a;
       p0[d.ps + j]     = (int16_t)b;
       p0[kPlPar1 * (size_t)d.ps + j] = (int16_t)c;
@@ -427,7 +439,7 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     const uint32_t tb = d.in_sb ? 3 * (K + kSbPadDev) : 3 * K;
     const uint32_t t = threadIdx.x, grp = t / 3, i = t % 3;
     const uint32_t src = (grp == 0) ? 2 * i : (grp == 1) ? 2 * i + 1 : (grp == 2) ? 6 + 2 * i : 6 + 2 * i + 1;
-    tails[(size_t)cb * 12 + t] = (int16_t)sb[tb + src];
+    tails[(size_t)cb * 12 + t] = (int16_t)sb[sb_swz<T>(tb + src)];
   }
   atomicMax(&s_g[0], g0);
   atomicMax(&s_g[1], g1);
