@@ -49,6 +49,7 @@ cb_batch(2368, 6144, 2)           # k_map_fused<Sat16,16> doing real work (the e
 ctx.set_option("fast16", 1)
 cb_batch(9472, 512, 3)            # k_map_fused<Fast16,8>
 cb_batch(4096, 40, 2)             # k_map_gen, k_decide_crc
+cb_batch(13, 6144, 4)             # k_scan_fused: one subframe, time-parallel (cooperative launch)
 for dt, mod in ((np.int16, 3), (np.int8, 4)):
     n, nsym = 256, 15000
     sym = ((rng.standard_normal((n, nsym)) + 1j * rng.standard_normal((n, nsym))) * 0.7).astype(np.complex64)
@@ -72,8 +73,10 @@ for i in range(ntb_ul):
     ul[i].q_bits, ul[i].Qm, ul[i].H_prime_total, ul[i].N_pusch_symbs, ul[i].g_bits = d_q + i * n_ul * 2, 6, 14400, 12, d_g + i * n_ul * 2
     ul[i].Q_prime_ack, ul[i].Q_prime_ri, ul[i].Q_prime_cqi = 36, 20, 57
 ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
-# one subframe at a time: k_map_lat<Fast16,16,*> (13 blocks of K = 6144) and k_map_lat<Sat8,32,*> (one 97896-bit block)
+# one subframe at a time, one launch per half-iteration: k_map_lat<Fast16,16,*> (13 blocks of K = 6144) and k_map_lat<Sat8,32,*> (one 97896-bit block)
+ctx.set_option("scan", 0)
 cb_batch(13, 6144, 3)
+ctx.set_option("scan", 1)
 tb_batch("c4", 1, 3)
 # transmit mirror: k_enc_tb_crc, k_enc_cb
 ntb, tbs, Qm, G = 364, 75376, 6, 90000

@@ -313,8 +313,8 @@ template <typename T>
 __device__ __forceinline__ uint32_t sb_swz(uint32_t i)
 {
   constexpr int  kShift = sizeof(T) == 2 ? 1 : 2;
-  const uint32_t h = i >> (5 + kShift);
-  return i ^ (((h ^ (h >> 5) ^ (h >> 10)) & 31u) << kShift);
+  const uint32_t h = i >> (5 + kShift); // (< 2^10 for every soft buffer: 18 600 elements)
+  return i ^ (((h ^ (h >> 5)) & 31u) << kShift);
 }
 template <typename T>
 __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict__ cbs, const int* __restrict__ list,
@@ -415,9 +415,10 @@ __global__ void __launch_bounds__(256) k_dematch_prepare(const CbDev* __restrict
     } else {
       for (uint32_t h = threadIdx.x; h < K / 2; h += blockDim.x) {
         const uint32_t j  = 2 * h;
-        auto at = [&](uint32_t i) -> int32_t { return sb[sb_swz<T>(i)]; };
-        const int32_t  a0 = at(j), a1 = at(j + 1), b0 = at(K + kSbPadDev + j), b1 = at(K + kSbPadDev + j + 1);
-        const int32_t  c0 = at(2 * (K + kSbPadDev) + j), c1 = at(2 * (K + kSbPadDev) + j + 1);
+        // (j is even: the two elements of a pair sit side by side under the swizzle as well)
+        const uint32_t ja = sb_swz<T>(j), jb = sb_swz<T>(K + kSbPadDev + j), jc = sb_swz<T>(2 * (K + kSbPadDev) + j);
+        const int32_t  a0 = sb[ja], a1 = sb[ja + 1], b0 = sb[jb], b1 = sb[jb + 1];
+        const int32_t  c0 = sb[jc], c1 = sb[jc + 1];
         q0[h] = pack16(a0, a1);
         q1[h] = pack16(b0, b1);
         q2[h] = pack16(c0, c1);
