@@ -681,7 +681,7 @@ def measure_batched(env, args, wl, steps, warmup, quick):
             return W16_OPS * K * nit * ncb
     else:
         if wl == "c3":
-            specs = c3_specs(args.c3_per_k if not quick else min(args.c3_per_k, 32))
+            specs = c3_specs(args.c3_per_k)  # (the same batch in the configs block of the default run and as --workload c3)
             dt, max_iter, is8 = np.int16, 8, False
             n_el = c3_elems(specs)
             pin_in = b.PinnedArray((n_el,), dt)

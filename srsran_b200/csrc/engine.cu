@@ -222,6 +222,8 @@ int Engine::create(Engine** out, int device)
     e->opt_fused_slice = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_SCAN"))
     e->opt_scan = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_SCAN_CPG"))
+    e->opt_scan_cpg = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_SCAN_FUSED"))
     e->opt_scan_fused = atoi(ev) != 0;
   cudaError_t ce = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
@@ -782,7 +784,9 @@ int Engine::build_plan(Plan& p)
       }
       const int n_groups = cls[only].n_slots / (64 / kWinClasses[only].lanes);
       const int items    = 4 * L.scan_lay[only].n_chunks + 2;
-      const int cpg      = std::min(items, max_ctas[only] * num_sms / std::max(1, n_groups));
+      // CTAs per group: one per phase-A item at least; more (up to one per output tile) spread the tiles of phase B over more SMs
+      const int want     = opt_scan_cpg > 0 ? opt_scan_cpg : std::max(items, L.scan_lay[only].n_tiles);
+      const int cpg      = std::min(want, max_ctas[only] * num_sms / std::max(1, n_groups));
       if (cpg >= 4) {
         L.scan_fused_cls = only;
         L.scan_cpg       = cpg;
@@ -1329,7 +1333,7 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   kb.put(*cfg);
   kb.put(flags);
   kb.put(d_llr);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg);
   if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
     // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
     rc = launch_plan();
@@ -1401,7 +1405,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
   bool       reusable = true;
   kb.put('T');
   kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg);
   for (uint32_t t = 0; t < nof_tb; t++) {
     const srslte_b200_tb_t& u = tbs[t];
     if (u.softbuffer)

@@ -104,6 +104,7 @@ public:
   DevBuf<int>      d_parked; // fused kernel: groups whose blocks the Fast16 monitor parked for the exact-arithmetic launch
   DevBuf<int32_t>  d_scanacc; // ... and the range-monitor accumulators of their groups
   DevBuf<int32_t>  d_scan;   // time-parallel latency kernels (map_scan.cuh): transfer matrices, boundary states, monitor records
+  int              opt_scan_cpg = 0;        // k_scan_fused: CTAs per group (0: chosen from the shape)
   bool             opt_scan_launch = false; // the per-half-iteration pair k_scan_mat + k_scan_out where k_scan_fused does not apply (transport blocks): off, k_map_lat's fewer launches win there
   bool             opt_scan_fused = true; // ... and, for a batch that is one run_all class, all half-iterations in ONE cooperative launch (k_scan_fused)
   bool             opt_scan = true;  // int16 classes of at most kScanMaxGroups groups: k_scan_mat + k_scan_out instead of k_map_lat
