@@ -638,11 +638,18 @@ __global__ void __launch_bounds__(384, 1) k_map_fused(const FusedArgs a)
       // with 1776 warps ending their slices together is quadratic: measured 7x slower than no slicing at all)
       if (lane == 0) {
         int* avail = reinterpret_cast<int*>(a.counters + a.ctr_avail);
-        if (atomicAdd(avail, -1) + n_groups <= 0) {
+        gi         = -1;
+        for (;;) {
+          if (atomicAdd(avail, -1) + n_groups > 0) {
+            gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
+            break;
+          }
+          // No credit: give the decrement back.  Another warp's transient decrement may have hidden a credit from a third
+          // one in the meantime (A finds nothing, B publishes an entry, B finds "nothing" because of A) -- whoever gives back
+          // LAST sees the true count, so look again before leaving: no entry is ever stranded
           atomicAdd(avail, 1);
-          gi = -1;
-        } else {
-          gi = (int)atomicAdd(&a.counters[a.ctr_fetch], 1u);
+          if (*(volatile int*)avail + n_groups <= 0)
+            break;
         }
         if (gi >= n_groups) {
           volatile int* slot_q = a.queue + (gi - n_groups);
