@@ -1110,7 +1110,7 @@ int Engine::launch_plan()
     CUDA_OK(cudaEventRecord(e1, stream));
     last_launches++;
     last_map_launches++;
-    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, 0};
+    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, 0, d_crctab.ptr};
     k_decide_crc<<<(L.n_old + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
@@ -1183,7 +1183,7 @@ int Engine::launch_plan()
       CUDA_OK(cudaGetLastError());
       last_launches++;
     }
-    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it};
+    DecideArgs da{d_lists.ptr + off_old, L.n_old, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_cbout.ptr, d_counters.ptr, (int)it, d_crctab.ptr};
     k_decide_crc<<<(L.n_old + kDecideWarps - 1) / kDecideWarps, kDecideWarps * 32, 0, stream>>>(da);
     CUDA_OK(cudaGetLastError());
     last_launches++;
@@ -1191,7 +1191,7 @@ int Engine::launch_plan()
 
   // ---- transport block assembly + CRC24A + HARQ bookkeeping
   if (L.n_tbs > 0) {
-    TbArgs ta{d_tbs.ptr, L.n_tbs, d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr};
+    TbArgs ta{d_tbs.ptr, L.n_tbs, d_cbs.ptr, d_state.ptr, d_cbout.ptr, d_res.ptr, d_crctab.ptr};
     k_tb_finish<<<L.n_tbs, kTbThreads, 0, stream>>>(ta);
     CUDA_OK(cudaGetLastError());
     last_launches++;

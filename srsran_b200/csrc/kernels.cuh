@@ -1027,11 +1027,66 @@ __device__ __forceinline__ uint32_t warp_crc24(uint32_t nbytes, const uint32_t* 
   return __shfl_sync(0xffffffffu, crc, 0);
 }
 
+// CRC24 of `nbytes` bytes in shared memory by a whole CTA of NT threads (every thread calls it; result in every thread): the
+// chunk scheme of warp_crc24 with NT chunks -- a 9.4 KB transport block is 37 byte steps per thread instead of 295 for the
+// lanes of one warp, whose two dependent shared-memory loads per byte made the CRC 20 of k_tb_finish's 45 us.  The chunk
+// constants x^(8 chunk 2^l) mod g are computed here (square and multiply by thread 0, ~20 polynomial products).
+// s_x: NT / 32 + 8 words of shared memory.
+template <int NT>
+__device__ __forceinline__ uint32_t cta_crc24(uint32_t nbytes, const uint8_t* bytes, const uint32_t* tab, uint32_t poly, uint32_t* s_x)
+{
+  constexpr int  kLevels = NT == 256 ? 8 : NT == 128 ? 7 : 5;
+  const int      g = threadIdx.x, lane = g & 31, wid = g >> 5;
+  const uint32_t cbk = (nbytes + NT - 1) / NT, pad = NT * cbk - nbytes;
+  if (g == 0) {
+    uint32_t r = 1u, base = 0x100u; // x^0, x^8
+    for (uint32_t e = cbk; e; e >>= 1) {
+      if (e & 1u)
+        r = crc24_mulmod(r, base, poly);
+      base = crc24_mulmod(base, base, poly);
+    }
+    s_x[NT / 32] = r; // x^(8 cbk)
+    for (int lv = 1; lv < kLevels; lv++) {
+      r                 = crc24_mulmod(r, r, poly);
+      s_x[NT / 32 + lv] = r;
+    }
+  }
+  uint32_t crc = 0;
+  for (uint32_t q = 0; q < cbk; q++) {
+    const uint32_t pos = (uint32_t)g * cbk + q;
+    if (pos >= pad)
+      crc = ((crc << 8) ^ tab[((crc >> 16) & 0xffu) ^ bytes[pos - pad]]) & 0xffffffu;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int lv = 0; lv < 5; lv++) {
+    const int      l     = 1 << lv;
+    const uint32_t other = __shfl_down_sync(0xffffffffu, crc, l); // chunk(s) to the right
+    if ((lane & (2 * l - 1)) == 0)
+      crc = crc24_mulmod(crc, s_x[NT / 32 + lv], poly) ^ other;
+  }
+  if (lane == 0)
+    s_x[wid] = crc;
+  __syncthreads();
+  crc = lane < NT / 32 ? s_x[lane] : 0u;
+#pragma unroll
+  for (int lv = 5; lv < kLevels; lv++) {
+    const int      l     = 1 << (lv - 5);
+    const uint32_t other = __shfl_down_sync(0xffffffffu, crc, l);
+    if ((lane & (2 * l - 1)) == 0)
+      crc = crc24_mulmod(crc, s_x[NT / 32 + lv], poly) ^ other;
+  }
+  return __shfl_sync(0xffffffffu, crc, 0);
+}
+
 // copies both CRC24 byte tables from constant to shared memory (call with all threads of the block, then sync)
-__device__ __forceinline__ void load_crc_tables(uint32_t (*s_tab)[256])
+// g_tab: the engine's copy of the two tables in global memory.  Constant memory serves ONE address per warp and access: 512
+// different words are 512 serialised constant-cache accesses, most of them misses -- 30 of the 50 us k_tb_finish took for one
+// transport block; from global memory the same copy is two coalesced loads per thread
+__device__ __forceinline__ void load_crc_tables(uint32_t (*s_tab)[256], const uint32_t* g_tab = nullptr)
 {
   for (int i = threadIdx.x; i < 512; i += blockDim.x)
-    s_tab[i >> 8][i & 255] = c_crc_tab[i >> 8][i & 255];
+    s_tab[i >> 8][i & 255] = g_tab ? g_tab[i] : c_crc_tab[i >> 8][i & 255];
 }
 
 struct DecideArgs {
@@ -1044,6 +1099,7 @@ struct DecideArgs {
   uint32_t*      counters; // [0]: half-iterations replayed with the exact policy, [1]: half-iterations run,
                            // [4 + t]: code blocks still undecided after half-iteration t of this batch
   int            iter;     // half-iteration index t of this launch within the batch
+  const uint32_t* crc_tab; // [2][256] CRC24A, CRC24B byte tables in global memory
 };
 
 // One warp per code block.  Hard decisions (win.h:925-993 / gen.c:260-277): the a-posteriori LLRs sit in lane
@@ -1113,7 +1169,7 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
   if (!__syncthreads_or(active))
     return; // none of this block's code blocks is still being decoded
   if (__syncthreads_or(need && d.crc_poly != 0)) { // (run_all semantics: no CRC, the tables are not needed)
-    load_crc_tables(s_tab);
+    load_crc_tables(s_tab, a.crc_tab);
     __syncthreads();
   }
   if (!active)
@@ -1431,11 +1487,13 @@ struct TbArgs {
   const CbState* state;
   const uint8_t* cb_out;
   TbResult*      res;
+  const uint32_t* crc_tab; // [2][256] CRC24A, CRC24B byte tables in global memory
 };
 
 // One CTA per transport block: assemble the payload (sch.c:390,422-424,462-467), TB CRC24A (sch.c:546-552), HARQ
 // bookkeeping (sch.c:469-484).  All threads copy; warp 0 computes the CRC over the assembled bytes.
 constexpr int kTbThreads = 256;
+constexpr uint32_t kTbStage = 38 * 1024; // bytes of a transport block staged in shared memory for its CRC (TBS <= 299 856 bits: LTE's largest)
 __global__ void __launch_bounds__(kTbThreads) k_tb_finish(const TbArgs a)
 {
   __shared__ uint32_t s_tab[2][256];
@@ -1446,44 +1504,47 @@ __global__ void __launch_bounds__(kTbThreads) k_tb_finish(const TbArgs a)
   uint8_t*    data = t.data;
   uint8_t*    hdat = t.hdata;
   uint8_t*    hcrc = t.hcrc;
-  load_crc_tables(s_tab);
+  load_crc_tables(s_tab, a.crc_tab);
   if (tid == 0) {
-    uint32_t ok = 0, it = 0;
-    for (uint32_t c = 0; c < t.C; c++) {
-      const uint32_t cb = t.first_cb + c;
-      if (a.cbs[cb].skip) {
-        ok |= 1u << c;
-      } else {
-        const CbState s = a.state[cb];
-        if (s.crc_ok)
-          ok |= 1u << c;
-        it += s.n_iter;
-      }
+    s_ok   = 0;
+    s_iter = 0;
+  }
+  __syncthreads();
+  // one thread per code block: the descriptor / state loads of a block are independent of the others', and so are the copies
+  // of the blocks' bytes below (a loop over the blocks paid four dependent round trips per block: 45 of the kernel's 52 us)
+  __shared__ const uint8_t* s_src[32];
+  __shared__ uint32_t       s_off[32], s_nb[32];
+  if ((uint32_t)tid < t.C) {
+    const uint32_t c    = tid;
+    const uint32_t cb   = t.first_cb + c;
+    const CbDev    d    = a.cbs[cb];
+    const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
+    s_off[c] = c * rlen;
+    if (d.skip) {
+      atomicOr(&s_ok, 1u << c);
+      s_src[c] = hdat + (size_t)c * 768;
+      s_nb[c]  = rlen;
+    } else {
+      const CbState st = a.state[cb];
+      if (st.crc_ok)
+        atomicOr(&s_ok, 1u << c);
+      atomicAdd(&s_iter, st.n_iter);
+      s_src[c] = a.cb_out + d.out_off;
+      // the reference writes K/8 bytes per CB; all but the last CB's trailing CRC bytes are overwritten by the
+      // next CB's copy, so write payload only, plus the 3 CRC bytes of the last CB
+      s_nb[c] = (c + 1 == t.C) ? d.K / 8 : rlen;
     }
-    s_ok   = ok;
-    s_iter = it;
   }
   // data[tbs/8 .. +2] = 0 happens before the CB loop in the reference; the payload copies below overwrite it
   if (tid < 3)
     data[t.tbs / 8 + tid] = 0;
   __syncthreads();
   const uint32_t ok_mask = s_ok;
-  for (uint32_t c = 0; c < t.C; c++) {
-    const uint32_t cb   = t.first_cb + c;
-    const CbDev    d    = a.cbs[cb];
-    const uint32_t rlen = t.rlen_bytes[c < t.C1 ? 0 : 1];
-    uint8_t*       dst  = data + (size_t)c * rlen;
-    if (d.skip) {
-      for (uint32_t i = tid; i < rlen; i += kTbThreads)
-        dst[i] = hdat[(size_t)c * 768 + i];
-    } else {
-      const uint8_t* src = a.cb_out + d.out_off;
-      // the reference writes K/8 bytes per CB; all but the last CB's trailing CRC bytes are overwritten by the
-      // next CB's copy, so write payload only, plus the 3 CRC bytes of the last CB
-      const uint32_t nb = (c + 1 == t.C) ? d.K / 8 : rlen;
-      for (uint32_t i = tid; i < nb; i += kTbThreads)
-        dst[i] = src[i];
-    }
+#pragma unroll 8
+  for (uint32_t idx = tid; idx < t.C * 768u; idx += kTbThreads) { // (a block has at most 768 bytes; the regions are disjoint)
+    const uint32_t c = idx / 768u, i = idx - c * 768u;
+    if (i < s_nb[c])
+      data[(size_t)s_off[c] + i] = s_src[c][i];
   }
   __syncthreads();
   const bool all_ok = ok_mask == (t.C >= 32 ? 0xffffffffu : ((1u << t.C) - 1u));
@@ -1500,11 +1561,34 @@ __global__ void __launch_bounds__(kTbThreads) k_tb_finish(const TbArgs a)
       }
     }
   }
+  // The transport block's bytes for the CRC come through shared memory: fetched by the whole CTA with independent loads (one
+  // round trip), not byte by byte from global memory inside the CRC recurrence of one warp
+  __shared__ __align__(16) uint8_t s_tb[kTbStage];
+  const uint32_t     n_tb   = t.tbs / 8;
+  const bool         staged = all_ok && n_tb <= kTbStage;
+  if (staged) {
+    if ((reinterpret_cast<uintptr_t>(data) & 3u) == 0) {
+      const uint32_t* d32 = reinterpret_cast<const uint32_t*>(data);
+      uint32_t*       s32 = reinterpret_cast<uint32_t*>(s_tb);
+#pragma unroll 8
+      for (uint32_t i = tid; i < (n_tb + 3) / 4; i += kTbThreads)
+        s32[i] = d32[i]; // (the last word may reach into the three CRC bytes that follow the payload: written above)
+    } else {
+#pragma unroll 8
+      for (uint32_t i = tid; i < n_tb; i += kTbThreads)
+        s_tb[i] = data[i];
+    }
+  }
+  __syncthreads();
+  __shared__ uint32_t s_x[kTbThreads / 32 + 8];
+  uint32_t crc_cta = 0;
+  if (staged) // (uniform over the CTA)
+    crc_cta = cta_crc24<kTbThreads>(n_tb, s_tb, s_tab[0], kCrc24A, s_x);
   if (tid < 32) {
     int32_t  ret    = -1;
     uint32_t par_rx = 0;
     if (all_ok) {
-      par_rx = warp_crc24(t.tbs / 8, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return data[b]; });
+      par_rx = staged ? crc_cta : warp_crc24(n_tb, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return data[b]; });
       const uint32_t o      = t.tbs / 8;
       const uint32_t par_tx = ((uint32_t)data[o] << 16) | ((uint32_t)data[o + 1] << 8) | data[o + 2];
       ret                   = (par_rx == par_tx && par_rx != 0) ? 0 : -1;
