@@ -1114,31 +1114,34 @@ template <int NQ>
 __device__ __forceinline__ void decide_rows(const int16_t* post, uint32_t W, u32* bits, uint32_t wpr, int lane)
 {
   constexpr uint32_t N = 8 * NQ;
-  uint4              cur[NQ], nxt[NQ];
-  auto load = [&](uint32_t r0, uint4 (&v)[NQ]) {
-    const uint32_t p = r0 + lane;
+  // kAhead chunks of 32 rows in flight: a lone warp pays the whole memory latency of every batch of loads (one chunk at a
+  // time was 12 round trips for K = 5824; the decision kernel sits on the per-TTI latency path after every half-iteration)
+  constexpr int kAhead = NQ == 4 ? 3 : 6;
+  uint4         v[kAhead][NQ];
+  for (uint32_t r0 = 0; r0 < W; r0 += 32 * kAhead) {
 #pragma unroll
-    for (int q = 0; q < NQ; q++)
-      v[q] = p < W ? *reinterpret_cast<const uint4*>(post + (size_t)p * N + 8 * q) : make_uint4(0, 0, 0, 0);
-  };
-  load(0, cur);
-  for (uint32_t r0 = 0; r0 < W; r0 += 32) {
-    if (r0 + 32 < W)
-      load(r0 + 32, nxt);
+    for (int c = 0; c < kAhead; c++) {
+      const uint32_t p = r0 + 32 * c + lane;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) {
-      const u32 ww[4] = {cur[q].x, cur[q].y, cur[q].z, cur[q].w};
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-        const int32_t val = (e & 1) ? hi16(ww[e >> 1]) : lo16(ww[e >> 1]);
-        const u32     b   = __ballot_sync(0xffffffffu, val > 0);
-        if (lane == 0)
-          bits[(8 * q + e) * wpr + r0 / 32] = b;
-      }
+      for (int q = 0; q < NQ; q++)
+        v[c][q] = p < W ? *reinterpret_cast<const uint4*>(post + (size_t)p * N + 8 * q) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
-    for (int q = 0; q < NQ; q++)
-      cur[q] = nxt[q];
+    for (int c = 0; c < kAhead; c++) {
+      if (r0 + 32 * c < W) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const u32 ww[4] = {v[c][q].x, v[c][q].y, v[c][q].z, v[c][q].w};
+#pragma unroll
+          for (int e = 0; e < 8; e++) {
+            const int32_t val = (e & 1) ? hi16(ww[e >> 1]) : lo16(ww[e >> 1]);
+            const u32     b   = __ballot_sync(0xffffffffu, val > 0);
+            if (lane == 0)
+              bits[(8 * q + e) * wpr + (r0 + 32 * c) / 32] = b;
+          }
+        }
+      }
+    }
   }
 }
 
