@@ -80,6 +80,10 @@ struct Sat16 {
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_max(p_add_sat(a, b), c); }
   // max(a + b, c + d), both sums saturating
   B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_max(p_add_sat(a, b), p_add_sat(c, d)); }
+  // running maximum of a-posteriori sums (fwd_step_llr): first term, further terms, final value
+  B200_HD static u32 sum0(u32 a, u32 b) { return add(a, b); }
+  B200_HD static u32 summax(u32 a, u32 b, u32 c) { return addmax(a, b, c); }
+  B200_HD static u32 sumfin(u32 m) { return m; }
   static constexpr int kNormPeriod = 2;
   B200_HD static void normalize_now(u32 (&o)[8])
   {
@@ -116,6 +120,10 @@ struct Fast16 {
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
   B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_addmax(a, b, p_add_wrap(c, d)); }
+  // running maximum of a-posteriori sums (fwd_step_llr): first term, further terms, final value
+  B200_HD static u32 sum0(u32 a, u32 b) { return add(a, b); }
+  B200_HD static u32 summax(u32 a, u32 b, u32 c) { return addmax(a, b, c); }
+  B200_HD static u32 sumfin(u32 m) { return m; }
   static constexpr int kNormPeriod = 2;
   B200_HD static void normalize_now(u32 (&o)[8])
   {
@@ -149,6 +157,12 @@ struct Sat8 {
   // max(clamp8(a + b), clamp8(c + d)) = clamp8(max(a + b, c + d)) (the clamp is monotone; the int16 containers hold the
   // unclamped sums exactly): one wrapping add on the add-type pipe, a fused add-max and one clamp
   B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return clamp8(p_addmax(a, b, p_add_wrap(c, d))); }
+  // max_i clamp8(b_i + c_i) = clamp8(max_i (b_i + c_i)): the clamp is monotone and the int16 containers hold the sum of two
+  // int8-range values exactly, so the chain of a-posteriori sums runs unclamped (one fused add-max per term instead of
+  // add-max + min) and is clamped once at the end
+  B200_HD static u32 sum0(u32 a, u32 b) { return p_add_wrap(a, b); }
+  B200_HD static u32 summax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  B200_HD static u32 sumfin(u32 m) { return clamp8(m); }
   static constexpr int kNormPeriod = 1;
   B200_HD static void normalize_now(u32 (&o)[8])
   {

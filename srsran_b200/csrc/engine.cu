@@ -214,6 +214,10 @@ int Engine::create(Engine** out, int device)
     e->opt_latency = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED"))
     e->opt_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_GEN_FUSED"))
+    e->opt_gen_fused = atoi(ev) != 0;
+  if (const char* ev = getenv("SRSLTE_B200_FUSED_SPREAD"))
+    e->opt_fused_spread = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
     e->opt_fused_warps = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_L2_PERSIST"))
@@ -558,6 +562,8 @@ struct ClassRun {
 struct LaunchState {
   bool      valid = false;
   int       n_cb = 0, n_dm16 = 0, n_dm8 = 0, n_plain = 0, n_pairs = 0, gen_threads = 0, n_old = 0, n_tbs = 0;
+  int       n_genf = 0, genf_kp = 0; // pairs of the fused generic kernel (map_gen_fused.cuh), row length of its shared arrays
+  size_t    off_genf = 0;
   size_t    off_dm16 = 0, off_dm8 = 0, off_plain = 0, off_gen = 0, off_old = 0, ctr_fetch0 = 0, n_counters = 0;
   uint32_t  max_iter = 0, iter0 = 0;
   bool      prepare = true;
@@ -712,8 +718,8 @@ int Engine::build_plan(Plan& p)
         cls[c].no_crc = false;
   }
   // generic decoder: pairs of equal K
-  std::vector<int> gen_pairs;
-  uint32_t         gen_max_k = 0;
+  std::vector<int> gen_pairs, genf_pairs; // (per-half-iteration kernel, fused kernel)
+  uint32_t         gen_max_k = 0, genf_max_k = 0;
   {
     std::vector<int> ids;
     for (int i : active)
@@ -725,20 +731,27 @@ int Engine::build_plan(Plan& p)
       ws_elems += 6ull * p.cbs[i].ps;
     }
     for (size_t i = 0; i < ids.size();) {
-      gen_max_k = std::max(gen_max_k, p.cbs[ids[i]].K);
-      if (i + 1 < ids.size() && p.cbs[ids[i + 1]].K == p.cbs[ids[i]].K) {
-        gen_pairs.push_back(ids[i]);
-        gen_pairs.push_back(ids[i + 1]);
+      const uint32_t K = p.cbs[ids[i]].K;
+      // short blocks (everything SRSLTE_TDEC_AUTO sends to the generic decoder): one CTA per pair for the whole run
+      const bool        fz = opt_gen_fused && K <= (uint32_t)kGenFusedMaxK;
+      std::vector<int>& v  = fz ? genf_pairs : gen_pairs;
+      (fz ? genf_max_k : gen_max_k) = std::max(fz ? genf_max_k : gen_max_k, K);
+      if (i + 1 < ids.size() && p.cbs[ids[i + 1]].K == K) {
+        v.push_back(ids[i]);
+        v.push_back(ids[i + 1]);
         i += 2;
       } else {
-        gen_pairs.push_back(ids[i]);
-        gen_pairs.push_back(-1);
+        v.push_back(ids[i]);
+        v.push_back(-1);
         i += 1;
       }
     }
   }
   const size_t off_gen = add_list(gen_pairs);
   const int    n_pairs = (int)gen_pairs.size() / 2;
+  const size_t off_genf = add_list(genf_pairs);
+  L.n_genf   = (int)genf_pairs.size() / 2;
+  L.genf_kp  = (int)genf_max_k + 4;
 
   // ---- which kernel runs a class: the latency-shaped per-half-iteration kernel when its groups leave most SMs empty (one
   //      subframe or a few), else ONE persistent fused launch for all half-iterations
@@ -771,7 +784,7 @@ int Engine::build_plan(Plan& p)
         n_active++;
         only = c;
       }
-    if (n_active == 1 && n_pairs == 0 && L.cls_scan[only] && cls[only].no_crc && opt_scan_fused) {
+    if (n_active == 1 && n_pairs == 0 && genf_pairs.empty() && L.cls_scan[only] && cls[only].no_crc && opt_scan_fused) {
       static int max_ctas[2] = {-1, -1}; // co-resident CTAs per SM of the kernel (the cooperative launch needs the whole grid resident)
       if (max_ctas[only] < 0) {
         int nb = 0;
@@ -802,7 +815,7 @@ int Engine::build_plan(Plan& p)
     for (int k = 0; k < 4; k++)
       if (d.N == kWinClasses[k].lanes && d.bits == kWinClasses[k].bits)
         c = k;
-    if (c < 0 || !cls_fused[c])
+    if (c < 0 ? !(opt_gen_fused && d.K <= (uint32_t)kGenFusedMaxK) : !cls_fused[c])
       old_path.push_back(i);
   }
   const size_t off_old = add_list(old_path);
@@ -866,7 +879,12 @@ int Engine::build_plan(Plan& p)
         // one checkpoint (256 words per warp) per 8-step tile + the start state, per RESIDENT warp
         // CTA size (measured, profiles/README.md): batches without early stop run 5 % faster as three 4-warp CTAs per SM;
         // with early stop (blocks finish at different times) one 12-warp CTA per SM is ahead
-        const int wpc = opt_fused_warps > 0 ? opt_fused_warps : (cls[c].no_crc ? 4 : 12);
+        int wpc = opt_fused_warps > 0 ? opt_fused_warps : (cls[c].no_crc ? 4 : 12);
+        // a class with fewer groups than the GPU holds resident warps: CTAs of ceil(groups / SMs) warps, so that every SM gets
+        // its share instead of groups / 12 SMs being full and the rest empty (264 groups of the 8-lane class in the all-sizes
+        // workload c3 ran on 22 SMs)
+        if (opt_fused_spread && opt_fused_warps <= 0)
+          wpc = std::max(1, std::min(wpc, (n_groups + num_sms - 1) / num_sms));
         fgeo[c] = kWinClasses[c].lanes == 8 ? fused_geometry<8>(n_groups, cls[c].max_k, num_sms, wpc)
                                             : kWinClasses[c].lanes == 16 ? fused_geometry<16>(n_groups, cls[c].max_k, num_sms, wpc)
                                                                          : fused_geometry<32>(n_groups, cls[c].max_k, num_sms, wpc);
@@ -899,7 +917,7 @@ int Engine::build_plan(Plan& p)
     return SRSLTE_B200_ERROR;
   L.n_cb = n_cb; L.n_dm16 = (int)dm16.size(); L.n_dm8 = (int)dm8.size(); L.n_plain = (int)plain.size(); L.n_pairs = n_pairs;
   L.gen_threads = gen_threads; L.n_old = (int)old_path.size(); L.n_tbs = (int)p.tbs.size();
-  L.off_dm16 = off_dm16; L.off_dm8 = off_dm8; L.off_plain = off_plain; L.off_gen = off_gen; L.off_old = off_old;
+  L.off_dm16 = off_dm16; L.off_dm8 = off_dm8; L.off_plain = off_plain; L.off_gen = off_gen; L.off_old = off_old; L.off_genf = off_genf;
   L.ctr_fetch0 = ctr_fetch0; L.n_counters = n_counters; L.max_iter = p.max_iter; L.iter0 = p.iter0; L.prepare = p.prepare;
   L.valid = true;
   return 0;
@@ -1046,6 +1064,23 @@ int Engine::launch_plan()
       e = c == 2 ? launch_fused<Sat8, 16>(a, fgeo[c], stream) : launch_fused<Sat8, 32>(a, fgeo[c], stream);
     }
     CUDA_OK(e);
+    CUDA_OK(cudaEventRecord(e1, stream));
+    last_launches++;
+    last_map_launches++;
+  }
+
+  // ---- short blocks of the generic decoder: every half-iteration, decisions, CRC and early stop in one launch, one CTA
+  //      per pair of equal-K blocks (map_gen_fused.cuh)
+  if (L.n_genf > 0) {
+    GenFusedArgs g{d_lists.ptr + L.off_genf, L.n_genf, d_cbs.ptr, d_state.ptr, d_ws.ptr, d_tails.ptr, d_qpp.ptr, d_cbout.ptr, d_crctab.ptr, d_counters.ptr, (int)p.max_iter, L.genf_kp};
+    const size_t smem = gen_fused_smem(L.genf_kp);
+    CUDA_OK(smem_attr_once((const void*)k_gen_fused, (int)gen_fused_smem(kGenFusedMaxK + 4)));
+    cudaEvent_t e0, e1;
+    if (map_event_pair(&e0, &e1))
+      return SRSLTE_B200_ERROR;
+    CUDA_OK(cudaEventRecord(e0, stream));
+    k_gen_fused<<<L.n_genf, kGenFusedThreads, smem, stream>>>(g);
+    CUDA_OK(cudaGetLastError());
     CUDA_OK(cudaEventRecord(e1, stream));
     last_launches++;
     last_map_launches++;
@@ -1333,7 +1368,7 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   kb.put(*cfg);
   kb.put(flags);
   kb.put(d_llr);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread);
   if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
     // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
     rc = launch_plan();
@@ -1405,7 +1440,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
   bool       reusable = true;
   kb.put('T');
   kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread);
   for (uint32_t t = 0; t < nof_tb; t++) {
     const srslte_b200_tb_t& u = tbs[t];
     if (u.softbuffer)
@@ -2420,6 +2455,14 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
   }
   if (!strcmp(name, "scan")) {
     ctx->e->opt_scan = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "gen_fused")) {
+    ctx->e->opt_gen_fused = value != 0;
+    return 0;
+  }
+  if (!strcmp(name, "fused_spread")) {
+    ctx->e->opt_fused_spread = value;
     return 0;
   }
   if (!strcmp(name, "scan_launch")) {

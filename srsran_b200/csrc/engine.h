@@ -113,6 +113,8 @@ public:
   int              opt_l2_persist = 0;   // experiment: 1 = L2 access policy window (persisting) over the checkpoint scratch, 2 = and no per-instruction hints on them
   int              opt_fused_slice = 21; // classes with CRC early stop: half-iterations per visit of a group, 10 x first + later (0: a group stays with its warp)
   bool             opt_fused = true; // large batches: one persistent launch per decoder class (map_fused.cuh)
+  bool             opt_gen_fused = true; // generic decoder, K <= kGenFusedMaxK: one CTA per pair of blocks for all half-iterations (map_gen_fused.cuh)
+  int              opt_fused_spread = 1; // fused kernel: smaller CTAs when a class has fewer groups than 12 per SM, so every SM gets some
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;
   PinBuf<uint8_t>  h_stage_in, h_stage_out, h_desc, h_tmaps;

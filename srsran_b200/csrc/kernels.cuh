@@ -846,6 +846,9 @@ struct Wrap16 { // turbodecoder_gen.c: plain C int16 arithmetic
   B200_HD static u32 max(u32 a, u32 b) { return p_max(a, b); }
   B200_HD static u32 addmax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
   B200_HD static u32 addmax2(u32 a, u32 b, u32 c, u32 d) { return p_addmax(a, b, p_add_wrap(c, d)); }
+  B200_HD static u32 sum0(u32 a, u32 b) { return p_add_wrap(a, b); }
+  B200_HD static u32 summax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
+  B200_HD static u32 sumfin(u32 m) { return m; }
   B200_HD static u32 out(u32 v) { return v; }
 };
 
@@ -1252,6 +1255,10 @@ __global__ void __launch_bounds__(kDecideWarps * 32) k_decide_crc(const DecideAr
   }
 }
 
+} // namespace b200
+#include "map_gen_fused.cuh"
+namespace b200 {
+
 // ------------------------------------------------------------------------------------------ soft demodulation
 // srslte_demod_soft_demodulate_{s,b} (modem/demod_soft.c:896-945) + srslte_scrambling_{s,sb}_offset
 // (scrambling/scrambling.c:43-53), the two steps between the equaliser and decode_tb (phch/pdsch.c:832-852), fused:
@@ -1584,14 +1591,20 @@ __global__ void __launch_bounds__(kTbThreads) k_tb_finish(const TbArgs a)
   }
   __syncthreads();
   __shared__ uint32_t s_x[kTbThreads / 32 + 8];
-  uint32_t crc_cta = 0;
-  if (staged) // (uniform over the CTA)
+  // ... by all threads when the block is long; a short block (the all-sizes workload c3 brings 12 000 of at most 768 bytes in
+  // one batch) is cheaper on one warp with the host's chunk constants than the CTA-wide scheme's fixed cost (constants by
+  // square and multiply in thread 0, two combination stages: ~4 us per CTA, 330 us per c3 batch)
+  const bool use_cta = staged && n_tb > 3072;
+  uint32_t   crc_cta = 0;
+  if (use_cta) // (uniform over the CTA)
     crc_cta = cta_crc24<kTbThreads>(n_tb, s_tb, s_tab[0], kCrc24A, s_x);
   if (tid < 32) {
     int32_t  ret    = -1;
     uint32_t par_rx = 0;
     if (all_ok) {
-      par_rx = staged ? crc_cta : warp_crc24(n_tb, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return data[b]; });
+      par_rx = use_cta ? crc_cta
+                       : staged ? warp_crc24(n_tb, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return s_tb[b]; })
+                                : warp_crc24(n_tb, s_tab[0], kCrc24A, t.crc_xp, [&](uint32_t b) -> uint32_t { return data[b]; });
       const uint32_t o      = t.tbs / 8;
       const uint32_t par_tx = ((uint32_t)data[o] << 16) | ((uint32_t)data[o + 1] << 8) | data[o + 2];
       ret                   = (par_rx == par_tx && par_rx != 0) ? 0 : -1;

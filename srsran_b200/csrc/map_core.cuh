@@ -58,14 +58,16 @@ B200_HD u32 fwd_step_llr(u32 (&o)[8], const u32 (&b)[8], u32 x, u32 y, u32 xy, M
   const u32 mb4 = o[1], mb5 = P::add(o[2], y), mb6 = P::add(o[5], y), mb7 = o[6];
   const u32 nw0 = P::add(o[1], xy), nw1 = P::add(o[2], x), nw2 = P::add(o[5], x), nw3 = P::add(o[6], xy);
   const u32 nw4 = P::add(o[0], xy), nw5 = P::add(o[3], x), nw6 = P::add(o[4], x), nw7 = P::add(o[7], xy);
-  u32 m1 = P::add(b[0], nw0), m0 = P::add(b[0], mb0);
-  m1 = P::addmax(b[1], nw1, m1); m0 = P::addmax(b[1], mb1, m0);
-  m1 = P::addmax(b[2], nw2, m1); m0 = P::addmax(b[2], mb2, m0);
-  m1 = P::addmax(b[3], nw3, m1); m0 = P::addmax(b[3], mb3, m0);
-  m1 = P::addmax(b[4], nw4, m1); m0 = P::addmax(b[4], mb4, m0);
-  m1 = P::addmax(b[5], nw5, m1); m0 = P::addmax(b[5], mb5, m0);
-  m1 = P::addmax(b[6], nw6, m1); m0 = P::addmax(b[6], mb6, m0);
-  m1 = P::addmax(b[7], nw7, m1); m0 = P::addmax(b[7], mb7, m0);
+  u32 m1 = P::sum0(b[0], nw0), m0 = P::sum0(b[0], mb0);
+  m1 = P::summax(b[1], nw1, m1); m0 = P::summax(b[1], mb1, m0);
+  m1 = P::summax(b[2], nw2, m1); m0 = P::summax(b[2], mb2, m0);
+  m1 = P::summax(b[3], nw3, m1); m0 = P::summax(b[3], mb3, m0);
+  m1 = P::summax(b[4], nw4, m1); m0 = P::summax(b[4], mb4, m0);
+  m1 = P::summax(b[5], nw5, m1); m0 = P::summax(b[5], mb5, m0);
+  m1 = P::summax(b[6], nw6, m1); m0 = P::summax(b[6], mb6, m0);
+  m1 = P::summax(b[7], nw7, m1); m0 = P::summax(b[7], mb7, m0);
+  m1 = P::sumfin(m1);
+  m0 = P::sumfin(m0);
   o[0] = P::max(mb0, nw0); o[1] = P::max(mb1, nw1); o[2] = P::max(mb2, nw2); o[3] = P::max(mb3, nw3);
   o[4] = P::max(mb4, nw4); o[5] = P::max(mb5, nw5); o[6] = P::max(mb6, nw6); o[7] = P::max(mb7, nw7);
   const u32 d = P::sub(m1, m0);

@@ -974,6 +974,85 @@ def test_fused_kernel_transport_blocks_at_scale(port):
             j[0].close()
 
 
+# ----------------------------------------------------------------------------------------- short blocks: the fused generic kernel
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,ncb,nit,amps", [(40, 1001, 6, (100, 3000)), (400, 777, 5, (100, 20000, 32767)), (208, 2, 3, (300,)), (104, 1, 8, (50,)),
+                                            (320, 1500, 1, (600,)), (360, 901, 2, (150, 9000))])
+def test_generic_decoder_fused_kernel_at_scale(port, K, ncb, nit, amps):
+    """k_gen_fused (K <= 400 under SRSLTE_TDEC_AUTO): batches of many CTAs with an odd block at the end (a pair with one half
+    empty), amplitudes up to the int16 wrap cases of turbodecoder_gen.c; decided bytes of EVERY block against the oracle,
+    the extrinsic planes of some against the oracle's arrays, and everything against the per-half-iteration kernel"""
+    rng = np.random.default_rng(K * 7 + ncb)
+    base = [bpsk_awgn_llr(rng, port.tcod_encode(rng.integers(0, 2, K, dtype=np.uint8)), amps[i % len(amps)], 0.7 + 0.15 * (i % 4), np.int16) for i in range(7)]
+    idx = _spread(ncb, len(base))
+    batch = np.ascontiguousarray(np.stack([base[j] for j in idx]))
+    hs, want = [], []
+    for x in base:
+        h = port.tdec_new(TDEC_AUTO, False)
+        rc, w = port.tdec_run_all(h, x, nit, K)
+        assert rc == 0
+        hs.append(h)
+        want.append(w)
+    c = b.Context(0)
+    try:
+        got = c.tdec_batch(batch, K, nit)
+        assert c.last_map_launches() == 1
+        for i in range(ncb):
+            assert (got[i] == want[idx[i]]).all(), (K, i)
+        for cb in sorted({0, 1, ncb // 2, ncb - 2, ncb - 1} & set(range(ncb))):
+            plane, w = _expected_planes(port, hs[idx[cb]], K, 0, nit, 16)
+            g = c.debug_read_plane(cb, plane, K)
+            assert (g == w).all(), "K=%d n=%d block %d: %d LLRs differ" % (K, nit, cb, int((g != w).sum()))
+        c.set_option("gen_fused", 0)
+        old = c.tdec_batch(batch, K, nit)
+        assert (old == got).all()
+    finally:
+        c.close()
+        for h in hs:
+            port.tdec_del(h)
+
+
+@pytest.mark.gpu
+def test_generic_decoder_fused_kernel_transport_blocks(port):
+    """single-block transport blocks of every generic-decoder size (40..400) in one batch, 9 of each with noise levels that
+    make blocks stop after 1..8 half-iterations or fail: return codes, bytes, CRC flags and half-iteration counts of every
+    block against the oracle; pairs whose halves stop at different times are the rule here"""
+    rng = np.random.default_rng(4004)
+    sizes = [K for K in all_K() if K <= 400]
+    cases, base = [], {}
+    for K in sizes:
+        tbs = K - 24
+        G = 2 * ((3 * K + 12) // 2 + (K // 8 % 3) * 30)
+        for j, sg in enumerate((0.5, 0.8, 1.1)):
+            _, llr = _tb_inputs(port, rng, tbs, 2, G, 0, np.int16, 100, sg)
+            sbp = port.softbuffer_new()
+            base[(K, j)] = (llr, G, port.decode_tb(sbp, tbs, 2, 0, llr, 8))
+            port.softbuffer_del(sbp)
+        for r in range(9):
+            cases.append((K, (r * 2 + K // 8) % 3))
+    n = len(cases)
+    t = b.make_tbs(n)
+    outs = np.zeros((n, 400 // 8 + 22), np.uint8)
+    for i, (K, j) in enumerate(cases):
+        llr, G, _ = base[(K, j)]
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = llr.ctypes.data, G, K - 24, 2, 0, outs[i].ctypes.data
+    c = b.Context(0)
+    try:
+        c.decode_tbs(t, False, 8)
+        assert c.last_map_launches() == 1
+        seen = set()
+        for i, (K, j) in enumerate(cases):
+            rc, d, nit, avg, crc = base[(K, j)][2]
+            nb = (K - 24) // 8 + 3
+            assert t[i].ret == rc, (K, i)
+            assert (outs[i][:nb] == d[:nb]).all(), (K, i)
+            assert t[i].cb_noi[0] == nit[0] and t[i].cb_crc[0] == crc[0], (K, i)
+            seen.add(int(nit[0]))
+        assert len(seen) >= 4
+    finally:
+        c.close()
+
+
 # ----------------------------------------------------------------------------------------- intermediate LLRs, not only decided bytes
 def _expected_planes(port, h, K, N, n_done, bits):
     """what the engine's a-priori (plane 2) / decoder-2 input (plane 3) planes must hold after n_done half-iterations, from the
