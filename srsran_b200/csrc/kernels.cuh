@@ -849,6 +849,7 @@ struct Wrap16 { // turbodecoder_gen.c: plain C int16 arithmetic
   B200_HD static u32 sum0(u32 a, u32 b) { return p_add_wrap(a, b); }
   B200_HD static u32 summax(u32 a, u32 b, u32 c) { return p_addmax(a, b, c); }
   B200_HD static u32 sumfin(u32 m) { return m; }
+  B200_HD static u32 cand(u32 a, u32 g) { return p_add_wrap(a, g); }
   B200_HD static u32 out(u32 v) { return v; }
 };
 

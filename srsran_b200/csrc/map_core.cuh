@@ -54,10 +54,10 @@ template <class P, class Mon>
 B200_HD u32 fwd_step_llr(u32 (&o)[8], const u32 (&b)[8], u32 x, u32 y, u32 xy, Mon& mon)
 {
   // branch candidates: mb = hypothesis 0, nw = hypothesis 1
-  const u32 mb0 = o[0], mb1 = P::add(o[3], y), mb2 = P::add(o[4], y), mb3 = o[7];
-  const u32 mb4 = o[1], mb5 = P::add(o[2], y), mb6 = P::add(o[5], y), mb7 = o[6];
-  const u32 nw0 = P::add(o[1], xy), nw1 = P::add(o[2], x), nw2 = P::add(o[5], x), nw3 = P::add(o[6], xy);
-  const u32 nw4 = P::add(o[0], xy), nw5 = P::add(o[3], x), nw6 = P::add(o[4], x), nw7 = P::add(o[7], xy);
+  const u32 mb0 = o[0], mb1 = P::cand(o[3], y), mb2 = P::cand(o[4], y), mb3 = o[7];
+  const u32 mb4 = o[1], mb5 = P::cand(o[2], y), mb6 = P::cand(o[5], y), mb7 = o[6];
+  const u32 nw0 = P::cand(o[1], xy), nw1 = P::cand(o[2], x), nw2 = P::cand(o[5], x), nw3 = P::cand(o[6], xy);
+  const u32 nw4 = P::cand(o[0], xy), nw5 = P::cand(o[3], x), nw6 = P::cand(o[4], x), nw7 = P::cand(o[7], xy);
   u32 m1 = P::sum0(b[0], nw0), m0 = P::sum0(b[0], mb0);
   m1 = P::summax(b[1], nw1, m1); m0 = P::summax(b[1], mb1, m0);
   m1 = P::summax(b[2], nw2, m1); m0 = P::summax(b[2], mb2, m0);

@@ -244,6 +244,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
   mon_a.reset();
   mon_h.reset();
   u32 st[8];
+  // the recursion steps run with the cheaper rules for normalised input metrics where the policy has them (Sat8F, arith.cuh);
+  // a step whose input is NOT normalised is followed by PS::fix (marked "un-normalised input" below)
+  using PS = typename StepPolicy<P>::type;
 
   // =============================================================== backward
   // pass 0: warm-up, steps 39..0 of the lane's own sub-block from the all-"unknown" state (win.h:622-630)
@@ -284,7 +287,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
         for (int i = (W & 7) - 1; i >= 0; i--) {
           u32 x, y;
           row(tb, i, x, y);
-          bwd_step<P>(st, x, y, P::add(x, y));
+          bwd_step<PS>(st, x, y, P::add(x, y));
+          if (PS::kNeedsFix && i == (W & 7) - 1)
+            PS::fix(st); // un-normalised input: the neighbour's estimate / the tail trellis
           if (i == 0)
             ck_store(t, st);
           if (P::kMonitor && (i & 1) == 0)
@@ -296,6 +301,7 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       }
     }
     const bool main_pass = pass == 1;
+    bool       raw_in    = main_pass && (W & 7) == 0; // the main pass starts from an un-normalised state
 #pragma unroll 1
     for (; t >= 0; t--) {
       const u32* tb = acquire(kBeta);
@@ -303,7 +309,11 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       for (int i = 7; i >= 0; i--) {
         u32 x, y;
         row(tb, i, x, y);
-        bwd_step<P>(st, x, y, P::add(x, y));
+        bwd_step<PS>(st, x, y, P::add(x, y));
+        if (PS::kNeedsFix && i == 7 && raw_in) {
+          PS::fix(st); // un-normalised input: the neighbour's estimate / the tail trellis
+          raw_in = false;
+        }
         if (i == 0 && main_pass)
           ck_store(t, st);
         // warm-up, k = 38 (t = 4, i = 6): the first two steps start from eight equal values (spread 0, covered by g)
@@ -344,7 +354,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       for (int i = i0; i < i1; i++, kk++) {
         u32 x, y;
         row(tb, i, x, y);
-        fwd_step<P>(st, x, y, P::add(x, y));
+        fwd_step<PS>(st, x, y, P::add(x, y));
+        if (PS::kNeedsFix && kk == 1)
+          PS::fix(st); // un-normalised input: step 0 is not followed by a normalisation
         if (P::kMonitor && (kk & 1) == 0 && kk > 2)
           mon_a.track(st);
         if ((kNP == 1 || (kk & 1) == 0) && kk != 0)
@@ -414,7 +426,10 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       llr = llr_factored<P>(al, b, x, y, xy, mon);
       fwd_step<P>(al, x, y, xy);
     } else { // saturating arithmetic: the operation order of the reference is part of the result
-      llr = fwd_step_llr<P>(al, b, x, y, xy, mon);
+      if (PS::kNeedsFix && i == 1 && p == 1)
+        llr = fwd_step_llr<P>(al, b, x, y, xy, mon); // un-normalised input: step 0 is not followed by a normalisation
+      else
+        llr = fwd_step_llr<PS>(al, b, x, y, xy, mon);
     }
     if (P::kMonitor && (i & 1) == 0)
       mon.track(al);
@@ -491,7 +506,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
     for (int kk = 7; kk >= 1; kk--) {
       u32 x, y;
       row(tb, kk, x, y);
-      bwd_step<P>(st, x, y, P::add(x, y));
+      bwd_step<PS>(st, x, y, P::add(x, y));
+      if (PS::kNeedsFix && kk == 7 && !(8 * (t + 1) < W))
+        PS::fix(st); // un-normalised input: beta[W]
       if (kk >= 5) {
         ysp[64 * (kk - 5)]      = make_uint4(st[0], st[1], st[2], st[3]);
         ysp[64 * (kk - 5) + 32] = make_uint4(st[4], st[5], st[6], st[7]);
@@ -547,7 +564,9 @@ __device__ __forceinline__ bool fused_half(FusedWarp<N / 2>& w, const FusedArgs&
       for (int kk = nv - 1; kk > i; kk--) { // -> beta_{8t+kk}, normalised on the way except the one that is used
         u32 x, y;
         row(tb, kk, x, y);
-        bwd_step<P>(b, x, y, P::add(x, y));
+        bwd_step<PS>(b, x, y, P::add(x, y));
+        if (PS::kNeedsFix && kk == nv - 1)
+          PS::fix(b); // un-normalised input: beta[W]
         if (kk > i + 1 && (kNP == 1 || (kk & 1) == 0))
           P::normalize_now(b);
       }

@@ -238,3 +238,60 @@ extern "C" uint32_t emul_glue_sub(int bits, uint32_t a, uint32_t b, int sat_lo, 
 {
   return bits == 16 ? Sat16::glue_sub(a, b, sat_lo, sat_hi) : Sat8::glue_sub(a, b, sat_lo, sat_hi);
 }
+
+// Sat8F (arith.cuh): the cheaper step rules for normalised input metrics.  Random trials; returns the number of mismatches:
+//   * input metrics normalised (normalize_max: every metric in [-128, 0], the maximum 0): bwd_step / fwd_step / fwd_step_llr
+//     with Sat8F give the integers of Sat8;
+//   * arbitrary int8-range input metrics: the Sat8F step followed by fix() gives the integers of the Sat8 step.
+extern "C" int emul_sat8f_check(uint32_t seed, int n_trials)
+{
+  uint32_t r   = seed * 2654435761u + 12345u;
+  auto     rnd = [&](int lo, int hi) { // uniform in [lo, hi]
+    r = r * 1664525u + 1013904223u;
+    return lo + (int)((r >> 8) % (uint32_t)(hi - lo + 1));
+  };
+  auto edge = [&](int lo, int hi) { // the ends of the range come up often
+    const int c = rnd(0, 9);
+    return c == 0 ? lo : c == 1 ? hi : c == 2 ? lo + 1 : c == 3 ? hi - 1 : rnd(lo, hi);
+  };
+  int bad = 0;
+  for (int it = 0; it < n_trials; it++) {
+    const bool norm_in = (it & 1) == 0;
+    u32        o[8], b[8];
+    for (int i = 0; i < 8; i++) {
+      o[i] = norm_in ? pack16(edge(-128, 0), edge(-128, 0)) : pack16(edge(-128, 127), edge(-128, 127));
+      b[i] = pack16(edge(-128, 127), edge(-128, 127));
+    }
+    if (norm_in)
+      o[rnd(0, 7)] = 0; // (both halves: the maximum of a normalised vector is 0; the other entries are <= 0 either way)
+    const u32 x = pack16(edge(-128, 127), edge(-128, 127)), y = pack16(edge(-128, 127), edge(-128, 127));
+    const u32 xy = Sat8::add(x, y);
+    for (int kind = 0; kind < 2; kind++) {
+      u32 a1[8], a2[8];
+      for (int i = 0; i < 8; i++)
+        a1[i] = a2[i] = o[i];
+      if (kind == 0) {
+        bwd_step<Sat8>(a1, x, y, xy);
+        bwd_step<Sat8F>(a2, x, y, xy);
+      } else {
+        fwd_step<Sat8>(a1, x, y, xy);
+        fwd_step<Sat8F>(a2, x, y, xy);
+      }
+      if (!norm_in)
+        Sat8F::fix(a2);
+      for (int i = 0; i < 8; i++)
+        bad += a1[i] != a2[i];
+    }
+    if (norm_in) {
+      u32 a1[8], a2[8];
+      for (int i = 0; i < 8; i++)
+        a1[i] = a2[i] = o[i];
+      RangeMon  nomon;
+      const u32 l1 = fwd_step_llr<Sat8>(a1, b, x, y, xy, nomon), l2 = fwd_step_llr<Sat8F>(a2, b, x, y, xy, nomon);
+      bad += l1 != l2;
+      for (int i = 0; i < 8; i++)
+        bad += a1[i] != a2[i];
+    }
+  }
+  return bad;
+}

@@ -113,6 +113,13 @@ def test_glue_sub_semantics(emul):
     assert un(emul.emul_glue_sub(8, pk(100, -100), pk(-100, 100), 1, 0)) == (127, 56)
 
 
+def test_sat8_fast_step_rules(emul):
+    """Sat8F (arith.cuh): with normalised input metrics the saturations' upper halves are dead -- same integers as Sat8 for
+    the backward / forward / output steps; with arbitrary input metrics the step followed by fix() is the Sat8 step"""
+    for seed in range(4):
+        assert emul.emul_sat8f_check(seed, 200000) == 0
+
+
 # ----------------------------------------------------------------------------------------- k_ulsch_deinterleave
 def test_ulsch_kernel_index_arithmetic(port):
     """The tile loops of k_ulsch_deinterleave with the index functions of srsran_b200/csrc/ulsch_core.cuh (compiled here with
