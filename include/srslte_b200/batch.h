@@ -210,6 +210,10 @@ SRSLTE_B200_API uint32_t srslte_b200_last_map_launches(srslte_b200_ctx_t* ctx);
 /*          "latency" (default 1): batches that leave at most one group of code blocks per SM (one subframe or a few) run
  * the latency-shaped MAP kernel (backward and forward recursions on two warps at once, LLRs spread over four); 0 keeps the
  * throughput kernel for every batch size.  Results are identical either way. */
+/*          "gen_fused" (default 1): code blocks of the generic decoder (K <= 400 under SRSLTE_TDEC_AUTO, turbodecoder.c:381-393)
+ * run all their half-iterations, decisions and CRC checks in one launch, one CTA per pair of blocks; 0 keeps one launch per
+ * half-iteration.  "fused_spread" (default 1): the persistent MAP kernel uses smaller CTAs when a decoder class has fewer
+ * groups of code blocks than the GPU has resident warps, so that every SM gets some.  Results are identical either way. */
 SRSLTE_B200_API int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value);
 /* statistics of the last completed batch: (code block x half-iteration) units run, and how many were replayed */
 SRSLTE_B200_API uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx);
