@@ -993,9 +993,16 @@ def measure_c5(env, args, steps, warmup, quick):
     rank, world, local = env.rank, env.world, env.local
     barrier, vmax, vsum = env.barrier, env.vmax, env.vsum
     rng = np.random.default_rng(shard_seed(rank) + 500)
-    # two pools per GPU, each with half of the rank's cells: while one pool's batch decodes, the other's is copied and planned
-    pools = [CellPool(rank, world, local) for _ in range(2)]
     cells = [c for c in range(args.cells) if owner_of(c, world) == rank]
+    # several pools per GPU, each with a share of the rank's cells: while one pool's batch decodes, the others' are copied
+    # and planned.  A batch lasts as long as its slowest code block -- 0.77 ms instead of 0.29 when it holds a first HARQ
+    # transmission that fails and runs all 8 half-iterations on a lone warp (profiles/README.md) -- so two batches in flight
+    # left the host waiting on that tail; four keep copies and the other batches' kernels going meanwhile
+    n_pools = args.c5_pools if args.c5_pools > 0 else max(2, min(4, len(cells) // 4))
+    # (measured on one GPU, 20 cells: 2 pools 12.6, 3 pools 13.8, 4 pools 14.7, 5 pools 14.4, 6 pools 13.5 Gbit/s with the
+    #  persistent kernel for every batch; batches of fewer than ~100 groups of code blocks keep the engines' own choice)
+    groups_per_batch = -(-len(cells) // n_pools) * 8 * 13 // 4
+    pools = [CellPool(rank, world, local, latency=0 if groups_per_batch >= 100 else None) for _ in range(n_pools)]
     tbs, Qm, G = 75376, 6, 90000
     rows, nsym, qp = 1200, 12, (36, 20, 57)
     n_q = rows * nsym * Qm
@@ -1016,7 +1023,7 @@ def measure_c5(env, args, steps, warmup, quick):
         per_phase = []
         for phase in range(2):  # the hard processes alternate: first transmission (fails) / retransmission (combines)
             jobs = []
-            for c in cells[pi::2]:
+            for c in cells[pi::n_pools]:
                 for pid in range(n_pid):
                     k = (c * n_pid + pid) % base
                     if (c * n_pid + pid) % 10 == 3:
@@ -1026,7 +1033,7 @@ def measure_c5(env, args, steps, warmup, quick):
                     jobs.append(Job(c, pid, "ul", pid, 0, True, tbs, Qm, pin_ul.ptr + k * n_q * 2, nsym, qp, n_llr=n_q))
             per_phase.append((jobs, pool.prepare(jobs)))
         batches.append(per_phase)
-    in_flight = [None, None]
+    in_flight = [None] * n_pools
     tally = [0, 0]  # decoded bits, kernel launches
 
     def retire(pi):
@@ -1039,7 +1046,7 @@ def measure_c5(env, args, steps, warmup, quick):
         in_flight[pi] = None
 
     def step(i):
-        for pi in range(2):
+        for pi in range(n_pools):
             retire(pi)
             if batches[pi][0][0]:
                 in_flight[pi] = batches[pi][i % 2][1]
@@ -1048,16 +1055,16 @@ def measure_c5(env, args, steps, warmup, quick):
     n_warm = 2 * max(1, warmup // 2)
     for i in range(n_warm):
         step(i)
-    retire(0)
-    retire(1)
+    for pi in range(n_pools):
+        retire(pi)
     barrier()
     env.sampler.mark()
     tally[0] = tally[1] = 0
     t0 = time.perf_counter()
     for i in range(steps):
         step(i)
-    retire(0)
-    retire(1)
+    for pi in range(n_pools):
+        retire(pi)
     bits, launches = tally
     dt = vmax(time.perf_counter() - t0)
     clocks = env.sampler.snapshot()
@@ -1067,13 +1074,14 @@ def measure_c5(env, args, steps, warmup, quick):
     from oracle.bindings import Port
     P = Port()
     n_ver = bad = 0
-    for pi in range(2):
+    for pi in range(n_pools):
         jobs, bt = batches[pi][0]
         if not jobs:
             continue
         pools[pi].submit(bt)
         res = pools[pi].wait(bt, collect=True)
-        pick = list(range(0, len(jobs), max(1, len(jobs) // (6 if not quick else 3))))[:6]
+        npick = max(2, (12 if not quick else 6) // n_pools)
+        pick = list(range(0, len(jobs), max(1, len(jobs) // npick)))[:npick]
         for i in pick:
             j = jobs[i]
             e = np.ctypeslib.as_array((C.c_int16 * j.n_llr).from_address(j.llr)).copy()
@@ -1089,7 +1097,7 @@ def measure_c5(env, args, steps, warmup, quick):
             bad += int(not ok)
     verified = {"n": n_ver, "mismatches": bad, "against": "oracle port (pinned to the reference)", "what": "return code, transport block bytes, cb_noi (DL and UL jobs)"}
     total = vsum(bits)
-    my_jobs = batches[0][0][0] + batches[1][0][0]
+    my_jobs = [j for pi in range(n_pools) for j in batches[pi][0][0]]
     n_jobs = vsum(len(my_jobs))
     val = total / dt / 1e6
     h2d = vsum(sum((j.n_llr * 2) for j in my_jobs))
@@ -1101,7 +1109,7 @@ def measure_c5(env, args, steps, warmup, quick):
            "e2e": {"value": val, "unit": "Mbit/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(n_jobs * (tbs // 8 + 6)),
                    "h2d_gbs": h2d * steps / dt / 1e9},
            "gpu_launches": int(vsum(launches)), "decoded_tb_fraction": total / (n_jobs * tbs * steps), "verified": verified, "clocks": clocks,
-           "latency": None, "roofline": None, "cpu_baseline": None, "sustained": None, "extra": {}, "engines": 4}
+           "latency": None, "roofline": None, "cpu_baseline": None, "sustained": None, "extra": {}, "engines": 2 * n_pools}
     for pi, pool in enumerate(pools):
         for _, bt in batches[pi]:
             pool.release(bt)
@@ -1207,6 +1215,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c1", choices=["c1", "c2", "c3", "c4", "c5"])
     ap.add_argument("--cells", type=int, default=20, help="cells of the pooled workload (c5), sharded over the ranks")
+    ap.add_argument("--c5-pools", type=int, default=0, help="cell pools (batches in flight) per GPU of the pooled workload (0: 2..4 by the rank's cell count)")
     ap.add_argument("--ncb", type=int, default=18944, help="code blocks per step per GPU (c1)")
     ap.add_argument("--ntb", type=int, default=1000, help="transport blocks per step per GPU (c2/c4)")
     ap.add_argument("--c3-per-k", type=int, default=64, help="transport blocks per LTE code block size and step per GPU (c3)")

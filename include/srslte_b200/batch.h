@@ -31,6 +31,10 @@ extern "C" {
 #define SRSLTE_B200_SEQ_DEVICE 4u /* srslte_b200_demod_descramble: the scrambling sequences are device pointers (a receiver uploads
                                    * the sequences of its RNTIs once) while the symbols still come from the host */
 
+#define SRSLTE_B200_UCI_DEFERRED 8u /* srslte_b200_ulsch_deinterleave with SRSLTE_B200_OUT_DEVICE: do not wait for the UCI LLRs --
+                                     * ack_llr / ri_llr / cqi_llr are filled by the next srslte_b200_wait() on the context (which a
+                                     * srslte_b200_decode_tbs_submit of the subframes' data normally precedes), so the call only enqueues */
+
 typedef struct srslte_b200_ctx srslte_b200_ctx_t;             /* one engine instance = one GPU + one stream */
 typedef struct srslte_b200_softbuffer srslte_b200_softbuffer_t; /* device-resident srslte_softbuffer_rx_t */
 
@@ -152,6 +156,8 @@ SRSLTE_B200_API void srslte_b200_sequence_bytes(uint32_t c_init, uint32_t len, u
  *   g_bits          out: int16[(H_prime_total - Q_prime_ri) * Qm] written, 4-byte aligned when a device pointer
  *   ack_llr, ri_llr, cqi_llr   HOST arrays of Q' * Qm int16 each, or NULL; when any is given the call returns after the
  *                   stream has drained (the values are needed before the UCI decoders can run)
+ *                   -- unless SRSLTE_B200_UCI_DEFERRED is set (with SRSLTE_B200_OUT_DEVICE): then they are written by the next
+ *                   srslte_b200_wait() on this context and the arrays must stay valid until then
  * flags: SRSLTE_B200_IN_DEVICE -> q_bits are device pointers; SRSLTE_B200_OUT_DEVICE -> g_bits are device pointers and stay
  * stream-ordered with a following srslte_b200_decode_tbs*(..., SRSLTE_B200_IN_DEVICE) on the same context.
  * Returns SRSLTE_B200_ERROR_INVALID_INPUTS for geometries the reference cannot index (H' not a multiple of N_pusch_symbs,

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("SRSLTE_B200_LIB", os.path.join(HERE, "libsrslte_fec_b
 
 IN_DEVICE = 1
 OUT_DEVICE = 2
+UCI_DEFERRED = 8  # ulsch_deinterleave with OUT_DEVICE: the UCI LLR arrays are filled by the next wait() on the context
 SEQ_DEVICE = 4
 MAX_CODEBLOCKS = 32
 

@@ -1657,10 +1657,22 @@ int Engine::finish_tb_submit(uint32_t flags)
   return 0;
 }
 
+int Engine::flush_uci()
+{
+  if (uci_deferred.empty())
+    return 0;
+  CUDA_OK(cudaSetDevice(device));
+  CUDA_OK(cudaStreamSynchronize(stream));
+  for (const UciCopy& c : uci_deferred)
+    memcpy(c.dst, h_ul_uci.ptr + c.src_off, c.bytes);
+  uci_deferred.clear();
+  return 0;
+}
+
 int Engine::wait()
 {
   if (pending == PENDING_NONE)
-    return 0;
+    return flush_uci();
   CUDA_OK(cudaSetDevice(device));
   cudaError_t e = cudaStreamSynchronize(stream);
   const int   kind = pending;
@@ -1669,6 +1681,8 @@ int Engine::wait()
     set_error(std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     return SRSLTE_B200_ERROR;
   }
+  if (flush_uci())
+    return SRSLTE_B200_ERROR;
   finish_timing();
   Plan& plan = *plan_ptr;
   if (kind == PENDING_CB) {
@@ -1897,6 +1911,8 @@ int Engine::ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, 
       uci_bytes += al16((size_t)(u.Q_prime_ack + u.Q_prime_ri + u.Q_prime_cqi) * u.Qm * 2);
     }
   }
+  if (flush_uci()) // (deferred UCI LLRs of an earlier call still sit in the pinned buffer reserve() can free)
+    return SRSLTE_B200_ERROR;
   CUDA_OK(cudaEventSynchronize(ev_desc)); // an earlier call's descriptor upload may still read the pinned buffer reserve() can free
   if ((!in_dev && d_ul_in.reserve(in_bytes + 64)) || (!out_dev && (d_ul_out.reserve(out_bytes + 64) || h_ul_out.reserve(out_bytes + 64))) ||
       (want_uci && (d_ul_uci.reserve(uci_bytes + 64) || h_ul_uci.reserve(uci_bytes + 64))) || d_ul_desc.reserve(nof_tb * sizeof(UlschDev)) ||
@@ -1979,6 +1995,24 @@ int Engine::ulsch_deinterleave(const srslte_b200_ulsch_t* tbs, uint32_t nof_tb, 
     CUDA_OK(cudaMemcpyAsync(h_ul_out.ptr, d_ul_out.ptr, out_off, cudaMemcpyDeviceToHost, stream));
   if (out_dev && !want_uci)
     return 0; // stream-ordered with whatever is submitted next on this context
+  if (out_dev && (flags & SRSLTE_B200_UCI_DEFERRED)) {
+    // the host's UCI decoders can wait for the data decode that follows: note where the LLRs go, wait() copies them
+    size_t at = 0;
+    for (uint32_t i = 0; i < nof_tb; i++) {
+      const srslte_b200_ulsch_t& u = tbs[i];
+      if (!(u.ack_llr || u.ri_llr || u.cqi_llr))
+        continue;
+      const size_t na = (size_t)u.Q_prime_ack * u.Qm * 2, nr = (size_t)u.Q_prime_ri * u.Qm * 2, nc = (size_t)u.Q_prime_cqi * u.Qm * 2;
+      if (u.ack_llr && na)
+        uci_deferred.push_back(UciCopy{u.ack_llr, at, na});
+      if (u.ri_llr && nr)
+        uci_deferred.push_back(UciCopy{u.ri_llr, at + na, nr});
+      if (u.cqi_llr && nc)
+        uci_deferred.push_back(UciCopy{u.cqi_llr, at + na + nr, nc});
+      at += al16(na + nr + nc);
+    }
+    return 0;
+  }
   CUDA_OK(cudaStreamSynchronize(stream));
   out_off = uci_off = 0;
   for (uint32_t i = 0; i < nof_tb; i++) {

@@ -150,6 +150,13 @@ private:
   srslte_b200_tb_t* tb_user   = nullptr;
   uint32_t          tb_user_n = 0;
   uint32_t          tb_flags  = 0;
+  // UCI LLRs of a srslte_b200_ulsch_deinterleave(..., SRSLTE_B200_UCI_DEFERRED): copied out of h_ul_uci by the next wait()
+  struct UciCopy {
+    void*  dst;
+    size_t src_off, bytes;
+  };
+  std::vector<UciCopy> uci_deferred;
+  int                  flush_uci(); // synchronises the stream when copies are outstanding
   struct H2dCopy {
     const uint8_t* src;
     size_t         dst, bytes;

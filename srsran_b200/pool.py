@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-from . import IN_DEVICE, OUT_DEVICE, B200Error, Context, Ulsch, make_tbs
+from . import IN_DEVICE, OUT_DEVICE, UCI_DEFERRED, B200Error, Context, Ulsch, make_tbs
 
 
 def owner_of(cell: int, world: int) -> int:
@@ -68,10 +68,15 @@ class Batch:
 class CellPool:
     """The cells one rank owns: two engines on its GPU and the device-resident HARQ soft buffers of its cells."""
 
-    def __init__(self, rank=0, world=1, device=0, max_iterations=8):
+    def __init__(self, rank=0, world=1, device=0, max_iterations=8, latency=None):
+        """latency: None keeps the engines' own choice of kernels per batch size; 0 = throughput pooling: small batches also
+        run the persistent kernel (one launch per batch instead of one per half-iteration; several pools share the GPU)"""
         self.rank, self.world, self.max_iterations = rank, world, max_iterations
         self.dl = Context(device)
         self.ul = Context(device)
+        if latency is not None:
+            self.dl.set_option("latency", latency)
+            self.ul.set_option("latency", latency)
         self._harq = {}
 
     def close(self):
@@ -154,7 +159,8 @@ class CellPool:
         if bt.dl:
             self.dl.decode_tbs(bt.t_dl, False, self.max_iterations, submit_only=True)
         if bt.ul:
-            self.ul.ulsch_deinterleave_raw(bt.arr_ul, OUT_DEVICE)
+            # (the UCI LLRs come back with the data: wait() fills them, so this call only enqueues)
+            self.ul.ulsch_deinterleave_raw(bt.arr_ul, OUT_DEVICE | UCI_DEFERRED)
             self.ul.decode_tbs(bt.t_ul, False, self.max_iterations, flags=IN_DEVICE, submit_only=True)
 
     def wait(self, bt, collect=True):

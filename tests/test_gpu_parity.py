@@ -690,6 +690,13 @@ def test_pusch_symbols_to_transport_block_on_device(port, ctx):
     ul[0].ack_llr, ul[0].ri_llr, ul[0].cqi_llr = a_l.ctypes.data, r_l.ctypes.data, c_l.ctypes.data
     ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE)
     assert (a_l == ack).all() and (r_l == ri).all() and (c_l == g[:qc * Qm]).all()
+    # SRSLTE_B200_UCI_DEFERRED: the same call only enqueues; the UCI LLRs arrive with the next wait() on the context
+    a_l[:], r_l[:], c_l[:] = 0, 0, 0
+    ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE | b.UCI_DEFERRED)
+    ctx.wait()
+    assert (a_l == ack).all() and (r_l == ri).all() and (c_l == g[:qc * Qm]).all()
+    a_l[:], r_l[:], c_l[:] = 0, 0, 0
+    ctx.ulsch_deinterleave_raw(ul, b.IN_DEVICE | b.OUT_DEVICE | b.UCI_DEFERRED)
     t = b.make_tbs(1)
     t[0].e_bits, t[0].nof_e_bits, t[0].tbs, t[0].Qm, t[0].rv, t[0].softbuffer, t[0].data = d_g + qc * Qm * 2, G, tbs, Qm, 0, None, d_out
     ctx.decode_tbs(t, False, 8, flags=b.IN_DEVICE | b.OUT_DEVICE)
@@ -697,6 +704,7 @@ def test_pusch_symbols_to_transport_block_on_device(port, ctx):
     ctx.d2h(out, d_out)
     for p in (d_q, d_g, d_out):
         ctx.device_free(p)
+    assert (a_l == ack).all() and (r_l == ri).all() and (c_l == g[:qc * Qm]).all()  # (filled by decode_tbs' wait)
     assert t[0].ret == 0 and (out == want[:tbs // 8 + 6]).all() and (out[:tbs // 8] == data).all()
     assert list(t[0].cb_noi[:13]) == nit[:13].tolist()
 
