@@ -1,5 +1,5 @@
 """One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
-k_prepare, k_map_fused (Fast16 8 / 16 lanes, Sat8 16 / 32 lanes, Sat16 = the exact path), k_map_gen, k_decide_crc,
+k_prepare, k_map_fused (Fast16 8 / 16 lanes, Sat8 16 / 32 lanes, Sat16 = the exact path), k_gen_fused, k_map_gen, k_decide_crc,
 k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8, with and without csi), k_csi_max,
 k_ulsch_deinterleave, k_map_lat + k_map_win (one subframe: the per-half-iteration path), k_enc_tb_crc, k_enc_cb."""
 import os
@@ -48,7 +48,10 @@ ctx.set_option("fast16", 0)
 cb_batch(2368, 6144, 2)           # k_map_fused<Sat16,16> doing real work (the exact path)
 ctx.set_option("fast16", 1)
 cb_batch(9472, 512, 3)            # k_map_fused<Fast16,8>
-cb_batch(4096, 40, 2)             # k_map_gen, k_decide_crc
+cb_batch(4096, 400, 6)            # k_gen_fused: the generic decoder's whole loop in one launch
+ctx.set_option("gen_fused", 0)
+cb_batch(4096, 40, 2)             # k_map_gen, k_decide_crc (the per-half-iteration path kept for K > 512 sessions and A/B)
+ctx.set_option("gen_fused", 1)
 cb_batch(13, 6144, 4)             # k_scan_fused: one subframe, time-parallel (cooperative launch)
 for dt, mod in ((np.int16, 3), (np.int8, 4)):
     n, nsym = 256, 15000
