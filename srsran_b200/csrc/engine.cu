@@ -567,6 +567,7 @@ struct LaunchState {
   size_t    off_dm16 = 0, off_dm8 = 0, off_plain = 0, off_gen = 0, off_old = 0, ctr_fetch0 = 0, n_counters = 0;
   uint32_t  max_iter = 0, iter0 = 0;
   bool      prepare = true;
+  size_t    prep_smem = 0; // dynamic shared memory of k_prepare for this batch
   ClassRun  cls[4];
   bool      cls_lat[4], cls_fused[4], cls_scan[4];
   ScanLay   scan_lay[4];
@@ -666,6 +667,21 @@ int Engine::build_plan(Plan& p)
   const size_t off_dm16 = add_list(dm16), off_dm8 = add_list(dm8), off_plain = add_list(plain);
   LaunchState& L   = *ls_ptr;
   L                = LaunchState();
+  // k_prepare's staging memory: the fast transposition (int16 LLRs in standard order into an int16 windowed decoder) needs the
+  // block plus one padding word per lane (37 KB at K = 6144: six CTAs per SM); only the general path needs the second plane
+  // (52 KB: four).  More resident CTAs = more loads in flight for a kernel that is bound by the memory system.
+  {
+    const size_t full = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
+    size_t       need = 0;
+    bool         all_fast = !plain.empty();
+    for (int i : plain) {
+      const CbDev& d = p.cbs[i];
+      all_fast = all_fast && !d.in_sb && d.in_bits == 16 && d.bits == 16 && d.N && (d.W & 3u) == 0 && (256 % (d.N / 2)) == 0 &&
+                 ((uintptr_t)d.in_ptr & 7u) == 0;
+      need = std::max(need, (size_t)(3 * d.K + 2 * d.N + 8) * sizeof(int16_t));
+    }
+    L.prep_smem = all_fast ? std::min(need, full) : full;
+  }
   ClassRun(&cls)[4] = L.cls;
   struct KGroup { // code blocks of one size in one decoder class: consecutive slots, consecutive workspace
     int      cls, first_slot, n_blocks;
@@ -966,9 +982,9 @@ int Engine::launch_plan()
   }
   if (L.n_plain > 0 && p.prepare) {
     // staging of one code block (3K+12 LLRs) + one padded plane for the transposition into the lane layout
-    const size_t prep_smem = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
-    CUDA_OK(smem_attr_once((const void*)k_prepare, (int)prep_smem));
-    k_prepare<<<L.n_plain, 256, prep_smem, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
+    const size_t prep_full = ((3 * kMaxK + 12 + 7) / 8 * 8 + (kMaxK / 8) * 10) * sizeof(int16_t);
+    CUDA_OK(smem_attr_once((const void*)k_prepare, (int)prep_full));
+    k_prepare<<<L.n_plain, 256, L.prep_smem ? L.prep_smem : prep_full, stream>>>(d_cbs.ptr, d_lists.ptr + off_plain, d_ws.ptr, d_tails.ptr, d_state.ptr, d_gmax.ptr, 1);
     last_launches++;
   }
   CUDA_OK(cudaGetLastError());
