@@ -687,7 +687,9 @@ def measure_batched(env, args, wl, steps, warmup, quick):
             pin_in = b.PinnedArray((n_el,), dt)
             off = make_c3(rng, specs, pin_in.array)
             workload = "c3-mixed: %d single-block transport blocks over all 188 LTE sizes K=40..6144 (%d per size), int16 e-bits, noise sigma %s, " \
-                       "rate de-matching + <=8 half-iterations with CRC early stop" % (len(specs), len(specs) // 188, list(C3_SIGMAS))
+                       "rate de-matching + <=8 half-iterations with CRC early stop%s" % (
+                           len(specs), len(specs) // 188, list(C3_SIGMAS),
+                           "" if args.no_hints else "; the per-block noise estimate is passed as a grouping hint (srslte_b200_set_tb_hints)")
             uniform = None
         else:
             cfg = TB_CFG[wl]
@@ -729,9 +731,15 @@ def measure_batched(env, args, wl, steps, warmup, quick):
             engines.append((c, tbd, d_o))
         tb_dev = engines[0][1]
 
+        # c3: the receiver's noise estimate per block goes along as a scheduling hint (srslte_b200_set_tb_hints: blocks of
+        # equal size are grouped by it; results never depend on it).  --no-hints measures without
+        hints = np.array([C3_SIGMAS[s[3]] for s in specs], np.float32) if (wl == "c3" and not args.no_hints) else None
+
         def dev_submit(i):
             e, t, _ = engines[i % n_eng]
             e.wait()
+            if hints is not None:
+                e.set_tb_hints(hints)
             e.decode_tbs(t, is8, max_iter, flags=b.IN_DEVICE | b.OUT_DEVICE, submit_only=True)
 
         n_chunks = args.e2e_chunks
@@ -749,6 +757,8 @@ def measure_batched(env, args, wl, steps, warmup, quick):
             for c, (lo, arr) in enumerate(host_chunks):
                 e = all_ctx[c % n_eng]
                 e.wait()
+                if hints is not None:
+                    e.set_tb_hints(hints[lo:lo + len(arr)])
                 e.decode_tbs(arr, is8, max_iter, flags=0, submit_only=True)
 
         def verify():
@@ -1222,6 +1232,7 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline budget")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-latency", action="store_true", help="skip the per-TTI latency loop (keeps profiler launch lists short)")
+    ap.add_argument("--no-hints", action="store_true", help="c3: do not pass the per-block noise estimates as scheduling hints")
     ap.add_argument("--no-symbols", action="store_true", help="c2 / c4: skip the symbols-in end-to-end section")
     ap.add_argument("--no-configs", action="store_true", help="c1 only: skip the compact c2 / c3 / c4 / c5 block")
     ap.add_argument("--config-steps", type=int, default=8, help="timed steps of each configuration of the compact block")

@@ -107,6 +107,14 @@ SRSLTE_B200_API int srslte_b200_tdec_batch_submit(srslte_b200_ctx_t* ctx, const 
 SRSLTE_B200_API int srslte_b200_decode_tbs_submit(srslte_b200_ctx_t* ctx, srslte_b200_tb_t* tbs, uint32_t nof_tb, int llr_is_8bit, uint32_t max_iterations, uint32_t flags);
 SRSLTE_B200_API int srslte_b200_wait(srslte_b200_ctx_t* ctx);
 
+/* Optional scheduling hint for the NEXT srslte_b200_decode_tbs[_submit] on this context: one number per transport block of that
+ * call, larger = expected to need more half-iterations (the noise estimate of the channel estimator, srslte_chest_dl_res_t::
+ * noise_estimate / the inverse of snr_db, is what a receiver has at pdsch.c:859; the MCS works too).  Code blocks of equal size
+ * are then grouped by hint, so that the blocks sharing a warp of the persistent kernel stop at about the same half-iteration
+ * instead of one slow block keeping the finished ones aboard.  Results do not depend on the hints in any way; without the call
+ * (or with nof_tb different from the batch's) blocks are grouped in submission order. */
+SRSLTE_B200_API int srslte_b200_set_tb_hints(srslte_b200_ctx_t* ctx, const float* hints, uint32_t nof_tb);
+
 /* ---- soft demodulation + descrambling on the device: the batched form of
  * srslte_demod_soft_demodulate_s / _b (lib/src/phy/modem/demod_soft.c:896-945) followed by
  * srslte_scrambling_s_offset / _sb_offset (lib/src/phy/scrambling/scrambling.c:43-53) -- the two steps between the

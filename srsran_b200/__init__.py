@@ -346,6 +346,13 @@ class Context:
         if rc:
             _err("srslte_b200_decode_tbs", rc)
 
+    def set_tb_hints(self, hints):
+        """difficulty hints (float per transport block) for the next decode_tbs on this context: grouping only, never results"""
+        h = np.ascontiguousarray(hints, np.float32)
+        rc = lib().srslte_b200_set_tb_hints(self.h, h.ctypes.data_as(C.POINTER(C.c_float)), len(h))
+        if rc:
+            _err("srslte_b200_set_tb_hints", rc)
+
     def softbuffer_create(self, max_cb=MAX_CODEBLOCKS):
         sb = C.c_void_p()
         rc = lib().srslte_b200_softbuffer_create(self.h, C.byref(sb), max_cb)

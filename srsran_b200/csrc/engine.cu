@@ -38,6 +38,7 @@ struct Plan {
   uint32_t           iter0        = 0; // half-iterations the code blocks have already run (single-block sessions)
   bool               prepare      = true;
   uint32_t           cb_out_bytes = 0;
+  std::vector<float> tb_hint; // per transport block (index of tbs[]): the caller's difficulty hint, or empty (srslte_b200_set_tb_hints)
 };
 
 struct LaunchState;
@@ -694,7 +695,15 @@ int Engine::build_plan(Plan& p)
     for (int i : active)
       if (p.cbs[i].N == kWinClasses[c].lanes && p.cbs[i].bits == kWinClasses[c].bits)
         ids.push_back(i);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p.cbs[a].K > p.cbs[b].K; });
+    // longest first; among equal sizes by the caller's difficulty hint when there is one (srslte_b200_set_tb_hints): blocks
+    // that will need about as many half-iterations then share a warp, instead of one slow block keeping three finished
+    // ones aboard as ghosts (a group runs until its slowest block stops)
+    const bool hinted = !p.tb_hint.empty();
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+      if (p.cbs[a].K != p.cbs[b].K)
+        return p.cbs[a].K > p.cbs[b].K;
+      return hinted && p.tb_hint[p.cbs[a].tb] < p.tb_hint[p.cbs[b].tb];
+    });
     const int        G = 32 / (kWinClasses[c].lanes / 2);
     std::vector<int> w;
     int              max_w = 0;
@@ -741,7 +750,12 @@ int Engine::build_plan(Plan& p)
     for (int i : active)
       if (p.cbs[i].N == 0)
         ids.push_back(i);
-    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) { return p.cbs[a].K > p.cbs[b].K; });
+    const bool hinted = !p.tb_hint.empty();
+    std::stable_sort(ids.begin(), ids.end(), [&](int a, int b) {
+      if (p.cbs[a].K != p.cbs[b].K)
+        return p.cbs[a].K > p.cbs[b].K;
+      return hinted && p.tb_hint[p.cbs[a].tb] < p.tb_hint[p.cbs[b].tb];
+    });
     for (int i : ids) {
       p.cbs[i].ws_off = ws_elems;
       ws_elems += 6ull * p.cbs[i].ps;
@@ -1463,6 +1477,13 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
       reusable = false;
     kb.put(u.e_bits); kb.put(u.nof_e_bits); kb.put(u.tbs); kb.put(u.Qm); kb.put(u.rv); kb.put(u.data);
   }
+  // difficulty hints of this batch (one-shot: they belong to the call that follows srslte_b200_set_tb_hints)
+  std::vector<float> hints;
+  hints.swap(tb_hints);
+  if (hints.size() != nof_tb)
+    hints.clear();
+  for (float h : hints)
+    kb.put(h);
   Plan& plan = *plan_ptr;
   tb_user   = tbs;
   tb_user_n = nof_tb;
@@ -1640,6 +1661,8 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
         d.dematch = 0;
       plan.cbs.push_back(d);
     }
+    if (!hints.empty())
+      plan.tb_hint.push_back(hints[t]);
     plan.tbs.push_back(td);
   }
   if (cp_bytes) {
@@ -2534,6 +2557,13 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
     return 0;
   }
   return SRSLTE_B200_ERROR_INVALID_INPUTS;
+}
+int srslte_b200_set_tb_hints(srslte_b200_ctx_t* ctx, const float* hints, uint32_t nof_tb)
+{
+  if (!ctx || (!hints && nof_tb))
+    return SRSLTE_B200_ERROR_INVALID_INPUTS;
+  ctx->e->tb_hints.assign(hints, hints + nof_tb);
+  return 0;
 }
 uint32_t srslte_b200_last_replayed(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_redo : 0; }
 uint32_t srslte_b200_last_half_iterations(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_half_iter : 0; }

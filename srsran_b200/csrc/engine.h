@@ -129,6 +129,8 @@ public:
   PinBuf<TbResult> h_res;
   PinBuf<CbState>  h_state;
 
+  std::vector<float> tb_hints; // difficulty hints for the next transport-block batch (srslte_b200_set_tb_hints)
+
 private:
   Engine() {}
   int build_tables();

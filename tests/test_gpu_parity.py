@@ -329,6 +329,48 @@ def test_decode_tbs_all_sizes_one_batch(port, ctx, dtype, amp):
     assert len(its) >= 4  # iteration counts really vary inside the batch
 
 
+@pytest.mark.gpu
+def test_tb_hints_change_the_grouping_not_the_results(port, ctx):
+    """srslte_b200_set_tb_hints: code blocks of equal size are grouped by the caller's difficulty hint.  240 transport blocks
+    of three sizes (8-, 16-lane and generic decoder classes) and four noise levels, decoded without hints, with the noise level
+    as hint, with random hints and with a hint array of the wrong length (ignored): identical return codes, bytes, CRC flags and
+    half-iteration counts every time, all equal to the oracle's"""
+    rng = np.random.default_rng(777)
+    shapes = [(6120, 2, 18700), (1000, 2, 3300), (376, 2, 1300)]
+    sigmas = (0.5, 0.8, 1.0, 1.4)
+    base = {}
+    for tbs, Qm, G in shapes:
+        for j, sg in enumerate(sigmas):
+            _, llr = _tb_inputs(port, rng, tbs, Qm, G, 0, np.int16, 100, sg)
+            sbp = port.softbuffer_new()
+            base[(tbs, j)] = (llr, port.decode_tb(sbp, tbs, Qm, 0, llr, 8))
+            port.softbuffer_del(sbp)
+    cases = [(shapes[i % 3], (i * 7 + i // 3) % 4) for i in range(240)]
+    n = len(cases)
+    runs = []
+    for mode in ("none", "sigma", "random", "wrong-length"):
+        t = b.make_tbs(n)
+        outs = np.zeros((n, 6120 // 8 + 22), np.uint8)
+        for i, ((tbs, Qm, G), j) in enumerate(cases):
+            llr = base[(tbs, j)][0]
+            t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].data = llr.ctypes.data, G, tbs, Qm, 0, outs[i].ctypes.data
+        if mode == "sigma":
+            ctx.set_tb_hints([sigmas[j] for _, j in cases])
+        elif mode == "random":
+            ctx.set_tb_hints(rng.standard_normal(n))
+        elif mode == "wrong-length":
+            ctx.set_tb_hints(np.ones(n - 1))
+        ctx.decode_tbs(t, False, 8)
+        for i, ((tbs, Qm, G), j) in enumerate(cases):
+            rc, d, nit, avg, crc = base[(tbs, j)][1]
+            nb = tbs // 8 + 3
+            assert t[i].ret == rc and (outs[i][:nb] == d[:nb]).all(), (mode, i)
+            assert t[i].cb_noi[0] == nit[0] and t[i].cb_crc[0] == crc[0], (mode, i)
+        runs.append((outs.copy(), [t[i].ret for i in range(n)]))
+    for o, r in runs[1:]:
+        assert (o == runs[0][0]).all() and r == runs[0][1]
+
+
 def test_decode_tb_invalid(ctx):
     t = b.make_tbs(3)
     out = np.zeros(20000, np.uint8)
