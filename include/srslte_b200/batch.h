@@ -112,7 +112,8 @@ SRSLTE_B200_API int srslte_b200_wait(srslte_b200_ctx_t* ctx);
  * noise_estimate / the inverse of snr_db, is what a receiver has at pdsch.c:859; the MCS works too).  Code blocks of equal size
  * are then grouped by hint, so that the blocks sharing a warp of the persistent kernel stop at about the same half-iteration
  * instead of one slow block keeping the finished ones aboard.  Results do not depend on the hints in any way; without the call
- * (or with nof_tb different from the batch's) blocks are grouped in submission order. */
+ * (or with nof_tb different from the batch's) the engine takes an estimate of its own from the e-bits of each block (option
+ * "auto_group", default 1; sizes whose neighbouring blocks belong to one transport block anyway keep submission order). */
 SRSLTE_B200_API int srslte_b200_set_tb_hints(srslte_b200_ctx_t* ctx, const float* hints, uint32_t nof_tb);
 
 /* ---- soft demodulation + descrambling on the device: the batched form of

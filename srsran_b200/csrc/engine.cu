@@ -219,6 +219,8 @@ int Engine::create(Engine** out, int device)
     e->opt_gen_fused = atoi(ev) != 0;
   if (const char* ev = getenv("SRSLTE_B200_FUSED_SPREAD"))
     e->opt_fused_spread = atoi(ev);
+  if (const char* ev = getenv("SRSLTE_B200_AUTO_GROUP"))
+    e->opt_auto_group = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_FUSED_WARPS"))
     e->opt_fused_warps = atoi(ev);
   if (const char* ev = getenv("SRSLTE_B200_L2_PERSIST"))
@@ -267,7 +269,7 @@ Engine::~Engine()
     cudaEventDestroy(ev_end);
   d_qpp.release(); d_rm.release(); d_cbs.release(); d_state.release(); d_tbs.release(); d_res.release();
   d_crctab.release(); d_parked.release(); d_queue.release(); d_scan.release(); d_scanacc.release(); d_ws.release(); d_tails.release(); d_cbout.release(); d_lists.release(); d_in.release(); d_tbout.release();
-  d_sb.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
+  d_sb.release(); d_stat.release(); d_genbeta.release(); d_gmax.release(); d_counters.release(); h_counters.release(); d_ckscratch.release();
   h_stage_in.release(); h_stage_out.release(); h_res.release(); h_state.release(); h_desc.release();
   h_tmaps.release(); d_tmaps.release();
   d_dm_in.release(); d_dm_out.release(); d_dm_desc.release(); d_dm_csimax.release(); h_dm_desc.release(); h_dm_out.release();
@@ -563,6 +565,8 @@ struct ClassRun {
 struct LaunchState {
   bool      valid = false;
   int       n_cb = 0, n_dm16 = 0, n_dm8 = 0, n_plain = 0, n_pairs = 0, gen_threads = 0, n_old = 0, n_tbs = 0;
+  int       n_kg = 0, n_stat16 = 0, n_stat8 = 0; // sizes regrouped by difficulty (k_regroup), blocks whose e-bits k_cb_stat reads
+  size_t    off_kg = 0, off_stat16 = 0, off_stat8 = 0;
   int       n_genf = 0, genf_kp = 0; // pairs of the fused generic kernel (map_gen_fused.cuh), row length of its shared arrays
   size_t    off_genf = 0;
   size_t    off_dm16 = 0, off_dm8 = 0, off_plain = 0, off_gen = 0, off_old = 0, ctr_fetch0 = 0, n_counters = 0;
@@ -848,12 +852,51 @@ int Engine::build_plan(Plan& p)
     if (c < 0 ? !(opt_gen_fused && d.K <= (uint32_t)kGenFusedMaxK) : !cls_fused[c])
       old_path.push_back(i);
   }
+  // ---- grouping by difficulty (kernels.cuh: k_cb_stat / k_regroup): sizes of early-stop classes of the persistent kernel whose
+  //      blocks all come with e-bits, when the caller gave no hints of its own
+  {
+    std::vector<int> kg, st16, st8;
+    if (opt_auto_group && p.tb_hint.empty()) {
+      for (const KGroup& g : groups) {
+        const int c = g.cls, G = 64 / kWinClasses[c].lanes;
+        if (!cls_fused[c] || cls[c].no_crc || g.n_blocks < 2 * G || g.n_blocks > kRegroupMax)
+          continue;
+        const int* slots = lists.data() + cls[c].off + g.first_slot;
+        bool       ok    = true;
+        int        n_tb  = 0;
+        for (int i = 0; i < g.n_blocks; i++) {
+          ok = ok && slots[i] >= 0 && p.cbs[slots[i]].dematch && p.cbs[slots[i]].e_ptr;
+          if (ok && (i == 0 || p.cbs[slots[i]].tb != p.cbs[slots[i - 1]].tb))
+            n_tb++;
+        }
+        // (the code blocks of one transport block sit next to each other and share its channel: when a warp's blocks come from
+        //  one transport block anyway there is nothing to gain, and the pooled workload c5 paid 4 % for the three extra launches)
+        if (!ok || g.n_blocks >= G * n_tb)
+          continue;
+        for (int i = 0; i < g.n_blocks; i++)
+          (p.cbs[slots[i]].in_bits == 16 ? st16 : st8).push_back(slots[i]);
+        kg.push_back((int)(cls[c].off + g.first_slot));
+        kg.push_back(g.n_blocks);
+        kg.push_back((int)g.ps);
+        kg.push_back((int)(uint32_t)(g.ws_off & 0xffffffffull));
+        kg.push_back((int)(uint32_t)(g.ws_off >> 32));
+      }
+    }
+    L.n_kg       = (int)kg.size() / 5;
+    L.n_stat16   = (int)st16.size();
+    L.n_stat8    = (int)st8.size();
+    L.off_kg     = add_list(kg);
+    L.off_stat16 = add_list(st16);
+    L.off_stat8  = add_list(st8);
+  }
   const size_t off_old = add_list(old_path);
 
   // ---- device buffers
   if (d_gmax.reserve((size_t)n_cb * 4) || d_cbs.reserve(n_cb) || d_state.reserve(n_cb) || d_ws.reserve(ws_elems) || d_tails.reserve((size_t)n_cb * 12) ||
       d_cbout.reserve(out_bytes + 64) || d_lists.reserve(lists.size() + 1) || d_tbs.reserve(p.tbs.size() + 1) ||
       d_res.reserve(p.tbs.size() + 1))
+    return SRSLTE_B200_ERROR;
+  if (L.n_kg && d_stat.reserve((size_t)n_cb))
     return SRSLTE_B200_ERROR;
   const int gen_threads = (n_pairs + 63) / 64 * 64;
   if (n_pairs && d_genbeta.reserve((size_t)(gen_max_k + 4) * 8 * gen_threads))
@@ -978,6 +1021,17 @@ int Engine::launch_plan()
   if (L.cls_scan[0] || L.cls_scan[1])
     CUDA_OK(cudaMemsetAsync(d_scanacc.ptr, 0, (size_t)2 * kScanMaxGroups * kScanAcc * 32 * sizeof(int32_t), stream));
   CUDA_OK(cudaEventRecord(ev_begin, stream));
+
+  // ---- blocks of a size ordered by a noise estimate of their e-bits, so that the blocks of a warp stop together
+  if (L.n_kg > 0) {
+    if (L.n_stat16 > 0)
+      k_cb_stat<int16_t><<<L.n_stat16, 128, 0, stream>>>(d_cbs.ptr, d_lists.ptr + L.off_stat16, d_stat.ptr);
+    if (L.n_stat8 > 0)
+      k_cb_stat<int8_t><<<L.n_stat8, 128, 0, stream>>>(d_cbs.ptr, d_lists.ptr + L.off_stat8, d_stat.ptr);
+    k_regroup<<<L.n_kg, 256, 0, stream>>>(d_lists.ptr + L.off_kg, d_lists.ptr, d_cbs.ptr, d_stat.ptr);
+    CUDA_OK(cudaGetLastError());
+    last_launches += 1 + (L.n_stat16 > 0) + (L.n_stat8 > 0);
+  }
 
   // ---- transport-block inputs: rate de-matching (HARQ combine) + extraction in one pass per code block;
   //      directly supplied LLRs: extraction only
@@ -1398,7 +1452,7 @@ int Engine::submit_cb_batch(const srslte_b200_cb_batch_t* cfg, const void* llr, 
   kb.put(*cfg);
   kb.put(flags);
   kb.put(d_llr);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread); kb.put(opt_auto_group);
   if (ls_ptr->valid && !cache_key.empty() && kb.k == cache_key) {
     // the same batch shape on the same buffers as the last one: descriptors, work lists and tensor maps are in place
     rc = launch_plan();
@@ -1470,7 +1524,7 @@ int Engine::submit_tb_batch(srslte_b200_tb_t* tbs, uint32_t nof_tb, int is8, uin
   bool       reusable = true;
   kb.put('T');
   kb.put(nof_tb); kb.put(is8); kb.put(max_iterations); kb.put(flags);
-  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread);
+  kb.put(opt_fast16); kb.put(opt_latency); kb.put(opt_fused); kb.put(opt_fused_warps); kb.put(opt_fused_slice); kb.put(opt_scan); kb.put(opt_scan_fused); kb.put(opt_scan_launch); kb.put(opt_scan_cpg); kb.put(opt_gen_fused); kb.put(opt_fused_spread); kb.put(opt_auto_group);
   for (uint32_t t = 0; t < nof_tb; t++) {
     const srslte_b200_tb_t& u = tbs[t];
     if (u.softbuffer)
@@ -2536,6 +2590,10 @@ int srslte_b200_set_option(srslte_b200_ctx_t* ctx, const char* name, int value)
   }
   if (!strcmp(name, "fused_spread")) {
     ctx->e->opt_fused_spread = value;
+    return 0;
+  }
+  if (!strcmp(name, "auto_group")) {
+    ctx->e->opt_auto_group = value;
     return 0;
   }
   if (!strcmp(name, "scan_launch")) {

@@ -102,6 +102,7 @@ public:
   bool             opt_latency = true; // small batches: the 4-warp latency-shaped MAP kernel (map_lat.cuh) instead of one warp per group
   DevBuf<uint32_t> d_genbeta, d_counters, d_ckscratch, d_crctab;
   DevBuf<int>      d_parked; // fused kernel: groups whose blocks the Fast16 monitor parked for the exact-arithmetic launch
+  DevBuf<int32_t>  d_stat;    // per code block: difficulty estimate of k_cb_stat
   DevBuf<int32_t>  d_scanacc; // ... and the range-monitor accumulators of their groups
   DevBuf<int32_t>  d_scan;   // time-parallel latency kernels (map_scan.cuh): transfer matrices, boundary states, monitor records
   int              opt_scan_cpg = 0;        // k_scan_fused: CTAs per group (0: chosen from the shape)
@@ -114,6 +115,7 @@ public:
   int              opt_fused_slice = 21; // classes with CRC early stop: half-iterations per visit of a group, 10 x first + later (0: a group stays with its warp)
   bool             opt_fused = true; // large batches: one persistent launch per decoder class (map_fused.cuh)
   bool             opt_gen_fused = true; // generic decoder, K <= kGenFusedMaxK: one CTA per pair of blocks for all half-iterations (map_gen_fused.cuh)
+  int              opt_auto_group = 1;   // transport-block batches without caller hints: blocks of a size ordered by a noise estimate taken from their e-bits (k_cb_stat / k_regroup)
   int              opt_fused_spread = 1; // fused kernel: smaller CTAs when a class has fewer groups than 12 per SM, so every SM gets some
   PinBuf<uint32_t> h_counters;
   uint32_t         last_redo = 0, last_half_iter = 0;

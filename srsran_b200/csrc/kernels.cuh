@@ -299,6 +299,89 @@ __global__ void __launch_bounds__(256) k_prepare(const CbDev* __restrict__ cbs, 
     gmax[(size_t)cb * 4 + 3] = 0;
 }
 
+// ------------------------------------------------------------------------------------------ grouping by difficulty
+// A warp of the persistent MAP kernel holds G code blocks of one size and runs until the slowest of them stops (CRC early stop,
+// sch.c:441-450); blocks that stopped ride along as ghosts.  Which blocks share a warp is free -- any blocks of equal size in
+// the same decoder class -- so the blocks of a size are ordered by how hard they look before their planes are written:
+//   k_cb_stat   one CTA per code block: 1 - (sum |e|)^2 / (E sum e^2) over its e-bits, the normalised spread of the LLR
+//               magnitudes (0 for a noiseless block, growing with the noise), as a fixed-point integer;
+//   k_regroup   one CTA per size: sorts the block ids of the size's slots by that number and rewrites the work list and the
+//               blocks' workspace offsets (slot i of a size sits at ws_base + i * 6 * ps: the tensor maps address blocks by slot).
+// Only the grouping changes; every block is decoded exactly as before.
+template <typename T>
+__global__ void __launch_bounds__(128) k_cb_stat(const CbDev* __restrict__ cbs, const int* __restrict__ list, int32_t* __restrict__ stat)
+{
+  const int      cb = list[blockIdx.x];
+  const CbDev    d  = cbs[cb];
+  const T*       in = (const T*)d.e_ptr;
+  unsigned long long sa = 0, sq = 0;
+  for (uint32_t i = threadIdx.x; i < d.E; i += blockDim.x) {
+    const int32_t v = (int32_t)in[i];
+    sa += (unsigned)(v < 0 ? -v : v);
+    sq += (unsigned)(v * v);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    sa += __shfl_down_sync(0xffffffffu, sa, o);
+    sq += __shfl_down_sync(0xffffffffu, sq, o);
+  }
+  __shared__ unsigned long long s_a[4], s_q[4];
+  if ((threadIdx.x & 31) == 0) {
+    s_a[threadIdx.x >> 5] = sa;
+    s_q[threadIdx.x >> 5] = sq;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const double a = (double)(s_a[0] + s_a[1] + s_a[2] + s_a[3]), q = (double)(s_q[0] + s_q[1] + s_q[2] + s_q[3]);
+    const double r = q > 0 ? (a * a) / ((double)d.E * q) : 1.0;
+    stat[cb]       = (int32_t)((1.0 - r) * 1.0e8);
+  }
+}
+
+constexpr int kRegroupMax = 1024; // blocks of one size the sort handles (larger sizes keep their order)
+// kg: per size {offset of its slots in the lists, number of blocks, plane stride, workspace base low, high}
+__global__ void __launch_bounds__(256) k_regroup(const int* __restrict__ kg, int* __restrict__ lists, CbDev* __restrict__ cbs, const int32_t* __restrict__ stat)
+{
+  __shared__ int32_t s_key[kRegroupMax];
+  __shared__ int     s_id[kRegroupMax];
+  const int*     g   = kg + 5 * blockIdx.x;
+  const int      off = g[0], n = g[1];
+  const uint32_t ps  = (uint32_t)g[2];
+  const uint64_t base = (uint64_t)(uint32_t)g[3] | ((uint64_t)(uint32_t)g[4] << 32);
+  int            m   = 1;
+  while (m < n)
+    m <<= 1;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) {
+    const int id = i < n ? lists[off + i] : 0x7fffffff;
+    s_id[i]      = id;
+    s_key[i]     = i < n ? stat[id] : 0x7fffffff;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += blockDim.x) {
+        const int l = i ^ j;
+        if (l > i) {
+          const bool up = (i & k) == 0;
+          const int32_t ka = s_key[i], kb = s_key[l];
+          const int     ia = s_id[i], ib = s_id[l];
+          const bool    gt = ka > kb || (ka == kb && ia > ib); // (ties by block id: the order is a function of the inputs only)
+          if (gt == up) {
+            s_key[i] = kb; s_key[l] = ka;
+            s_id[i]  = ib; s_id[l]  = ia;
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int id       = s_id[i];
+    lists[off + i]     = id;
+    cbs[id].ws_off     = base + (uint64_t)i * 6ull * ps;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ dematch + extraction
 // Transport-block path: rate de-matching (HARQ combining) and input extraction in ONE pass per code block.  The
 // soft buffer of the block is assembled in shared memory (zero-filled for a new transmission, loaded for a

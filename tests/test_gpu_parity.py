@@ -331,7 +331,8 @@ def test_decode_tbs_all_sizes_one_batch(port, ctx, dtype, amp):
 
 @pytest.mark.gpu
 def test_tb_hints_change_the_grouping_not_the_results(port, ctx):
-    """srslte_b200_set_tb_hints: code blocks of equal size are grouped by the caller's difficulty hint.  240 transport blocks
+    """srslte_b200_set_tb_hints / automatic grouping: code blocks of equal size are grouped by the caller's difficulty hint, or
+    by the engine's own noise estimate when there is none.  240 transport blocks
     of three sizes (8-, 16-lane and generic decoder classes) and four noise levels, decoded without hints, with the noise level
     as hint, with random hints and with a hint array of the wrong length (ignored): identical return codes, bytes, CRC flags and
     half-iteration counts every time, all equal to the oracle's"""
@@ -348,7 +349,7 @@ def test_tb_hints_change_the_grouping_not_the_results(port, ctx):
     cases = [(shapes[i % 3], (i * 7 + i // 3) % 4) for i in range(240)]
     n = len(cases)
     runs = []
-    for mode in ("none", "sigma", "random", "wrong-length"):
+    for mode in ("none", "sigma", "random", "wrong-length", "no-auto-group"):
         t = b.make_tbs(n)
         outs = np.zeros((n, 6120 // 8 + 22), np.uint8)
         for i, ((tbs, Qm, G), j) in enumerate(cases):
@@ -360,6 +361,9 @@ def test_tb_hints_change_the_grouping_not_the_results(port, ctx):
             ctx.set_tb_hints(rng.standard_normal(n))
         elif mode == "wrong-length":
             ctx.set_tb_hints(np.ones(n - 1))
+        # (without hints the engine orders the blocks of a size by a noise estimate of its own, k_cb_stat / k_regroup:
+        #  "none" and "wrong-length" run that path, "no-auto-group" the plain submission order)
+        ctx.set_option("auto_group", 0 if mode == "no-auto-group" else 1)
         ctx.decode_tbs(t, False, 8)
         for i, ((tbs, Qm, G), j) in enumerate(cases):
             rc, d, nit, avg, crc = base[(tbs, j)][1]
