@@ -1,6 +1,6 @@
 """One launch (at least) of EVERY kernel of the library, for a single `ncu --set full` capture:
 k_prepare, k_map_fused (Fast16 8 / 16 lanes, Sat8 16 / 32 lanes, Sat16 = the exact path), k_gen_fused, k_map_gen, k_decide_crc,
-k_dematch_prepare (int16 / int8), k_tb_finish, k_demod_descramble (int16 / int8, with and without csi), k_csi_max,
+k_dematch_prepare (int16 / int8), k_cb_stat, k_regroup, k_tb_finish, k_demod_descramble (int16 / int8, with and without csi), k_csi_max,
 k_ulsch_deinterleave, k_map_lat + k_map_win (one subframe: the per-half-iteration path), k_enc_tb_crc, k_enc_cb."""
 import os
 import sys
@@ -53,6 +53,25 @@ ctx.set_option("gen_fused", 0)
 cb_batch(4096, 40, 2)             # k_map_gen, k_decide_crc (the per-half-iteration path kept for K > 512 sessions and A/B)
 ctx.set_option("gen_fused", 1)
 cb_batch(13, 6144, 4)             # k_scan_fused: one subframe, time-parallel (cooperative launch)
+
+
+def mixed_tb_batch(per_k):
+    """all 188 sizes, single-block transport blocks of several noise levels (c3): k_cb_stat + k_regroup order the blocks of a size"""
+    specs = bench.c3_specs(per_k)
+    flat = np.zeros(bench.c3_elems(specs), np.int16)
+    off = bench.make_c3(np.random.default_rng(1), specs, flat)
+    ntb = len(specs)
+    ostr = [(s_[0] // 8 + 6 + 15) // 16 * 16 for s_ in specs]
+    ooff = np.concatenate([[0], np.cumsum(ostr)[:-1]])
+    d_llr, d_out = ctx.device_alloc(flat.nbytes), ctx.device_alloc(int(sum(ostr)))
+    ctx.h2d(d_llr, flat)
+    t = b.make_tbs(ntb)
+    for i in range(ntb):
+        t[i].e_bits, t[i].nof_e_bits, t[i].tbs, t[i].Qm, t[i].rv, t[i].softbuffer, t[i].data = d_llr + int(off[i]) * 2, specs[i][2], specs[i][0], specs[i][1], 0, None, d_out + int(ooff[i])
+    ctx.decode_tbs(t, False, 8, flags=b.IN_DEVICE | b.OUT_DEVICE)
+
+
+mixed_tb_batch(16)                # k_cb_stat, k_regroup (+ every decoder class in one batch)
 for dt, mod in ((np.int16, 3), (np.int8, 4)):
     n, nsym = 256, 15000
     sym = ((rng.standard_normal((n, nsym)) + 1j * rng.standard_normal((n, nsym))) * 0.7).astype(np.complex64)
