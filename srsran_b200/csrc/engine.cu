@@ -2621,6 +2621,9 @@ int srslte_b200_set_tb_hints(srslte_b200_ctx_t* ctx, const float* hints, uint32_
   if (!ctx || (!hints && nof_tb))
     return SRSLTE_B200_ERROR_INVALID_INPUTS;
   ctx->e->tb_hints.assign(hints, hints + nof_tb);
+  for (float& h : ctx->e->tb_hints)
+    if (!(h == h))
+      h = 0.f; // (a NaN would not order: the planner sorts by these)
   return 0;
 }
 uint32_t srslte_b200_last_replayed(srslte_b200_ctx_t* ctx) { return ctx ? ctx->e->last_redo : 0; }
